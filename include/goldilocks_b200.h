@@ -1,0 +1,203 @@
+/*
+ * goldilocks_b200.h -- C ABI of the B200-native batched Ed448-Goldilocks engine.
+ *
+ * This is the drop-in boundary.  It has two halves:
+ *
+ *  1. LEGACY single-element entry points with exactly the names, argument order, struct sizes
+ *     and return conventions of libgoldilocks' own public headers
+ *     (reference: src/public_include/goldilocks/{common,point_448,ed448}.h).  Each one runs a
+ *     batch of one on the GPU; there is no CPU fallback.
+ *
+ *  2. `*_batch` entry points: the same operation over n independent elements.  Every
+ *     per-element argument of the legacy call becomes a packed array (element i at
+ *     base + i*sizeof(element)), `n` is appended, fallible operations gain a per-element
+ *     `goldilocks_error_t status[n]`, and variable-length messages are passed as one arena plus
+ *     `msg_off[n+1]` byte offsets.  All pointers are HOST pointers unless the function name ends
+ *     in `_dev`.  A batch call returns GOLDILOCKS_SUCCESS when the device executed the batch and
+ *     GOLDILOCKS_FAILURE on a CUDA error (see goldilocks_b200_last_error()).
+ *
+ * Types below are layout-compatible with the reference's x86_64 ABI (GOLDILOCKS_WORD_BITS 64):
+ *   gf_448_s       64 bytes, 8 x u64 limbs radix 2^56, aligned(32)   (reference f_field.h:23-27)
+ *   point_s        256 bytes = x,y,z,t                                (reference point_448.h:66-70)
+ *   scalar_s       56 bytes, 7 x u64, value < q                       (reference point_448.h:82-86)
+ * Field limbs are only defined mod p: the library accepts any limb values below 2^60 and always
+ * emits canonical limbs (< 2^56, value < p).
+ *
+ * The header is self-contained C99/C++ and pulls in no CUDA or torch types.
+ */
+#ifndef GOLDILOCKS_B200_H
+#define GOLDILOCKS_B200_H 1
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOLDILOCKS_B200_API __attribute__((visibility("default")))
+
+/* ---- scalar types and sizes (reference common.h:51-85, point_448.h:23-63, ed448.h:24-52) ---- */
+typedef uint64_t goldilocks_word_t;
+typedef uint64_t goldilocks_bool_t;           /* all-ones = true, 0 = false */
+typedef enum { GOLDILOCKS_SUCCESS = -1, GOLDILOCKS_FAILURE = 0 } goldilocks_error_t;
+
+#define GOLDILOCKS_448_SCALAR_LIMBS 7
+#define GOLDILOCKS_448_SCALAR_BITS 446
+#define GOLDILOCKS_448_SER_BYTES 56
+#define GOLDILOCKS_448_HASH_BYTES 56
+#define GOLDILOCKS_448_SCALAR_BYTES 56
+#define GOLDILOCKS_X448_PUBLIC_BYTES 56
+#define GOLDILOCKS_X448_PRIVATE_BYTES 56
+#define GOLDILOCKS_EDDSA_448_PUBLIC_BYTES 57
+#define GOLDILOCKS_EDDSA_448_PRIVATE_BYTES 57
+#define GOLDILOCKS_EDDSA_448_SIGNATURE_BYTES 114
+
+typedef struct gf_448_s { goldilocks_word_t limb[8]; } __attribute__((aligned(32))) gf_448_s;
+typedef struct goldilocks_448_point_s { gf_448_s x, y, z, t; } goldilocks_448_point_s, goldilocks_448_point_p[1];
+typedef struct goldilocks_448_scalar_s { goldilocks_word_t limb[GOLDILOCKS_448_SCALAR_LIMBS]; } goldilocks_448_scalar_s, goldilocks_448_scalar_p[1];
+/* Opaque fixed-base table handle.  Only goldilocks_448_precomputed_base is accepted (the comb
+ * table lives in device memory; reference goldilocks.c:59-64). */
+typedef struct goldilocks_448_precomputed_s goldilocks_448_precomputed_s;
+
+GOLDILOCKS_B200_API extern const goldilocks_448_precomputed_s *goldilocks_448_precomputed_base;
+GOLDILOCKS_B200_API extern const goldilocks_448_point_p goldilocks_448_point_base;       /* reference point_448.h:283 */
+GOLDILOCKS_B200_API extern const goldilocks_448_point_p goldilocks_448_point_identity;   /* reference goldilocks.c:83 */
+GOLDILOCKS_B200_API extern const goldilocks_448_scalar_p goldilocks_448_scalar_one, goldilocks_448_scalar_zero;
+GOLDILOCKS_B200_API extern const uint8_t goldilocks_x448_base_point[GOLDILOCKS_X448_PUBLIC_BYTES]; /* goldilocks.c:39 */
+
+/* ======================================================================================
+ * 1. Legacy single-element entry points (batch of one on the GPU)
+ * ====================================================================================== */
+/* reference point_448.h:303-334 / goldilocks.c:178-258 */
+GOLDILOCKS_B200_API void goldilocks_448_point_add(goldilocks_448_point_p sum, const goldilocks_448_point_p a, const goldilocks_448_point_p b);
+GOLDILOCKS_B200_API void goldilocks_448_point_sub(goldilocks_448_point_p diff, const goldilocks_448_point_p a, const goldilocks_448_point_p b);
+GOLDILOCKS_B200_API void goldilocks_448_point_double(goldilocks_448_point_p two_a, const goldilocks_448_point_p a);
+GOLDILOCKS_B200_API void goldilocks_448_point_negate(goldilocks_448_point_p nega, const goldilocks_448_point_p a);
+/* reference point_448.h:241-264 / goldilocks.c:136-176 */
+GOLDILOCKS_B200_API void goldilocks_448_point_encode(uint8_t ser[56], const goldilocks_448_point_p pt);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_decode(goldilocks_448_point_p pt, const uint8_t ser[56], goldilocks_bool_t allow_identity);
+/* reference point_448.h:270-281,555-563 / goldilocks.c:644-673 */
+GOLDILOCKS_B200_API goldilocks_bool_t goldilocks_448_point_eq(const goldilocks_448_point_p a, const goldilocks_448_point_p b);
+GOLDILOCKS_B200_API goldilocks_bool_t goldilocks_448_point_valid(const goldilocks_448_point_p a);
+/* reference point_448.h:355-359 / goldilocks.c:405-465 (constant time) */
+GOLDILOCKS_B200_API void goldilocks_448_point_scalarmul(goldilocks_448_point_p scaled, const goldilocks_448_point_p base, const goldilocks_448_scalar_p scalar);
+/* reference point_448.h:477-481 / goldilocks.c:830-877 (constant time fixed-base comb) */
+GOLDILOCKS_B200_API void goldilocks_448_precomputed_scalarmul(goldilocks_448_point_p scaled, const goldilocks_448_precomputed_s *base, const goldilocks_448_scalar_p scalar);
+/* reference point_448.h:494-500 / goldilocks.c:467-541 (constant time) */
+GOLDILOCKS_B200_API void goldilocks_448_point_double_scalarmul(goldilocks_448_point_p combo, const goldilocks_448_point_p base1, const goldilocks_448_scalar_p scalar1, const goldilocks_448_point_p base2, const goldilocks_448_scalar_p scalar2);
+/* reference point_448.h:542-547 / goldilocks.c:1260-1330 (variable time, public inputs only) */
+GOLDILOCKS_B200_API void goldilocks_448_base_double_scalarmul_non_secret(goldilocks_448_point_p combo, const goldilocks_448_scalar_p scalar1, const goldilocks_448_point_p base2, const goldilocks_448_scalar_p scalar2);
+/* reference point_448.h:647-664 / elligator.c:32-94 */
+GOLDILOCKS_B200_API void goldilocks_448_point_from_hash_nonuniform(goldilocks_448_point_p pt, const uint8_t hashed_data[56]);
+GOLDILOCKS_B200_API void goldilocks_448_point_from_hash_uniform(goldilocks_448_point_p pt, const uint8_t hashed_data[112]);
+/* reference ed448.h:215-232 / goldilocks.c:905-1004 ; point_448.h:430-434 / goldilocks.c:1104-1115 */
+GOLDILOCKS_B200_API void goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa(uint8_t enc[57], const goldilocks_448_point_p p);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio(goldilocks_448_point_p p, const uint8_t enc[57]);
+GOLDILOCKS_B200_API void goldilocks_448_point_mul_by_ratio_and_encode_like_x448(uint8_t out[56], const goldilocks_448_point_p p);
+/* reference point_448.h:398-402,445-448 / goldilocks.c:1006-1076,1117-1141 */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448(uint8_t out[56], const uint8_t base[56], const uint8_t scalar[56]);
+GOLDILOCKS_B200_API void goldilocks_x448_derive_public_key(uint8_t out[56], const uint8_t scalar[56]);
+/* reference ed448.h:61-165 / eddsa.c:98-306 */
+GOLDILOCKS_B200_API void goldilocks_ed448_derive_secret_scalar(goldilocks_448_scalar_p secret, const uint8_t privkey[57]);
+GOLDILOCKS_B200_API void goldilocks_ed448_derive_public_key(uint8_t pubkey[57], const uint8_t privkey[57]);
+GOLDILOCKS_B200_API void goldilocks_ed448_sign(uint8_t signature[114], const uint8_t privkey[57], const uint8_t pubkey[57], const uint8_t *message, size_t message_len, uint8_t prehashed, const uint8_t *context, uint8_t context_len);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify(const uint8_t signature[114], const uint8_t pubkey[57], const uint8_t *message, size_t message_len, uint8_t prehashed, const uint8_t *context, uint8_t context_len);
+/* reference point_448.h:113-233 / scalar.c */
+GOLDILOCKS_B200_API void goldilocks_448_scalar_add(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b);
+GOLDILOCKS_B200_API void goldilocks_448_scalar_sub(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b);
+GOLDILOCKS_B200_API void goldilocks_448_scalar_mul(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b);
+GOLDILOCKS_B200_API void goldilocks_448_scalar_halve(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_decode(goldilocks_448_scalar_p out, const uint8_t ser[56]);
+GOLDILOCKS_B200_API void goldilocks_448_scalar_decode_long(goldilocks_448_scalar_p out, const uint8_t *ser, size_t ser_len);
+GOLDILOCKS_B200_API void goldilocks_448_scalar_encode(uint8_t ser[56], const goldilocks_448_scalar_p s);
+
+/* ======================================================================================
+ * 2. Batched entry points (host pointers; element i at base + i*sizeof(element))
+ * ====================================================================================== */
+/* Field level, canonical 56-byte little-endian elements (BASELINE config 1).  Replaces the
+ * reference's hidden gf_448_{mul,sqr,add,sub,isr} (f_field.h:66-84) composed with
+ * gf_deserialize/gf_serialize (f_generic.c:19-68): out = serialize(op(deserialize(a), deserialize(b))).
+ * Inputs >= p are taken mod p, like gf_deserialize's ignored-result callers. */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_gf_mul_batch(uint8_t *out, const uint8_t *a, const uint8_t *b, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_gf_sqr_batch(uint8_t *out, const uint8_t *a, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_gf_add_batch(uint8_t *out, const uint8_t *a, const uint8_t *b, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_gf_sub_batch(uint8_t *out, const uint8_t *a, const uint8_t *b, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_gf_mulw_batch(uint8_t *out, const uint8_t *a, uint32_t w, size_t n);
+/* out = x^((p-3)/4), status = SUCCESS iff out^2 * x == 1 (f_arithmetic.c:14-47) */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_gf_isr_batch(uint8_t *out, goldilocks_error_t *status, const uint8_t *x, size_t n);
+/* out = 1/x (0 for x = 0) (goldilocks.c:69-80) */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_gf_invert_batch(uint8_t *out, const uint8_t *x, size_t n);
+
+/* Group level */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_add_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *a, const goldilocks_448_point_s *b, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_sub_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *a, const goldilocks_448_point_s *b, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_double_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *a, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_negate_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *a, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_eq_batch(goldilocks_bool_t *out, const goldilocks_448_point_s *a, const goldilocks_448_point_s *b, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_valid_batch(goldilocks_bool_t *out, const goldilocks_448_point_s *a, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_encode_batch(uint8_t *ser /*n*56*/, const goldilocks_448_point_s *pts, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_decode_batch(goldilocks_448_point_s *pts, goldilocks_error_t *status, const uint8_t *ser /*n*56*/, goldilocks_bool_t allow_identity, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_from_hash_nonuniform_batch(goldilocks_448_point_s *pts, const uint8_t *hashed /*n*56*/, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_from_hash_uniform_batch(goldilocks_448_point_s *pts, const uint8_t *hashed /*n*112*/, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_scalarmul_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *base, const goldilocks_448_scalar_s *scalar, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_double_scalarmul_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *base1, const goldilocks_448_scalar_s *scalar1, const goldilocks_448_point_s *base2, const goldilocks_448_scalar_s *scalar2, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(goldilocks_448_point_s *out, const goldilocks_448_precomputed_s *base, const goldilocks_448_scalar_s *scalar, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_base_double_scalarmul_non_secret_batch(goldilocks_448_point_s *out, const goldilocks_448_scalar_s *scalar1, const goldilocks_448_point_s *base2, const goldilocks_448_scalar_s *scalar2, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uint8_t *enc /*n*57*/, const goldilocks_448_point_s *pts, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(goldilocks_448_point_s *pts, goldilocks_error_t *status, const uint8_t *enc /*n*57*/, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint8_t *out /*n*56*/, const goldilocks_448_point_s *pts, size_t n);
+
+/* Scalars mod q */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_add_batch(goldilocks_448_scalar_s *out, const goldilocks_448_scalar_s *a, const goldilocks_448_scalar_s *b, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_sub_batch(goldilocks_448_scalar_s *out, const goldilocks_448_scalar_s *a, const goldilocks_448_scalar_s *b, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_mul_batch(goldilocks_448_scalar_s *out, const goldilocks_448_scalar_s *a, const goldilocks_448_scalar_s *b, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_halve_batch(goldilocks_448_scalar_s *out, const goldilocks_448_scalar_s *a, size_t n);
+/* every element has the same serialized length ser_len (any length, reduced mod q; scalar.c:257-293) */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_decode_long_batch(goldilocks_448_scalar_s *out, const uint8_t *ser /*n*ser_len*/, size_t ser_len, size_t n);
+
+/* CFRG cryptosystems */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448_batch(uint8_t *out /*n*56*/, goldilocks_error_t *status, const uint8_t *base /*n*56*/, const uint8_t *scalar /*n*56*/, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448_derive_public_key_batch(uint8_t *out /*n*56*/, const uint8_t *scalar /*n*56*/, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_derive_public_key_batch(uint8_t *pubkey /*n*57*/, const uint8_t *privkey /*n*57*/, size_t n);
+/* message i = msg[msg_off[i] .. msg_off[i+1]); prehashed/context are shared by the whole batch,
+ * exactly the per-call arguments of the reference (eddsa.c:146-155,253-261). */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature /*n*114*/, const uint8_t *privkey /*n*57*/, const uint8_t *pubkey /*n*57*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature /*n*114*/, const uint8_t *pubkey /*n*57*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n);
+/* SHAKE256 one-shot over n inputs, each squeezed to outlen bytes (shake.c:177-190, SHAKE256 params 211-213) */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out /*n*outlen*/, size_t outlen, const uint8_t *in, const size_t *in_off /*n+1*/, size_t n);
+
+/* ======================================================================================
+ * 3. Device-resident variants of the headline paths: every pointer is a DEVICE pointer on the
+ *    current CUDA device, `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *    Calls are asynchronous on that stream; `scratch` must hold goldilocks_b200_*_scratch_bytes(n).
+ * ====================================================================================== */
+GOLDILOCKS_B200_API size_t goldilocks_b200_verify_scratch_bytes(size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off, uint8_t prehashed, const uint8_t *context /*device or NULL*/, uint8_t context_len, size_t n, void *scratch, void *stream);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch_dev(goldilocks_448_point_s *out, const goldilocks_448_scalar_s *scalar, size_t n, void *stream);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_gf_mul_batch_dev(uint8_t *out, const uint8_t *a, const uint8_t *b, size_t n, void *stream);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_add_batch_dev(goldilocks_448_point_s *out, const goldilocks_448_point_s *a, const goldilocks_448_point_s *b, size_t n, void *stream);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_double_batch_dev(goldilocks_448_point_s *out, const goldilocks_448_point_s *a, size_t n, void *stream);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_decode_batch_dev(goldilocks_448_point_s *pts, goldilocks_error_t *status, const uint8_t *ser, goldilocks_bool_t allow_identity, size_t n, void *stream);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_encode_batch_dev(uint8_t *ser, const goldilocks_448_point_s *pts, size_t n, void *stream);
+
+/* ======================================================================================
+ * 4. Library control / introspection
+ * ====================================================================================== */
+/* Initialise the library on the current CUDA device (builds the fixed-base tables on the device).
+ * Called lazily by every entry point; thread-safe.  Returns FAILURE when no usable GPU exists. */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_init(void);
+GOLDILOCKS_B200_API const char *goldilocks_b200_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+GOLDILOCKS_B200_API uint64_t goldilocks_b200_launch_count(void);
+/* Copies the device-built fixed-base comb table (80 niels x 3 gf, canonical radix-2^56 limbs =
+ * 15360 bytes, the layout of the reference's goldilocks_448_precomputed_base) to `out`. */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_export_comb_table(uint8_t out[15360]);
+/* Same for the 32-entry wNAF base table (reference goldilocks_448_precomputed_wnaf_as_fe, 6144 bytes). */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_export_wnaf_table(uint8_t out[6144]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOLDILOCKS_B200_H */

@@ -1,0 +1,259 @@
+"""ctypes binding of the batched C ABI declared in include/goldilocks_b200.h.
+
+`BatchLib(path)` binds any shared library that exports the `*_batch` entry points: the CUDA product
+library (libgoldilocks_b200.so), and -- in the tests only -- the reference build, the oracle and the
+host simulator, which export the same names.  All arrays are numpy uint8 with one element per row
+(field element/decaf point encoding: 56 bytes, point struct: 256, scalar struct: 56, EdDSA key: 57,
+signature: 114), exactly the packed host layout of the C ABI.
+"""
+import ctypes as C
+import numpy as np
+
+SUCCESS = -1
+FAILURE = 0
+
+_P = C.c_void_p
+_Z = C.c_size_t
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+def _u8(a, width=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if width is not None:
+        a = a.reshape(-1, width)
+    return a
+
+
+def pack_messages(msgs):
+    """list of bytes -> (arena uint8[total], offsets uint64[n+1])"""
+    off = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    if msgs:
+        off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+    arena = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if msgs and int(off[-1]) else np.zeros(1, np.uint8)
+    return arena, off
+
+
+class BatchLib:
+    def __init__(self, path):
+        self.path = str(path)
+        self.lib = C.CDLL(self.path, mode=C.RTLD_LOCAL)
+
+    def has(self, name):
+        return hasattr(self.lib, name)
+
+    def _call(self, name, *args):
+        fn = getattr(self.lib, name)
+        fn.restype = C.c_int32
+        conv = []
+        for a in args:
+            if isinstance(a, np.ndarray) or a is None:
+                conv.append(_ptr(a))
+            else:
+                conv.append(a)
+        r = fn(*conv)
+        if r != SUCCESS:
+            err = ""
+            if self.has("goldilocks_b200_last_error"):
+                f = self.lib.goldilocks_b200_last_error
+                f.restype = C.c_char_p
+                err = (f() or b"").decode()
+            raise RuntimeError("%s failed: %s" % (name, err))
+
+    # ---- field ----
+    def _gf2(self, name, a, b):
+        a, b = _u8(a, 56), _u8(b, 56)
+        out = np.empty_like(a)
+        self._call(name, out, a, b, _Z(len(a)))
+        return out
+
+    def gf_mul(self, a, b): return self._gf2("goldilocks_448_gf_mul_batch", a, b)
+    def gf_add(self, a, b): return self._gf2("goldilocks_448_gf_add_batch", a, b)
+    def gf_sub(self, a, b): return self._gf2("goldilocks_448_gf_sub_batch", a, b)
+
+    def gf_sqr(self, a):
+        a = _u8(a, 56); out = np.empty_like(a)
+        self._call("goldilocks_448_gf_sqr_batch", out, a, _Z(len(a)))
+        return out
+
+    def gf_mulw(self, a, w):
+        a = _u8(a, 56); out = np.empty_like(a)
+        self._call("goldilocks_448_gf_mulw_batch", out, a, C.c_uint32(w), _Z(len(a)))
+        return out
+
+    def gf_isr(self, a):
+        a = _u8(a, 56); out = np.empty_like(a); st = np.zeros(len(a), np.int32)
+        self._call("goldilocks_448_gf_isr_batch", out, st, a, _Z(len(a)))
+        return out, st
+
+    def gf_invert(self, a):
+        a = _u8(a, 56); out = np.empty_like(a)
+        self._call("goldilocks_448_gf_invert_batch", out, a, _Z(len(a)))
+        return out
+
+    # ---- group ----
+    def _pt2(self, name, a, b):
+        a, b = _u8(a, 256), _u8(b, 256); out = np.empty_like(a)
+        self._call(name, out, a, b, _Z(len(a)))
+        return out
+
+    def _pt1(self, name, a):
+        a = _u8(a, 256); out = np.empty_like(a)
+        self._call(name, out, a, _Z(len(a)))
+        return out
+
+    def point_add(self, a, b): return self._pt2("goldilocks_448_point_add_batch", a, b)
+    def point_sub(self, a, b): return self._pt2("goldilocks_448_point_sub_batch", a, b)
+    def point_double(self, a): return self._pt1("goldilocks_448_point_double_batch", a)
+    def point_negate(self, a): return self._pt1("goldilocks_448_point_negate_batch", a)
+
+    def point_eq(self, a, b):
+        a, b = _u8(a, 256), _u8(b, 256); out = np.zeros(len(a), np.uint64)
+        self._call("goldilocks_448_point_eq_batch", out, a, b, _Z(len(a)))
+        return out != 0
+
+    def point_valid(self, a):
+        a = _u8(a, 256); out = np.zeros(len(a), np.uint64)
+        self._call("goldilocks_448_point_valid_batch", out, a, _Z(len(a)))
+        return out != 0
+
+    def point_encode(self, a):
+        a = _u8(a, 256); out = np.empty((len(a), 56), np.uint8)
+        self._call("goldilocks_448_point_encode_batch", out, a, _Z(len(a)))
+        return out
+
+    def point_decode(self, ser, allow_identity=False):
+        ser = _u8(ser, 56); out = np.empty((len(ser), 256), np.uint8); st = np.zeros(len(ser), np.int32)
+        self._call("goldilocks_448_point_decode_batch", out, st, ser, C.c_uint64(0xFFFFFFFFFFFFFFFF if allow_identity else 0), _Z(len(ser)))
+        return out, st
+
+    def from_hash_nonuniform(self, h):
+        h = _u8(h, 56); out = np.empty((len(h), 256), np.uint8)
+        self._call("goldilocks_448_point_from_hash_nonuniform_batch", out, h, _Z(len(h)))
+        return out
+
+    def from_hash_uniform(self, h):
+        h = _u8(h, 112); out = np.empty((len(h), 256), np.uint8)
+        self._call("goldilocks_448_point_from_hash_uniform_batch", out, h, _Z(len(h)))
+        return out
+
+    def encode_like_eddsa(self, a):
+        a = _u8(a, 256); out = np.empty((len(a), 57), np.uint8)
+        self._call("goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch", out, a, _Z(len(a)))
+        return out
+
+    def decode_like_eddsa(self, enc):
+        enc = _u8(enc, 57); out = np.empty((len(enc), 256), np.uint8); st = np.zeros(len(enc), np.int32)
+        self._call("goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch", out, st, enc, _Z(len(enc)))
+        return out, st
+
+    def encode_like_x448(self, a):
+        a = _u8(a, 256); out = np.empty((len(a), 56), np.uint8)
+        self._call("goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch", out, a, _Z(len(a)))
+        return out
+
+    # ---- scalar multiplication ----
+    def precomputed_scalarmul(self, scalars):
+        s = _u8(scalars, 56); out = np.empty((len(s), 256), np.uint8)
+        base = None
+        if self.has("goldilocks_448_precomputed_base"):
+            base = C.c_void_p.in_dll(self.lib, "goldilocks_448_precomputed_base")
+        self._call("goldilocks_448_precomputed_scalarmul_batch", out, base, s, _Z(len(s)))
+        return out
+
+    def point_scalarmul(self, pts, scalars):
+        p, s = _u8(pts, 256), _u8(scalars, 56); out = np.empty_like(p)
+        self._call("goldilocks_448_point_scalarmul_batch", out, p, s, _Z(len(p)))
+        return out
+
+    def point_double_scalarmul(self, p1, s1, p2, s2):
+        p1, s1, p2, s2 = _u8(p1, 256), _u8(s1, 56), _u8(p2, 256), _u8(s2, 56); out = np.empty_like(p1)
+        self._call("goldilocks_448_point_double_scalarmul_batch", out, p1, s1, p2, s2, _Z(len(p1)))
+        return out
+
+    def base_double_scalarmul_non_secret(self, s1, p2, s2):
+        s1, p2, s2 = _u8(s1, 56), _u8(p2, 256), _u8(s2, 56); out = np.empty_like(p2)
+        self._call("goldilocks_448_base_double_scalarmul_non_secret_batch", out, s1, p2, s2, _Z(len(p2)))
+        return out
+
+    # ---- scalars ----
+    def _sc2(self, name, a, b):
+        a, b = _u8(a, 56), _u8(b, 56); out = np.empty_like(a)
+        self._call(name, out, a, b, _Z(len(a)))
+        return out
+
+    def scalar_add(self, a, b): return self._sc2("goldilocks_448_scalar_add_batch", a, b)
+    def scalar_sub(self, a, b): return self._sc2("goldilocks_448_scalar_sub_batch", a, b)
+    def scalar_mul(self, a, b): return self._sc2("goldilocks_448_scalar_mul_batch", a, b)
+
+    def scalar_halve(self, a):
+        a = _u8(a, 56); out = np.empty_like(a)
+        self._call("goldilocks_448_scalar_halve_batch", out, a, _Z(len(a)))
+        return out
+
+    def scalar_decode_long(self, ser, ser_len):
+        ser = _u8(ser, ser_len) if ser_len else np.zeros((len(ser), 0), np.uint8)
+        out = np.empty((len(ser), 56), np.uint8)
+        self._call("goldilocks_448_scalar_decode_long_batch", out, ser if ser_len else np.zeros(1, np.uint8), _Z(ser_len), _Z(len(ser)))
+        return out
+
+    # ---- CFRG ----
+    def x448(self, base, scalar):
+        base, scalar = _u8(base, 56), _u8(scalar, 56)
+        out = np.empty_like(base); st = np.zeros(len(base), np.int32)
+        self._call("goldilocks_x448_batch", out, st, base, scalar, _Z(len(base)))
+        return out, st
+
+    def x448_derive_public_key(self, scalar):
+        scalar = _u8(scalar, 56); out = np.empty_like(scalar)
+        self._call("goldilocks_x448_derive_public_key_batch", out, scalar, _Z(len(scalar)))
+        return out
+
+    def shake256(self, msgs, outlen):
+        arena, off = pack_messages(msgs)
+        out = np.empty((len(msgs), outlen), np.uint8)
+        self._call("goldilocks_shake256_hash_batch", out, _Z(outlen), arena, off, _Z(len(msgs)))
+        return out
+
+    def ed448_derive_public_key(self, sk):
+        sk = _u8(sk, 57); out = np.empty_like(sk)
+        self._call("goldilocks_ed448_derive_public_key_batch", out, sk, _Z(len(sk)))
+        return out
+
+    @staticmethod
+    def _ctx(context):
+        ctx = np.frombuffer(bytes(context), dtype=np.uint8).copy() if context else np.zeros(1, np.uint8)
+        return ctx, len(context) if context else 0
+
+    def ed448_sign(self, sk, pk, msgs, prehashed=False, context=b""):
+        sk, pk = _u8(sk, 57), _u8(pk, 57)
+        arena, off = pack_messages(msgs) if isinstance(msgs, list) else msgs
+        ctx, ctx_len = self._ctx(context)
+        sig = np.empty((len(sk), 114), np.uint8)
+        self._call("goldilocks_ed448_sign_batch", sig, sk, pk, arena, off, C.c_uint8(1 if prehashed else 0), ctx, C.c_uint8(ctx_len), _Z(len(sk)))
+        return sig
+
+    def ed448_verify(self, sig, pk, msgs, prehashed=False, context=b""):
+        sig, pk = _u8(sig, 114), _u8(pk, 57)
+        arena, off = pack_messages(msgs) if isinstance(msgs, list) else msgs
+        ctx, ctx_len = self._ctx(context)
+        st = np.zeros(len(sig), np.int32)
+        self._call("goldilocks_ed448_verify_batch", st, sig, pk, arena, off, C.c_uint8(1 if prehashed else 0), ctx, C.c_uint8(ctx_len), _Z(len(sig)))
+        return st
+
+    # ---- tables ----
+    def export_comb_table(self):
+        out = np.empty(15360, np.uint8)
+        name = "goldilocks_b200_export_comb_table" if self.has("goldilocks_b200_export_comb_table") else "refb_export_comb_table"
+        fn = getattr(self.lib, name); fn.restype = C.c_int32
+        fn(_ptr(out))
+        return out
+
+    def export_wnaf_table(self):
+        out = np.empty(6144, np.uint8)
+        name = "goldilocks_b200_export_wnaf_table" if self.has("goldilocks_b200_export_wnaf_table") else "refb_export_wnaf_table"
+        fn = getattr(self.lib, name); fn.restype = C.c_int32
+        fn(_ptr(out))
+        return out

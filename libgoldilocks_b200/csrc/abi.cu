@@ -1,0 +1,690 @@
+// abi.cu -- CUDA launch wrappers and the C ABI of include/goldilocks_b200.h.
+//
+// Host arrays -> device arena (one grow-only allocation per device) -> kernel sequence -> host.
+// Everything between the first and the last kernel of a call stays in HBM.  There is NO CPU
+// implementation behind these symbols: without a usable sm_100 GPU every call fails loudly.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/goldilocks_b200.h"
+#include "lanes.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Kernels: thin launch shapes around the lane functors of lanes.cuh
+// ------------------------------------------------------------------------------------------------
+#define BLOCK 128
+
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_lanes(F f, size_t n) {
+    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (i < n) f(i);
+}
+// Persistent grid-stride shape for functors that own a per-thread scratch slot in HBM.
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_lanes_slot(F f, size_t n) {
+    const size_t slot = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * BLOCK;
+    for (size_t i = slot; i < n; i += stride) f(i, slot);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-device context
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+struct Block { void *p; size_t cap; };
+struct Ctx {
+    std::mutex mu;
+    bool ready = false, failed = false;
+    int dev = -1, sms = 0;
+    cudaStream_t stream = nullptr;
+    fixed_tables *ft = nullptr;
+    std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
+    size_t used = 0;             // bytes used in the active block
+    void *slot_scratch = nullptr;
+    size_t slot_cap = 0;
+};
+constexpr int MAX_DEV = 64;
+Ctx g_ctx[MAX_DEV];
+
+bool fail(const char *what, cudaError_t e) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    fprintf(stderr, "[goldilocks_b200] %s\n", g_err.c_str());
+    return false;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(#x, e_); } while (0)
+
+template <class F>
+bool launch(Ctx &c, const F &f, size_t n, cudaStream_t s) {
+    if (n == 0) return true;
+    k_lanes<F><<<(unsigned)((n + BLOCK - 1) / BLOCK), BLOCK, 0, s>>>(f, n);
+    g_launches++;
+    CU(cudaGetLastError());
+    return true;
+}
+// grid = SMs x resident blocks of this kernel, so every thread owns exactly one scratch slot
+template <class F>
+bool slot_grid(Ctx &c, int *grid) {
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lanes_slot<F>, BLOCK, 0));
+    if (occ < 1) occ = 1;
+    *grid = c.sms * occ;
+    return true;
+}
+template <class F>
+bool launch_slot(Ctx &c, const F &f, size_t n, int grid, cudaStream_t s) {
+    if (n == 0) return true;
+    size_t need_blocks = (n + BLOCK - 1) / BLOCK;
+    if ((size_t)grid > need_blocks) grid = (int)need_blocks;
+    k_lanes_slot<F><<<grid, BLOCK, 0, s>>>(f, n);
+    g_launches++;
+    CU(cudaGetLastError());
+    return true;
+}
+
+bool ctx_init(Ctx &c, int dev) {
+    if (c.ready) return true;
+    if (c.failed) { g_err = "device initialisation failed earlier"; return false; }
+    c.failed = true;
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, dev));
+    if (p.major < 10) {
+        g_err = "goldilocks_b200 needs an sm_100-class GPU (found sm_" + std::to_string(p.major) + std::to_string(p.minor) + ")";
+        fprintf(stderr, "[goldilocks_b200] %s\n", g_err.c_str());
+        return false;
+    }
+    c.dev = dev;
+    c.sms = p.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c.ft, sizeof(fixed_tables)));
+    LaneBuildTables f = {c.ft};
+    if (!launch(c, f, COMB_N + 2, c.stream)) return false;
+    CU(cudaStreamSynchronize(c.stream));
+    c.failed = false;
+    c.ready = true;
+    return true;
+}
+
+// One API call: locks the device context, carves device buffers from the arena, copies, launches.
+struct Call {
+    Ctx *c = nullptr;
+    std::unique_lock<std::mutex> lk;
+    bool ok = false;
+    Call() {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) { fail("cudaGetDevice (is there a GPU?)", e); return; }
+        if (dev >= MAX_DEV) { g_err = "device index too large"; return; }
+        c = &g_ctx[dev];
+        lk = std::unique_lock<std::mutex>(c->mu);
+        ok = ctx_init(*c, dev);
+        if (ok && !c->blocks.empty()) c->used = 0;
+    }
+    void *alloc(size_t bytes) {
+        if (!ok) return nullptr;
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes == 0) bytes = 256;
+        if (c->blocks.empty() || c->used + bytes > c->blocks.back().cap) {
+            size_t cap = c->blocks.empty() ? 0 : c->blocks.back().cap;
+            size_t want = bytes > 2 * cap ? bytes : 2 * cap;
+            if (want < (1u << 20)) want = 1u << 20;
+            void *p = nullptr;
+            cudaError_t e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) { ok = fail("cudaMalloc(arena)", e); return nullptr; }
+            c->blocks.push_back({p, want});
+            c->used = 0;
+        }
+        void *r = (char *)c->blocks.back().p + c->used;
+        c->used += bytes;
+        return r;
+    }
+    template <class T> T *in(const T *host, size_t count) {
+        T *d = (T *)alloc(count * sizeof(T));
+        if (!d || count == 0) return d;
+        cudaError_t e = cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { ok = fail("cudaMemcpyAsync(H2D)", e); return nullptr; }
+        return d;
+    }
+    template <class T> T *out(size_t count) { return (T *)alloc(count * sizeof(T)); }
+    template <class T> void fetch(T *host, const T *dev, size_t count) {
+        if (!ok || count == 0) return;
+        cudaError_t e = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) ok = fail("cudaMemcpyAsync(D2H)", e);
+    }
+    pniels *slots(size_t nthreads, size_t pniels_per_thread) {
+        if (!ok) return nullptr;
+        size_t bytes = nthreads * pniels_per_thread * sizeof(pniels);
+        if (bytes > c->slot_cap) {
+            if (c->slot_scratch) cudaFree(c->slot_scratch);
+            c->slot_scratch = nullptr; c->slot_cap = 0;
+            cudaError_t e = cudaMalloc(&c->slot_scratch, bytes);
+            if (e != cudaSuccess) { ok = fail("cudaMalloc(slot scratch)", e); return nullptr; }
+            c->slot_cap = bytes;
+        }
+        return (pniels *)c->slot_scratch;
+    }
+    template <class F> void run(const F &f, size_t n) { if (ok) ok = launch(*c, f, n, c->stream); }
+    template <class F> int grid_for() { int g = 1; if (ok) ok = slot_grid<F>(*c, &g); return g; }
+    template <class F> void run_slot(const F &f, size_t n, int grid) { if (ok) ok = launch_slot(*c, f, n, grid, c->stream); }
+    goldilocks_error_t finish() {
+        if (ok) {
+            cudaError_t e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) ok = fail("cudaStreamSynchronize", e);
+        }
+        if (c && lk.owns_lock() && c->blocks.size() > 1) { /* coalesce into one block for the next call */
+            size_t total = 0;
+            for (auto &b : c->blocks) { total += b.cap; cudaFree(b.p); }
+            c->blocks.clear();
+            void *p = nullptr;
+            if (cudaMalloc(&p, total) == cudaSuccess) c->blocks.push_back({p, total});
+            c->used = 0;
+        }
+        return ok ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+    }
+};
+
+typedef goldilocks_448_point_s hpt;
+typedef goldilocks_448_scalar_s hsc;
+inline const abi_pt *P(const hpt *p) { return (const abi_pt *)p; }
+inline abi_pt *P(hpt *p) { return (abi_pt *)p; }
+inline const abi_sc *S(const hsc *p) { return (const abi_sc *)p; }
+inline abi_sc *S(hsc *p) { return (abi_sc *)p; }
+static_assert(sizeof(hpt) == sizeof(abi_pt) && sizeof(hsc) == sizeof(abi_sc), "ABI layout");
+static_assert(sizeof(niels) == 192 && sizeof(pniels) == 256, "table layout");
+
+cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
+// Device-pointer entry points only need the tables; they never touch the arena or the lock while
+// kernels run (the caller owns the stream ordering).
+Ctx *dev_ctx() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEV) { g_err = "no CUDA device"; return nullptr; }
+    Ctx &c = g_ctx[dev];
+    std::lock_guard<std::mutex> g(c.mu);
+    return ctx_init(c, dev) ? &c : nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- data symbols ----------------------------------------------------------------------------------
+static const int precomputed_base_tag = 448;
+const goldilocks_448_precomputed_s *goldilocks_448_precomputed_base = (const goldilocks_448_precomputed_s *)&precomputed_base_tag;
+const goldilocks_448_point_p goldilocks_448_point_base = {{{GOLD_CONST_BASE_X56}, {GOLD_CONST_BASE_Y56}, {{1, 0, 0, 0, 0, 0, 0, 0}}, {GOLD_CONST_BASE_T56}}};
+const goldilocks_448_point_p goldilocks_448_point_identity = {{{{0}}, {{1}}, {{1}}, {{0}}}};
+const goldilocks_448_scalar_p goldilocks_448_scalar_one = {{{1}}}, goldilocks_448_scalar_zero = {{{0}}};
+const uint8_t goldilocks_x448_base_point[GOLDILOCKS_X448_PUBLIC_BYTES] = {5};
+
+// ---- control -------------------------------------------------------------------------------------------
+goldilocks_error_t goldilocks_b200_init(void) { Call k; return k.finish(); }
+const char *goldilocks_b200_last_error(void) { return g_err.c_str(); }
+uint64_t goldilocks_b200_launch_count(void) { return g_launches.load(); }
+
+goldilocks_error_t goldilocks_b200_export_comb_table(uint8_t out[15360]) {
+    Call k;
+    if (!k.ok) return k.finish();
+    std::vector<niels> h(COMB_ENTRIES);
+    k.fetch(h.data(), k.c->ft->comb, COMB_ENTRIES);
+    goldilocks_error_t r = k.finish();
+    if (r != GOLDILOCKS_SUCCESS) return r;
+    uint64_t *o = (uint64_t *)out;
+    for (int e = 0; e < COMB_ENTRIES; e++) {
+        const gf *g[3] = {&h[e].a, &h[e].b, &h[e].c};
+        for (int j = 0; j < 3; j++)
+            for (int l = 0; l < 8; l++) o[(e * 3 + j) * 8 + l] = (uint64_t)g[j]->v[2 * l] | ((uint64_t)g[j]->v[2 * l + 1] << 28);
+    }
+    return r;
+}
+goldilocks_error_t goldilocks_b200_export_wnaf_table(uint8_t out[6144]) {
+    Call k;
+    if (!k.ok) return k.finish();
+    std::vector<niels> h(WNAF_FIXED_ENTRIES);
+    k.fetch(h.data(), k.c->ft->wnaf, WNAF_FIXED_ENTRIES);
+    goldilocks_error_t r = k.finish();
+    if (r != GOLDILOCKS_SUCCESS) return r;
+    uint64_t *o = (uint64_t *)out;
+    for (int e = 0; e < WNAF_FIXED_ENTRIES; e++) {
+        const gf *g[3] = {&h[e].a, &h[e].b, &h[e].c};
+        for (int j = 0; j < 3; j++)
+            for (int l = 0; l < 8; l++) o[(e * 3 + j) * 8 + l] = (uint64_t)g[j]->v[2 * l] | ((uint64_t)g[j]->v[2 * l + 1] << 28);
+    }
+    return r;
+}
+
+// ---- field level ---------------------------------------------------------------------------------------
+#define GF_BINOP(NAME, OP)                                                                                   \
+    goldilocks_error_t NAME(uint8_t *out, const uint8_t *a, const uint8_t *b, size_t n) {                    \
+        Call k;                                                                                              \
+        LaneGf<OP> f = {k.out<uint8_t>(56 * n), nullptr, k.in(a, 56 * n), k.in(b, 56 * n), 0};               \
+        k.run(f, n);                                                                                         \
+        k.fetch(out, f.out, 56 * n);                                                                         \
+        return k.finish();                                                                                   \
+    }
+GF_BINOP(goldilocks_448_gf_mul_batch, GFOP_MUL)
+GF_BINOP(goldilocks_448_gf_add_batch, GFOP_ADD)
+GF_BINOP(goldilocks_448_gf_sub_batch, GFOP_SUB)
+goldilocks_error_t goldilocks_448_gf_sqr_batch(uint8_t *out, const uint8_t *a, size_t n) {
+    Call k;
+    LaneGf<GFOP_SQR> f = {k.out<uint8_t>(56 * n), nullptr, k.in(a, 56 * n), nullptr, 0};
+    k.run(f, n);
+    k.fetch(out, f.out, 56 * n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_gf_mulw_batch(uint8_t *out, const uint8_t *a, uint32_t w, size_t n) {
+    Call k;
+    if (w >= (1u << 28)) { g_err = "gf_mulw: w must be < 2^28"; return GOLDILOCKS_FAILURE; }
+    LaneGf<GFOP_MULW> f = {k.out<uint8_t>(56 * n), nullptr, k.in(a, 56 * n), nullptr, w};
+    k.run(f, n);
+    k.fetch(out, f.out, 56 * n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_gf_isr_batch(uint8_t *out, goldilocks_error_t *status, const uint8_t *x, size_t n) {
+    Call k;
+    LaneGf<GFOP_ISR> f = {k.out<uint8_t>(56 * n), k.out<int32_t>(n), k.in(x, 56 * n), nullptr, 0};
+    k.run(f, n);
+    k.fetch(out, f.out, 56 * n);
+    k.fetch((int32_t *)status, f.status, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_gf_invert_batch(uint8_t *out, const uint8_t *x, size_t n) {
+    Call k;
+    LaneGf<GFOP_INVERT> f = {k.out<uint8_t>(56 * n), nullptr, k.in(x, 56 * n), nullptr, 0};
+    k.run(f, n);
+    k.fetch(out, f.out, 56 * n);
+    return k.finish();
+}
+
+// ---- group level ---------------------------------------------------------------------------------------
+#define PT_BINOP(NAME, OP)                                                                                   \
+    goldilocks_error_t NAME(hpt *out, const hpt *a, const hpt *b, size_t n) {                                \
+        Call k;                                                                                              \
+        LanePt<OP> f = {k.out<abi_pt>(n), k.in(P(a), n), k.in(P(b), n)};                                     \
+        k.run(f, n);                                                                                         \
+        k.fetch(P(out), f.out, n);                                                                           \
+        return k.finish();                                                                                   \
+    }
+PT_BINOP(goldilocks_448_point_add_batch, PTOP_ADD)
+PT_BINOP(goldilocks_448_point_sub_batch, PTOP_SUB)
+#define PT_UNOP(NAME, OP)                                                                                    \
+    goldilocks_error_t NAME(hpt *out, const hpt *a, size_t n) {                                              \
+        Call k;                                                                                              \
+        LanePt<OP> f = {k.out<abi_pt>(n), k.in(P(a), n), nullptr};                                           \
+        k.run(f, n);                                                                                         \
+        k.fetch(P(out), f.out, n);                                                                           \
+        return k.finish();                                                                                   \
+    }
+PT_UNOP(goldilocks_448_point_double_batch, PTOP_DBL)
+PT_UNOP(goldilocks_448_point_negate_batch, PTOP_NEG)
+
+goldilocks_error_t goldilocks_448_point_eq_batch(goldilocks_bool_t *out, const hpt *a, const hpt *b, size_t n) {
+    Call k;
+    LanePtEq f = {k.out<uint64_t>(n), k.in(P(a), n), k.in(P(b), n)};
+    k.run(f, n);
+    k.fetch((uint64_t *)out, f.out, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_valid_batch(goldilocks_bool_t *out, const hpt *a, size_t n) {
+    Call k;
+    LanePtValid f = {k.out<uint64_t>(n), k.in(P(a), n)};
+    k.run(f, n);
+    k.fetch((uint64_t *)out, f.out, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_encode_batch(uint8_t *ser, const hpt *pts, size_t n) {
+    Call k;
+    LanePtEncode f = {k.out<uint8_t>(56 * n), k.in(P(pts), n)};
+    k.run(f, n);
+    k.fetch(ser, f.out, 56 * n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_decode_batch(hpt *pts, goldilocks_error_t *status, const uint8_t *ser, goldilocks_bool_t allow_identity, size_t n) {
+    Call k;
+    LanePtDecode f = {k.out<abi_pt>(n), k.out<int32_t>(n), k.in(ser, 56 * n), allow_identity ? 1u : 0u};
+    k.run(f, n);
+    k.fetch(P(pts), f.out, n);
+    k.fetch((int32_t *)status, f.status, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_from_hash_nonuniform_batch(hpt *pts, const uint8_t *hashed, size_t n) {
+    Call k;
+    LaneFromHash<false> f = {k.out<abi_pt>(n), k.in(hashed, 56 * n)};
+    k.run(f, n);
+    k.fetch(P(pts), f.out, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_from_hash_uniform_batch(hpt *pts, const uint8_t *hashed, size_t n) {
+    Call k;
+    LaneFromHash<true> f = {k.out<abi_pt>(n), k.in(hashed, 112 * n)};
+    k.run(f, n);
+    k.fetch(P(pts), f.out, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uint8_t *enc, const hpt *pts, size_t n) {
+    Call k;
+    LaneEncodeEddsa f = {k.out<uint8_t>(57 * n), k.in(P(pts), n)};
+    k.run(f, n);
+    k.fetch(enc, f.out, 57 * n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(hpt *pts, goldilocks_error_t *status, const uint8_t *enc, size_t n) {
+    Call k;
+    LaneDecodeEddsa f = {k.out<abi_pt>(n), k.out<int32_t>(n), k.in(enc, 57 * n)};
+    k.run(f, n);
+    k.fetch(P(pts), f.out, n);
+    k.fetch((int32_t *)status, f.status, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint8_t *out, const hpt *pts, size_t n) {
+    Call k;
+    LaneEncodeX448 f = {k.out<uint8_t>(56 * n), k.in(P(pts), n)};
+    k.run(f, n);
+    k.fetch(out, f.out, 56 * n);
+    return k.finish();
+}
+
+// ---- scalar multiplications ------------------------------------------------------------------------------
+goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(hpt *out, const goldilocks_448_precomputed_s *base, const hsc *scalar, size_t n) {
+    if (base != goldilocks_448_precomputed_base) { g_err = "only goldilocks_448_precomputed_base is supported"; return GOLDILOCKS_FAILURE; }
+    Call k;
+    LaneComb f = {k.out<abi_pt>(n), k.in(S(scalar), n), k.ok ? k.c->ft : nullptr};
+    k.run(f, n);
+    k.fetch(P(out), f.out, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_scalarmul_batch(hpt *out, const hpt *base, const hsc *scalar, size_t n) {
+    Call k;
+    int grid = k.grid_for<LaneScalarmul>();
+    LaneScalarmul f = {k.out<abi_pt>(n), k.in(P(base), n), k.in(S(scalar), n), k.slots((size_t)grid * BLOCK, WINDOW_NTABLE)};
+    k.run_slot(f, n, grid);
+    k.fetch(P(out), f.out, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_double_scalarmul_batch(hpt *out, const hpt *base1, const hsc *scalar1, const hpt *base2, const hsc *scalar2, size_t n) {
+    Call k;
+    int grid = k.grid_for<LaneDoubleScalarmul>();
+    LaneDoubleScalarmul f = {k.out<abi_pt>(n), k.in(P(base1), n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n),
+                             k.slots((size_t)grid * BLOCK, 2 * WINDOW_NTABLE)};
+    k.run_slot(f, n, grid);
+    k.fetch(P(out), f.out, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *out, const hsc *scalar1, const hpt *base2, const hsc *scalar2, size_t n) {
+    Call k;
+    int grid = k.grid_for<LaneBaseDoubleScalarmul>();
+    LaneBaseDoubleScalarmul f = {k.out<abi_pt>(n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n), k.ok ? k.c->ft : nullptr,
+                                 k.slots((size_t)grid * BLOCK, WINDOW_NTABLE)};
+    k.run_slot(f, n, grid);
+    k.fetch(P(out), f.out, n);
+    return k.finish();
+}
+
+// ---- scalars -----------------------------------------------------------------------------------------------
+#define SC_BINOP(NAME, OP)                                                                                   \
+    goldilocks_error_t NAME(hsc *out, const hsc *a, const hsc *b, size_t n) {                                \
+        Call k;                                                                                              \
+        LaneSc<OP> f = {k.out<abi_sc>(n), k.in(S(a), n), k.in(S(b), n)};                                     \
+        k.run(f, n);                                                                                         \
+        k.fetch(S(out), f.out, n);                                                                           \
+        return k.finish();                                                                                   \
+    }
+SC_BINOP(goldilocks_448_scalar_add_batch, SCOP_ADD)
+SC_BINOP(goldilocks_448_scalar_sub_batch, SCOP_SUB)
+SC_BINOP(goldilocks_448_scalar_mul_batch, SCOP_MUL)
+goldilocks_error_t goldilocks_448_scalar_halve_batch(hsc *out, const hsc *a, size_t n) {
+    Call k;
+    LaneSc<SCOP_HALVE> f = {k.out<abi_sc>(n), k.in(S(a), n), nullptr};
+    k.run(f, n);
+    k.fetch(S(out), f.out, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_scalar_decode_long_batch(hsc *out, const uint8_t *ser, size_t ser_len, size_t n) {
+    Call k;
+    LaneScDecodeLong f = {k.out<abi_sc>(n), k.in(ser, ser_len * n), ser_len};
+    k.run(f, n);
+    k.fetch(S(out), f.out, n);
+    return k.finish();
+}
+
+// ---- CFRG ----------------------------------------------------------------------------------------------------
+goldilocks_error_t goldilocks_x448_batch(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n) {
+    Call k;
+    LaneX448 f = {k.out<uint8_t>(56 * n), k.out<int32_t>(n), k.in(base, 56 * n), k.in(scalar, 56 * n)};
+    k.run(f, n);
+    k.fetch(out, f.out, 56 * n);
+    k.fetch((int32_t *)status, f.status, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_x448_derive_public_key_batch(uint8_t *out, const uint8_t *scalar, size_t n) {
+    Call k;
+    LaneX448DerivePk f = {k.out<uint8_t>(56 * n), k.in(scalar, 56 * n), k.ok ? k.c->ft : nullptr};
+    k.run(f, n);
+    k.fetch(out, f.out, 56 * n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out, size_t outlen, const uint8_t *in, const size_t *in_off, size_t n) {
+    Call k;
+    size_t total = n ? in_off[n] : 0;
+    LaneShake256 f = {k.out<uint8_t>(outlen * n), outlen, k.in(in, total), k.in(in_off, n + 1)};
+    k.run(f, n);
+    k.fetch(out, f.out, outlen * n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_ed448_derive_public_key_batch(uint8_t *pubkey, const uint8_t *privkey, size_t n) {
+    Call k;
+    LaneEdDerivePk f = {k.out<uint8_t>(57 * n), k.in(privkey, 57 * n), k.ok ? k.c->ft : nullptr};
+    k.run(f, n);
+    k.fetch(pubkey, f.pk, 57 * n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t *privkey, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
+                                               uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n) {
+    Call k;
+    size_t total = n ? msg_off[n] : 0;
+    const uint8_t *dmsg = k.in(msg, total);
+    const size_t *doff = k.in(msg_off, n + 1);
+    const uint8_t *dctx = k.in(context, context_len);
+    const uint8_t *dsk = k.in(privkey, 57 * n), *dpk = k.in(pubkey, 57 * n);
+    abi_sc *secret = k.out<abi_sc>(n), *nonce = k.out<abi_sc>(n), *nonce4 = k.out<abi_sc>(n);
+    uint8_t *dsig = k.out<uint8_t>(114 * n);
+    LaneEdSignNonce f1 = {secret, nonce, nonce4, dsk, dmsg, doff, prehashed, dctx, context_len};
+    k.run(f1, n);
+    LaneEdSignR f2 = {dsig, nonce4, k.ok ? k.c->ft : nullptr};
+    k.run(f2, n);
+    LaneEdSignFinish f3 = {dsig, secret, nonce, dpk, dmsg, doff, prehashed, dctx, context_len};
+    k.run(f3, n);
+    k.fetch(signature, dsig, 114 * n);
+    if (k.ok) { /* wipe secret scratch */
+        cudaMemsetAsync(secret, 0, sizeof(abi_sc) * n, k.c->stream);
+        cudaMemsetAsync(nonce, 0, sizeof(abi_sc) * n, k.c->stream);
+        cudaMemsetAsync(nonce4, 0, sizeof(abi_sc) * n, k.c->stream);
+    }
+    return k.finish();
+}
+
+size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    return al(2 * n * sizeof(abi_pt)) + al(2 * n * sizeof(int32_t)) + 2 * al(n * sizeof(abi_sc));
+}
+static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off, uint8_t prehashed,
+                       const uint8_t *ctx, uint8_t ctx_len, size_t n, void *scratch, pniels *slots, int grid, cudaStream_t s) {
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    char *p = (char *)scratch;
+    abi_pt *pts = (abi_pt *)p; p += al(2 * n * sizeof(abi_pt));
+    int32_t *ok = (int32_t *)p; p += al(2 * n * sizeof(int32_t));
+    abi_sc *chal = (abi_sc *)p; p += al(n * sizeof(abi_sc));
+    abi_sc *resp = (abi_sc *)p;
+    LaneEdVerifyDecode f1 = {pts, ok, sig, pk};
+    if (!launch(c, f1, 2 * n, s)) return false;
+    LaneEdVerifyScalars f2 = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len};
+    if (!launch(c, f2, n, s)) return false;
+    LaneEdVerifyFinish f3 = {status, pts, ok, chal, resp, c.ft, slots};
+    return launch_slot(c, f3, n, grid, s);
+}
+goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
+                                                 uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n) {
+    Call k;
+    size_t total = n ? msg_off[n] : 0;
+    const uint8_t *dmsg = k.in(msg, total);
+    const size_t *doff = k.in(msg_off, n + 1);
+    const uint8_t *dctx = k.in(context, context_len);
+    const uint8_t *dsig = k.in(signature, 114 * n), *dpk = k.in(pubkey, 57 * n);
+    int32_t *dst = k.out<int32_t>(n);
+    void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(n));
+    int grid = k.grid_for<LaneEdVerifyFinish>();
+    pniels *slots = k.slots((size_t)grid * BLOCK, WINDOW_NTABLE);
+    if (k.ok) k.ok = verify_dev(*k.c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, scratch, slots, grid, k.c->stream);
+    k.fetch((int32_t *)status, dst, n);
+    return k.finish();
+}
+
+// ---- device-resident variants -------------------------------------------------------------------------------
+goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
+                                                     uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, void *scratch, void *stream) {
+    Ctx *c = dev_ctx();
+    if (!c) return GOLDILOCKS_FAILURE;
+    std::lock_guard<std::mutex> g(c->mu); /* the per-thread table slots are shared per device */
+    int grid = 1;
+    if (!slot_grid<LaneEdVerifyFinish>(*c, &grid)) return GOLDILOCKS_FAILURE;
+    size_t bytes = (size_t)grid * BLOCK * WINDOW_NTABLE * sizeof(pniels);
+    if (bytes > c->slot_cap) {
+        if (c->slot_scratch) cudaFree(c->slot_scratch);
+        c->slot_scratch = nullptr; c->slot_cap = 0;
+        if (cudaMalloc(&c->slot_scratch, bytes) != cudaSuccess) { g_err = "cudaMalloc(slot scratch)"; return GOLDILOCKS_FAILURE; }
+        c->slot_cap = bytes;
+    }
+    return verify_dev(*c, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, scratch, (pniels *)c->slot_scratch, grid, as_stream(stream))
+               ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream) {
+    Ctx *c = dev_ctx();
+    if (!c) return GOLDILOCKS_FAILURE;
+    LaneX448 f = {out, (int32_t *)status, base, scalar};
+    return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch_dev(hpt *out, const hsc *scalar, size_t n, void *stream) {
+    Ctx *c = dev_ctx();
+    if (!c) return GOLDILOCKS_FAILURE;
+    LaneComb f = {P(out), S(scalar), c->ft};
+    return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_448_gf_mul_batch_dev(uint8_t *out, const uint8_t *a, const uint8_t *b, size_t n, void *stream) {
+    Ctx *c = dev_ctx();
+    if (!c) return GOLDILOCKS_FAILURE;
+    LaneGf<GFOP_MUL> f = {out, nullptr, a, b, 0};
+    return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_448_point_add_batch_dev(hpt *out, const hpt *a, const hpt *b, size_t n, void *stream) {
+    Ctx *c = dev_ctx();
+    if (!c) return GOLDILOCKS_FAILURE;
+    LanePt<PTOP_ADD> f = {P(out), P(a), P(b)};
+    return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_448_point_double_batch_dev(hpt *out, const hpt *a, size_t n, void *stream) {
+    Ctx *c = dev_ctx();
+    if (!c) return GOLDILOCKS_FAILURE;
+    LanePt<PTOP_DBL> f = {P(out), P(a), nullptr};
+    return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_448_point_decode_batch_dev(hpt *pts, goldilocks_error_t *status, const uint8_t *ser, goldilocks_bool_t allow_identity, size_t n, void *stream) {
+    Ctx *c = dev_ctx();
+    if (!c) return GOLDILOCKS_FAILURE;
+    LanePtDecode f = {P(pts), (int32_t *)status, ser, allow_identity ? 1u : 0u};
+    return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_448_point_encode_batch_dev(uint8_t *ser, const hpt *pts, size_t n, void *stream) {
+    Ctx *c = dev_ctx();
+    if (!c) return GOLDILOCKS_FAILURE;
+    LanePtEncode f = {ser, P(pts)};
+    return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+
+// ---- legacy single-element entry points: a batch of one on the GPU ------------------------------------------
+void goldilocks_448_point_add(goldilocks_448_point_p o, const goldilocks_448_point_p a, const goldilocks_448_point_p b) { goldilocks_448_point_add_batch(o, a, b, 1); }
+void goldilocks_448_point_sub(goldilocks_448_point_p o, const goldilocks_448_point_p a, const goldilocks_448_point_p b) { goldilocks_448_point_sub_batch(o, a, b, 1); }
+void goldilocks_448_point_double(goldilocks_448_point_p o, const goldilocks_448_point_p a) { goldilocks_448_point_double_batch(o, a, 1); }
+void goldilocks_448_point_negate(goldilocks_448_point_p o, const goldilocks_448_point_p a) { goldilocks_448_point_negate_batch(o, a, 1); }
+void goldilocks_448_point_encode(uint8_t ser[56], const goldilocks_448_point_p pt) { goldilocks_448_point_encode_batch(ser, pt, 1); }
+goldilocks_error_t goldilocks_448_point_decode(goldilocks_448_point_p pt, const uint8_t ser[56], goldilocks_bool_t allow_identity) {
+    goldilocks_error_t st = GOLDILOCKS_FAILURE;
+    if (goldilocks_448_point_decode_batch(pt, &st, ser, allow_identity, 1) != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
+    return st;
+}
+goldilocks_bool_t goldilocks_448_point_eq(const goldilocks_448_point_p a, const goldilocks_448_point_p b) {
+    goldilocks_bool_t r = 0;
+    goldilocks_448_point_eq_batch(&r, a, b, 1);
+    return r;
+}
+goldilocks_bool_t goldilocks_448_point_valid(const goldilocks_448_point_p a) {
+    goldilocks_bool_t r = 0;
+    goldilocks_448_point_valid_batch(&r, a, 1);
+    return r;
+}
+void goldilocks_448_point_scalarmul(goldilocks_448_point_p o, const goldilocks_448_point_p b, const goldilocks_448_scalar_p s) { goldilocks_448_point_scalarmul_batch(o, b, s, 1); }
+void goldilocks_448_precomputed_scalarmul(goldilocks_448_point_p o, const goldilocks_448_precomputed_s *b, const goldilocks_448_scalar_p s) { goldilocks_448_precomputed_scalarmul_batch(o, b, s, 1); }
+void goldilocks_448_point_double_scalarmul(goldilocks_448_point_p o, const goldilocks_448_point_p b1, const goldilocks_448_scalar_p s1, const goldilocks_448_point_p b2, const goldilocks_448_scalar_p s2) {
+    goldilocks_448_point_double_scalarmul_batch(o, b1, s1, b2, s2, 1);
+}
+void goldilocks_448_base_double_scalarmul_non_secret(goldilocks_448_point_p o, const goldilocks_448_scalar_p s1, const goldilocks_448_point_p b2, const goldilocks_448_scalar_p s2) {
+    goldilocks_448_base_double_scalarmul_non_secret_batch(o, s1, b2, s2, 1);
+}
+void goldilocks_448_point_from_hash_nonuniform(goldilocks_448_point_p pt, const uint8_t h[56]) { goldilocks_448_point_from_hash_nonuniform_batch(pt, h, 1); }
+void goldilocks_448_point_from_hash_uniform(goldilocks_448_point_p pt, const uint8_t h[112]) { goldilocks_448_point_from_hash_uniform_batch(pt, h, 1); }
+void goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa(uint8_t enc[57], const goldilocks_448_point_p p) { goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(enc, p, 1); }
+goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio(goldilocks_448_point_p p, const uint8_t enc[57]) {
+    goldilocks_error_t st = GOLDILOCKS_FAILURE;
+    if (goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(p, &st, enc, 1) != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
+    return st;
+}
+void goldilocks_448_point_mul_by_ratio_and_encode_like_x448(uint8_t out[56], const goldilocks_448_point_p p) { goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(out, p, 1); }
+goldilocks_error_t goldilocks_x448(uint8_t out[56], const uint8_t base[56], const uint8_t scalar[56]) {
+    goldilocks_error_t st = GOLDILOCKS_FAILURE;
+    if (goldilocks_x448_batch(out, &st, base, scalar, 1) != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
+    return st;
+}
+void goldilocks_x448_derive_public_key(uint8_t out[56], const uint8_t scalar[56]) { goldilocks_x448_derive_public_key_batch(out, scalar, 1); }
+void goldilocks_ed448_derive_secret_scalar(goldilocks_448_scalar_p secret, const uint8_t privkey[57]) {
+    Call k;
+    LaneEdSecretScalar f = {k.out<abi_sc>(1), k.in(privkey, 57)};
+    k.run(f, 1);
+    k.fetch(S(secret), f.out, 1);
+    k.finish();
+}
+void goldilocks_ed448_derive_public_key(uint8_t pubkey[57], const uint8_t privkey[57]) { goldilocks_ed448_derive_public_key_batch(pubkey, privkey, 1); }
+void goldilocks_ed448_sign(uint8_t signature[114], const uint8_t privkey[57], const uint8_t pubkey[57], const uint8_t *message, size_t message_len,
+                           uint8_t prehashed, const uint8_t *context, uint8_t context_len) {
+    const size_t off[2] = {0, message_len};
+    goldilocks_ed448_sign_batch(signature, privkey, pubkey, message, off, prehashed, context, context_len, 1);
+}
+goldilocks_error_t goldilocks_ed448_verify(const uint8_t signature[114], const uint8_t pubkey[57], const uint8_t *message, size_t message_len,
+                                           uint8_t prehashed, const uint8_t *context, uint8_t context_len) {
+    const size_t off[2] = {0, message_len};
+    goldilocks_error_t st = GOLDILOCKS_FAILURE;
+    if (goldilocks_ed448_verify_batch(&st, signature, pubkey, message, off, prehashed, context, context_len, 1) != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
+    return st;
+}
+void goldilocks_448_scalar_add(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { goldilocks_448_scalar_add_batch(o, a, b, 1); }
+void goldilocks_448_scalar_sub(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { goldilocks_448_scalar_sub_batch(o, a, b, 1); }
+void goldilocks_448_scalar_mul(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { goldilocks_448_scalar_mul_batch(o, a, b, 1); }
+void goldilocks_448_scalar_halve(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a) { goldilocks_448_scalar_halve_batch(o, a, 1); }
+void goldilocks_448_scalar_decode_long(goldilocks_448_scalar_p o, const uint8_t *ser, size_t ser_len) { goldilocks_448_scalar_decode_long_batch(o, ser, ser_len, 1); }
+goldilocks_error_t goldilocks_448_scalar_decode(goldilocks_448_scalar_p o, const uint8_t ser[56]) { /* scalar.c:234-249 */
+    /* success iff the 448-bit value is < q: compare on the host (56 bytes), reduce on the device */
+    static const uint8_t q_le[56] = {0xf3, 0x44, 0x58, 0xab, 0x92, 0xc2, 0x78, 0x23, 0x55, 0x8f, 0xc5, 0x8d, 0x72, 0xc2, 0x6c, 0x21, 0x90, 0x36, 0xd6, 0xae,
+                                     0x49, 0xdb, 0x4e, 0xc4, 0xe9, 0x23, 0xca, 0x7c, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff,
+                                     0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0x3f};
+    int lt = 0;
+    for (int i = 55; i >= 0; i--) { if (ser[i] != q_le[i]) { lt = ser[i] < q_le[i]; break; } }
+    goldilocks_448_scalar_decode_long_batch(o, ser, 56, 1);
+    return lt ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+void goldilocks_448_scalar_encode(uint8_t ser[56], const goldilocks_448_scalar_p s) { memcpy(ser, s->limb, 56); }
+
+}  // extern "C"

@@ -1,0 +1,403 @@
+// algos.cuh -- per-lane scalar-multiplication algorithms and the CFRG glue built on point.cuh:
+//   x448 Montgomery ladder, fixed-base signed comb, constant-time signed-window scalarmul,
+//   warp-uniform double-scalar multiplication for verification, table construction, EdDSA pieces.
+//
+// "Constant time" here means per lane: no branch and no memory address depends on secret data;
+// table lookups on secret indices scan the whole row and select with masks (the semantics of the
+// reference's constant_time_lookup, src/include/constant_time.h:134-183).
+#pragma once
+#include "gf.cuh"
+#include "sc.cuh"
+#include "point.cuh"
+#include "keccak.cuh"
+
+#define COMB_N 5   /* reference goldilocks.c:25-27 */
+#define COMB_T 5
+#define COMB_S 18
+#define COMB_ENTRIES (COMB_N << (COMB_T - 1)) /* 80 niels */
+#define WNAF_FIXED_ENTRIES 32                 /* goldilocks.c:29: odd multiples 1B..63B */
+#define WINDOW_BITS 5                         /* goldilocks.c:28 */
+#define WINDOW_NTABLE 16
+
+// Device-resident fixed-base tables (built once per device by build_tables_lane()).
+struct fixed_tables {
+    niels comb[COMB_ENTRIES];        /* canonical affine niels, layout of goldilocks_448_precomputed_base */
+    niels wnaf[WNAF_FIXED_ENTRIES];  /* canonical affine niels, layout of goldilocks_448_precomputed_wnaf_as_fe */
+    pt base;                         /* decoded decaf base point */
+};
+
+// ---------------------------------------------------------------------------------------------
+// X448 (RFC 7748) -- reference goldilocks.c:1006-1076.  5M + 4S + 1w per bit, constant time.
+// scalar/base are the 56-byte strings as 14 little-endian words.  Returns the nonzero mask
+// (the reference returns FAILURE iff the shared secret is zero) and always writes `out`.
+// ---------------------------------------------------------------------------------------------
+GD gmask_t x448_ladder(uint32_t out[14], const uint32_t base[14], const uint32_t scalar[14]) {
+    gf x1, x2, z2, x3, z3, t1, t2;
+    (void)gf_from_words(x1, base); /* u >= p is accepted mod p, like the reference's ignored result */
+    gf_set_ui(x2, 1);
+    gf_set_zero(z2);
+    gf_copy(x3, x1);
+    gf_set_ui(z3, 1);
+    gmask_t swap = 0;
+#pragma unroll 1
+    for (int w = 13; w >= 0; w--) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < 14; i++) word |= (i == w) ? scalar[i] : 0u;
+        if (w == 0) word &= ~3u;            /* clear the cofactor bits (low 2 bits of byte 0) */
+        if (w == 13) word |= 0x80000000u;   /* force bit 447 */
+#pragma unroll 1
+        for (int b = 31; b >= 0; b--) {
+            gmask_t k_t = (gmask_t)(-(int32_t)((word >> b) & 1u));
+            swap ^= k_t;
+            gf_cond_swap(x2, x3, swap);
+            gf_cond_swap(z2, z3, swap);
+            swap = k_t;
+            gf_add_nr(t1, x2, z2);   /* A  */
+            gf_sub(t2, x2, z2);      /* B  */
+            gf_sub(z2, x3, z3);      /* D  */
+            gf_mul(x2, t1, z2);      /* DA */
+            gf_add_nr(z2, z3, x3);   /* C  */
+            gf_mul(x3, t2, z2);      /* CB */
+            gf_sub(z3, x2, x3);
+            gf_sqr(z2, z3);
+            gf_mul(z3, x1, z2);      /* x1 (DA-CB)^2 */
+            gf_add_nr(z2, x2, x3);
+            gf_sqr(x3, z2);          /* (DA+CB)^2 */
+            gf_sqr(z2, t1);          /* AA */
+            gf_sqr(t1, t2);          /* BB */
+            gf_mul(x2, z2, t1);
+            gf_sub(t2, z2, t1);      /* E  */
+            gf_mulw(t1, t2, (uint32_t)(-GOLD_EDWARDS_D)); /* a24 * E */
+            gf_add_nr(t1, t1, z2);
+            gf_mul(z2, t2, t1);
+        }
+    }
+    gf_cond_swap(x2, x3, swap);
+    gf_cond_swap(z2, z3, swap);
+    gf_invert(z2, z2);
+    gf_mul(x1, x2, z2);
+    gf_to_words(out, x1);
+    return ~gf_is_zero(x1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Constant-time lookup: scan all `n` niels of a row, keep the one whose index matches.
+// ---------------------------------------------------------------------------------------------
+GD void niels_lookup_ct(niels &out, const niels *row, int n, uint32_t idx) {
+    gf_set_zero(out.a); gf_set_zero(out.b); gf_set_zero(out.c);
+#pragma unroll 1
+    for (int e = 0; e < n; e++) {
+        const gmask_t m = (gmask_t)(((uint64_t)((uint32_t)e ^ idx) - 1) >> 32); /* all-ones iff e == idx */
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            out.a.v[i] |= row[e].a.v[i] & m;
+            out.b.v[i] |= row[e].b.v[i] & m;
+            out.c.v[i] |= row[e].c.v[i] & m;
+        }
+    }
+}
+GD void pniels_lookup_ct(pniels &out, const pniels *row, int n, uint32_t idx) {
+    gf_set_zero(out.n.a); gf_set_zero(out.n.b); gf_set_zero(out.n.c); gf_set_zero(out.z);
+#pragma unroll 1
+    for (int e = 0; e < n; e++) {
+        const gmask_t m = (gmask_t)(((uint64_t)((uint32_t)e ^ idx) - 1) >> 32);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            out.n.a.v[i] |= row[e].n.a.v[i] & m;
+            out.n.b.v[i] |= row[e].n.b.v[i] & m;
+            out.n.c.v[i] |= row[e].n.c.v[i] & m;
+            out.z.v[i] |= row[e].z.v[i] & m;
+        }
+    }
+}
+
+// scalar1x = (scalar + adjustment) / 2 mod q  (goldilocks.c:420-421, 842-843)
+GD void sc_recode_signed(sc &out, const sc &scalar) {
+    sc adj, t;
+    sc_set_adj(adj);
+    sc_add(t, scalar, adj);
+    sc_halve(out, t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-base signed comb, constant time -- reference goldilocks.c:830-877.
+// 18 rounds x 5 combs; 17 doublings + 90 mixed additions (T skipped before a doubling).
+// `table` may live in shared, constant or global memory; every lane reads every entry.
+// ---------------------------------------------------------------------------------------------
+GD void comb_scalarmul(pt &out, const niels *table, const sc &scalar) {
+    sc s1x;
+    sc_recode_signed(s1x, scalar);
+    niels ni;
+#pragma unroll 1
+    for (int i = COMB_S - 1; i >= 0; i--) {
+        if (i != COMB_S - 1) pt_double(out, out, false);
+#pragma unroll 1
+        for (int j = 0; j < COMB_N; j++) {
+            uint32_t tab = 0;
+#pragma unroll
+            for (int k = 0; k < COMB_T; k++) {
+                const int bit = i + COMB_S * (k + j * COMB_T);
+                if (bit < GOLDILOCKS_SCALAR_BITS_) tab |= sc_bit(s1x, bit) << k;
+            }
+            const gmask_t invert = (gmask_t)((int32_t)(tab >> (COMB_T - 1)) - 1);
+            tab ^= invert;
+            tab &= (1u << (COMB_T - 1)) - 1;
+            niels_lookup_ct(ni, table + (j << (COMB_T - 1)), 1 << (COMB_T - 1), tab);
+            niels_cond_neg(ni, invert);
+            if (i != COMB_S - 1 || j != 0) pt_addsub_niels<false>(out, ni, j == COMB_N - 1 && i != 0);
+            else niels_to_pt(out, ni);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variable-base signed fixed-window table: odd multiples 1P,3P,...,(2n-1)P as pniels
+// (goldilocks.c:382-403 prepare_fixed_window).
+// ---------------------------------------------------------------------------------------------
+GD void prepare_fixed_window(pniels *multiples, const pt &b, int ntable) {
+    pt tmp;
+    pniels pn;
+    pt_double(tmp, b, false);
+    pt_to_pniels(pn, tmp);
+    pt_to_pniels(multiples[0], b);
+    pt_copy(tmp, b);
+#pragma unroll 1
+    for (int i = 1; i < ntable; i++) {
+        pt_addsub_pniels<false>(tmp, pn, false);
+        pt_to_pniels(multiples[i], tmp);
+    }
+}
+
+// 5-bit window starting at bit i of s (bits above 446+ are zero because s < q < 2^446)
+GD uint32_t sc_window5(const sc &s, int i) { return sc_bits(s, i, WINDOW_BITS); }
+
+// ---------------------------------------------------------------------------------------------
+// Variable-base scalar multiplication, constant time -- reference goldilocks.c:405-465.
+// `multiples` is this lane's scratch table of 16 pniels.
+// ---------------------------------------------------------------------------------------------
+GD void window_scalarmul(pt &a, const pt &b, const sc &scalar, pniels *multiples) {
+    sc s1x;
+    sc_recode_signed(s1x, scalar);
+    prepare_fixed_window(multiples, b, WINDOW_NTABLE);
+    pt tmp;
+    pniels pn;
+    bool first = true;
+#pragma unroll 1
+    for (int i = GOLDILOCKS_SCALAR_BITS_ - ((GOLDILOCKS_SCALAR_BITS_ - 1) % WINDOW_BITS) - 1; i >= 0; i -= WINDOW_BITS) {
+        uint32_t bits = sc_window5(s1x, i);
+        const gmask_t inv = (gmask_t)((int32_t)(bits >> (WINDOW_BITS - 1)) - 1);
+        bits ^= inv;
+        pniels_lookup_ct(pn, multiples, WINDOW_NTABLE, bits & (WINDOW_NTABLE - 1));
+        niels_cond_neg(pn.n, inv);
+        if (first) {
+            pniels_to_pt(tmp, pn);
+            first = false;
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < WINDOW_BITS - 1; j++) pt_double(tmp, tmp, true);
+            pt_double(tmp, tmp, false);
+            pt_addsub_pniels<false>(tmp, pn, i != 0);
+        }
+    }
+    pt_copy(a, tmp);
+}
+
+// a = scalarb*b + scalarc*c, constant time -- reference goldilocks.c:467-541.
+GD void window_double_scalarmul(pt &a, const pt &b, const sc &scalarb, const pt &c, const sc &scalarc,
+                                pniels *multiples1, pniels *multiples2) {
+    sc s1x, s2x;
+    sc_recode_signed(s1x, scalarb);
+    sc_recode_signed(s2x, scalarc);
+    prepare_fixed_window(multiples1, b, WINDOW_NTABLE);
+    prepare_fixed_window(multiples2, c, WINDOW_NTABLE);
+    pt tmp;
+    pniels pn;
+    bool first = true;
+#pragma unroll 1
+    for (int i = GOLDILOCKS_SCALAR_BITS_ - ((GOLDILOCKS_SCALAR_BITS_ - 1) % WINDOW_BITS) - 1; i >= 0; i -= WINDOW_BITS) {
+        uint32_t bits1 = sc_window5(s1x, i), bits2 = sc_window5(s2x, i);
+        const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WINDOW_BITS - 1)) - 1);
+        const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
+        bits1 ^= inv1;
+        bits2 ^= inv2;
+        pniels_lookup_ct(pn, multiples1, WINDOW_NTABLE, bits1 & (WINDOW_NTABLE - 1));
+        niels_cond_neg(pn.n, inv1);
+        if (first) {
+            pniels_to_pt(tmp, pn);
+            first = false;
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < WINDOW_BITS - 1; j++) pt_double(tmp, tmp, true);
+            pt_double(tmp, tmp, false);
+            pt_addsub_pniels<false>(tmp, pn, false);
+        }
+        pniels_lookup_ct(pn, multiples2, WINDOW_NTABLE, bits2 & (WINDOW_NTABLE - 1));
+        niels_cond_neg(pn.n, inv2);
+        pt_addsub_pniels<false>(tmp, pn, i != 0);
+    }
+    pt_copy(a, tmp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// combo = scalar1*B + scalar2*base2 for PUBLIC inputs (signature verification).
+//
+// The reference (goldilocks.c:1260-1330) walks two wNAF expansions, so the positions of its
+// additions depend on the scalars; executed per lane that diverges on almost every bit.  Only the
+// resulting group element is observable (the projective representative is not part of the
+// contract), so the GPU uses a warp-uniform schedule instead: both scalars are
+// recoded into 90 signed odd 5-bit digits (the same recoding as the constant-time paths) and every
+// lane does 5 doublings + one variable-base add (direct index into its own 16-pniels table) + one
+// fixed-base add (direct index into the first 16 entries of the shared wNAF table, which are
+// exactly 1B,3B,...,31B) per window.  Indices are public, so lookups are plain loads.
+// ---------------------------------------------------------------------------------------------
+GD void load_pniels(pniels &o, const pniels *src) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        o.n.a.v[i] = src->n.a.v[i]; o.n.b.v[i] = src->n.b.v[i];
+        o.n.c.v[i] = src->n.c.v[i]; o.z.v[i] = src->z.v[i];
+    }
+}
+GD void load_niels(niels &o, const niels *src) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) { o.a.v[i] = src->a.v[i]; o.b.v[i] = src->b.v[i]; o.c.v[i] = src->c.v[i]; }
+}
+GD void base_double_scalarmul_uniform(pt &combo, const sc &scalar1, const pt &base2, const sc &scalar2,
+                                      const niels *wnaf_base, pniels *multiples) {
+    sc s1x, s2x;
+    sc_recode_signed(s1x, scalar1);
+    sc_recode_signed(s2x, scalar2);
+    prepare_fixed_window(multiples, base2, WINDOW_NTABLE);
+    pt tmp;
+    pniels pn;
+    niels ni;
+    bool first = true;
+#pragma unroll 1
+    for (int i = GOLDILOCKS_SCALAR_BITS_ - ((GOLDILOCKS_SCALAR_BITS_ - 1) % WINDOW_BITS) - 1; i >= 0; i -= WINDOW_BITS) {
+        uint32_t bits1 = sc_window5(s1x, i), bits2 = sc_window5(s2x, i);
+        const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WINDOW_BITS - 1)) - 1);
+        const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
+        bits1 ^= inv1;
+        bits2 ^= inv2;
+        load_pniels(pn, multiples + (bits2 & (WINDOW_NTABLE - 1)));
+        niels_cond_neg(pn.n, inv2);
+        if (first) {
+            pniels_to_pt(tmp, pn);
+            first = false;
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < WINDOW_BITS - 1; j++) pt_double(tmp, tmp, true);
+            pt_double(tmp, tmp, false);
+            pt_addsub_pniels<false>(tmp, pn, false);
+        }
+        load_niels(ni, wnaf_base + (bits1 & (WINDOW_NTABLE - 1)));
+        niels_cond_neg(ni, inv1);
+        pt_addsub_niels<false>(tmp, ni, i != 0);
+    }
+    pt_copy(combo, tmp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table construction (runs once per device, a handful of lanes).
+// ---------------------------------------------------------------------------------------------
+// out[i] = 1/in[i] for i < n, one inversion (Montgomery's trick; reference goldilocks.c:703-726).
+GD void gf_batch_invert(gf *out, const gf *in, int n) {
+    gf acc, t;
+    gf_copy(acc, in[0]);
+    gf_copy(out[0], in[0]);
+    for (int i = 1; i < n; i++) { gf_mul(acc, acc, in[i]); gf_copy(out[i], acc); } /* out[i] = prod_{k<=i} in[k] */
+    gf_invert(acc, acc);
+    for (int i = n - 1; i > 0; i--) {
+        gf_mul(t, acc, out[i - 1]); /* 1/in[i] */
+        gf_mul(acc, acc, in[i]);
+        gf_copy(out[i], t);
+    }
+    gf_copy(out[0], acc);
+}
+// Normalise projective niels to canonical affine niels (goldilocks.c:728-755).
+GD void normalize_niels(niels *table, const gf *zs, gf *zis, int n) {
+    gf_batch_invert(zis, zs, n);
+    for (int i = 0; i < n; i++) {
+        gf_mul(table[i].a, table[i].a, zis[i]); gf_strong_reduce(table[i].a);
+        gf_mul(table[i].b, table[i].b, zis[i]); gf_strong_reduce(table[i].b);
+        gf_mul(table[i].c, table[i].c, zis[i]); gf_strong_reduce(table[i].c);
+    }
+}
+// One comb (16 entries) of the signed fixed-base comb table:
+//   entry[idx] = ( 2^(18*4) + sum_{k<4} (2*bit_k(idx) - 1) * 2^(18k) ) * 2^(90*comb) * B
+// Same table as the reference's precompute() (goldilocks.c:757-818), built comb-by-comb so the
+// five combs can be produced by five lanes in parallel.
+GD void build_comb(niels *out16, const pt &base, int comb) {
+    pt working, start, doubles[COMB_T - 1];
+    gf zs[16], zis[16];
+    pt_copy(working, base);
+    for (int k = 0; k < COMB_S * COMB_T * comb; k++) pt_double(working, working, false);
+    for (int j = 0; j < COMB_T; j++) {
+        if (j) pt_add(start, start, working);
+        else pt_copy(start, working);
+        if (j == COMB_T - 1) break;
+        pt_double(working, working, false);
+        pt_copy(doubles[j], working);          /* 2 * 2^(18 j) * (comb base) */
+        for (int k = 0; k < COMB_S - 1; k++) pt_double(working, working, false);
+    }
+    /* start = all teeth positive = entry 15; walk a Gray code flipping one tooth at a time */
+    for (int j = 0;; j++) {
+        const int gray = j ^ (j >> 1);
+        const int idx = 15 ^ gray;
+        pniels pn;
+        pt_to_pniels(pn, start);
+        gf_copy(out16[idx].a, pn.n.a); gf_copy(out16[idx].b, pn.n.b); gf_copy(out16[idx].c, pn.n.c);
+        gf_copy(zs[idx], pn.z);
+        if (j >= 15) break;
+        int delta = (j + 1) ^ ((j + 1) >> 1) ^ gray, k = 0;
+        while (delta > 1) { delta >>= 1; k++; }
+        if (gray & (1 << k)) pt_add(start, start, doubles[k]);
+        else pt_sub(start, start, doubles[k]);
+    }
+    normalize_niels(out16, zs, zis, 16);
+}
+// Odd multiples 1B,3B,...,63B as canonical affine niels (goldilocks.c:1204-1258).
+GD void build_wnaf_base(niels *out32, const pt &base) {
+    gf zs[WNAF_FIXED_ENTRIES], zis[WNAF_FIXED_ENTRIES];
+    pt tmp, twob;
+    pniels pn;
+    pt_double(twob, base, false);
+    pt_copy(tmp, base);
+    for (int i = 0; i < WNAF_FIXED_ENTRIES; i++) {
+        if (i) pt_add(tmp, tmp, twob);
+        pt_to_pniels(pn, tmp);
+        gf_copy(out32[i].a, pn.n.a); gf_copy(out32[i].b, pn.n.b); gf_copy(out32[i].c, pn.n.c);
+        gf_copy(zs[i], pn.z);
+    }
+    normalize_niels(out32, zs, zis, WNAF_FIXED_ENTRIES);
+}
+GD void build_tables_lane(fixed_tables *ft, int lane) {
+    const uint32_t bw[14] = GOLD_CONST_BASE_WORDS;
+    pt base;
+    (void)pt_decode(base, bw, 0);
+    if (lane < COMB_N) build_comb(ft->comb + 16 * lane, base, lane);
+    else if (lane == COMB_N) build_wnaf_base(ft->wnaf, base);
+    else if (lane == COMB_N + 1) pt_copy(ft->base, base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// EdDSA glue (reference src/eddsa.c)
+// ---------------------------------------------------------------------------------------------
+// clamp (eddsa.c:34-48) applied to the 57 hash bytes held as 15 words (byte 56 in word 14)
+GD void ed448_clamp_words(uint32_t w[15]) {
+    w[0] &= ~3u;
+    w[14] &= ~0xffu;          /* byte 56 = 0 */
+    w[13] |= 0x80000000u;     /* top bit of byte 55 */
+}
+// "SigEd448" || prehashed || ctx_len || ctx   (eddsa.c:51-74; dom byte = prehashed ? 1 : 0)
+template <typename CtxAt>
+GD void ed448_hash_init_with_dom(shake256_ctx &h, uint32_t prehashed, CtxAt ctx_at, uint32_t ctx_len) {
+    shake256_init(h);
+    const uint8_t dom[8] = {'S', 'i', 'g', 'E', 'd', '4', '4', '8'};
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) shake256_absorb_byte(h, dom[i]);
+    shake256_absorb_byte(h, prehashed ? 1 : 0);
+    shake256_absorb_byte(h, (uint8_t)ctx_len);
+#pragma unroll 1
+    for (uint32_t i = 0; i < ctx_len; i++) shake256_absorb_byte(h, ctx_at(i));
+}

@@ -1,0 +1,463 @@
+// lanes.cuh -- one functor per batched entry point: `operator()(i)` processes element i of the
+// packed host-layout arrays (include/goldilocks_b200.h).  The CUDA kernels in kernels.cu are thin
+// launch wrappers around these functors; the test-only host simulator runs the same functors in a
+// plain loop.  Nothing here allocates or synchronises.
+#pragma once
+#include <stddef.h>
+#include "algos.cuh"
+
+// ---- host-ABI layouts (reference x86_64 ABI: f_field.h:23-27, point_448.h:66-86) -------------
+struct abi_gf { uint64_t limb[8]; };
+struct abi_pt { abi_gf x, y, z, t; };
+struct abi_sc { uint64_t limb[7]; };
+
+// radix-2^56 limbs (any value < 2^60 per limb) -> TIGHT radix-2^28
+GD void gf_from_abi(gf &o, const abi_gf *a) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint64_t l = a->limb[k];
+        o.v[2 * k] = (uint32_t)l & GF_MASK;
+        o.v[2 * k + 1] = (uint32_t)(l >> 28);
+    }
+    gf_weak_reduce(o);
+}
+// canonical radix-2^56 limbs
+GD void gf_to_abi(abi_gf *o, const gf &a_in) {
+    gf a;
+    gf_copy(a, a_in);
+    gf_strong_reduce(a);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o->limb[k] = (uint64_t)a.v[2 * k] | ((uint64_t)a.v[2 * k + 1] << 28);
+}
+GD void pt_from_abi(pt &o, const abi_pt *a) { gf_from_abi(o.x, &a->x); gf_from_abi(o.y, &a->y); gf_from_abi(o.z, &a->z); gf_from_abi(o.t, &a->t); }
+GD void pt_to_abi(abi_pt *o, const pt &a) { gf_to_abi(&o->x, a.x); gf_to_abi(&o->y, a.y); gf_to_abi(&o->z, a.z); gf_to_abi(&o->t, a.t); }
+GD void sc_from_abi(sc &o, const abi_sc *a) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) { o.w[2 * k] = (uint32_t)a->limb[k]; o.w[2 * k + 1] = (uint32_t)(a->limb[k] >> 32); }
+}
+GD void sc_to_abi(abi_sc *o, const sc &a) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) o->limb[k] = (uint64_t)a.w[2 * k] | ((uint64_t)a.w[2 * k + 1] << 32);
+}
+// 56-byte records are 8-byte aligned in every batch array (element stride 56, 256-byte aligned base)
+GD void words_load56(uint32_t w[14], const uint8_t *p) {
+    const uint64_t *q = (const uint64_t *)p;
+#pragma unroll
+    for (int k = 0; k < 7; k++) { const uint64_t x = q[k]; w[2 * k] = (uint32_t)x; w[2 * k + 1] = (uint32_t)(x >> 32); }
+}
+GD void words_store56(uint8_t *p, const uint32_t w[14]) {
+    uint64_t *q = (uint64_t *)p;
+#pragma unroll
+    for (int k = 0; k < 7; k++) q[k] = (uint64_t)w[2 * k] | ((uint64_t)w[2 * k + 1] << 32);
+}
+// unaligned byte records (57-byte EdDSA strings)
+GD void words_load_bytes(uint32_t *w, int nwords, const uint8_t *p, int nbytes) {
+    for (int k = 0; k < nwords; k++) {
+        uint32_t x = 0;
+        for (int b = 0; b < 4; b++) { const int idx = 4 * k + b; if (idx < nbytes) x |= (uint32_t)p[idx] << (8 * b); }
+        w[k] = x;
+    }
+}
+GD void words_store_bytes(uint8_t *p, int nbytes, const uint32_t *w) {
+    for (int idx = 0; idx < nbytes; idx++) p[idx] = (uint8_t)(w[idx >> 2] >> (8 * (idx & 3)));
+}
+#define ST_OK(m) ((int32_t)(m)) /* mask -> goldilocks_error_t (-1 success / 0 failure) */
+
+// ---- field level (BASELINE config 1) --------------------------------------------------------
+enum { GFOP_MUL, GFOP_SQR, GFOP_ADD, GFOP_SUB, GFOP_MULW, GFOP_ISR, GFOP_INVERT };
+template <int OP>
+struct LaneGf {
+    uint8_t *out; int32_t *status; const uint8_t *a, *b; uint32_t w;
+    GDM void operator()(size_t i) const {
+        uint32_t wa[14], wb[14], wo[14];
+        gf x, y, z;
+        words_load56(wa, a + 56 * i);
+        (void)gf_from_words(x, wa);
+        if (OP == GFOP_MUL || OP == GFOP_ADD || OP == GFOP_SUB) { words_load56(wb, b + 56 * i); (void)gf_from_words(y, wb); }
+        if (OP == GFOP_MUL) gf_mul(z, x, y);
+        if (OP == GFOP_SQR) gf_sqr(z, x);
+        if (OP == GFOP_ADD) gf_add(z, x, y);
+        if (OP == GFOP_SUB) gf_sub(z, x, y);
+        if (OP == GFOP_MULW) gf_mulw(z, x, w);
+        if (OP == GFOP_ISR) status[i] = ST_OK(gf_isr(z, x));
+        if (OP == GFOP_INVERT) gf_invert(z, x);
+        gf_to_words(wo, z);
+        words_store56(out + 56 * i, wo);
+    }
+};
+
+// ---- group level -----------------------------------------------------------------------------
+enum { PTOP_ADD, PTOP_SUB, PTOP_DBL, PTOP_NEG };
+template <int OP>
+struct LanePt {
+    abi_pt *out; const abi_pt *a, *b;
+    GDM void operator()(size_t i) const {
+        pt p, q, r;
+        pt_from_abi(q, a + i);
+        if (OP == PTOP_ADD || OP == PTOP_SUB) pt_from_abi(r, b + i);
+        if (OP == PTOP_ADD) pt_add(p, q, r);
+        if (OP == PTOP_SUB) pt_sub(p, q, r);
+        if (OP == PTOP_DBL) pt_double(p, q, false);
+        if (OP == PTOP_NEG) pt_negate(p, q);
+        pt_to_abi(out + i, p);
+    }
+};
+struct LanePtEq {
+    uint64_t *out; const abi_pt *a, *b;
+    GDM void operator()(size_t i) const {
+        pt q, r;
+        pt_from_abi(q, a + i);
+        pt_from_abi(r, b + i);
+        out[i] = pt_eq(q, r) ? ~0ull : 0ull;
+    }
+};
+struct LanePtValid {
+    uint64_t *out; const abi_pt *a;
+    GDM void operator()(size_t i) const {
+        pt q;
+        pt_from_abi(q, a + i);
+        out[i] = pt_valid(q) ? ~0ull : 0ull;
+    }
+};
+struct LanePtEncode {
+    uint8_t *out; const abi_pt *a;
+    GDM void operator()(size_t i) const {
+        pt q; gf s; uint32_t w[14];
+        pt_from_abi(q, a + i);
+        pt_deisogenize(s, q);
+        gf_to_words(w, s);
+        words_store56(out + 56 * i, w);
+    }
+};
+struct LanePtDecode {
+    abi_pt *out; int32_t *status; const uint8_t *ser; uint32_t allow_identity;
+    GDM void operator()(size_t i) const {
+        pt p; uint32_t w[14];
+        words_load56(w, ser + 56 * i);
+        gmask_t ok = pt_decode(p, w, allow_identity ? ~0u : 0u);
+        pt_to_abi(out + i, p);
+        status[i] = ST_OK(ok);
+    }
+};
+template <bool UNIFORM>
+struct LaneFromHash {
+    abi_pt *out; const uint8_t *hashed;
+    GDM void operator()(size_t i) const {
+        pt p; uint32_t w[14];
+        words_load56(w, hashed + (UNIFORM ? 112 : 56) * i);
+        pt_from_hash_nonuniform(p, w);
+        if (UNIFORM) { /* elligator.c:86-94 */
+            pt p2;
+            words_load56(w, hashed + 112 * i + 56);
+            pt_from_hash_nonuniform(p2, w);
+            pt_add(p, p, p2);
+        }
+        pt_to_abi(out + i, p);
+    }
+};
+struct LaneEncodeEddsa {
+    uint8_t *out; const abi_pt *a;
+    GDM void operator()(size_t i) const {
+        pt q; uint32_t w[15], sign;
+        pt_from_abi(q, a + i);
+        pt_encode_like_eddsa(w, sign, q);
+        w[14] = sign << 7;
+        words_store_bytes(out + 57 * i, 57, w);
+    }
+};
+struct LaneDecodeEddsa {
+    abi_pt *out; int32_t *status; const uint8_t *enc;
+    GDM void operator()(size_t i) const {
+        pt p; uint32_t w[15];
+        words_load_bytes(w, 15, enc + 57 * i, 57);
+        gmask_t ok = pt_decode_like_eddsa(p, w, w[14] & 0xff);
+        pt_to_abi(out + i, p);
+        status[i] = ST_OK(ok);
+    }
+};
+struct LaneEncodeX448 {
+    uint8_t *out; const abi_pt *a;
+    GDM void operator()(size_t i) const {
+        pt q; uint32_t w[14];
+        pt_from_abi(q, a + i);
+        pt_encode_like_x448(w, q);
+        words_store56(out + 56 * i, w);
+    }
+};
+
+// ---- scalar multiplications ------------------------------------------------------------------
+struct LaneComb { /* goldilocks_448_precomputed_scalarmul */
+    abi_pt *out; const abi_sc *scalar; const fixed_tables *ft;
+    GDM void operator()(size_t i) const {
+        sc s; pt p;
+        sc_from_abi(s, scalar + i);
+        comb_scalarmul(p, ft->comb, s);
+        pt_to_abi(out + i, p);
+    }
+};
+struct LaneScalarmul { /* goldilocks_448_point_scalarmul; `slot` indexes per-thread scratch */
+    abi_pt *out; const abi_pt *base; const abi_sc *scalar; pniels *scratch;
+    GDM void operator()(size_t i, size_t slot) const {
+        sc s; pt p, b;
+        sc_from_abi(s, scalar + i);
+        pt_from_abi(b, base + i);
+        window_scalarmul(p, b, s, scratch + WINDOW_NTABLE * slot);
+        pt_to_abi(out + i, p);
+    }
+};
+struct LaneDoubleScalarmul { /* goldilocks_448_point_double_scalarmul */
+    abi_pt *out; const abi_pt *base1; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; pniels *scratch;
+    GDM void operator()(size_t i, size_t slot) const {
+        sc s1, s2; pt p, b1, b2;
+        sc_from_abi(s1, scalar1 + i); sc_from_abi(s2, scalar2 + i);
+        pt_from_abi(b1, base1 + i); pt_from_abi(b2, base2 + i);
+        window_double_scalarmul(p, b1, s1, b2, s2, scratch + 2 * WINDOW_NTABLE * slot, scratch + 2 * WINDOW_NTABLE * slot + WINDOW_NTABLE);
+        pt_to_abi(out + i, p);
+    }
+};
+struct LaneBaseDoubleScalarmul { /* goldilocks_448_base_double_scalarmul_non_secret */
+    abi_pt *out; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; const fixed_tables *ft; pniels *scratch;
+    GDM void operator()(size_t i, size_t slot) const {
+        sc s1, s2; pt p, b2;
+        sc_from_abi(s1, scalar1 + i); sc_from_abi(s2, scalar2 + i);
+        pt_from_abi(b2, base2 + i);
+        base_double_scalarmul_uniform(p, s1, b2, s2, ft->wnaf, scratch + WINDOW_NTABLE * slot);
+        pt_to_abi(out + i, p);
+    }
+};
+
+// ---- scalars mod q ---------------------------------------------------------------------------
+enum { SCOP_ADD, SCOP_SUB, SCOP_MUL, SCOP_HALVE };
+template <int OP>
+struct LaneSc {
+    abi_sc *out; const abi_sc *a, *b;
+    GDM void operator()(size_t i) const {
+        sc x, y, z;
+        sc_from_abi(x, a + i);
+        if (OP != SCOP_HALVE) sc_from_abi(y, b + i);
+        if (OP == SCOP_ADD) sc_add(z, x, y);
+        if (OP == SCOP_SUB) sc_sub(z, x, y);
+        if (OP == SCOP_MUL) sc_mul(z, x, y);
+        if (OP == SCOP_HALVE) sc_halve(z, x);
+        sc_to_abi(out + i, z);
+    }
+};
+struct ByteAtPtr { const uint8_t *p; GDM uint8_t operator()(int k) const { return p[k]; } };
+struct LaneScDecodeLong {
+    abi_sc *out; const uint8_t *ser; size_t len;
+    GDM void operator()(size_t i) const {
+        sc z;
+        ByteAtPtr at = {ser + len * i};
+        sc_decode_long(z, at, (int)len);
+        sc_to_abi(out + i, z);
+    }
+};
+
+// ---- X448 --------------------------------------------------------------------------------------
+struct LaneX448 {
+    uint8_t *out; int32_t *status; const uint8_t *base, *scalar;
+    GDM void operator()(size_t i) const {
+        uint32_t wb[14], ws[14], wo[14];
+        words_load56(wb, base + 56 * i);
+        words_load56(ws, scalar + 56 * i);
+        gmask_t nz = x448_ladder(wo, wb, ws);
+        words_store56(out + 56 * i, wo);
+        status[i] = ST_OK(nz);
+    }
+};
+struct ByteAtWords { const uint32_t *w; GDM uint8_t operator()(int k) const { return (uint8_t)(w[k >> 2] >> (8 * (k & 3))); } };
+struct LaneX448DerivePk { /* goldilocks.c:1117-1141 */
+    uint8_t *out; const uint8_t *scalar; const fixed_tables *ft;
+    GDM void operator()(size_t i) const {
+        uint32_t ws[14], wo[14];
+        words_load56(ws, scalar + 56 * i);
+        ws[0] &= ~3u;
+        ws[13] |= 0x80000000u; /* X_PRIVATE_BITS = 448: top byte keeps all its bits, bit 447 is set */
+        sc s, h; pt p;
+        ByteAtWords at = {ws};
+        sc_decode_long(s, at, 56);
+        sc_halve(h, s);        /* GOLDILOCKS_X448_ENCODE_RATIO = 2 */
+        comb_scalarmul(p, ft->comb, h);
+        pt_encode_like_x448(wo, p);
+        words_store56(out + 56 * i, wo);
+    }
+};
+
+// ---- SHAKE256 one-shot ---------------------------------------------------------------------------
+struct LaneShake256 {
+    uint8_t *out; size_t outlen; const uint8_t *in; const size_t *off;
+    GDM void operator()(size_t i) const {
+        shake256_ctx h;
+        shake256_init(h);
+        for (size_t k = off[i]; k < off[i + 1]; k++) shake256_absorb_byte(h, in[k]);
+        shake256_finish_absorb(h);
+        for (size_t k = 0; k < outlen; k++) out[outlen * i + k] = shake256_squeeze_byte(h);
+    }
+};
+
+// ---- EdDSA -----------------------------------------------------------------------------------------
+struct CtxAt { const uint8_t *p; GDM uint8_t operator()(uint32_t k) const { return p[k]; } };
+
+// secret scalar of a private key: SHAKE256(sk)[0..57) clamped, mod q  (eddsa.c:98-117)
+GD void ed448_secret_scalar(sc &secret, uint32_t seed_words[15], const uint8_t *sk, bool want_seed) {
+    shake256_ctx h;
+    shake256_init(h);
+    for (int k = 0; k < 57; k++) shake256_absorb_byte(h, sk[k]);
+    shake256_finish_absorb(h);
+    uint32_t w[15];
+    for (int k = 0; k < 15; k++) w[k] = 0;
+    for (int k = 0; k < 57; k++) w[k >> 2] |= (uint32_t)shake256_squeeze_byte(h) << (8 * (k & 3));
+    ed448_clamp_words(w);
+    ByteAtWords at = {w};
+    sc_decode_long(secret, at, 57);
+    if (want_seed) {
+        for (int k = 0; k < 15; k++) seed_words[k] = 0;
+        for (int k = 0; k < 57; k++) seed_words[k >> 2] |= (uint32_t)shake256_squeeze_byte(h) << (8 * (k & 3));
+    }
+}
+struct LaneEdDerivePk { /* eddsa.c:129-144 */
+    uint8_t *pk; const uint8_t *sk; const fixed_tables *ft;
+    GDM void operator()(size_t i) const {
+        sc s, h1, h2; pt p; uint32_t w[15], sign;
+        ed448_secret_scalar(s, w, sk + 57 * i, false);
+        sc_halve(h1, s);
+        sc_halve(h2, h1);      /* GOLDILOCKS_448_EDDSA_ENCODE_RATIO = 4 */
+        comb_scalarmul(p, ft->comb, h2);
+        pt_encode_like_eddsa(w, sign, p);
+        w[14] = sign << 7;
+        words_store_bytes(pk + 57 * i, 57, w);
+    }
+};
+struct LaneEdSecretScalar { /* goldilocks_ed448_derive_secret_scalar, eddsa.c:98-127 */
+    abi_sc *out; const uint8_t *sk;
+    GDM void operator()(size_t i) const {
+        sc s, h1, h2; uint32_t w[15];
+        ed448_secret_scalar(s, w, sk + 57 * i, false);
+        sc_halve(h1, s);
+        sc_halve(h2, h1);
+        sc_to_abi(out + i, h2);
+    }
+};
+// Signing is split in three launches so each keeps its own register budget:
+//   1) nonce: secret scalar, nonce scalar, nonce/4          (eddsa.c:161-199)
+//   2) R = encode(comb(nonce/4))                            (eddsa.c:201-205)
+//   3) S = challenge * secret + nonce ; sig = R || S || 0   (eddsa.c:207-229)
+struct LaneEdSignNonce {
+    abi_sc *secret, *nonce, *nonce4; const uint8_t *sk, *msg; const size_t *off; uint32_t prehashed; const uint8_t *ctx; uint32_t ctx_len;
+    GDM void operator()(size_t i) const {
+        sc s, n, h1, h2; uint32_t seed[15];
+        ed448_secret_scalar(s, seed, sk + 57 * i, true);
+        shake256_ctx h;
+        CtxAt cat = {ctx};
+        ed448_hash_init_with_dom(h, prehashed, cat, ctx_len);
+        for (int k = 0; k < 57; k++) shake256_absorb_byte(h, (uint8_t)(seed[k >> 2] >> (8 * (k & 3))));
+        for (size_t k = off[i]; k < off[i + 1]; k++) shake256_absorb_byte(h, msg[k]);
+        shake256_finish_absorb(h);
+        uint32_t w[29];
+        for (int k = 0; k < 29; k++) w[k] = 0;
+        for (int k = 0; k < 114; k++) w[k >> 2] |= (uint32_t)shake256_squeeze_byte(h) << (8 * (k & 3));
+        ByteAtWords at = {w};
+        sc_decode_long(n, at, 114);
+        sc_halve(h1, n);
+        sc_halve(h2, h1);
+        sc_to_abi(secret + i, s);
+        sc_to_abi(nonce + i, n);
+        sc_to_abi(nonce4 + i, h2);
+    }
+};
+struct LaneEdSignR {
+    uint8_t *sig; const abi_sc *nonce4; const fixed_tables *ft;
+    GDM void operator()(size_t i) const {
+        sc s; pt p; uint32_t w[15], sign;
+        sc_from_abi(s, nonce4 + i);
+        comb_scalarmul(p, ft->comb, s);
+        pt_encode_like_eddsa(w, sign, p);
+        w[14] = sign << 7;
+        words_store_bytes(sig + 114 * i, 57, w);
+    }
+};
+GD void ed448_challenge(sc &c, const uint8_t *r57, const uint8_t *pk57, const uint8_t *msg, size_t lo, size_t hi,
+                        uint32_t prehashed, const uint8_t *ctx, uint32_t ctx_len) {
+    shake256_ctx h;
+    CtxAt cat = {ctx};
+    ed448_hash_init_with_dom(h, prehashed, cat, ctx_len);
+    for (int k = 0; k < 57; k++) shake256_absorb_byte(h, r57[k]);
+    for (int k = 0; k < 57; k++) shake256_absorb_byte(h, pk57[k]);
+    for (size_t k = lo; k < hi; k++) shake256_absorb_byte(h, msg[k]);
+    shake256_finish_absorb(h);
+    uint32_t w[29];
+    for (int k = 0; k < 29; k++) w[k] = 0;
+    for (int k = 0; k < 114; k++) w[k >> 2] |= (uint32_t)shake256_squeeze_byte(h) << (8 * (k & 3));
+    ByteAtWords at = {w};
+    sc_decode_long(c, at, 114);
+}
+struct LaneEdSignFinish {
+    uint8_t *sig; const abi_sc *secret, *nonce; const uint8_t *pk, *msg; const size_t *off; uint32_t prehashed; const uint8_t *ctx; uint32_t ctx_len;
+    GDM void operator()(size_t i) const {
+        sc c, s, n, t, r;
+        ed448_challenge(c, sig + 114 * i, pk + 57 * i, msg, off[i], off[i + 1], prehashed, ctx, ctx_len);
+        sc_from_abi(s, secret + i);
+        sc_from_abi(n, nonce + i);
+        sc_mul(t, c, s);
+        sc_add(r, t, n);
+        uint32_t w[15];
+        for (int k = 0; k < 14; k++) w[k] = r.w[k];
+        w[14] = 0;
+        words_store_bytes(sig + 114 * i + 57, 57, w);
+    }
+};
+// Verification is three launches (eddsa.c:253-306):
+//   1) decode A and R (2n lanes, one isr each)            -> points + ok flags
+//   2) challenge = -SHAKE256(dom || R || A || M) mod q, response = S mod q
+//   3) combo = response*B + challenge*A ; accept iff combo == R (mod 2-torsion) and both decodes succeeded
+struct LaneEdVerifyDecode { /* lane 2i = public key i, lane 2i+1 = R of signature i */
+    abi_pt *pts; int32_t *ok; const uint8_t *sig, *pk;
+    GDM void operator()(size_t j) const {
+        const size_t i = j >> 1;
+        const uint8_t *enc = (j & 1) ? sig + 114 * i : pk + 57 * i;
+        pt p; uint32_t w[15];
+        words_load_bytes(w, 15, enc, 57);
+        gmask_t good = pt_decode_like_eddsa(p, w, w[14] & 0xff);
+        /* the third launch only needs TIGHT limbs back, so store weakly reduced (not canonical) limbs */
+        abi_pt *o = pts + j;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            o->x.limb[k] = (uint64_t)p.x.v[2 * k] + ((uint64_t)p.x.v[2 * k + 1] << 28);
+            o->y.limb[k] = (uint64_t)p.y.v[2 * k] + ((uint64_t)p.y.v[2 * k + 1] << 28);
+            o->z.limb[k] = (uint64_t)p.z.v[2 * k] + ((uint64_t)p.z.v[2 * k + 1] << 28);
+            o->t.limb[k] = (uint64_t)p.t.v[2 * k] + ((uint64_t)p.t.v[2 * k + 1] << 28);
+        }
+        ok[j] = ST_OK(good);
+    }
+};
+struct LaneEdVerifyScalars {
+    abi_sc *challenge, *response; const uint8_t *sig, *pk, *msg; const size_t *off; uint32_t prehashed; const uint8_t *ctx; uint32_t ctx_len;
+    GDM void operator()(size_t i) const {
+        sc c, nc, r;
+        ed448_challenge(c, sig + 114 * i, pk + 57 * i, msg, off[i], off[i + 1], prehashed, ctx, ctx_len);
+        sc_neg(nc, c);
+        ByteAtPtr at = {sig + 114 * i + 57};
+        sc_decode_long(r, at, 57);   /* reduces mod q, no range check (eddsa.c:287-291) */
+        /* GOLDILOCKS_448_EDDSA_DECODE_RATIO = 1: no doubling of the response */
+        sc_to_abi(challenge + i, nc);
+        sc_to_abi(response + i, r);
+    }
+};
+struct LaneEdVerifyFinish {
+    int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const fixed_tables *ft; pniels *scratch;
+    GDM void operator()(size_t i, size_t slot) const {
+        sc c, r; pt a, rp, combo;
+        sc_from_abi(c, challenge + i);
+        sc_from_abi(r, response + i);
+        pt_from_abi(a, pts + 2 * i);
+        base_double_scalarmul_uniform(combo, r, a, c, ft->wnaf, scratch + WINDOW_NTABLE * slot);
+        pt_from_abi(rp, pts + 2 * i + 1);
+        gmask_t good = pt_eq(combo, rp);
+        good &= (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1];
+        status[i] = ST_OK(good);
+    }
+};
+struct LaneBuildTables {
+    fixed_tables *ft;
+    GDM void operator()(size_t lane) const { build_tables_lane(ft, (int)lane); }
+};

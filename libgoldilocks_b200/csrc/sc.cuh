@@ -1,0 +1,192 @@
+// sc.cuh -- arithmetic mod the group order q (446 bits), one scalar per lane, 14 x 32-bit words.
+//
+// Replaces the reference's src/scalar.c (7 x 64-bit limbs, __uint128_t chains) with word-serial
+// Montgomery multiplication on 32-bit words: every step is one IMAD.WIDE.U32 whose 64-bit result
+// absorbs the running carry, so there are no carry flags.  All results are canonical (< q), which
+// is what makes them byte-identical to the reference's outputs.
+#pragma once
+#include "gf.cuh"
+#include "consts.cuh"
+
+#define SC_WORDS 14
+#define GOLDILOCKS_SCALAR_BITS_ 446 /* reference point_448.h:27 */
+struct sc { uint32_t w[SC_WORDS]; };
+
+// Constants are function-local constexpr tables: after inlining and unrolling every index is a
+// compile-time constant, so the words become immediates of the IMAD/IADD3 instructions.
+GD uint32_t sc_q(int i) { const uint32_t t[SC_WORDS] = GOLD_CONST_SC_Q; return t[i]; }
+GD uint32_t sc_r2(int i) { const uint32_t t[SC_WORDS] = GOLD_CONST_SC_R2; return t[i]; }
+GD uint32_t sc_adj(int i) { const uint32_t t[SC_WORDS] = GOLD_CONST_SC_ADJ; return t[i]; }
+
+GD void sc_set_zero(sc &a) {
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) a.w[i] = 0;
+}
+GD void sc_copy(sc &o, const sc &a) {
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) o.w[i] = a.w[i];
+}
+GD void sc_set_q(sc &o) {
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) o.w[i] = sc_q(i);
+}
+GD void sc_set_r2(sc &o) {
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) o.w[i] = sc_r2(i);
+}
+GD void sc_set_adj(sc &o) {
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) o.w[i] = sc_adj(i);
+}
+
+// out = {extra, accum} - sub, then + q if that went negative.  (reference scalar.c:27-53 sc_subx)
+GD void sc_subx(sc &out, const uint32_t accum[SC_WORDS], const uint32_t sub[SC_WORDS], uint32_t extra) {
+    int64_t chain = 0;
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) {
+        chain = chain + accum[i] - sub[i];
+        out.w[i] = (uint32_t)chain;
+        chain >>= 32;
+    }
+    uint32_t borrow = (uint32_t)chain + extra; /* 0 or 0xffffffff */
+    uint64_t c2 = 0;
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) {
+        c2 = c2 + out.w[i] + (sc_q(i) & borrow);
+        out.w[i] = (uint32_t)c2;
+        c2 >>= 32;
+    }
+}
+
+GD void sc_add(sc &out, const sc &a, const sc &b) { /* reference scalar.c:176-189 */
+    uint64_t chain = 0;
+    uint32_t t[SC_WORDS];
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) {
+        chain = chain + a.w[i] + b.w[i];
+        t[i] = (uint32_t)chain;
+        chain >>= 32;
+    }
+    sc q;
+    sc_set_q(q);
+    sc_subx(out, t, q.w, (uint32_t)chain);
+}
+GD void sc_sub(sc &out, const sc &a, const sc &b) { /* reference scalar.c:168-174 */
+    sc_subx(out, a.w, b.w, 0);
+}
+GD void sc_neg(sc &out, const sc &a) {
+    uint32_t z[SC_WORDS];
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) z[i] = 0;
+    sc_subx(out, z, a.w, 0);
+}
+
+// out = a * b / 2^448 mod q.  a < 2^448, b < 2^448 with a*b < q*2^448 (true whenever one side is
+// canonical).  (reference scalar.c:55-91 sc_montmul, word-serial CIOS)
+GD void sc_montmul(sc &out, const sc &a, const sc &b) {
+    uint32_t acc[SC_WORDS + 1];
+#pragma unroll
+    for (int i = 0; i <= SC_WORDS; i++) acc[i] = 0;
+    uint32_t hi_carry = 0;
+#pragma unroll 1
+    for (int i = 0; i < SC_WORDS; i++) {
+        uint32_t mand = a.w[i];
+        uint64_t chain = 0;
+#pragma unroll
+        for (int j = 0; j < SC_WORDS; j++) {
+            chain += (uint64_t)mand * b.w[j] + acc[j];
+            acc[j] = (uint32_t)chain;
+            chain >>= 32;
+        }
+        acc[SC_WORDS] = (uint32_t)chain;
+        mand = acc[0] * GOLD_SC_MONT32;
+        chain = 0;
+#pragma unroll
+        for (int j = 0; j < SC_WORDS; j++) {
+            chain += (uint64_t)mand * sc_q(j) + acc[j];
+            if (j) acc[j - 1] = (uint32_t)chain;
+            chain >>= 32;
+        }
+        chain += acc[SC_WORDS];
+        chain += hi_carry;
+        acc[SC_WORDS - 1] = (uint32_t)chain;
+        hi_carry = (uint32_t)(chain >> 32);
+    }
+    sc q;
+    sc_set_q(q);
+    sc_subx(out, acc, q.w, hi_carry);
+}
+GD void sc_mul(sc &out, const sc &a, const sc &b) { /* reference scalar.c:93-100 */
+    sc t, r2;
+    sc_set_r2(r2);
+    sc_montmul(t, a, b);
+    sc_montmul(out, t, r2);
+}
+GD void sc_reduce_short(sc &out, const sc &a) { /* "ham-handed reduce": a*1/R then *R^2/R (scalar.c:246) */
+    sc one, t, r2;
+    sc_set_zero(one);
+    one.w[0] = 1;
+    sc_set_r2(r2);
+    sc_montmul(t, a, one);
+    sc_montmul(out, t, r2);
+}
+
+GD void sc_halve(sc &out, const sc &a) { /* reference scalar.c:316-332 */
+    uint32_t mask = (uint32_t)(-(int32_t)(a.w[0] & 1));
+    uint64_t chain = 0;
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) {
+        chain = chain + a.w[i] + (sc_q(i) & mask);
+        out.w[i] = (uint32_t)chain;
+        chain >>= 32;
+    }
+#pragma unroll
+    for (int i = 0; i < SC_WORDS - 1; i++) out.w[i] = (out.w[i] >> 1) | (out.w[i + 1] << 31);
+    out.w[SC_WORDS - 1] = (out.w[SC_WORDS - 1] >> 1) | ((uint32_t)chain << 31);
+}
+
+// Little-endian bytes of any length -> canonical scalar (value mod q).  `get(k)` returns byte k.
+// (reference scalar.c:257-293 scalar_decode_long: Horner over 56-byte chunks from the top)
+template <typename ByteAt>
+GD void sc_decode_long(sc &out, ByteAt get, int len) {
+    if (len == 0) { sc_set_zero(out); return; }
+    int i = len - (len % 56);
+    if (i == len) i -= 56;
+    sc t1;
+    sc_set_zero(t1);
+    for (int k = 0; k < len - i; k++) t1.w[k >> 2] |= (uint32_t)get(i + k) << (8 * (k & 3));
+    if (len == 56) { sc_reduce_short(out, t1); return; }
+    if (i == 0) { /* fewer than 56 bytes: already < 2^440 < q */ sc_copy(out, t1); return; }
+#pragma unroll 1
+    while (i) {
+        i -= 56;
+        sc t2, t3, r2;
+        sc_set_r2(r2);
+        sc_montmul(t3, t1, r2); /* t1 * 2^448 mod q */
+        sc_set_zero(t2);
+        for (int k = 0; k < 56; k++) t2.w[k >> 2] |= (uint32_t)get(i + k) << (8 * (k & 3));
+        sc_reduce_short(t2, t2);
+        sc_add(t1, t3, t2);
+    }
+    sc_copy(out, t1);
+}
+
+// bit `pos` of the scalar (0 for pos >= 448)
+GD uint32_t sc_bit(const sc &a, int pos) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) r |= (i == (pos >> 5)) ? a.w[i] : 0u; /* no dynamic register indexing */
+    return (r >> (pos & 31)) & 1u;
+}
+// `nbits` (<= 8) bits starting at bit `pos`
+GD uint32_t sc_bits(const sc &a, int pos, int nbits) {
+    uint32_t lo = 0, hi = 0;
+    const int wi = pos >> 5;
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) {
+        lo |= (i == wi) ? a.w[i] : 0u;
+        hi |= (i == wi + 1) ? a.w[i] : 0u;
+    }
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (uint32_t)(x >> (pos & 31)) & ((1u << nbits) - 1u);
+}

@@ -1,0 +1,130 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY (never shipped, never loaded by the product).
+//
+// Compiles the device math headers of libgoldilocks_b200/csrc (gf/sc/point/algos/lanes .cuh are
+// __host__ __device__ clean) with the host compiler and runs the very same per-lane functors the
+// CUDA kernels run, in a plain loop.  This lets the CPU-only test tier (`-m "not gpu"`) check the
+// CUDA source's arithmetic, limb-bound discipline (-DGF_CHECK_BOUNDS aborts on any violation) and
+// host-layout I/O against the oracle and the golden vectors in a container without a GPU.
+// It exports the `*_batch` names of include/goldilocks_b200.h so the tests can drive it with the
+// same ctypes bindings as the real library.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../libgoldilocks_b200/csrc/lanes.cuh"
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+static int g_threads = 1;
+EXPORT void hostsim_set_threads(int t) { g_threads = t < 1 ? 1 : t; }
+
+template <class F>
+static void run(const F &f, size_t n) {
+    int nt = g_threads;
+    if ((size_t)nt > n) nt = n ? (int)n : 1;
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&f, n, nt, t]() { for (size_t i = n * t / nt; i < n * (t + 1) / nt; i++) f(i); });
+    for (auto &x : th) x.join();
+}
+template <class F>
+static void run_slot(const F &f, size_t n) { /* one scratch slot per worker thread */
+    int nt = g_threads;
+    if ((size_t)nt > n) nt = n ? (int)n : 1;
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) f(i, 0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&f, n, nt, t]() { for (size_t i = n * t / nt; i < n * (t + 1) / nt; i++) f(i, (size_t)t); });
+    for (auto &x : th) x.join();
+}
+
+static fixed_tables *tables() {
+    static fixed_tables *ft = nullptr;
+    if (!ft) {
+        ft = (fixed_tables *)aligned_alloc(64, sizeof(fixed_tables));
+        for (int lane = 0; lane < COMB_N + 2; lane++) build_tables_lane(ft, lane);
+    }
+    return ft;
+}
+static void export_niels(uint8_t *out, const niels *t, int n) {
+    uint64_t *o = (uint64_t *)out;
+    for (int e = 0; e < n; e++) {
+        const gf *g[3] = {&t[e].a, &t[e].b, &t[e].c};
+        for (int j = 0; j < 3; j++)
+            for (int l = 0; l < 8; l++) o[(e * 3 + j) * 8 + l] = (uint64_t)g[j]->v[2 * l] | ((uint64_t)g[j]->v[2 * l + 1] << 28);
+    }
+}
+EXPORT int32_t goldilocks_b200_export_comb_table(uint8_t *out) { export_niels(out, tables()->comb, COMB_ENTRIES); return -1; }
+EXPORT int32_t goldilocks_b200_export_wnaf_table(uint8_t *out) { export_niels(out, tables()->wnaf, WNAF_FIXED_ENTRIES); return -1; }
+EXPORT int32_t goldilocks_b200_init(void) { tables(); return -1; }
+
+typedef abi_pt hpt;
+typedef abi_sc hsc;
+static std::vector<pniels> g_slots;
+static pniels *slots(size_t per_thread) { g_slots.resize((size_t)g_threads * per_thread); return g_slots.data(); }
+
+#define GF2(NAME, OP) EXPORT int32_t NAME(uint8_t *o, const uint8_t *a, const uint8_t *b, size_t n) { LaneGf<OP> f = {o, nullptr, a, b, 0}; run(f, n); return -1; }
+GF2(goldilocks_448_gf_mul_batch, GFOP_MUL)
+GF2(goldilocks_448_gf_add_batch, GFOP_ADD)
+GF2(goldilocks_448_gf_sub_batch, GFOP_SUB)
+EXPORT int32_t goldilocks_448_gf_sqr_batch(uint8_t *o, const uint8_t *a, size_t n) { LaneGf<GFOP_SQR> f = {o, nullptr, a, nullptr, 0}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_gf_mulw_batch(uint8_t *o, const uint8_t *a, uint32_t w, size_t n) { LaneGf<GFOP_MULW> f = {o, nullptr, a, nullptr, w}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_gf_isr_batch(uint8_t *o, int32_t *st, const uint8_t *a, size_t n) { LaneGf<GFOP_ISR> f = {o, st, a, nullptr, 0}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_gf_invert_batch(uint8_t *o, const uint8_t *a, size_t n) { LaneGf<GFOP_INVERT> f = {o, nullptr, a, nullptr, 0}; run(f, n); return -1; }
+
+EXPORT int32_t goldilocks_448_point_add_batch(hpt *o, const hpt *a, const hpt *b, size_t n) { LanePt<PTOP_ADD> f = {o, a, b}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_sub_batch(hpt *o, const hpt *a, const hpt *b, size_t n) { LanePt<PTOP_SUB> f = {o, a, b}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_double_batch(hpt *o, const hpt *a, size_t n) { LanePt<PTOP_DBL> f = {o, a, nullptr}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_negate_batch(hpt *o, const hpt *a, size_t n) { LanePt<PTOP_NEG> f = {o, a, nullptr}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_eq_batch(uint64_t *o, const hpt *a, const hpt *b, size_t n) { LanePtEq f = {o, a, b}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_valid_batch(uint64_t *o, const hpt *a, size_t n) { LanePtValid f = {o, a}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_encode_batch(uint8_t *o, const hpt *a, size_t n) { LanePtEncode f = {o, a}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_decode_batch(hpt *o, int32_t *st, const uint8_t *ser, uint64_t allow_identity, size_t n) { LanePtDecode f = {o, st, ser, allow_identity ? 1u : 0u}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_from_hash_nonuniform_batch(hpt *o, const uint8_t *h, size_t n) { LaneFromHash<false> f = {o, h}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_from_hash_uniform_batch(hpt *o, const uint8_t *h, size_t n) { LaneFromHash<true> f = {o, h}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uint8_t *o, const hpt *a, size_t n) { LaneEncodeEddsa f = {o, a}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(hpt *o, int32_t *st, const uint8_t *enc, size_t n) { LaneDecodeEddsa f = {o, st, enc}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint8_t *o, const hpt *a, size_t n) { LaneEncodeX448 f = {o, a}; run(f, n); return -1; }
+
+EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(hpt *o, const void *, const hsc *s, size_t n) { LaneComb f = {o, s, tables()}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_scalarmul_batch(hpt *o, const hpt *b, const hsc *s, size_t n) { LaneScalarmul f = {o, b, s, slots(WINDOW_NTABLE)}; run_slot(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_double_scalarmul_batch(hpt *o, const hpt *b1, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { LaneDoubleScalarmul f = {o, b1, s1, b2, s2, slots(2 * WINDOW_NTABLE)}; run_slot(f, n); return -1; }
+EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *o, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { LaneBaseDoubleScalarmul f = {o, s1, b2, s2, tables(), slots(WINDOW_NTABLE)}; run_slot(f, n); return -1; }
+
+EXPORT int32_t goldilocks_448_scalar_add_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_ADD> f = {o, a, b}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_scalar_sub_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_SUB> f = {o, a, b}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_scalar_mul_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_MUL> f = {o, a, b}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_scalar_halve_batch(hsc *o, const hsc *a, size_t n) { LaneSc<SCOP_HALVE> f = {o, a, nullptr}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_scalar_decode_long_batch(hsc *o, const uint8_t *ser, size_t len, size_t n) { LaneScDecodeLong f = {o, ser, len}; run(f, n); return -1; }
+
+EXPORT int32_t goldilocks_x448_batch(uint8_t *o, int32_t *st, const uint8_t *base, const uint8_t *sc, size_t n) { LaneX448 f = {o, st, base, sc}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_x448_derive_public_key_batch(uint8_t *o, const uint8_t *sc, size_t n) { LaneX448DerivePk f = {o, sc, tables()}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_shake256_hash_batch(uint8_t *o, size_t outlen, const uint8_t *in, const size_t *off, size_t n) { LaneShake256 f = {o, outlen, in, off}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_ed448_derive_public_key_batch(uint8_t *pk, const uint8_t *sk, size_t n) { LaneEdDerivePk f = {pk, sk, tables()}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_ed448_sign_batch(uint8_t *sig, const uint8_t *sk, const uint8_t *pk, const uint8_t *msg, const size_t *off,
+                                           uint8_t prehashed, const uint8_t *ctx, uint8_t ctx_len, size_t n) {
+    std::vector<abi_sc> secret(n), nonce(n), nonce4(n);
+    LaneEdSignNonce f1 = {secret.data(), nonce.data(), nonce4.data(), sk, msg, off, prehashed, ctx, ctx_len};
+    run(f1, n);
+    LaneEdSignR f2 = {sig, nonce4.data(), tables()};
+    run(f2, n);
+    LaneEdSignFinish f3 = {sig, secret.data(), nonce.data(), pk, msg, off, prehashed, ctx, ctx_len};
+    run(f3, n);
+    return -1;
+}
+EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off,
+                                             uint8_t prehashed, const uint8_t *ctx, uint8_t ctx_len, size_t n) {
+    std::vector<abi_pt> pts(2 * n);
+    std::vector<int32_t> ok(2 * n);
+    std::vector<abi_sc> chal(n), resp(n);
+    LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk};
+    run(f1, 2 * n);
+    LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len};
+    run(f2, n);
+    LaneEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), tables(), slots(WINDOW_NTABLE)};
+    run_slot(f3, n);
+    return -1;
+}

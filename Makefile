@@ -1,0 +1,36 @@
+# Builds the product library (CUDA, sm_100a only) and the test-only artefacts.
+#   make lib       -> libgoldilocks_b200/libgoldilocks_b200.so   (the C ABI of include/goldilocks_b200.h)
+#   make hostsim   -> tests/hostsim/_hostsim.so                  (device math compiled for the host; tests only)
+#   make oracle    -> oracle/liboracle.so (+ oracle/_ref/*.so when /root/reference is present; tests/bench baseline only)
+NVCC      ?= nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden $(EXTRA_NVCCFLAGS)
+CSRC      := libgoldilocks_b200/csrc
+OBJDIR    := build/obj
+KERNELS   := $(wildcard $(CSRC)/k_*.cu)
+OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(KERNELS)) $(OBJDIR)/abi.o
+HDRS      := $(wildcard $(CSRC)/*.cuh) include/goldilocks_b200.h
+LIB       := libgoldilocks_b200/libgoldilocks_b200.so
+
+.PHONY: all lib hostsim oracle clean
+all: lib hostsim oracle
+lib: $(LIB)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c -o $@ $< 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(OBJS)
+
+hostsim: tests/hostsim/_hostsim.so
+tests/hostsim/_hostsim.so: tests/hostsim/hostsim.cpp $(HDRS)
+	$(CXX) -std=c++17 -O2 -fPIC -shared -DGF_CHECK_BOUNDS -o $@ $< -lpthread
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf build $(LIB) tests/hostsim/_hostsim.so
+	$(MAKE) -C oracle clean

@@ -1,0 +1,342 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json's metric on its own config: Ed448 verifies/s at batch 2^20 (config 4),
+with X448 ops/s (config 3) and fixed-base comb scalarmuls/s (config 2) at 2^20 riding along in `extra`.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm  (under torchrun for N > 1)
+  python bench.py --impl reference [...]                        the reference's CPU path on all host cores
+
+A step = one pass of the hot path (goldilocks_ed448_verify_batch) over one batch of 2^20 synthetic
+signatures per GPU (weak scaling: the batch shards into independent contiguous ranges, one per rank,
+no collective on the data path; torch.distributed is used only for the barrier and max-over-ranks time).
+
+`value`  : device-resident -- inputs already in HBM, CUDA events on the launching stream.
+`e2e`    : the same batch through the host-pointer C-ABI call with pinned host buffers; H2D + kernels +
+           D2H inside the timed region.
+`roofline`: the dominant kernel (LaneEdVerifyFinish = double scalar multiplication + point_eq), its
+           launches timed with CUDA events inside the timed region; algorithmic MAC32 per signature from
+           SURVEY.md 8(d); peak = measured IMAD.WIDE.U32 rate (profiles/r01_imad_peak.json).
+`cpu_baseline`: the unmodified reference (oracle/_ref, arch_x86_64) on all host cores over a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_PER_GPU = 1 << 20
+MSG_LEN = 32
+MAC32 = {"verify": 981120, "verify_finish": 800300, "x448": 870208, "comb": 142656}
+METRIC = "Ed448 verifies/s at batch 2^20 per GPU (X448 and comb ops/s in extra)"
+UNIT = "verifies/s"
+
+
+def imad_peak():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_imad_peak.json")) as f:
+            return float(json.load(f)["imad_wide_u32_gmac_s"]), "measured (tools/imad_peak.cu on this pool's B200)"
+    except Exception:
+        return 148 * 32 * 1.965, "nominal 148 SMs x 32 IMAD.WIDE/clk x 1.965 GHz"
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# workload (synthetic, seeded): 2^16 keys x 16 messages of 32 bytes, 1/8 corrupted
+# ------------------------------------------------------------------------------------------------
+def make_corpus(signer, n, label):
+    from util import stream_bytes
+    per = 16
+    nk = max(1, n // per)
+    sk = stream_bytes(label + "/sk", nk * 57).reshape(nk, 57)
+    pk = signer.ed448_derive_public_key(sk)
+    sk_all = np.repeat(sk, per, axis=0)[:n]
+    pk_all = np.repeat(pk, per, axis=0)[:n].copy()
+    arena = stream_bytes(label + "/msg", n * MSG_LEN)
+    off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
+    sig = signer.ed448_sign(sk_all, pk_all, (arena, off))
+    kinds = np.zeros(n, np.int32)
+    kinds[::8] = 1 + (np.arange((n + 7) // 8) % 4)
+    sel = stream_bytes(label + "/sel", n)
+    i = np.flatnonzero(kinds == 1); sig[i, sel[i] % 57] ^= 1
+    i = np.flatnonzero(kinds == 2); sig[i, 57 + sel[i] % 56] ^= 2
+    i = np.flatnonzero(kinds == 3); pk_all[i, sel[i] % 57] ^= 4
+    i = np.flatnonzero(kinds == 4); arena[i * MSG_LEN + sel[i] % MSG_LEN] ^= 8
+    expect = np.where(kinds == 0, -1, 0).astype(np.int32)
+    return sig, pk_all, arena, off, expect
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(n_sample, steps, warmup, corpus=None):
+    """The reference's own goldilocks_ed448_verify over `n_sample` signatures of the bench corpus, all host cores."""
+    import util
+    ref = util.ref_lib()
+    kind = "reference"
+    if ref is None:
+        ref, kind = util.oracle_lib(), "port"
+    cores = host_cores()
+    util.set_threads(ref, cores)
+    if corpus is None:
+        corpus = make_corpus(ref, n_sample, "bench/cpu")
+    sig, pk, arena, off, expect = corpus
+    sig, pk, arena, off, expect = sig[:n_sample], pk[:n_sample], arena[: n_sample * MSG_LEN], off[: n_sample + 1], expect[:n_sample]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        st = ref.ed448_verify(sig, pk, (arena, off))
+        dt = time.perf_counter() - t0
+        assert (st == expect).all(), "reference disagrees with the corpus' expected accept bits"
+        if it >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    return {"value": n_sample / t, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d signatures of the bench corpus (32-byte messages, 1/8 corrupted), %d timed passes, %s threads via pthreads" % (n_sample, len(times), cores),
+            "lib": os.path.basename(ref.path)}, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    n_sample = min(N_PER_GPU, 1024 * cores)
+    base, t = cpu_reference_rate(n_sample, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (448-bit integers)",
+            "data": "synthetic", "config": config_dict(args.gpus, n_sample),
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(gpus, n_per_step):
+    return {"workload": "BASELINE configs[3]: Ed448 batch verify (SHAKE256 + double scalarmul), 2^16 keys x 16 messages of 32 B, 1/8 corrupted",
+            "signatures_per_gpu_per_step": n_per_step, "parallelism": "independent shards x%d, no collective" % gpus,
+            "l2": "inputs+scratch per step (>700 MB) exceed the 126 MB L2; no flush needed"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import libgoldilocks_b200 as g
+    from libgoldilocks_b200.engine import DeviceEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    eng = DeviceEngine()
+    lib = eng.capi
+    n = args.n
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs (host, pinned) -----------------------------------------------------------------------
+    sig, pk, arena, off, expect = make_corpus(lib, n, "bench/rank%d" % rank)
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+
+    h_sig, h_pk, h_msg = pinned(sig.reshape(-1)), pinned(pk.reshape(-1)), pinned(arena)
+    h_off = pinned(off.view(np.int64))
+    h_st = torch.empty(n, dtype=torch.int32).pin_memory()
+    d_sig, d_pk, d_msg, d_off = (t.to(dev) for t in (h_sig, h_pk, h_msg, h_off))
+    d_st = torch.empty(n, dtype=torch.int32, device=dev)
+    d_scratch = torch.empty(eng.verify_scratch_bytes(n), dtype=torch.uint8, device=dev)
+
+    def step():
+        eng.ed448_verify(d_st, d_sig, d_pk, d_msg, d_off, d_scratch)
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    assert (d_st.cpu().numpy() == expect).all(), "device verify disagrees with the corpus' expected accept bits"
+
+    # ---- device-resident timed region -------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    l0 = eng.launch_count()
+    lib.lib.goldilocks_b200_profile(C.c_int(1))
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    barrier()
+    lib.lib.goldilocks_b200_profile(C.c_int(0))
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop()
+    t_step = max_over_ranks(e0.elapsed_time(e1) / 1e3 / K)
+    names = C.create_string_buffer(64 * 4096)
+    ms = (C.c_float * 4096)()
+    lib.lib.goldilocks_b200_profile_read.restype = C.c_size_t
+    cnt = lib.lib.goldilocks_b200_profile_read(names, ms, C.c_size_t(4096))
+    per_kernel = {}
+    for k in range(cnt):
+        nm = names.raw[64 * k:64 * k + 64].split(b"\0")[0].decode()
+        per_kernel.setdefault(nm, []).append(ms[k])
+    kavg = {k: float(np.mean(v)) for k, v in per_kernel.items()}
+    t_finish = kavg.get("LaneEdVerifyFinish", 0.0) / 1e3
+    peak, peak_how = imad_peak()
+    achieved = n * MAC32["verify_finish"] / t_finish / 1e9 if t_finish > 0 else 0.0
+    roofline = {"bound": "imad", "kernel": "k_lanes_slot<LaneEdVerifyFinish>", "achieved": achieved, "peak": peak, "unit": "GMAC32/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_how,
+                "algorithmic_mac32_per_signature": MAC32["verify_finish"], "kernel_ms": kavg,
+                "kernel_share_of_step": t_finish / (e0.elapsed_time(e1) / 1e3 / K) if t_finish > 0 else None,
+                "step_frac": n * MAC32["verify"] / t_step / 1e9 / peak,
+                "note": "integer-multiply-pipe roofline (north_star); HBM traffic is <0.1% of the HBM roof for this kernel"}
+
+    # ---- end to end through the host-pointer C ABI ---------------------------------------------------------
+    fn = lib.lib.goldilocks_ed448_verify_batch
+    fn.restype = C.c_int32
+    argv = [C.c_void_p(h_st.data_ptr()), C.c_void_p(h_sig.data_ptr()), C.c_void_p(h_pk.data_ptr()), C.c_void_p(h_msg.data_ptr()),
+            C.c_void_p(h_off.data_ptr()), C.c_uint8(0), None, C.c_uint8(0), C.c_size_t(n)]
+    for _ in range(max(1, W - 1)):
+        assert fn(*argv) == -1
+    assert (h_st.numpy() == expect).all()
+    ke = max(2, min(K, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        assert fn(*argv) == -1
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks((time.perf_counter() - t0) / ke)
+    barrier()
+    h2d = sig.nbytes + pk.nbytes + arena.nbytes + off.nbytes
+    e2e = {"value": world * n / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(4 * n), "ms_per_step": t_e2e * 1e3,
+           "api": "goldilocks_ed448_verify_batch (host pointers, pinned)"}
+
+    # ---- extra: X448 (config 3) and comb (config 2), device-resident, 2^20 each ------------------------------
+    extra = {}
+    if not args.no_extra:
+        from util import stream_bytes
+        u = torch.from_numpy(stream_bytes("bench/x448/u%d" % rank, n * 56)).to(dev)
+        kk = torch.from_numpy(stream_bytes("bench/x448/k%d" % rank, n * 56)).to(dev)
+        xo = torch.empty(n * 56, dtype=torch.uint8, device=dev)
+        xs = torch.empty(n, dtype=torch.int32, device=dev)
+        sc = torch.from_numpy(lib.scalar_decode_long(stream_bytes("bench/comb/s%d" % rank, n * 56).reshape(n, 56), 56).reshape(-1)).to(dev)
+        co = torch.empty(n * 256, dtype=torch.uint8, device=dev)
+        for name, fnc, mac in (("x448", lambda: eng.x448(xo, xs, u, kk), MAC32["x448"]), ("comb", lambda: eng.precomputed_scalarmul(co, sc), MAC32["comb"])):
+            for _ in range(2):
+                fnc()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kx = max(2, min(K, 3))
+            barrier()
+            a.record()
+            for _ in range(kx):
+                fnc()
+            b.record()
+            barrier()
+            t = max_over_ranks(a.elapsed_time(b) / 1e3 / kx)
+            extra[name] = {"value": world * n / t, "unit": "ops/s", "ms_per_step": t * 1e3, "batch_per_gpu": n,
+                           "imad_frac": n * mac / t / 1e9 / peak, "algorithmic_mac32_per_op": mac}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = host_cores()
+        n_cpu = min(n, 2048 * cores)
+        cpu, _ = cpu_reference_rate(n_cpu, 1, 0, corpus=(sig, pk, arena, off, expect))
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": world * n / t_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_step * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (448-bit integers)", "data": "synthetic",
+                "config": config_dict(world, n), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu, "extra": extra}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="signatures per GPU per step (default 2^20, the BASELINE size)")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -191,6 +191,12 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_init(void);
 GOLDILOCKS_B200_API const char *goldilocks_b200_last_error(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 GOLDILOCKS_B200_API uint64_t goldilocks_b200_launch_count(void);
+/* Per-launch CUDA-event timing for bench.py's roofline leg.  profile(1) clears the log and starts
+ * bracketing every kernel launch with two events on its stream; profile(0) stops.  profile_read()
+ * waits for the recorded events and writes up to `max` entries: names[64*k..] = lane functor name of
+ * launch k (e.g. "LaneEdVerifyFinish"), ms[k] = its device time.  Returns the number written. */
+GOLDILOCKS_B200_API void goldilocks_b200_profile(int enable);
+GOLDILOCKS_B200_API size_t goldilocks_b200_profile_read(char *names, float *ms, size_t max);
 /* Copies the device-built fixed-base comb table (80 niels x 3 gf, canonical radix-2^56 limbs =
  * 15360 bytes, the layout of the reference's goldilocks_448_precomputed_base) to `out`. */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_export_comb_table(uint8_t out[15360]);

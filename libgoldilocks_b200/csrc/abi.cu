@@ -9,28 +9,15 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <typeinfo>
 #include <vector>
 
 #include "../../include/goldilocks_b200.h"
-#include "lanes.cuh"
+#include "launch.cuh"
 
-// ------------------------------------------------------------------------------------------------
-// Kernels: thin launch shapes around the lane functors of lanes.cuh
-// ------------------------------------------------------------------------------------------------
-#define BLOCK 128
-
-template <class F>
-__global__ void __launch_bounds__(BLOCK) k_lanes(F f, size_t n) {
-    const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    if (i < n) f(i);
-}
-// Persistent grid-stride shape for functors that own a per-thread scratch slot in HBM.
-template <class F>
-__global__ void __launch_bounds__(BLOCK) k_lanes_slot(F f, size_t n) {
-    const size_t slot = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * BLOCK;
-    for (size_t i = slot; i < n; i += stride) f(i, slot);
-}
+// kernels live in k_*.cu
+LANES_PLAIN(DECLARE_PLAIN)
+LANES_SLOT(DECLARE_SLOT)
 
 // ------------------------------------------------------------------------------------------------
 // Per-device context
@@ -62,19 +49,43 @@ bool fail(const char *what, cudaError_t e) {
 }
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(#x, e_); } while (0)
 
+// Optional per-launch CUDA-event timing (bench.py's roofline leg): when enabled every launch is
+// bracketed by two events on its own stream; goldilocks_b200_profile_read() resolves them later.
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+std::atomic<int> g_prof_on{0};
+cudaEvent_t prof_begin(const char *name, cudaStream_t s, cudaEvent_t *end) {
+    cudaEvent_t a = nullptr;
+    *end = nullptr;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(end) != cudaSuccess) return nullptr;
+    cudaEventRecord(a, s);
+    (void)name;
+    return a;
+}
+void prof_end(const char *name, cudaStream_t s, cudaEvent_t a, cudaEvent_t b) {
+    if (!a || !b) return;
+    cudaEventRecord(b, s);
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    g_prof.push_back({name, a, b});
+}
+
 template <class F>
 bool launch(Ctx &c, const F &f, size_t n, cudaStream_t s) {
     if (n == 0) return true;
-    k_lanes<F><<<(unsigned)((n + BLOCK - 1) / BLOCK), BLOCK, 0, s>>>(f, n);
     g_launches++;
-    CU(cudaGetLastError());
+    cudaEvent_t a = nullptr, b = nullptr;
+    const bool prof = g_prof_on.load() != 0;
+    if (prof) a = prof_begin(typeid(F).name(), s, &b);
+    CU(launch_lanes<F>(f, n, s));
+    if (prof) prof_end(typeid(F).name(), s, a, b);
     return true;
 }
 // grid = SMs x resident blocks of this kernel, so every thread owns exactly one scratch slot
 template <class F>
 bool slot_grid(Ctx &c, int *grid) {
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lanes_slot<F>, BLOCK, 0));
+    CU(lanes_slot_occupancy<F>(&occ));
     if (occ < 1) occ = 1;
     *grid = c.sms * occ;
     return true;
@@ -84,9 +95,12 @@ bool launch_slot(Ctx &c, const F &f, size_t n, int grid, cudaStream_t s) {
     if (n == 0) return true;
     size_t need_blocks = (n + BLOCK - 1) / BLOCK;
     if ((size_t)grid > need_blocks) grid = (int)need_blocks;
-    k_lanes_slot<F><<<grid, BLOCK, 0, s>>>(f, n);
     g_launches++;
-    CU(cudaGetLastError());
+    cudaEvent_t a = nullptr, b = nullptr;
+    const bool prof = g_prof_on.load() != 0;
+    if (prof) a = prof_begin(typeid(F).name(), s, &b);
+    CU(launch_lanes_slot<F>(f, n, grid, s));
+    if (prof) prof_end(typeid(F).name(), s, a, b);
     return true;
 }
 
@@ -227,6 +241,29 @@ const uint8_t goldilocks_x448_base_point[GOLDILOCKS_X448_PUBLIC_BYTES] = {5};
 goldilocks_error_t goldilocks_b200_init(void) { Call k; return k.finish(); }
 const char *goldilocks_b200_last_error(void) { return g_err.c_str(); }
 uint64_t goldilocks_b200_launch_count(void) { return g_launches.load(); }
+void goldilocks_b200_profile(int enable) {
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    if (enable) {
+        for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        g_prof.clear();
+    }
+    g_prof_on.store(enable ? 1 : 0);
+}
+size_t goldilocks_b200_profile_read(char *names, float *ms, size_t max) {
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    size_t k = 0;
+    for (auto &r : g_prof) {
+        if (k >= max) break;
+        float t = 0.f;
+        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) t = -1.f;
+        const char *nm = r.name;
+        while (*nm >= '0' && *nm <= '9') nm++; /* strip the Itanium length prefix of typeid().name() */
+        snprintf(names + 64 * k, 64, "%s", nm);
+        ms[k] = t;
+        k++;
+    }
+    return k;
+}
 
 goldilocks_error_t goldilocks_b200_export_comb_table(uint8_t out[15360]) {
     Call k;

@@ -294,7 +294,18 @@ GD void base_double_scalarmul_uniform(pt &combo, const sc &scalar1, const pt &ba
         niels_cond_neg(ni, inv1);
         pt_addsub_niels<false>(tmp, ni, i != 0);
     }
-    pt_copy(combo, tmp);
+    /* Reference quirk kept for bit-exact parity: when scalar2 == 0 its wNAF is empty and
+     * goldilocks.c:1281-1284 returns the identity WITHOUT adding scalar1*B. */
+    uint32_t any2 = 0;
+#pragma unroll
+    for (int k = 0; k < SC_WORDS; k++) any2 |= scalar2.w[k];
+    pt ident;
+    pt_set_identity(ident);
+    const gmask_t z2 = (gmask_t)(((uint64_t)any2 - 1) >> 32);
+    gf_cond_sel(combo.x, tmp.x, ident.x, z2);
+    gf_cond_sel(combo.y, tmp.y, ident.y, z2);
+    gf_cond_sel(combo.z, tmp.z, ident.z, z2);
+    gf_cond_sel(combo.t, tmp.t, ident.t, z2);
 }
 
 // ---------------------------------------------------------------------------------------------

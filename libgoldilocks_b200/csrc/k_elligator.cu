@@ -1,0 +1,4 @@
+// k_elligator.cu -- explicit kernel instantiations (see launch.cuh)
+#include "launch.cuh"
+INSTANTIATE_PLAIN(LaneFromHash<false>)
+INSTANTIATE_PLAIN(LaneFromHash<true>)

@@ -1,0 +1,8 @@
+// k_point.cu -- explicit kernel instantiations (see launch.cuh)
+#include "launch.cuh"
+INSTANTIATE_PLAIN(LanePt<PTOP_ADD>)
+INSTANTIATE_PLAIN(LanePt<PTOP_SUB>)
+INSTANTIATE_PLAIN(LanePt<PTOP_DBL>)
+INSTANTIATE_PLAIN(LanePt<PTOP_NEG>)
+INSTANTIATE_PLAIN(LanePtEq)
+INSTANTIATE_PLAIN(LanePtValid)

@@ -1,0 +1,3 @@
+// k_tables.cu -- explicit kernel instantiations (see launch.cuh)
+#include "launch.cuh"
+INSTANTIATE_PLAIN(LaneBuildTables)

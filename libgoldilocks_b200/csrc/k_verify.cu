@@ -1,0 +1,5 @@
+// k_verify.cu -- explicit kernel instantiations (see launch.cuh)
+#include "launch.cuh"
+INSTANTIATE_PLAIN(LaneEdVerifyDecode)
+INSTANTIATE_PLAIN(LaneEdVerifyScalars)
+INSTANTIATE_SLOT(LaneEdVerifyFinish)

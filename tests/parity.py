@@ -1,0 +1,262 @@
+"""Parity checks shared by the CPU tier (lib = host simulator of the CUDA sources) and the GPU tier
+(lib = libgoldilocks_b200.so on a B200).  `chk` is the checker (reference build or oracle).
+Every comparison is bit-exact (integer/byte work)."""
+import hashlib
+
+import numpy as np
+
+import util
+from util import P, Q, le, stream_bytes
+
+
+def eq(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, a.shape, b.shape)
+    if not (a == b).all():
+        bad = np.argwhere((a != b).reshape(len(a), -1).any(axis=1)).ravel()
+        raise AssertionError("%s: %d of %d elements differ, first at %d" % (what, len(bad), len(a), bad[0]))
+
+
+def check_field(lib, chk, n):
+    """BASELINE config 1 (field half): gf_mul/sqr/add/sub/mulw on n random + edge pairs"""
+    a, b = util.field_inputs("c1/field", n)
+    eq(lib.gf_mul(a, b), chk.gf_mul(a, b), "gf_mul")
+    eq(lib.gf_sqr(a), chk.gf_sqr(a), "gf_sqr")
+    eq(lib.gf_add(a, b), chk.gf_add(a, b), "gf_add")
+    eq(lib.gf_sub(a, b), chk.gf_sub(a, b), "gf_sub")
+    for w in (1, 39081, 39082, 156326, (1 << 28) - 1):
+        eq(lib.gf_mulw(a[: max(64, n // 8)], w), chk.gf_mulw(a[: max(64, n // 8)], w), "gf_mulw %d" % w)
+
+
+def check_field_isr(lib, chk, n):
+    a, _ = util.field_inputs("c1/isr", n)
+    r1, s1 = lib.gf_isr(a)
+    r2, s2 = chk.gf_isr(a)
+    eq(s1, s2, "gf_isr status")
+    eq(r1, r2, "gf_isr value")
+    eq(lib.gf_invert(a), chk.gf_invert(a), "gf_invert")
+
+
+def check_points(lib, chk, n):
+    """BASELINE config 1 (group half): all four coordinates of add/sub/double, canonicalised"""
+    p = util.random_points(chk, "c1/p", n)
+    q = util.random_points(chk, "c1/q", n)
+    # also feed non-trivial projective representatives (outputs of earlier group operations)
+    p2 = chk.point_add(p, q)
+    q2 = chk.point_double(q)
+    ident = np.zeros((1, 4, 8), "<u8"); ident[0, 1, 0] = 1; ident[0, 2, 0] = 1
+    ident = ident.view(np.uint8).reshape(1, 256)
+    pa = np.concatenate([p, p2, ident, p[:1], ident])
+    qa = np.concatenate([q, q2, ident, ident, q[:1]])
+    c = util.coords_fast
+    eq(c(chk, lib.point_add(pa, qa)), c(chk, chk.point_add(pa, qa)), "point_add coords")
+    eq(c(chk, lib.point_sub(pa, qa)), c(chk, chk.point_sub(pa, qa)), "point_sub coords")
+    eq(c(chk, lib.point_double(pa)), c(chk, chk.point_double(pa)), "point_double coords")
+    eq(c(chk, lib.point_negate(pa)), c(chk, chk.point_negate(pa)), "point_negate coords")
+    eq(lib.point_eq(pa, qa), chk.point_eq(pa, qa), "point_eq")
+    eq(lib.point_eq(pa, pa), chk.point_eq(pa, pa), "point_eq self")
+    eq(lib.point_valid(pa), chk.point_valid(pa), "point_valid")
+    garbage = stream_bytes("c1/garbage", 8 * 256).reshape(8, 256) & 0x7f
+    eq(lib.point_valid(garbage), chk.point_valid(garbage), "point_valid garbage")
+
+
+def check_codec(lib, chk, n):
+    """BASELINE config 5: decaf encode/decode + Elligator"""
+    h = stream_bytes("c5/h", n * 112).reshape(n, 112)
+    c = util.coords_fast
+    pts = chk.from_hash_uniform(h)
+    eq(c(chk, lib.from_hash_uniform(h)), c(chk, pts), "from_hash_uniform coords")
+    eq(c(chk, lib.from_hash_nonuniform(h[:, :56])), c(chk, chk.from_hash_nonuniform(h[:, :56])), "from_hash_nonuniform coords")
+    proj = chk.point_add(pts, chk.point_double(pts[::-1].copy()))
+    allp = np.concatenate([pts, proj])
+    ser = chk.point_encode(allp)
+    eq(lib.point_encode(allp), ser, "point_encode")
+    d1, s1 = lib.point_decode(ser)
+    d2, s2 = chk.point_decode(ser)
+    eq(s1, s2, "point_decode status (valid)")
+    assert (s2 == -1).all()
+    eq(c(chk, d1), c(chk, d2), "point_decode coords")
+    # random strings (about a quarter decode), edge strings, identity with both flags
+    rnd = np.concatenate([stream_bytes("c5/rnd", n * 56).reshape(n, 56), util.field_edge_values()])
+    rnd[: n // 2, 0] &= 0xfe
+    rnd[: n // 2, 55] &= 0x7f
+    for allow in (False, True):
+        d1, s1 = lib.point_decode(rnd, allow)
+        d2, s2 = chk.point_decode(rnd, allow)
+        eq(s1, s2, "point_decode status (random, allow_identity=%s)" % allow)
+        ok = s2 == -1
+        eq(c(chk, d1[ok]), c(chk, d2[ok]), "point_decode coords (random)")
+    eq(lib.encode_like_eddsa(allp), chk.encode_like_eddsa(allp), "encode_like_eddsa")
+    eq(lib.encode_like_x448(allp), chk.encode_like_x448(allp), "encode_like_x448")
+    enc = chk.encode_like_eddsa(allp)
+    extra = np.zeros((6, 57), np.uint8)
+    extra[0] = le(1, 57); extra[1] = le(P - 1, 57); extra[2] = le(0, 57); extra[3] = le(0, 57); extra[3, 56] = 0x80
+    extra[4] = le(P, 57); extra[5] = enc[0]; extra[5, 56] |= 0x01
+    flip = enc.copy(); flip[:, 56] ^= 0x80
+    rnd57 = stream_bytes("c5/rnd57", n * 57).reshape(n, 57); rnd57[:, 56] &= 0x80
+    allenc = np.concatenate([enc, flip, extra, rnd57])
+    d1, s1 = lib.decode_like_eddsa(allenc)
+    d2, s2 = chk.decode_like_eddsa(allenc)
+    eq(s1, s2, "decode_like_eddsa status")
+    ok = s2 == -1
+    eq(c(chk, d1[ok]), c(chk, d2[ok]), "decode_like_eddsa coords")
+
+
+def check_scalars(lib, chk, n):
+    a = np.concatenate([util.random_scalars(chk, "sc/a", n), util.scalar_edge_bytes()])
+    b = np.concatenate([util.random_scalars(chk, "sc/b", n), util.scalar_edge_bytes()[::-1]])
+    eq(lib.scalar_add(a, b), chk.scalar_add(a, b), "scalar_add")
+    eq(lib.scalar_sub(a, b), chk.scalar_sub(a, b), "scalar_sub")
+    eq(lib.scalar_mul(a, b), chk.scalar_mul(a, b), "scalar_mul")
+    eq(lib.scalar_halve(a), chk.scalar_halve(a), "scalar_halve")
+    for ln in (0, 1, 31, 55, 56, 57, 112, 113, 114, 200):
+        ser = stream_bytes("sc/long%d" % ln, max(1, 64 * ln)).reshape(64, ln) if ln else np.zeros((4, 0), np.uint8)
+        if ln:
+            ser[0] = 0xff
+        got, want = lib.scalar_decode_long(ser, ln), chk.scalar_decode_long(ser, ln)
+        eq(got, want, "scalar_decode_long len %d" % ln)
+        for i in range(min(4, len(ser))):
+            assert util.from_le(want[i]) == util.from_le(ser[i]) % Q
+
+
+def check_comb(lib, chk, n):
+    """BASELINE config 2: fixed-base comb, compared as decaf and EdDSA encodings"""
+    s = np.concatenate([util.random_scalars(chk, "c2/s", n), util.scalar_edge_bytes()])
+    got, want = lib.precomputed_scalarmul(s), chk.precomputed_scalarmul(s)
+    eq(lib.point_eq(got, want), np.ones(len(s), bool), "comb point_eq")
+    eq(chk.point_encode(got), chk.point_encode(want), "comb decaf encoding")
+    eq(chk.encode_like_eddsa(got), chk.encode_like_eddsa(want), "comb eddsa encoding")
+    assert chk.point_valid(got).all()
+
+
+def check_scalarmul(lib, chk, n):
+    s = np.concatenate([util.random_scalars(chk, "sm/s", n), util.scalar_edge_bytes()])
+    t = np.concatenate([util.random_scalars(chk, "sm/t", n), util.scalar_edge_bytes()[::-1]])
+    p = util.random_points(chk, "sm/p", len(s))
+    got, want = lib.point_scalarmul(p, s), chk.point_scalarmul(p, s)
+    eq(chk.point_encode(got), chk.point_encode(want), "point_scalarmul")
+    eq(chk.encode_like_eddsa(got), chk.encode_like_eddsa(want), "point_scalarmul eddsa encoding")
+    got, want = lib.base_double_scalarmul_non_secret(s, p, t), chk.base_double_scalarmul_non_secret(s, p, t)
+    eq(chk.point_encode(got), chk.point_encode(want), "base_double_scalarmul_non_secret")
+    q = util.random_points(chk, "sm/q", len(s))
+    got, want = lib.point_double_scalarmul(p, s, q, t), chk.point_double_scalarmul(p, s, q, t)
+    eq(chk.point_encode(got), chk.point_encode(want), "point_double_scalarmul")
+
+
+def x448_inputs(n):
+    u = stream_bytes("c3/u", n * 56).reshape(n, 56)
+    k = stream_bytes("c3/k", n * 56).reshape(n, 56)
+    edge_u = np.stack([le(v) for v in (0, 1, P - 1, P, P + 5, 2**448 - 1, 5, P + 1, 2**447)])
+    edge_k = stream_bytes("c3/ek", len(edge_u) * 56).reshape(-1, 56)
+    return np.concatenate([u, edge_u]), np.concatenate([k, edge_k])
+
+
+def check_x448(lib, chk, n):
+    """BASELINE config 3: X448 incl. the non-canonical / low-order inputs of SURVEY.md 8(a) notes"""
+    u, k = x448_inputs(n)
+    o1, s1 = lib.x448(u, k)
+    o2, s2 = chk.x448(u, k)
+    eq(s1, s2, "x448 status")
+    eq(o1, o2, "x448 output")
+    assert (s2[n:n + 3] == 0).all() and (o2[n:n + 3] == 0).all()      # u in {0,1,p-1}: FAILURE and zeros
+    eq(lib.x448_derive_public_key(k), chk.x448_derive_public_key(k), "x448_derive_public_key")
+    base = np.zeros((len(k), 56), np.uint8); base[:, 0] = 5
+    eq(lib.x448(base, k)[0], chk.x448_derive_public_key(k), "x448(base) == derive_public_key")
+
+
+def check_x448_vectors(lib, vectors, iters=1000):
+    """RFC 7748 iterated ladder (reference test_goldilocks.cxx:546-565)"""
+    k = np.zeros((1, 56), np.uint8); k[0, 0] = 5
+    u = k.copy()
+    for i in range(iters):
+        n, st = lib.x448(u, k)
+        assert st[0] == -1
+        u, k = k, n
+        if i == 0:
+            assert bytes(k[0]).hex() == vectors["x448_iter"]["1"]
+    if iters >= 1000:
+        assert bytes(k[0]).hex() == vectors["x448_iter"]["1000"]
+
+
+def eddsa_case(c):
+    msg = bytes.fromhex(c["msg"])
+    if c["prehashed"]:
+        msg = hashlib.shake_256(msg).digest(64)     # Ed448ph: PH = SHAKE256(msg, 64) (reference ed448.h prehash)
+    return (np.frombuffer(bytes.fromhex(c["sk"]), np.uint8)[None], bytes.fromhex(c["pk"]), msg, c["prehashed"],
+            bytes.fromhex(c["context"]), bytes.fromhex(c["sig"]))
+
+
+def check_eddsa_vectors(lib, vectors):
+    """RFC 8032 Ed448 x 11: public key, signature bytes, verify (reference test_goldilocks.cxx:501-543)"""
+    for t, c in enumerate(vectors["eddsa"]):
+        sk, pk, msg, ph, ctx, sig = eddsa_case(c)
+        got_pk = lib.ed448_derive_public_key(sk)
+        assert bytes(got_pk[0]) == pk, "RFC 8032 case %d: public key" % t
+        got_sig = lib.ed448_sign(sk, got_pk, [msg], ph, ctx)
+        assert bytes(got_sig[0]) == sig, "RFC 8032 case %d: signature" % t
+        assert lib.ed448_verify(got_sig, got_pk, [msg], ph, ctx)[0] == -1, "RFC 8032 case %d: verify" % t
+        assert lib.ed448_verify(got_sig, got_pk, [msg + b"x"], ph, ctx)[0] == 0
+        assert lib.ed448_verify(got_sig, got_pk, [msg], not ph, ctx)[0] == 0
+        assert lib.ed448_verify(got_sig, got_pk, [msg], ph, ctx + b"y")[0] == 0
+
+
+def check_decaf_vectors(lib, vectors):
+    """16 multiples of the base point and 16 Elligator pairs (reference test_goldilocks.cxx:665-680)"""
+    want = np.stack([np.frombuffer(bytes.fromhex(x), np.uint8) for x in vectors["base_multiples"]])
+    sc = np.zeros((16, 56), np.uint8); sc[:, 0] = np.arange(16)
+    eq(lib.point_encode(lib.precomputed_scalarmul(sc)), want, "i*B encodings via comb")
+    base, st = lib.point_decode(want[1:2])
+    assert st[0] == -1
+    acc = np.zeros((1, 4, 8), "<u8"); acc[0, 1, 0] = 1; acc[0, 2, 0] = 1
+    acc = acc.view(np.uint8).reshape(1, 256)
+    for i in range(16):
+        assert bytes(lib.point_encode(acc)[0]) == bytes(want[i]), "%d*B" % i
+        acc = lib.point_add(acc, base)
+    d, st = lib.point_decode(want, True)
+    assert (st == -1).all()
+    d, st = lib.point_decode(want, False)
+    assert st[0] == 0 and (st[1:] == -1).all()
+    one = np.zeros((1, 56), np.uint8); one[0, 0] = 1
+    assert lib.point_decode(one, True)[1][0] == 0            # decode rejects [1] (test_goldilocks.cxx:334-341)
+    inp = np.stack([np.frombuffer(bytes.fromhex(x), np.uint8) for x in vectors["elligator_inputs"]])
+    out = np.stack([np.frombuffer(bytes.fromhex(x), np.uint8) for x in vectors["elligator_outputs"]])
+    eq(lib.point_encode(lib.from_hash_nonuniform(inp)), out, "Elligator KATs")
+    patho = np.frombuffer(bytes.fromhex(vectors["elli_patho"]), np.uint8)[None]
+    assert lib.point_valid(lib.from_hash_nonuniform(patho)).all()
+
+
+def check_eddsa_random(lib, chk, n, label="c4"):
+    """BASELINE config 4 shape: keys x messages with 1/8 corrupted; keygen/sign bytes and accept bits"""
+    sig, pk, msgs, kinds = util.verify_corpus(chk, label, n)
+    sk = stream_bytes(label + "/sk", n * 57).reshape(n, 57)
+    good = kinds == 0
+    pk0 = chk.ed448_derive_public_key(sk)
+    eq(lib.ed448_derive_public_key(sk), pk0, "ed448_derive_public_key")
+    clean_msgs = list(msgs)
+    want = chk.ed448_verify(sig, pk, msgs)
+    eq(lib.ed448_verify(sig, pk, msgs), want, "ed448_verify status")
+    assert (want[good] == -1).all()
+    assert (want[kinds == 5] == -1).all(), "S+q must be accepted like the reference"
+    assert (want[(kinds != 0) & (kinds != 5)] == 0).all()
+    # signing is deterministic: bytes must match for the untouched entries
+    idx = np.flatnonzero(good)
+    sub_msgs = [clean_msgs[i] for i in idx]
+    eq(lib.ed448_sign(sk[idx], pk0[idx], sub_msgs), sig[idx], "ed448_sign bytes")
+    for ctx, ph in ((b"ctx", False), (b"", True), (b"\xff" * 255, True)):
+        m = min(len(idx), 24)
+        s1 = lib.ed448_sign(sk[idx[:m]], pk0[idx[:m]], sub_msgs[:m], ph, ctx)
+        eq(s1, chk.ed448_sign(sk[idx[:m]], pk0[idx[:m]], sub_msgs[:m], ph, ctx), "sign ctx/ph")
+        eq(lib.ed448_verify(s1, pk0[idx[:m]], sub_msgs[:m], ph, ctx), np.full(m, -1, np.int32), "verify ctx/ph")
+
+
+def check_shake(lib, n=40):
+    msgs = [bytes(stream_bytes("shake/%d" % i, i * 7)) for i in range(n)] + [b"", b"a" * 135, b"b" * 136, b"c" * 137, b"d" * 272]
+    for outlen in (32, 57, 114, 136, 137, 300):
+        got = lib.shake256(msgs, outlen)
+        for i, m in enumerate(msgs):
+            assert bytes(got[i]) == hashlib.shake_256(m).digest(outlen), "shake256 len %d out %d" % (len(m), outlen)
+
+
+def check_tables(lib, chk):
+    eq(lib.export_comb_table(), chk.export_comb_table(), "comb table (15360 B)")
+    eq(lib.export_wnaf_table(), chk.export_wnaf_table(), "wNAF base table (6144 B)")

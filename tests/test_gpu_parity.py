@@ -1,0 +1,178 @@
+"""GPU tier: the product library (libgoldilocks_b200.so, through its C ABI) against the checker,
+the reference's golden vectors, and size-independent properties at BASELINE.json's full 2^20 sizes."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+import util
+from util import stream_bytes
+
+pytestmark = pytest.mark.gpu
+FULL = 1 << 20
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _threads(chk):
+    util.set_threads(chk, os.cpu_count() or 1)
+
+
+def test_tables(gpu, chk):
+    parity.check_tables(gpu, chk)
+
+
+def test_field_full(gpu, chk):
+    """config 1: 2^20 random + edge pairs, bit-exact against the checker"""
+    parity.check_field(gpu, chk, FULL)
+    parity.check_field_isr(gpu, chk, 1 << 14)
+
+
+def test_points_full(gpu, chk):
+    parity.check_points(gpu, chk, 1 << 17)
+
+
+def test_codec_elligator(gpu, chk):
+    parity.check_codec(gpu, chk, 1 << 14)
+
+
+def test_scalars(gpu, chk):
+    parity.check_scalars(gpu, chk, 1 << 16)
+
+
+def test_comb(gpu, chk):
+    parity.check_comb(gpu, chk, 1 << 14)
+
+
+def test_scalarmul(gpu, chk):
+    parity.check_scalarmul(gpu, chk, 1 << 11)
+
+
+def test_x448(gpu, chk, vectors):
+    parity.check_x448(gpu, chk, 1 << 12)
+    parity.check_x448_vectors(gpu, vectors, iters=1000)
+
+
+def test_eddsa_vectors(gpu, vectors):
+    parity.check_eddsa_vectors(gpu, vectors)
+
+
+def test_eddsa_random(gpu, chk):
+    parity.check_eddsa_random(gpu, chk, 1 << 12)
+
+
+def test_decaf_vectors(gpu, vectors):
+    parity.check_decaf_vectors(gpu, vectors)
+
+
+def test_shake(gpu):
+    parity.check_shake(gpu)
+
+
+def test_empty_and_single(gpu):
+    z56 = np.zeros((0, 56), np.uint8)
+    assert gpu.gf_mul(z56, z56).shape == (0, 56)
+    assert gpu.x448(z56, z56)[0].shape == (0, 56)
+    assert gpu.ed448_verify(np.zeros((0, 114), np.uint8), np.zeros((0, 57), np.uint8), []).shape == (0,)
+
+
+def test_legacy_single_element_symbols(gpu, vectors):
+    """the reference's own function names, batch of one on the GPU"""
+    import ctypes as C
+    L = gpu.lib
+    c = vectors["eddsa"][0]
+    sk = (C.c_uint8 * 57).from_buffer_copy(bytes.fromhex(c["sk"]))
+    pk = (C.c_uint8 * 57)()
+    sig = (C.c_uint8 * 114)()
+    L.goldilocks_ed448_derive_public_key(pk, sk)
+    assert bytes(pk).hex() == c["pk"]
+    L.goldilocks_ed448_sign(sig, sk, pk, None, C.c_size_t(0), C.c_uint8(0), None, C.c_uint8(0))
+    assert bytes(sig).hex() == c["sig"]
+    L.goldilocks_ed448_verify.restype = C.c_int32
+    assert L.goldilocks_ed448_verify(sig, pk, None, C.c_size_t(0), C.c_uint8(0), None, C.c_uint8(0)) == -1
+    sig[3] ^= 1
+    assert L.goldilocks_ed448_verify(sig, pk, None, C.c_size_t(0), C.c_uint8(0), None, C.c_uint8(0)) == 0
+    base = (C.c_uint8 * 56)(5)
+    out = (C.c_uint8 * 56)()
+    L.goldilocks_x448.restype = C.c_int32
+    assert L.goldilocks_x448(out, base, base) == -1
+    assert bytes(out).hex() == vectors["x448_iter"]["1"]
+    zero = (C.c_uint8 * 56)()
+    assert L.goldilocks_x448(out, zero, base) == 0 and bytes(out) == bytes(56)
+
+
+# ---- size-independent properties at the full 2^20 batch -------------------------------------------
+
+def test_x448_full_dh_commutes(gpu, chk):
+    """config 3 at 2^20: x448(x448(5,a),b) == x448(x448(5,b),a); a checker-compared sample rides along"""
+    n = FULL
+    a = stream_bytes("c3full/a", n * 56).reshape(n, 56)
+    b = stream_bytes("c3full/b", n * 56).reshape(n, 56)
+    base = np.zeros((n, 56), np.uint8); base[:, 0] = 5
+    pa, sa = gpu.x448(base, a)
+    pb, sb = gpu.x448(base, b)
+    ab, s1 = gpu.x448(pa, b)
+    ba, s2 = gpu.x448(pb, a)
+    assert (sa == -1).all() and (sb == -1).all() and (s1 == -1).all() and (s2 == -1).all()
+    parity.eq(ab, ba, "x448 DH commutativity over 2^20")
+    m = 1 << 11
+    idx = np.arange(0, n, n // m)
+    parity.eq(ab[idx], chk.x448(pa[idx], b[idx])[0], "x448 sample vs checker")
+
+
+def test_comb_full_linearity(gpu, chk):
+    """config 2 at 2^20: comb(a) + comb(b) == comb(a+b), plus a checker-compared sample"""
+    n = FULL
+    a = gpu.scalar_decode_long(stream_bytes("c2full/a", n * 56).reshape(n, 56), 56)
+    b = gpu.scalar_decode_long(stream_bytes("c2full/b", n * 56).reshape(n, 56), 56)
+    pa, pb = gpu.precomputed_scalarmul(a), gpu.precomputed_scalarmul(b)
+    pab = gpu.precomputed_scalarmul(gpu.scalar_add(a, b))
+    assert gpu.point_eq(gpu.point_add(pa, pb), pab).all()
+    idx = np.arange(0, n, n // (1 << 12))
+    parity.eq(gpu.point_encode(pa[idx]), chk.point_encode(chk.precomputed_scalarmul(a[idx])), "comb sample vs checker")
+
+
+def test_verify_full(gpu, chk):
+    """config 4 at 2^20: 2^16 keys x 16 messages, 1/8 corrupted; accept bits must follow the corruption
+    kinds (S+q accepted, everything else rejected) and a checker-compared sample must agree bit for bit"""
+    nk, per = 1 << 16, 16
+    n = nk * per
+    sk = stream_bytes("c4full/sk", nk * 57).reshape(nk, 57)
+    pk = gpu.ed448_derive_public_key(sk)
+    sk_all, pk_all = np.repeat(sk, per, axis=0), np.repeat(pk, per, axis=0)
+    arena = stream_bytes("c4full/msg", n * 32)
+    off = (np.arange(n + 1, dtype=np.uint64) * 32)
+    sig = gpu.ed448_sign(sk_all, pk_all, (arena, off))
+    kinds = np.zeros(n, np.int32)
+    kinds[::8] = 1 + (np.arange(n // 8) % 5)
+    sel = stream_bytes("c4full/sel", n)
+    i1 = np.flatnonzero(kinds == 1); sig[i1, sel[i1] % 57] ^= 1
+    i2 = np.flatnonzero(kinds == 2); sig[i2, 57 + sel[i2] % 56] ^= 2
+    i3 = np.flatnonzero(kinds == 3); pk_all[i3, sel[i3] % 57] ^= 4
+    i4 = np.flatnonzero(kinds == 4); arena[i4 * 32 + sel[i4] % 32] ^= 8
+    for i in np.flatnonzero(kinds == 5)[:4096]:
+        sig[i, 57:114] = util.le(util.from_le(sig[i, 57:114]) + util.Q, 57)
+    kinds[np.flatnonzero(kinds == 5)[4096:]] = 0
+    st = gpu.ed448_verify(sig, pk_all, (arena, off))
+    expect = np.where((kinds == 0) | (kinds == 5), -1, 0).astype(np.int32)
+    parity.eq(st, expect, "verify accept bits over 2^20")
+    idx = np.arange(0, n, n // (1 << 12) - 1)[: 1 << 12]
+    sub = (np.concatenate([arena[i * 32:(i + 1) * 32] for i in idx]), np.arange(len(idx) + 1, dtype=np.uint64) * 32)
+    parity.eq(st[idx], chk.ed448_verify(sig[idx], pk_all[idx], sub), "verify sample vs checker")
+    parity.eq(sig[idx[:512]] if False else gpu.ed448_sign(sk_all[idx[:512]], pk_all[idx[:512]] if False else np.repeat(pk, per, axis=0)[idx[:512]],
+              (sub[0][: 512 * 32], sub[1][:513])),
+              chk.ed448_sign(sk_all[idx[:512]], np.repeat(pk, per, axis=0)[idx[:512]], (sub[0][: 512 * 32], sub[1][:513])), "sign sample vs checker")
+
+
+def test_codec_roundtrip_large(gpu, chk):
+    """config 5 shape (2^20 here): encode(decode(encode(P))) is idempotent and hashed points are valid"""
+    n = FULL
+    h = stream_bytes("c5full/h", n * 56).reshape(n, 56)
+    pts = gpu.from_hash_nonuniform(h)
+    ser = gpu.point_encode(pts)
+    dec, st = gpu.point_decode(ser)
+    assert (st == -1).all()
+    parity.eq(gpu.point_encode(dec), ser, "encode/decode round trip over 2^20")
+    assert gpu.point_eq(dec, pts).all()
+    idx = np.arange(0, n, n // (1 << 13))
+    parity.eq(ser[idx], chk.point_encode(chk.from_hash_nonuniform(h[idx])), "elligator+encode sample vs checker")

@@ -1,0 +1,61 @@
+"""CPU tier: the CUDA sources' device math compiled for the host (tests/hostsim, with limb-bound
+assertions on) against the checker and the reference's golden vectors.  No GPU needed."""
+import os
+
+import parity
+import util
+
+
+def _threads(*libs):
+    for lib in libs:
+        util.set_threads(lib, os.cpu_count() or 1)
+
+
+def test_field(sim, chk):
+    _threads(sim, chk)
+    parity.check_field(sim, chk, 4096)
+    parity.check_field_isr(sim, chk, 256)
+
+
+def test_points(sim, chk):
+    parity.check_points(sim, chk, 1024)
+
+
+def test_codec_elligator(sim, chk):
+    parity.check_codec(sim, chk, 256)
+
+
+def test_scalars(sim, chk):
+    parity.check_scalars(sim, chk, 1024)
+
+
+def test_tables(sim, chk):
+    parity.check_tables(sim, chk)
+
+
+def test_comb(sim, chk):
+    parity.check_comb(sim, chk, 256)
+
+
+def test_scalarmul(sim, chk):
+    parity.check_scalarmul(sim, chk, 64)
+
+
+def test_x448(sim, chk, vectors):
+    _threads(sim, chk)
+    parity.check_x448(sim, chk, 128)
+    parity.check_x448_vectors(sim, vectors, iters=1000)
+
+
+def test_eddsa(sim, chk, vectors):
+    _threads(sim, chk)
+    parity.check_eddsa_vectors(sim, vectors)
+    parity.check_eddsa_random(sim, chk, 192)
+
+
+def test_decaf_vectors(sim, vectors):
+    parity.check_decaf_vectors(sim, vectors)
+
+
+def test_shake(sim):
+    parity.check_shake(sim)

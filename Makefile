@@ -17,7 +17,7 @@ LIB       := libgoldilocks_b200/libgoldilocks_b200.so
 all: lib hostsim oracle
 lib: $(LIB)
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS_$*) $(HDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c -o $@ $< 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
 

@@ -531,7 +531,10 @@ goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t
     const uint8_t *dsk = k.in(privkey, 57 * n), *dpk = k.in(pubkey, 57 * n);
     abi_sc *secret = k.out<abi_sc>(n), *nonce = k.out<abi_sc>(n), *nonce4 = k.out<abi_sc>(n);
     uint8_t *dsig = k.out<uint8_t>(114 * n);
-    LaneEdSignNonce f1 = {secret, nonce, nonce4, dsk, dmsg, doff, prehashed, dctx, context_len};
+    uint8_t *seed = k.out<uint8_t>(57 * n);
+    LaneEdSignExpand f0 = {secret, seed, dsk};
+    k.run(f0, n);
+    LaneEdSignNonce f1 = {nonce, nonce4, seed, dmsg, doff, prehashed, dctx, context_len};
     k.run(f1, n);
     LaneEdSignR f2 = {dsig, nonce4, k.ok ? k.c->ft : nullptr};
     k.run(f2, n);
@@ -542,6 +545,7 @@ goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t
         cudaMemsetAsync(secret, 0, sizeof(abi_sc) * n, k.c->stream);
         cudaMemsetAsync(nonce, 0, sizeof(abi_sc) * n, k.c->stream);
         cudaMemsetAsync(nonce4, 0, sizeof(abi_sc) * n, k.c->stream);
+        cudaMemsetAsync(seed, 0, 57 * n, k.c->stream);
     }
     return k.finish();
 }

@@ -54,48 +54,59 @@ GD void keccak_f1600(keccak_state &st) {
     for (int r = 0; r < 24; r++) kc_round(st.a, kc_rc(r));
 }
 
-// Streaming byte-wise SHAKE256 sponge kept deliberately simple: callers feed bytes one at a time
-// through xor_byte(); hashing is <1% of an EdDSA verification.
+// Streaming byte-wise SHAKE256 sponge.  Bytes are staged in a 136-byte word buffer (dynamic indexing
+// -> local memory, L1 resident) and whole blocks are XORed into the register-resident state with
+// compile-time lane indices; squeezing reads the same buffer.  Hashing is <1% of an EdDSA verify.
 struct shake256_ctx {
     keccak_state st;
+    uint32_t buf[SHAKE256_RATE / 4];
     int pos;
 };
+GD void kc_buf_clear(shake256_ctx &c) {
+#pragma unroll
+    for (int i = 0; i < SHAKE256_RATE / 4; i++) c.buf[i] = 0;
+}
 GD void shake256_init(shake256_ctx &c) {
 #pragma unroll
     for (int i = 0; i < 25; i++) c.st.a[i] = 0;
+    kc_buf_clear(c);
     c.pos = 0;
 }
-// XOR one byte into lane storage without dynamic register indexing.
-GD void kc_xor_byte(keccak_state &st, int pos, uint8_t v) {
-    const uint64_t x = (uint64_t)v << (8 * (pos & 7));
-    const int lane = pos >> 3;
+// state ^= buffered block; permute (reference shake.c:89-112 absorb + dokeccak)
+GD void kc_absorb_block(shake256_ctx &c) {
 #pragma unroll
-    for (int i = 0; i < SHAKE256_RATE / 8; i++) st.a[i] ^= (i == lane) ? x : 0ull;
+    for (int i = 0; i < SHAKE256_RATE / 8; i++) c.st.a[i] ^= (uint64_t)c.buf[2 * i] | ((uint64_t)c.buf[2 * i + 1] << 32);
+    keccak_f1600(c.st);
 }
-GD uint8_t kc_get_byte(const keccak_state &st, int pos) {
-    const int lane = pos >> 3;
-    uint64_t x = 0;
+GD void kc_fill_output(shake256_ctx &c) {
 #pragma unroll
-    for (int i = 0; i < SHAKE256_RATE / 8; i++) x |= (i == lane) ? st.a[i] : 0ull;
-    return (uint8_t)(x >> (8 * (pos & 7)));
+    for (int i = 0; i < SHAKE256_RATE / 8; i++) {
+        c.buf[2 * i] = (uint32_t)c.st.a[i];
+        c.buf[2 * i + 1] = (uint32_t)(c.st.a[i] >> 32);
+    }
 }
 GD void shake256_absorb_byte(shake256_ctx &c, uint8_t v) {
-    kc_xor_byte(c.st, c.pos, v);
+    c.buf[c.pos >> 2] |= (uint32_t)v << (8 * (c.pos & 3));
     if (++c.pos == SHAKE256_RATE) {
-        keccak_f1600(c.st);
+        kc_absorb_block(c);
+        kc_buf_clear(c);
         c.pos = 0;
     }
 }
 GD void shake256_finish_absorb(shake256_ctx &c) { /* reference shake.c:136-142: pad 0x1f ... 0x80 */
-    kc_xor_byte(c.st, c.pos, 0x1f);
-    kc_xor_byte(c.st, SHAKE256_RATE - 1, 0x80);
-    keccak_f1600(c.st);
+    c.buf[c.pos >> 2] ^= 0x1fu << (8 * (c.pos & 3));
+    c.buf[SHAKE256_RATE / 4 - 1] ^= 0x80000000u;
+    kc_absorb_block(c);
+    kc_fill_output(c);
     c.pos = 0;
 }
 GD uint8_t shake256_squeeze_byte(shake256_ctx &c) {
     if (c.pos == SHAKE256_RATE) {
         keccak_f1600(c.st);
+        kc_fill_output(c);
         c.pos = 0;
     }
-    return kc_get_byte(c.st, c.pos++);
+    const uint8_t r = (uint8_t)(c.buf[c.pos >> 2] >> (8 * (c.pos & 3)));
+    c.pos++;
+    return r;
 }

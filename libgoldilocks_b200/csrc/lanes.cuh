@@ -298,9 +298,10 @@ struct LaneShake256 {
 // ---- EdDSA -----------------------------------------------------------------------------------------
 struct CtxAt { const uint8_t *p; GDM uint8_t operator()(uint32_t k) const { return p[k]; } };
 
-// secret scalar of a private key: SHAKE256(sk)[0..57) clamped, mod q  (eddsa.c:98-117)
-GD void ed448_secret_scalar(sc &secret, uint32_t seed_words[15], const uint8_t *sk, bool want_seed) {
-    shake256_ctx h;
+// secret scalar of a private key: SHAKE256(sk)[0..57) clamped, mod q  (eddsa.c:98-117).
+// `h` is left squeezing at byte 57, so a signer can pull the 57 seed bytes straight out of it
+// (eddsa.c:161-176: secret_scalar_ser and seed are the two halves of one 114-byte SHAKE output).
+GD void ed448_secret_scalar(sc &secret, shake256_ctx &h, const uint8_t *sk) {
     shake256_init(h);
     for (int k = 0; k < 57; k++) shake256_absorb_byte(h, sk[k]);
     shake256_finish_absorb(h);
@@ -310,16 +311,12 @@ GD void ed448_secret_scalar(sc &secret, uint32_t seed_words[15], const uint8_t *
     ed448_clamp_words(w);
     ByteAtWords at = {w};
     sc_decode_long(secret, at, 57);
-    if (want_seed) {
-        for (int k = 0; k < 15; k++) seed_words[k] = 0;
-        for (int k = 0; k < 57; k++) seed_words[k >> 2] |= (uint32_t)shake256_squeeze_byte(h) << (8 * (k & 3));
-    }
 }
 struct LaneEdDerivePk { /* eddsa.c:129-144 */
     uint8_t *pk; const uint8_t *sk; const fixed_tables *ft;
     GDM void operator()(size_t i) const {
-        sc s, h1, h2; pt p; uint32_t w[15], sign;
-        ed448_secret_scalar(s, w, sk + 57 * i, false);
+        sc s, h1, h2; pt p; uint32_t w[15], sign; shake256_ctx hk;
+        ed448_secret_scalar(s, hk, sk + 57 * i);
         sc_halve(h1, s);
         sc_halve(h2, h1);      /* GOLDILOCKS_448_EDDSA_ENCODE_RATIO = 4 */
         comb_scalarmul(p, ft->comb, h2);
@@ -331,26 +328,38 @@ struct LaneEdDerivePk { /* eddsa.c:129-144 */
 struct LaneEdSecretScalar { /* goldilocks_ed448_derive_secret_scalar, eddsa.c:98-127 */
     abi_sc *out; const uint8_t *sk;
     GDM void operator()(size_t i) const {
-        sc s, h1, h2; uint32_t w[15];
-        ed448_secret_scalar(s, w, sk + 57 * i, false);
+        sc s, h1, h2; shake256_ctx hk;
+        ed448_secret_scalar(s, hk, sk + 57 * i);
         sc_halve(h1, s);
         sc_halve(h2, h1);
         sc_to_abi(out + i, h2);
     }
 };
-// Signing is split in three launches so each keeps its own register budget:
-//   1) nonce: secret scalar, nonce scalar, nonce/4          (eddsa.c:161-199)
+// Signing is split in four launches so each keeps its own register budget and holds ONE sponge
+// (nvcc 12.9 -O3 miscompiled the kernel that ran the key-expansion sponge and the nonce sponge
+// back to back with the seed handed over in local memory; RFC 8032 vectors guard this on the GPU):
+//   0) expand: secret scalar and seed from SHAKE256(sk)     (eddsa.c:161-171)
+//   1) nonce: nonce scalar, nonce/4                          (eddsa.c:173-199)
 //   2) R = encode(comb(nonce/4))                            (eddsa.c:201-205)
 //   3) S = challenge * secret + nonce ; sig = R || S || 0   (eddsa.c:207-229)
-struct LaneEdSignNonce {
-    abi_sc *secret, *nonce, *nonce4; const uint8_t *sk, *msg; const size_t *off; uint32_t prehashed; const uint8_t *ctx; uint32_t ctx_len;
+struct LaneEdSignExpand { /* eddsa.c:161-171: SHAKE256(sk) -> clamped secret scalar || 57-byte seed (device scratch) */
+    abi_sc *secret; uint8_t *seed; const uint8_t *sk;
     GDM void operator()(size_t i) const {
-        sc s, n, h1, h2; uint32_t seed[15];
-        ed448_secret_scalar(s, seed, sk + 57 * i, true);
+        sc s;
+        shake256_ctx hk;
+        ed448_secret_scalar(s, hk, sk + 57 * i);
+        for (int k = 0; k < 57; k++) seed[57 * i + k] = shake256_squeeze_byte(hk);
+        sc_to_abi(secret + i, s);
+    }
+};
+struct LaneEdSignNonce { /* eddsa.c:173-199: nonce = SHAKE256(dom || seed || msg) mod q, and nonce/4 for the comb */
+    abi_sc *nonce, *nonce4; const uint8_t *seed, *msg; const size_t *off; uint32_t prehashed; const uint8_t *ctx; uint32_t ctx_len;
+    GDM void operator()(size_t i) const {
+        sc n, h1, h2;
         shake256_ctx h;
         CtxAt cat = {ctx};
         ed448_hash_init_with_dom(h, prehashed, cat, ctx_len);
-        for (int k = 0; k < 57; k++) shake256_absorb_byte(h, (uint8_t)(seed[k >> 2] >> (8 * (k & 3))));
+        for (int k = 0; k < 57; k++) shake256_absorb_byte(h, seed[57 * i + k]);
         for (size_t k = off[i]; k < off[i + 1]; k++) shake256_absorb_byte(h, msg[k]);
         shake256_finish_absorb(h);
         uint32_t w[29];
@@ -360,7 +369,6 @@ struct LaneEdSignNonce {
         sc_decode_long(n, at, 114);
         sc_halve(h1, n);
         sc_halve(h2, h1);
-        sc_to_abi(secret + i, s);
         sc_to_abi(nonce + i, n);
         sc_to_abi(nonce4 + i, h2);
     }

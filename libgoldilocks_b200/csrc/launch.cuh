@@ -48,7 +48,7 @@ cudaError_t lanes_slot_occupancy(int *occ) {
     X(LaneComb) X(LaneX448DerivePk) X(LaneX448)                                                     \
     X(LaneSc<SCOP_ADD>) X(LaneSc<SCOP_SUB>) X(LaneSc<SCOP_MUL>) X(LaneSc<SCOP_HALVE>)               \
     X(LaneScDecodeLong) X(LaneShake256)                                                             \
-    X(LaneEdDerivePk) X(LaneEdSecretScalar) X(LaneEdSignNonce) X(LaneEdSignR) X(LaneEdSignFinish)   \
+    X(LaneEdDerivePk) X(LaneEdSecretScalar) X(LaneEdSignExpand) X(LaneEdSignNonce) X(LaneEdSignR) X(LaneEdSignFinish)   \
     X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneBuildTables)
 #define LANES_SLOT(X)                                                                               \
     X(LaneScalarmul) X(LaneDoubleScalarmul) X(LaneBaseDoubleScalarmul) X(LaneEdVerifyFinish)

@@ -107,7 +107,10 @@ EXPORT int32_t goldilocks_ed448_derive_public_key_batch(uint8_t *pk, const uint8
 EXPORT int32_t goldilocks_ed448_sign_batch(uint8_t *sig, const uint8_t *sk, const uint8_t *pk, const uint8_t *msg, const size_t *off,
                                            uint8_t prehashed, const uint8_t *ctx, uint8_t ctx_len, size_t n) {
     std::vector<abi_sc> secret(n), nonce(n), nonce4(n);
-    LaneEdSignNonce f1 = {secret.data(), nonce.data(), nonce4.data(), sk, msg, off, prehashed, ctx, ctx_len};
+    std::vector<uint8_t> seed(57 * n + 1);
+    LaneEdSignExpand f0 = {secret.data(), seed.data(), sk};
+    run(f0, n);
+    LaneEdSignNonce f1 = {nonce.data(), nonce4.data(), seed.data(), msg, off, prehashed, ctx, ctx_len};
     run(f1, n);
     LaneEdSignR f2 = {sig, nonce4.data(), tables()};
     run(f2, n);

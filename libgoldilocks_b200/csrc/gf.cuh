@@ -141,7 +141,7 @@ GD void gf_fold_top(gf &c, uint64_t acc0, uint64_t acc1) {
 //   high[j] = PM[j] - P0[j] + P1[j+8] + PM[j+8]
 // (same identity as the reference's arch_32/f_impl.c:15-69; the subtracted P0[j+8] terms are
 //  accumulated with a signed IMAD.WIDE on a pre-negated operand so they cost no extra instruction.)
-GD void gf_mul(gf &c, const gf &a, const gf &b) {
+GD void gf_mul_body(gf &c, const gf &a, const gf &b) {
     GF_ASSERT_LOOSE(a);
     GF_ASSERT_LOOSE(b);
     uint32_t aa[8], bb[8];
@@ -203,7 +203,7 @@ GD void gf_mul(gf &c, const gf &a, const gf &b) {
 
 // c = a^2 mod p.  LOOSE input, TIGHT output.  108 IMAD.WIDE (the reference's arch_32 has no
 // dedicated squaring, arch_32/f_impl.c:98-100; arch_ref64/f_impl.c:151-301 does).
-GD void gf_sqr(gf &c, const gf &a) {
+GD void gf_sqr_body(gf &c, const gf &a) {
     GF_ASSERT_LOOSE(a);
     uint32_t lo[8], hi[8], aa[8], lo2[8], hi2[8], aa2[8];
     int32_t nlo[8];
@@ -243,6 +243,33 @@ GD void gf_sqr(gf &c, const gf &a) {
     gf_fold_top(r, acc0, acc1);
     gf_copy(c, r);
 }
+
+// Call shape of the two heavy operations.  On the device they are real (non-inlined) functions taking
+// and returning field elements BY VALUE: ptxas passes the 16-limb structs in registers (no local
+// memory, checked in SASS), so a whole scalar multiplication holds exactly one multiplier body and one
+// squaring body (~8 KB of SASS) instead of dozens of inlined copies.  Fully inlined, the verify loop
+// was ~140 KB of code and spent 4 of every 8.5 cycles per issued instruction stalled on instruction
+// fetch (ncu `no_instruction`, profiles/r01_verify_finish_inlined.txt); the instruction cache is
+// 32 KB (L1.5).  Tiny kernels (one or two multiplications) define GF_INLINE_MUL and keep the inline form.
+#if defined(__CUDA_ARCH__) && !defined(GF_INLINE_MUL)
+static __device__ __noinline__ gf gf_mul_fn(gf a, gf b) { gf c; gf_mul_body(c, a, b); return c; }
+static __device__ __noinline__ gf gf_sqr_fn(gf a) { gf c; gf_sqr_body(c, a); return c; }
+static __device__ __noinline__ gf gf_sqrn_fn(gf a, int n) { /* n >= 1 squarings, loop inside the callee */
+#pragma unroll 1
+    for (int i = 0; i < n; i++) gf_sqr_body(a, a);
+    return a;
+}
+GD void gf_mul(gf &c, const gf &a, const gf &b) { c = gf_mul_fn(a, b); }
+GD void gf_sqr(gf &c, const gf &a) { c = gf_sqr_fn(a); }
+GD void gf_sqrn(gf &y, const gf &x, int n) { y = gf_sqrn_fn(x, n); }
+#else
+GD void gf_mul(gf &c, const gf &a, const gf &b) { gf_mul_body(c, a, b); }
+GD void gf_sqr(gf &c, const gf &a) { gf_sqr_body(c, a); }
+GD void gf_sqrn(gf &y, const gf &x, int n) { /* reference field.h:19-38 */
+    gf_sqr(y, x);
+    for (int i = 1; i < n; i++) gf_sqr(y, y);
+}
+#endif
 
 // c = a * w for a small unsigned w < 2^28.  LOOSE input, TIGHT output.  16 IMAD.WIDE.
 // (reference arch_32/f_impl.c:71-96 gf_mulw_unsigned)
@@ -350,11 +377,6 @@ GD gmask_t gf_lobit(const gf &a_in) { /* reference f_generic.c:40-45 */
     return (gmask_t)(-(int32_t)(a.v[0] & 1));
 }
 
-GD void gf_sqrn(gf &y, const gf &x, int n) { /* reference field.h:19-38 */
-    gf_sqr(y, x);
-    for (int i = 1; i < n; i++) gf_sqr(y, y);
-}
-
 // a = x^((p-3)/4) = +-1/sqrt(x); returns all-ones iff a^2 * x == 1 (so x = 0 and non-squares fail).
 // Same exponent as the reference's addition chain (f_arithmetic.c:14-47: 446 S + 13 M) walked as a
 // 12-step table so the GPU code holds one squaring loop and one multiply instead of 26 inlined bodies:
@@ -370,8 +392,7 @@ GD gmask_t gf_isr(gf &a, const gf &x) {
     for (int s = 0; s < 12; s++) {
         const int n = steps[s] & 0xff;
         const gmask_t by_x = (steps[s] & 0x100) ? ~0u : 0u;
-#pragma unroll 1
-        for (int i = 0; i < n; i++) gf_sqr(cur, cur);
+        gf_sqrn(cur, cur, n);
         gf m;
         gf_cond_sel(m, saved, x, by_x); /* schedule is public: not secret dependent */
         gf_mul(cur, cur, m);

@@ -1,4 +1,5 @@
 // k_field.cu -- explicit kernel instantiations (see launch.cuh)
+#define GF_INLINE_MUL 1 /* one or two multiplications per kernel: keep them inline */
 #include "launch.cuh"
 INSTANTIATE_PLAIN(LaneGf<GFOP_MUL>)
 INSTANTIATE_PLAIN(LaneGf<GFOP_SQR>)

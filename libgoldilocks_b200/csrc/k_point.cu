@@ -1,4 +1,5 @@
 // k_point.cu -- explicit kernel instantiations (see launch.cuh)
+#define GF_INLINE_MUL 1 /* one or two multiplications per kernel: keep them inline */
 #include "launch.cuh"
 INSTANTIATE_PLAIN(LanePt<PTOP_ADD>)
 INSTANTIATE_PLAIN(LanePt<PTOP_SUB>)

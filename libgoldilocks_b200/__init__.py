@@ -12,7 +12,8 @@ import os
 
 from .capi import BatchLib, pack_messages, SUCCESS, FAILURE  # noqa: F401
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgoldilocks_b200.so")
+# GOLDILOCKS_B200_LIB selects another build of the same CUDA library (kernel experiments); never a CPU library.
+LIB_PATH = os.environ.get("GOLDILOCKS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgoldilocks_b200.so")
 _lib = None
 
 

@@ -34,6 +34,7 @@ struct Ctx {
     int dev = -1, sms = 0;
     cudaStream_t stream = nullptr;
     fixed_tables *ft = nullptr;
+    niels *wide = nullptr;       // 16384-entry verification table (3 MB)
     std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
     size_t used = 0;             // bytes used in the active block
     void *slot_scratch = nullptr;
@@ -121,6 +122,16 @@ bool ctx_init(Ctx &c, int dev) {
     CU(cudaMalloc(&c.ft, sizeof(fixed_tables)));
     LaneBuildTables f = {c.ft};
     if (!launch(c, f, COMB_N + 2, c.stream)) return false;
+    CU(cudaMalloc(&c.wide, sizeof(niels) * WIDE_ENTRIES));
+    {
+        pniels *tmp = nullptr; gf *pre = nullptr;
+        CU(cudaMalloc(&tmp, sizeof(pniels) * WIDE_ENTRIES));
+        CU(cudaMalloc(&pre, sizeof(gf) * WIDE_ENTRIES));
+        LaneBuildWide fw = {c.wide, tmp, pre, c.ft};
+        if (!launch(c, fw, WIDE_LANES, c.stream)) return false;
+        CU(cudaStreamSynchronize(c.stream));
+        cudaFree(tmp); cudaFree(pre);
+    }
     CU(cudaStreamSynchronize(c.stream));
     c.failed = false;
     c.ready = true;
@@ -284,7 +295,7 @@ goldilocks_error_t goldilocks_b200_export_wnaf_table(uint8_t out[6144]) {
     Call k;
     if (!k.ok) return k.finish();
     std::vector<niels> h(WNAF_FIXED_ENTRIES);
-    k.fetch(h.data(), k.c->ft->wnaf, WNAF_FIXED_ENTRIES);
+    k.fetch(h.data(), k.c->wide, WNAF_FIXED_ENTRIES); /* first 32 entries = 1B..63B, the reference's wNAF table */
     goldilocks_error_t r = k.finish();
     if (r != GOLDILOCKS_SUCCESS) return r;
     uint64_t *o = (uint64_t *)out;
@@ -456,7 +467,7 @@ goldilocks_error_t goldilocks_448_point_double_scalarmul_batch(hpt *out, const h
 goldilocks_error_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *out, const hsc *scalar1, const hpt *base2, const hsc *scalar2, size_t n) {
     Call k;
     int grid = k.grid_for<LaneBaseDoubleScalarmul>();
-    LaneBaseDoubleScalarmul f = {k.out<abi_pt>(n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n), k.ok ? k.c->ft : nullptr,
+    LaneBaseDoubleScalarmul f = {k.out<abi_pt>(n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n), k.ok ? k.c->wide : nullptr,
                                  k.slots((size_t)grid * BLOCK, WINDOW_NTABLE)};
     k.run_slot(f, n, grid);
     k.fetch(P(out), f.out, n);
@@ -566,7 +577,7 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
     if (!launch(c, f1, 2 * n, s)) return false;
     LaneEdVerifyScalars f2 = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len};
     if (!launch(c, f2, n, s)) return false;
-    LaneEdVerifyFinish f3 = {status, pts, ok, chal, resp, c.ft, slots};
+    LaneEdVerifyFinish f3 = {status, pts, ok, chal, resp, c.wide, slots};
     return launch_slot(c, f3, n, grid, s);
 }
 goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,

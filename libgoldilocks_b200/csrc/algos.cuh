@@ -18,6 +18,12 @@
 #define WNAF_FIXED_ENTRIES 32                 /* goldilocks.c:29: odd multiples 1B..63B */
 #define WINDOW_BITS 5                         /* goldilocks.c:28 */
 #define WINDOW_NTABLE 16
+/* Verification-only fixed-base table: odd multiples 1B,3B,...,(2^15-1)B as canonical affine niels
+ * (16384 x 192 B = 3 MB, L2 resident).  Public indices only -- never used on a secret scalar. */
+#define WIDE_BITS 15
+#define WIDE_ENTRIES (1 << (WIDE_BITS - 1))
+#define WIDE_LANES 128                         /* lanes that build the table at init */
+#define WIDE_PER_LANE (WIDE_ENTRIES / WIDE_LANES)
 
 // Device-resident fixed-base tables (built once per device by build_tables_lane()).
 struct fixed_tables {
@@ -89,12 +95,9 @@ GD void niels_lookup_ct(niels &out, const niels *row, int n, uint32_t idx) {
 #pragma unroll 1
     for (int e = 0; e < n; e++) {
         const gmask_t m = (gmask_t)(((uint64_t)((uint32_t)e ^ idx) - 1) >> 32); /* all-ones iff e == idx */
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            out.a.v[i] |= row[e].a.v[i] & m;
-            out.b.v[i] |= row[e].b.v[i] & m;
-            out.c.v[i] |= row[e].c.v[i] & m;
-        }
+        gf_ld_or_masked<true>(out.a, &row[e].a, m);   /* fixed-base table: read-only */
+        gf_ld_or_masked<true>(out.b, &row[e].b, m);
+        gf_ld_or_masked<true>(out.c, &row[e].c, m);
     }
 }
 GD void pniels_lookup_ct(pniels &out, const pniels *row, int n, uint32_t idx) {
@@ -102,13 +105,10 @@ GD void pniels_lookup_ct(pniels &out, const pniels *row, int n, uint32_t idx) {
 #pragma unroll 1
     for (int e = 0; e < n; e++) {
         const gmask_t m = (gmask_t)(((uint64_t)((uint32_t)e ^ idx) - 1) >> 32);
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            out.n.a.v[i] |= row[e].n.a.v[i] & m;
-            out.n.b.v[i] |= row[e].n.b.v[i] & m;
-            out.n.c.v[i] |= row[e].n.c.v[i] & m;
-            out.z.v[i] |= row[e].z.v[i] & m;
-        }
+        gf_ld_or_masked<false>(out.n.a, &row[e].n.a, m); /* this lane's own table, written by this kernel */
+        gf_ld_or_masked<false>(out.n.b, &row[e].n.b, m);
+        gf_ld_or_masked<false>(out.n.c, &row[e].n.c, m);
+        gf_ld_or_masked<false>(out.z, &row[e].z, m);
     }
 }
 
@@ -246,53 +246,53 @@ GD void window_double_scalarmul(pt &a, const pt &b, const sc &scalarb, const pt 
 // additions depend on the scalars; executed per lane that diverges on almost every bit.  Only the
 // resulting group element is observable (the projective representative is not part of the
 // contract), so the GPU uses a warp-uniform schedule instead: both scalars are
-// recoded into 90 signed odd 5-bit digits (the same recoding as the constant-time paths) and every
-// lane does 5 doublings + one variable-base add (direct index into its own 16-pniels table) + one
-// fixed-base add (direct index into the first 16 entries of the shared wNAF table, which are
-// exactly 1B,3B,...,31B) per window.  Indices are public, so lookups are plain loads.
+// recoded with the constant-time paths' signed-digit recoding: scalar2 into 90 odd 5-bit digits,
+// scalar1 into 30 odd 15-bit digits.  Every lane does, per 5-bit window, 5 doublings + one
+// variable-base add (direct index into its own 16-pniels table) and, on every third window, one
+// fixed-base add (direct index into the shared 16384-entry table of odd multiples of B): 445
+// doublings + 90 + 30 additions, against the reference's expected 444 + 75 + 56.  Indices are
+// public, so lookups are plain loads.
 // ---------------------------------------------------------------------------------------------
 GD void load_pniels(pniels &o, const pniels *src) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        o.n.a.v[i] = src->n.a.v[i]; o.n.b.v[i] = src->n.b.v[i];
-        o.n.c.v[i] = src->n.c.v[i]; o.z.v[i] = src->z.v[i];
-    }
+    gf_ld<false>(o.n.a, &src->n.a); gf_ld<false>(o.n.b, &src->n.b); gf_ld<false>(o.n.c, &src->n.c); gf_ld<false>(o.z, &src->z);
 }
 GD void load_niels(niels &o, const niels *src) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) { o.a.v[i] = src->a.v[i]; o.b.v[i] = src->b.v[i]; o.c.v[i] = src->c.v[i]; }
+    gf_ld<true>(o.a, &src->a); gf_ld<true>(o.b, &src->b); gf_ld<true>(o.c, &src->c);
 }
 GD void base_double_scalarmul_uniform(pt &combo, const sc &scalar1, const pt &base2, const sc &scalar2,
-                                      const niels *wnaf_base, pniels *multiples) {
+                                      const niels *wide_base, pniels *multiples) {
     sc s1x, s2x;
-    sc_recode_signed(s1x, scalar1);
+    sc_recode_signed(s1x, scalar1);   /* both recodings cover 450 = 90 x 5 = 30 x 15 bits */
     sc_recode_signed(s2x, scalar2);
     prepare_fixed_window(multiples, base2, WINDOW_NTABLE);
     pt tmp;
     pniels pn;
     niels ni;
-    bool first = true;
 #pragma unroll 1
-    for (int i = GOLDILOCKS_SCALAR_BITS_ - ((GOLDILOCKS_SCALAR_BITS_ - 1) % WINDOW_BITS) - 1; i >= 0; i -= WINDOW_BITS) {
-        uint32_t bits1 = sc_window5(s1x, i), bits2 = sc_window5(s2x, i);
-        const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WINDOW_BITS - 1)) - 1);
+    for (int k = 89; k >= 0; k--) {
+        const int i = k * WINDOW_BITS;
+        const bool fixed_here = (k % 3) == 0;           /* 15-bit fixed-base digit starts at this bit */
+        uint32_t bits2 = sc_window5(s2x, i);
         const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
-        bits1 ^= inv1;
         bits2 ^= inv2;
         load_pniels(pn, multiples + (bits2 & (WINDOW_NTABLE - 1)));
         niels_cond_neg(pn.n, inv2);
-        if (first) {
+        if (k == 89) {
             pniels_to_pt(tmp, pn);
-            first = false;
         } else {
 #pragma unroll 1
             for (int j = 0; j < WINDOW_BITS - 1; j++) pt_double(tmp, tmp, true);
             pt_double(tmp, tmp, false);
-            pt_addsub_pniels<false>(tmp, pn, false);
+            pt_addsub_pniels<false>(tmp, pn, !fixed_here && k != 0);
         }
-        load_niels(ni, wnaf_base + (bits1 & (WINDOW_NTABLE - 1)));
-        niels_cond_neg(ni, inv1);
-        pt_addsub_niels<false>(tmp, ni, i != 0);
+        if (fixed_here) {
+            uint32_t bits1 = sc_bits(s1x, i, WIDE_BITS);
+            const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
+            bits1 ^= inv1;
+            load_niels(ni, wide_base + (bits1 & (WIDE_ENTRIES - 1)));
+            niels_cond_neg(ni, inv1);
+            pt_addsub_niels<false>(tmp, ni, k != 0);
+        }
     }
     /* Reference quirk kept for bit-exact parity: when scalar2 == 0 its wNAF is empty and
      * goldilocks.c:1281-1284 returns the identity WITHOUT adding scalar1*B. */
@@ -381,6 +381,37 @@ GD void build_wnaf_base(niels *out32, const pt &base) {
         gf_copy(zs[i], pn.z);
     }
     normalize_niels(out32, zs, zis, WNAF_FIXED_ENTRIES);
+}
+// One lane's share of the verification table: entries [per*lane, per*(lane+1)) = odd multiples
+// (2e+1)B.  `tmp`/`pre` are global scratch (one pniels / one gf per entry).  Start point from the
+// comb table, then repeated +2B; normalised with one inversion per lane (Montgomery's trick).
+GD void build_wide_lane(niels *out, pniels *tmp, gf *pre, const niels *comb, int lane) {
+    const uint32_t bw[14] = GOLD_CONST_BASE_WORDS;
+    pt base, twob, p;
+    (void)pt_decode(base, bw, 0);
+    pt_double(twob, base, false);
+    sc start;
+    sc_set_zero(start);
+    start.w[0] = 2u * (uint32_t)(WIDE_PER_LANE * lane) + 1u;
+    comb_scalarmul(p, comb, start);
+    const int e0 = WIDE_PER_LANE * lane;
+    for (int i = 0; i < WIDE_PER_LANE; i++) {
+        if (i) pt_add(p, p, twob);
+        pt_to_pniels(tmp[e0 + i], p);
+        if (i == 0) gf_copy(pre[e0], tmp[e0].z);
+        else gf_mul(pre[e0 + i], pre[e0 + i - 1], tmp[e0 + i].z);
+    }
+    gf inv, zi;
+    gf_invert(inv, pre[e0 + WIDE_PER_LANE - 1]);
+    for (int i = WIDE_PER_LANE - 1; i >= 0; i--) {
+        if (i) { gf_mul(zi, inv, pre[e0 + i - 1]); gf_mul(inv, inv, tmp[e0 + i].z); }
+        else gf_copy(zi, inv);
+        niels n;
+        gf_mul(n.a, tmp[e0 + i].n.a, zi); gf_strong_reduce(n.a);
+        gf_mul(n.b, tmp[e0 + i].n.b, zi); gf_strong_reduce(n.b);
+        gf_mul(n.c, tmp[e0 + i].n.c, zi); gf_strong_reduce(n.c);
+        gf_copy(out[e0 + i].a, n.a); gf_copy(out[e0 + i].b, n.b); gf_copy(out[e0 + i].c, n.c);
+    }
 }
 GD void build_tables_lane(fixed_tables *ft, int lane) {
     const uint32_t bw[14] = GOLD_CONST_BASE_WORDS;

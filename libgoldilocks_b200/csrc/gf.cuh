@@ -48,7 +48,7 @@
 #define GF_ASSERT_TIGHT(x) do { } while (0)
 #endif
 
-struct gf { uint32_t v[GF_NLIMBS]; };
+struct alignas(16) gf { uint32_t v[GF_NLIMBS]; }; /* 16-byte aligned: table rows move as 128-bit loads */
 
 typedef uint32_t gmask_t; /* all-ones / zero, like the reference's mask_t (word.h:263-278) */
 
@@ -63,6 +63,31 @@ GD void gf_set_ui(gf &a, uint32_t w) { /* w < 2^28 */
 GD void gf_copy(gf &o, const gf &a) {
 #pragma unroll
     for (int i = 0; i < 16; i++) o.v[i] = a.v[i];
+}
+
+// Whole-element load from a 16-byte aligned table row: four 128-bit loads on the device.
+// RO = true only for tables that are never written while the kernel runs (fixed-base tables): it
+// takes the non-coherent path (LDG.CONSTANT).  Per-lane tables built by the same kernel use RO = false.
+template <bool RO>
+GD void gf_ld(gf &o, const gf *src) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint4 x = RO ? __ldg(p + q) : p[q];
+        o.v[4 * q] = x.x; o.v[4 * q + 1] = x.y; o.v[4 * q + 2] = x.z; o.v[4 * q + 3] = x.w;
+    }
+#else
+    for (int i = 0; i < 16; i++) o.v[i] = src->v[i];
+#endif
+}
+// o |= row & mask (masked full-row scan step of the constant-time lookups)
+template <bool RO>
+GD void gf_ld_or_masked(gf &o, const gf *src, uint32_t m) {
+    gf t;
+    gf_ld<RO>(t, src);
+#pragma unroll
+    for (int i = 0; i < 16; i++) o.v[i] |= t.v[i] & m;
 }
 
 // Carry-propagate once: TIGHT output for any input with limbs < 2^32.

@@ -1,3 +1,4 @@
 // k_tables.cu -- explicit kernel instantiations (see launch.cuh)
 #include "launch.cuh"
 INSTANTIATE_PLAIN(LaneBuildTables)
+INSTANTIATE_PLAIN(LaneBuildWide)

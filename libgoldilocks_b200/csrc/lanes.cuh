@@ -216,12 +216,12 @@ struct LaneDoubleScalarmul { /* goldilocks_448_point_double_scalarmul */
     }
 };
 struct LaneBaseDoubleScalarmul { /* goldilocks_448_base_double_scalarmul_non_secret */
-    abi_pt *out; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; const fixed_tables *ft; pniels *scratch;
+    abi_pt *out; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; const niels *wide; pniels *scratch;
     GDM void operator()(size_t i, size_t slot) const {
         sc s1, s2; pt p, b2;
         sc_from_abi(s1, scalar1 + i); sc_from_abi(s2, scalar2 + i);
         pt_from_abi(b2, base2 + i);
-        base_double_scalarmul_uniform(p, s1, b2, s2, ft->wnaf, scratch + WINDOW_NTABLE * slot);
+        base_double_scalarmul_uniform(p, s1, b2, s2, wide, scratch + WINDOW_NTABLE * slot);
         pt_to_abi(out + i, p);
     }
 };
@@ -452,18 +452,22 @@ struct LaneEdVerifyScalars {
     }
 };
 struct LaneEdVerifyFinish {
-    int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const fixed_tables *ft; pniels *scratch;
+    int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; pniels *scratch;
     GDM void operator()(size_t i, size_t slot) const {
         sc c, r; pt a, rp, combo;
         sc_from_abi(c, challenge + i);
         sc_from_abi(r, response + i);
         pt_from_abi(a, pts + 2 * i);
-        base_double_scalarmul_uniform(combo, r, a, c, ft->wnaf, scratch + WINDOW_NTABLE * slot);
+        base_double_scalarmul_uniform(combo, r, a, c, wide, scratch + WINDOW_NTABLE * slot);
         pt_from_abi(rp, pts + 2 * i + 1);
         gmask_t good = pt_eq(combo, rp);
         good &= (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1];
         status[i] = ST_OK(good);
     }
+};
+struct LaneBuildWide { /* verification table, WIDE_LANES lanes */
+    niels *wide; pniels *tmp; gf *pre; const fixed_tables *ft;
+    GDM void operator()(size_t lane) const { build_wide_lane(wide, tmp, pre, ft->comb, (int)lane); }
 };
 struct LaneBuildTables {
     fixed_tables *ft;

@@ -49,7 +49,7 @@ cudaError_t lanes_slot_occupancy(int *occ) {
     X(LaneSc<SCOP_ADD>) X(LaneSc<SCOP_SUB>) X(LaneSc<SCOP_MUL>) X(LaneSc<SCOP_HALVE>)               \
     X(LaneScDecodeLong) X(LaneShake256)                                                             \
     X(LaneEdDerivePk) X(LaneEdSecretScalar) X(LaneEdSignExpand) X(LaneEdSignNonce) X(LaneEdSignR) X(LaneEdSignFinish)   \
-    X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneBuildTables)
+    X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneBuildTables) X(LaneBuildWide)
 #define LANES_SLOT(X)                                                                               \
     X(LaneScalarmul) X(LaneDoubleScalarmul) X(LaneBaseDoubleScalarmul) X(LaneEdVerifyFinish)
 

@@ -178,7 +178,7 @@ GD uint32_t sc_bit(const sc &a, int pos) {
     for (int i = 0; i < SC_WORDS; i++) r |= (i == (pos >> 5)) ? a.w[i] : 0u; /* no dynamic register indexing */
     return (r >> (pos & 31)) & 1u;
 }
-// `nbits` (<= 8) bits starting at bit `pos`
+// `nbits` (<= 31) bits starting at bit `pos`
 GD uint32_t sc_bits(const sc &a, int pos, int nbits) {
     uint32_t lo = 0, hi = 0;
     const int wi = pos >> 5;

@@ -49,6 +49,16 @@ static fixed_tables *tables() {
     }
     return ft;
 }
+static niels *wide_table() {
+    static niels *w = nullptr;
+    if (!w) {
+        w = (niels *)aligned_alloc(64, sizeof(niels) * WIDE_ENTRIES);
+        std::vector<pniels> tmp(WIDE_ENTRIES);
+        std::vector<gf> pre(WIDE_ENTRIES);
+        for (int lane = 0; lane < WIDE_LANES; lane++) build_wide_lane(w, tmp.data(), pre.data(), tables()->comb, lane);
+    }
+    return w;
+}
 static void export_niels(uint8_t *out, const niels *t, int n) {
     uint64_t *o = (uint64_t *)out;
     for (int e = 0; e < n; e++) {
@@ -58,7 +68,7 @@ static void export_niels(uint8_t *out, const niels *t, int n) {
     }
 }
 EXPORT int32_t goldilocks_b200_export_comb_table(uint8_t *out) { export_niels(out, tables()->comb, COMB_ENTRIES); return -1; }
-EXPORT int32_t goldilocks_b200_export_wnaf_table(uint8_t *out) { export_niels(out, tables()->wnaf, WNAF_FIXED_ENTRIES); return -1; }
+EXPORT int32_t goldilocks_b200_export_wnaf_table(uint8_t *out) { export_niels(out, wide_table(), WNAF_FIXED_ENTRIES); return -1; }
 EXPORT int32_t goldilocks_b200_init(void) { tables(); return -1; }
 
 typedef abi_pt hpt;
@@ -92,7 +102,7 @@ EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint
 EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(hpt *o, const void *, const hsc *s, size_t n) { LaneComb f = {o, s, tables()}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_scalarmul_batch(hpt *o, const hpt *b, const hsc *s, size_t n) { LaneScalarmul f = {o, b, s, slots(WINDOW_NTABLE)}; run_slot(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_double_scalarmul_batch(hpt *o, const hpt *b1, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { LaneDoubleScalarmul f = {o, b1, s1, b2, s2, slots(2 * WINDOW_NTABLE)}; run_slot(f, n); return -1; }
-EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *o, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { LaneBaseDoubleScalarmul f = {o, s1, b2, s2, tables(), slots(WINDOW_NTABLE)}; run_slot(f, n); return -1; }
+EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *o, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { LaneBaseDoubleScalarmul f = {o, s1, b2, s2, wide_table(), slots(WINDOW_NTABLE)}; run_slot(f, n); return -1; }
 
 EXPORT int32_t goldilocks_448_scalar_add_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_ADD> f = {o, a, b}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_scalar_sub_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_SUB> f = {o, a, b}; run(f, n); return -1; }
@@ -127,7 +137,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     run(f1, 2 * n);
     LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len};
     run(f2, n);
-    LaneEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), tables(), slots(WINDOW_NTABLE)};
+    LaneEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), slots(WINDOW_NTABLE)};
     run_slot(f3, n);
     return -1;
 }

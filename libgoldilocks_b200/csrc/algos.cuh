@@ -272,19 +272,18 @@ GD void base_double_scalarmul_uniform(pt &combo, const sc &scalar1, const pt &ba
     for (int k = 89; k >= 0; k--) {
         const int i = k * WINDOW_BITS;
         const bool fixed_here = (k % 3) == 0;           /* 15-bit fixed-base digit starts at this bit */
+        if (k != 89) { /* doublings first: the table row is only live across the addition */
+#pragma unroll 1
+            for (int j = 0; j < WINDOW_BITS - 1; j++) pt_double(tmp, tmp, true);
+            pt_double(tmp, tmp, false);
+        }
         uint32_t bits2 = sc_window5(s2x, i);
         const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
         bits2 ^= inv2;
         load_pniels(pn, multiples + (bits2 & (WINDOW_NTABLE - 1)));
         niels_cond_neg(pn.n, inv2);
-        if (k == 89) {
-            pniels_to_pt(tmp, pn);
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < WINDOW_BITS - 1; j++) pt_double(tmp, tmp, true);
-            pt_double(tmp, tmp, false);
-            pt_addsub_pniels<false>(tmp, pn, !fixed_here && k != 0);
-        }
+        if (k == 89) pniels_to_pt(tmp, pn);
+        else pt_addsub_pniels<false>(tmp, pn, !fixed_here && k != 0);
         if (fixed_here) {
             uint32_t bits1 = sc_bits(s1x, i, WIDE_BITS);
             const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);

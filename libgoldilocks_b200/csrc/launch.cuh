@@ -9,8 +9,15 @@
 
 #define BLOCK 128
 
+// Resident blocks per SM the register allocator is asked to allow (default: whatever fits).
+template <class F> struct lane_min_blocks { static constexpr int value = 1; };
+// Measured on B200 at 2^20 (tools/opbench.py): comb 34.5 -> 38.5 Mops/s with 3 blocks (168 regs, no spills);
+// X448 gains 1% at 3 blocks but spills, so it stays at 2.
+template <> struct lane_min_blocks<LaneComb> { static constexpr int value = 3; };
+template <> struct lane_min_blocks<LaneX448DerivePk> { static constexpr int value = 3; };
+
 template <class F>
-__global__ void __launch_bounds__(BLOCK) k_lanes(F f, size_t n) {
+__global__ void __launch_bounds__(BLOCK, lane_min_blocks<F>::value) k_lanes(F f, size_t n) {
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i < n) f(i);
 }

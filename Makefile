@@ -7,11 +7,11 @@ CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden $(EXTRA_NVCCFLAGS)
 CSRC      := libgoldilocks_b200/csrc
-OBJDIR    := build/obj
+OBJDIR    ?= build/obj
 KERNELS   := $(wildcard $(CSRC)/k_*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(KERNELS)) $(OBJDIR)/abi.o
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/goldilocks_b200.h
-LIB       := libgoldilocks_b200/libgoldilocks_b200.so
+LIB       ?= libgoldilocks_b200/libgoldilocks_b200.so
 
 .PHONY: all lib hostsim oracle clean
 all: lib hostsim oracle

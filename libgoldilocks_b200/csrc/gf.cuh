@@ -48,6 +48,20 @@
 #define GF_ASSERT_TIGHT(x) do { } while (0)
 #endif
 
+// A zero the compiler cannot see through (constant bank, never written).  Adding it as a third
+// operand keeps an addition a three-input IADD3 on the ALU pipe: ptxas otherwise turns about half of
+// the two-input adds and register moves around the multiplier into IMAD.IADD / IMAD.MOV, which
+// compete with IMAD.WIDE for the multiply pipe (profiles/r01_verify_finish_calls.txt).
+#if defined(__CUDACC__)
+static __constant__ uint32_t gf_opaque_zero;
+#endif
+#if defined(__CUDA_ARCH__)
+#define GF_Z gf_opaque_zero
+#else
+#define GF_Z 0u
+#endif
+#define GF_ZS GF_Z /* measured: +2% on verify / X448 / comb (tools/expbench.sh, B200) */
+
 struct alignas(16) gf { uint32_t v[GF_NLIMBS]; }; /* 16-byte aligned: table rows move as 128-bit loads */
 
 typedef uint32_t gmask_t; /* all-ones / zero, like the reference's mask_t (word.h:263-278) */
@@ -173,9 +187,9 @@ GD void gf_mul_body(gf &c, const gf &a, const gf &b) {
     int32_t nb[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        aa[i] = a.v[i] + a.v[i + 8];
-        bb[i] = b.v[i] + b.v[i + 8];
-        nb[i] = -(int32_t)b.v[i];
+        aa[i] = a.v[i] + a.v[i + 8] + GF_ZS;
+        bb[i] = b.v[i] + b.v[i + 8] + GF_ZS;
+        nb[i] = (int32_t)(GF_ZS - b.v[i]);
     }
     uint64_t acc0 = 0, acc1 = 0;
     gf r;
@@ -236,11 +250,11 @@ GD void gf_sqr_body(gf &c, const gf &a) {
     for (int i = 0; i < 8; i++) {
         lo[i] = a.v[i];
         hi[i] = a.v[i + 8];
-        aa[i] = lo[i] + hi[i];
-        lo2[i] = lo[i] << 1;
-        hi2[i] = hi[i] << 1;
-        aa2[i] = aa[i] << 1;
-        nlo[i] = -(int32_t)lo[i];
+        aa[i] = lo[i] + hi[i] + GF_ZS;
+        lo2[i] = lo[i] + lo[i] + GF_ZS;
+        hi2[i] = hi[i] + hi[i] + GF_ZS;
+        aa2[i] = aa[i] + aa[i] + GF_ZS;
+        nlo[i] = (int32_t)(GF_ZS - lo[i]);
     }
     uint64_t acc0 = 0, acc1 = 0;
     gf r;

@@ -12,7 +12,7 @@ no collective on the data path; torch.distributed is used only for the barrier a
 `value`  : device-resident -- inputs already in HBM, CUDA events on the launching stream.
 `e2e`    : the same batch through the host-pointer C-ABI call with pinned host buffers; H2D + kernels +
            D2H inside the timed region.
-`roofline`: the dominant kernel (LaneEdVerifyFinish = double scalar multiplication + point_eq), its
+`roofline`: the dominant kernel (SlotEdVerifyFinish = double scalar multiplication + point_eq), its
            launches timed with CUDA events inside the timed region; algorithmic MAC32 per signature from
            SURVEY.md 8(d); peak = measured IMAD.WIDE.U32 rate (profiles/r01_imad_peak.json).
 `cpu_baseline`: the unmodified reference (oracle/_ref, arch_x86_64) on all host cores over a bounded sample.
@@ -249,10 +249,10 @@ def run_ours(args):
         nm = names.raw[64 * k:64 * k + 64].split(b"\0")[0].decode()
         per_kernel.setdefault(nm, []).append(ms[k])
     kavg = {k: float(np.mean(v)) for k, v in per_kernel.items()}
-    t_finish = kavg.get("LaneEdVerifyFinish", 0.0) / 1e3
+    t_finish = kavg.get("SlotEdVerifyFinish", 0.0) / 1e3
     peak, peak_how = imad_peak()
     achieved = n * MAC32["verify_finish"] / t_finish / 1e9 if t_finish > 0 else 0.0
-    roofline = {"bound": "imad", "kernel": "k_lanes_slot<LaneEdVerifyFinish>", "achieved": achieved, "peak": peak, "unit": "GMAC32/s",
+    roofline = {"bound": "imad", "kernel": "k_slots_persist<SlotEdVerifyFinish>", "achieved": achieved, "peak": peak, "unit": "GMAC32/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_how,
                 "algorithmic_mac32_per_signature": MAC32["verify_finish"], "kernel_ms": kavg,
                 "kernel_share_of_step": t_finish / (e0.elapsed_time(e1) / 1e3 / K) if t_finish > 0 else None,

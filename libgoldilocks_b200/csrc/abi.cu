@@ -18,6 +18,8 @@
 // kernels live in k_*.cu
 LANES_PLAIN(DECLARE_PLAIN)
 LANES_SLOT(DECLARE_SLOT)
+LANES_SM(DECLARE_SM)
+LANES_SMP(DECLARE_SMP)
 
 // ------------------------------------------------------------------------------------------------
 // Per-device context
@@ -79,6 +81,39 @@ bool launch(Ctx &c, const F &f, size_t n, cudaStream_t s) {
     const bool prof = g_prof_on.load() != 0;
     if (prof) a = prof_begin(typeid(F).name(), s, &b);
     CU(launch_lanes<F>(f, n, s));
+    if (prof) prof_end(typeid(F).name(), s, a, b);
+    return true;
+}
+template <class F>
+bool launch_slots(Ctx &c, const F &f, size_t n, cudaStream_t s) { /* shared-memory slot machine (slots.cuh) */
+    if (n == 0) return true;
+    g_launches++;
+    cudaEvent_t a = nullptr, b = nullptr;
+    const bool prof = g_prof_on.load() != 0;
+    if (prof) a = prof_begin(typeid(F).name(), s, &b);
+    CU(launch_sm<F>(f, n, s));
+    if (prof) prof_end(typeid(F).name(), s, a, b);
+    return true;
+}
+// persistent slot-machine kernels: grid = SMs x resident blocks, so every thread owns one scratch area
+template <class F>
+bool smp_grid(Ctx &c, int *grid) {
+    int occ = 0;
+    CU(sm_configure<F>(&occ)); /* also sets the dynamic shared-memory attributes on this device */
+    if (occ < 1) { g_err = "slot-machine kernel does not fit on an SM"; return false; }
+    *grid = c.sms * occ;
+    return true;
+}
+template <class F>
+bool launch_smp(Ctx &c, const F &f, size_t n, int grid, cudaStream_t s) {
+    if (n == 0) return true;
+    size_t need_blocks = (n + SLOT_BLOCK - 1) / SLOT_BLOCK;
+    if ((size_t)grid > need_blocks) grid = (int)need_blocks;
+    g_launches++;
+    cudaEvent_t a = nullptr, b = nullptr;
+    const bool prof = g_prof_on.load() != 0;
+    if (prof) a = prof_begin(typeid(F).name(), s, &b);
+    CU(launch_sm_persist<F>(f, n, grid, s));
     if (prof) prof_end(typeid(F).name(), s, a, b);
     return true;
 }
@@ -197,7 +232,10 @@ struct Call {
         return (pniels *)c->slot_scratch;
     }
     template <class F> void run(const F &f, size_t n) { if (ok) ok = launch(*c, f, n, c->stream); }
+    template <class F> void run_sm(const F &f, size_t n) { if (ok) ok = launch_slots(*c, f, n, c->stream); }
     template <class F> int grid_for() { int g = 1; if (ok) ok = slot_grid<F>(*c, &g); return g; }
+    template <class F> int smp_grid_for() { int g = 1; if (ok) ok = smp_grid<F>(*c, &g); return g; }
+    template <class F> void run_smp(const F &f, size_t n, int grid) { if (ok) ok = launch_smp(*c, f, n, grid, c->stream); }
     template <class F> void run_slot(const F &f, size_t n, int grid) { if (ok) ok = launch_slot(*c, f, n, grid, c->stream); }
     goldilocks_error_t finish() {
         if (ok) {
@@ -466,10 +504,10 @@ goldilocks_error_t goldilocks_448_point_double_scalarmul_batch(hpt *out, const h
 }
 goldilocks_error_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *out, const hsc *scalar1, const hpt *base2, const hsc *scalar2, size_t n) {
     Call k;
-    int grid = k.grid_for<LaneBaseDoubleScalarmul>();
-    LaneBaseDoubleScalarmul f = {k.out<abi_pt>(n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n), k.ok ? k.c->wide : nullptr,
-                                 k.slots((size_t)grid * BLOCK, WINDOW_NTABLE)};
-    k.run_slot(f, n, grid);
+    int grid = k.smp_grid_for<SlotBaseDoubleScalarmul>();
+    SlotBaseDoubleScalarmul f = {k.out<abi_pt>(n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n), k.ok ? k.c->wide : nullptr,
+                                 k.slots((size_t)grid * SLOT_BLOCK, BDSM_TABLE)};
+    k.run_smp(f, n, grid);
     k.fetch(P(out), f.out, n);
     return k.finish();
 }
@@ -504,8 +542,8 @@ goldilocks_error_t goldilocks_448_scalar_decode_long_batch(hsc *out, const uint8
 // ---- CFRG ----------------------------------------------------------------------------------------------------
 goldilocks_error_t goldilocks_x448_batch(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n) {
     Call k;
-    LaneX448 f = {k.out<uint8_t>(56 * n), k.out<int32_t>(n), k.in(base, 56 * n), k.in(scalar, 56 * n)};
-    k.run(f, n);
+    SlotX448 f = {k.out<uint8_t>(56 * n), k.out<int32_t>(n), k.in(base, 56 * n), k.in(scalar, 56 * n)};
+    k.run_sm(f, n);
     k.fetch(out, f.out, 56 * n);
     k.fetch((int32_t *)status, f.status, n);
     return k.finish();
@@ -577,8 +615,8 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
     if (!launch(c, f1, 2 * n, s)) return false;
     LaneEdVerifyScalars f2 = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len};
     if (!launch(c, f2, n, s)) return false;
-    LaneEdVerifyFinish f3 = {status, pts, ok, chal, resp, c.wide, slots};
-    return launch_slot(c, f3, n, grid, s);
+    SlotEdVerifyFinish f3 = {status, pts, ok, chal, resp, c.wide, slots};
+    return launch_smp(c, f3, n, grid, s);
 }
 goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                  uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n) {
@@ -590,8 +628,8 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
     const uint8_t *dsig = k.in(signature, 114 * n), *dpk = k.in(pubkey, 57 * n);
     int32_t *dst = k.out<int32_t>(n);
     void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(n));
-    int grid = k.grid_for<LaneEdVerifyFinish>();
-    pniels *slots = k.slots((size_t)grid * BLOCK, WINDOW_NTABLE);
+    int grid = k.smp_grid_for<SlotEdVerifyFinish>();
+    pniels *slots = k.slots((size_t)grid * SLOT_BLOCK, BDSM_TABLE);
     if (k.ok) k.ok = verify_dev(*k.c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, scratch, slots, grid, k.c->stream);
     k.fetch((int32_t *)status, dst, n);
     return k.finish();
@@ -604,8 +642,8 @@ goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status,
     if (!c) return GOLDILOCKS_FAILURE;
     std::lock_guard<std::mutex> g(c->mu); /* the per-thread table slots are shared per device */
     int grid = 1;
-    if (!slot_grid<LaneEdVerifyFinish>(*c, &grid)) return GOLDILOCKS_FAILURE;
-    size_t bytes = (size_t)grid * BLOCK * WINDOW_NTABLE * sizeof(pniels);
+    if (!smp_grid<SlotEdVerifyFinish>(*c, &grid)) return GOLDILOCKS_FAILURE;
+    size_t bytes = (size_t)grid * SLOT_BLOCK * BDSM_TABLE * sizeof(pniels);
     if (bytes > c->slot_cap) {
         if (c->slot_scratch) cudaFree(c->slot_scratch);
         c->slot_scratch = nullptr; c->slot_cap = 0;
@@ -618,8 +656,8 @@ goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status,
 goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream) {
     Ctx *c = dev_ctx();
     if (!c) return GOLDILOCKS_FAILURE;
-    LaneX448 f = {out, (int32_t *)status, base, scalar};
-    return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+    SlotX448 f = {out, (int32_t *)status, base, scalar};
+    return launch_slots(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
 }
 goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch_dev(hpt *out, const hsc *scalar, size_t n, void *stream) {
     Ctx *c = dev_ctx();

@@ -120,7 +120,7 @@ GD void gf_weak_reduce(gf &a) {
 // o = a + b, no reduction: TIGHT + TIGHT -> LOOSE.  (reference gf_add_nr / gf_add_RAW)
 GD void gf_add_nr(gf &o, const gf &a, const gf &b) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) o.v[i] = a.v[i] + b.v[i];
+    for (int i = 0; i < 16; i++) o.v[i] = a.v[i] + b.v[i] + GF_ZS; /* three-input: stays an IADD3 (ALU pipe) */
 }
 // o = a + b, TIGHT output for any LOOSE inputs.  (reference f_generic.c:114-117 gf_add)
 GD void gf_add(gf &o, const gf &a, const gf &b) {
@@ -202,8 +202,6 @@ GD void gf_mul_body(gf &c, const gf &a, const gf &b) {
             acc1 += (uint64_t)aa[j - i] * bb[i];            /* PM[j]   */
             acc0 += (uint64_t)a.v[8 + j - i] * b.v[8 + i];  /* P1[j]   */
         }
-        acc1 -= s;
-        acc0 += s;
         uint64_t t = 0; /* PM[j+8] */
 #pragma unroll
         for (int i = j + 1; i < 8; i++) {
@@ -211,8 +209,10 @@ GD void gf_mul_body(gf &c, const gf &a, const gf &b) {
             t += (uint64_t)aa[8 + j - i] * bb[i];
             acc1 += (uint64_t)a.v[16 + j - i] * b.v[8 + i]; /* P1[j+8] */
         }
-        acc1 += t;
-        acc0 += t;
+        /* all four 64-bit combinations together, after the products: ptxas then emits three-input
+         * IADD3 / IADD3.X pairs on the ALU pipe instead of IMAD.X on the multiply pipe */
+        acc0 = acc0 + s + t;
+        acc1 = acc1 + t - s;
         r.v[j] = (uint32_t)acc0 & GF_MASK;
         r.v[j + 8] = (uint32_t)acc1 & GF_MASK;
         acc0 >>= 28;
@@ -264,16 +264,14 @@ GD void gf_sqr_body(gf &c, const gf &a) {
         GF_SQR_COL(s, lo, lo2, j);        /* P0[j] */
         GF_SQR_COL(acc1, aa, aa2, j);     /* PM[j] */
         GF_SQR_COL(acc0, hi, hi2, j);     /* P1[j] */
-        acc1 -= s;
-        acc0 += s;
+        uint64_t t = 0;
         if (j < 7) {
-            uint64_t t = 0;
             GF_SQR_COL(t, aa, aa2, j + 8);            /* PM[j+8] */
             GF_SQR_COL_NEG(acc0, nlo, lo2, lo, j + 8); /* -P0[j+8] */
             GF_SQR_COL(acc1, hi, hi2, j + 8);         /* P1[j+8] */
-            acc1 += t;
-            acc0 += t;
         }
+        acc0 = acc0 + s + t;
+        acc1 = acc1 + t - s;
         r.v[j] = (uint32_t)acc0 & GF_MASK;
         r.v[j + 8] = (uint32_t)acc1 & GF_MASK;
         acc0 >>= 28;

@@ -1,3 +1,3 @@
 // k_bdsm.cu -- explicit kernel instantiations (see launch.cuh)
 #include "launch.cuh"
-INSTANTIATE_SLOT(LaneBaseDoubleScalarmul)
+INSTANTIATE_SMP(SlotBaseDoubleScalarmul)

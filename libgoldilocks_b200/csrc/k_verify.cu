@@ -2,4 +2,4 @@
 #include "launch.cuh"
 INSTANTIATE_PLAIN(LaneEdVerifyDecode)
 INSTANTIATE_PLAIN(LaneEdVerifyScalars)
-INSTANTIATE_SLOT(LaneEdVerifyFinish)
+INSTANTIATE_SMP(SlotEdVerifyFinish)

@@ -1,3 +1,3 @@
 // k_x448.cu -- explicit kernel instantiations (see launch.cuh)
 #include "launch.cuh"
-INSTANTIATE_PLAIN(LaneX448)
+INSTANTIATE_SM(SlotX448)

@@ -5,7 +5,7 @@
 // builds in parallel and a change to one kernel recompiles one file.
 #pragma once
 #include <cuda_runtime.h>
-#include "lanes.cuh"
+#include "slot_lanes.cuh"
 
 #define BLOCK 128
 
@@ -45,6 +45,46 @@ cudaError_t lanes_slot_occupancy(int *occ) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_lanes_slot<F>, BLOCK, 0);
 }
 
+// Slot-machine kernels (slots.cuh): F::NSLOTS x 64 B of dynamic shared memory per lane.
+// Resident blocks per SM: measured choice per functor (registers <= 65536 / (128 * blocks)).
+template <> struct slot_min_blocks<SlotX448> { static constexpr int value = 4; };
+template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int value = 4; };
+template <> struct slot_min_blocks<SlotBaseDoubleScalarmul> { static constexpr int value = 4; };
+template <class F>
+cudaError_t launch_sm(const F &f, size_t n, cudaStream_t s) {
+    const int smem = F::NSLOTS * 64 * SLOT_BLOCK;
+    static bool configured_dev[64]; /* per functor and device; racing first calls set the same values */
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    bool &configured = configured_dev[dev & 63];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_slots<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_slots<F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_slots<F><<<(unsigned)((n + SLOT_BLOCK - 1) / SLOT_BLOCK), SLOT_BLOCK, smem, s>>>(f, n);
+    return cudaGetLastError();
+}
+
+// Persistent variant: grid = SMs x resident blocks (sm_persist_grid), one HBM scratch area per thread.
+template <class F>
+cudaError_t sm_configure(int *blocks_per_sm) {
+    const int smem = F::NSLOTS * 64 * SLOT_BLOCK;
+    cudaError_t e = cudaFuncSetAttribute(k_slots_persist<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_slots_persist<F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_slots_persist<F>, SLOT_BLOCK, smem);
+}
+template <class F>
+cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
+    k_slots_persist<F><<<grid, SLOT_BLOCK, F::NSLOTS * 64 * SLOT_BLOCK, s>>>(f, n);
+    return cudaGetLastError();
+}
+
 #define LANES_PLAIN(X)                                                                              \
     X(LaneGf<GFOP_MUL>) X(LaneGf<GFOP_SQR>) X(LaneGf<GFOP_ADD>) X(LaneGf<GFOP_SUB>)                 \
     X(LaneGf<GFOP_MULW>) X(LaneGf<GFOP_ISR>) X(LaneGf<GFOP_INVERT>)                                 \
@@ -52,14 +92,24 @@ cudaError_t lanes_slot_occupancy(int *occ) {
     X(LanePtEq) X(LanePtValid) X(LanePtEncode) X(LanePtDecode)                                      \
     X(LaneFromHash<false>) X(LaneFromHash<true>)                                                    \
     X(LaneEncodeEddsa) X(LaneDecodeEddsa) X(LaneEncodeX448)                                         \
-    X(LaneComb) X(LaneX448DerivePk) X(LaneX448)                                                     \
+    X(LaneComb) X(LaneX448DerivePk)                                                                 \
     X(LaneSc<SCOP_ADD>) X(LaneSc<SCOP_SUB>) X(LaneSc<SCOP_MUL>) X(LaneSc<SCOP_HALVE>)               \
     X(LaneScDecodeLong) X(LaneShake256)                                                             \
     X(LaneEdDerivePk) X(LaneEdSecretScalar) X(LaneEdSignExpand) X(LaneEdSignNonce) X(LaneEdSignR) X(LaneEdSignFinish)   \
     X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneBuildTables) X(LaneBuildWide)
 #define LANES_SLOT(X)                                                                               \
-    X(LaneScalarmul) X(LaneDoubleScalarmul) X(LaneBaseDoubleScalarmul) X(LaneEdVerifyFinish)
+    X(LaneScalarmul) X(LaneDoubleScalarmul)
 
+#define LANES_SM(X) X(SlotX448)
+#define INSTANTIATE_SM(F) template cudaError_t launch_sm<F>(const F &, size_t, cudaStream_t);
+#define DECLARE_SM(F) extern INSTANTIATE_SM(F)
+#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotBaseDoubleScalarmul)
+#define INSTANTIATE_SMP(F)                                                                          \
+    template cudaError_t sm_configure<F>(int *);                                                    \
+    template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t);
+#define DECLARE_SMP(F)                                                                              \
+    extern template cudaError_t sm_configure<F>(int *);                                             \
+    extern template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t);
 #define INSTANTIATE_PLAIN(F) template cudaError_t launch_lanes<F>(const F &, size_t, cudaStream_t);
 #define INSTANTIATE_SLOT(F)                                                                         \
     template cudaError_t launch_lanes_slot<F>(const F &, size_t, int, cudaStream_t);                \

@@ -1,0 +1,193 @@
+// slot_algos.cuh -- the long-running scalar multiplications written against the slot machine
+// (slots.cuh): X448 ladder, verification double-scalar multiplication, fixed-base comb.
+// Formula-for-formula the same group law as point.cuh / algos.cuh (which cite the reference);
+// only the storage discipline differs: operands are slot handles, conditional swaps are handle
+// selections, table entries are multiplied straight out of global memory.
+#pragma once
+#include "slots.cuh"
+#include "algos.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// X448 (RFC 7748) -- reference goldilocks.c:1006-1076.  Per bit: 3 addsub, 5 M, 4 S, 1 sub,
+// 1 mulw+add = 14 slot operations on 7 slots; the two conditional swaps exchange handles only.
+// ---------------------------------------------------------------------------------------------
+#define X448_NSLOTS 7
+GD gmask_t x448_ladder_slots(uint32_t out[14], const uint32_t base[14], const uint32_t scalar[14], sref sb) {
+    sref x1 = s_slot(sb, 0), x2 = s_slot(sb, 1), z2 = s_slot(sb, 2), x3 = s_slot(sb, 3), z3 = s_slot(sb, 4), t1 = s_slot(sb, 5), t2 = s_slot(sb, 6);
+    {
+        gf v;
+        (void)gf_from_words(v, base); /* u >= p is accepted mod p, like the reference's ignored result */
+        s_st(x1, v); s_st(x3, v);
+        gf_set_ui(v, 1);
+        s_st(x2, v); s_st(z3, v);
+        gf_set_zero(v);
+        s_st(z2, v);
+    }
+    gmask_t swap = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int w = 13; w >= 0; w--) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < 14; i++) word |= (i == w) ? scalar[i] : 0u;
+        if (w == 0) word &= ~3u;            /* clear the cofactor bits */
+        if (w == 13) word |= 0x80000000u;   /* force bit 447 */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int b = 31; b >= 0; b--) {
+            const gmask_t k_t = (gmask_t)(-(int32_t)((word >> b) & 1u));
+            swap ^= k_t;
+            { /* cswap(x2,x3), cswap(z2,z3): the lane renames its slots, no data moves */
+                const sref nx2 = s_sel(x2, x3, swap), nx3 = s_sel(x3, x2, swap);
+                const sref nz2 = s_sel(z2, z3, swap), nz3 = s_sel(z3, z2, swap);
+                x2 = nx2; x3 = nx3; z2 = nz2; z3 = nz3;
+            }
+            swap = k_t;
+            s_addsub(t1, t2, x2, z2);          /* A = x2+z2, B = x2-z2 */
+            s_addsub(x2, z2, x3, z3);          /* C = x3+z3, D = x3-z3 */
+            s_mul(x3, z2, t1);                 /* DA */
+            s_mul(z3, x2, t2);                 /* CB */
+            s_addsub(x2, z2, x3, z3);          /* DA+CB, DA-CB */
+            s_sqr(x3, x2);                     /* x3 = (DA+CB)^2 */
+            s_sqr(z3, z2);
+            s_mul(z3, x1, z3);                 /* z3 = x1 (DA-CB)^2 */
+            s_sqr(x2, t1);                     /* AA */
+            s_sqr(z2, t2);                     /* BB */
+            s_sub(t2, x2, z2);                 /* E = AA-BB */
+            s_mulw_add(t1, t2, (uint32_t)(-GOLD_EDWARDS_D), x2); /* a24*E + AA */
+            s_mul(x2, x2, z2);                 /* x2 = AA*BB */
+            s_mul(z2, t2, t1);                 /* z2 = E (AA + a24 E) */
+        }
+    }
+    {
+        const sref nx2 = s_sel(x2, x3, swap), nx3 = s_sel(x3, x2, swap);
+        const sref nz2 = s_sel(z2, z3, swap), nz3 = s_sel(z3, z2, swap);
+        x2 = nx2; x3 = nx3; z2 = nz2; z3 = nz3;
+    }
+    s_invert(t1, z2, x3, z3);                  /* x3, z3 are dead: scratch */
+    s_mul(t2, x2, t1);
+    gf r;
+    s_ld(r, t2);
+    gf_to_words(out, r);
+    return ~gf_is_zero(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Group law on slots.  A point occupies four slots (X, Y, Z, T); `w` names three scratch slots.
+// Same formulas as point.cuh (goldilocks.c:232-254, 315-380); sign handling of table entries is a
+// per-lane handle/pointer selection instead of a data swap.
+// ---------------------------------------------------------------------------------------------
+struct spt { sref x, y, z, t; };
+struct swk { sref t0, t1, t2; };
+
+// p = 2p.  4S + 3M (+1M for T).  (goldilocks.c:232-254 point_double_internal)  T is dead on entry
+// and serves as the fourth temporary.
+GD void s_pt_double(const spt &p, const swk &w, bool before_double) {
+    s_sqr(w.t0, p.x);                  /* c */
+    s_sqr(w.t1, p.y);                  /* a */
+    s_sqr_sum(w.t2, p.y, p.x);         /* (x+y)^2 */
+    s_addsub(p.t, w.t1, w.t1, w.t0);   /* d = a + c ; e = a - c */
+    s_sub(w.t2, w.t2, p.t);            /* b = (x+y)^2 - d */
+    s_sqr2_sub(w.t0, p.z, w.t1);       /* a' = 2 z^2 - e */
+    s_mul(p.x, w.t0, w.t2);
+    s_mul(p.z, w.t1, w.t0);
+    s_mul(p.y, w.t1, p.t);
+    if (!before_double) s_mul(p.t, w.t2, p.t);
+}
+
+// p += (+-) e for an affine niels e = (a, b, c) in global memory.  7M (6M without T).
+//   swap_ab : use (b, a) instead of (a, b)       \  a negated entry is swap_ab = neg_c = all-ones
+//   neg_c   : the stored c is minus the real one  /  (goldilocks.c:271-278 cond_neg_niels)
+// (goldilocks.c:315-359 add_niels_to_pt / sub_niels_from_pt)
+GD void s_pt_add_niels_g(const spt &p, const swk &w, const gf *ea, const gf *eb, const gf *ec, gmask_t swap_ab, gmask_t neg_c, bool before_double) {
+#if defined(__CUDA_ARCH__)
+    const gf *pa = swap_ab ? eb : ea, *pb = swap_ab ? ea : eb; /* per-lane select of two addresses: no divergence */
+#else
+    const gf *pa = swap_ab ? eb : ea, *pb = swap_ab ? ea : eb;
+#endif
+    s_addsub(w.t1, w.t0, p.y, p.x);    /* y+x ; y-x */
+    s_mulg(w.t0, w.t0, pa);            /* a  = e.a (y-x) */
+    s_mulg(w.t1, w.t1, pb);            /* dy = e.b (y+x) */
+    s_mulg(p.x, p.t, ec);              /* x  = e.c t */
+    s_addsub(w.t2, w.t1, w.t1, w.t0);  /* c = dy + a ; b = dy - a */
+    s_addsub(w.t0, p.y, p.z, p.x);     /* v = z + x ; u = z - x */
+    s_mul(p.z, w.t0, p.y);             /* z = u v */
+    s_mul(p.x, s_sel(p.y, w.t0, neg_c), w.t1);   /* x = (neg ? v : u) b */
+    s_mul(p.y, s_sel(w.t0, p.y, neg_c), w.t2);   /* y = (neg ? u : v) c */
+    if (!before_double) s_mul(p.t, w.t1, w.t2);  /* t = b c */
+}
+// projective niels in global memory: z first (goldilocks.c:361-380)
+GD void s_pt_add_pniels_g(const spt &p, const swk &w, const pniels *e, gmask_t swap_ab, gmask_t neg_c, bool before_double) {
+    s_mulg(p.z, p.z, &e->z);
+    s_pt_add_niels_g(p, w, &e->n.a, &e->n.b, &e->n.c, swap_ab, neg_c, before_double);
+}
+// dst = pniels(p) with c stored NEGATED (c' = +2*39082*t = -(2 d' t), saves a negation per entry;
+// readers pass neg_c = ~sign).  a TIGHT, b and z LOOSE (they only ever feed multiplications).
+// (goldilocks.c:280-288 pt_to_pniels)
+GD void s_pt_to_pniels_negc_g(pniels *dst, const spt &p, const swk &w) {
+    s_addsub(w.t1, w.t0, p.y, p.x);
+    s_stg(&dst->n.a, w.t0);
+    s_stg(&dst->n.b, w.t1);
+    s_mulw(w.t0, p.t, (uint32_t)(-2 * GOLD_TWISTED_D));
+    s_stg(&dst->n.c, w.t0);
+    s_add(w.t0, p.z, p.z);
+    s_stg(&dst->z, w.t0);
+}
+
+#define BDSM_NSLOTS 7
+#define BDSM_TABLE 17 /* 16 odd multiples + pniels(2P) while the table is being built */
+// combo = scalar1*B + scalar2*base2 for PUBLIC inputs, warp-uniform schedule -- see the comment on
+// base_double_scalarmul_uniform (algos.cuh), whose digits, tables and operation order this follows.
+// On entry the slots X,Y,Z,T (0..3) hold base2; on exit they hold the result (X, Y, Z valid, T valid).
+// `multiples` = this lane's BDSM_TABLE pniels of global scratch.
+GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide_base, pniels *multiples) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    sc s1x, s2x;
+    sc_recode_signed(s1x, scalar1);
+    sc_recode_signed(s2x, scalar2);
+    /* odd multiples 1P, 3P, ..., 31P: P, then 2P + P, then += 2P (goldilocks.c:382-403) */
+    s_pt_to_pniels_negc_g(multiples + 0, p, w);
+    s_pt_double(p, w, false);
+    s_pt_to_pniels_negc_g(multiples + 16, p, w);
+    s_pt_add_pniels_g(p, w, multiples + 0, 0, ~0u, false);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 1; i < WINDOW_NTABLE; i++) {
+        s_pt_to_pniels_negc_g(multiples + i, p, w);
+        if (i != WINDOW_NTABLE - 1) s_pt_add_pniels_g(p, w, multiples + 16, 0, ~0u, false);
+    }
+    { /* accumulator = identity (0, 1, 1, 0); the unified addition law takes it from there */
+        gf v;
+        gf_set_zero(v); s_st(p.x, v); s_st(p.t, v);
+        gf_set_ui(v, 1); s_st(p.y, v); s_st(p.z, v);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 89; k >= 0; k--) {
+        const int i = k * WINDOW_BITS;
+        const bool fixed_here = (k % 3) == 0;           /* 15-bit fixed-base digit starts at this bit */
+        if (k != 89) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = 0; j < WINDOW_BITS - 1; j++) s_pt_double(p, w, true);
+            s_pt_double(p, w, false);
+        }
+        uint32_t bits2 = sc_window5(s2x, i);
+        const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
+        bits2 ^= inv2;
+        s_pt_add_pniels_g(p, w, multiples + (bits2 & (WINDOW_NTABLE - 1)), inv2, ~inv2, !fixed_here && k != 0);
+        if (fixed_here) {
+            uint32_t bits1 = sc_bits(s1x, i, WIDE_BITS);
+            const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
+            bits1 ^= inv1;
+            const niels *e = wide_base + (bits1 & (WIDE_ENTRIES - 1));
+            s_pt_add_niels_g(p, w, &e->a, &e->b, &e->c, inv1, inv1, k != 0);
+        }
+    }
+}

@@ -1,0 +1,83 @@
+// slot_lanes.cuh -- functors of the slot-machine kernels (slots.cuh): `operator()(i, base)` processes
+// element i with this lane's shared-memory slots starting at handle `base`.
+#pragma once
+#include "lanes.cuh"
+#include "slot_algos.cuh"
+
+struct SlotX448 { /* goldilocks_x448 (goldilocks.c:1006-1076) */
+    static constexpr int NSLOTS = X448_NSLOTS;
+    uint8_t *out; int32_t *status; const uint8_t *base, *scalar;
+    GDM void operator()(size_t i, sref sb) const {
+        uint32_t wb[14], ws[14], wo[14];
+        words_load56(wb, base + 56 * i);
+        words_load56(ws, scalar + 56 * i);
+        gmask_t nz = x448_ladder_slots(wo, wb, ws, sb);
+        words_store56(out + 56 * i, wo);
+        status[i] = ST_OK(nz);
+    }
+};
+
+GD void s_pt_from_abi(sref sb, const abi_pt *a) { /* slots 0..3 = X, Y, Z, T */
+    gf v;
+    gf_from_abi(v, &a->x); s_st(s_slot(sb, 0), v);
+    gf_from_abi(v, &a->y); s_st(s_slot(sb, 1), v);
+    gf_from_abi(v, &a->z); s_st(s_slot(sb, 2), v);
+    gf_from_abi(v, &a->t); s_st(s_slot(sb, 3), v);
+}
+// Reference quirk kept for bit-exact parity: when scalar2 == 0 its wNAF is empty and
+// goldilocks.c:1281-1284 returns the identity WITHOUT adding scalar1*B.
+GD void s_bdsm_quirk(sref sb, const sc &scalar2) {
+    uint32_t any2 = 0;
+#pragma unroll
+    for (int k = 0; k < SC_WORDS; k++) any2 |= scalar2.w[k];
+    const gmask_t z2 = (gmask_t)(((uint64_t)any2 - 1) >> 32);
+    gf v, zero, one;
+    gf_set_zero(zero);
+    gf_set_ui(one, 1);
+    s_ld(v, s_slot(sb, 0)); gf_cond_sel(v, v, zero, z2); s_st(s_slot(sb, 0), v);
+    s_ld(v, s_slot(sb, 1)); gf_cond_sel(v, v, one, z2); s_st(s_slot(sb, 1), v);
+    s_ld(v, s_slot(sb, 2)); gf_cond_sel(v, v, one, z2); s_st(s_slot(sb, 2), v);
+    s_ld(v, s_slot(sb, 3)); gf_cond_sel(v, v, zero, z2); s_st(s_slot(sb, 3), v);
+}
+struct SlotBaseDoubleScalarmul { /* goldilocks_448_base_double_scalarmul_non_secret (goldilocks.c:1260-1330) */
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    abi_pt *out; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; const niels *wide; pniels *scratch;
+    GDM void operator()(size_t i, sref sb, size_t slot) const {
+        sc s1, s2;
+        sc_from_abi(s1, scalar1 + i); sc_from_abi(s2, scalar2 + i);
+        s_pt_from_abi(sb, base2 + i);
+        s_base_double_scalarmul(sb, s1, s2, wide, scratch + BDSM_TABLE * slot);
+        s_bdsm_quirk(sb, s2);
+        gf v;
+        s_ld(v, s_slot(sb, 0)); gf_to_abi(&out[i].x, v);
+        s_ld(v, s_slot(sb, 1)); gf_to_abi(&out[i].y, v);
+        s_ld(v, s_slot(sb, 2)); gf_to_abi(&out[i].z, v);
+        s_ld(v, s_slot(sb, 3)); gf_to_abi(&out[i].t, v);
+    }
+};
+// Third launch of verification (eddsa.c:293-305): combo = response*B + challenge*A, accept iff
+// combo == R on the quotient group (goldilocks.c:644-653) and both decodes succeeded.
+struct SlotEdVerifyFinish {
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; pniels *scratch;
+    GDM void operator()(size_t i, sref sb, size_t slot) const {
+        sc c, r;
+        sc_from_abi(c, challenge + i);
+        sc_from_abi(r, response + i);
+        s_pt_from_abi(sb, pts + 2 * i);
+        s_base_double_scalarmul(sb, r, c, wide, scratch + BDSM_TABLE * slot);
+        s_bdsm_quirk(sb, c);
+        /* pt_eq(combo, R): combo.y * R.x == R.y * combo.x */
+        const sref t0 = s_slot(sb, 4), t1 = s_slot(sb, 5);
+        gf a, b;
+        gf_from_abi(a, &pts[2 * i + 1].x); s_st(t0, a);
+        gf_from_abi(b, &pts[2 * i + 1].y); s_st(t1, b);
+        s_mul(t0, s_slot(sb, 1), t0);
+        s_mul(t1, s_slot(sb, 0), t1);
+        s_ld(a, t0);
+        s_ld(b, t1);
+        gmask_t good = gf_eq(a, b);
+        good &= (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1];
+        status[i] = ST_OK(good);
+    }
+};

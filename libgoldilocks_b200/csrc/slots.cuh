@@ -1,0 +1,162 @@
+// slots.cuh -- the "slot machine": field elements of the long-running scalar multiplications live in
+// a per-lane register file in SHARED MEMORY, and every field operation is a small non-inlined
+// device function that takes slot handles (d, a, b) instead of 16-limb structs.
+//
+// Why (measured on B200, profiles/r01h_*): with by-value calls (gf.cuh gf_mul_fn) a third of the
+// caller's instructions were IMAD.MOV register shuffles in front of each call -- they run on the same
+// multiply pipe as IMAD.WIDE -- and the 7..12 live field elements of a ladder/double-and-add step
+// pinned the kernels at 255 registers + spills = 2 warps per scheduler.  With slots
+//   * a call moves three 32-bit handles, the operands are fetched with 8 LDS.128 on the otherwise
+//     idle load/store pipe and the result leaves with 4 STS.128;
+//   * conditional swaps / conditional negations of table entries become per-lane HANDLE selections
+//     (the data never moves), so the masked-swap ALU work of the ladder disappears;
+//   * the kernels need ~100 registers, no local memory, and their whole code (one body per field
+//     operation + a list of calls) stays inside the 32 KB instruction cache.
+// Layout: slot s, quad q (4 limbs), lane t of a block of SLOT_BLOCK lanes sits at
+// slot_mem[(4*s + q) * SLOT_BLOCK + t] (uint4), so every LDS.128/STS.128 of a warp is conflict-free.
+//
+// On the host (tests/hostsim) a handle is a plain pointer into a per-worker array of gf, so the same
+// algorithm source is checked against the oracle on the CPU tier.
+#pragma once
+#include "gf.cuh"
+
+#define SLOT_BLOCK 128
+
+#if defined(__CUDA_ARCH__)
+extern __shared__ uint4 slot_mem[];
+struct sref { uint32_t a; };                       /* uint4 index of this lane's quad 0 */
+#define SLOT_STRIDE (4 * SLOT_BLOCK)
+#define SFN static __device__ __noinline__
+GD sref s_slot(sref base, int k) { sref r = {base.a + (uint32_t)k * SLOT_STRIDE}; return r; }
+GD sref s_sel(sref y, sref z, gmask_t is_z) { sref r = {(y.a & ~is_z) | (z.a & is_z)}; return r; }
+GD void s_ld(gf &o, sref s) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint4 x = slot_mem[s.a + q * SLOT_BLOCK];
+        o.v[4 * q] = x.x; o.v[4 * q + 1] = x.y; o.v[4 * q + 2] = x.z; o.v[4 * q + 3] = x.w;
+    }
+}
+GD void s_st(sref s, const gf &x) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) slot_mem[s.a + q * SLOT_BLOCK] = make_uint4(x.v[4 * q], x.v[4 * q + 1], x.v[4 * q + 2], x.v[4 * q + 3]);
+}
+#else
+struct sref { gf *a; };
+#define SLOT_STRIDE 1
+#define SFN static inline
+GD sref s_slot(sref base, int k) { sref r = {base.a + k}; return r; }
+GD sref s_sel(sref y, sref z, gmask_t is_z) { return is_z ? z : y; }
+GD void s_ld(gf &o, sref s) { gf_copy(o, *s.a); }
+GD void s_st(sref s, const gf &x) { gf_copy(*s.a, x); }
+#endif
+
+// ---- the operation set (LOOSE inputs allowed wherever gf.cuh allows them) -------------------------
+SFN void s_mul(sref d, sref a, sref b) { gf x, y, z; s_ld(x, a); s_ld(y, b); gf_mul_body(z, x, y); s_st(d, z); }
+SFN void s_sqr(sref d, sref a) { gf x, z; s_ld(x, a); gf_sqr_body(z, x); s_st(d, z); }
+SFN void s_sqrn(sref d, sref a, int n) { /* n >= 1 */
+    gf x;
+    s_ld(x, a);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 0; i < n; i++) gf_sqr_body(x, x);
+    s_st(d, x);
+}
+// d = a * g, g a 16-byte aligned element in global memory (table rows; never a secret-indexed address
+// on the constant-time paths -- those scan with masks, see s_lookup_*).
+SFN void s_mulg(sref d, sref a, const gf *g) { gf x, y, z; s_ld(x, a); gf_ld<false>(y, g); gf_mul_body(z, x, y); s_st(d, z); }
+SFN void s_add(sref d, sref a, sref b) { gf x, y; s_ld(x, a); s_ld(y, b); gf_add_nr(x, x, y); s_st(d, x); }   /* TIGHT+TIGHT -> LOOSE */
+SFN void s_addr(sref d, sref a, sref b) { gf x, y; s_ld(x, a); s_ld(y, b); gf_add(x, x, y); s_st(d, x); }     /* reduced */
+SFN void s_sub(sref d, sref a, sref b) { gf x, y; s_ld(x, a); s_ld(y, b); gf_sub(x, x, y); s_st(d, x); }
+// sum = a + b (LOOSE), diff = a - b (TIGHT); one pass over the operands
+SFN void s_addsub(sref sum, sref diff, sref a, sref b) {
+    gf x, y, z;
+    s_ld(x, a); s_ld(y, b);
+    gf_sub(z, x, y);
+    gf_add_nr(x, x, y);
+    s_st(sum, x);
+    s_st(diff, z);
+}
+// d = (a + b)^2
+SFN void s_sqr_sum(sref d, sref a, sref b) { gf x, y, z; s_ld(x, a); s_ld(y, b); gf_add_nr(x, x, y); gf_sqr_body(z, x); s_st(d, z); }
+// d = 2 a^2 - b
+SFN void s_sqr2_sub(sref d, sref a, sref b) {
+    gf x, y, z;
+    s_ld(x, a);
+    gf_sqr_body(z, x);
+    s_ld(y, b);
+    gf_add_nr(z, z, z);
+    gf_sub(z, z, y);
+    s_st(d, z);
+}
+SFN void s_neg(sref d, sref a) { gf x; s_ld(x, a); gf_neg(x, x); s_st(d, x); }
+SFN void s_mulw(sref d, sref a, uint32_t w) { gf x, z; s_ld(x, a); gf_mulw(z, x, w); s_st(d, z); }
+// d = a * w + c  (LOOSE)
+SFN void s_mulw_add(sref d, sref a, uint32_t w, sref c) { gf x, y, z; s_ld(x, a); s_ld(y, c); gf_mulw(z, x, w); gf_add_nr(z, z, y); s_st(d, z); }
+SFN void s_copy(sref d, sref a) { gf x; s_ld(x, a); s_st(d, x); }
+SFN void s_stg(gf *g, sref a) { /* slot -> global, 128-bit stores */
+    gf x;
+    s_ld(x, a);
+#if defined(__CUDA_ARCH__)
+    uint4 *p = reinterpret_cast<uint4 *>(g);
+#pragma unroll
+    for (int q = 0; q < 4; q++) p[q] = make_uint4(x.v[4 * q], x.v[4 * q + 1], x.v[4 * q + 2], x.v[4 * q + 3]);
+#else
+    gf_copy(*g, x);
+#endif
+}
+
+// a = x^((p-3)/4); returns all-ones iff a^2 x == 1.  Same addition chain as gf_isr (gf.cuh), walked
+// on slots: `a` and `saved` are scratch/output slots distinct from x.
+GD gmask_t s_isr(sref a, sref saved, sref x) {
+    s_copy(a, x);
+    s_copy(saved, x);
+    const uint16_t steps[12] = {1 | 0x100,  1 | 0x100 | 0x200, 3,           3 | 0x200,  9 | 0x200,  1 | 0x100,
+                                18 | 0x200, 37,                37 | 0x200, 111 | 0x200, 1 | 0x100, 223};
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = 0; s < 12; s++) {
+        s_sqrn(a, a, steps[s] & 0xff);
+        s_mul(a, a, (steps[s] & 0x100) ? x : saved); /* public schedule */
+        if (steps[s] & 0x200) s_copy(saved, a);
+    }
+    s_sqr(saved, a);
+    s_mul(saved, saved, x);
+    gf t, one;
+    s_ld(t, saved);
+    gf_set_ui(one, 1);
+    return gf_eq(t, one);
+}
+// y = 1/x (0 for x = 0); t1, t2 scratch slots, all four distinct.  (goldilocks.c:69-80)
+GD void s_invert(sref y, sref x, sref t1, sref t2) {
+    s_sqr(t1, x);
+    (void)s_isr(y, t2, t1);
+    s_sqr(t1, y);
+    s_mul(y, t1, x);
+}
+
+// Kernel shape for slot functors: F::NSLOTS slots of dynamic shared memory per lane,
+// `f(i, base)` with base = handle of this lane's slot 0.  (Host simulator: tests/hostsim run_slots.)
+#if defined(__CUDACC__)
+template <class F> struct slot_min_blocks { static constexpr int value = 1; };
+template <class F>
+__global__ void __launch_bounds__(SLOT_BLOCK, slot_min_blocks<F>::value) k_slots(F f, size_t n) {
+    const size_t i = (size_t)blockIdx.x * SLOT_BLOCK + threadIdx.x;
+#if defined(__CUDA_ARCH__)
+    sref base = {threadIdx.x};
+    if (i < n) f(i, base);
+#endif
+}
+// Persistent grid-stride shape for functors that also own a per-thread scratch area in HBM
+// (`slot` = global thread index): f(i, base, slot).
+template <class F>
+__global__ void __launch_bounds__(SLOT_BLOCK, slot_min_blocks<F>::value) k_slots_persist(F f, size_t n) {
+    const size_t slot = (size_t)blockIdx.x * SLOT_BLOCK + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * SLOT_BLOCK;
+#if defined(__CUDA_ARCH__)
+    sref base = {threadIdx.x};
+    for (size_t i = slot; i < n; i += stride) f(i, base, slot);
+#endif
+}
+#endif

@@ -13,7 +13,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../libgoldilocks_b200/csrc/lanes.cuh"
+#include "../../libgoldilocks_b200/csrc/slot_lanes.cuh"
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -38,6 +38,36 @@ static void run_slot(const F &f, size_t n) { /* one scratch slot per worker thre
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++)
         th.emplace_back([&f, n, nt, t]() { for (size_t i = n * t / nt; i < n * (t + 1) / nt; i++) f(i, (size_t)t); });
+    for (auto &x : th) x.join();
+}
+
+template <class F>
+static void run_sm(const F &f, size_t n) { /* slot machine: F::NSLOTS field elements of scratch per worker */
+    int nt = g_threads;
+    if ((size_t)nt > n) nt = n ? (int)n : 1;
+    auto work = [&f](size_t lo, size_t hi) {
+        std::vector<gf> slots(F::NSLOTS);
+        sref base = {slots.data()};
+        for (size_t i = lo; i < hi; i++) f(i, base);
+    };
+    if (nt <= 1) { work(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&work, n, nt, t]() { work(n * t / nt, n * (t + 1) / nt); });
+    for (auto &x : th) x.join();
+}
+
+template <class F>
+static void run_smp(const F &f, size_t n) { /* persistent slot machine: slots + one HBM scratch area per worker */
+    int nt = g_threads;
+    if ((size_t)nt > n) nt = n ? (int)n : 1;
+    auto work = [&f](size_t lo, size_t hi, size_t slot) {
+        std::vector<gf> slots(F::NSLOTS);
+        sref base = {slots.data()};
+        for (size_t i = lo; i < hi; i++) f(i, base, slot);
+    };
+    if (nt <= 1) { work(0, n, 0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&work, n, nt, t]() { work(n * t / nt, n * (t + 1) / nt, (size_t)t); });
     for (auto &x : th) x.join();
 }
 
@@ -102,7 +132,7 @@ EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint
 EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(hpt *o, const void *, const hsc *s, size_t n) { LaneComb f = {o, s, tables()}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_scalarmul_batch(hpt *o, const hpt *b, const hsc *s, size_t n) { LaneScalarmul f = {o, b, s, slots(WINDOW_NTABLE)}; run_slot(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_double_scalarmul_batch(hpt *o, const hpt *b1, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { LaneDoubleScalarmul f = {o, b1, s1, b2, s2, slots(2 * WINDOW_NTABLE)}; run_slot(f, n); return -1; }
-EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *o, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { LaneBaseDoubleScalarmul f = {o, s1, b2, s2, wide_table(), slots(WINDOW_NTABLE)}; run_slot(f, n); return -1; }
+EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *o, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { SlotBaseDoubleScalarmul f = {o, s1, b2, s2, wide_table(), slots(BDSM_TABLE)}; run_smp(f, n); return -1; }
 
 EXPORT int32_t goldilocks_448_scalar_add_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_ADD> f = {o, a, b}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_scalar_sub_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_SUB> f = {o, a, b}; run(f, n); return -1; }
@@ -110,7 +140,7 @@ EXPORT int32_t goldilocks_448_scalar_mul_batch(hsc *o, const hsc *a, const hsc *
 EXPORT int32_t goldilocks_448_scalar_halve_batch(hsc *o, const hsc *a, size_t n) { LaneSc<SCOP_HALVE> f = {o, a, nullptr}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_scalar_decode_long_batch(hsc *o, const uint8_t *ser, size_t len, size_t n) { LaneScDecodeLong f = {o, ser, len}; run(f, n); return -1; }
 
-EXPORT int32_t goldilocks_x448_batch(uint8_t *o, int32_t *st, const uint8_t *base, const uint8_t *sc, size_t n) { LaneX448 f = {o, st, base, sc}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_x448_batch(uint8_t *o, int32_t *st, const uint8_t *base, const uint8_t *sc, size_t n) { SlotX448 f = {o, st, base, sc}; run_sm(f, n); return -1; }
 EXPORT int32_t goldilocks_x448_derive_public_key_batch(uint8_t *o, const uint8_t *sc, size_t n) { LaneX448DerivePk f = {o, sc, tables()}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_shake256_hash_batch(uint8_t *o, size_t outlen, const uint8_t *in, const size_t *off, size_t n) { LaneShake256 f = {o, outlen, in, off}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_ed448_derive_public_key_batch(uint8_t *pk, const uint8_t *sk, size_t n) { LaneEdDerivePk f = {pk, sk, tables()}; run(f, n); return -1; }
@@ -137,7 +167,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     run(f1, 2 * n);
     LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len};
     run(f2, n);
-    LaneEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), slots(WINDOW_NTABLE)};
-    run_slot(f3, n);
+    SlotEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), slots(BDSM_TABLE)};
+    run_smp(f3, n);
     return -1;
 }

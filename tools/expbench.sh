@@ -5,5 +5,5 @@ for v in base "$@"; do
   echo "== $v"
   python tools/opbench.py --ops comb,x448,decode 2>&1 | grep -v "^$"
   python bench.py --no-cpu --no-extra --steps 3 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('verify %.3f M/s  finish %.2f ms  decode %.2f ms' % (d['value']/1e6, d['roofline']['kernel_ms']['LaneEdVerifyFinish'], d['roofline']['kernel_ms']['LaneEdVerifyDecode']))"
+import json,sys; d=json.loads(sys.stdin.read()); print('verify %.3f M/s  finish %.2f ms  decode %.2f ms' % (d['value']/1e6, d['roofline']['kernel_ms']['SlotEdVerifyFinish'], d['roofline']['kernel_ms']['LaneEdVerifyDecode']))"
 done

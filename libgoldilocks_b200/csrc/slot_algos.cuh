@@ -7,6 +7,37 @@
 #include "slots.cuh"
 #include "algos.cuh"
 
+#if defined(__CUDA_ARCH__)
+// Block-shared inversion (Montgomery's trick across lanes; the reference does the same thing across table
+// entries in goldilocks.c:703-726).  Every lane of the block has a NONZERO field element in slot `zin`;
+// on return its inverse is in slot `zout`.  Warp 0 does the work for the four lanes (w, l), w = 0..3, that
+// share lane index l: 3 prefix products, ONE inversion chain, 6 multiplications -- the other three warps
+// wait at the barrier (other resident blocks keep the multiplier busy).  All 128 lanes of the block must
+// call it (k_slots keeps out-of-range lanes alive for this); slots 0..4 of every lane are clobbered.
+// Constant time: the schedule is fixed, operands are only multiplied.
+GD void s_block_invert4(sref sb, int zin, int zout) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        sref t[4]; /* slot 0 of the four lanes served by this lane */
+#pragma unroll
+        for (int w = 0; w < 4; w++) t[w].a = sb.a + 32u * w;
+        const sref z0 = s_slot(t[0], zin), z1 = s_slot(t[1], zin), z2 = s_slot(t[2], zin), z3 = s_slot(t[3], zin);
+        const sref p1 = s_slot(t[0], 0), p2 = s_slot(t[0], 1), p3 = s_slot(t[0], 2), inv = s_slot(t[0], 3);
+        s_mul(p1, z0, z1);
+        s_mul(p2, p1, z2);
+        s_mul(p3, p2, z3);
+        s_invert(inv, p3, s_slot(t[1], 0), s_slot(t[1], 1));
+        s_mul(s_slot(t[3], zout), inv, p2);
+        s_mul(inv, inv, z3);
+        s_mul(s_slot(t[2], zout), inv, p1);
+        s_mul(inv, inv, z2);
+        s_mul(s_slot(t[1], zout), inv, z0);
+        s_mul(s_slot(t[0], zout), inv, z1);
+    }
+    __syncthreads();
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // X448 (RFC 7748) -- reference goldilocks.c:1006-1076.  Per bit: 3 addsub, 5 M, 4 S, 1 sub,
 // 1 mulw+add = 14 slot operations on 7 slots; the two conditional swaps exchange handles only.
@@ -66,10 +97,31 @@ GD gmask_t x448_ladder_slots(uint32_t out[14], const uint32_t base[14], const ui
         const sref nz2 = s_sel(z2, z3, swap), nz3 = s_sel(z3, z2, swap);
         x2 = nx2; x3 = nx3; z2 = nz2; z3 = nz3;
     }
-    s_invert(t1, z2, x3, z3);                  /* x3, z3 are dead: scratch */
-    s_mul(t2, x2, t1);
-    gf r;
-    s_ld(r, t2);
+    /* u = x2 / z2 with 0 for z2 = 0 (goldilocks.c:69-80 gf_invert(0) = 0).  On the device the inversion is
+     * shared by the four lanes of a block that have the same lane index (s_block_invert4 below): one
+     * addition chain per four elements instead of one per element. */
+    const sref zi = s_slot(sb, 5), xs = s_slot(sb, 6), res = s_slot(sb, 0);
+    gmask_t nz;
+    {
+        gf z, one;
+        s_ld(z, z2);
+        nz = ~gf_is_zero(z);
+        gf_set_ui(one, 1);
+        gf_cond_sel(z, one, z, nz);             /* 0 -> 1 so it cannot poison the shared product */
+        s_st(zi, z);
+        s_copy(xs, x2);
+    }
+#if defined(__CUDA_ARCH__)
+    s_block_invert4(sb, 5, 4);                  /* slot 5 -> its inverse in slot 4 */
+    s_mul(res, xs, s_slot(sb, 4));
+#else
+    s_invert(s_slot(sb, 4), zi, s_slot(sb, 1), s_slot(sb, 2));
+    s_mul(res, xs, s_slot(sb, 4));
+#endif
+    gf r, zero;
+    s_ld(r, res);
+    gf_set_zero(zero);
+    gf_cond_sel(r, zero, r, nz);
     gf_to_words(out, r);
     return ~gf_is_zero(r);
 }

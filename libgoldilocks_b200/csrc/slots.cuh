@@ -144,8 +144,10 @@ template <class F>
 __global__ void __launch_bounds__(SLOT_BLOCK, slot_min_blocks<F>::value) k_slots(F f, size_t n) {
     const size_t i = (size_t)blockIdx.x * SLOT_BLOCK + threadIdx.x;
 #if defined(__CUDA_ARCH__)
+    /* out-of-range lanes of the last block stay alive on a clamped index (block-wide barriers inside
+     * the functors need all 128 lanes); `live` = false tells the functor not to store anything */
     sref base = {threadIdx.x};
-    if (i < n) f(i, base);
+    f(i < n ? i : n - 1, base, i < n);
 #endif
 }
 // Persistent grid-stride shape for functors that also own a per-thread scratch area in HBM

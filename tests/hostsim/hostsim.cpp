@@ -48,7 +48,7 @@ static void run_sm(const F &f, size_t n) { /* slot machine: F::NSLOTS field elem
     auto work = [&f](size_t lo, size_t hi) {
         std::vector<gf> slots(F::NSLOTS);
         sref base = {slots.data()};
-        for (size_t i = lo; i < hi; i++) f(i, base);
+        for (size_t i = lo; i < hi; i++) f(i, base, true);
     };
     if (nt <= 1) { work(0, n); return; }
     std::vector<std::thread> th;

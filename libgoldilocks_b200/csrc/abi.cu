@@ -156,7 +156,7 @@ bool ctx_init(Ctx &c, int dev) {
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&c.ft, sizeof(fixed_tables)));
     LaneBuildTables f = {c.ft};
-    if (!launch(c, f, COMB_N + 2, c.stream)) return false;
+    if (!launch(c, f, TABLE_LANES, c.stream)) return false;
     CU(cudaMalloc(&c.wide, sizeof(niels) * WIDE_ENTRIES));
     {
         pniels *tmp = nullptr; gf *pre = nullptr;
@@ -480,8 +480,8 @@ goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(
 goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(hpt *out, const goldilocks_448_precomputed_s *base, const hsc *scalar, size_t n) {
     if (base != goldilocks_448_precomputed_base) { g_err = "only goldilocks_448_precomputed_base is supported"; return GOLDILOCKS_FAILURE; }
     Call k;
-    LaneComb f = {k.out<abi_pt>(n), k.in(S(scalar), n), k.ok ? k.c->ft : nullptr};
-    k.run(f, n);
+    SlotComb f = {k.out<abi_pt>(n), k.in(S(scalar), n), k.ok ? k.c->ft : nullptr};
+    k.run_sm(f, n);
     k.fetch(P(out), f.out, n);
     return k.finish();
 }
@@ -662,8 +662,8 @@ goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *s
 goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch_dev(hpt *out, const hsc *scalar, size_t n, void *stream) {
     Ctx *c = dev_ctx();
     if (!c) return GOLDILOCKS_FAILURE;
-    LaneComb f = {P(out), S(scalar), c->ft};
-    return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+    SlotComb f = {P(out), S(scalar), c->ft};
+    return launch_slots(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
 }
 goldilocks_error_t goldilocks_448_gf_mul_batch_dev(uint8_t *out, const uint8_t *a, const uint8_t *b, size_t n, void *stream) {
     Ctx *c = dev_ctx();

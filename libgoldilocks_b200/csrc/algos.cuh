@@ -25,9 +25,17 @@
 #define WIDE_LANES 128                         /* lanes that build the table at init */
 #define WIDE_PER_LANE (WIDE_ENTRIES / WIDE_LANES)
 
+/* Doubling-free fixed-base table of the batched comb kernel: the reference's signed comb generalised to
+ * (n, t, s) = (90, 5, 1) -- 90 rows of 16 canonical affine niels, row j = {(16 +- 8 +- 4 +- 2 +- 1) 2^(5j) B}.
+ * Same 450-bit signed recoding as (5, 5, 18) (goldilocks.c:25-27, 842-843), but the 17 doublings are
+ * gone: 90 constant-time additions.  270 KB, L2 resident. */
+#define WIN_ROWS 90
+#define TABLE_LANES (COMB_N + 2 + WIN_ROWS)    /* lanes that build the fixed tables at init */
+
 // Device-resident fixed-base tables (built once per device by build_tables_lane()).
 struct fixed_tables {
     niels comb[COMB_ENTRIES];        /* canonical affine niels, layout of goldilocks_448_precomputed_base */
+    niels win[WIN_ROWS * 16];        /* doubling-free comb rows (see WIN_ROWS) */
     niels wnaf[WNAF_FIXED_ENTRIES];  /* canonical affine niels, layout of goldilocks_448_precomputed_wnaf_as_fe */
     pt base;                         /* decoded decaf base point */
 };
@@ -337,18 +345,18 @@ GD void normalize_niels(niels *table, const gf *zs, gf *zis, int n) {
 //   entry[idx] = ( 2^(18*4) + sum_{k<4} (2*bit_k(idx) - 1) * 2^(18k) ) * 2^(90*comb) * B
 // Same table as the reference's precompute() (goldilocks.c:757-818), built comb-by-comb so the
 // five combs can be produced by five lanes in parallel.
-GD void build_comb(niels *out16, const pt &base, int comb) {
+GD void build_comb_row(niels *out16, const pt &base, int skip_doublings, int spacing) {
     pt working, start, doubles[COMB_T - 1];
     gf zs[16], zis[16];
     pt_copy(working, base);
-    for (int k = 0; k < COMB_S * COMB_T * comb; k++) pt_double(working, working, false);
+    for (int k = 0; k < skip_doublings; k++) pt_double(working, working, false);
     for (int j = 0; j < COMB_T; j++) {
         if (j) pt_add(start, start, working);
         else pt_copy(start, working);
         if (j == COMB_T - 1) break;
         pt_double(working, working, false);
-        pt_copy(doubles[j], working);          /* 2 * 2^(18 j) * (comb base) */
-        for (int k = 0; k < COMB_S - 1; k++) pt_double(working, working, false);
+        pt_copy(doubles[j], working);          /* 2 * 2^(spacing j) * (row base) */
+        for (int k = 0; k < spacing - 1; k++) pt_double(working, working, false);
     }
     /* start = all teeth positive = entry 15; walk a Gray code flipping one tooth at a time */
     for (int j = 0;; j++) {
@@ -366,6 +374,7 @@ GD void build_comb(niels *out16, const pt &base, int comb) {
     }
     normalize_niels(out16, zs, zis, 16);
 }
+GD void build_comb(niels *out16, const pt &base, int comb) { build_comb_row(out16, base, COMB_S * COMB_T * comb, COMB_S); }
 // Odd multiples 1B,3B,...,63B as canonical affine niels (goldilocks.c:1204-1258).
 GD void build_wnaf_base(niels *out32, const pt &base) {
     gf zs[WNAF_FIXED_ENTRIES], zis[WNAF_FIXED_ENTRIES];
@@ -419,6 +428,7 @@ GD void build_tables_lane(fixed_tables *ft, int lane) {
     if (lane < COMB_N) build_comb(ft->comb + 16 * lane, base, lane);
     else if (lane == COMB_N) build_wnaf_base(ft->wnaf, base);
     else if (lane == COMB_N + 1) pt_copy(ft->base, base);
+    else if (lane < TABLE_LANES) { const int row = lane - (COMB_N + 2); build_comb_row(ft->win + 16 * row, base, COMB_T * row, 1); }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -243,3 +243,52 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-base signed comb, constant time -- reference goldilocks.c:830-877 (same digits, table and
+// operation order as comb_scalarmul in algos.cuh).  9 slots: X,Y,Z,T, three temporaries and two
+// lookup slots; the three coordinates of the selected entry are fetched just in time (a and b, then c),
+// the conditional negation of the entry is a handle selection (goldilocks.c:271-278).
+// ---------------------------------------------------------------------------------------------
+#define COMB_NSLOTS 9
+// p += (+-) entry idx of the 16-entry comb row; `first` = true sets p to the entry instead (niels_to_pt)
+GD void s_pt_add_niels_ct(const spt &p, const swk &w, sref la, sref lb, const niels *row, uint32_t idx, gmask_t neg, bool before_double) {
+    const int stride = (int)(sizeof(niels) / sizeof(gf));
+    s_lookup_ct(la, &row->a, stride, 1 << (COMB_T - 1), idx);
+    s_lookup_ct(lb, &row->b, stride, 1 << (COMB_T - 1), idx);
+    s_addsub(w.t1, w.t0, p.y, p.x);                      /* y+x ; y-x */
+    s_mul(w.t0, w.t0, s_sel(la, lb, neg));               /* a  = e.a (y-x) */
+    s_mul(w.t1, w.t1, s_sel(lb, la, neg));               /* dy = e.b (y+x) */
+    s_lookup_ct(la, &row->c, stride, 1 << (COMB_T - 1), idx);
+    s_mul(p.x, p.t, la);                                 /* x  = e.c t */
+    s_addsub(w.t2, w.t1, w.t1, w.t0);                    /* c = dy + a ; b = dy - a */
+    s_addsub(w.t0, p.y, p.z, p.x);                       /* v = z + x ; u = z - x */
+    s_mul(p.z, w.t0, p.y);
+    s_mul(p.x, s_sel(p.y, w.t0, neg), w.t1);
+    s_mul(p.y, s_sel(w.t0, p.y, neg), w.t2);
+    if (!before_double) s_mul(p.t, w.t1, w.t2);
+}
+// out = scalar * B over the doubling-free table `win` (WIN_ROWS rows of 16, algos.cuh): 90 constant-time
+// additions, no doublings.  Digit j of the signed recoding = bits [5j, 5j+5) of (scalar + adj)/2.
+GD void s_comb_scalarmul(sref sb, const niels *win, const sc &scalar) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    const sref la = s_slot(sb, 7), lb = s_slot(sb, 8);
+    sc s1x;
+    sc_recode_signed(s1x, scalar);
+    { /* accumulator = identity; the unified addition law takes the first entry from there */
+        gf v;
+        gf_set_zero(v); s_st(p.x, v); s_st(p.t, v);
+        gf_set_ui(v, 1); s_st(p.y, v); s_st(p.z, v);
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < WIN_ROWS; j++) {
+        uint32_t tab = sc_bits(s1x, COMB_T * j, COMB_T);
+        const gmask_t invert = (gmask_t)((int32_t)(tab >> (COMB_T - 1)) - 1);
+        tab ^= invert;
+        tab &= (1u << (COMB_T - 1)) - 1;
+        s_pt_add_niels_ct(p, w, la, lb, win + 16 * j, tab, invert, false);
+    }
+}

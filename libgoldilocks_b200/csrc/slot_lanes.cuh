@@ -82,3 +82,21 @@ struct SlotEdVerifyFinish {
         status[i] = ST_OK(good);
     }
 };
+
+GD void s_pt_to_abi(abi_pt *o, sref sb) { /* slots 0..3 -> canonical host limbs */
+    gf v;
+    s_ld(v, s_slot(sb, 0)); gf_to_abi(&o->x, v);
+    s_ld(v, s_slot(sb, 1)); gf_to_abi(&o->y, v);
+    s_ld(v, s_slot(sb, 2)); gf_to_abi(&o->z, v);
+    s_ld(v, s_slot(sb, 3)); gf_to_abi(&o->t, v);
+}
+struct SlotComb { /* goldilocks_448_precomputed_scalarmul (goldilocks.c:830-877) */
+    static constexpr int NSLOTS = COMB_NSLOTS;
+    abi_pt *out; const abi_sc *scalar; const fixed_tables *ft;
+    GDM void operator()(size_t i, sref sb, bool live) const {
+        sc s;
+        sc_from_abi(s, scalar + i);
+        s_comb_scalarmul(sb, ft->win, s);
+        if (live) s_pt_to_abi(out + i, sb);
+    }
+};

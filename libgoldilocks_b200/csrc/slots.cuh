@@ -93,6 +93,22 @@ SFN void s_neg(sref d, sref a) { gf x; s_ld(x, a); gf_neg(x, x); s_st(d, x); }
 SFN void s_mulw(sref d, sref a, uint32_t w) { gf x, z; s_ld(x, a); gf_mulw(z, x, w); s_st(d, z); }
 // d = a * w + c  (LOOSE)
 SFN void s_mulw_add(sref d, sref a, uint32_t w, sref c) { gf x, y, z; s_ld(x, a); s_ld(y, c); gf_mulw(z, x, w); gf_add_nr(z, z, y); s_st(d, z); }
+// Constant-time table lookup of ONE coordinate: d = row[idx].<coordinate>, where `first` points at
+// that coordinate of entry 0 and entries are `stride` gf apart.  Every lane reads every entry (the
+// addresses do not depend on idx) and keeps the one whose index matches, by masks -- the semantics of
+// the reference's constant_time_lookup (src/include/constant_time.h:134-183).  n <= 32 entries.
+SFN void s_lookup_ct(sref d, const gf *first, int stride, int n, uint32_t idx) {
+    gf o;
+    gf_set_zero(o);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+    for (int e = 0; e < n; e++) {
+        const gmask_t m = (gmask_t)(((uint64_t)((uint32_t)e ^ idx) - 1) >> 32); /* all-ones iff e == idx */
+        gf_ld_or_masked<true>(o, first + (size_t)e * stride, m);
+    }
+    s_st(d, o);
+}
 SFN void s_copy(sref d, sref a) { gf x; s_ld(x, a); s_st(d, x); }
 SFN void s_stg(gf *g, sref a) { /* slot -> global, 128-bit stores */
     gf x;

@@ -75,7 +75,7 @@ static fixed_tables *tables() {
     static fixed_tables *ft = nullptr;
     if (!ft) {
         ft = (fixed_tables *)aligned_alloc(64, sizeof(fixed_tables));
-        for (int lane = 0; lane < COMB_N + 2; lane++) build_tables_lane(ft, lane);
+        for (int lane = 0; lane < TABLE_LANES; lane++) build_tables_lane(ft, lane);
     }
     return ft;
 }
@@ -129,7 +129,7 @@ EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uin
 EXPORT int32_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(hpt *o, int32_t *st, const uint8_t *enc, size_t n) { LaneDecodeEddsa f = {o, st, enc}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint8_t *o, const hpt *a, size_t n) { LaneEncodeX448 f = {o, a}; run(f, n); return -1; }
 
-EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(hpt *o, const void *, const hsc *s, size_t n) { LaneComb f = {o, s, tables()}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(hpt *o, const void *, const hsc *s, size_t n) { SlotComb f = {o, s, tables()}; run_sm(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_scalarmul_batch(hpt *o, const hpt *b, const hsc *s, size_t n) { LaneScalarmul f = {o, b, s, slots(WINDOW_NTABLE)}; run_slot(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_double_scalarmul_batch(hpt *o, const hpt *b1, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { LaneDoubleScalarmul f = {o, b1, s1, b2, s2, slots(2 * WINDOW_NTABLE)}; run_slot(f, n); return -1; }
 EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *o, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { SlotBaseDoubleScalarmul f = {o, s1, b2, s2, wide_table(), slots(BDSM_TABLE)}; run_smp(f, n); return -1; }

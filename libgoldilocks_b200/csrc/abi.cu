@@ -550,8 +550,8 @@ goldilocks_error_t goldilocks_x448_batch(uint8_t *out, goldilocks_error_t *statu
 }
 goldilocks_error_t goldilocks_x448_derive_public_key_batch(uint8_t *out, const uint8_t *scalar, size_t n) {
     Call k;
-    LaneX448DerivePk f = {k.out<uint8_t>(56 * n), k.in(scalar, 56 * n), k.ok ? k.c->ft : nullptr};
-    k.run(f, n);
+    SlotX448DerivePk f = {k.out<uint8_t>(56 * n), k.in(scalar, 56 * n), k.ok ? k.c->ft : nullptr};
+    k.run_sm(f, n);
     k.fetch(out, f.out, 56 * n);
     return k.finish();
 }
@@ -565,8 +565,8 @@ goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out, size_t outlen, c
 }
 goldilocks_error_t goldilocks_ed448_derive_public_key_batch(uint8_t *pubkey, const uint8_t *privkey, size_t n) {
     Call k;
-    LaneEdDerivePk f = {k.out<uint8_t>(57 * n), k.in(privkey, 57 * n), k.ok ? k.c->ft : nullptr};
-    k.run(f, n);
+    SlotEdDerivePk f = {k.out<uint8_t>(57 * n), k.in(privkey, 57 * n), k.ok ? k.c->ft : nullptr};
+    k.run_sm(f, n);
     k.fetch(pubkey, f.pk, 57 * n);
     return k.finish();
 }
@@ -585,8 +585,8 @@ goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t
     k.run(f0, n);
     LaneEdSignNonce f1 = {nonce, nonce4, seed, dmsg, doff, prehashed, dctx, context_len};
     k.run(f1, n);
-    LaneEdSignR f2 = {dsig, nonce4, k.ok ? k.c->ft : nullptr};
-    k.run(f2, n);
+    SlotEdSignR f2 = {dsig, nonce4, k.ok ? k.c->ft : nullptr};
+    k.run_sm(f2, n);
     LaneEdSignFinish f3 = {dsig, secret, nonce, dpk, dmsg, doff, prehashed, dctx, context_len};
     k.run(f3, n);
     k.fetch(signature, dsig, 114 * n);

@@ -1,4 +1,4 @@
 // k_comb.cu -- explicit kernel instantiations (see launch.cuh)
 #include "launch.cuh"
 INSTANTIATE_SM(SlotComb)
-INSTANTIATE_PLAIN(LaneX448DerivePk)
+INSTANTIATE_SM(SlotX448DerivePk)

@@ -13,7 +13,6 @@
 template <class F> struct lane_min_blocks { static constexpr int value = 1; };
 // Measured on B200 at 2^20 (tools/opbench.py): comb 34.5 -> 38.5 Mops/s with 3 blocks (168 regs, no spills);
 // X448 gains 1% at 3 blocks but spills, so it stays at 2.
-template <> struct lane_min_blocks<LaneX448DerivePk> { static constexpr int value = 3; };
 
 template <class F>
 __global__ void __launch_bounds__(BLOCK, lane_min_blocks<F>::value) k_lanes(F f, size_t n) {
@@ -48,6 +47,9 @@ cudaError_t lanes_slot_occupancy(int *occ) {
 // Resident blocks per SM: measured choice per functor (registers <= 65536 / (128 * blocks)).
 template <> struct slot_min_blocks<SlotX448> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotComb> { static constexpr int value = 3; };
+template <> struct slot_min_blocks<SlotX448DerivePk> { static constexpr int value = 3; };
+template <> struct slot_min_blocks<SlotEdDerivePk> { static constexpr int value = 3; };
+template <> struct slot_min_blocks<SlotEdSignR> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotBaseDoubleScalarmul> { static constexpr int value = 4; };
 template <class F>
@@ -92,15 +94,14 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
     X(LanePtEq) X(LanePtValid) X(LanePtEncode) X(LanePtDecode)                                      \
     X(LaneFromHash<false>) X(LaneFromHash<true>)                                                    \
     X(LaneEncodeEddsa) X(LaneDecodeEddsa) X(LaneEncodeX448)                                         \
-    X(LaneX448DerivePk)                                                                             \
     X(LaneSc<SCOP_ADD>) X(LaneSc<SCOP_SUB>) X(LaneSc<SCOP_MUL>) X(LaneSc<SCOP_HALVE>)               \
     X(LaneScDecodeLong) X(LaneShake256)                                                             \
-    X(LaneEdDerivePk) X(LaneEdSecretScalar) X(LaneEdSignExpand) X(LaneEdSignNonce) X(LaneEdSignR) X(LaneEdSignFinish)   \
+    X(LaneEdSecretScalar) X(LaneEdSignExpand) X(LaneEdSignNonce) X(LaneEdSignFinish)   \
     X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneBuildTables) X(LaneBuildWide)
 #define LANES_SLOT(X)                                                                               \
     X(LaneScalarmul) X(LaneDoubleScalarmul)
 
-#define LANES_SM(X) X(SlotX448) X(SlotComb)
+#define LANES_SM(X) X(SlotX448) X(SlotComb) X(SlotX448DerivePk) X(SlotEdDerivePk) X(SlotEdSignR)
 #define INSTANTIATE_SM(F) template cudaError_t launch_sm<F>(const F &, size_t, cudaStream_t);
 #define DECLARE_SM(F) extern INSTANTIATE_SM(F)
 #define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotBaseDoubleScalarmul)

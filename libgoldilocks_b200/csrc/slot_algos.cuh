@@ -292,3 +292,66 @@ GD void s_comb_scalarmul(sref sb, const niels *win, const sc &scalar) {
         s_pt_add_niels_ct(p, w, la, lb, win + 16 * j, tab, invert, false);
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Encoders that follow a comb multiplication (slots 0..3 = the point, 9 slots available).  The one
+// inversion each needs is shared by four lanes on the device (s_block_invert4); inverse of 0 is 0 as in
+// the reference's gf_invert (goldilocks.c:69-80).
+// ---------------------------------------------------------------------------------------------
+// slot `zin` <- z or 1 when z == 0; returns the nonzero mask
+GD gmask_t s_nonzero_or_one(sref zin, sref z) {
+    gf v, one;
+    s_ld(v, z);
+    const gmask_t nz = ~gf_is_zero(v);
+    gf_set_ui(one, 1);
+    gf_cond_sel(v, one, v, nz);
+    s_st(zin, v);
+    return nz;
+}
+// slot 4 <- 1 / slot 5 (slot 5 nonzero); slots 0..3 are scratch, slots >= 6 are preserved
+GD void s_invert_5_to_4(sref sb) {
+#if defined(__CUDA_ARCH__)
+    s_block_invert4(sb, 5, 4);
+#else
+    s_invert(s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 1), s_slot(sb, 2));
+#endif
+}
+// RFC 8032 encoding after the 4-isogeny back to the untwisted curve (goldilocks.c:905-946):
+// yw = canonical y words, xsign = low bit of x.
+GD void s_encode_like_eddsa(uint32_t yw[14], uint32_t &xsign, sref sb) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const sref t0 = s_slot(sb, 4), t1 = s_slot(sb, 5), t2 = s_slot(sb, 6), xs = s_slot(sb, 6), ys = s_slot(sb, 7);
+    s_sqr(t0, p.x);                    /* x^2 */
+    s_sqr(t1, p.y);                    /* y^2 */
+    s_sqr_sum(t2, p.y, p.x);
+    s_addsub(p.t, t1, t1, t0);         /* u = y^2 + x^2 ; z = y^2 - x^2 */
+    s_sub(t2, t2, p.t);                /* 2xy */
+    s_sqr2_sub(t0, p.z, t1);           /* t = 2 z^2 - (y^2 - x^2) */
+    s_mul(p.x, t0, t2);                /* x = t * 2xy */
+    s_mul(ys, t1, p.t);                /* y = (y^2 - x^2) u */
+    s_mul(p.z, p.t, t0);               /* z = u t */
+    s_copy(xs, p.x);
+    const gmask_t nz = s_nonzero_or_one(s_slot(sb, 5), p.z);
+    s_invert_5_to_4(sb);
+    s_mul(xs, xs, s_slot(sb, 4));      /* affine x */
+    s_mul(ys, ys, s_slot(sb, 4));      /* affine y */
+    gf x, y, zero;
+    gf_set_zero(zero);
+    s_ld(x, xs); gf_cond_sel(x, zero, x, nz);
+    s_ld(y, ys); gf_cond_sel(y, zero, y, nz);
+    gf_to_words(yw, y);
+    xsign = gf_lobit(x) & 1u;
+}
+// u = (y/x)^2 (goldilocks.c:1104-1115)
+GD void s_encode_like_x448(uint32_t uw[14], sref sb) {
+    const sref xs = s_slot(sb, 6);
+    s_copy(xs, s_slot(sb, 1));         /* y survives the inversion in slot 6 */
+    const gmask_t nz = s_nonzero_or_one(s_slot(sb, 5), s_slot(sb, 0));
+    s_invert_5_to_4(sb);
+    s_mul(xs, xs, s_slot(sb, 4));
+    s_sqr(xs, xs);
+    gf u, zero;
+    gf_set_zero(zero);
+    s_ld(u, xs); gf_cond_sel(u, zero, u, nz);
+    gf_to_words(uw, u);
+}

@@ -100,3 +100,47 @@ struct SlotComb { /* goldilocks_448_precomputed_scalarmul (goldilocks.c:830-877)
         if (live) s_pt_to_abi(out + i, sb);
     }
 };
+
+struct SlotX448DerivePk { /* goldilocks.c:1117-1141 */
+    static constexpr int NSLOTS = COMB_NSLOTS;
+    uint8_t *out; const uint8_t *scalar; const fixed_tables *ft;
+    GDM void operator()(size_t i, sref sb, bool live) const {
+        uint32_t ws[14], wo[14];
+        words_load56(ws, scalar + 56 * i);
+        ws[0] &= ~3u;
+        ws[13] |= 0x80000000u; /* X_PRIVATE_BITS = 448: top byte keeps all its bits, bit 447 is set */
+        sc s, h;
+        ByteAtWords at = {ws};
+        sc_decode_long(s, at, 56);
+        sc_halve(h, s);        /* GOLDILOCKS_X448_ENCODE_RATIO = 2 */
+        s_comb_scalarmul(sb, ft->win, h);
+        s_encode_like_x448(wo, sb);
+        if (live) words_store56(out + 56 * i, wo);
+    }
+};
+struct SlotEdDerivePk { /* eddsa.c:129-144 */
+    static constexpr int NSLOTS = COMB_NSLOTS;
+    uint8_t *pk; const uint8_t *sk; const fixed_tables *ft;
+    GDM void operator()(size_t i, sref sb, bool live) const {
+        sc s, h1, h2; uint32_t w[15], sign; shake256_ctx hk;
+        ed448_secret_scalar(s, hk, sk + 57 * i);
+        sc_halve(h1, s);
+        sc_halve(h2, h1);      /* GOLDILOCKS_448_EDDSA_ENCODE_RATIO = 4 */
+        s_comb_scalarmul(sb, ft->win, h2);
+        s_encode_like_eddsa(w, sign, sb);
+        w[14] = sign << 7;
+        if (live) words_store_bytes(pk + 57 * i, 57, w);
+    }
+};
+struct SlotEdSignR { /* eddsa.c:201-205: R = encode(comb(nonce / 4)) */
+    static constexpr int NSLOTS = COMB_NSLOTS;
+    uint8_t *sig; const abi_sc *nonce4; const fixed_tables *ft;
+    GDM void operator()(size_t i, sref sb, bool live) const {
+        sc s; uint32_t w[15], sign;
+        sc_from_abi(s, nonce4 + i);
+        s_comb_scalarmul(sb, ft->win, s);
+        s_encode_like_eddsa(w, sign, sb);
+        w[14] = sign << 7;
+        if (live) words_store_bytes(sig + 114 * i, 57, w);
+    }
+};

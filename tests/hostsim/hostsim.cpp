@@ -141,9 +141,9 @@ EXPORT int32_t goldilocks_448_scalar_halve_batch(hsc *o, const hsc *a, size_t n)
 EXPORT int32_t goldilocks_448_scalar_decode_long_batch(hsc *o, const uint8_t *ser, size_t len, size_t n) { LaneScDecodeLong f = {o, ser, len}; run(f, n); return -1; }
 
 EXPORT int32_t goldilocks_x448_batch(uint8_t *o, int32_t *st, const uint8_t *base, const uint8_t *sc, size_t n) { SlotX448 f = {o, st, base, sc}; run_sm(f, n); return -1; }
-EXPORT int32_t goldilocks_x448_derive_public_key_batch(uint8_t *o, const uint8_t *sc, size_t n) { LaneX448DerivePk f = {o, sc, tables()}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_x448_derive_public_key_batch(uint8_t *o, const uint8_t *sc, size_t n) { SlotX448DerivePk f = {o, sc, tables()}; run_sm(f, n); return -1; }
 EXPORT int32_t goldilocks_shake256_hash_batch(uint8_t *o, size_t outlen, const uint8_t *in, const size_t *off, size_t n) { LaneShake256 f = {o, outlen, in, off}; run(f, n); return -1; }
-EXPORT int32_t goldilocks_ed448_derive_public_key_batch(uint8_t *pk, const uint8_t *sk, size_t n) { LaneEdDerivePk f = {pk, sk, tables()}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_ed448_derive_public_key_batch(uint8_t *pk, const uint8_t *sk, size_t n) { SlotEdDerivePk f = {pk, sk, tables()}; run_sm(f, n); return -1; }
 EXPORT int32_t goldilocks_ed448_sign_batch(uint8_t *sig, const uint8_t *sk, const uint8_t *pk, const uint8_t *msg, const size_t *off,
                                            uint8_t prehashed, const uint8_t *ctx, uint8_t ctx_len, size_t n) {
     std::vector<abi_sc> secret(n), nonce(n), nonce4(n);
@@ -152,8 +152,8 @@ EXPORT int32_t goldilocks_ed448_sign_batch(uint8_t *sig, const uint8_t *sk, cons
     run(f0, n);
     LaneEdSignNonce f1 = {nonce.data(), nonce4.data(), seed.data(), msg, off, prehashed, ctx, ctx_len};
     run(f1, n);
-    LaneEdSignR f2 = {sig, nonce4.data(), tables()};
-    run(f2, n);
+    SlotEdSignR f2 = {sig, nonce4.data(), tables()};
+    run_sm(f2, n);
     LaneEdSignFinish f3 = {sig, secret.data(), nonce.data(), pk, msg, off, prehashed, ctx, ctx_len};
     run(f3, n);
     return -1;

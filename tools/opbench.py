@@ -22,8 +22,26 @@ def main():
     fns = {"comb": lambda: eng.precomputed_scalarmul(pts3, sc), "x448": lambda: eng.x448(o56, st, u, k), "gf_mul": lambda: eng.gf_mul(o56, u, k),
            "point_add": lambda: eng.point_add(pts3, pts, pts2), "point_double": lambda: eng.point_double(pts3, pts),
            "decode": lambda: eng.point_decode(pts3, st, ser), "encode": lambda: eng.point_encode(o56, pts)}
+    def kernel_ms(fn):
+        """per-kernel CUDA-event times of one host-API call (library profile hooks)"""
+        import ctypes as C
+        lib.lib.goldilocks_b200_profile(C.c_int(1)); fn(); lib.lib.goldilocks_b200_profile(C.c_int(0))
+        names = C.create_string_buffer(64 * 256); ms = (C.c_float * 256)()
+        lib.lib.goldilocks_b200_profile_read.restype = C.c_size_t
+        cnt = lib.lib.goldilocks_b200_profile_read(names, ms, C.c_size_t(256))
+        return [(names.raw[64 * k:64 * k + 64].split(b"\0")[0].decode(), round(ms[k], 3)) for k in range(cnt)]
+    if "sign" in a.ops.split(","):
+        m = min(n, 1 << 18)
+        sk = stream_bytes("opbench/sk", m * 57).reshape(m, 57)
+        arena = stream_bytes("opbench/msg", m * 32); off = np.arange(m + 1, dtype=np.uint64) * 32
+        pk = lib.ed448_derive_public_key(sk)
+        print("derive_pk n=%d kernels %s" % (m, kernel_ms(lambda: lib.ed448_derive_public_key(sk))))
+        ks = kernel_ms(lambda: lib.ed448_sign(sk, pk, (arena, off)))
+        tot = sum(t for _, t in ks)
+        print("sign      n=%d kernels %s  -> %.2f M signatures/s (kernels only)" % (m, ks, m / tot / 1e3))
+        a.ops = ",".join(o for o in a.ops.split(",") if o != "sign")
     peak = json.load(open(os.path.join(ROOT, "profiles", "r01_imad_peak.json")))["imad_wide_u32_gmac_s"]
-    for op in a.ops.split(","):
+    for op in [o for o in a.ops.split(",") if o]:
         f = fns[op]; f(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

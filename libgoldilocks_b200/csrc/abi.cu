@@ -17,7 +17,6 @@
 
 // kernels live in k_*.cu
 LANES_PLAIN(DECLARE_PLAIN)
-LANES_SLOT(DECLARE_SLOT)
 LANES_SM(DECLARE_SM)
 LANES_SMP(DECLARE_SMP)
 
@@ -117,29 +116,6 @@ bool launch_smp(Ctx &c, const F &f, size_t n, int grid, cudaStream_t s) {
     if (prof) prof_end(typeid(F).name(), s, a, b);
     return true;
 }
-// grid = SMs x resident blocks of this kernel, so every thread owns exactly one scratch slot
-template <class F>
-bool slot_grid(Ctx &c, int *grid) {
-    int occ = 0;
-    CU(lanes_slot_occupancy<F>(&occ));
-    if (occ < 1) occ = 1;
-    *grid = c.sms * occ;
-    return true;
-}
-template <class F>
-bool launch_slot(Ctx &c, const F &f, size_t n, int grid, cudaStream_t s) {
-    if (n == 0) return true;
-    size_t need_blocks = (n + BLOCK - 1) / BLOCK;
-    if ((size_t)grid > need_blocks) grid = (int)need_blocks;
-    g_launches++;
-    cudaEvent_t a = nullptr, b = nullptr;
-    const bool prof = g_prof_on.load() != 0;
-    if (prof) a = prof_begin(typeid(F).name(), s, &b);
-    CU(launch_lanes_slot<F>(f, n, grid, s));
-    if (prof) prof_end(typeid(F).name(), s, a, b);
-    return true;
-}
-
 bool ctx_init(Ctx &c, int dev) {
     if (c.ready) return true;
     if (c.failed) { g_err = "device initialisation failed earlier"; return false; }
@@ -219,9 +195,9 @@ struct Call {
         cudaError_t e = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream);
         if (e != cudaSuccess) ok = fail("cudaMemcpyAsync(D2H)", e);
     }
-    pniels *slots(size_t nthreads, size_t pniels_per_thread) {
+    uint4 *slots(size_t nthreads, size_t tables_per_thread) { /* per-thread window tables (wtab, slot_algos.cuh) */
         if (!ok) return nullptr;
-        size_t bytes = nthreads * pniels_per_thread * sizeof(pniels);
+        size_t bytes = nthreads * tables_per_thread * WTAB_QUADS_PER_LANE * sizeof(uint4);
         if (bytes > c->slot_cap) {
             if (c->slot_scratch) cudaFree(c->slot_scratch);
             c->slot_scratch = nullptr; c->slot_cap = 0;
@@ -229,14 +205,12 @@ struct Call {
             if (e != cudaSuccess) { ok = fail("cudaMalloc(slot scratch)", e); return nullptr; }
             c->slot_cap = bytes;
         }
-        return (pniels *)c->slot_scratch;
+        return (uint4 *)c->slot_scratch;
     }
     template <class F> void run(const F &f, size_t n) { if (ok) ok = launch(*c, f, n, c->stream); }
     template <class F> void run_sm(const F &f, size_t n) { if (ok) ok = launch_slots(*c, f, n, c->stream); }
-    template <class F> int grid_for() { int g = 1; if (ok) ok = slot_grid<F>(*c, &g); return g; }
     template <class F> int smp_grid_for() { int g = 1; if (ok) ok = smp_grid<F>(*c, &g); return g; }
     template <class F> void run_smp(const F &f, size_t n, int grid) { if (ok) ok = launch_smp(*c, f, n, grid, c->stream); }
-    template <class F> void run_slot(const F &f, size_t n, int grid) { if (ok) ok = launch_slot(*c, f, n, grid, c->stream); }
     goldilocks_error_t finish() {
         if (ok) {
             cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -487,18 +461,18 @@ goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(hpt *out, const go
 }
 goldilocks_error_t goldilocks_448_point_scalarmul_batch(hpt *out, const hpt *base, const hsc *scalar, size_t n) {
     Call k;
-    int grid = k.grid_for<LaneScalarmul>();
-    LaneScalarmul f = {k.out<abi_pt>(n), k.in(P(base), n), k.in(S(scalar), n), k.slots((size_t)grid * BLOCK, WINDOW_NTABLE)};
-    k.run_slot(f, n, grid);
+    int grid = k.smp_grid_for<SlotScalarmul>();
+    SlotScalarmul f = {k.out<abi_pt>(n), k.in(P(base), n), k.in(S(scalar), n), k.slots((size_t)grid * SLOT_BLOCK, 1)};
+    k.run_smp(f, n, grid);
     k.fetch(P(out), f.out, n);
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_double_scalarmul_batch(hpt *out, const hpt *base1, const hsc *scalar1, const hpt *base2, const hsc *scalar2, size_t n) {
     Call k;
-    int grid = k.grid_for<LaneDoubleScalarmul>();
-    LaneDoubleScalarmul f = {k.out<abi_pt>(n), k.in(P(base1), n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n),
-                             k.slots((size_t)grid * BLOCK, 2 * WINDOW_NTABLE)};
-    k.run_slot(f, n, grid);
+    int grid = k.smp_grid_for<SlotDoubleScalarmul>();
+    SlotDoubleScalarmul f = {k.out<abi_pt>(n), k.in(P(base1), n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n),
+                             k.slots((size_t)grid * SLOT_BLOCK, 2), (size_t)grid * SLOT_BLOCK};
+    k.run_smp(f, n, grid);
     k.fetch(P(out), f.out, n);
     return k.finish();
 }
@@ -506,7 +480,7 @@ goldilocks_error_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *ou
     Call k;
     int grid = k.smp_grid_for<SlotBaseDoubleScalarmul>();
     SlotBaseDoubleScalarmul f = {k.out<abi_pt>(n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n), k.ok ? k.c->wide : nullptr,
-                                 k.slots((size_t)grid * SLOT_BLOCK, BDSM_TABLE)};
+                                 k.slots((size_t)grid * SLOT_BLOCK, 1)};
     k.run_smp(f, n, grid);
     k.fetch(P(out), f.out, n);
     return k.finish();
@@ -604,7 +578,7 @@ size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
     return al(2 * n * sizeof(abi_pt)) + al(2 * n * sizeof(int32_t)) + 2 * al(n * sizeof(abi_sc));
 }
 static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off, uint8_t prehashed,
-                       const uint8_t *ctx, uint8_t ctx_len, size_t n, void *scratch, pniels *slots, int grid, cudaStream_t s) {
+                       const uint8_t *ctx, uint8_t ctx_len, size_t n, void *scratch, uint4 *slots, int grid, cudaStream_t s) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     char *p = (char *)scratch;
     abi_pt *pts = (abi_pt *)p; p += al(2 * n * sizeof(abi_pt));
@@ -629,7 +603,7 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
     int32_t *dst = k.out<int32_t>(n);
     void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(n));
     int grid = k.smp_grid_for<SlotEdVerifyFinish>();
-    pniels *slots = k.slots((size_t)grid * SLOT_BLOCK, BDSM_TABLE);
+    uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
     if (k.ok) k.ok = verify_dev(*k.c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, scratch, slots, grid, k.c->stream);
     k.fetch((int32_t *)status, dst, n);
     return k.finish();
@@ -643,14 +617,14 @@ goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status,
     std::lock_guard<std::mutex> g(c->mu); /* the per-thread table slots are shared per device */
     int grid = 1;
     if (!smp_grid<SlotEdVerifyFinish>(*c, &grid)) return GOLDILOCKS_FAILURE;
-    size_t bytes = (size_t)grid * SLOT_BLOCK * BDSM_TABLE * sizeof(pniels);
+    size_t bytes = (size_t)grid * SLOT_BLOCK * WTAB_QUADS_PER_LANE * sizeof(uint4);
     if (bytes > c->slot_cap) {
         if (c->slot_scratch) cudaFree(c->slot_scratch);
         c->slot_scratch = nullptr; c->slot_cap = 0;
         if (cudaMalloc(&c->slot_scratch, bytes) != cudaSuccess) { g_err = "cudaMalloc(slot scratch)"; return GOLDILOCKS_FAILURE; }
         c->slot_cap = bytes;
     }
-    return verify_dev(*c, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, scratch, (pniels *)c->slot_scratch, grid, as_stream(stream))
+    return verify_dev(*c, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, scratch, (uint4 *)c->slot_scratch, grid, as_stream(stream))
                ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
 }
 goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream) {

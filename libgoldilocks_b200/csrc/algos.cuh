@@ -41,61 +41,6 @@ struct fixed_tables {
 };
 
 // ---------------------------------------------------------------------------------------------
-// X448 (RFC 7748) -- reference goldilocks.c:1006-1076.  5M + 4S + 1w per bit, constant time.
-// scalar/base are the 56-byte strings as 14 little-endian words.  Returns the nonzero mask
-// (the reference returns FAILURE iff the shared secret is zero) and always writes `out`.
-// ---------------------------------------------------------------------------------------------
-GD gmask_t x448_ladder(uint32_t out[14], const uint32_t base[14], const uint32_t scalar[14]) {
-    gf x1, x2, z2, x3, z3, t1, t2;
-    (void)gf_from_words(x1, base); /* u >= p is accepted mod p, like the reference's ignored result */
-    gf_set_ui(x2, 1);
-    gf_set_zero(z2);
-    gf_copy(x3, x1);
-    gf_set_ui(z3, 1);
-    gmask_t swap = 0;
-#pragma unroll 1
-    for (int w = 13; w >= 0; w--) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int i = 0; i < 14; i++) word |= (i == w) ? scalar[i] : 0u;
-        if (w == 0) word &= ~3u;            /* clear the cofactor bits (low 2 bits of byte 0) */
-        if (w == 13) word |= 0x80000000u;   /* force bit 447 */
-#pragma unroll 1
-        for (int b = 31; b >= 0; b--) {
-            gmask_t k_t = (gmask_t)(-(int32_t)((word >> b) & 1u));
-            swap ^= k_t;
-            gf_cond_swap(x2, x3, swap);
-            gf_cond_swap(z2, z3, swap);
-            swap = k_t;
-            gf_add_nr(t1, x2, z2);   /* A  */
-            gf_sub(t2, x2, z2);      /* B  */
-            gf_sub(z2, x3, z3);      /* D  */
-            gf_mul(x2, t1, z2);      /* DA */
-            gf_add_nr(z2, z3, x3);   /* C  */
-            gf_mul(x3, t2, z2);      /* CB */
-            gf_sub(z3, x2, x3);
-            gf_sqr(z2, z3);
-            gf_mul(z3, x1, z2);      /* x1 (DA-CB)^2 */
-            gf_add_nr(z2, x2, x3);
-            gf_sqr(x3, z2);          /* (DA+CB)^2 */
-            gf_sqr(z2, t1);          /* AA */
-            gf_sqr(t1, t2);          /* BB */
-            gf_mul(x2, z2, t1);
-            gf_sub(t2, z2, t1);      /* E  */
-            gf_mulw(t1, t2, (uint32_t)(-GOLD_EDWARDS_D)); /* a24 * E */
-            gf_add_nr(t1, t1, z2);
-            gf_mul(z2, t2, t1);
-        }
-    }
-    gf_cond_swap(x2, x3, swap);
-    gf_cond_swap(z2, z3, swap);
-    gf_invert(z2, z2);
-    gf_mul(x1, x2, z2);
-    gf_to_words(out, x1);
-    return ~gf_is_zero(x1);
-}
-
-// ---------------------------------------------------------------------------------------------
 // Constant-time lookup: scan all `n` niels of a row, keep the one whose index matches.
 // ---------------------------------------------------------------------------------------------
 GD void niels_lookup_ct(niels &out, const niels *row, int n, uint32_t idx) {
@@ -261,59 +206,7 @@ GD void window_double_scalarmul(pt &a, const pt &b, const sc &scalarb, const pt 
 // doublings + 90 + 30 additions, against the reference's expected 444 + 75 + 56.  Indices are
 // public, so lookups are plain loads.
 // ---------------------------------------------------------------------------------------------
-GD void load_pniels(pniels &o, const pniels *src) {
-    gf_ld<false>(o.n.a, &src->n.a); gf_ld<false>(o.n.b, &src->n.b); gf_ld<false>(o.n.c, &src->n.c); gf_ld<false>(o.z, &src->z);
-}
-GD void load_niels(niels &o, const niels *src) {
-    gf_ld<true>(o.a, &src->a); gf_ld<true>(o.b, &src->b); gf_ld<true>(o.c, &src->c);
-}
-GD void base_double_scalarmul_uniform(pt &combo, const sc &scalar1, const pt &base2, const sc &scalar2,
-                                      const niels *wide_base, pniels *multiples) {
-    sc s1x, s2x;
-    sc_recode_signed(s1x, scalar1);   /* both recodings cover 450 = 90 x 5 = 30 x 15 bits */
-    sc_recode_signed(s2x, scalar2);
-    prepare_fixed_window(multiples, base2, WINDOW_NTABLE);
-    pt tmp;
-    pniels pn;
-    niels ni;
-#pragma unroll 1
-    for (int k = 89; k >= 0; k--) {
-        const int i = k * WINDOW_BITS;
-        const bool fixed_here = (k % 3) == 0;           /* 15-bit fixed-base digit starts at this bit */
-        if (k != 89) { /* doublings first: the table row is only live across the addition */
-#pragma unroll 1
-            for (int j = 0; j < WINDOW_BITS - 1; j++) pt_double(tmp, tmp, true);
-            pt_double(tmp, tmp, false);
-        }
-        uint32_t bits2 = sc_window5(s2x, i);
-        const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
-        bits2 ^= inv2;
-        load_pniels(pn, multiples + (bits2 & (WINDOW_NTABLE - 1)));
-        niels_cond_neg(pn.n, inv2);
-        if (k == 89) pniels_to_pt(tmp, pn);
-        else pt_addsub_pniels<false>(tmp, pn, !fixed_here && k != 0);
-        if (fixed_here) {
-            uint32_t bits1 = sc_bits(s1x, i, WIDE_BITS);
-            const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
-            bits1 ^= inv1;
-            load_niels(ni, wide_base + (bits1 & (WIDE_ENTRIES - 1)));
-            niels_cond_neg(ni, inv1);
-            pt_addsub_niels<false>(tmp, ni, k != 0);
-        }
-    }
-    /* Reference quirk kept for bit-exact parity: when scalar2 == 0 its wNAF is empty and
-     * goldilocks.c:1281-1284 returns the identity WITHOUT adding scalar1*B. */
-    uint32_t any2 = 0;
-#pragma unroll
-    for (int k = 0; k < SC_WORDS; k++) any2 |= scalar2.w[k];
-    pt ident;
-    pt_set_identity(ident);
-    const gmask_t z2 = (gmask_t)(((uint64_t)any2 - 1) >> 32);
-    gf_cond_sel(combo.x, tmp.x, ident.x, z2);
-    gf_cond_sel(combo.y, tmp.y, ident.y, z2);
-    gf_cond_sel(combo.z, tmp.z, ident.z, z2);
-    gf_cond_sel(combo.t, tmp.t, ident.t, z2);
-}
+// Implementation: s_base_double_scalarmul (slot_algos.cuh).
 
 // ---------------------------------------------------------------------------------------------
 // Table construction (runs once per device, a handful of lanes).

@@ -186,45 +186,8 @@ struct LaneEncodeX448 {
 };
 
 // ---- scalar multiplications ------------------------------------------------------------------
-struct LaneComb { /* goldilocks_448_precomputed_scalarmul */
-    abi_pt *out; const abi_sc *scalar; const fixed_tables *ft;
-    GDM void operator()(size_t i) const {
-        sc s; pt p;
-        sc_from_abi(s, scalar + i);
-        comb_scalarmul(p, ft->comb, s);
-        pt_to_abi(out + i, p);
-    }
-};
-struct LaneScalarmul { /* goldilocks_448_point_scalarmul; `slot` indexes per-thread scratch */
-    abi_pt *out; const abi_pt *base; const abi_sc *scalar; pniels *scratch;
-    GDM void operator()(size_t i, size_t slot) const {
-        sc s; pt p, b;
-        sc_from_abi(s, scalar + i);
-        pt_from_abi(b, base + i);
-        window_scalarmul(p, b, s, scratch + WINDOW_NTABLE * slot);
-        pt_to_abi(out + i, p);
-    }
-};
-struct LaneDoubleScalarmul { /* goldilocks_448_point_double_scalarmul */
-    abi_pt *out; const abi_pt *base1; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; pniels *scratch;
-    GDM void operator()(size_t i, size_t slot) const {
-        sc s1, s2; pt p, b1, b2;
-        sc_from_abi(s1, scalar1 + i); sc_from_abi(s2, scalar2 + i);
-        pt_from_abi(b1, base1 + i); pt_from_abi(b2, base2 + i);
-        window_double_scalarmul(p, b1, s1, b2, s2, scratch + 2 * WINDOW_NTABLE * slot, scratch + 2 * WINDOW_NTABLE * slot + WINDOW_NTABLE);
-        pt_to_abi(out + i, p);
-    }
-};
-struct LaneBaseDoubleScalarmul { /* goldilocks_448_base_double_scalarmul_non_secret */
-    abi_pt *out; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; const niels *wide; pniels *scratch;
-    GDM void operator()(size_t i, size_t slot) const {
-        sc s1, s2; pt p, b2;
-        sc_from_abi(s1, scalar1 + i); sc_from_abi(s2, scalar2 + i);
-        pt_from_abi(b2, base2 + i);
-        base_double_scalarmul_uniform(p, s1, b2, s2, wide, scratch + WINDOW_NTABLE * slot);
-        pt_to_abi(out + i, p);
-    }
-};
+// goldilocks_448_precomputed_scalarmul / point_scalarmul / point_double_scalarmul /
+// base_double_scalarmul_non_secret: SlotComb, SlotScalarmul, SlotDoubleScalarmul, SlotBaseDoubleScalarmul (slot_lanes.cuh)
 
 // ---- scalars mod q ---------------------------------------------------------------------------
 enum { SCOP_ADD, SCOP_SUB, SCOP_MUL, SCOP_HALVE };
@@ -253,35 +216,7 @@ struct LaneScDecodeLong {
     }
 };
 
-// ---- X448 --------------------------------------------------------------------------------------
-struct LaneX448 {
-    uint8_t *out; int32_t *status; const uint8_t *base, *scalar;
-    GDM void operator()(size_t i) const {
-        uint32_t wb[14], ws[14], wo[14];
-        words_load56(wb, base + 56 * i);
-        words_load56(ws, scalar + 56 * i);
-        gmask_t nz = x448_ladder(wo, wb, ws);
-        words_store56(out + 56 * i, wo);
-        status[i] = ST_OK(nz);
-    }
-};
 struct ByteAtWords { const uint32_t *w; GDM uint8_t operator()(int k) const { return (uint8_t)(w[k >> 2] >> (8 * (k & 3))); } };
-struct LaneX448DerivePk { /* goldilocks.c:1117-1141 */
-    uint8_t *out; const uint8_t *scalar; const fixed_tables *ft;
-    GDM void operator()(size_t i) const {
-        uint32_t ws[14], wo[14];
-        words_load56(ws, scalar + 56 * i);
-        ws[0] &= ~3u;
-        ws[13] |= 0x80000000u; /* X_PRIVATE_BITS = 448: top byte keeps all its bits, bit 447 is set */
-        sc s, h; pt p;
-        ByteAtWords at = {ws};
-        sc_decode_long(s, at, 56);
-        sc_halve(h, s);        /* GOLDILOCKS_X448_ENCODE_RATIO = 2 */
-        comb_scalarmul(p, ft->comb, h);
-        pt_encode_like_x448(wo, p);
-        words_store56(out + 56 * i, wo);
-    }
-};
 
 // ---- SHAKE256 one-shot ---------------------------------------------------------------------------
 struct LaneShake256 {
@@ -312,19 +247,6 @@ GD void ed448_secret_scalar(sc &secret, shake256_ctx &h, const uint8_t *sk) {
     ByteAtWords at = {w};
     sc_decode_long(secret, at, 57);
 }
-struct LaneEdDerivePk { /* eddsa.c:129-144 */
-    uint8_t *pk; const uint8_t *sk; const fixed_tables *ft;
-    GDM void operator()(size_t i) const {
-        sc s, h1, h2; pt p; uint32_t w[15], sign; shake256_ctx hk;
-        ed448_secret_scalar(s, hk, sk + 57 * i);
-        sc_halve(h1, s);
-        sc_halve(h2, h1);      /* GOLDILOCKS_448_EDDSA_ENCODE_RATIO = 4 */
-        comb_scalarmul(p, ft->comb, h2);
-        pt_encode_like_eddsa(w, sign, p);
-        w[14] = sign << 7;
-        words_store_bytes(pk + 57 * i, 57, w);
-    }
-};
 struct LaneEdSecretScalar { /* goldilocks_ed448_derive_secret_scalar, eddsa.c:98-127 */
     abi_sc *out; const uint8_t *sk;
     GDM void operator()(size_t i) const {
@@ -340,7 +262,7 @@ struct LaneEdSecretScalar { /* goldilocks_ed448_derive_secret_scalar, eddsa.c:98
 // back to back with the seed handed over in local memory; RFC 8032 vectors guard this on the GPU):
 //   0) expand: secret scalar and seed from SHAKE256(sk)     (eddsa.c:161-171)
 //   1) nonce: nonce scalar, nonce/4                          (eddsa.c:173-199)
-//   2) R = encode(comb(nonce/4))                            (eddsa.c:201-205)
+//   2) R = encode(comb(nonce/4))                            (eddsa.c:201-205; SlotEdSignR, slot_lanes.cuh)
 //   3) S = challenge * secret + nonce ; sig = R || S || 0   (eddsa.c:207-229)
 struct LaneEdSignExpand { /* eddsa.c:161-171: SHAKE256(sk) -> clamped secret scalar || 57-byte seed (device scratch) */
     abi_sc *secret; uint8_t *seed; const uint8_t *sk;
@@ -371,17 +293,6 @@ struct LaneEdSignNonce { /* eddsa.c:173-199: nonce = SHAKE256(dom || seed || msg
         sc_halve(h2, h1);
         sc_to_abi(nonce + i, n);
         sc_to_abi(nonce4 + i, h2);
-    }
-};
-struct LaneEdSignR {
-    uint8_t *sig; const abi_sc *nonce4; const fixed_tables *ft;
-    GDM void operator()(size_t i) const {
-        sc s; pt p; uint32_t w[15], sign;
-        sc_from_abi(s, nonce4 + i);
-        comb_scalarmul(p, ft->comb, s);
-        pt_encode_like_eddsa(w, sign, p);
-        w[14] = sign << 7;
-        words_store_bytes(sig + 114 * i, 57, w);
     }
 };
 GD void ed448_challenge(sc &c, const uint8_t *r57, const uint8_t *pk57, const uint8_t *msg, size_t lo, size_t hi,
@@ -418,6 +329,7 @@ struct LaneEdSignFinish {
 //   1) decode A and R (2n lanes, one isr each)            -> points + ok flags
 //   2) challenge = -SHAKE256(dom || R || A || M) mod q, response = S mod q
 //   3) combo = response*B + challenge*A ; accept iff combo == R (mod 2-torsion) and both decodes succeeded
+//      (SlotEdVerifyFinish, slot_lanes.cuh)
 struct LaneEdVerifyDecode { /* lane 2i = public key i, lane 2i+1 = R of signature i */
     abi_pt *pts; int32_t *ok; const uint8_t *sig, *pk;
     GDM void operator()(size_t j) const {
@@ -449,20 +361,6 @@ struct LaneEdVerifyScalars {
         /* GOLDILOCKS_448_EDDSA_DECODE_RATIO = 1: no doubling of the response */
         sc_to_abi(challenge + i, nc);
         sc_to_abi(response + i, r);
-    }
-};
-struct LaneEdVerifyFinish {
-    int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; pniels *scratch;
-    GDM void operator()(size_t i, size_t slot) const {
-        sc c, r; pt a, rp, combo;
-        sc_from_abi(c, challenge + i);
-        sc_from_abi(r, response + i);
-        pt_from_abi(a, pts + 2 * i);
-        base_double_scalarmul_uniform(combo, r, a, c, wide, scratch + WINDOW_NTABLE * slot);
-        pt_from_abi(rp, pts + 2 * i + 1);
-        gmask_t good = pt_eq(combo, rp);
-        good &= (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1];
-        status[i] = ST_OK(good);
     }
 };
 struct LaneBuildWide { /* verification table, WIDE_LANES lanes */

@@ -19,30 +19,11 @@ __global__ void __launch_bounds__(BLOCK, lane_min_blocks<F>::value) k_lanes(F f,
     const size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     if (i < n) f(i);
 }
-// Persistent grid-stride shape for functors that own a per-thread scratch slot in HBM.
-template <class F>
-__global__ void __launch_bounds__(BLOCK) k_lanes_slot(F f, size_t n) {
-    const size_t slot = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * BLOCK;
-    for (size_t i = slot; i < n; i += stride) f(i, slot);
-}
-
 template <class F>
 cudaError_t launch_lanes(const F &f, size_t n, cudaStream_t s) {
     k_lanes<F><<<(unsigned)((n + BLOCK - 1) / BLOCK), BLOCK, 0, s>>>(f, n);
     return cudaGetLastError();
 }
-template <class F>
-cudaError_t launch_lanes_slot(const F &f, size_t n, int grid, cudaStream_t s) {
-    k_lanes_slot<F><<<grid, BLOCK, 0, s>>>(f, n);
-    return cudaGetLastError();
-}
-// resident blocks per SM of the slot kernel of F
-template <class F>
-cudaError_t lanes_slot_occupancy(int *occ) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_lanes_slot<F>, BLOCK, 0);
-}
-
 // Slot-machine kernels (slots.cuh): F::NSLOTS x 64 B of dynamic shared memory per lane.
 // Resident blocks per SM: measured choice per functor (registers <= 65536 / (128 * blocks)).
 template <> struct slot_min_blocks<SlotX448> { static constexpr int value = 4; };
@@ -50,6 +31,8 @@ template <> struct slot_min_blocks<SlotComb> { static constexpr int value = 3; }
 template <> struct slot_min_blocks<SlotX448DerivePk> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotEdDerivePk> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotEdSignR> { static constexpr int value = 3; };
+template <> struct slot_min_blocks<SlotScalarmul> { static constexpr int value = 3; };
+template <> struct slot_min_blocks<SlotDoubleScalarmul> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotBaseDoubleScalarmul> { static constexpr int value = 4; };
 template <class F>
@@ -98,13 +81,11 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
     X(LaneScDecodeLong) X(LaneShake256)                                                             \
     X(LaneEdSecretScalar) X(LaneEdSignExpand) X(LaneEdSignNonce) X(LaneEdSignFinish)   \
     X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneBuildTables) X(LaneBuildWide)
-#define LANES_SLOT(X)                                                                               \
-    X(LaneScalarmul) X(LaneDoubleScalarmul)
 
 #define LANES_SM(X) X(SlotX448) X(SlotComb) X(SlotX448DerivePk) X(SlotEdDerivePk) X(SlotEdSignR)
 #define INSTANTIATE_SM(F) template cudaError_t launch_sm<F>(const F &, size_t, cudaStream_t);
 #define DECLARE_SM(F) extern INSTANTIATE_SM(F)
-#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotBaseDoubleScalarmul)
+#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul)
 #define INSTANTIATE_SMP(F)                                                                          \
     template cudaError_t sm_configure<F>(int *);                                                    \
     template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t);
@@ -112,10 +93,4 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
     extern template cudaError_t sm_configure<F>(int *);                                             \
     extern template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t);
 #define INSTANTIATE_PLAIN(F) template cudaError_t launch_lanes<F>(const F &, size_t, cudaStream_t);
-#define INSTANTIATE_SLOT(F)                                                                         \
-    template cudaError_t launch_lanes_slot<F>(const F &, size_t, int, cudaStream_t);                \
-    template cudaError_t lanes_slot_occupancy<F>(int *);
 #define DECLARE_PLAIN(F) extern INSTANTIATE_PLAIN(F)
-#define DECLARE_SLOT(F)                                                                             \
-    extern template cudaError_t launch_lanes_slot<F>(const F &, size_t, int, cudaStream_t);         \
-    extern template cudaError_t lanes_slot_occupancy<F>(int *);

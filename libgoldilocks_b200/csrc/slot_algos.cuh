@@ -149,20 +149,36 @@ GD void s_pt_double(const spt &p, const swk &w, bool before_double) {
     if (!before_double) s_mul(p.t, w.t2, p.t);
 }
 
+// A lane's window table of pniels in global memory (coordinate order a, b, c, z), in one of the two
+// layouts of slots.cuh: QS = 1 lane-contiguous (256 B per entry; public-index gathers of verification),
+// QS = 32 warp-interleaved (constant-time scans are fully coalesced).
+template <int QS>
+struct wtab {
+    uint4 *base; /* this lane's quad 0 of coordinate 0 of entry 0 */
+    GDM uint4 *coord(int e, int c) const { return base + (size_t)(e * 4 + c) * 4 * QS; }
+    static constexpr int ESTRIDE = 16 * QS; /* quads between the same coordinate of consecutive entries */
+};
+#define WTAB_ENTRIES 17 /* 16 odd multiples + pniels(2P) while the table is being built */
+#define WTAB_QUADS_PER_LANE (WTAB_ENTRIES * 16)
+template <int QS>
+GD wtab<QS> wtab_of(uint4 *scratch, size_t thread) { /* thread = global thread index (device) or worker index (host) */
+    wtab<QS> t;
+    if (QS == 1) t.base = scratch + thread * WTAB_QUADS_PER_LANE;
+    else t.base = scratch + (thread / 32) * (size_t)(WTAB_QUADS_PER_LANE * 32) + (thread % 32);
+    return t;
+}
+
 // p += (+-) e for an affine niels e = (a, b, c) in global memory.  7M (6M without T).
-//   swap_ab : use (b, a) instead of (a, b)       \  a negated entry is swap_ab = neg_c = all-ones
+//   swap_ab : use (b, a) instead of (a, b)       \\  a negated entry is swap_ab = neg_c = all-ones
 //   neg_c   : the stored c is minus the real one  /  (goldilocks.c:271-278 cond_neg_niels)
 // (goldilocks.c:315-359 add_niels_to_pt / sub_niels_from_pt)
-GD void s_pt_add_niels_g(const spt &p, const swk &w, const gf *ea, const gf *eb, const gf *ec, gmask_t swap_ab, gmask_t neg_c, bool before_double) {
-#if defined(__CUDA_ARCH__)
-    const gf *pa = swap_ab ? eb : ea, *pb = swap_ab ? ea : eb; /* per-lane select of two addresses: no divergence */
-#else
-    const gf *pa = swap_ab ? eb : ea, *pb = swap_ab ? ea : eb;
-#endif
+template <int QS>
+GD void s_pt_add_niels_g(const spt &p, const swk &w, const uint4 *ea, const uint4 *eb, const uint4 *ec, gmask_t swap_ab, gmask_t neg_c, bool before_double) {
+    const uint4 *pa = swap_ab ? eb : ea, *pb = swap_ab ? ea : eb; /* per-lane select of two addresses: no divergence */
     s_addsub(w.t1, w.t0, p.y, p.x);    /* y+x ; y-x */
-    s_mulg(w.t0, w.t0, pa);            /* a  = e.a (y-x) */
-    s_mulg(w.t1, w.t1, pb);            /* dy = e.b (y+x) */
-    s_mulg(p.x, p.t, ec);              /* x  = e.c t */
+    s_mulg<QS>(w.t0, w.t0, pa);        /* a  = e.a (y-x) */
+    s_mulg<QS>(w.t1, w.t1, pb);        /* dy = e.b (y+x) */
+    s_mulg<QS>(p.x, p.t, ec);          /* x  = e.c t */
     s_addsub(w.t2, w.t1, w.t1, w.t0);  /* c = dy + a ; b = dy - a */
     s_addsub(w.t0, p.y, p.z, p.x);     /* v = z + x ; u = z - x */
     s_mul(p.z, w.t0, p.y);             /* z = u v */
@@ -170,53 +186,60 @@ GD void s_pt_add_niels_g(const spt &p, const swk &w, const gf *ea, const gf *eb,
     s_mul(p.y, s_sel(w.t0, p.y, neg_c), w.t2);   /* y = (neg ? u : v) c */
     if (!before_double) s_mul(p.t, w.t1, w.t2);  /* t = b c */
 }
-// projective niels in global memory: z first (goldilocks.c:361-380)
-GD void s_pt_add_pniels_g(const spt &p, const swk &w, const pniels *e, gmask_t swap_ab, gmask_t neg_c, bool before_double) {
-    s_mulg(p.z, p.z, &e->z);
-    s_pt_add_niels_g(p, w, &e->n.a, &e->n.b, &e->n.c, swap_ab, neg_c, before_double);
+// entry e of a window table: z first (goldilocks.c:361-380)
+template <int QS>
+GD void s_pt_add_pniels_g(const spt &p, const swk &w, const wtab<QS> &t, int e, gmask_t swap_ab, gmask_t neg_c, bool before_double) {
+    s_mulg<QS>(p.z, p.z, t.coord(e, 3));
+    s_pt_add_niels_g<QS>(p, w, t.coord(e, 0), t.coord(e, 1), t.coord(e, 2), swap_ab, neg_c, before_double);
 }
-// dst = pniels(p) with c stored NEGATED (c' = +2*39082*t = -(2 d' t), saves a negation per entry;
+// table[e] = pniels(p) with c stored NEGATED (c' = +2*39082*t = -(2 d' t), saves a negation per entry;
 // readers pass neg_c = ~sign).  a TIGHT, b and z LOOSE (they only ever feed multiplications).
 // (goldilocks.c:280-288 pt_to_pniels)
-GD void s_pt_to_pniels_negc_g(pniels *dst, const spt &p, const swk &w) {
+template <int QS>
+GD void s_pt_to_pniels_negc_g(const wtab<QS> &t, int e, const spt &p, const swk &w) {
     s_addsub(w.t1, w.t0, p.y, p.x);
-    s_stg(&dst->n.a, w.t0);
-    s_stg(&dst->n.b, w.t1);
+    s_stg<QS>(t.coord(e, 0), w.t0);
+    s_stg<QS>(t.coord(e, 1), w.t1);
     s_mulw(w.t0, p.t, (uint32_t)(-2 * GOLD_TWISTED_D));
-    s_stg(&dst->n.c, w.t0);
+    s_stg<QS>(t.coord(e, 2), w.t0);
     s_add(w.t0, p.z, p.z);
-    s_stg(&dst->z, w.t0);
+    s_stg<QS>(t.coord(e, 3), w.t0);
+}
+// table[0..15] = odd multiples 1P..31P of the point in slots 0..3; table[16] is scratch.  Clobbers the
+// point: P, then 2P + P, then += 2P.  (goldilocks.c:382-403 prepare_fixed_window)
+template <int QS>
+GD void s_prepare_fixed_window(const spt &p, const swk &w, const wtab<QS> &t) {
+    s_pt_to_pniels_negc_g<QS>(t, 0, p, w);
+    s_pt_double(p, w, false);
+    s_pt_to_pniels_negc_g<QS>(t, 16, p, w);
+    s_pt_add_pniels_g<QS>(p, w, t, 0, 0, ~0u, false);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 1; i < WINDOW_NTABLE; i++) {
+        s_pt_to_pniels_negc_g<QS>(t, i, p, w);
+        if (i != WINDOW_NTABLE - 1) s_pt_add_pniels_g<QS>(p, w, t, 16, 0, ~0u, false);
+    }
+}
+GD void s_pt_set_identity(const spt &p) {
+    gf v;
+    gf_set_zero(v); s_st(p.x, v); s_st(p.t, v);
+    gf_set_ui(v, 1); s_st(p.y, v); s_st(p.z, v);
 }
 
 #define BDSM_NSLOTS 7
-#define BDSM_TABLE 17 /* 16 odd multiples + pniels(2P) while the table is being built */
 // combo = scalar1*B + scalar2*base2 for PUBLIC inputs, warp-uniform schedule -- see the comment on
-// base_double_scalarmul_uniform (algos.cuh), whose digits, tables and operation order this follows.
+// "combo = scalar1*B + scalar2*base2" in algos.cuh, which defines the digits and the tables.
 // On entry the slots X,Y,Z,T (0..3) hold base2; on exit they hold the result (X, Y, Z valid, T valid).
-// `multiples` = this lane's BDSM_TABLE pniels of global scratch.
-GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide_base, pniels *multiples) {
+// `multiples` = this lane's window table (lane-contiguous layout: the digits are public, entries are gathered).
+GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide_base, const wtab<1> &multiples) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
     const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
     sc s1x, s2x;
     sc_recode_signed(s1x, scalar1);
     sc_recode_signed(s2x, scalar2);
-    /* odd multiples 1P, 3P, ..., 31P: P, then 2P + P, then += 2P (goldilocks.c:382-403) */
-    s_pt_to_pniels_negc_g(multiples + 0, p, w);
-    s_pt_double(p, w, false);
-    s_pt_to_pniels_negc_g(multiples + 16, p, w);
-    s_pt_add_pniels_g(p, w, multiples + 0, 0, ~0u, false);
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int i = 1; i < WINDOW_NTABLE; i++) {
-        s_pt_to_pniels_negc_g(multiples + i, p, w);
-        if (i != WINDOW_NTABLE - 1) s_pt_add_pniels_g(p, w, multiples + 16, 0, ~0u, false);
-    }
-    { /* accumulator = identity (0, 1, 1, 0); the unified addition law takes it from there */
-        gf v;
-        gf_set_zero(v); s_st(p.x, v); s_st(p.t, v);
-        gf_set_ui(v, 1); s_st(p.y, v); s_st(p.z, v);
-    }
+    s_prepare_fixed_window<1>(p, w, multiples);   /* odd multiples 1P, 3P, ..., 31P */
+    s_pt_set_identity(p);                      /* the unified addition law takes it from there */
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -233,13 +256,13 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
         uint32_t bits2 = sc_window5(s2x, i);
         const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
         bits2 ^= inv2;
-        s_pt_add_pniels_g(p, w, multiples + (bits2 & (WINDOW_NTABLE - 1)), inv2, ~inv2, !fixed_here && k != 0);
+        s_pt_add_pniels_g<1>(p, w, multiples, (int)(bits2 & (WINDOW_NTABLE - 1)), inv2, ~inv2, !fixed_here && k != 0);
         if (fixed_here) {
             uint32_t bits1 = sc_bits(s1x, i, WIDE_BITS);
             const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
             bits1 ^= inv1;
             const niels *e = wide_base + (bits1 & (WIDE_ENTRIES - 1));
-            s_pt_add_niels_g(p, w, &e->a, &e->b, &e->c, inv1, inv1, k != 0);
+            s_pt_add_niels_g<1>(p, w, gq(&e->a), gq(&e->b), gq(&e->c), inv1, inv1, k != 0);
         }
     }
 }
@@ -253,13 +276,13 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
 #define COMB_NSLOTS 9
 // p += (+-) entry idx of the 16-entry comb row; `first` = true sets p to the entry instead (niels_to_pt)
 GD void s_pt_add_niels_ct(const spt &p, const swk &w, sref la, sref lb, const niels *row, uint32_t idx, gmask_t neg, bool before_double) {
-    const int stride = (int)(sizeof(niels) / sizeof(gf));
-    s_lookup_ct(la, &row->a, stride, 1 << (COMB_T - 1), idx);
-    s_lookup_ct(lb, &row->b, stride, 1 << (COMB_T - 1), idx);
+    const int stride = (int)(sizeof(niels) / sizeof(uint4));
+    s_lookup_ct<true, 1>(la, gq(&row->a), stride, 1 << (COMB_T - 1), idx);
+    s_lookup_ct<true, 1>(lb, gq(&row->b), stride, 1 << (COMB_T - 1), idx);
     s_addsub(w.t1, w.t0, p.y, p.x);                      /* y+x ; y-x */
     s_mul(w.t0, w.t0, s_sel(la, lb, neg));               /* a  = e.a (y-x) */
     s_mul(w.t1, w.t1, s_sel(lb, la, neg));               /* dy = e.b (y+x) */
-    s_lookup_ct(la, &row->c, stride, 1 << (COMB_T - 1), idx);
+    s_lookup_ct<true, 1>(la, gq(&row->c), stride, 1 << (COMB_T - 1), idx);
     s_mul(p.x, p.t, la);                                 /* x  = e.c t */
     s_addsub(w.t2, w.t1, w.t1, w.t0);                    /* c = dy + a ; b = dy - a */
     s_addsub(w.t0, p.y, p.z, p.x);                       /* v = z + x ; u = z - x */
@@ -354,4 +377,95 @@ GD void s_encode_like_x448(uint32_t uw[14], sref sb) {
     gf_set_zero(zero);
     s_ld(u, xs); gf_cond_sel(u, zero, u, nz);
     gf_to_words(uw, u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variable-base scalar multiplication, constant time -- reference goldilocks.c:405-465 (and 467-541
+// for two bases): signed 5-bit fixed windows over this lane's own table of 16 odd multiples in global
+// memory; every lookup scans the whole table with masks (s_lookup_ct_rw), the sign is a handle
+// selection.  9 slots; the accumulator starts from the identity (unified addition law) instead of
+// pniels_to_pt of the first digit -- same group element.
+// ---------------------------------------------------------------------------------------------
+#define WINDOW_NSLOTS 9
+// p += (+-) table[idx], constant time in idx and the sign (`neg` all-ones = subtract).  The table is in
+// the warp-interleaved layout, so each of the 4 x 16 x 4 loads of the scan is one coalesced 512-byte row.
+GD void s_pt_add_pniels_ct(const spt &p, const swk &w, sref la, sref lb, const wtab<32> &t, uint32_t idx, gmask_t neg, bool before_double) {
+    const int es = wtab<32>::ESTRIDE;
+    s_lookup_ct<false, 32>(la, t.coord(0, 3), es, WINDOW_NTABLE, idx);
+    s_mul(p.z, p.z, la);
+    s_lookup_ct<false, 32>(la, t.coord(0, 0), es, WINDOW_NTABLE, idx);
+    s_lookup_ct<false, 32>(lb, t.coord(0, 1), es, WINDOW_NTABLE, idx);
+    s_addsub(w.t1, w.t0, p.y, p.x);
+    s_mul(w.t0, w.t0, s_sel(la, lb, neg));
+    s_mul(w.t1, w.t1, s_sel(lb, la, neg));
+    s_lookup_ct<false, 32>(la, t.coord(0, 2), es, WINDOW_NTABLE, idx);   /* stored negated: neg_c = ~neg */
+    s_mul(p.x, p.t, la);
+    s_addsub(w.t2, w.t1, w.t1, w.t0);
+    s_addsub(w.t0, p.y, p.z, p.x);
+    s_mul(p.z, w.t0, p.y);
+    s_mul(p.x, s_sel(w.t0, p.y, neg), w.t1);             /* x = (neg_c ? v : u) b, neg_c = ~neg */
+    s_mul(p.y, s_sel(p.y, w.t0, neg), w.t2);
+    if (!before_double) s_mul(p.t, w.t1, w.t2);
+}
+GD void s_window_digit(uint32_t &idx, gmask_t &neg, const sc &s1x, int i) {
+    uint32_t bits = sc_window5(s1x, i);
+    neg = (gmask_t)((int32_t)(bits >> (WINDOW_BITS - 1)) - 1);
+    bits ^= neg;
+    idx = bits & (WINDOW_NTABLE - 1);
+}
+// slots 0..3: base on entry, scalar * base on exit
+GD void s_window_scalarmul(sref sb, const sc &scalar, const wtab<32> &multiples) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    const sref la = s_slot(sb, 7), lb = s_slot(sb, 8);
+    sc s1x;
+    sc_recode_signed(s1x, scalar);
+    s_prepare_fixed_window<32>(p, w, multiples);
+    s_pt_set_identity(p);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 89; k >= 0; k--) {
+        if (k != 89) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = 0; j < WINDOW_BITS - 1; j++) s_pt_double(p, w, true);
+            s_pt_double(p, w, false);
+        }
+        uint32_t idx; gmask_t neg;
+        s_window_digit(idx, neg, s1x, k * WINDOW_BITS);
+        s_pt_add_pniels_ct(p, w, la, lb, multiples, idx, neg, k != 0);
+    }
+}
+// slots 0..3: base b on entry and the result scalarb*b + scalarc*c on exit; `c_abi` is loaded when needed
+template <class LoadC>
+GD void s_window_double_scalarmul(sref sb, const sc &scalarb, const sc &scalarc, LoadC load_c, const wtab<32> &multiples1, const wtab<32> &multiples2) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    const sref la = s_slot(sb, 7), lb = s_slot(sb, 8);
+    sc s1x, s2x;
+    sc_recode_signed(s1x, scalarb);
+    sc_recode_signed(s2x, scalarc);
+    s_prepare_fixed_window<32>(p, w, multiples1);
+    load_c(sb);
+    s_prepare_fixed_window<32>(p, w, multiples2);
+    s_pt_set_identity(p);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 89; k >= 0; k--) {
+        if (k != 89) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = 0; j < WINDOW_BITS - 1; j++) s_pt_double(p, w, true);
+            s_pt_double(p, w, false);
+        }
+        uint32_t idx; gmask_t neg;
+        s_window_digit(idx, neg, s1x, k * WINDOW_BITS);
+        s_pt_add_pniels_ct(p, w, la, lb, multiples1, idx, neg, false);
+        s_window_digit(idx, neg, s2x, k * WINDOW_BITS);
+        s_pt_add_pniels_ct(p, w, la, lb, multiples2, idx, neg, k != 0);
+    }
 }

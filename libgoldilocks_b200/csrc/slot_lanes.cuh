@@ -42,12 +42,12 @@ GD void s_bdsm_quirk(sref sb, const sc &scalar2) {
 }
 struct SlotBaseDoubleScalarmul { /* goldilocks_448_base_double_scalarmul_non_secret (goldilocks.c:1260-1330) */
     static constexpr int NSLOTS = BDSM_NSLOTS;
-    abi_pt *out; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; const niels *wide; pniels *scratch;
+    abi_pt *out; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; const niels *wide; uint4 *scratch;
     GDM void operator()(size_t i, sref sb, size_t slot) const {
         sc s1, s2;
         sc_from_abi(s1, scalar1 + i); sc_from_abi(s2, scalar2 + i);
         s_pt_from_abi(sb, base2 + i);
-        s_base_double_scalarmul(sb, s1, s2, wide, scratch + BDSM_TABLE * slot);
+        s_base_double_scalarmul(sb, s1, s2, wide, wtab_of<1>(scratch, slot));
         s_bdsm_quirk(sb, s2);
         gf v;
         s_ld(v, s_slot(sb, 0)); gf_to_abi(&out[i].x, v);
@@ -60,13 +60,13 @@ struct SlotBaseDoubleScalarmul { /* goldilocks_448_base_double_scalarmul_non_sec
 // combo == R on the quotient group (goldilocks.c:644-653) and both decodes succeeded.
 struct SlotEdVerifyFinish {
     static constexpr int NSLOTS = BDSM_NSLOTS;
-    int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; pniels *scratch;
+    int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; uint4 *scratch;
     GDM void operator()(size_t i, sref sb, size_t slot) const {
         sc c, r;
         sc_from_abi(c, challenge + i);
         sc_from_abi(r, response + i);
         s_pt_from_abi(sb, pts + 2 * i);
-        s_base_double_scalarmul(sb, r, c, wide, scratch + BDSM_TABLE * slot);
+        s_base_double_scalarmul(sb, r, c, wide, wtab_of<1>(scratch, slot));
         s_bdsm_quirk(sb, c);
         /* pt_eq(combo, R): combo.y * R.x == R.y * combo.x */
         const sref t0 = s_slot(sb, 4), t1 = s_slot(sb, 5);
@@ -142,5 +142,30 @@ struct SlotEdSignR { /* eddsa.c:201-205: R = encode(comb(nonce / 4)) */
         s_encode_like_eddsa(w, sign, sb);
         w[14] = sign << 7;
         if (live) words_store_bytes(sig + 114 * i, 57, w);
+    }
+};
+
+struct SlotScalarmul { /* goldilocks_448_point_scalarmul (goldilocks.c:405-465); `slot` indexes per-thread HBM scratch */
+    static constexpr int NSLOTS = WINDOW_NSLOTS;
+    abi_pt *out; const abi_pt *base; const abi_sc *scalar; uint4 *scratch;
+    GDM void operator()(size_t i, sref sb, size_t slot) const {
+        sc s;
+        sc_from_abi(s, scalar + i);
+        s_pt_from_abi(sb, base + i);
+        s_window_scalarmul(sb, s, wtab_of<32>(scratch, slot));
+        s_pt_to_abi(out + i, sb);
+    }
+};
+struct LoadAbiPt { const abi_pt *p; GDM void operator()(sref sb) const { s_pt_from_abi(sb, p); } };
+struct SlotDoubleScalarmul { /* goldilocks_448_point_double_scalarmul (goldilocks.c:467-541) */
+    static constexpr int NSLOTS = WINDOW_NSLOTS;
+    abi_pt *out; const abi_pt *base1; const abi_sc *scalar1; const abi_pt *base2; const abi_sc *scalar2; uint4 *scratch; size_t nthreads; /* scratch = two tables per thread */
+    GDM void operator()(size_t i, sref sb, size_t slot) const {
+        sc s1, s2;
+        sc_from_abi(s1, scalar1 + i); sc_from_abi(s2, scalar2 + i);
+        s_pt_from_abi(sb, base1 + i);
+        LoadAbiPt load2 = {base2 + i};
+        s_window_double_scalarmul(sb, s1, s2, load2, wtab_of<32>(scratch, slot), wtab_of<32>(scratch + nthreads * WTAB_QUADS_PER_LANE, slot));
+        s_pt_to_abi(out + i, sb);
     }
 };

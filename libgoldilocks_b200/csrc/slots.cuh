@@ -22,6 +22,33 @@
 
 #define SLOT_BLOCK 128
 
+#if !defined(__CUDACC__)
+struct alignas(16) uint4 { uint32_t x, y, z, w; }; /* host simulator only */
+#endif
+
+// Field elements in GLOBAL memory are four 128-bit quads, QS quads apart:
+//   QS = 1  : contiguous 64 bytes (`gf` arrays: fixed-base tables, lane-contiguous window tables)
+//   QS = 32 : warp-interleaved -- quad q of the 32 lanes of a warp is one 512-byte row, so a table
+//             access in which all lanes touch the same entry is fully coalesced (constant-time scans).
+template <bool RO, int QS>
+GD void gq_ld(gf &o, const uint4 *p) { /* RO: never written while the kernel runs -> non-coherent path */
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#if defined(__CUDA_ARCH__)
+        const uint4 x = RO ? __ldg(p + q * QS) : p[q * QS];
+#else
+        const uint4 x = p[q * QS];
+#endif
+        o.v[4 * q] = x.x; o.v[4 * q + 1] = x.y; o.v[4 * q + 2] = x.z; o.v[4 * q + 3] = x.w;
+    }
+}
+template <int QS>
+GD void gq_st(uint4 *p, const gf &x) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) { uint4 v; v.x = x.v[4 * q]; v.y = x.v[4 * q + 1]; v.z = x.v[4 * q + 2]; v.w = x.v[4 * q + 3]; p[q * QS] = v; }
+}
+GD const uint4 *gq(const gf *g) { return reinterpret_cast<const uint4 *>(g); }
+
 #if defined(__CUDA_ARCH__)
 extern __shared__ uint4 slot_mem[];
 struct sref { uint32_t a; };                       /* uint4 index of this lane's quad 0 */
@@ -62,9 +89,10 @@ SFN void s_sqrn(sref d, sref a, int n) { /* n >= 1 */
     for (int i = 0; i < n; i++) gf_sqr_body(x, x);
     s_st(d, x);
 }
-// d = a * g, g a 16-byte aligned element in global memory (table rows; never a secret-indexed address
-// on the constant-time paths -- those scan with masks, see s_lookup_*).
-SFN void s_mulg(sref d, sref a, const gf *g) { gf x, y, z; s_ld(x, a); gf_ld<false>(y, g); gf_mul_body(z, x, y); s_st(d, z); }
+// d = a * g, g an element in global memory (table rows; never a secret-indexed address on the
+// constant-time paths -- those scan with masks, see s_lookup_ct).
+template <int QS>
+SFN void s_mulg(sref d, sref a, const uint4 *g) { gf x, y, z; s_ld(x, a); gq_ld<false, QS>(y, g); gf_mul_body(z, x, y); s_st(d, z); }
 SFN void s_add(sref d, sref a, sref b) { gf x, y; s_ld(x, a); s_ld(y, b); gf_add_nr(x, x, y); s_st(d, x); }   /* TIGHT+TIGHT -> LOOSE */
 SFN void s_addr(sref d, sref a, sref b) { gf x, y; s_ld(x, a); s_ld(y, b); gf_add(x, x, y); s_st(d, x); }     /* reduced */
 SFN void s_sub(sref d, sref a, sref b) { gf x, y; s_ld(x, a); s_ld(y, b); gf_sub(x, x, y); s_st(d, x); }
@@ -93,11 +121,12 @@ SFN void s_neg(sref d, sref a) { gf x; s_ld(x, a); gf_neg(x, x); s_st(d, x); }
 SFN void s_mulw(sref d, sref a, uint32_t w) { gf x, z; s_ld(x, a); gf_mulw(z, x, w); s_st(d, z); }
 // d = a * w + c  (LOOSE)
 SFN void s_mulw_add(sref d, sref a, uint32_t w, sref c) { gf x, y, z; s_ld(x, a); s_ld(y, c); gf_mulw(z, x, w); gf_add_nr(z, z, y); s_st(d, z); }
-// Constant-time table lookup of ONE coordinate: d = row[idx].<coordinate>, where `first` points at
-// that coordinate of entry 0 and entries are `stride` gf apart.  Every lane reads every entry (the
+// Constant-time table lookup of ONE coordinate: d = entry[idx].<coordinate>, where `first` points at that
+// coordinate of entry 0 and entries are `estride` quads apart.  Every lane reads every entry (the
 // addresses do not depend on idx) and keeps the one whose index matches, by masks -- the semantics of
 // the reference's constant_time_lookup (src/include/constant_time.h:134-183).  n <= 32 entries.
-SFN void s_lookup_ct(sref d, const gf *first, int stride, int n, uint32_t idx) {
+template <bool RO, int QS>
+SFN void s_lookup_ct(sref d, const uint4 *first, int estride, int n, uint32_t idx) {
     gf o;
     gf_set_zero(o);
 #if defined(__CUDA_ARCH__)
@@ -105,22 +134,16 @@ SFN void s_lookup_ct(sref d, const gf *first, int stride, int n, uint32_t idx) {
 #endif
     for (int e = 0; e < n; e++) {
         const gmask_t m = (gmask_t)(((uint64_t)((uint32_t)e ^ idx) - 1) >> 32); /* all-ones iff e == idx */
-        gf_ld_or_masked<true>(o, first + (size_t)e * stride, m);
+        gf t;
+        gq_ld<RO, QS>(t, first + (size_t)e * estride);
+#pragma unroll
+        for (int i = 0; i < 16; i++) o.v[i] |= t.v[i] & m;
     }
     s_st(d, o);
 }
 SFN void s_copy(sref d, sref a) { gf x; s_ld(x, a); s_st(d, x); }
-SFN void s_stg(gf *g, sref a) { /* slot -> global, 128-bit stores */
-    gf x;
-    s_ld(x, a);
-#if defined(__CUDA_ARCH__)
-    uint4 *p = reinterpret_cast<uint4 *>(g);
-#pragma unroll
-    for (int q = 0; q < 4; q++) p[q] = make_uint4(x.v[4 * q], x.v[4 * q + 1], x.v[4 * q + 2], x.v[4 * q + 3]);
-#else
-    gf_copy(*g, x);
-#endif
-}
+template <int QS>
+SFN void s_stg(uint4 *g, sref a) { gf x; s_ld(x, a); gq_st<QS>(g, x); } /* slot -> global */
 
 // a = x^((p-3)/4); returns all-ones iff a^2 x == 1.  Same addition chain as gf_isr (gf.cuh), walked
 // on slots: `a` and `saved` are scratch/output slots distinct from x.

@@ -31,17 +31,6 @@ static void run(const F &f, size_t n) {
     for (auto &x : th) x.join();
 }
 template <class F>
-static void run_slot(const F &f, size_t n) { /* one scratch slot per worker thread */
-    int nt = g_threads;
-    if ((size_t)nt > n) nt = n ? (int)n : 1;
-    if (nt <= 1) { for (size_t i = 0; i < n; i++) f(i, 0); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++)
-        th.emplace_back([&f, n, nt, t]() { for (size_t i = n * t / nt; i < n * (t + 1) / nt; i++) f(i, (size_t)t); });
-    for (auto &x : th) x.join();
-}
-
-template <class F>
 static void run_sm(const F &f, size_t n) { /* slot machine: F::NSLOTS field elements of scratch per worker */
     int nt = g_threads;
     if ((size_t)nt > n) nt = n ? (int)n : 1;
@@ -103,8 +92,11 @@ EXPORT int32_t goldilocks_b200_init(void) { tables(); return -1; }
 
 typedef abi_pt hpt;
 typedef abi_sc hsc;
-static std::vector<pniels> g_slots;
-static pniels *slots(size_t per_thread) { g_slots.resize((size_t)g_threads * per_thread); return g_slots.data(); }
+static std::vector<uint4> g_slots;
+static uint4 *slots(size_t tables_per_thread) { /* window tables (wtab): workers rounded up to whole warps of 32 */
+    g_slots.resize((size_t)((g_threads + 31) / 32 * 32) * tables_per_thread * WTAB_QUADS_PER_LANE);
+    return g_slots.data();
+}
 
 #define GF2(NAME, OP) EXPORT int32_t NAME(uint8_t *o, const uint8_t *a, const uint8_t *b, size_t n) { LaneGf<OP> f = {o, nullptr, a, b, 0}; run(f, n); return -1; }
 GF2(goldilocks_448_gf_mul_batch, GFOP_MUL)
@@ -130,9 +122,9 @@ EXPORT int32_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(hpt
 EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint8_t *o, const hpt *a, size_t n) { LaneEncodeX448 f = {o, a}; run(f, n); return -1; }
 
 EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(hpt *o, const void *, const hsc *s, size_t n) { SlotComb f = {o, s, tables()}; run_sm(f, n); return -1; }
-EXPORT int32_t goldilocks_448_point_scalarmul_batch(hpt *o, const hpt *b, const hsc *s, size_t n) { LaneScalarmul f = {o, b, s, slots(WINDOW_NTABLE)}; run_slot(f, n); return -1; }
-EXPORT int32_t goldilocks_448_point_double_scalarmul_batch(hpt *o, const hpt *b1, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { LaneDoubleScalarmul f = {o, b1, s1, b2, s2, slots(2 * WINDOW_NTABLE)}; run_slot(f, n); return -1; }
-EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *o, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { SlotBaseDoubleScalarmul f = {o, s1, b2, s2, wide_table(), slots(BDSM_TABLE)}; run_smp(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_scalarmul_batch(hpt *o, const hpt *b, const hsc *s, size_t n) { SlotScalarmul f = {o, b, s, slots(1)}; run_smp(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_double_scalarmul_batch(hpt *o, const hpt *b1, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { SlotDoubleScalarmul f = {o, b1, s1, b2, s2, slots(2), (size_t)((g_threads + 31) / 32 * 32)}; run_smp(f, n); return -1; }
+EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *o, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { SlotBaseDoubleScalarmul f = {o, s1, b2, s2, wide_table(), slots(1)}; run_smp(f, n); return -1; }
 
 EXPORT int32_t goldilocks_448_scalar_add_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_ADD> f = {o, a, b}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_scalar_sub_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_SUB> f = {o, a, b}; run(f, n); return -1; }
@@ -167,7 +159,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     run(f1, 2 * n);
     LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len};
     run(f2, n);
-    SlotEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), slots(BDSM_TABLE)};
+    SlotEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), slots(1)};
     run_smp(f3, n);
     return -1;
 }

@@ -4,7 +4,7 @@ tag=${1:-q}
 mkdir -p gpurun_out
 ( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/${tag}_pytest.log 2>&1
 tail -5 gpurun_out/${tag}_pytest.log
-timeout 300 python tools/opbench.py --ops sign,comb,x448 > gpurun_out/${tag}_opbench.txt 2>&1
+timeout 300 python tools/opbench.py --ops sign,scalarmul,comb,x448 > gpurun_out/${tag}_opbench.txt 2>&1
 cat gpurun_out/${tag}_opbench.txt
 timeout 900 python bench.py --no-cpu --no-extra --steps 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 tail -3 gpurun_out/${tag}_bench.err

@@ -40,6 +40,18 @@ def main():
         tot = sum(t for _, t in ks)
         print("sign      n=%d kernels %s  -> %.2f M signatures/s (kernels only)" % (m, ks, m / tot / 1e3))
         a.ops = ",".join(o for o in a.ops.split(",") if o != "sign")
+    if "scalarmul" in a.ops.split(","):
+        m = min(n, 1 << 18)
+        hs = lib.scalar_decode_long(stream_bytes("opbench/vs", m * 56).reshape(m, 56), 56)
+        hp = lib.precomputed_scalarmul(hs[::-1].copy())
+        for name, fn, mac in (("point_scalarmul", lambda: lib.point_scalarmul(hp, hs), 760592),
+                              ("base_double_scalarmul_non_secret", lambda: lib.base_double_scalarmul_non_secret(hs, hp, hs[::-1].copy()), 800300),
+                              ("point_double_scalarmul", lambda: lib.point_double_scalarmul(hp, hs, hp[::-1].copy(), hs[::-1].copy()), 1500000)):
+            fn()
+            ks = kernel_ms(fn)
+            tot = sum(t for _, t in ks)
+            print("%-34s n=%d kernels %s -> %.2f Mops/s imad_frac %.3f" % (name, m, ks, m / tot / 1e3, m * mac / (tot / 1e3) / 1e9 / json.load(open(os.path.join(ROOT, "profiles", "r01_imad_peak.json")))["imad_wide_u32_gmac_s"]))
+        a.ops = ",".join(o for o in a.ops.split(",") if o != "scalarmul")
     peak = json.load(open(os.path.join(ROOT, "profiles", "r01_imad_peak.json")))["imad_wide_u32_gmac_s"]
     for op in [o for o in a.ops.split(",") if o]:
         f = fns[op]; f(); torch.cuda.synchronize()

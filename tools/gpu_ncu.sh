@@ -8,7 +8,7 @@ for k in "${@:-finish}"; do
     finish) timeout 600 $NCU -k regex:SlotEdVerifyFinish -s 1 -c 1 -f -o gpurun_out/${tag}_finish python bench.py --steps 1 --warmup 3 --no-cpu --no-extra > gpurun_out/${tag}_ncu_finish.log 2>&1 ;;
     decode) timeout 600 $NCU -k regex:LaneEdVerifyDecode -s 1 -c 1 -f -o gpurun_out/${tag}_decode python bench.py --steps 1 --warmup 3 --no-cpu --no-extra > gpurun_out/${tag}_ncu_decode.log 2>&1 ;;
     x448)   timeout 600 $NCU -k regex:SlotX448 -s 1 -c 1 -f -o gpurun_out/${tag}_x448 python tools/opbench.py --ops x448 --reps 1 > gpurun_out/${tag}_ncu_x448.log 2>&1 ;;
-    comb)   timeout 600 $NCU -k regex:LaneComb -s 1 -c 1 -f -o gpurun_out/${tag}_comb python tools/opbench.py --ops comb --reps 1 > gpurun_out/${tag}_ncu_comb.log 2>&1 ;;
+    comb)   timeout 600 $NCU -k regex:SlotComb -s 1 -c 1 -f -o gpurun_out/${tag}_comb python tools/opbench.py --ops comb --reps 1 > gpurun_out/${tag}_ncu_comb.log 2>&1 ;;
   esac
   tail -2 gpurun_out/${tag}_ncu_$k.log
 done

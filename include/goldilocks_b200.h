@@ -56,9 +56,12 @@ typedef enum { GOLDILOCKS_SUCCESS = -1, GOLDILOCKS_FAILURE = 0 } goldilocks_erro
 typedef struct gf_448_s { goldilocks_word_t limb[8]; } __attribute__((aligned(32))) gf_448_s;
 typedef struct goldilocks_448_point_s { gf_448_s x, y, z, t; } goldilocks_448_point_s, goldilocks_448_point_p[1];
 typedef struct goldilocks_448_scalar_s { goldilocks_word_t limb[GOLDILOCKS_448_SCALAR_LIMBS]; } goldilocks_448_scalar_s, goldilocks_448_scalar_p[1];
-/* Opaque fixed-base table handle.  Only goldilocks_448_precomputed_base is accepted (the comb
- * table lives in device memory; reference goldilocks.c:59-64). */
+/* Fixed-base table handle (reference goldilocks.c:59-66).  goldilocks_448_precomputed_base selects the
+ * library's device-resident base-point tables; any other pointer must address a caller-allocated table of
+ * goldilocks_448_sizeof_precomputed_s bytes filled by goldilocks_448_precompute(), byte-compatible with
+ * the reference's (80 affine niels, canonical radix-2^56 limbs). */
 typedef struct goldilocks_448_precomputed_s goldilocks_448_precomputed_s;
+GOLDILOCKS_B200_API extern const size_t goldilocks_448_sizeof_precomputed_s, goldilocks_448_alignof_precomputed_s; /* point_448.h:79 */
 
 GOLDILOCKS_B200_API extern const goldilocks_448_precomputed_s *goldilocks_448_precomputed_base;
 GOLDILOCKS_B200_API extern const goldilocks_448_point_p goldilocks_448_point_base;       /* reference point_448.h:283 */
@@ -88,6 +91,19 @@ GOLDILOCKS_B200_API void goldilocks_448_precomputed_scalarmul(goldilocks_448_poi
 GOLDILOCKS_B200_API void goldilocks_448_point_double_scalarmul(goldilocks_448_point_p combo, const goldilocks_448_point_p base1, const goldilocks_448_scalar_p scalar1, const goldilocks_448_point_p base2, const goldilocks_448_scalar_p scalar2);
 /* reference point_448.h:542-547 / goldilocks.c:1260-1330 (variable time, public inputs only) */
 GOLDILOCKS_B200_API void goldilocks_448_base_double_scalarmul_non_secret(goldilocks_448_point_p combo, const goldilocks_448_scalar_p scalar1, const goldilocks_448_point_p base2, const goldilocks_448_scalar_p scalar2);
+/* reference point_448.h:510-531 / goldilocks.c:543-642 (constant time): a1 = scalar1*base, a2 = scalar2*base */
+GOLDILOCKS_B200_API void goldilocks_448_point_dual_scalarmul(goldilocks_448_point_p a1, goldilocks_448_point_p a2, const goldilocks_448_point_p base, const goldilocks_448_scalar_p scalar1, const goldilocks_448_scalar_p scalar2);
+/* reference point_448.h:371-384 / goldilocks.c:888-903: decode, scalarmul, encode; a failed decode multiplies the base point
+ * (or, with short_circuit, returns at once without writing `scaled`) */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_direct_scalarmul(uint8_t scaled[56], const uint8_t base[56], const goldilocks_448_scalar_p scalar, goldilocks_bool_t allow_identity, goldilocks_bool_t short_circuit);
+/* reference point_448.h:455-466,483-486 / goldilocks.c:757-818,1337-1343 */
+GOLDILOCKS_B200_API void goldilocks_448_precompute(goldilocks_448_precomputed_s *table, const goldilocks_448_point_p base);
+GOLDILOCKS_B200_API void goldilocks_448_precomputed_destroy(goldilocks_448_precomputed_s *table);
+/* reference point_448.h:565-594 / goldilocks.c:675-702,879-886 */
+GOLDILOCKS_B200_API void goldilocks_448_point_debugging_torque(goldilocks_448_point_p q, const goldilocks_448_point_p p);
+GOLDILOCKS_B200_API void goldilocks_448_point_debugging_pscale(goldilocks_448_point_p q, const goldilocks_448_point_p p, const uint8_t factor[56]);
+GOLDILOCKS_B200_API void goldilocks_448_point_cond_sel(goldilocks_448_point_p out, const goldilocks_448_point_p a, const goldilocks_448_point_p b, goldilocks_bool_t pick_b);
+GOLDILOCKS_B200_API void goldilocks_448_point_destroy(goldilocks_448_point_p point);
 /* reference point_448.h:647-664 / elligator.c:32-94 */
 GOLDILOCKS_B200_API void goldilocks_448_point_from_hash_nonuniform(goldilocks_448_point_p pt, const uint8_t hashed_data[56]);
 GOLDILOCKS_B200_API void goldilocks_448_point_from_hash_uniform(goldilocks_448_point_p pt, const uint8_t hashed_data[112]);
@@ -103,7 +119,18 @@ GOLDILOCKS_B200_API void goldilocks_ed448_derive_secret_scalar(goldilocks_448_sc
 GOLDILOCKS_B200_API void goldilocks_ed448_derive_public_key(uint8_t pubkey[57], const uint8_t privkey[57]);
 GOLDILOCKS_B200_API void goldilocks_ed448_sign(uint8_t signature[114], const uint8_t privkey[57], const uint8_t pubkey[57], const uint8_t *message, size_t message_len, uint8_t prehashed, const uint8_t *context, uint8_t context_len);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify(const uint8_t signature[114], const uint8_t pubkey[57], const uint8_t *message, size_t message_len, uint8_t prehashed, const uint8_t *context, uint8_t context_len);
+/* reference ed448.h:234-262 / goldilocks.c:1079-1103, eddsa.c:83-95 */
+GOLDILOCKS_B200_API void goldilocks_ed448_convert_public_key_to_x448(uint8_t x[56], const uint8_t ed[57]);
+GOLDILOCKS_B200_API void goldilocks_ed448_convert_private_key_to_x448(uint8_t x[56], const uint8_t ed[57]);
 /* reference point_448.h:113-233 / scalar.c */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_invert(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a);
+GOLDILOCKS_B200_API goldilocks_bool_t goldilocks_448_scalar_eq(const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b);
+GOLDILOCKS_B200_API void goldilocks_448_scalar_cond_sel(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b, goldilocks_bool_t pick_b);
+GOLDILOCKS_B200_API void goldilocks_448_scalar_set_unsigned(goldilocks_448_scalar_p out, uint64_t a);
+GOLDILOCKS_B200_API void goldilocks_448_scalar_destroy(goldilocks_448_scalar_p scalar);
+/* reference common.h:98-114 / utils.c */
+GOLDILOCKS_B200_API void goldilocks_bzero(void *data, size_t size);
+GOLDILOCKS_B200_API goldilocks_bool_t goldilocks_memeq(const void *data1, const void *data2, size_t size);
 GOLDILOCKS_B200_API void goldilocks_448_scalar_add(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b);
 GOLDILOCKS_B200_API void goldilocks_448_scalar_sub(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b);
 GOLDILOCKS_B200_API void goldilocks_448_scalar_mul(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b);
@@ -144,6 +171,13 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_scalarmul_batch(gold
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_double_scalarmul_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *base1, const goldilocks_448_scalar_s *scalar1, const goldilocks_448_point_s *base2, const goldilocks_448_scalar_s *scalar2, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(goldilocks_448_point_s *out, const goldilocks_448_precomputed_s *base, const goldilocks_448_scalar_s *scalar, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_base_double_scalarmul_non_secret_batch(goldilocks_448_point_s *out, const goldilocks_448_scalar_s *scalar1, const goldilocks_448_point_s *base2, const goldilocks_448_scalar_s *scalar2, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_dual_scalarmul_batch(goldilocks_448_point_s *out1, goldilocks_448_point_s *out2, const goldilocks_448_point_s *base, const goldilocks_448_scalar_s *scalar1, const goldilocks_448_scalar_s *scalar2, size_t n);
+/* status[i] = the decode's; with short_circuit the bytes of a failed element are left as the caller passed them */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_direct_scalarmul_batch(uint8_t *scaled /*n*56*/, goldilocks_error_t *status, const uint8_t *base /*n*56*/, const goldilocks_448_scalar_s *scalar, goldilocks_bool_t allow_identity, goldilocks_bool_t short_circuit, size_t n);
+/* tables = n consecutive tables of goldilocks_448_sizeof_precomputed_s bytes */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_precompute_batch(goldilocks_448_precomputed_s *tables, const goldilocks_448_point_s *points, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_debugging_torque_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *a, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_debugging_pscale_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *a, const uint8_t *factor /*n*56*/, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uint8_t *enc /*n*57*/, const goldilocks_448_point_s *pts, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(goldilocks_448_point_s *pts, goldilocks_error_t *status, const uint8_t *enc /*n*57*/, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint8_t *out /*n*56*/, const goldilocks_448_point_s *pts, size_t n);
@@ -153,12 +187,15 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_add_batch(goldilock
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_sub_batch(goldilocks_448_scalar_s *out, const goldilocks_448_scalar_s *a, const goldilocks_448_scalar_s *b, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_mul_batch(goldilocks_448_scalar_s *out, const goldilocks_448_scalar_s *a, const goldilocks_448_scalar_s *b, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_halve_batch(goldilocks_448_scalar_s *out, const goldilocks_448_scalar_s *a, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_invert_batch(goldilocks_448_scalar_s *out, goldilocks_error_t *status, const goldilocks_448_scalar_s *a, size_t n);
 /* every element has the same serialized length ser_len (any length, reduced mod q; scalar.c:257-293) */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_decode_long_batch(goldilocks_448_scalar_s *out, const uint8_t *ser /*n*ser_len*/, size_t ser_len, size_t n);
 
 /* CFRG cryptosystems */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448_batch(uint8_t *out /*n*56*/, goldilocks_error_t *status, const uint8_t *base /*n*56*/, const uint8_t *scalar /*n*56*/, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448_derive_public_key_batch(uint8_t *out /*n*56*/, const uint8_t *scalar /*n*56*/, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_convert_public_key_to_x448_batch(uint8_t *x /*n*56*/, const uint8_t *ed /*n*57*/, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_convert_private_key_to_x448_batch(uint8_t *x /*n*56*/, const uint8_t *ed /*n*57*/, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_derive_public_key_batch(uint8_t *pubkey /*n*57*/, const uint8_t *privkey /*n*57*/, size_t n);
 /* message i = msg[msg_off[i] .. msg_off[i+1]); prehashed/context are shared by the whole batch,
  * exactly the per-call arguments of the reference (eddsa.c:146-155,253-261). */

@@ -27,6 +27,19 @@ def _u8(a, width=None):
     return a
 
 
+ALL = (1 << 64) - 1  # goldilocks_bool_t true
+
+
+def _aligned(a, align):
+    """copy of the flat uint8 array `a` whose data pointer is `align`-byte aligned (the reference's AVX2
+    build loads table and point structs with aligned vector moves)"""
+    buf = np.empty(a.size + align, np.uint8)
+    off = (-buf.ctypes.data) % align
+    out = buf[off:off + a.size]
+    out[:] = a
+    return out
+
+
 def pack_messages(msgs):
     """list of bytes -> (arena uint8[total], offsets uint64[n+1])"""
     off = np.zeros(len(msgs) + 1, dtype=np.uint64)
@@ -155,12 +168,41 @@ class BatchLib:
         return out
 
     # ---- scalar multiplication ----
-    def precomputed_scalarmul(self, scalars):
+    def precomputed_scalarmul(self, scalars, table=None):
+        """table = None: the base-point table; else one 15360-byte table from precompute()"""
         s = _u8(scalars, 56); out = np.empty((len(s), 256), np.uint8)
         base = None
-        if self.has("goldilocks_448_precomputed_base"):
+        if table is not None:
+            base = _aligned(np.ascontiguousarray(table, np.uint8).reshape(-1), 32)
+        elif self.has("goldilocks_448_precomputed_base"):
             base = C.c_void_p.in_dll(self.lib, "goldilocks_448_precomputed_base")
         self._call("goldilocks_448_precomputed_scalarmul_batch", out, base, s, _Z(len(s)))
+        return out
+
+    def precompute(self, pts):
+        p = _u8(pts, 256); out = _aligned(np.zeros(len(p) * 15360, np.uint8), 32)
+        self._call("goldilocks_448_precompute_batch", out, p, _Z(len(p)))
+        return out.reshape(len(p), 15360)
+
+    def point_dual_scalarmul(self, pts, s1, s2):
+        p, s1, s2 = _u8(pts, 256), _u8(s1, 56), _u8(s2, 56); o1 = np.empty_like(p); o2 = np.empty_like(p)
+        self._call("goldilocks_448_point_dual_scalarmul_batch", o1, o2, p, s1, s2, _Z(len(p)))
+        return o1, o2
+
+    def direct_scalarmul(self, base, scalars, allow_identity=False, short_circuit=True, prefill=0):
+        b, s = _u8(base, 56), _u8(scalars, 56)
+        out = np.full((len(b), 56), prefill, np.uint8); st = np.zeros(len(b), np.int32)
+        self._call("goldilocks_448_direct_scalarmul_batch", out, st, b, s, C.c_uint64(ALL if allow_identity else 0), C.c_uint64(ALL if short_circuit else 0), _Z(len(b)))
+        return out, st
+
+    def debugging_torque(self, pts):
+        p = _u8(pts, 256); out = np.empty_like(p)
+        self._call("goldilocks_448_point_debugging_torque_batch", out, p, _Z(len(p)))
+        return out
+
+    def debugging_pscale(self, pts, factor):
+        p, f = _u8(pts, 256), _u8(factor, 56); out = np.empty_like(p)
+        self._call("goldilocks_448_point_debugging_pscale_batch", out, p, f, _Z(len(p)))
         return out
 
     def point_scalarmul(self, pts, scalars):
@@ -188,6 +230,11 @@ class BatchLib:
     def scalar_sub(self, a, b): return self._sc2("goldilocks_448_scalar_sub_batch", a, b)
     def scalar_mul(self, a, b): return self._sc2("goldilocks_448_scalar_mul_batch", a, b)
 
+    def scalar_invert(self, a):
+        a = _u8(a, 56); out = np.empty_like(a); st = np.zeros(len(a), np.int32)
+        self._call("goldilocks_448_scalar_invert_batch", out, st, a, _Z(len(a)))
+        return out, st
+
     def scalar_halve(self, a):
         a = _u8(a, 56); out = np.empty_like(a)
         self._call("goldilocks_448_scalar_halve_batch", out, a, _Z(len(a)))
@@ -205,6 +252,16 @@ class BatchLib:
         out = np.empty_like(base); st = np.zeros(len(base), np.int32)
         self._call("goldilocks_x448_batch", out, st, base, scalar, _Z(len(base)))
         return out, st
+
+    def convert_public_key_to_x448(self, ed):
+        ed = _u8(ed, 57); out = np.empty((len(ed), 56), np.uint8)
+        self._call("goldilocks_ed448_convert_public_key_to_x448_batch", out, ed, _Z(len(ed)))
+        return out
+
+    def convert_private_key_to_x448(self, ed):
+        ed = _u8(ed, 57); out = np.empty((len(ed), 56), np.uint8)
+        self._call("goldilocks_ed448_convert_private_key_to_x448_batch", out, ed, _Z(len(ed)))
+        return out
 
     def x448_derive_public_key(self, scalar):
         scalar = _u8(scalar, 56); out = np.empty_like(scalar)

@@ -271,6 +271,7 @@ const goldilocks_448_point_p goldilocks_448_point_base = {{{GOLD_CONST_BASE_X56}
 const goldilocks_448_point_p goldilocks_448_point_identity = {{{{0}}, {{1}}, {{1}}, {{0}}}};
 const goldilocks_448_scalar_p goldilocks_448_scalar_one = {{{1}}}, goldilocks_448_scalar_zero = {{{0}}};
 const uint8_t goldilocks_x448_base_point[GOLDILOCKS_X448_PUBLIC_BYTES] = {5};
+const size_t goldilocks_448_sizeof_precomputed_s = 15360, goldilocks_448_alignof_precomputed_s = 32; /* goldilocks.c:65-66 */
 
 // ---- control -------------------------------------------------------------------------------------------
 goldilocks_error_t goldilocks_b200_init(void) { Call k; return k.finish(); }
@@ -395,6 +396,14 @@ PT_BINOP(goldilocks_448_point_sub_batch, PTOP_SUB)
     }
 PT_UNOP(goldilocks_448_point_double_batch, PTOP_DBL)
 PT_UNOP(goldilocks_448_point_negate_batch, PTOP_NEG)
+PT_UNOP(goldilocks_448_point_debugging_torque_batch, PTOP_TORQUE)
+goldilocks_error_t goldilocks_448_point_debugging_pscale_batch(hpt *out, const hpt *a, const uint8_t *factor, size_t n) {
+    Call k;
+    LanePtPscale f = {k.out<abi_pt>(n), k.in(P(a), n), k.in(factor, 56 * n)};
+    k.run(f, n);
+    k.fetch(P(out), f.out, n);
+    return k.finish();
+}
 
 goldilocks_error_t goldilocks_448_point_eq_batch(goldilocks_bool_t *out, const hpt *a, const hpt *b, size_t n) {
     Call k;
@@ -464,11 +473,50 @@ goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(
 
 // ---- scalar multiplications ------------------------------------------------------------------------------
 goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(hpt *out, const goldilocks_448_precomputed_s *base, const hsc *scalar, size_t n) {
-    if (base != goldilocks_448_precomputed_base) { g_err = "only goldilocks_448_precomputed_base is supported"; return GOLDILOCKS_FAILURE; }
     Call k;
-    SlotComb f = {k.out<abi_pt>(n), k.in(S(scalar), n), k.ok ? k.c->ft : nullptr};
+    if (base == goldilocks_448_precomputed_base) { /* the library's own base-point table: doubling-free comb */
+        SlotComb f = {k.out<abi_pt>(n), k.in(S(scalar), n), k.ok ? k.c->ft : nullptr};
+        k.run_sm(f, n);
+        k.fetch(P(out), f.out, n);
+        return k.finish();
+    }
+    /* a table made by goldilocks_448_precompute(): upload it, convert to device limbs, reference-shaped comb */
+    const abi_niels *up = k.in((const abi_niels *)base, COMB_ENTRIES);
+    niels *tab = k.out<niels>(COMB_ENTRIES);
+    LaneNielsFromAbi cv = {tab, up};
+    k.run(cv, COMB_ENTRIES);
+    SlotCombTable f = {k.out<abi_pt>(n), k.in(S(scalar), n), tab};
     k.run_sm(f, n);
     k.fetch(P(out), f.out, n);
+    return k.finish();
+}
+/* tables[k] = precompute(points[k]): 15 360 bytes each, byte-identical to the reference's (goldilocks.c:757-818) */
+goldilocks_error_t goldilocks_448_precompute_batch(goldilocks_448_precomputed_s *tables, const hpt *points, size_t n) {
+    Call k;
+    LanePrecompute f = {k.out<abi_niels>(COMB_ENTRIES * n), k.in(P(points), n), k.out<niels>(16 * COMB_N * n)};
+    k.run(f, COMB_N * n);
+    k.fetch((abi_niels *)tables, f.tables, COMB_ENTRIES * n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_point_dual_scalarmul_batch(hpt *out1, hpt *out2, const hpt *base, const hsc *scalar1, const hsc *scalar2, size_t n) {
+    Call k;
+    int grid = k.smp_grid_for<SlotDualScalarmul>();
+    SlotDualScalarmul f = {k.out<abi_pt>(n), k.out<abi_pt>(n), k.in(P(base), n), k.in(S(scalar1), n), k.in(S(scalar2), n), k.slots((size_t)grid * SLOT_BLOCK, 1)};
+    k.run_smp(f, n, grid);
+    k.fetch(P(out1), f.out1, n);
+    k.fetch(P(out2), f.out2, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_direct_scalarmul_batch(uint8_t *scaled, goldilocks_error_t *status, const uint8_t *base, const hsc *scalar,
+                                                         goldilocks_bool_t allow_identity, goldilocks_bool_t short_circuit, size_t n) {
+    Call k;
+    int grid = k.smp_grid_for<SlotDirectScalarmul>();
+    uint8_t *dout = k.in(scaled, 56 * n); /* short-circuited elements keep the caller's bytes */
+    SlotDirectScalarmul f = {dout, k.out<int32_t>(n), k.in(base, 56 * n), k.in(S(scalar), n), allow_identity ? 1u : 0u, short_circuit ? 1u : 0u,
+                             k.ok ? k.c->ft : nullptr, k.slots((size_t)grid * SLOT_BLOCK, 1)};
+    k.run_smp(f, n, grid);
+    k.fetch(scaled, dout, 56 * n);
+    k.fetch((int32_t *)status, f.status, n);
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_scalarmul_batch(hpt *out, const hpt *base, const hsc *scalar, size_t n) {
@@ -510,6 +558,29 @@ goldilocks_error_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *ou
 SC_BINOP(goldilocks_448_scalar_add_batch, SCOP_ADD)
 SC_BINOP(goldilocks_448_scalar_sub_batch, SCOP_SUB)
 SC_BINOP(goldilocks_448_scalar_mul_batch, SCOP_MUL)
+goldilocks_error_t goldilocks_448_scalar_invert_batch(hsc *out, goldilocks_error_t *status, const hsc *a, size_t n) {
+    Call k;
+    LaneScInvert f = {k.out<abi_sc>(n), k.out<int32_t>(n), k.in(S(a), n)};
+    k.run(f, n);
+    k.fetch(S(out), f.out, n);
+    k.fetch((int32_t *)status, f.status, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_ed448_convert_public_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) {
+    Call k;
+    LaneEdPkToX448 f = {k.out<uint8_t>(56 * n), k.in(ed, 57 * n)};
+    k.run(f, n);
+    k.fetch(x, f.x, 56 * n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_ed448_convert_private_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) {
+    Call k;
+    LaneEdSkToX448 f = {k.out<uint8_t>(56 * n), k.in(ed, 57 * n)};
+    k.run(f, n);
+    k.fetch(x, f.x, 56 * n);
+    if (k.ok) cudaMemsetAsync((void *)f.ed, 0, 57 * n, k.c->stream); /* wipe the private keys' device copy */
+    return k.finish();
+}
 goldilocks_error_t goldilocks_448_scalar_halve_batch(hsc *out, const hsc *a, size_t n) {
     Call k;
     LaneSc<SCOP_HALVE> f = {k.out<abi_sc>(n), k.in(S(a), n), nullptr};
@@ -763,6 +834,43 @@ goldilocks_error_t goldilocks_ed448_verify(const uint8_t signature[114], const u
     if (goldilocks_ed448_verify_batch(&st, signature, pubkey, message, off, prehashed, context, context_len, 1) != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
     return st;
 }
+void goldilocks_448_point_dual_scalarmul(goldilocks_448_point_p a1, goldilocks_448_point_p a2, const goldilocks_448_point_p b, const goldilocks_448_scalar_p s1, const goldilocks_448_scalar_p s2) {
+    goldilocks_448_point_dual_scalarmul_batch(a1, a2, b, s1, s2, 1);
+}
+goldilocks_error_t goldilocks_448_direct_scalarmul(uint8_t scaled[56], const uint8_t base[56], const goldilocks_448_scalar_p scalar, goldilocks_bool_t allow_identity, goldilocks_bool_t short_circuit) {
+    goldilocks_error_t st = GOLDILOCKS_FAILURE;
+    if (goldilocks_448_direct_scalarmul_batch(scaled, &st, base, scalar, allow_identity, short_circuit, 1) != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
+    return st;
+}
+void goldilocks_448_precompute(goldilocks_448_precomputed_s *table, const goldilocks_448_point_p base) { goldilocks_448_precompute_batch(table, base, 1); }
+void goldilocks_448_point_debugging_torque(goldilocks_448_point_p q, const goldilocks_448_point_p p) { goldilocks_448_point_debugging_torque_batch(q, p, 1); }
+void goldilocks_448_point_debugging_pscale(goldilocks_448_point_p q, const goldilocks_448_point_p p, const uint8_t factor[56]) { goldilocks_448_point_debugging_pscale_batch(q, p, factor, 1); }
+void goldilocks_ed448_convert_public_key_to_x448(uint8_t x[56], const uint8_t ed[57]) { goldilocks_ed448_convert_public_key_to_x448_batch(x, ed, 1); }
+void goldilocks_ed448_convert_private_key_to_x448(uint8_t x[56], const uint8_t ed[57]) { goldilocks_ed448_convert_private_key_to_x448_batch(x, ed, 1); }
+goldilocks_error_t goldilocks_448_scalar_invert(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a) {
+    goldilocks_error_t st = GOLDILOCKS_FAILURE;
+    if (goldilocks_448_scalar_invert_batch(out, &st, a, 1) != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
+    return st;
+}
+/* Pure data movement / comparison on host structs: no arithmetic, nothing to run on the device.
+ * (reference scalar.c:190-232,305-312; goldilocks.c:879-886; utils.c) */
+static void ct_select(void *out, const void *a, const void *b, size_t bytes, goldilocks_bool_t pick_b) {
+    const uint8_t m = (uint8_t)(pick_b ? 0xff : 0x00);
+    for (size_t i = 0; i < bytes; i++) ((uint8_t *)out)[i] = (uint8_t)((((const uint8_t *)a)[i] & (uint8_t)~m) | (((const uint8_t *)b)[i] & m));
+}
+void goldilocks_bzero(void *data, size_t size) { volatile uint8_t *p = (volatile uint8_t *)data; for (size_t i = 0; i < size; i++) p[i] = 0; }
+goldilocks_bool_t goldilocks_memeq(const void *data1, const void *data2, size_t size) {
+    uint8_t d = 0;
+    for (size_t i = 0; i < size; i++) d |= (uint8_t)(((const uint8_t *)data1)[i] ^ ((const uint8_t *)data2)[i]);
+    return d ? 0 : ~(goldilocks_bool_t)0;
+}
+goldilocks_bool_t goldilocks_448_scalar_eq(const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { return goldilocks_memeq(a, b, sizeof(goldilocks_448_scalar_s)); }
+void goldilocks_448_scalar_cond_sel(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b, goldilocks_bool_t pick_b) { ct_select(out, a, b, sizeof(goldilocks_448_scalar_s), pick_b); }
+void goldilocks_448_point_cond_sel(goldilocks_448_point_p out, const goldilocks_448_point_p a, const goldilocks_448_point_p b, goldilocks_bool_t pick_b) { ct_select(out, a, b, sizeof(goldilocks_448_point_s), pick_b); }
+void goldilocks_448_scalar_set_unsigned(goldilocks_448_scalar_p out, uint64_t w) { memset(out, 0, sizeof(goldilocks_448_scalar_s)); out->limb[0] = w; }
+void goldilocks_448_scalar_destroy(goldilocks_448_scalar_p s) { goldilocks_bzero(s, sizeof(goldilocks_448_scalar_s)); }
+void goldilocks_448_point_destroy(goldilocks_448_point_p p) { goldilocks_bzero(p, sizeof(goldilocks_448_point_s)); }
+void goldilocks_448_precomputed_destroy(goldilocks_448_precomputed_s *t) { goldilocks_bzero(t, 15360); }
 void goldilocks_448_scalar_add(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { goldilocks_448_scalar_add_batch(o, a, b, 1); }
 void goldilocks_448_scalar_sub(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { goldilocks_448_scalar_sub_batch(o, a, b, 1); }
 void goldilocks_448_scalar_mul(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { goldilocks_448_scalar_mul_batch(o, a, b, 1); }

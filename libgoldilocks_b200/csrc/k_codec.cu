@@ -5,3 +5,4 @@ INSTANTIATE_PLAIN(LanePtDecode)
 INSTANTIATE_PLAIN(LaneEncodeEddsa)
 INSTANTIATE_PLAIN(LaneDecodeEddsa)
 INSTANTIATE_PLAIN(LaneEncodeX448)
+INSTANTIATE_PLAIN(LaneEdPkToX448)

@@ -2,3 +2,4 @@
 #include "launch.cuh"
 INSTANTIATE_SM(SlotComb)
 INSTANTIATE_SM(SlotX448DerivePk)
+INSTANTIATE_SM(SlotCombTable)

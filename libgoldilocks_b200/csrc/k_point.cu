@@ -7,3 +7,5 @@ INSTANTIATE_PLAIN(LanePt<PTOP_DBL>)
 INSTANTIATE_PLAIN(LanePt<PTOP_NEG>)
 INSTANTIATE_PLAIN(LanePtEq)
 INSTANTIATE_PLAIN(LanePtValid)
+INSTANTIATE_PLAIN(LanePt<PTOP_TORQUE>)
+INSTANTIATE_PLAIN(LanePtPscale)

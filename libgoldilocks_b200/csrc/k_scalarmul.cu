@@ -2,3 +2,5 @@
 #include "launch.cuh"
 INSTANTIATE_SMP(SlotScalarmul)
 INSTANTIATE_SMP(SlotDoubleScalarmul)
+INSTANTIATE_SMP(SlotDualScalarmul)
+INSTANTIATE_SMP(SlotDirectScalarmul)

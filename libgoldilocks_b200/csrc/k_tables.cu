@@ -2,3 +2,5 @@
 #include "launch.cuh"
 INSTANTIATE_PLAIN(LaneBuildTables)
 INSTANTIATE_PLAIN(LaneBuildWide)
+INSTANTIATE_PLAIN(LanePrecompute)
+INSTANTIATE_PLAIN(LaneNielsFromAbi)

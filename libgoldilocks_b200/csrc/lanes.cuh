@@ -87,7 +87,7 @@ struct LaneGf {
 };
 
 // ---- group level -----------------------------------------------------------------------------
-enum { PTOP_ADD, PTOP_SUB, PTOP_DBL, PTOP_NEG };
+enum { PTOP_ADD, PTOP_SUB, PTOP_DBL, PTOP_NEG, PTOP_TORQUE };
 template <int OP>
 struct LanePt {
     abi_pt *out; const abi_pt *a, *b;
@@ -99,6 +99,20 @@ struct LanePt {
         if (OP == PTOP_SUB) pt_sub(p, q, r);
         if (OP == PTOP_DBL) pt_double(p, q, false);
         if (OP == PTOP_NEG) pt_negate(p, q);
+        if (OP == PTOP_TORQUE) { gf_neg(p.x, q.x); gf_neg(p.y, q.y); gf_copy(p.z, q.z); gf_copy(p.t, q.t); } /* goldilocks.c:675-683: add the 2-torsion point */
+        pt_to_abi(out + i, p);
+    }
+};
+struct LanePtPscale { /* goldilocks_448_point_debugging_pscale (goldilocks.c:685-702): another representative of the same point */
+    abi_pt *out; const abi_pt *a; const uint8_t *factor;
+    GDM void operator()(size_t i) const {
+        pt q, p; gf f, one; uint32_t w[14];
+        pt_from_abi(q, a + i);
+        words_load56(w, factor + 56 * i);
+        (void)gf_from_words(f, w);
+        gf_set_ui(one, 1);
+        gf_cond_sel(f, f, one, gf_is_zero(f));
+        gf_mul(p.x, q.x, f); gf_mul(p.y, q.y, f); gf_mul(p.z, q.z, f); gf_mul(p.t, q.t, f);
         pt_to_abi(out + i, p);
     }
 };
@@ -206,6 +220,19 @@ struct LaneSc {
     }
 };
 struct ByteAtPtr { const uint8_t *p; GDM uint8_t operator()(int k) const { return p[k]; } };
+struct LaneScInvert { /* goldilocks_448_scalar_invert (scalar.c:107-166): SUCCESS iff the result is nonzero */
+    abi_sc *out; int32_t *status; const abi_sc *a;
+    GDM void operator()(size_t i) const {
+        sc x, z;
+        sc_from_abi(x, a + i);
+        sc_invert(z, x);
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < SC_WORDS; k++) any |= z.w[k];
+        sc_to_abi(out + i, z);
+        status[i] = any ? -1 : 0;
+    }
+};
 struct LaneScDecodeLong {
     abi_sc *out; const uint8_t *ser; size_t len;
     GDM void operator()(size_t i) const {
@@ -217,6 +244,58 @@ struct LaneScDecodeLong {
 };
 
 struct ByteAtWords { const uint32_t *w; GDM uint8_t operator()(int k) const { return (uint8_t)(w[k >> 2] >> (8 * (k & 3))); } };
+
+// ---- EdDSA <-> X448 key conversions ----------------------------------------------------------------
+struct LaneEdPkToX448 { /* goldilocks_ed448_convert_public_key_to_x448 (goldilocks.c:1079-1103): u = y^2 (1 - d y^2) / (1 - y^2) */
+    uint8_t *x; const uint8_t *ed;
+    GDM void operator()(size_t i) const {
+        uint32_t w[15], wo[14];
+        words_load_bytes(w, 15, ed + 57 * i, 57);   /* the 57th byte (sign) is not read by the reference either */
+        gf y, n, d, one;
+        (void)gf_from_words(y, w);
+        gf_set_ui(one, 1);
+        gf_sqr(n, y);
+        gf_sub(d, one, n);
+        gf_invert(d, d);
+        gf_mul(y, n, d);
+        gf_mulw_signed(d, n, GOLD_EDWARDS_D);
+        gf_sub(d, one, d);
+        gf_mul(n, y, d);
+        gf_to_words(wo, n);
+        words_store56(x + 56 * i, wo);
+    }
+};
+struct LaneEdSkToX448 { /* goldilocks_ed448_convert_private_key_to_x448 (eddsa.c:83-95): SHAKE256(sk)[0..56) */
+    uint8_t *x; const uint8_t *ed;
+    GDM void operator()(size_t i) const {
+        shake256_ctx h;
+        shake256_init(h);
+        for (int k = 0; k < 57; k++) shake256_absorb_byte(h, ed[57 * i + k]);
+        shake256_finish_absorb(h);
+        for (int k = 0; k < 56; k++) x[56 * i + k] = shake256_squeeze_byte(h);
+    }
+};
+// ---- caller-supplied fixed-base tables (goldilocks_448_precompute, goldilocks.c:757-818) -------------
+// Host layout of precomputed_s: 80 niels x {a, b, c} x 8 u64 canonical radix-2^56 limbs (15 360 bytes).
+struct abi_niels { abi_gf a, b, c; };
+struct LanePrecompute { /* lane 5k + c builds comb c of table k */
+    abi_niels *tables; const abi_pt *points; niels *scratch /* 16 per lane */;
+    GDM void operator()(size_t lane) const {
+        const size_t k = lane / COMB_N; const int c = (int)(lane % COMB_N);
+        pt b;
+        pt_from_abi(b, points + k);
+        niels *mine = scratch + 16 * lane;
+        build_comb(mine, b, c);
+        for (int e = 0; e < 16; e++) {
+            abi_niels *o = tables + (COMB_ENTRIES * k + 16 * c + e);
+            gf_to_abi(&o->a, mine[e].a); gf_to_abi(&o->b, mine[e].b); gf_to_abi(&o->c, mine[e].c);
+        }
+    }
+};
+struct LaneNielsFromAbi { /* uploaded table -> device limbs */
+    niels *out; const abi_niels *in;
+    GDM void operator()(size_t e) const { gf_from_abi(out[e].a, &in[e].a); gf_from_abi(out[e].b, &in[e].b); gf_from_abi(out[e].c, &in[e].c); }
+};
 
 // ---- SHAKE256 one-shot ---------------------------------------------------------------------------
 struct LaneShake256 {

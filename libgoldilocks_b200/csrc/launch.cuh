@@ -31,6 +31,9 @@ template <> struct slot_min_blocks<SlotComb> { static constexpr int value = 3; }
 template <> struct slot_min_blocks<SlotX448DerivePk> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotEdDerivePk> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotEdSignR> { static constexpr int value = 3; };
+template <> struct slot_min_blocks<SlotCombTable> { static constexpr int value = 3; };
+template <> struct slot_min_blocks<SlotDualScalarmul> { static constexpr int value = 3; };
+template <> struct slot_min_blocks<SlotDirectScalarmul> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotScalarmul> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotDoubleScalarmul> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int value = 4; };
@@ -73,19 +76,19 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
 #define LANES_PLAIN(X)                                                                              \
     X(LaneGf<GFOP_MUL>) X(LaneGf<GFOP_SQR>) X(LaneGf<GFOP_ADD>) X(LaneGf<GFOP_SUB>)                 \
     X(LaneGf<GFOP_MULW>) X(LaneGf<GFOP_ISR>) X(LaneGf<GFOP_INVERT>)                                 \
-    X(LanePt<PTOP_ADD>) X(LanePt<PTOP_SUB>) X(LanePt<PTOP_DBL>) X(LanePt<PTOP_NEG>)                 \
+    X(LanePt<PTOP_ADD>) X(LanePt<PTOP_SUB>) X(LanePt<PTOP_DBL>) X(LanePt<PTOP_NEG>) X(LanePt<PTOP_TORQUE>) X(LanePtPscale)                 \
     X(LanePtEq) X(LanePtValid) X(LanePtEncode) X(LanePtDecode)                                      \
     X(LaneFromHash<false>) X(LaneFromHash<true>)                                                    \
     X(LaneEncodeEddsa) X(LaneDecodeEddsa) X(LaneEncodeX448)                                         \
     X(LaneSc<SCOP_ADD>) X(LaneSc<SCOP_SUB>) X(LaneSc<SCOP_MUL>) X(LaneSc<SCOP_HALVE>)               \
-    X(LaneScDecodeLong) X(LaneShake256)                                                             \
+    X(LaneScDecodeLong) X(LaneScInvert) X(LaneShake256) X(LaneEdPkToX448) X(LaneEdSkToX448) X(LanePrecompute) X(LaneNielsFromAbi)                                                             \
     X(LaneEdSecretScalar) X(LaneEdSignExpand) X(LaneEdSignNonce) X(LaneEdSignFinish)   \
     X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneBuildTables) X(LaneBuildWide)
 
-#define LANES_SM(X) X(SlotX448) X(SlotComb) X(SlotX448DerivePk) X(SlotEdDerivePk) X(SlotEdSignR)
+#define LANES_SM(X) X(SlotX448) X(SlotComb) X(SlotCombTable) X(SlotX448DerivePk) X(SlotEdDerivePk) X(SlotEdSignR)
 #define INSTANTIATE_SM(F) template cudaError_t launch_sm<F>(const F &, size_t, cudaStream_t);
 #define DECLARE_SM(F) extern INSTANTIATE_SM(F)
-#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul)
+#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul) X(SlotDualScalarmul) X(SlotDirectScalarmul)
 #define INSTANTIATE_SMP(F)                                                                          \
     template cudaError_t sm_configure<F>(int *);                                                    \
     template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t);

@@ -122,6 +122,28 @@ GD void sc_mul(sc &out, const sc &a, const sc &b) { /* reference scalar.c:93-100
     sc_montmul(t, a, b);
     sc_montmul(out, t, r2);
 }
+// out = a^(q-2) mod q = 1/a (0 for a = 0).  The reference walks the same public exponent with a sliding
+// window (scalar.c:107-166); the result is the unique inverse mod q, so a plain left-to-right
+// square-and-multiply in the Montgomery domain gives identical bytes.  The exponent is public.
+GD void sc_invert(sc &out, const sc &a) {
+    sc am, acc, r2, one;
+    sc_set_r2(r2);
+    sc_montmul(am, a, r2);          /* a R */
+    sc_copy(acc, am);               /* top bit of q - 2 (bit 445) is set */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = GOLDILOCKS_SCALAR_BITS_ - 2; i >= 0; i--) {
+        sc_montmul(acc, acc, acc);
+        /* bit i of q - 2: q is odd and q = ...11 (low word 0xab5844f3), so only the low word differs from q */
+        uint32_t w = sc_q(i >> 5);
+        if ((i >> 5) == 0) w -= 2u;
+        if ((w >> (i & 31)) & 1u) sc_montmul(acc, acc, am);
+    }
+    sc_set_zero(one);
+    one.w[0] = 1;
+    sc_montmul(out, acc, one);      /* leave the Montgomery domain */
+}
 GD void sc_reduce_short(sc &out, const sc &a) { /* "ham-handed reduce": a*1/R then *R^2/R (scalar.c:246) */
     sc one, t, r2;
     sc_set_zero(one);

@@ -413,14 +413,8 @@ GD void s_window_digit(uint32_t &idx, gmask_t &neg, const sc &s1x, int i) {
     bits ^= neg;
     idx = bits & (WINDOW_NTABLE - 1);
 }
-// slots 0..3: base on entry, scalar * base on exit
-GD void s_window_scalarmul(sref sb, const sc &scalar, const wtab<32> &multiples) {
-    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
-    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
-    const sref la = s_slot(sb, 7), lb = s_slot(sb, 8);
-    sc s1x;
-    sc_recode_signed(s1x, scalar);
-    s_prepare_fixed_window<32>(p, w, multiples);
+// slots 0..3 <- sum of the signed 5-bit digits of s1x (already recoded) times the table's odd multiples
+GD void s_window_mainloop(const spt &p, const swk &w, sref la, sref lb, const sc &s1x, const wtab<32> &multiples) {
     s_pt_set_identity(p);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -437,6 +431,15 @@ GD void s_window_scalarmul(sref sb, const sc &scalar, const wtab<32> &multiples)
         s_window_digit(idx, neg, s1x, k * WINDOW_BITS);
         s_pt_add_pniels_ct(p, w, la, lb, multiples, idx, neg, k != 0);
     }
+}
+// slots 0..3: base on entry, scalar * base on exit
+GD void s_window_scalarmul(sref sb, const sc &scalar, const wtab<32> &multiples) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    sc s1x;
+    sc_recode_signed(s1x, scalar);
+    s_prepare_fixed_window<32>(p, w, multiples);
+    s_window_mainloop(p, w, s_slot(sb, 7), s_slot(sb, 8), s1x, multiples);
 }
 // slots 0..3: base b on entry and the result scalarb*b + scalarc*c on exit; `c_abi` is loaded when needed
 template <class LoadC>
@@ -467,5 +470,40 @@ GD void s_window_double_scalarmul(sref sb, const sc &scalarb, const sc &scalarc,
         s_pt_add_pniels_ct(p, w, la, lb, multiples1, idx, neg, false);
         s_window_digit(idx, neg, s2x, k * WINDOW_BITS);
         s_pt_add_pniels_ct(p, w, la, lb, multiples2, idx, neg, k != 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-base comb over a caller-supplied (5,5,18) table (goldilocks_448_precompute output), constant
+// time -- reference goldilocks.c:830-877 verbatim: 18 rounds x 5 combs, 17 doublings + 90 additions.
+// The library's own base-point path uses the doubling-free table instead (s_comb_scalarmul).
+// ---------------------------------------------------------------------------------------------
+GD void s_comb_scalarmul_table(sref sb, const niels *table, const sc &scalar) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    const sref la = s_slot(sb, 7), lb = s_slot(sb, 8);
+    sc s1x;
+    sc_recode_signed(s1x, scalar);
+    s_pt_set_identity(p);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = COMB_S - 1; i >= 0; i--) {
+        if (i != COMB_S - 1) s_pt_double(p, w, false);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < COMB_N; j++) {
+            uint32_t tab = 0;
+#pragma unroll
+            for (int k = 0; k < COMB_T; k++) {
+                const int bit = i + COMB_S * (k + j * COMB_T);
+                if (bit < GOLDILOCKS_SCALAR_BITS_) tab |= sc_bit(s1x, bit) << k;
+            }
+            const gmask_t invert = (gmask_t)((int32_t)(tab >> (COMB_T - 1)) - 1);
+            tab ^= invert;
+            tab &= (1u << (COMB_T - 1)) - 1;
+            s_pt_add_niels_ct(p, w, la, lb, table + (j << (COMB_T - 1)), tab, invert, j == COMB_N - 1 && i != 0);
+        }
     }
 }

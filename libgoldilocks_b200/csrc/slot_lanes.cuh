@@ -169,3 +169,65 @@ struct SlotDoubleScalarmul { /* goldilocks_448_point_double_scalarmul (goldilock
         s_pt_to_abi(out + i, sb);
     }
 };
+
+struct SlotDualScalarmul { /* goldilocks_448_point_dual_scalarmul (goldilocks.c:543-642): a1 = scalar1*b, a2 = scalar2*b, one table */
+    static constexpr int NSLOTS = WINDOW_NSLOTS;
+    abi_pt *out1, *out2; const abi_pt *base; const abi_sc *scalar1, *scalar2; uint4 *scratch;
+    GDM void operator()(size_t i, sref sb, size_t slot) const {
+        const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+        const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+        const wtab<32> t = wtab_of<32>(scratch, slot);
+        sc s, sx;
+        s_pt_from_abi(sb, base + i);
+        s_prepare_fixed_window<32>(p, w, t);
+        sc_from_abi(s, scalar1 + i);
+        sc_recode_signed(sx, s);
+        s_window_mainloop(p, w, s_slot(sb, 7), s_slot(sb, 8), sx, t);
+        s_pt_to_abi(out1 + i, sb);
+        sc_from_abi(s, scalar2 + i);
+        sc_recode_signed(sx, s);
+        s_window_mainloop(p, w, s_slot(sb, 7), s_slot(sb, 8), sx, t);
+        s_pt_to_abi(out2 + i, sb);
+    }
+};
+// goldilocks_448_direct_scalarmul (goldilocks.c:888-903): decode, (base point when the decode failed),
+// constant-time scalarmul, encode.  status = the decode's; with short_circuit a failed element is not written.
+struct SlotDirectScalarmul {
+    static constexpr int NSLOTS = WINDOW_NSLOTS;
+    uint8_t *scaled; int32_t *status; const uint8_t *base; const abi_sc *scalar; uint32_t allow_identity, short_circuit;
+    const fixed_tables *ft; uint4 *scratch;
+    GDM void operator()(size_t i, sref sb, size_t slot) const {
+        uint32_t wd[14];
+        words_load56(wd, base + 56 * i);
+        gmask_t ok;
+        {
+            pt p;
+            ok = pt_decode(p, wd, allow_identity ? ~0u : 0u);
+            gf v; /* point_cond_sel(basep, point_base, basep, succ) */
+            gf_cond_sel(v, ft->base.x, p.x, ok); s_st(s_slot(sb, 0), v);
+            gf_cond_sel(v, ft->base.y, p.y, ok); s_st(s_slot(sb, 1), v);
+            gf_cond_sel(v, ft->base.z, p.z, ok); s_st(s_slot(sb, 2), v);
+            gf_cond_sel(v, ft->base.t, p.t, ok); s_st(s_slot(sb, 3), v);
+        }
+        sc s;
+        sc_from_abi(s, scalar + i);
+        s_window_scalarmul(sb, s, wtab_of<32>(scratch, slot));
+        pt q;
+        s_ld(q.x, s_slot(sb, 0)); s_ld(q.y, s_slot(sb, 1)); s_ld(q.z, s_slot(sb, 2)); s_ld(q.t, s_slot(sb, 3));
+        gf e;
+        pt_deisogenize(e, q);
+        gf_to_words(wd, e);
+        status[i] = ST_OK(ok);
+        if (ok || !short_circuit) words_store56(scaled + 56 * i, wd);
+    }
+};
+struct SlotCombTable { /* goldilocks_448_precomputed_scalarmul over a caller-supplied table (goldilocks.c:830-877) */
+    static constexpr int NSLOTS = COMB_NSLOTS;
+    abi_pt *out; const abi_sc *scalar; const niels *table;
+    GDM void operator()(size_t i, sref sb, bool live) const {
+        sc s;
+        sc_from_abi(s, scalar + i);
+        s_comb_scalarmul_table(sb, table, s);
+        if (live) s_pt_to_abi(out + i, sb);
+    }
+};

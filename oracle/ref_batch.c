@@ -69,7 +69,8 @@ enum {
     OP_PT_ADD, OP_PT_SUB, OP_PT_DBL, OP_PT_NEG, OP_PT_EQ, OP_PT_VALID, OP_PT_ENC, OP_PT_DEC,
     OP_H2C_NU, OP_H2C_U, OP_PT_SMUL, OP_PT_DSMUL, OP_COMB, OP_BDSM, OP_ENC_EDDSA, OP_DEC_EDDSA, OP_ENC_X448,
     OP_SC_ADD, OP_SC_SUB, OP_SC_MUL, OP_SC_HALVE, OP_SC_DECODE_LONG,
-    OP_X448, OP_X448_PK, OP_ED_PK, OP_ED_SIGN, OP_ED_VERIFY, OP_SHAKE256, OP_PT_COORDS
+    OP_X448, OP_X448_PK, OP_ED_PK, OP_ED_SIGN, OP_ED_VERIFY, OP_SHAKE256, OP_PT_COORDS,
+    OP_SC_INVERT, OP_PT_DUAL, OP_DIRECT, OP_PRECOMPUTE, OP_COMB_TABLE, OP_TORQUE, OP_PSCALE, OP_PK_TO_X, OP_SK_TO_X
 };
 
 static void run_range(size_t lo, size_t hi, void *vp) {
@@ -222,6 +223,54 @@ static void run_range(size_t lo, size_t hi, void *vp) {
             ((int32_t *)a->o0)[i] = (int32_t)e;
             break;
         }
+        case OP_SC_INVERT: {
+            sc_t r, x; memcpy(&x, (const sc_t *)a->i0 + i, sizeof(sc_t));
+            goldilocks_error_t e = goldilocks_448_scalar_invert(&r, &x);
+            memcpy((sc_t *)a->o0 + i, &r, sizeof(sc_t));
+            ((int32_t *)a->o1)[i] = (int32_t)e;
+            break;
+        }
+        case OP_PT_DUAL: {
+            pt_t p1, p2, q; sc_t s, t;
+            memcpy(&q, (const pt_t *)a->i0 + i, sizeof(pt_t)); memcpy(&s, (const sc_t *)a->i1 + i, sizeof(sc_t)); memcpy(&t, (const sc_t *)a->i2 + i, sizeof(sc_t));
+            goldilocks_448_point_dual_scalarmul(&p1, &p2, &q, &s, &t);
+            memcpy((pt_t *)a->o0 + i, &p1, sizeof(pt_t)); memcpy((pt_t *)a->o1 + i, &p2, sizeof(pt_t));
+            break;
+        }
+        case OP_DIRECT: {
+            sc_t s; memcpy(&s, (const sc_t *)a->i1 + i, sizeof(sc_t));
+            goldilocks_error_t e = goldilocks_448_direct_scalarmul((uint8_t *)a->o0 + 56 * i, (const uint8_t *)a->i0 + 56 * i, &s, a->flag, a->len);
+            ((int32_t *)a->o1)[i] = (int32_t)e;
+            break;
+        }
+        case OP_PRECOMPUTE: {
+            pt_t q; memcpy(&q, (const pt_t *)a->i0 + i, sizeof(pt_t));
+            void *t = NULL;
+            if (posix_memalign(&t, 32, goldilocks_448_sizeof_precomputed_s)) break;
+            goldilocks_448_precompute((goldilocks_448_precomputed_s *)t, &q);
+            memcpy((uint8_t *)a->o0 + goldilocks_448_sizeof_precomputed_s * i, t, goldilocks_448_sizeof_precomputed_s);
+            free(t);
+            break;
+        }
+        case OP_COMB_TABLE: {
+            pt_t p; sc_t s; memcpy(&s, (const sc_t *)a->i0 + i, sizeof(sc_t));
+            goldilocks_448_precomputed_scalarmul(&p, (const goldilocks_448_precomputed_s *)a->i1, &s);
+            memcpy((pt_t *)a->o0 + i, &p, sizeof(pt_t));
+            break;
+        }
+        case OP_TORQUE: case OP_PSCALE: {
+            pt_t p, q; memcpy(&q, (const pt_t *)a->i0 + i, sizeof(pt_t));
+            if (a->op == OP_TORQUE) goldilocks_448_point_debugging_torque(&p, &q);
+            else goldilocks_448_point_debugging_pscale(&p, &q, (const uint8_t *)a->i1 + 56 * i);
+            memcpy((pt_t *)a->o0 + i, &p, sizeof(pt_t));
+            break;
+        }
+        case OP_PK_TO_X:
+            goldilocks_ed448_convert_public_key_to_x448((uint8_t *)a->o0 + 56 * i, (const uint8_t *)a->i0 + 57 * i);
+            break;
+        case OP_SK_TO_X:
+            goldilocks_ed448_convert_private_key_to_x448((uint8_t *)a->o0 + 56 * i, (const uint8_t *)a->i0 + 57 * i);
+            break;
         case OP_SHAKE256:
             goldilocks_shake256_hash((uint8_t *)a->o0 + a->len * i, a->len, (const uint8_t *)a->i0 + a->off[i], a->off[i + 1] - a->off[i]);
             break;
@@ -253,7 +302,21 @@ EXPORT int32_t goldilocks_448_point_from_hash_nonuniform_batch(pt_t *o, const ui
 EXPORT int32_t goldilocks_448_point_from_hash_uniform_batch(pt_t *o, const uint8_t *h, size_t n) { A0; a.op = OP_H2C_U; a.o0 = o; a.i0 = h; return go(&a, n); }
 EXPORT int32_t goldilocks_448_point_scalarmul_batch(pt_t *o, const pt_t *b, const sc_t *s, size_t n) { A0; a.op = OP_PT_SMUL; a.o0 = o; a.i0 = b; a.i1 = s; return go(&a, n); }
 EXPORT int32_t goldilocks_448_point_double_scalarmul_batch(pt_t *o, const pt_t *b1, const sc_t *s1, const pt_t *b2, const sc_t *s2, size_t n) { A0; a.op = OP_PT_DSMUL; a.o0 = o; a.i0 = b1; a.i1 = s1; a.i2 = b2; a.i3 = s2; return go(&a, n); }
-EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(pt_t *o, const void *table, const sc_t *s, size_t n) { (void)table; A0; a.op = OP_COMB; a.o0 = o; a.i0 = s; return go(&a, n); }
+EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(pt_t *o, const void *table, const sc_t *s, size_t n) {
+    A0; a.o0 = o; a.i0 = s;
+    if (table && table != (const void *)goldilocks_448_precomputed_base) { a.op = OP_COMB_TABLE; a.i1 = table; } else a.op = OP_COMB;
+    return go(&a, n);
+}
+EXPORT int32_t goldilocks_448_precompute_batch(void *tables, const pt_t *pts, size_t n) { A0; a.op = OP_PRECOMPUTE; a.o0 = tables; a.i0 = pts; return go(&a, n); }
+EXPORT int32_t goldilocks_448_point_dual_scalarmul_batch(pt_t *o1, pt_t *o2, const pt_t *b, const sc_t *s1, const sc_t *s2, size_t n) { A0; a.op = OP_PT_DUAL; a.o0 = o1; a.o1 = o2; a.i0 = b; a.i1 = s1; a.i2 = s2; return go(&a, n); }
+EXPORT int32_t goldilocks_448_direct_scalarmul_batch(uint8_t *o, int32_t *st, const uint8_t *b, const sc_t *s, uint64_t allow_identity, uint64_t short_circuit, size_t n) {
+    A0; a.op = OP_DIRECT; a.o0 = o; a.o1 = st; a.i0 = b; a.i1 = s; a.flag = allow_identity; a.len = short_circuit; return go(&a, n);
+}
+EXPORT int32_t goldilocks_448_point_debugging_torque_batch(pt_t *o, const pt_t *x, size_t n) { A0; a.op = OP_TORQUE; a.o0 = o; a.i0 = x; return go(&a, n); }
+EXPORT int32_t goldilocks_448_point_debugging_pscale_batch(pt_t *o, const pt_t *x, const uint8_t *f, size_t n) { A0; a.op = OP_PSCALE; a.o0 = o; a.i0 = x; a.i1 = f; return go(&a, n); }
+EXPORT int32_t goldilocks_448_scalar_invert_batch(sc_t *o, int32_t *st, const sc_t *x, size_t n) { A0; a.op = OP_SC_INVERT; a.o0 = o; a.o1 = st; a.i0 = x; return go(&a, n); }
+EXPORT int32_t goldilocks_ed448_convert_public_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) { A0; a.op = OP_PK_TO_X; a.o0 = x; a.i0 = ed; return go(&a, n); }
+EXPORT int32_t goldilocks_ed448_convert_private_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) { A0; a.op = OP_SK_TO_X; a.o0 = x; a.i0 = ed; return go(&a, n); }
 EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(pt_t *o, const sc_t *s1, const pt_t *b2, const sc_t *s2, size_t n) { A0; a.op = OP_BDSM; a.o0 = o; a.i0 = s1; a.i1 = b2; a.i2 = s2; return go(&a, n); }
 EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uint8_t *o, const pt_t *x, size_t n) { A0; a.op = OP_ENC_EDDSA; a.o0 = o; a.i0 = x; return go(&a, n); }
 EXPORT int32_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(pt_t *o, int32_t *st, const uint8_t *enc, size_t n) { A0; a.op = OP_DEC_EDDSA; a.o0 = o; a.o1 = st; a.i0 = enc; return go(&a, n); }

@@ -121,9 +121,34 @@ EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uin
 EXPORT int32_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(hpt *o, int32_t *st, const uint8_t *enc, size_t n) { LaneDecodeEddsa f = {o, st, enc}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint8_t *o, const hpt *a, size_t n) { LaneEncodeX448 f = {o, a}; run(f, n); return -1; }
 
-EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(hpt *o, const void *, const hsc *s, size_t n) { SlotComb f = {o, s, tables()}; run_sm(f, n); return -1; }
+EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(hpt *o, const void *table, const hsc *s, size_t n) {
+    if (!table) { SlotComb f = {o, s, tables()}; run_sm(f, n); return -1; }
+    std::vector<niels> tab(COMB_ENTRIES);
+    LaneNielsFromAbi cv = {tab.data(), (const abi_niels *)table};
+    run(cv, COMB_ENTRIES);
+    SlotCombTable f = {o, s, tab.data()};
+    run_sm(f, n);
+    return -1;
+}
 EXPORT int32_t goldilocks_448_point_scalarmul_batch(hpt *o, const hpt *b, const hsc *s, size_t n) { SlotScalarmul f = {o, b, s, slots(1)}; run_smp(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_double_scalarmul_batch(hpt *o, const hpt *b1, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { SlotDoubleScalarmul f = {o, b1, s1, b2, s2, slots(2), (size_t)((g_threads + 31) / 32 * 32)}; run_smp(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_dual_scalarmul_batch(hpt *o1, hpt *o2, const hpt *b, const hsc *s1, const hsc *s2, size_t n) { SlotDualScalarmul f = {o1, o2, b, s1, s2, slots(1)}; run_smp(f, n); return -1; }
+EXPORT int32_t goldilocks_448_direct_scalarmul_batch(uint8_t *o, int32_t *st, const uint8_t *b, const hsc *s, uint64_t allow_identity, uint64_t short_circuit, size_t n) {
+    SlotDirectScalarmul f = {o, st, b, s, allow_identity ? 1u : 0u, short_circuit ? 1u : 0u, tables(), slots(1)};
+    run_smp(f, n);
+    return -1;
+}
+EXPORT int32_t goldilocks_448_precompute_batch(void *tables_out, const hpt *pts, size_t n) {
+    std::vector<niels> scratch(16 * COMB_N * n + 1);
+    LanePrecompute f = {(abi_niels *)tables_out, pts, scratch.data()};
+    run(f, COMB_N * n);
+    return -1;
+}
+EXPORT int32_t goldilocks_448_point_debugging_torque_batch(hpt *o, const hpt *a, size_t n) { LanePt<PTOP_TORQUE> f = {o, a, nullptr}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_point_debugging_pscale_batch(hpt *o, const hpt *a, const uint8_t *fac, size_t n) { LanePtPscale f = {o, a, fac}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_scalar_invert_batch(hsc *o, int32_t *st, const hsc *a, size_t n) { LaneScInvert f = {o, st, a}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_ed448_convert_public_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) { LaneEdPkToX448 f = {x, ed}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_ed448_convert_private_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) { LaneEdSkToX448 f = {x, ed}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *o, const hsc *s1, const hpt *b2, const hsc *s2, size_t n) { SlotBaseDoubleScalarmul f = {o, s1, b2, s2, wide_table(), slots(1)}; run_smp(f, n); return -1; }
 
 EXPORT int32_t goldilocks_448_scalar_add_batch(hsc *o, const hsc *a, const hsc *b, size_t n) { LaneSc<SCOP_ADD> f = {o, a, b}; run(f, n); return -1; }

@@ -260,3 +260,66 @@ def check_shake(lib, n=40):
 def check_tables(lib, chk):
     eq(lib.export_comb_table(), chk.export_comb_table(), "comb table (15360 B)")
     eq(lib.export_wnaf_table(), chk.export_wnaf_table(), "wNAF base table (6144 B)")
+
+
+def check_widened(lib, chk, n):
+    """the rest of the reference ABI that sits next to the hot path -- scalar_invert,
+    point_dual_scalarmul, direct_scalarmul, precompute + caller-supplied comb tables, key conversions,
+    debugging_torque/pscale.  Skipped against a checker that does not export them (the C restatement)."""
+    if not chk.has("goldilocks_448_scalar_invert_batch"):
+        import pytest
+        pytest.skip("checker has no widened entry points (reference build absent)")
+    c = util.coords_fast
+    # scalar_invert: random + edge scalars (0 fails, like the reference)
+    a = np.concatenate([util.random_scalars(chk, "w/inv", n), util.scalar_edge_bytes()])
+    r1, s1 = lib.scalar_invert(a)
+    r2, s2 = chk.scalar_invert(a)
+    eq(s1, s2, "scalar_invert status")
+    eq(r1, r2, "scalar_invert value")
+    ok = s2 == -1
+    one = np.zeros(56, np.uint8); one[0] = 1
+    assert (chk.scalar_mul(r1[ok], a[ok]) == one).all()
+    # dual scalarmul
+    m = max(8, n // 4)
+    p = util.random_points(chk, "w/p", m)
+    s = np.concatenate([util.random_scalars(chk, "w/s", m - 4), util.scalar_edge_bytes()[:4]])
+    t = util.random_scalars(chk, "w/t", m)
+    g1, g2 = lib.point_dual_scalarmul(p, s, t)
+    w1, w2 = chk.point_dual_scalarmul(p, s, t)
+    eq(chk.point_encode(g1), chk.point_encode(w1), "dual_scalarmul a1")
+    eq(chk.point_encode(g2), chk.point_encode(w2), "dual_scalarmul a2")
+    eq(chk.point_encode(g1), chk.point_encode(chk.point_scalarmul(p, s)), "dual_scalarmul a1 == scalarmul")
+    # direct scalarmul: valid encodings, random strings (most fail), identity
+    enc = chk.point_encode(p)
+    bad = stream_bytes("w/bad", m * 56).reshape(m, 56)
+    ident = np.zeros((1, 56), np.uint8)
+    base = np.concatenate([enc, bad, ident])
+    sc = np.concatenate([s, t, s[:1]])
+    for allow in (False, True):
+        for short in (False, True):
+            o1, st1 = lib.direct_scalarmul(base, sc, allow, short, prefill=0xa5)
+            o2, st2 = chk.direct_scalarmul(base, sc, allow, short, prefill=0xa5)
+            eq(st1, st2, "direct_scalarmul status allow=%s short=%s" % (allow, short))
+            eq(o1, o2, "direct_scalarmul bytes allow=%s short=%s" % (allow, short))
+    # precompute: byte-identical tables, and the comb over them
+    q = p[:3]
+    t1, t2 = lib.precompute(q), chk.precompute(q)
+    eq(t1, t2, "precompute tables (15360 B each)")
+    for k in range(len(q)):
+        got, want = lib.precomputed_scalarmul(s, table=t2[k]), chk.precomputed_scalarmul(s, table=t2[k])
+        eq(chk.point_encode(got), chk.point_encode(want), "precomputed_scalarmul over a caller table")
+        eq(chk.point_encode(got), chk.point_encode(chk.point_scalarmul(np.repeat(q[k:k + 1], len(s), axis=0), s)), "comb == scalarmul")
+    # key conversions
+    sk = stream_bytes("w/sk", n * 57).reshape(n, 57)
+    pk = chk.ed448_derive_public_key(sk)
+    extra = np.zeros((4, 57), np.uint8); extra[1] = le(1, 57); extra[2] = le(P - 1, 57); extra[3] = le(P + 3, 57)
+    pk = np.concatenate([pk, extra, stream_bytes("w/rndpk", 16 * 57).reshape(16, 57)])
+    eq(lib.convert_public_key_to_x448(pk), chk.convert_public_key_to_x448(pk), "convert_public_key_to_x448")
+    eq(lib.convert_private_key_to_x448(sk), chk.convert_private_key_to_x448(sk), "convert_private_key_to_x448")
+    xs = chk.convert_private_key_to_x448(sk[:8])
+    eq(lib.x448_derive_public_key(xs), chk.convert_public_key_to_x448(chk.ed448_derive_public_key(sk[:8])), "x448 pk of converted sk == converted ed pk")
+    # debugging helpers: same group element, exact coordinates
+    eq(c(chk, lib.debugging_torque(p)), c(chk, chk.debugging_torque(p)), "debugging_torque coords")
+    fac = np.concatenate([stream_bytes("w/fac", (m - 2) * 56).reshape(m - 2, 56), np.zeros((1, 56), np.uint8), le(P)[None]])
+    eq(c(chk, lib.debugging_pscale(p, fac)), c(chk, chk.debugging_pscale(p, fac)), "debugging_pscale coords")
+    eq(lib.point_eq(lib.debugging_pscale(p, fac), p), np.ones(m, bool), "pscale keeps the point")

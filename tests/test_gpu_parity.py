@@ -48,6 +48,10 @@ def test_scalarmul(gpu, chk):
     parity.check_scalarmul(gpu, chk, 1 << 11)
 
 
+def test_widened(gpu, chk):
+    parity.check_widened(gpu, chk, 1 << 10)
+
+
 def test_x448(gpu, chk, vectors):
     parity.check_x448(gpu, chk, 1 << 12)
     parity.check_x448_vectors(gpu, vectors, iters=1000)

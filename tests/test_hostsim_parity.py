@@ -59,3 +59,7 @@ def test_decaf_vectors(sim, vectors):
 
 def test_shake(sim):
     parity.check_shake(sim)
+
+
+def test_widened(sim, chk):
+    parity.check_widened(sim, chk, 96)

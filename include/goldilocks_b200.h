@@ -122,6 +122,26 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify(const uint8_t sig
 /* reference ed448.h:234-262 / goldilocks.c:1079-1103, eddsa.c:83-95 */
 GOLDILOCKS_B200_API void goldilocks_ed448_convert_public_key_to_x448(uint8_t x[56], const uint8_t ed[57]);
 GOLDILOCKS_B200_API void goldilocks_ed448_convert_private_key_to_x448(uint8_t x[56], const uint8_t ed[57]);
+/* Streaming SHA-3 / SHAKE objects (reference shake.h:27-120, keccak_internal.h, shake.c:89-250) and the Ed448ph
+ * entry points built on them (ed448.h:36-46,107-137,170-190 / eddsa.c:76-80,232-251,309-329).  The sponge object
+ * is the reference's (26 x u64, caller-owned); every Keccak-f runs on the device, one round trip per call --
+ * bulk hashing belongs in goldilocks_shake256_hash_batch. */
+typedef struct goldilocks_keccak_sponge_s { uint64_t opaque[26]; } goldilocks_keccak_sponge_s, goldilocks_keccak_sponge_p[1];
+struct goldilocks_kparams_s { uint8_t position, flags, rate, start_round, pad, rate_pad, max_out, remaining; };
+GOLDILOCKS_B200_API extern const struct goldilocks_kparams_s GOLDILOCKS_SHAKE128_params_s, GOLDILOCKS_SHAKE256_params_s,
+    GOLDILOCKS_SHA3_224_params_s, GOLDILOCKS_SHA3_256_params_s, GOLDILOCKS_SHA3_384_params_s, GOLDILOCKS_SHA3_512_params_s;
+GOLDILOCKS_B200_API void goldilocks_sha3_init(goldilocks_keccak_sponge_p sponge, const struct goldilocks_kparams_s *params);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_sha3_update(struct goldilocks_keccak_sponge_s *sponge, const uint8_t *in, size_t len);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_sha3_output(goldilocks_keccak_sponge_p sponge, uint8_t *out, size_t len);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_sha3_final(goldilocks_keccak_sponge_p sponge, uint8_t *out, size_t len);
+GOLDILOCKS_B200_API void goldilocks_sha3_reset(goldilocks_keccak_sponge_p sponge);
+GOLDILOCKS_B200_API void goldilocks_sha3_destroy(goldilocks_keccak_sponge_p sponge);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_sha3_hash(uint8_t *out, size_t outlen, const uint8_t *in, size_t inlen, const struct goldilocks_kparams_s *params);
+GOLDILOCKS_B200_API size_t goldilocks_sha3_default_output_bytes(const goldilocks_keccak_sponge_p sponge);
+GOLDILOCKS_B200_API size_t goldilocks_sha3_max_output_bytes(const goldilocks_keccak_sponge_p sponge);
+GOLDILOCKS_B200_API void goldilocks_ed448_prehash_init(goldilocks_keccak_sponge_p hash);
+GOLDILOCKS_B200_API void goldilocks_ed448_sign_prehash(uint8_t signature[114], const uint8_t privkey[57], const uint8_t pubkey[57], const goldilocks_keccak_sponge_p hash, const uint8_t *context, uint8_t context_len);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_prehash(const uint8_t signature[114], const uint8_t pubkey[57], const goldilocks_keccak_sponge_p hash, const uint8_t *context, uint8_t context_len);
 /* reference point_448.h:113-233 / scalar.c */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_scalar_invert(goldilocks_448_scalar_p out, const goldilocks_448_scalar_p a);
 GOLDILOCKS_B200_API goldilocks_bool_t goldilocks_448_scalar_eq(const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b);

@@ -871,6 +871,95 @@ void goldilocks_448_scalar_set_unsigned(goldilocks_448_scalar_p out, uint64_t w)
 void goldilocks_448_scalar_destroy(goldilocks_448_scalar_p s) { goldilocks_bzero(s, sizeof(goldilocks_448_scalar_s)); }
 void goldilocks_448_point_destroy(goldilocks_448_point_p p) { goldilocks_bzero(p, sizeof(goldilocks_448_point_s)); }
 void goldilocks_448_precomputed_destroy(goldilocks_448_precomputed_s *t) { goldilocks_bzero(t, 15360); }
+// ---- streaming SHA-3 / SHAKE objects and Ed448ph (reference shake.c:89-250, eddsa.c:76-80,232-251,309-329) ----
+#define KP(n, rate, pad, maxo) const struct goldilocks_kparams_s n = {0, 'A', rate, 0, pad, 0x80, maxo, maxo};
+KP(GOLDILOCKS_SHAKE128_params_s, 200 - 128 / 4, 0x1f, 0xFF)
+KP(GOLDILOCKS_SHAKE256_params_s, 200 - 256 / 4, 0x1f, 0xFF)
+KP(GOLDILOCKS_SHA3_224_params_s, 200 - 224 / 4, 0x06, 224 / 8)
+KP(GOLDILOCKS_SHA3_256_params_s, 200 - 256 / 4, 0x06, 256 / 8)
+KP(GOLDILOCKS_SHA3_384_params_s, 200 - 384 / 4, 0x06, 384 / 8)
+KP(GOLDILOCKS_SHA3_512_params_s, 200 - 512 / 4, 0x06, 512 / 8)
+#undef KP
+static_assert(sizeof(goldilocks_keccak_sponge_s) == sizeof(sponge_abi) && sizeof(sponge_abi) == 208, "sponge layout (keccak_internal.h)");
+static sponge_abi *SP(goldilocks_keccak_sponge_s *s) { return (sponge_abi *)s; }
+void goldilocks_sha3_init(goldilocks_keccak_sponge_p sponge, const struct goldilocks_kparams_s *params) {
+    struct goldilocks_kparams_s p = *params; /* params may alias the sponge's own copy (reset) */
+    memset(sponge, 0, sizeof(goldilocks_keccak_sponge_s));
+    memcpy(&SP(sponge)->position, &p, sizeof p);
+    SP(sponge)->position = 0;
+}
+void goldilocks_sha3_reset(goldilocks_keccak_sponge_p sponge) {
+    goldilocks_sha3_init(sponge, (const struct goldilocks_kparams_s *)&SP(sponge)->position);
+    SP(sponge)->flags = 'A';
+    SP(sponge)->remaining = SP(sponge)->max_out;
+}
+void goldilocks_sha3_destroy(goldilocks_keccak_sponge_p sponge) { goldilocks_bzero(sponge, sizeof(goldilocks_keccak_sponge_s)); }
+goldilocks_error_t goldilocks_sha3_update(struct goldilocks_keccak_sponge_s *sponge, const uint8_t *in, size_t len) {
+    sponge_abi *h = SP(sponge);
+    if (h->start_round != 0 || h->rate == 0 || h->rate >= 200 || h->position >= h->rate) return GOLDILOCKS_FAILURE;
+    if (len) {
+        Call k;
+        LaneSpongeUpdate f = {k.in(h, 1), k.in(in, len), len};
+        k.run(f, 1);
+        k.fetch(h, f.sp, 1);
+        if (k.finish() != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
+    }
+    return h->flags == 'A' ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_sha3_output(goldilocks_keccak_sponge_p sponge, uint8_t *out, size_t len) {
+    sponge_abi *h = SP(sponge);
+    if (h->start_round != 0 || h->rate == 0 || h->rate >= 200 || h->position >= h->rate) return GOLDILOCKS_FAILURE;
+    Call k;
+    LaneSpongeOutput f = {k.in(h, 1), k.out<uint8_t>(len), len, k.out<int32_t>(1)};
+    k.run(f, 1);
+    int32_t st = 0;
+    k.fetch(h, f.sp, 1);
+    k.fetch(out, f.out, len);
+    k.fetch(&st, f.status, 1);
+    if (k.finish() != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
+    return st == -1 ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_sha3_final(goldilocks_keccak_sponge_p sponge, uint8_t *out, size_t len) {
+    goldilocks_error_t ret = goldilocks_sha3_output(sponge, out, len);
+    goldilocks_sha3_reset(sponge);
+    return ret;
+}
+goldilocks_error_t goldilocks_sha3_hash(uint8_t *out, size_t outlen, const uint8_t *in, size_t inlen, const struct goldilocks_kparams_s *params) {
+    goldilocks_keccak_sponge_p sponge;
+    goldilocks_sha3_init(sponge, params);
+    goldilocks_sha3_update(sponge, in, inlen);
+    goldilocks_error_t ret = goldilocks_sha3_output(sponge, out, outlen);
+    goldilocks_sha3_destroy(sponge);
+    return ret;
+}
+size_t goldilocks_sha3_default_output_bytes(const goldilocks_keccak_sponge_p s) {
+    const sponge_abi *h = (const sponge_abi *)s;
+    return h->max_out == 0xFF ? (size_t)(200 - h->rate) : (size_t)((200 - h->rate) / 2);
+}
+size_t goldilocks_sha3_max_output_bytes(const goldilocks_keccak_sponge_p s) {
+    const sponge_abi *h = (const sponge_abi *)s;
+    return h->max_out == 0xFF ? SIZE_MAX : (size_t)((200 - h->rate) / 2);
+}
+void goldilocks_ed448_prehash_init(goldilocks_keccak_sponge_p hash) { goldilocks_sha3_init(hash, &GOLDILOCKS_SHAKE256_params_s); }
+static void prehash_output(uint8_t ph[64], const goldilocks_keccak_sponge_p hash) {
+    goldilocks_keccak_sponge_p too;
+    memcpy(too, hash, sizeof(too));
+    goldilocks_sha3_final(too, ph, 64);
+    goldilocks_sha3_destroy(too);
+}
+void goldilocks_ed448_sign_prehash(uint8_t signature[114], const uint8_t privkey[57], const uint8_t pubkey[57], const goldilocks_keccak_sponge_p hash,
+                                   const uint8_t *context, uint8_t context_len) {
+    uint8_t ph[64];
+    prehash_output(ph, hash);
+    goldilocks_ed448_sign(signature, privkey, pubkey, ph, sizeof ph, 1, context, context_len);
+    goldilocks_bzero(ph, sizeof ph);
+}
+goldilocks_error_t goldilocks_ed448_verify_prehash(const uint8_t signature[114], const uint8_t pubkey[57], const goldilocks_keccak_sponge_p hash,
+                                                   const uint8_t *context, uint8_t context_len) {
+    uint8_t ph[64];
+    prehash_output(ph, hash);
+    return goldilocks_ed448_verify(signature, pubkey, ph, sizeof ph, 1, context, context_len);
+}
 void goldilocks_448_scalar_add(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { goldilocks_448_scalar_add_batch(o, a, b, 1); }
 void goldilocks_448_scalar_sub(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { goldilocks_448_scalar_sub_batch(o, a, b, 1); }
 void goldilocks_448_scalar_mul(goldilocks_448_scalar_p o, const goldilocks_448_scalar_p a, const goldilocks_448_scalar_p b) { goldilocks_448_scalar_mul_batch(o, a, b, 1); }

@@ -245,6 +245,76 @@ struct LaneScDecodeLong {
 
 struct ByteAtWords { const uint32_t *w; GDM uint8_t operator()(int k) const { return (uint8_t)(w[k >> 2] >> (8 * (k & 3))); } };
 
+// ---- streaming SHA-3 / SHAKE front end (reference shake.c:89-213) ------------------------------------
+// The caller-owned sponge object of goldilocks/shake.h (26 x u64: 200 state bytes + 8 parameter bytes,
+// keccak_internal.h) is copied to the device, one lane runs the reference's absorb / pad / squeeze loop
+// with every Keccak-f on the device, and the object is copied back.  Bulk hashing belongs in
+// goldilocks_shake256_hash_batch; this exists so prehash (Ed448ph) callers keep working.
+struct sponge_abi { uint64_t w[25]; uint8_t position, flags, rate, start_round, pad, rate_pad, max_out, remaining; };
+GD void sponge_permute(sponge_abi *s) { /* dokeccak (keccak_internal.h): start_round is 0 for every exported parameter set */
+    keccak_state st;
+#pragma unroll
+    for (int i = 0; i < 25; i++) st.a[i] = s->w[i];
+    keccak_f1600(st);
+#pragma unroll
+    for (int i = 0; i < 25; i++) s->w[i] = st.a[i];
+    s->position = 0;
+}
+struct LaneSpongeUpdate { /* shake.c:89-112 */
+    sponge_abi *sp; const uint8_t *in; size_t len;
+    GDM void operator()(size_t) const {
+        uint8_t *b = (uint8_t *)sp->w;
+        const uint8_t *p = in;
+        size_t left = len;
+        while (left) {
+            const size_t cando = (size_t)sp->rate - sp->position;
+            uint8_t *state = b + sp->position;
+            if (cando > left) {
+                for (size_t i = 0; i < left; i++) state[i] ^= p[i];
+                sp->position = (uint8_t)(sp->position + left);
+                break;
+            }
+            for (size_t i = 0; i < cando; i++) state[i] ^= p[i];
+            sponge_permute(sp);
+            left -= cando;
+            p += cando;
+        }
+    }
+};
+struct LaneSpongeOutput { /* shake.c:114-162; status = FAILURE when more than max_out bytes were asked of a fixed-length hash */
+    sponge_abi *sp; uint8_t *out; size_t len; int32_t *status;
+    GDM void operator()(size_t) const {
+        int32_t ret = -1;
+        if (sp->max_out != 0xFF) {
+            if (sp->remaining >= len) sp->remaining = (uint8_t)(sp->remaining - len);
+            else { sp->remaining = 0; ret = 0; }
+        }
+        uint8_t *b = (uint8_t *)sp->w;
+        if (sp->flags == 'A') {
+            b[sp->position] ^= sp->pad;
+            b[sp->rate - 1] ^= sp->rate_pad;
+            sponge_permute(sp);
+            sp->flags = 'Z';
+        }
+        uint8_t *o = out;
+        size_t left = len;
+        while (left) {
+            const size_t cando = (size_t)sp->rate - sp->position;
+            const uint8_t *state = b + sp->position;
+            if (cando > left) {
+                for (size_t i = 0; i < left; i++) o[i] = state[i];
+                sp->position = (uint8_t)(sp->position + left);
+                break;
+            }
+            for (size_t i = 0; i < cando; i++) o[i] = state[i];
+            sponge_permute(sp);
+            left -= cando;
+            o += cando;
+        }
+        status[0] = ret;
+    }
+};
+
 // ---- EdDSA <-> X448 key conversions ----------------------------------------------------------------
 struct LaneEdPkToX448 { /* goldilocks_ed448_convert_public_key_to_x448 (goldilocks.c:1079-1103): u = y^2 (1 - d y^2) / (1 - y^2) */
     uint8_t *x; const uint8_t *ed;

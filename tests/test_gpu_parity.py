@@ -105,6 +105,65 @@ def test_legacy_single_element_symbols(gpu, vectors):
     assert L.goldilocks_x448(out, zero, base) == 0 and bytes(out) == bytes(56)
 
 
+def test_streaming_sha3_and_prehash(gpu, vectors):
+    """goldilocks_sha3_* objects (reference shake.c) and Ed448ph through them (eddsa.c:232-251,309-329):
+    FIPS 202 outputs from hashlib for every exported parameter set, multi-part update/output, and the
+    RFC 8032 Ed448ph vectors through sign_prehash / verify_prehash."""
+    import ctypes as C
+    import hashlib
+    L = gpu.lib
+    for f in ("goldilocks_sha3_update", "goldilocks_sha3_output", "goldilocks_sha3_final", "goldilocks_sha3_hash", "goldilocks_ed448_verify_prehash"):
+        getattr(L, f).restype = C.c_int32
+    L.goldilocks_sha3_default_output_bytes.restype = C.c_size_t
+    msg = bytes(stream_bytes("sha3/msg", 1000))
+    cases = [("GOLDILOCKS_SHAKE128_params_s", hashlib.shake_128, None), ("GOLDILOCKS_SHAKE256_params_s", hashlib.shake_256, None),
+             ("GOLDILOCKS_SHA3_224_params_s", hashlib.sha3_224, 28), ("GOLDILOCKS_SHA3_256_params_s", hashlib.sha3_256, 32),
+             ("GOLDILOCKS_SHA3_384_params_s", hashlib.sha3_384, 48), ("GOLDILOCKS_SHA3_512_params_s", hashlib.sha3_512, 64)]
+    for sym, href, fixed in cases:
+        params = C.c_void_p(C.addressof(C.c_uint8.in_dll(L, sym)))
+        for cut in (0, 1, 135, 136, 137, 500, 1000):
+            sp = (C.c_uint64 * 26)()
+            L.goldilocks_sha3_init(sp, params)
+            buf = (C.c_uint8 * 1000).from_buffer_copy(msg)
+            assert L.goldilocks_sha3_update(sp, buf, C.c_size_t(cut)) == -1
+            rest = (C.c_uint8 * (1000 - cut)).from_buffer_copy(msg[cut:]) if cut < 1000 else None
+            assert L.goldilocks_sha3_update(sp, rest, C.c_size_t(1000 - cut)) == -1
+            if fixed is None:
+                o1, o2 = (C.c_uint8 * 100)(), (C.c_uint8 * 300)()
+                assert L.goldilocks_sha3_output(sp, o1, C.c_size_t(100)) == -1
+                assert L.goldilocks_sha3_output(sp, o2, C.c_size_t(300)) == -1
+                assert bytes(o1) + bytes(o2) == href(msg).digest(400), "%s cut %d" % (sym, cut)
+            else:
+                assert L.goldilocks_sha3_default_output_bytes(sp) == fixed
+                o = (C.c_uint8 * fixed)()
+                assert L.goldilocks_sha3_final(sp, o, C.c_size_t(fixed)) == -1
+                assert bytes(o) == href(msg).digest(), "%s cut %d" % (sym, cut)
+                o2 = (C.c_uint8 * (fixed + 1))()
+                L.goldilocks_sha3_update(sp, buf, C.c_size_t(3))
+                assert L.goldilocks_sha3_output(sp, o2, C.c_size_t(fixed + 1)) == 0   # more than max_out: FAILURE like the reference
+    o = (C.c_uint8 * 64)()
+    assert L.goldilocks_sha3_hash(o, C.c_size_t(64), (C.c_uint8 * 1000).from_buffer_copy(msg), C.c_size_t(1000), C.c_void_p(C.addressof(C.c_uint8.in_dll(L, "GOLDILOCKS_SHAKE256_params_s")))) == -1
+    assert bytes(o) == hashlib.shake_256(msg).digest(64)
+    done = 0
+    for c in vectors["eddsa"]:
+        if not c["prehashed"]:
+            continue
+        m = bytes.fromhex(c["msg"]); ctx = bytes.fromhex(c["context"])
+        sk = (C.c_uint8 * 57).from_buffer_copy(bytes.fromhex(c["sk"])); pk = (C.c_uint8 * 57).from_buffer_copy(bytes.fromhex(c["pk"]))
+        cb = (C.c_uint8 * max(1, len(ctx))).from_buffer_copy(ctx or b"\0")
+        h = (C.c_uint64 * 26)()
+        L.goldilocks_ed448_prehash_init(h)
+        L.goldilocks_sha3_update(h, (C.c_uint8 * max(1, len(m))).from_buffer_copy(m or b"\0"), C.c_size_t(len(m)))
+        sig = (C.c_uint8 * 114)()
+        L.goldilocks_ed448_sign_prehash(sig, sk, pk, h, cb, C.c_uint8(len(ctx)))
+        assert bytes(sig).hex() == c["sig"], "Ed448ph signature"
+        assert L.goldilocks_ed448_verify_prehash(sig, pk, h, cb, C.c_uint8(len(ctx))) == -1
+        L.goldilocks_sha3_update(h, (C.c_uint8 * 1)(1), C.c_size_t(1))
+        assert L.goldilocks_ed448_verify_prehash(sig, pk, h, cb, C.c_uint8(len(ctx))) == 0
+        done += 1
+    assert done >= 1
+
+
 # ---- size-independent properties at the full 2^20 batch -------------------------------------------
 
 def test_x448_full_dh_commutes(gpu, chk):

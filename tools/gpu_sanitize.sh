@@ -1,0 +1,30 @@
+cd $GRAFT_REPO_ROOT
+cat > /tmp/san_small.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np
+import libgoldilocks_b200 as g
+from util import stream_bytes
+lib = g.load()
+n = 200
+sk = stream_bytes("san/sk", n * 57).reshape(n, 57)
+msgs = [bytes(stream_bytes("san/m%d" % i, i % 40)) for i in range(n)]
+pk = lib.ed448_derive_public_key(sk)
+sig = lib.ed448_sign(sk, pk, msgs)
+st = lib.ed448_verify(sig, pk, msgs)
+assert (st == -1).all()
+u = stream_bytes("san/u", n * 56).reshape(n, 56); k = stream_bytes("san/k", n * 56).reshape(n, 56)
+o, s = lib.x448(u, k)
+sc = lib.scalar_decode_long(k, 56)
+p = lib.precomputed_scalarmul(sc)
+q = lib.point_scalarmul(p, sc)
+r = lib.point_double_scalarmul(p, sc, q, sc)
+d1, d2 = lib.point_dual_scalarmul(p, sc, sc[::-1].copy())
+e, st2 = lib.direct_scalarmul(lib.point_encode(p), sc)
+lib.x448_derive_public_key(k)
+t = lib.precompute(p[:2]); lib.precomputed_scalarmul(sc, table=t[0])
+print("san small ok")
+PY
+for tool in memcheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san_small.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|san small ok|Error|hazard" | head -12
+done

@@ -11,8 +11,6 @@
 
 // Resident blocks per SM the register allocator is asked to allow (default: whatever fits).
 template <class F> struct lane_min_blocks { static constexpr int value = 1; };
-// Measured on B200 at 2^20 (tools/opbench.py): comb 34.5 -> 38.5 Mops/s with 3 blocks (168 regs, no spills);
-// X448 gains 1% at 3 blocks but spills, so it stays at 2.
 
 template <class F>
 __global__ void __launch_bounds__(BLOCK, lane_min_blocks<F>::value) k_lanes(F f, size_t n) {

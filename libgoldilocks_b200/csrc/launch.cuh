@@ -34,7 +34,7 @@ template <> struct slot_min_blocks<SlotDualScalarmul> { static constexpr int val
 template <> struct slot_min_blocks<SlotDirectScalarmul> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotScalarmul> { static constexpr int value = 3; };
 template <> struct slot_min_blocks<SlotDoubleScalarmul> { static constexpr int value = 3; };
-template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int value = 4; };
+template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int value = 4; }; /* 3 blocks (no spills): 111.7 vs 110.9 ms */
 template <> struct slot_min_blocks<SlotBaseDoubleScalarmul> { static constexpr int value = 4; };
 template <class F>
 cudaError_t launch_sm(const F &f, size_t n, cudaStream_t s) {

@@ -24,16 +24,19 @@ cudaError_t launch_lanes(const F &f, size_t n, cudaStream_t s) {
 }
 // Slot-machine kernels (slots.cuh): F::NSLOTS x 64 B of dynamic shared memory per lane.
 // Resident blocks per SM: measured choice per functor (registers <= 65536 / (128 * blocks)).
+#ifndef SLOT7_MIN_BLOCKS
+#define SLOT7_MIN_BLOCKS 4 /* 7 slots = 56 KB per block: four blocks (16 warps) per SM, 128 registers */
+#endif
 template <> struct slot_min_blocks<SlotX448> { static constexpr int value = 4; };
-template <> struct slot_min_blocks<SlotComb> { static constexpr int value = 3; };
-template <> struct slot_min_blocks<SlotX448DerivePk> { static constexpr int value = 3; };
-template <> struct slot_min_blocks<SlotEdDerivePk> { static constexpr int value = 3; };
-template <> struct slot_min_blocks<SlotEdSignR> { static constexpr int value = 3; };
-template <> struct slot_min_blocks<SlotCombTable> { static constexpr int value = 3; };
-template <> struct slot_min_blocks<SlotDualScalarmul> { static constexpr int value = 3; };
-template <> struct slot_min_blocks<SlotDirectScalarmul> { static constexpr int value = 3; };
-template <> struct slot_min_blocks<SlotScalarmul> { static constexpr int value = 3; };
-template <> struct slot_min_blocks<SlotDoubleScalarmul> { static constexpr int value = 3; };
+template <> struct slot_min_blocks<SlotComb> { static constexpr int value = SLOT7_MIN_BLOCKS; };
+template <> struct slot_min_blocks<SlotX448DerivePk> { static constexpr int value = SLOT7_MIN_BLOCKS; };
+template <> struct slot_min_blocks<SlotEdDerivePk> { static constexpr int value = SLOT7_MIN_BLOCKS; };
+template <> struct slot_min_blocks<SlotEdSignR> { static constexpr int value = SLOT7_MIN_BLOCKS; };
+template <> struct slot_min_blocks<SlotCombTable> { static constexpr int value = SLOT7_MIN_BLOCKS; };
+template <> struct slot_min_blocks<SlotDualScalarmul> { static constexpr int value = SLOT7_MIN_BLOCKS; };
+template <> struct slot_min_blocks<SlotDirectScalarmul> { static constexpr int value = SLOT7_MIN_BLOCKS; };
+template <> struct slot_min_blocks<SlotScalarmul> { static constexpr int value = SLOT7_MIN_BLOCKS; };
+template <> struct slot_min_blocks<SlotDoubleScalarmul> { static constexpr int value = SLOT7_MIN_BLOCKS; };
 template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int value = 4; }; /* 3 blocks (no spills): 111.7 vs 110.9 ms */
 template <> struct slot_min_blocks<SlotBaseDoubleScalarmul> { static constexpr int value = 4; };
 template <class F>

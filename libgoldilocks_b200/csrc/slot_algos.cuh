@@ -13,7 +13,7 @@
 // on return its inverse is in slot `zout`.  Warp 0 does the work for the four lanes (w, l), w = 0..3, that
 // share lane index l: 3 prefix products, ONE inversion chain, 6 multiplications -- the other three warps
 // wait at the barrier (other resident blocks keep the multiplier busy).  All 128 lanes of the block must
-// call it (k_slots keeps out-of-range lanes alive for this); slots 0..4 of every lane are clobbered.
+// call it (k_slots keeps out-of-range lanes alive for this); slots 0..2 and `zout` of every lane are clobbered.
 // Constant time: the schedule is fixed, operands are only multiplied.
 GD void s_block_invert4(sref sb, int zin, int zout) {
     __syncthreads();
@@ -22,11 +22,11 @@ GD void s_block_invert4(sref sb, int zin, int zout) {
 #pragma unroll
         for (int w = 0; w < 4; w++) t[w] = s_lane_shift(sb, 32u * w);
         const sref z0 = s_slot(t[0], zin), z1 = s_slot(t[1], zin), z2 = s_slot(t[2], zin), z3 = s_slot(t[3], zin);
-        const sref p1 = s_slot(t[0], 0), p2 = s_slot(t[0], 1), p3 = s_slot(t[0], 2), inv = s_slot(t[0], 3);
+        const sref p1 = s_slot(t[0], 0), p2 = s_slot(t[0], 1), p3 = s_slot(t[0], 2), inv = s_slot(t[1], 0);
         s_mul(p1, z0, z1);
         s_mul(p2, p1, z2);
         s_mul(p3, p2, z3);
-        s_invert(inv, p3, s_slot(t[1], 0), s_slot(t[1], 1));
+        s_invert(inv, p3, s_slot(t[1], 1), s_slot(t[1], 2));
         s_mul(s_slot(t[3], zout), inv, p2);
         s_mul(inv, inv, z3);
         s_mul(s_slot(t[2], zout), inv, p1);
@@ -137,14 +137,9 @@ struct swk { sref t0, t1, t2; };
 // p = 2p.  4S + 3M (+1M for T).  (goldilocks.c:232-254 point_double_internal)  T is dead on entry
 // and serves as the fourth temporary.
 GD void s_pt_double(const spt &p, const swk &w, bool before_double) { /* 9 (10 with T) slot operations */
-#if defined(SLOT_FUSE2)
-    s_sqr2_addsub(p.t, w.t1, p.x, p.y); /* d = y^2 + x^2 ; e = y^2 - x^2 (one pass: -0.6 % on verify) */
-    s_sqr_sum_sub(w.t2, p.y, p.x, p.t); /* b = (x+y)^2 - d */
-#else
     s_sqr_sum(w.t2, p.y, p.x);          /* (x+y)^2 */
     s_sqr2_addsub(p.t, w.t1, p.x, p.y); /* d = y^2 + x^2 ; e = y^2 - x^2 (one pass: -0.6 % on verify) */
-    s_sub(w.t2, w.t2, p.t);            /* b = (x+y)^2 - d */
-#endif
+    s_sub(w.t2, w.t2, p.t);            /* b = (x+y)^2 - d  (fusing this into the square above: no gain) */
     s_sqr2_sub(w.t0, p.z, w.t1);       /* a' = 2 z^2 - e */
     s_mul(p.x, w.t0, w.t2);
     s_mul(p.z, w.t1, w.t0);
@@ -272,21 +267,23 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
 
 // ---------------------------------------------------------------------------------------------
 // Fixed-base signed comb, constant time -- reference goldilocks.c:830-877 (same digits, table and
-// operation order as comb_scalarmul in algos.cuh).  9 slots: X,Y,Z,T, three temporaries and two
-// lookup slots; the three coordinates of the selected entry are fetched just in time (a and b, then c),
-// the conditional negation of the entry is a handle selection (goldilocks.c:271-278).
+// operation order as comb_scalarmul in algos.cuh).  7 slots: X,Y,Z,T and three temporaries; the three
+// coordinates of the selected entry are fetched just in time (a and b, then c) into slots that are dead at
+// that point, the conditional negation of the entry is a handle selection (goldilocks.c:271-278).
 // ---------------------------------------------------------------------------------------------
-#define COMB_NSLOTS 9
-// p += (+-) entry idx of the 16-entry comb row; `first` = true sets p to the entry instead (niels_to_pt)
-GD void s_pt_add_niels_ct(const spt &p, const swk &w, sref la, sref lb, const niels *row, uint32_t idx, gmask_t neg, bool before_double) {
+#define COMB_NSLOTS 7
+// p += (+-) entry idx of a 16-entry row of affine niels, constant time in idx and the sign.  No extra
+// slots: once y+x and y-x are taken, X and Y are dead until the end and receive the looked-up a and b
+// (then c); (goldilocks.c:315-359 with the sign as a handle selection, 271-278).
+GD void s_pt_add_niels_ct(const spt &p, const swk &w, const niels *row, uint32_t idx, gmask_t neg, bool before_double) {
     const int stride = (int)(sizeof(niels) / sizeof(uint4));
-    s_lookup_ct<true, 1>(la, gq(&row->a), stride, 1 << (COMB_T - 1), idx);
-    s_lookup_ct<true, 1>(lb, gq(&row->b), stride, 1 << (COMB_T - 1), idx);
     s_addsub(w.t1, w.t0, p.y, p.x);                      /* y+x ; y-x */
-    s_mul(w.t0, w.t0, s_sel(la, lb, neg));               /* a  = e.a (y-x) */
-    s_mul(w.t1, w.t1, s_sel(lb, la, neg));               /* dy = e.b (y+x) */
-    s_lookup_ct<true, 1>(la, gq(&row->c), stride, 1 << (COMB_T - 1), idx);
-    s_mul(p.x, p.t, la);                                 /* x  = e.c t */
+    s_lookup_ct<true, 1>(p.x, gq(&row->a), stride, 1 << (COMB_T - 1), idx);
+    s_lookup_ct<true, 1>(p.y, gq(&row->b), stride, 1 << (COMB_T - 1), idx);
+    s_mul(w.t0, w.t0, s_sel(p.x, p.y, neg));             /* a  = e.a (y-x) */
+    s_mul(w.t1, w.t1, s_sel(p.y, p.x, neg));             /* dy = e.b (y+x) */
+    s_lookup_ct<true, 1>(p.y, gq(&row->c), stride, 1 << (COMB_T - 1), idx);
+    s_mul(p.x, p.t, p.y);                                /* x  = e.c t */
     s_addsub(w.t2, w.t1, w.t1, w.t0);                    /* c = dy + a ; b = dy - a */
     s_addsub(w.t0, p.y, p.z, p.x);                       /* v = z + x ; u = z - x */
     s_mul(p.z, w.t0, p.y);
@@ -299,7 +296,6 @@ GD void s_pt_add_niels_ct(const spt &p, const swk &w, sref la, sref lb, const ni
 GD void s_comb_scalarmul(sref sb, const niels *win, const sc &scalar) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
     const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
-    const sref la = s_slot(sb, 7), lb = s_slot(sb, 8);
     sc s1x;
     sc_recode_signed(s1x, scalar);
     { /* accumulator = identity; the unified addition law takes the first entry from there */
@@ -315,7 +311,7 @@ GD void s_comb_scalarmul(sref sb, const niels *win, const sc &scalar) {
         const gmask_t invert = (gmask_t)((int32_t)(tab >> (COMB_T - 1)) - 1);
         tab ^= invert;
         tab &= (1u << (COMB_T - 1)) - 1;
-        s_pt_add_niels_ct(p, w, la, lb, win + 16 * j, tab, invert, false);
+        s_pt_add_niels_ct(p, w, win + 16 * j, tab, invert, false);
     }
 }
 
@@ -334,7 +330,7 @@ GD gmask_t s_nonzero_or_one(sref zin, sref z) {
     s_st(zin, v);
     return nz;
 }
-// slot 4 <- 1 / slot 5 (slot 5 nonzero); slots 0..3 are scratch, slots >= 6 are preserved
+// slot 4 <- 1 / slot 5 (slot 5 nonzero); slots 0..2 are scratch, slots 3 and 6 are preserved
 GD void s_invert_5_to_4(sref sb) {
 #if defined(__CUDA_ARCH__)
     s_block_invert4(sb, 5, 4);
@@ -346,17 +342,16 @@ GD void s_invert_5_to_4(sref sb) {
 // yw = canonical y words, xsign = low bit of x.
 GD void s_encode_like_eddsa(uint32_t yw[14], uint32_t &xsign, sref sb) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
-    const sref t0 = s_slot(sb, 4), t1 = s_slot(sb, 5), t2 = s_slot(sb, 6), xs = s_slot(sb, 6), ys = s_slot(sb, 7);
+    const sref t0 = s_slot(sb, 4), t1 = s_slot(sb, 5), t2 = s_slot(sb, 6), xs = s_slot(sb, 6), ys = s_slot(sb, 3);
     s_sqr(t0, p.x);                    /* x^2 */
     s_sqr(t1, p.y);                    /* y^2 */
     s_sqr_sum(t2, p.y, p.x);
     s_addsub(p.t, t1, t1, t0);         /* u = y^2 + x^2 ; z = y^2 - x^2 */
     s_sub(t2, t2, p.t);                /* 2xy */
     s_sqr2_sub(t0, p.z, t1);           /* t = 2 z^2 - (y^2 - x^2) */
-    s_mul(p.x, t0, t2);                /* x = t * 2xy */
-    s_mul(ys, t1, p.t);                /* y = (y^2 - x^2) u */
+    s_mul(xs, t0, t2);                 /* x = t * 2xy        (t2 = slot 6 is read before it is written) */
     s_mul(p.z, p.t, t0);               /* z = u t */
-    s_copy(xs, p.x);
+    s_mul(ys, t1, p.t);                /* y = (y^2 - x^2) u  (in place over u, slot 3) */
     const gmask_t nz = s_nonzero_or_one(s_slot(sb, 5), p.z);
     s_invert_5_to_4(sb);
     s_mul(xs, xs, s_slot(sb, 4));      /* affine x */
@@ -386,23 +381,23 @@ GD void s_encode_like_x448(uint32_t uw[14], sref sb) {
 // Variable-base scalar multiplication, constant time -- reference goldilocks.c:405-465 (and 467-541
 // for two bases): signed 5-bit fixed windows over this lane's own table of 16 odd multiples in global
 // memory; every lookup scans the whole table with masks (s_lookup_ct_rw), the sign is a handle
-// selection.  9 slots; the accumulator starts from the identity (unified addition law) instead of
+// selection.  7 slots; the accumulator starts from the identity (unified addition law) instead of
 // pniels_to_pt of the first digit -- same group element.
 // ---------------------------------------------------------------------------------------------
-#define WINDOW_NSLOTS 9
+#define WINDOW_NSLOTS 7
 // p += (+-) table[idx], constant time in idx and the sign (`neg` all-ones = subtract).  The table is in
 // the warp-interleaved layout, so each of the 4 x 16 x 4 loads of the scan is one coalesced 512-byte row.
-GD void s_pt_add_pniels_ct(const spt &p, const swk &w, sref la, sref lb, const wtab<32> &t, uint32_t idx, gmask_t neg, bool before_double) {
+GD void s_pt_add_pniels_ct(const spt &p, const swk &w, const wtab<32> &t, uint32_t idx, gmask_t neg, bool before_double) {
     const int es = wtab<32>::ESTRIDE;
-    s_lookup_ct<false, 32>(la, t.coord(0, 3), es, WINDOW_NTABLE, idx);
-    s_mul(p.z, p.z, la);
-    s_lookup_ct<false, 32>(la, t.coord(0, 0), es, WINDOW_NTABLE, idx);
-    s_lookup_ct<false, 32>(lb, t.coord(0, 1), es, WINDOW_NTABLE, idx);
-    s_addsub(w.t1, w.t0, p.y, p.x);
-    s_mul(w.t0, w.t0, s_sel(la, lb, neg));
-    s_mul(w.t1, w.t1, s_sel(lb, la, neg));
-    s_lookup_ct<false, 32>(la, t.coord(0, 2), es, WINDOW_NTABLE, idx);   /* stored negated: neg_c = ~neg */
-    s_mul(p.x, p.t, la);
+    s_lookup_ct<false, 32>(w.t2, t.coord(0, 3), es, WINDOW_NTABLE, idx);
+    s_mul(p.z, p.z, w.t2);
+    s_addsub(w.t1, w.t0, p.y, p.x);                      /* X and Y are dead from here: they hold a and b, then c */
+    s_lookup_ct<false, 32>(p.x, t.coord(0, 0), es, WINDOW_NTABLE, idx);
+    s_lookup_ct<false, 32>(p.y, t.coord(0, 1), es, WINDOW_NTABLE, idx);
+    s_mul(w.t0, w.t0, s_sel(p.x, p.y, neg));
+    s_mul(w.t1, w.t1, s_sel(p.y, p.x, neg));
+    s_lookup_ct<false, 32>(p.y, t.coord(0, 2), es, WINDOW_NTABLE, idx);   /* stored negated: neg_c = ~neg */
+    s_mul(p.x, p.t, p.y);
     s_addsub(w.t2, w.t1, w.t1, w.t0);
     s_addsub(w.t0, p.y, p.z, p.x);
     s_mul(p.z, w.t0, p.y);
@@ -417,7 +412,7 @@ GD void s_window_digit(uint32_t &idx, gmask_t &neg, const sc &s1x, int i) {
     idx = bits & (WINDOW_NTABLE - 1);
 }
 // slots 0..3 <- sum of the signed 5-bit digits of s1x (already recoded) times the table's odd multiples
-GD void s_window_mainloop(const spt &p, const swk &w, sref la, sref lb, const sc &s1x, const wtab<32> &multiples) {
+GD void s_window_mainloop(const spt &p, const swk &w, const sc &s1x, const wtab<32> &multiples) {
     s_pt_set_identity(p);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -432,7 +427,7 @@ GD void s_window_mainloop(const spt &p, const swk &w, sref la, sref lb, const sc
         }
         uint32_t idx; gmask_t neg;
         s_window_digit(idx, neg, s1x, k * WINDOW_BITS);
-        s_pt_add_pniels_ct(p, w, la, lb, multiples, idx, neg, k != 0);
+        s_pt_add_pniels_ct(p, w, multiples, idx, neg, k != 0);
     }
 }
 // slots 0..3: base on entry, scalar * base on exit
@@ -442,14 +437,13 @@ GD void s_window_scalarmul(sref sb, const sc &scalar, const wtab<32> &multiples)
     sc s1x;
     sc_recode_signed(s1x, scalar);
     s_prepare_fixed_window<32>(p, w, multiples);
-    s_window_mainloop(p, w, s_slot(sb, 7), s_slot(sb, 8), s1x, multiples);
+    s_window_mainloop(p, w, s1x, multiples);
 }
 // slots 0..3: base b on entry and the result scalarb*b + scalarc*c on exit; `c_abi` is loaded when needed
 template <class LoadC>
 GD void s_window_double_scalarmul(sref sb, const sc &scalarb, const sc &scalarc, LoadC load_c, const wtab<32> &multiples1, const wtab<32> &multiples2) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
     const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
-    const sref la = s_slot(sb, 7), lb = s_slot(sb, 8);
     sc s1x, s2x;
     sc_recode_signed(s1x, scalarb);
     sc_recode_signed(s2x, scalarc);
@@ -470,9 +464,9 @@ GD void s_window_double_scalarmul(sref sb, const sc &scalarb, const sc &scalarc,
         }
         uint32_t idx; gmask_t neg;
         s_window_digit(idx, neg, s1x, k * WINDOW_BITS);
-        s_pt_add_pniels_ct(p, w, la, lb, multiples1, idx, neg, false);
+        s_pt_add_pniels_ct(p, w, multiples1, idx, neg, false);
         s_window_digit(idx, neg, s2x, k * WINDOW_BITS);
-        s_pt_add_pniels_ct(p, w, la, lb, multiples2, idx, neg, k != 0);
+        s_pt_add_pniels_ct(p, w, multiples2, idx, neg, k != 0);
     }
 }
 
@@ -484,7 +478,6 @@ GD void s_window_double_scalarmul(sref sb, const sc &scalarb, const sc &scalarc,
 GD void s_comb_scalarmul_table(sref sb, const niels *table, const sc &scalar) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
     const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
-    const sref la = s_slot(sb, 7), lb = s_slot(sb, 8);
     sc s1x;
     sc_recode_signed(s1x, scalar);
     s_pt_set_identity(p);
@@ -506,7 +499,7 @@ GD void s_comb_scalarmul_table(sref sb, const niels *table, const sc &scalar) {
             const gmask_t invert = (gmask_t)((int32_t)(tab >> (COMB_T - 1)) - 1);
             tab ^= invert;
             tab &= (1u << (COMB_T - 1)) - 1;
-            s_pt_add_niels_ct(p, w, la, lb, table + (j << (COMB_T - 1)), tab, invert, j == COMB_N - 1 && i != 0);
+            s_pt_add_niels_ct(p, w, table + (j << (COMB_T - 1)), tab, invert, j == COMB_N - 1 && i != 0);
         }
     }
 }

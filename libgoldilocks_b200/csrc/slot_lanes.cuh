@@ -182,11 +182,11 @@ struct SlotDualScalarmul { /* goldilocks_448_point_dual_scalarmul (goldilocks.c:
         s_prepare_fixed_window<32>(p, w, t);
         sc_from_abi(s, scalar1 + i);
         sc_recode_signed(sx, s);
-        s_window_mainloop(p, w, s_slot(sb, 7), s_slot(sb, 8), sx, t);
+        s_window_mainloop(p, w, sx, t);
         s_pt_to_abi(out1 + i, sb);
         sc_from_abi(s, scalar2 + i);
         sc_recode_signed(sx, s);
-        s_window_mainloop(p, w, s_slot(sb, 7), s_slot(sb, 8), sx, t);
+        s_window_mainloop(p, w, sx, t);
         s_pt_to_abi(out2 + i, sb);
     }
 };

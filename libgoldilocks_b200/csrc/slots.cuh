@@ -115,16 +115,6 @@ SFN void s_addsub(sref sum, sref diff, sref a, sref b) {
 }
 // d = (a + b)^2
 SFN void s_sqr_sum(sref d, sref a, sref b) { gf x, y, z; s_ld(x, a); s_ld(y, b); gf_add_nr(x, x, y); gf_sqr_body(z, x); s_st(d, z); }
-// d = (a + b)^2 - c   (c may be LOOSE)
-SFN void s_sqr_sum_sub(sref d, sref a, sref b, sref c) {
-    gf x, y, z;
-    s_ld(x, a); s_ld(y, b);
-    gf_add_nr(x, x, y);
-    gf_sqr_body(z, x);
-    s_ld(y, c);
-    gf_sub(z, z, y);
-    s_st(d, z);
-}
 // d = 2 a^2 - b
 SFN void s_sqr2_sub(sref d, sref a, sref b) {
     gf x, y, z;

@@ -107,6 +107,11 @@ GOLDILOCKS_B200_API void goldilocks_448_point_destroy(goldilocks_448_point_p poi
 /* reference point_448.h:647-664 / elligator.c:32-94 */
 GOLDILOCKS_B200_API void goldilocks_448_point_from_hash_nonuniform(goldilocks_448_point_p pt, const uint8_t hashed_data[56]);
 GOLDILOCKS_B200_API void goldilocks_448_point_from_hash_uniform(goldilocks_448_point_p pt, const uint8_t hashed_data[112]);
+/* reference point_448.h:666-709 / elligator.c:104-164: one preimage of pt under the maps above, chosen by `which`
+ * (bit 0 sign of s, bit 1 alternative x, bit 2 sign of r0); FAILURE when that branch has no preimage.  The uniform
+ * variant reads partial_hash[56..111] and writes partial_hash[0..55]. */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_invert_elligator_nonuniform(uint8_t recovered_hash[56], const goldilocks_448_point_p pt, uint32_t which);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_invert_elligator_uniform(uint8_t partial_hash[112], const goldilocks_448_point_p pt, uint32_t which);
 /* reference ed448.h:215-232 / goldilocks.c:905-1004 ; point_448.h:430-434 / goldilocks.c:1104-1115 */
 GOLDILOCKS_B200_API void goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa(uint8_t enc[57], const goldilocks_448_point_p p);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio(goldilocks_448_point_p p, const uint8_t enc[57]);
@@ -139,6 +144,17 @@ GOLDILOCKS_B200_API void goldilocks_sha3_destroy(goldilocks_keccak_sponge_p spon
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_sha3_hash(uint8_t *out, size_t outlen, const uint8_t *in, size_t inlen, const struct goldilocks_kparams_s *params);
 GOLDILOCKS_B200_API size_t goldilocks_sha3_default_output_bytes(const goldilocks_keccak_sponge_p sponge);
 GOLDILOCKS_B200_API size_t goldilocks_sha3_max_output_bytes(const goldilocks_keccak_sponge_p sponge);
+/* Sponge-based CSPRNG (reference spongerng.h:22-87 / spongerng.c:92-205): a SHAKE256 object that is re-keyed after every
+ * request.  Host-side composition of the streaming calls above, so its Keccak-f permutations run on the device too.  A
+ * deterministic generator reproduces the reference's byte stream exactly (the reference's tests draw their inputs from it);
+ * a non-deterministic one stirs in 32 bytes of OS entropy before each request. */
+typedef struct { goldilocks_keccak_sponge_p sponge; } goldilocks_keccak_prng_s;
+typedef goldilocks_keccak_prng_s goldilocks_keccak_prng_p[1];
+GOLDILOCKS_B200_API void goldilocks_spongerng_init_from_buffer(goldilocks_keccak_prng_p prng, const uint8_t *in, size_t len, int deterministic);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_spongerng_init_from_file(goldilocks_keccak_prng_p prng, const char *file, size_t len, int deterministic);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_spongerng_init_from_dev_urandom(goldilocks_keccak_prng_p prng);
+GOLDILOCKS_B200_API void goldilocks_spongerng_next(goldilocks_keccak_prng_p prng, uint8_t *out, size_t len);
+GOLDILOCKS_B200_API void goldilocks_spongerng_stir(goldilocks_keccak_prng_p prng, const uint8_t *in, size_t len);
 GOLDILOCKS_B200_API void goldilocks_ed448_prehash_init(goldilocks_keccak_sponge_p hash);
 GOLDILOCKS_B200_API void goldilocks_ed448_sign_prehash(uint8_t signature[114], const uint8_t privkey[57], const uint8_t pubkey[57], const goldilocks_keccak_sponge_p hash, const uint8_t *context, uint8_t context_len);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_prehash(const uint8_t signature[114], const uint8_t pubkey[57], const goldilocks_keccak_sponge_p hash, const uint8_t *context, uint8_t context_len);
@@ -187,6 +203,9 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_encode_batch(uint8_t
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_decode_batch(goldilocks_448_point_s *pts, goldilocks_error_t *status, const uint8_t *ser /*n*56*/, goldilocks_bool_t allow_identity, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_from_hash_nonuniform_batch(goldilocks_448_point_s *pts, const uint8_t *hashed /*n*56*/, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_from_hash_uniform_batch(goldilocks_448_point_s *pts, const uint8_t *hashed /*n*112*/, size_t n);
+/* which[i] selects the branch of element i; the bytes of a failed element are written all the same (like the reference) */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_invert_elligator_nonuniform_batch(uint8_t *recovered /*n*56*/, goldilocks_error_t *status, const goldilocks_448_point_s *pts, const uint32_t *which, size_t n);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_invert_elligator_uniform_batch(uint8_t *partial /*n*112, in/out*/, goldilocks_error_t *status, const goldilocks_448_point_s *pts, const uint32_t *which, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_scalarmul_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *base, const goldilocks_448_scalar_s *scalar, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_double_scalarmul_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *base1, const goldilocks_448_scalar_s *scalar1, const goldilocks_448_point_s *base2, const goldilocks_448_scalar_s *scalar2, size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(goldilocks_448_point_s *out, const goldilocks_448_precomputed_s *base, const goldilocks_448_scalar_s *scalar, size_t n);

@@ -152,6 +152,21 @@ class BatchLib:
         self._call("goldilocks_448_point_from_hash_uniform_batch", out, h, _Z(len(h)))
         return out
 
+    def invert_elligator_nonuniform(self, pts, which):
+        """elligator.c:104-152: (recovered (n,56) u8, status int32[n]); which[i] picks the preimage branch"""
+        pts = _u8(pts, 256); which = np.ascontiguousarray(which, np.uint32)
+        out = np.empty((len(pts), 56), np.uint8); st = np.zeros(len(pts), np.int32)
+        self._call("goldilocks_448_invert_elligator_nonuniform_batch", out, st, pts, which, _Z(len(pts)))
+        return out, st
+
+    def invert_elligator_uniform(self, pts, second_half, which):
+        """elligator.c:154-164: completes (n,112) hashes whose bytes 56..111 are `second_half`"""
+        pts = _u8(pts, 256); which = np.ascontiguousarray(which, np.uint32)
+        buf = np.zeros((len(pts), 112), np.uint8); buf[:, 56:] = _u8(second_half, 56)
+        st = np.zeros(len(pts), np.int32)
+        self._call("goldilocks_448_invert_elligator_uniform_batch", buf, st, pts, which, _Z(len(pts)))
+        return buf, st
+
     def encode_like_eddsa(self, a):
         a = _u8(a, 256); out = np.empty((len(a), 57), np.uint8)
         self._call("goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch", out, a, _Z(len(a)))

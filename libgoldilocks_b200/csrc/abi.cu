@@ -448,6 +448,22 @@ goldilocks_error_t goldilocks_448_point_from_hash_uniform_batch(hpt *pts, const 
     k.fetch(P(pts), f.out, n);
     return k.finish();
 }
+goldilocks_error_t goldilocks_448_invert_elligator_nonuniform_batch(uint8_t *recovered, goldilocks_error_t *status, const hpt *pts, const uint32_t *which, size_t n) {
+    Call k;
+    LaneInvertElligator<false> f = {k.out<uint8_t>(56 * n), k.out<int32_t>(n), k.in(P(pts), n), k.in(which, n)};
+    k.run(f, n);
+    k.fetch(recovered, f.hashed, 56 * n);
+    k.fetch((int32_t *)status, f.status, n);
+    return k.finish();
+}
+goldilocks_error_t goldilocks_448_invert_elligator_uniform_batch(uint8_t *partial, goldilocks_error_t *status, const hpt *pts, const uint32_t *which, size_t n) {
+    Call k;
+    LaneInvertElligator<true> f = {k.in(partial, 112 * n), k.out<int32_t>(n), k.in(P(pts), n), k.in(which, n)};
+    k.run(f, n);
+    k.fetch(partial, f.hashed, 112 * n);
+    k.fetch((int32_t *)status, f.status, n);
+    return k.finish();
+}
 goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uint8_t *enc, const hpt *pts, size_t n) {
     Call k;
     LaneEncodeEddsa f = {k.out<uint8_t>(57 * n), k.in(P(pts), n)};
@@ -801,6 +817,14 @@ void goldilocks_448_base_double_scalarmul_non_secret(goldilocks_448_point_p o, c
 }
 void goldilocks_448_point_from_hash_nonuniform(goldilocks_448_point_p pt, const uint8_t h[56]) { goldilocks_448_point_from_hash_nonuniform_batch(pt, h, 1); }
 void goldilocks_448_point_from_hash_uniform(goldilocks_448_point_p pt, const uint8_t h[112]) { goldilocks_448_point_from_hash_uniform_batch(pt, h, 1); }
+goldilocks_error_t goldilocks_448_invert_elligator_nonuniform(uint8_t recovered_hash[56], const goldilocks_448_point_p pt, uint32_t which) {
+    goldilocks_error_t st = GOLDILOCKS_FAILURE;
+    return goldilocks_448_invert_elligator_nonuniform_batch(recovered_hash, &st, pt, &which, 1) == GOLDILOCKS_SUCCESS ? st : GOLDILOCKS_FAILURE;
+}
+goldilocks_error_t goldilocks_448_invert_elligator_uniform(uint8_t partial_hash[112], const goldilocks_448_point_p pt, uint32_t which) {
+    goldilocks_error_t st = GOLDILOCKS_FAILURE;
+    return goldilocks_448_invert_elligator_uniform_batch(partial_hash, &st, pt, &which, 1) == GOLDILOCKS_SUCCESS ? st : GOLDILOCKS_FAILURE;
+}
 void goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa(uint8_t enc[57], const goldilocks_448_point_p p) { goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(enc, p, 1); }
 goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio(goldilocks_448_point_p p, const uint8_t enc[57]) {
     goldilocks_error_t st = GOLDILOCKS_FAILURE;
@@ -939,6 +963,61 @@ size_t goldilocks_sha3_default_output_bytes(const goldilocks_keccak_sponge_p s) 
 size_t goldilocks_sha3_max_output_bytes(const goldilocks_keccak_sponge_p s) {
     const sponge_abi *h = (const sponge_abi *)s;
     return h->max_out == 0xFF ? SIZE_MAX : (size_t)((200 - h->rate) / 2);
+}
+// ---- sponge CSPRNG (reference spongerng.c:92-205): host composition of the streaming calls above ----
+static void os_entropy(uint8_t *buf, size_t len) { /* stands in for the reference's RDRAND/RDTSC read (spongerng.c:28-90) */
+    FILE *f = fopen("/dev/urandom", "rb");
+    if (f) { size_t got = fread(buf, 1, len, f); (void)got; fclose(f); }
+}
+void goldilocks_spongerng_stir(goldilocks_keccak_prng_p prng, const uint8_t *in, size_t len) {
+    uint8_t seed[32];
+    (void)goldilocks_sha3_output(prng->sponge, seed, sizeof seed);
+    const uint8_t nondet = SP(prng->sponge)->remaining;
+    goldilocks_sha3_reset(prng->sponge);
+    (void)goldilocks_sha3_update(prng->sponge, seed, sizeof seed);
+    (void)goldilocks_sha3_update(prng->sponge, in, len);
+    SP(prng->sponge)->remaining = nondet;
+    goldilocks_bzero(seed, sizeof seed);
+}
+void goldilocks_spongerng_next(goldilocks_keccak_prng_p prng, uint8_t *out, size_t len) {
+    uint8_t lenx[8];
+    if (SP(prng->sponge)->remaining) { /* non-deterministic generator */
+        uint8_t fresh[32] = {0};
+        os_entropy(fresh, sizeof fresh);
+        goldilocks_spongerng_stir(prng, fresh, sizeof fresh);
+        goldilocks_bzero(fresh, sizeof fresh);
+    }
+    for (unsigned i = 0; i < sizeof lenx; i++) lenx[i] = (uint8_t)((uint64_t)len >> (8 * i));
+    (void)goldilocks_sha3_update(prng->sponge, lenx, sizeof lenx);
+    (void)goldilocks_sha3_output(prng->sponge, out, len);
+    goldilocks_spongerng_stir(prng, lenx, 0);
+}
+void goldilocks_spongerng_init_from_buffer(goldilocks_keccak_prng_p prng, const uint8_t *in, size_t len, int deterministic) {
+    goldilocks_sha3_init(prng->sponge, &GOLDILOCKS_SHAKE256_params_s);
+    SP(prng->sponge)->remaining = !deterministic; /* the reference parks the flag in a field SHAKE ignores */
+    goldilocks_spongerng_stir(prng, in, len);
+}
+goldilocks_error_t goldilocks_spongerng_init_from_file(goldilocks_keccak_prng_p prng, const char *file, size_t len, int deterministic) {
+    uint8_t buffer[128];
+    goldilocks_sha3_init(prng->sponge, &GOLDILOCKS_SHAKE256_params_s);
+    SP(prng->sponge)->remaining = !deterministic;
+    if (!len) return GOLDILOCKS_FAILURE;
+    FILE *f = fopen(file, "rb");
+    if (!f) return GOLDILOCKS_FAILURE;
+    setvbuf(f, nullptr, _IONBF, 0); /* read exactly `len` bytes, like the reference's read(2) loop */
+    while (len) {
+        size_t got = fread(buffer, 1, len > sizeof buffer ? sizeof buffer : len, f);
+        if (got == 0) { fclose(f); return GOLDILOCKS_FAILURE; }
+        (void)goldilocks_sha3_update(prng->sponge, buffer, got);
+        len -= got;
+    }
+    fclose(f);
+    goldilocks_spongerng_stir(prng, buffer, 0);
+    goldilocks_bzero(buffer, sizeof buffer);
+    return GOLDILOCKS_SUCCESS;
+}
+goldilocks_error_t goldilocks_spongerng_init_from_dev_urandom(goldilocks_keccak_prng_p prng) {
+    return goldilocks_spongerng_init_from_file(prng, "/dev/urandom", 64, 0);
 }
 void goldilocks_ed448_prehash_init(goldilocks_keccak_sponge_p hash) { goldilocks_sha3_init(hash, &GOLDILOCKS_SHAKE256_params_s); }
 static void prehash_output(uint8_t ph[64], const goldilocks_keccak_sponge_p hash) {

@@ -2,3 +2,5 @@
 #include "launch.cuh"
 INSTANTIATE_PLAIN(LaneFromHash<false>)
 INSTANTIATE_PLAIN(LaneFromHash<true>)
+INSTANTIATE_PLAIN(LaneInvertElligator<false>)
+INSTANTIATE_PLAIN(LaneInvertElligator<true>)

@@ -169,6 +169,25 @@ struct LaneFromHash {
         pt_to_abi(out + i, p);
     }
 };
+// Elligator inverses (elligator.c:104-164).  Uniform: hashed[112*i+56..] is the caller's second half, the
+// first half is written (elligator.c:154-164).
+template <bool UNIFORM>
+struct LaneInvertElligator {
+    uint8_t *hashed; int32_t *status; const abi_pt *a; const uint32_t *hint;
+    GDM void operator()(size_t i) const {
+        pt p; uint32_t w[14];
+        pt_from_abi(p, a + i);
+        if (UNIFORM) {
+            pt p2;
+            words_load56(w, hashed + 112 * i + 56);
+            pt_from_hash_nonuniform(p2, w);
+            pt_sub(p, p, p2);
+        }
+        gmask_t ok = pt_invert_elligator_nonuniform(w, p, hint[i]);
+        words_store56(hashed + (UNIFORM ? 112 : 56) * i, w);
+        status[i] = ST_OK(ok);
+    }
+};
 struct LaneEncodeEddsa {
     uint8_t *out; const abi_pt *a;
     GDM void operator()(size_t i) const {

@@ -79,7 +79,7 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
     X(LaneGf<GFOP_MULW>) X(LaneGf<GFOP_ISR>) X(LaneGf<GFOP_INVERT>)                                 \
     X(LanePt<PTOP_ADD>) X(LanePt<PTOP_SUB>) X(LanePt<PTOP_DBL>) X(LanePt<PTOP_NEG>) X(LanePt<PTOP_TORQUE>) X(LanePtPscale)                 \
     X(LanePtEq) X(LanePtValid) X(LanePtEncode) X(LanePtDecode)                                      \
-    X(LaneFromHash<false>) X(LaneFromHash<true>)                                                    \
+    X(LaneFromHash<false>) X(LaneFromHash<true>) X(LaneInvertElligator<false>) X(LaneInvertElligator<true>)                                                    \
     X(LaneEncodeEddsa) X(LaneDecodeEddsa) X(LaneEncodeX448)                                         \
     X(LaneSc<SCOP_ADD>) X(LaneSc<SCOP_SUB>) X(LaneSc<SCOP_MUL>) X(LaneSc<SCOP_HALVE>)               \
     X(LaneScDecodeLong) X(LaneScInvert) X(LaneShake256) X(LaneSpongeUpdate) X(LaneSpongeOutput) X(LaneEdPkToX448) X(LaneEdSkToX448) X(LanePrecompute) X(LaneNielsFromAbi)                                                             \

@@ -189,6 +189,60 @@ GD void pt_deisogenize(gf &s, const pt &p) {
     gf_mul(s, t4, t1);
     gf_cond_neg(s, gf_lobit(s));
 }
+// Full deisogenize (goldilocks.c:98-140) with the Elligator-inverse by-products: `sum` = ratio*z - t and
+// `m1` = +-x + t; toggle_s / toggle_altx pick one of the four preimage branches (elligator.c:107-118).
+GD void pt_deisogenize_full(gf &s, gf &sum, gf &m1, const pt &p, gmask_t toggle_s, gmask_t toggle_altx) {
+    gf t1, t2, t3, t4, factor;
+    gf_add_nr(t1, p.x, p.t);
+    gf_sub(t2, p.x, p.t);
+    gf_mul(t3, t1, t2);
+    gf_sqr(t2, p.x);
+    gf_mul(t1, t2, t3);
+    gf_mulw(t2, t1, (uint32_t)(-1 - GOLD_TWISTED_D));
+    (void)gf_isr(t1, t2);
+    gf_mul(t2, t1, t3);
+    gf_load_factor(factor);
+    gf_mul(t4, t2, factor);
+    gmask_t negx = gf_lobit(t4) ^ toggle_altx;
+    gf_cond_neg(t2, negx);
+    gf_mul(t3, t2, p.z);
+    gf_sub(sum, t3, p.t);
+    gf_mul(t2, sum, p.x);
+    gf_mulw(t4, t2, (uint32_t)(-1 - GOLD_TWISTED_D));
+    gf_mul(s, t4, t1);
+    gmask_t lobs = gf_lobit(s);
+    gf_cond_neg(s, lobs);
+    gf_copy(m1, p.x);
+    gf_cond_neg(m1, ~lobs ^ negx ^ toggle_s);
+    gf_add(m1, m1, p.t);
+}
+// Elligator inverse (elligator.c:104-152): one of up to 8 preimages of p selected by `hint`; returns the
+// success mask, `out` (canonical words) is always written.
+GD gmask_t pt_invert_elligator_nonuniform(uint32_t out[14], const pt &p, uint32_t hint) {
+    const gmask_t sgn_s = 0u - (hint & 1u), sgn_altx = 0u - ((hint >> 1) & 1u), sgn_r0 = 0u - ((hint >> 2) & 1u);
+    gf a, b, c, one, zero;
+    gf_set_ui(one, 1);
+    gf_set_zero(zero);
+    pt_deisogenize_full(a, b, c, p, sgn_s, sgn_altx);
+    const gmask_t is_identity = gf_is_zero(p.t);
+    gf_cond_sel(b, b, one, is_identity & sgn_altx);
+    gf_cond_sel(c, c, one, is_identity & sgn_s & ~sgn_altx);
+    gf_mulw_signed(a, b, GOLD_EDWARDS_D - 1);
+    gf_add(b, a, b);
+    gf_sub(a, a, c);
+    gf_add(b, b, c);
+    gf_cond_swap(a, b, sgn_s);
+    gf_neg(c, b);                               /* gf_mul_qnr, qnr = -1 (field.h:84-90) */
+    gf_mul(b, c, a);
+    gmask_t succ = gf_isr(c, b);
+    succ |= gf_is_zero(b);
+    gf t;
+    gf_mul(t, c, a);
+    gf_cond_neg(t, sgn_r0 ^ gf_lobit(t));
+    succ &= ~(gf_is_zero(t) & (sgn_r0 | sgn_s)); /* duplicate preimages of the identity */
+    gf_to_words(out, t);
+    return succ;
+}
 // (goldilocks.c:142-176) returns success mask; p is always written.
 GD gmask_t pt_decode(pt &p, const uint32_t ser[14], gmask_t allow_identity) {
     gf s, s2, num, tmp, tmp2, ynum, isr, den, factor;

@@ -539,6 +539,60 @@ static void pt_from_hash_uniform(pt *p, const uint8_t ser[112]) { /* ref: elliga
     pt_addsub(p, p, &p2, 0);
 }
 
+/* ---- Elligator inverse ------------------------------------------------------------------------------ */
+static void pt_deisogenize_full(fe *s, fe *sum, fe *m1, const pt *p, int toggle_s, int toggle_altx) { /* ref: goldilocks.c:98-134 */
+    fe t1, t2, t3, t4;
+    fe_add(&t1, &p->x, &p->t);
+    fe_sub(&t2, &p->x, &p->t);
+    fe_mul(&t3, &t1, &t2);
+    fe_sqr(&t2, &p->x);
+    fe_mul(&t1, &t2, &t3);
+    fe_mulw(&t2, &t1, -1 - TWISTED_D);
+    (void)fe_isr(&t1, &t2);
+    fe_mul(&t2, &t1, &t3);
+    fe_mul(&t4, &t2, &FACTOR);
+    int negx = fe_lobit(&t4) ^ toggle_altx;
+    fe_cond_neg(&t2, negx);
+    fe_mul(&t3, &t2, &p->z);
+    fe_sub(sum, &t3, &p->t);
+    fe_mul(&t2, sum, &p->x);
+    fe_mulw(&t4, &t2, -1 - TWISTED_D);
+    fe_mul(s, &t4, &t1);
+    int lobs = fe_lobit(s);
+    fe_cond_neg(s, lobs);
+    *m1 = p->x;
+    fe_cond_neg(m1, (!lobs) ^ negx ^ toggle_s);
+    fe_add(m1, m1, &p->t);
+}
+static int pt_invert_elligator_nonuniform(uint8_t out[56], const pt *p, uint32_t hint) { /* ref: elligator.c:104-152 */
+    int sgn_s = hint & 1, sgn_altx = (hint >> 1) & 1, sgn_r0 = (hint >> 2) & 1;
+    fe a, b, c, t;
+    pt_deisogenize_full(&a, &b, &c, p, sgn_s, sgn_altx);
+    int is_identity = fe_is_zero(&p->t);
+    if (is_identity && sgn_altx) b = FE_ONE;
+    if (is_identity && sgn_s && !sgn_altx) c = FE_ONE;
+    fe_mulw(&a, &b, EDWARDS_D - 1);
+    fe_add(&b, &a, &b);
+    fe_sub(&a, &a, &c);
+    fe_add(&b, &b, &c);
+    if (sgn_s) { t = a; a = b; b = t; }
+    fe_neg(&c, &b);
+    fe_mul(&b, &c, &a);
+    int succ = fe_isr(&c, &b);
+    succ |= fe_is_zero(&b);
+    fe_mul(&b, &c, &a);
+    fe_cond_neg(&b, sgn_r0 ^ fe_lobit(&b));
+    succ &= !(fe_is_zero(&b) && (sgn_r0 | sgn_s));
+    fe_serialize(out, &b);
+    return succ;
+}
+static int pt_invert_elligator_uniform(uint8_t partial[112], const pt *p, uint32_t hint) { /* ref: elligator.c:154-164 */
+    pt p2;
+    pt_from_hash_nonuniform(&p2, partial + 56);
+    pt_addsub(&p2, p, &p2, 1);
+    return pt_invert_elligator_nonuniform(partial, &p2, hint);
+}
+
 /* ---- scalar multiplications --------------------------------------------------------------------------- */
 static void sc_adjusted_half(scl *r, const scl *s) { /* ref: goldilocks.c:420-421, 842-843 */
     scl t;
@@ -1016,7 +1070,7 @@ typedef struct {
 } args_t;
 enum { GF_MUL, GF_SQR, GF_ADD, GF_SUB, GF_MULW, GF_ISR, GF_INV, PT_ADD, PT_SUB, PT_DBL, PT_NEG, PT_EQ, PT_VALID, PT_ENC, PT_DEC,
        H2C_NU, H2C_U, PT_SMUL, PT_DSMUL, COMB_MUL, BDSM, ENC_ED, DEC_ED, ENC_X, SC_ADD, SC_SUB, SC_MUL, SC_HALVE, SC_DECODE_LONG,
-       X448, X448_PK, ED_PK, ED_SIGN, ED_VERIFY, SHAKE, PT_COORDS };
+       X448, X448_PK, ED_PK, ED_SIGN, ED_VERIFY, SHAKE, PT_COORDS, INV_ELL_NU, INV_ELL_U };
 static const uint8_t EMPTY = 0;
 
 static void elem(size_t i, void *vp) {
@@ -1064,6 +1118,14 @@ static void elem(size_t i, void *vp) {
     }
     case H2C_NU: { pt p; pt_from_hash_nonuniform(&p, (const uint8_t *)a->i0 + 56 * i); pt_to_abi((abi_pt *)a->o0 + i, &p); break; }
     case H2C_U: { pt p; pt_from_hash_uniform(&p, (const uint8_t *)a->i0 + 112 * i); pt_to_abi((abi_pt *)a->o0 + i, &p); break; }
+    case INV_ELL_NU: case INV_ELL_U: {
+        pt q; pt_from_abi(&q, (const abi_pt *)a->i0 + i);
+        const uint32_t hint = ((const uint32_t *)a->i1)[i];
+        int ok = a->op == INV_ELL_NU ? pt_invert_elligator_nonuniform((uint8_t *)a->o0 + 56 * i, &q, hint)
+                                     : pt_invert_elligator_uniform((uint8_t *)a->o0 + 112 * i, &q, hint);
+        ((int32_t *)a->o1)[i] = ok ? -1 : 0;
+        break;
+    }
     case PT_SMUL: {
         pt p, q; scl s;
         pt_from_abi(&q, (const abi_pt *)a->i0 + i); memcpy(s.w, (const uint8_t *)a->i1 + 56 * i, 56);
@@ -1157,6 +1219,8 @@ EXPORT int32_t goldilocks_448_point_encode_batch(uint8_t *o, const abi_pt *x, si
 EXPORT int32_t goldilocks_448_point_decode_batch(abi_pt *o, int32_t *st, const uint8_t *ser, uint64_t allow_identity, size_t n) { A0(PT_DEC); a.o0 = o; a.o1 = st; a.i0 = ser; a.flag = allow_identity; return pfor(elem, &a, n); }
 EXPORT int32_t goldilocks_448_point_from_hash_nonuniform_batch(abi_pt *o, const uint8_t *h, size_t n) { A0(H2C_NU); a.o0 = o; a.i0 = h; return pfor(elem, &a, n); }
 EXPORT int32_t goldilocks_448_point_from_hash_uniform_batch(abi_pt *o, const uint8_t *h, size_t n) { A0(H2C_U); a.o0 = o; a.i0 = h; return pfor(elem, &a, n); }
+EXPORT int32_t goldilocks_448_invert_elligator_nonuniform_batch(uint8_t *h, int32_t *st, const abi_pt *x, const uint32_t *hint, size_t n) { A0(INV_ELL_NU); a.o0 = h; a.o1 = st; a.i0 = x; a.i1 = hint; return pfor(elem, &a, n); }
+EXPORT int32_t goldilocks_448_invert_elligator_uniform_batch(uint8_t *h, int32_t *st, const abi_pt *x, const uint32_t *hint, size_t n) { A0(INV_ELL_U); a.o0 = h; a.o1 = st; a.i0 = x; a.i1 = hint; return pfor(elem, &a, n); }
 EXPORT int32_t goldilocks_448_point_scalarmul_batch(abi_pt *o, const abi_pt *b, const void *s, size_t n) { A0(PT_SMUL); a.o0 = o; a.i0 = b; a.i1 = s; return pfor(elem, &a, n); }
 EXPORT int32_t goldilocks_448_point_double_scalarmul_batch(abi_pt *o, const abi_pt *b1, const void *s1, const abi_pt *b2, const void *s2, size_t n) { A0(PT_DSMUL); a.o0 = o; a.i0 = b1; a.i1 = s1; a.i2 = b2; a.i3 = s2; return pfor(elem, &a, n); }
 EXPORT int32_t goldilocks_448_precomputed_scalarmul_batch(abi_pt *o, const void *table, const void *s, size_t n) { (void)table; A0(COMB_MUL); a.o0 = o; a.i0 = s; return pfor(elem, &a, n); }

@@ -70,7 +70,7 @@ enum {
     OP_H2C_NU, OP_H2C_U, OP_PT_SMUL, OP_PT_DSMUL, OP_COMB, OP_BDSM, OP_ENC_EDDSA, OP_DEC_EDDSA, OP_ENC_X448,
     OP_SC_ADD, OP_SC_SUB, OP_SC_MUL, OP_SC_HALVE, OP_SC_DECODE_LONG,
     OP_X448, OP_X448_PK, OP_ED_PK, OP_ED_SIGN, OP_ED_VERIFY, OP_SHAKE256, OP_PT_COORDS,
-    OP_SC_INVERT, OP_PT_DUAL, OP_DIRECT, OP_PRECOMPUTE, OP_COMB_TABLE, OP_TORQUE, OP_PSCALE, OP_PK_TO_X, OP_SK_TO_X
+    OP_SC_INVERT, OP_PT_DUAL, OP_DIRECT, OP_PRECOMPUTE, OP_COMB_TABLE, OP_TORQUE, OP_PSCALE, OP_PK_TO_X, OP_SK_TO_X, OP_INV_ELL_NU, OP_INV_ELL_U
 };
 
 static void run_range(size_t lo, size_t hi, void *vp) {
@@ -265,6 +265,15 @@ static void run_range(size_t lo, size_t hi, void *vp) {
             memcpy((pt_t *)a->o0 + i, &p, sizeof(pt_t));
             break;
         }
+        case OP_INV_ELL_NU: case OP_INV_ELL_U: { /* elligator.c:104-164; hints are per element */
+            pt_t q; memcpy(&q, (const pt_t *)a->i0 + i, sizeof(pt_t));
+            const uint32_t hint = ((const uint32_t *)a->i1)[i];
+            goldilocks_error_t e = a->op == OP_INV_ELL_NU
+                ? goldilocks_448_invert_elligator_nonuniform((uint8_t *)a->o0 + 56 * i, &q, hint)
+                : goldilocks_448_invert_elligator_uniform((uint8_t *)a->o0 + 112 * i, &q, hint);
+            ((int32_t *)a->o1)[i] = (int32_t)e;
+            break;
+        }
         case OP_PK_TO_X:
             goldilocks_ed448_convert_public_key_to_x448((uint8_t *)a->o0 + 56 * i, (const uint8_t *)a->i0 + 57 * i);
             break;
@@ -314,6 +323,8 @@ EXPORT int32_t goldilocks_448_direct_scalarmul_batch(uint8_t *o, int32_t *st, co
 }
 EXPORT int32_t goldilocks_448_point_debugging_torque_batch(pt_t *o, const pt_t *x, size_t n) { A0; a.op = OP_TORQUE; a.o0 = o; a.i0 = x; return go(&a, n); }
 EXPORT int32_t goldilocks_448_point_debugging_pscale_batch(pt_t *o, const pt_t *x, const uint8_t *f, size_t n) { A0; a.op = OP_PSCALE; a.o0 = o; a.i0 = x; a.i1 = f; return go(&a, n); }
+EXPORT int32_t goldilocks_448_invert_elligator_nonuniform_batch(uint8_t *h, int32_t *st, const pt_t *x, const uint32_t *hint, size_t n) { A0; a.op = OP_INV_ELL_NU; a.o0 = h; a.o1 = st; a.i0 = x; a.i1 = hint; return go(&a, n); }
+EXPORT int32_t goldilocks_448_invert_elligator_uniform_batch(uint8_t *h, int32_t *st, const pt_t *x, const uint32_t *hint, size_t n) { A0; a.op = OP_INV_ELL_U; a.o0 = h; a.o1 = st; a.i0 = x; a.i1 = hint; return go(&a, n); }
 EXPORT int32_t goldilocks_448_scalar_invert_batch(sc_t *o, int32_t *st, const sc_t *x, size_t n) { A0; a.op = OP_SC_INVERT; a.o0 = o; a.o1 = st; a.i0 = x; return go(&a, n); }
 EXPORT int32_t goldilocks_ed448_convert_public_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) { A0; a.op = OP_PK_TO_X; a.o0 = x; a.i0 = ed; return go(&a, n); }
 EXPORT int32_t goldilocks_ed448_convert_private_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) { A0; a.op = OP_SK_TO_X; a.o0 = x; a.i0 = ed; return go(&a, n); }

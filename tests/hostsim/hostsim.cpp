@@ -117,6 +117,8 @@ EXPORT int32_t goldilocks_448_point_encode_batch(uint8_t *o, const hpt *a, size_
 EXPORT int32_t goldilocks_448_point_decode_batch(hpt *o, int32_t *st, const uint8_t *ser, uint64_t allow_identity, size_t n) { LanePtDecode f = {o, st, ser, allow_identity ? 1u : 0u}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_from_hash_nonuniform_batch(hpt *o, const uint8_t *h, size_t n) { LaneFromHash<false> f = {o, h}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_from_hash_uniform_batch(hpt *o, const uint8_t *h, size_t n) { LaneFromHash<true> f = {o, h}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_invert_elligator_nonuniform_batch(uint8_t *h, int32_t *st, const hpt *a, const uint32_t *which, size_t n) { LaneInvertElligator<false> f = {h, st, a, which}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_448_invert_elligator_uniform_batch(uint8_t *h, int32_t *st, const hpt *a, const uint32_t *which, size_t n) { LaneInvertElligator<true> f = {h, st, a, which}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uint8_t *o, const hpt *a, size_t n) { LaneEncodeEddsa f = {o, a}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(hpt *o, int32_t *st, const uint8_t *enc, size_t n) { LaneDecodeEddsa f = {o, st, enc}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint8_t *o, const hpt *a, size_t n) { LaneEncodeX448 f = {o, a}; run(f, n); return -1; }

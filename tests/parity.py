@@ -102,6 +102,35 @@ def check_codec(lib, chk, n):
     eq(c(chk, d1[ok]), c(chk, d2[ok]), "decode_like_eddsa coords")
 
 
+def check_elligator_inverse(lib, chk, n):
+    """Elligator inverses (elligator.c:104-164): status + bytes for all 8 branches per point, and the round trip
+    from_hash(recovered) == point on every success (the reference's own test, test_goldilocks.cxx:291-361)."""
+    h = stream_bytes("c5/inv", n * 56).reshape(n, 56)
+    ident = np.zeros((1, 256), np.uint8); ident[0, 64] = 1; ident[0, 128] = 1
+    pts = np.concatenate([chk.from_hash_nonuniform(h), chk.from_hash_uniform(stream_bytes("c5/inv2", 8 * 112).reshape(8, 112)), ident])
+    m = len(pts)
+    total_ok = 0
+    for base in range(8):
+        which = ((np.arange(m) + base) % 8).astype(np.uint32)
+        which[::5] += 8 * (1 + base)          # upper bits are ignored on this curve (elligator.c:113-118)
+        r1, s1 = lib.invert_elligator_nonuniform(pts, which)
+        r2, s2 = chk.invert_elligator_nonuniform(pts, which)
+        eq(s1, s2, "invert_elligator_nonuniform status")
+        eq(r1, r2, "invert_elligator_nonuniform bytes")
+        ok = s2 == -1
+        total_ok += int(ok.sum())
+        back = lib.from_hash_nonuniform(r1[ok])
+        assert lib.point_eq(back, pts[ok]).all(), "from_hash_nonuniform(invert(p)) != p"
+        second = stream_bytes("c5/inv3/%d" % base, m * 56).reshape(m, 56)
+        u1, t1 = lib.invert_elligator_uniform(pts, second, which)
+        u2, t2 = chk.invert_elligator_uniform(pts, second, which)
+        eq(t1, t2, "invert_elligator_uniform status")
+        eq(u1, u2, "invert_elligator_uniform bytes")
+        okk = t2 == -1
+        assert lib.point_eq(lib.from_hash_uniform(u1[okk]), pts[okk]).all(), "from_hash_uniform(invert(p)) != p"
+    assert total_ok > m, "too few Elligator preimages found"
+
+
 def check_scalars(lib, chk, n):
     a = np.concatenate([util.random_scalars(chk, "sc/a", n), util.scalar_edge_bytes()])
     b = np.concatenate([util.random_scalars(chk, "sc/b", n), util.scalar_edge_bytes()[::-1]])

@@ -7,7 +7,7 @@ import pytest
 
 import parity
 import util
-from util import stream_bytes
+from util import ROOT, stream_bytes
 
 pytestmark = pytest.mark.gpu
 FULL = 1 << 20
@@ -34,6 +34,7 @@ def test_points_full(gpu, chk):
 
 def test_codec_elligator(gpu, chk):
     parity.check_codec(gpu, chk, 1 << 14)
+    parity.check_elligator_inverse(gpu, chk, 1 << 12)
 
 
 def test_scalars(gpu, chk):
@@ -162,6 +163,82 @@ def test_streaming_sha3_and_prehash(gpu, vectors):
         assert L.goldilocks_ed448_verify_prehash(sig, pk, h, cb, C.c_uint8(len(ctx))) == 0
         done += 1
     assert done >= 1
+
+
+def test_spongerng(gpu, chk):
+    """goldilocks_spongerng_* (spongerng.c:92-205): a deterministic generator reproduces the reference's stream (the
+    reference's own tests draw every input from it, test_goldilocks.cxx:151) -- checked against a hashlib restatement
+    and, when the reference build is present, against the reference itself; a non-deterministic one must differ."""
+    import ctypes as C
+    import hashlib
+    L = gpu.lib
+
+    class Model:  # stir = squeeze 32 bytes, re-key with them + input; next = absorb the length, squeeze, stir
+        def __init__(self, seed): self.data = b""; self.stir(seed)
+        def stir(self, more, skip=0): self.data = hashlib.shake_256(self.data).digest(skip + 32)[skip:] + more
+        def next(self, n):
+            self.data += n.to_bytes(8, "little")
+            out = hashlib.shake_256(self.data).digest(n)
+            self.stir(b"", n)
+            return out
+
+    seed = b"test_field arithmetic"
+    lens = [56, 1, 0, 136, 137, 32, 400, 56]
+    prng = (C.c_uint64 * 26)()
+    L.goldilocks_spongerng_init_from_buffer(prng, (C.c_uint8 * len(seed)).from_buffer_copy(seed), C.c_size_t(len(seed)), C.c_int(1))
+    model = Model(seed)
+    ref = None
+    if chk.has("goldilocks_spongerng_next"):
+        ref = (C.c_uint64 * 26)()
+        chk.lib.goldilocks_spongerng_init_from_buffer(ref, (C.c_uint8 * len(seed)).from_buffer_copy(seed), C.c_size_t(len(seed)), C.c_int(1))
+    for k, n in enumerate(lens):
+        out = (C.c_uint8 * max(1, n))()
+        L.goldilocks_spongerng_next(prng, out, C.c_size_t(n))
+        want = model.next(n)
+        assert bytes(out)[:n] == want, "spongerng_next #%d (%d bytes) vs hashlib model" % (k, n)
+        if ref is not None:
+            o2 = (C.c_uint8 * max(1, n))()
+            chk.lib.goldilocks_spongerng_next(ref, o2, C.c_size_t(n))
+            assert bytes(o2)[:n] == want, "reference spongerng_next #%d" % k
+        if k == 3:
+            extra = b"more entropy"
+            L.goldilocks_spongerng_stir(prng, (C.c_uint8 * len(extra)).from_buffer_copy(extra), C.c_size_t(len(extra)))
+            model.stir(extra)
+            if ref is not None:
+                chk.lib.goldilocks_spongerng_stir(ref, (C.c_uint8 * len(extra)).from_buffer_copy(extra), C.c_size_t(len(extra)))
+    # non-deterministic: same seed, different streams
+    a, b = (C.c_uint64 * 26)(), (C.c_uint64 * 26)()
+    oa, ob = (C.c_uint8 * 32)(), (C.c_uint8 * 32)()
+    for st, o in ((a, oa), (b, ob)):
+        L.goldilocks_spongerng_init_from_buffer(st, (C.c_uint8 * len(seed)).from_buffer_copy(seed), C.c_size_t(len(seed)), C.c_int(0))
+        L.goldilocks_spongerng_next(st, o, C.c_size_t(32))
+    assert bytes(oa) != bytes(ob)
+    L.goldilocks_spongerng_init_from_dev_urandom.restype = C.c_int32
+    L.goldilocks_spongerng_init_from_file.restype = C.c_int32
+    assert L.goldilocks_spongerng_init_from_dev_urandom(a) == -1
+    assert L.goldilocks_spongerng_init_from_file(a, b"/nonexistent/file", C.c_size_t(8), C.c_int(1)) == 0
+    assert L.goldilocks_spongerng_init_from_file(a, b"/dev/zero", C.c_size_t(300), C.c_int(1)) == -1
+    L.goldilocks_spongerng_next(a, oa, C.c_size_t(32))
+    m = Model.__new__(Model); m.data = bytes(300); m.stir(b"")
+    assert bytes(oa) == m.next(32), "init_from_file stream"
+
+
+def test_reference_test_program_passes_on_this_library(gpu):
+    """the reference's own test/test_goldilocks.cxx, compiled against the reference's public C++
+    headers and linked against THIS library (oracle/Makefile: reftest_b200; only NTESTS is lowered), must pass:
+    scalar arithmetic, Elligator + inverses, point laws, codecs, X448 / EdDSA vectors, SHAKE objects, SpongeRng --
+    every call a batch of one on the GPU."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "reftest_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/reftest_b200 not built (reference sources absent at build time)")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    out = r.stdout.decode(errors="replace")
+    log_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log_dir):
+        with open(os.path.join(log_dir, "reftest_b200.log"), "w") as f:
+            f.write(out)
+    assert r.returncode == 0 and "Passed all tests." in out, out[-3000:]
 
 
 # ---- size-independent properties at the full 2^20 batch -------------------------------------------

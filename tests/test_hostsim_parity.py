@@ -23,6 +23,7 @@ def test_points(sim, chk):
 
 def test_codec_elligator(sim, chk):
     parity.check_codec(sim, chk, 256)
+    parity.check_elligator_inverse(sim, chk, 96)
 
 
 def test_scalars(sim, chk):

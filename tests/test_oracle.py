@@ -39,6 +39,7 @@ def test_oracle_vs_reference(oracle, ref):
     parity.check_field_isr(oracle, ref, 128)
     parity.check_points(oracle, ref, 512)
     parity.check_codec(oracle, ref, 128)
+    parity.check_elligator_inverse(oracle, ref, 96)
     parity.check_scalars(oracle, ref, 1024)
     parity.check_comb(oracle, ref, 128)
     parity.check_scalarmul(oracle, ref, 48)

@@ -14,9 +14,12 @@
 
 #include "../../include/goldilocks_b200.h"
 #include "launch.cuh"
+#include "staged.cuh"
 
 // kernels live in k_*.cu
 LANES_PLAIN(DECLARE_PLAIN)
+STAGED_GF(DECLARE_STAGED_GF)
+STAGED_PT(DECLARE_STAGED_PT)
 LANES_SM(DECLARE_SM)
 LANES_SMP(DECLARE_SMP)
 
@@ -83,6 +86,38 @@ bool launch(Ctx &c, const F &f, size_t n, cudaStream_t s) {
     if (prof) a = prof_begin(typeid(F).name(), s, &b);
     CU(launch_lanes<F>(f, n, s));
     if (prof) prof_end(typeid(F).name(), s, a, b);
+    return true;
+}
+// The HBM-bound field / point entry points run in their shared-memory staged shape (staged.cuh); these
+// overloads are more specialised than launch<F>, so every caller of launch() picks them up.
+template <int OP>
+bool launch(Ctx &c, const LaneGf<OP> &f, size_t n, cudaStream_t s) {
+    if (n == 0) return true;
+    g_launches++;
+    cudaEvent_t a = nullptr, b = nullptr;
+    const bool prof = g_prof_on.load() != 0;
+    if (prof) a = prof_begin(typeid(StagedGf<OP>).name(), s, &b);
+    const StagedGf<OP> sf = {f.out, f.status, f.a, f.b, f.w};
+    CU(launch_gf_staged<OP>(sf, n, s));
+    if (prof) prof_end(typeid(StagedGf<OP>).name(), s, a, b);
+    return true;
+}
+template <int OP>
+bool launch(Ctx &c, const LanePt<OP> &f, size_t n, cudaStream_t s) {
+    if (n == 0) return true;
+    g_launches++;
+    cudaEvent_t a = nullptr, b = nullptr;
+    const bool prof = g_prof_on.load() != 0;
+    if constexpr (OP == PTOP_ADD || OP == PTOP_SUB || OP == PTOP_DBL) {
+        if (prof) a = prof_begin(typeid(StagedPt<OP>).name(), s, &b);
+        const StagedPt<OP> sf = {f.out, f.a, f.b};
+        CU(launch_pt_staged<OP>(sf, n, s));
+        if (prof) prof_end(typeid(StagedPt<OP>).name(), s, a, b);
+    } else {
+        if (prof) a = prof_begin(typeid(LanePt<OP>).name(), s, &b);
+        CU(launch_lanes<LanePt<OP>>(f, n, s));
+        if (prof) prof_end(typeid(LanePt<OP>).name(), s, a, b);
+    }
     return true;
 }
 template <class F>

@@ -75,9 +75,7 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
 }
 
 #define LANES_PLAIN(X)                                                                              \
-    X(LaneGf<GFOP_MUL>) X(LaneGf<GFOP_SQR>) X(LaneGf<GFOP_ADD>) X(LaneGf<GFOP_SUB>)                 \
-    X(LaneGf<GFOP_MULW>) X(LaneGf<GFOP_ISR>) X(LaneGf<GFOP_INVERT>)                                 \
-    X(LanePt<PTOP_ADD>) X(LanePt<PTOP_SUB>) X(LanePt<PTOP_DBL>) X(LanePt<PTOP_NEG>) X(LanePt<PTOP_TORQUE>) X(LanePtPscale)                 \
+    X(LanePt<PTOP_NEG>) X(LanePt<PTOP_TORQUE>) X(LanePtPscale)                 \
     X(LanePtEq) X(LanePtValid) X(LanePtEncode) X(LanePtDecode)                                      \
     X(LaneFromHash<false>) X(LaneFromHash<true>) X(LaneInvertElligator<false>) X(LaneInvertElligator<true>)                                                    \
     X(LaneEncodeEddsa) X(LaneDecodeEddsa) X(LaneEncodeX448)                                         \

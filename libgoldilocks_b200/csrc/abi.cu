@@ -40,7 +40,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;   // H2D of the next chunk while the current one computes (verify)
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     fixed_tables *ft = nullptr;
-    niels *wide = nullptr;       // 16384-entry verification table (3 MB)
+    niels *wide = nullptr;       // 4 x 16384-entry verification tables: odd multiples of 2^(115c) B (12 MB)
     std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
     size_t used = 0;             // bytes used in the active block
     void *slot_scratch = nullptr;
@@ -172,13 +172,13 @@ bool ctx_init(Ctx &c, int dev) {
     CU(cudaMalloc(&c.ft, sizeof(fixed_tables)));
     LaneBuildTables f = {c.ft};
     if (!launch(c, f, TABLE_LANES, c.stream)) return false;
-    CU(cudaMalloc(&c.wide, sizeof(niels) * WIDE_ENTRIES));
+    CU(cudaMalloc(&c.wide, sizeof(niels) * WIDE_ENTRIES * WIDE_TABLES));
     {
         pniels *tmp = nullptr; gf *pre = nullptr;
-        CU(cudaMalloc(&tmp, sizeof(pniels) * WIDE_ENTRIES));
-        CU(cudaMalloc(&pre, sizeof(gf) * WIDE_ENTRIES));
+        CU(cudaMalloc(&tmp, sizeof(pniels) * WIDE_ENTRIES * WIDE_TABLES));
+        CU(cudaMalloc(&pre, sizeof(gf) * WIDE_ENTRIES * WIDE_TABLES));
         LaneBuildWide fw = {c.wide, tmp, pre, c.ft};
-        if (!launch(c, fw, WIDE_LANES, c.stream)) return false;
+        if (!launch(c, fw, WIDE_LANES * WIDE_TABLES, c.stream)) return false;
         CU(cudaStreamSynchronize(c.stream));
         cudaFree(tmp); cudaFree(pre);
     }
@@ -707,24 +707,51 @@ goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t
     return k.finish();
 }
 
+// Batches of at least VERIFY_GROUP_MIN signatures are grouped by public key on the device (k_group.cu); keys that
+// occur more than once get one shared table (at most n/8 + 1 tables per call; the rest verify stand-alone).
+constexpr size_t VERIFY_GROUP_MIN = 64;
+static size_t verify_tab_cap(size_t n) { return n / 8 + 1; }
 size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return al(2 * n * sizeof(abi_pt)) + al(2 * n * sizeof(int32_t)) + 2 * al(n * sizeof(abi_sc));
+    size_t base = al(2 * n * sizeof(abi_pt)) + al(2 * n * sizeof(int32_t)) + 2 * al(n * sizeof(abi_sc));
+    if (n >= VERIFY_GROUP_MIN) base += al(group_scratch_bytes(n, verify_tab_cap(n))) + al(verify_tab_cap(n) * KTAB_QUADS * sizeof(uint4));
+    return base;
+}
+struct VerifyGrids { int unique = 1, shared = 1, tables = 1; };
+static bool verify_grids(Ctx &c, VerifyGrids *g) {
+    return smp_grid<SlotEdVerifyFinish>(c, &g->unique) && smp_grid<SlotEdVerifyFinishShared>(c, &g->shared) && smp_grid<SlotKeyTables>(c, &g->tables);
 }
 static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off, uint8_t prehashed,
-                       const uint8_t *ctx, uint8_t ctx_len, size_t n, void *scratch, uint4 *slots, int grid, cudaStream_t s) {
+                       const uint8_t *ctx, uint8_t ctx_len, size_t n, void *scratch, uint4 *slots, const VerifyGrids &grids, cudaStream_t s) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     char *p = (char *)scratch;
     abi_pt *pts = (abi_pt *)p; p += al(2 * n * sizeof(abi_pt));
     int32_t *ok = (int32_t *)p; p += al(2 * n * sizeof(int32_t));
     abi_sc *chal = (abi_sc *)p; p += al(n * sizeof(abi_sc));
-    abi_sc *resp = (abi_sc *)p;
-    LaneEdVerifyDecode f1 = {pts, ok, sig, pk};
+    abi_sc *resp = (abi_sc *)p; p += al(n * sizeof(abi_sc));
+    verify_plan plan = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint4 *ktabs = nullptr;
+    const size_t cap = verify_tab_cap(n);
+    if (n >= VERIFY_GROUP_MIN) {
+        void *gs = p; p += al(group_scratch_bytes(n, cap));
+        ktabs = (uint4 *)p;
+        uint64_t launched = 0;
+        cudaError_t e = group_keys(pk, n, (uint32_t)cap, gs, &plan, s, &launched);
+        if (e != cudaSuccess) return fail("group_keys", e);
+        g_launches += launched;
+    }
+    LaneEdVerifyDecode f1 = {pts, ok, sig, pk, n, plan};
     if (!launch(c, f1, 2 * n, s)) return false;
     LaneEdVerifyScalars f2 = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len};
     if (!launch(c, f2, n, s)) return false;
+    if (plan.unique_sig) {
+        SlotKeyTables ft = {pts, ktabs, plan};
+        if (!launch_smp(c, ft, cap, grids.tables, s)) return false;
+        SlotEdVerifyFinishShared fs = {status, pts, ok, chal, resp, c.wide, ktabs, slots, plan};
+        return launch_smp(c, fs, n, grids.shared, s);
+    }
     SlotEdVerifyFinish f3 = {status, pts, ok, chal, resp, c.wide, slots};
-    return launch_smp(c, f3, n, grid, s);
+    return launch_smp(c, f3, n, grids.unique, s);
 }
 goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                  uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n) {
@@ -734,7 +761,9 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
     const uint8_t *dctx = k.in(context, context_len);
     uint8_t *dmsg = k.out<uint8_t>(total), *dsig = k.out<uint8_t>(114 * n), *dpk = k.out<uint8_t>(57 * n);
     int32_t *dst = k.out<int32_t>(n);
-    int grid = k.smp_grid_for<SlotEdVerifyFinish>();
+    VerifyGrids grids;
+    if (k.ok) k.ok = verify_grids(*k.c, &grids);
+    const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
     uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
     /* Two chunks: a head of two full rounds of the persistent finish kernel, then the rest.  The head's
      * inputs cross PCIe first; the rest is copied on the copy stream while the head computes, so only the
@@ -753,7 +782,7 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
     for (int c = 0; c < chunks && k.ok; c++) {
         k.copy_wait(c);
         const size_t m = hi[c] - lo[c];
-        if (k.ok) k.ok = verify_dev(*k.c, dst + lo[c], dsig + 114 * lo[c], dpk + 57 * lo[c], dmsg, doff + lo[c], prehashed, dctx, context_len, m, scratch[c], slots, grid, k.c->stream);
+        if (k.ok) k.ok = verify_dev(*k.c, dst + lo[c], dsig + 114 * lo[c], dpk + 57 * lo[c], dmsg, doff + lo[c], prehashed, dctx, context_len, m, scratch[c], slots, grids, k.c->stream);
         k.fetch((int32_t *)status + lo[c], dst + lo[c], m);
     }
     if (!k.ok && k.c) cudaStreamSynchronize(k.c->copy_stream); /* never leave copies in flight behind an error */
@@ -766,16 +795,16 @@ goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status,
     Ctx *c = dev_ctx();
     if (!c) return GOLDILOCKS_FAILURE;
     std::lock_guard<std::mutex> g(c->mu); /* the per-thread table slots are shared per device */
-    int grid = 1;
-    if (!smp_grid<SlotEdVerifyFinish>(*c, &grid)) return GOLDILOCKS_FAILURE;
-    size_t bytes = (size_t)grid * SLOT_BLOCK * WTAB_QUADS_PER_LANE * sizeof(uint4);
+    VerifyGrids grids;
+    if (!verify_grids(*c, &grids)) return GOLDILOCKS_FAILURE;
+    size_t bytes = (size_t)(grids.unique > grids.shared ? grids.unique : grids.shared) * SLOT_BLOCK * WTAB_QUADS_PER_LANE * sizeof(uint4);
     if (bytes > c->slot_cap) {
         if (c->slot_scratch) cudaFree(c->slot_scratch);
         c->slot_scratch = nullptr; c->slot_cap = 0;
         if (cudaMalloc(&c->slot_scratch, bytes) != cudaSuccess) { g_err = "cudaMalloc(slot scratch)"; return GOLDILOCKS_FAILURE; }
         c->slot_cap = bytes;
     }
-    return verify_dev(*c, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, scratch, (uint4 *)c->slot_scratch, grid, as_stream(stream))
+    return verify_dev(*c, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, scratch, (uint4 *)c->slot_scratch, grids, as_stream(stream))
                ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
 }
 goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream) {

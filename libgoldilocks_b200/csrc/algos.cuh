@@ -22,8 +22,15 @@
  * (16384 x 192 B = 3 MB, L2 resident).  Public indices only -- never used on a secret scalar. */
 #define WIDE_BITS 15
 #define WIDE_ENTRIES (1 << (WIDE_BITS - 1))
-#define WIDE_LANES 128                         /* lanes that build the table at init */
+#define WIDE_LANES 128                         /* lanes that build one table at init */
 #define WIDE_PER_LANE (WIDE_ENTRIES / WIDE_LANES)
+/* Verification under a REPEATED public key splits both scalars into VSH_CHUNKS columns of VSH_ROWS
+ * 5-bit digits: digit k = VSH_ROWS*c + r is served by tables of 2^(115c)*A (built once per key) and 2^(115c)*B
+ * (wide tables 1..3, built at init next to table 0), so one signature costs 22*5 doublings instead of 89*5. */
+#define VSH_CHUNKS 4
+#define VSH_ROWS 23
+#define VSH_SHIFT (VSH_ROWS * WINDOW_BITS)     /* 115 bits between columns */
+#define WIDE_TABLES VSH_CHUNKS
 
 /* Doubling-free fixed-base table of the batched comb kernel: the reference's signed comb generalised to
  * (n, t, s) = (90, 5, 1) -- 90 rows of 16 canonical affine niels, row j = {(16 +- 8 +- 4 +- 2 +- 1) 2^(5j) B}.
@@ -286,14 +293,22 @@ GD void build_wnaf_base(niels *out32, const pt &base) {
 // One lane's share of the verification table: entries [per*lane, per*(lane+1)) = odd multiples
 // (2e+1)B.  `tmp`/`pre` are global scratch (one pniels / one gf per entry).  Start point from the
 // comb table, then repeated +2B; normalised with one inversion per lane (Montgomery's trick).
-GD void build_wide_lane(niels *out, pniels *tmp, gf *pre, const niels *comb, int lane) {
-    const uint32_t bw[14] = GOLD_CONST_BASE_WORDS;
-    pt base, twob, p;
-    (void)pt_decode(base, bw, 0);
-    pt_double(twob, base, false);
-    sc start;
+GD void build_wide_lane(niels *out, pniels *tmp, gf *pre, const niels *comb, int lane_all) {
+    const int c = lane_all / WIDE_LANES, lane = lane_all % WIDE_LANES;   /* table c holds multiples of 2^(115c) B */
+    out += (size_t)c * WIDE_ENTRIES; tmp += (size_t)c * WIDE_ENTRIES; pre += (size_t)c * WIDE_ENTRIES;
+    pt twob, p;
+    sc start, two;
     sc_set_zero(start);
-    start.w[0] = 2u * (uint32_t)(WIDE_PER_LANE * lane) + 1u;
+    sc_set_zero(two);
+    {   /* (2 e0 + 1) << 115c and 2 << 115c: both far below q, no reduction needed */
+        const uint64_t odd = 2u * (uint32_t)(WIDE_PER_LANE * lane) + 1u;
+        const int sh = VSH_SHIFT * c, word = sh / 32, bit = sh % 32;
+        const uint64_t lo = odd << bit;                    /* odd < 2^15, bit < 32 */
+        start.w[word] = (uint32_t)lo; start.w[word + 1] = (uint32_t)(lo >> 32);
+        const uint64_t t2 = (uint64_t)2 << bit;
+        two.w[word] = (uint32_t)t2; two.w[word + 1] = (uint32_t)(t2 >> 32);
+    }
+    comb_scalarmul(twob, comb, two);
     comb_scalarmul(p, comb, start);
     const int e0 = WIDE_PER_LANE * lane;
     for (int i = 0; i < WIDE_PER_LANE; i++) {

@@ -3,3 +3,5 @@
 INSTANTIATE_PLAIN(LaneEdVerifyDecode)
 INSTANTIATE_PLAIN(LaneEdVerifyScalars)
 INSTANTIATE_SMP(SlotEdVerifyFinish)
+INSTANTIATE_SMP(SlotEdVerifyFinishShared)
+INSTANTIATE_SMP(SlotKeyTables)

@@ -5,6 +5,7 @@
 #pragma once
 #include <stddef.h>
 #include "algos.cuh"
+#include "verify_plan.cuh"
 
 // ---- host-ABI layouts (reference x86_64 ABI: f_field.h:23-27, point_448.h:66-86) -------------
 struct abi_gf { uint64_t limb[8]; };
@@ -498,16 +499,30 @@ struct LaneEdSignFinish {
 //   2) challenge = -SHAKE256(dom || R || A || M) mod q, response = S mod q
 //   3) combo = response*B + challenge*A ; accept iff combo == R (mod 2-torsion) and both decodes succeeded
 //      (SlotEdVerifyFinish, slot_lanes.cuh)
-struct LaneEdVerifyDecode { /* lane 2i = public key i, lane 2i+1 = R of signature i */
-    abi_pt *pts; int32_t *ok; const uint8_t *sig, *pk;
+struct LaneEdVerifyDecode {
+    /* Without a plan: lane 2i = public key i, lane 2i+1 = R of signature i.  With the plan of a grouped batch
+     * (verify_plan.cuh) a public key is decoded once per key: lanes [0, n) = R of every signature, then the keys of
+     * the stand-alone signatures, then one representative per key table; the remaining lanes retire at once.
+     * Either way the result lands in pts[2i] (key of signature i) / pts[2i+1] (its R). */
+    abi_pt *pts; int32_t *ok; const uint8_t *sig, *pk; size_t n; verify_plan plan;
     GDM void operator()(size_t j) const {
-        const size_t i = j >> 1;
-        const uint8_t *enc = (j & 1) ? sig + 114 * i : pk + 57 * i;
+        size_t i = j >> 1, which = j & 1;
+        if (plan.unique_sig) {
+            if (j < n) { i = j; which = 1; }
+            else {
+                const size_t k = j - n, nu = plan.counts[1];
+                if (k < nu) i = plan.unique_sig[k];
+                else if (k - nu < plan.counts[2]) i = plan.tab_rep[k - nu];
+                else return;
+                which = 0;
+            }
+        }
+        const uint8_t *enc = which ? sig + 114 * i : pk + 57 * i;
         pt p; uint32_t w[15];
         words_load_bytes(w, 15, enc, 57);
         gmask_t good = pt_decode_like_eddsa(p, w, w[14] & 0xff);
         /* the third launch only needs TIGHT limbs back, so store weakly reduced (not canonical) limbs */
-        abi_pt *o = pts + j;
+        abi_pt *o = pts + 2 * i + which;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             o->x.limb[k] = (uint64_t)p.x.v[2 * k] + ((uint64_t)p.x.v[2 * k + 1] << 28);
@@ -515,7 +530,7 @@ struct LaneEdVerifyDecode { /* lane 2i = public key i, lane 2i+1 = R of signatur
             o->z.limb[k] = (uint64_t)p.z.v[2 * k] + ((uint64_t)p.z.v[2 * k + 1] << 28);
             o->t.limb[k] = (uint64_t)p.t.v[2 * k] + ((uint64_t)p.t.v[2 * k + 1] << 28);
         }
-        ok[j] = ST_OK(good);
+        ok[2 * i + which] = ST_OK(good);
     }
 };
 struct LaneEdVerifyScalars {

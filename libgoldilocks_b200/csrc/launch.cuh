@@ -39,6 +39,8 @@ template <> struct slot_min_blocks<SlotScalarmul> { static constexpr int value =
 template <> struct slot_min_blocks<SlotDoubleScalarmul> { static constexpr int value = SLOT7_MIN_BLOCKS; };
 template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int value = 4; }; /* 3 blocks (no spills): 111.7 vs 110.9 ms */
 template <> struct slot_min_blocks<SlotBaseDoubleScalarmul> { static constexpr int value = 4; };
+template <> struct slot_min_blocks<SlotEdVerifyFinishShared> { static constexpr int value = 4; };
+template <> struct slot_min_blocks<SlotKeyTables> { static constexpr int value = 4; };
 template <class F>
 cudaError_t launch_sm(const F &f, size_t n, cudaStream_t s) {
     const int smem = F::NSLOTS * 64 * SLOT_BLOCK;
@@ -87,7 +89,7 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
 #define LANES_SM(X) X(SlotX448) X(SlotComb) X(SlotCombTable) X(SlotX448DerivePk) X(SlotEdDerivePk) X(SlotEdSignR)
 #define INSTANTIATE_SM(F) template cudaError_t launch_sm<F>(const F &, size_t, cudaStream_t);
 #define DECLARE_SM(F) extern INSTANTIATE_SM(F)
-#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul) X(SlotDualScalarmul) X(SlotDirectScalarmul)
+#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotEdVerifyFinishShared) X(SlotKeyTables) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul) X(SlotDualScalarmul) X(SlotDirectScalarmul)
 #define INSTANTIATE_SMP(F)                                                                          \
     template cudaError_t sm_configure<F>(int *);                                                    \
     template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t);

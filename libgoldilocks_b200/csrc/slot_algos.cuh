@@ -266,6 +266,85 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Verification under a repeated public key (same group element as s_base_double_scalarmul).
+// The 90 signed 5-bit digits d_k of scalar2 and the 30 signed 15-bit digits e_m of scalar1 (the very recoding
+// above) are regrouped by column: k = 23c + r, so
+//     combo = sum_r 2^(5r) * ( sum_c d_(23c+r) * A_c  +  sum_{c : 3 | 23c+r} e_((23c+r)/3) * B_c ),
+// with A_c = 2^(115c) A from a table built ONCE PER KEY (s_build_key_tables: 3 x 115 doublings + four
+// 16-entry tables of odd multiples, shared read-only by every signature under that key) and B_c = 2^(115c) B from
+// the init-time wide tables.  One signature then costs 22 x 5 doublings + 90 + 30 additions.
+// Table layout: KTAB_ENTRIES pniels, entry 16c + e = (2e+1) A_c; entries 64, 65 are build scratch.
+// ---------------------------------------------------------------------------------------------
+#define KTAB_ENTRIES (VSH_CHUNKS * WINDOW_NTABLE + 2)
+#define KTAB_QUADS (KTAB_ENTRIES * 16)
+GD wtab<1> ktab_of(uint4 *ktabs, size_t table) { wtab<1> t; t.base = ktabs + table * KTAB_QUADS; return t; }
+// On entry slots 0..3 hold A (all four coordinates valid).
+GD void s_build_key_tables(sref sb, const wtab<1> &t) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    const int save = VSH_CHUNKS * WINDOW_NTABLE + 1;       /* A_c parked here while its table is built (the builder clobbers p) */
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int c = 0; c < VSH_CHUNKS; c++) {
+        s_stg<1>(t.coord(save, 0), p.x); s_stg<1>(t.coord(save, 1), p.y); s_stg<1>(t.coord(save, 2), p.z); s_stg<1>(t.coord(save, 3), p.t);
+        wtab<1> tc;
+        tc.base = t.base + (size_t)c * WINDOW_NTABLE * 16;  /* its scratch entry 16 is entry 0 of the next column, written later */
+        s_prepare_fixed_window<1>(p, w, tc);
+        if (c == VSH_CHUNKS - 1) break;
+        s_ldg<1>(p.x, t.coord(save, 0)); s_ldg<1>(p.y, t.coord(save, 1)); s_ldg<1>(p.z, t.coord(save, 2));
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < VSH_SHIFT - 1; j++) s_pt_double(p, w, true);
+        s_pt_double(p, w, false);
+    }
+}
+// combo (slots 0..3) = scalar1*B + scalar2*A with A's tables in `kt`; `wide4` = the four init-time tables.
+GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide4, const wtab<1> &kt) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    sc s1x, s2x;
+    sc_recode_signed(s1x, scalar1);
+    sc_recode_signed(s2x, scalar2);
+    s_pt_set_identity(p);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int r = VSH_ROWS - 1; r >= 0; r--) {
+        if (r != VSH_ROWS - 1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = 0; j < WINDOW_BITS - 1; j++) s_pt_double(p, w, true);
+            s_pt_double(p, w, false);
+        }
+        const int last_k = (VSH_CHUNKS - 1) * VSH_ROWS + r <= 89 ? (VSH_CHUNKS - 1) * VSH_ROWS + r : (VSH_CHUNKS - 2) * VSH_ROWS + r;
+        const bool last_fixed = (last_k % 3) == 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int c = 0; c < VSH_CHUNKS; c++) {
+            const int k = VSH_ROWS * c + r;
+            if (k > 89) break;
+            const bool fixed_here = (k % 3) == 0;
+            const bool row_ends = r != 0 && k == last_k;    /* a doubling follows: T is not needed */
+            uint32_t bits2 = sc_window5(s2x, k * WINDOW_BITS);
+            const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
+            bits2 ^= inv2;
+            s_pt_add_pniels_g<1>(p, w, kt, c * WINDOW_NTABLE + (int)(bits2 & (WINDOW_NTABLE - 1)), inv2, ~inv2, row_ends && !last_fixed);
+            if (fixed_here) {
+                uint32_t bits1 = sc_bits(s1x, k * WINDOW_BITS, WIDE_BITS);
+                const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
+                bits1 ^= inv1;
+                const niels *e = wide4 + (size_t)c * WIDE_ENTRIES + (bits1 & (WIDE_ENTRIES - 1));
+                s_pt_add_niels_g<1>(p, w, gq(&e->a), gq(&e->b), gq(&e->c), inv1, inv1, row_ends);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fixed-base signed comb, constant time -- reference goldilocks.c:830-877 (same digits, table and
 // operation order as comb_scalarmul in algos.cuh).  7 slots: X,Y,Z,T and three temporaries; the three
 // coordinates of the selected entry are fetched just in time (a and b, then c) into slots that are dead at

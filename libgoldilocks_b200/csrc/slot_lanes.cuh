@@ -3,6 +3,7 @@
 #pragma once
 #include "lanes.cuh"
 #include "slot_algos.cuh"
+#include "verify_plan.cuh"
 
 struct SlotX448 { /* goldilocks_x448 (goldilocks.c:1006-1076) */
     static constexpr int NSLOTS = X448_NSLOTS;
@@ -58,6 +59,19 @@ struct SlotBaseDoubleScalarmul { /* goldilocks_448_base_double_scalarmul_non_sec
 };
 // Third launch of verification (eddsa.c:293-305): combo = response*B + challenge*A, accept iff
 // combo == R on the quotient group (goldilocks.c:644-653) and both decodes succeeded.
+// accept iff combo (slots 0..3) == R on the quotient group and both decodes succeeded
+GD void s_verify_accept(int32_t *status, size_t i, sref sb, const abi_pt *r_pt, gmask_t decoded) {
+    /* pt_eq(combo, R): combo.y * R.x == R.y * combo.x */
+    const sref t0 = s_slot(sb, 4), t1 = s_slot(sb, 5);
+    gf a, b;
+    gf_from_abi(a, &r_pt->x); s_st(t0, a);
+    gf_from_abi(b, &r_pt->y); s_st(t1, b);
+    s_mul(t0, s_slot(sb, 1), t0);
+    s_mul(t1, s_slot(sb, 0), t1);
+    s_ld(a, t0);
+    s_ld(b, t1);
+    status[i] = ST_OK(gf_eq(a, b) & decoded);
+}
 struct SlotEdVerifyFinish {
     static constexpr int NSLOTS = BDSM_NSLOTS;
     int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; uint4 *scratch;
@@ -68,18 +82,49 @@ struct SlotEdVerifyFinish {
         s_pt_from_abi(sb, pts + 2 * i);
         s_base_double_scalarmul(sb, r, c, wide, wtab_of<1>(scratch, slot));
         s_bdsm_quirk(sb, c);
-        /* pt_eq(combo, R): combo.y * R.x == R.y * combo.x */
-        const sref t0 = s_slot(sb, 4), t1 = s_slot(sb, 5);
-        gf a, b;
-        gf_from_abi(a, &pts[2 * i + 1].x); s_st(t0, a);
-        gf_from_abi(b, &pts[2 * i + 1].y); s_st(t1, b);
-        s_mul(t0, s_slot(sb, 1), t0);
-        s_mul(t1, s_slot(sb, 0), t1);
-        s_ld(a, t0);
-        s_ld(b, t1);
-        gmask_t good = gf_eq(a, b);
-        good &= (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1];
-        status[i] = ST_OK(good);
+        s_verify_accept(status, i, sb, pts + 2 * i + 1, (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1]);
+    }
+};
+// One lane per key table: the decoded public key of the group's representative signature -> its column tables.
+struct SlotKeyTables {
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    const abi_pt *pts; uint4 *ktabs; verify_plan plan;
+    GDM void operator()(size_t t, sref sb, size_t slot) const {
+        (void)slot;
+        if (t >= plan.counts[2]) return;
+        s_pt_from_abi(sb, pts + 2 * (size_t)plan.tab_rep[t]);
+        s_build_key_tables(sb, ktab_of(ktabs, t));
+    }
+};
+// The finish kernel of a grouped batch.  Work items [0, counts[0]) are signatures whose public key (byte-identical)
+// occurs more than once: the multiples of the key come from the table its group built.  Items [counts[0],
+// counts[0] + counts[1]) are the stand-alone signatures, verified exactly like SlotEdVerifyFinish (own window table in
+// `scratch`).  One launch for both, so the stand-alone tail fills the lanes the table path leaves idle.
+struct SlotEdVerifyFinishShared {
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; uint4 *ktabs; uint4 *scratch;
+    verify_plan plan;
+    GDM void operator()(size_t j, sref sb, size_t slot) const {
+        const size_t ns = plan.counts[0];
+        sc c, r;
+        if (j < ns) {
+            const size_t i = plan.shared_sig[j], t = plan.shared_tab[j];
+            sc_from_abi(c, challenge + i);
+            sc_from_abi(r, response + i);
+            s_verify_shared_key(sb, r, c, wide, ktab_of(ktabs, t));
+            s_bdsm_quirk(sb, c);
+            /* the key bytes are the representative's, so its decode flag is this signature's */
+            s_verify_accept(status, i, sb, pts + 2 * i + 1, (gmask_t)ok[2 * (size_t)plan.tab_rep[t]] & (gmask_t)ok[2 * i + 1]);
+        } else {
+            if (j - ns >= plan.counts[1]) return;
+            const size_t i = plan.unique_sig[j - ns];
+            sc_from_abi(c, challenge + i);
+            sc_from_abi(r, response + i);
+            s_pt_from_abi(sb, pts + 2 * i);
+            s_base_double_scalarmul(sb, r, c, wide, wtab_of<1>(scratch, slot));
+            s_bdsm_quirk(sb, c);
+            s_verify_accept(status, i, sb, pts + 2 * i + 1, (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1]);
+        }
     }
 };
 

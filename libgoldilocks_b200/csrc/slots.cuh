@@ -178,6 +178,8 @@ SFN void s_lookup_ct(sref d, const uint4 *first, int estride, int n, uint32_t id
 }
 SFN void s_copy(sref d, sref a) { gf x; s_ld(x, a); s_st(d, x); }
 template <int QS>
+SFN void s_ldg(sref d, const uint4 *g) { gf x; gq_ld<false, QS>(x, g); s_st(d, x); } /* global -> slot */
+template <int QS>
 SFN void s_stg(uint4 *g, sref a) { gf x; s_ld(x, a); gq_st<QS>(g, x); } /* slot -> global */
 
 // a = x^((p-3)/4); returns all-ones iff a^2 x == 1.  Same addition chain as gf_isr (gf.cuh), walked

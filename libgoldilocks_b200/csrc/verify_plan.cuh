@@ -1,0 +1,22 @@
+// verify_plan.cuh -- work lists of a verification batch, made on the device by the key-grouping pass (k_group.cu).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+// Signatures whose 57 public-key bytes occur at least twice in the batch are verified against one per-key table
+// (SlotKeyTables / SlotEdVerifyFinishShared); everything else goes through SlotEdVerifyFinish on its own.
+//   shared_sig[j], shared_tab[j] : signature index and key-table index of the j-th table-path signature, ordered so
+//                                  that signatures under one key are adjacent lanes (their table rows stay in L1/L2)
+//   unique_sig[j]                : signature index of the j-th stand-alone signature
+//   tab_rep[t]                   : a signature whose public key is key t (its decoded point seeds the table)
+//   counts[0..2]                 : number of table-path signatures, stand-alone signatures, key tables
+// A null unique_sig means "no plan: every signature, in order, stand-alone".
+struct verify_plan {
+    const uint32_t *shared_sig, *shared_tab, *unique_sig, *tab_rep, *counts;
+};
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+// Bytes of device scratch group_keys() needs for n signatures and at most `cap` key tables.
+size_t group_scratch_bytes(size_t n, size_t cap);
+// Enqueues the grouping pass on `s`; `plan` receives pointers into `scratch`.  No host synchronisation.
+cudaError_t group_keys(const uint8_t *pk, size_t n, uint32_t cap, void *scratch, verify_plan *plan, cudaStream_t s, uint64_t *launches);
+#endif

@@ -10,6 +10,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -71,10 +73,10 @@ static fixed_tables *tables() {
 static niels *wide_table() {
     static niels *w = nullptr;
     if (!w) {
-        w = (niels *)aligned_alloc(64, sizeof(niels) * WIDE_ENTRIES);
-        std::vector<pniels> tmp(WIDE_ENTRIES);
-        std::vector<gf> pre(WIDE_ENTRIES);
-        for (int lane = 0; lane < WIDE_LANES; lane++) build_wide_lane(w, tmp.data(), pre.data(), tables()->comb, lane);
+        w = (niels *)aligned_alloc(64, sizeof(niels) * WIDE_ENTRIES * WIDE_TABLES);
+        std::vector<pniels> tmp(WIDE_ENTRIES * WIDE_TABLES);
+        std::vector<gf> pre(WIDE_ENTRIES * WIDE_TABLES);
+        for (int lane = 0; lane < WIDE_LANES * WIDE_TABLES; lane++) build_wide_lane(w, tmp.data(), pre.data(), tables()->comb, lane);
     }
     return w;
 }
@@ -182,11 +184,30 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     std::vector<abi_pt> pts(2 * n);
     std::vector<int32_t> ok(2 * n);
     std::vector<abi_sc> chal(n), resp(n);
-    LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk};
-    run(f1, 2 * n);
     LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len};
     run(f2, n);
-    SlotEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), slots(1)};
-    run_smp(f3, n);
+    /* the key-grouping pass of k_group.cu restated on the host: byte-identical keys that occur at least twice share a table */
+    std::map<std::string, std::vector<uint32_t>> groups;
+    for (size_t i = 0; i < n; i++) groups[std::string((const char *)pk + 57 * i, 57)].push_back((uint32_t)i);
+    std::vector<uint32_t> shared_sig, shared_tab, unique_sig, tab_rep, counts(3);
+    const size_t cap = n / 8 + 1;
+    for (auto &g : groups) {
+        if (g.second.size() >= 2 && tab_rep.size() < cap) {
+            for (uint32_t i : g.second) { shared_sig.push_back(i); shared_tab.push_back((uint32_t)tab_rep.size()); }
+            tab_rep.push_back(g.second[0]);
+        } else {
+            for (uint32_t i : g.second) unique_sig.push_back(i);
+        }
+    }
+    counts[0] = (uint32_t)shared_sig.size(); counts[1] = (uint32_t)unique_sig.size(); counts[2] = (uint32_t)tab_rep.size();
+    shared_sig.push_back(0); shared_tab.push_back(0); unique_sig.push_back(0); tab_rep.push_back(0); /* never empty */
+    verify_plan plan = {shared_sig.data(), shared_tab.data(), unique_sig.data(), tab_rep.data(), counts.data()};
+    std::vector<uint4> ktabs((size_t)(counts[2] + 1) * KTAB_QUADS);
+    LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, plan};
+    run(f1, 2 * n);
+    SlotKeyTables ft = {pts.data(), ktabs.data(), plan};
+    run_smp(ft, counts[2]);
+    SlotEdVerifyFinishShared fs = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), ktabs.data(), slots(1), plan};
+    run_smp(fs, (size_t)counts[0] + counts[1]);
     return -1;
 }

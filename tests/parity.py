@@ -278,6 +278,46 @@ def check_eddsa_random(lib, chk, n, label="c4"):
         eq(lib.ed448_verify(s1, pk0[idx[:m]], sub_msgs[:m], ph, ctx), np.full(m, -1, np.int32), "verify ctx/ph")
 
 
+def check_eddsa_grouped(lib, chk, n, label="c4g", per_key=(1, 2, 3, 16, 5, 1, 40)):
+    """Repeated public keys: the batch path groups byte-identical keys and verifies them against one
+    per-key table; accept bits must still be the reference's, whatever the multiplicities and the order.  Keys come with
+    multiplicities cycling through `per_key`, the batch is shuffled, 1/8 of the entries are corrupted (R, S, A, message,
+    S+q) and two whole groups use undecodable keys (y = 1 and a non-canonical y >= p)."""
+    mult = []
+    while sum(mult) < n:
+        mult.append(per_key[len(mult) % len(per_key)])
+    nk = len(mult)
+    key_of = np.repeat(np.arange(nk), mult)[:n]
+    sk = stream_bytes(label + "/sk", nk * 57).reshape(nk, 57)
+    pk_k = chk.ed448_derive_public_key(sk)
+    lens = stream_bytes(label + "/len", n).astype(np.int64) % 70
+    blob = stream_bytes(label + "/msg", int(lens.sum()) + 1)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    msgs = [bytes(blob[offs[i]:offs[i + 1]]) for i in range(n)]
+    pk = pk_k[key_of].copy()
+    sig = chk.ed448_sign(sk[key_of], pk, msgs)
+    sel = stream_bytes(label + "/sel", 2 * n)
+    for i in range(0, n, 8):
+        kind = 1 + (i // 8) % 5
+        bit = 1 << (sel[2 * i] & 7); pos = int(sel[2 * i + 1])
+        if kind == 1: sig[i, pos % 57] ^= bit
+        elif kind == 2: sig[i, 57 + pos % 56] ^= bit
+        elif kind == 3: pk[i, pos % 57] ^= bit
+        elif kind == 4:
+            m = bytearray(msgs[i]) or bytearray(b"\0"); m[pos % len(m)] ^= bit; msgs[i] = bytes(m)
+        else: sig[i, 57:114] = le(util.from_le(sig[i, 57:114]) + util.Q, 57)
+    bad_groups = [g for g in range(nk) if 3 <= mult[g] <= 16][:2]
+    for g, enc in zip(bad_groups, (le(1, 57), le(P + 2, 57))):
+        pk[key_of == g] = enc
+    perm = np.argsort(stream_bytes(label + "/perm", 4 * n).view("<u4")[:n], kind="stable")
+    sig, pk, msgs = sig[perm], pk[perm], [msgs[i] for i in perm]
+    want = chk.ed448_verify(sig, pk, msgs)
+    got = lib.ed448_verify(sig, pk, msgs)
+    eq(got, want, "ed448_verify status with repeated public keys")
+    assert (want == -1).sum() > n // 2 and (want == 0).sum() >= n // 16
+    return want
+
+
 def check_shake(lib, n=40):
     msgs = [bytes(stream_bytes("shake/%d" % i, i * 7)) for i in range(n)] + [b"", b"a" * 135, b"b" * 136, b"c" * 137, b"d" * 272]
     for outlen in (32, 57, 114, 136, 137, 300):

@@ -66,6 +66,16 @@ def test_eddsa_random(gpu, chk):
     parity.check_eddsa_random(gpu, chk, 1 << 12)
 
 
+def test_eddsa_repeated_keys(gpu, chk):
+    """per-key tables (device-side key grouping): mixed multiplicities, more groups than tables (all pairs: the
+    table budget of n/8 + 1 overflows and the rest must fall back to stand-alone verification), one key for the
+    whole batch, and a batch just at the grouping threshold"""
+    parity.check_eddsa_grouped(gpu, chk, 1 << 12)
+    parity.check_eddsa_grouped(gpu, chk, 1 << 11, label="c4g/pairs", per_key=(2,))
+    parity.check_eddsa_grouped(gpu, chk, 1 << 10, label="c4g/one", per_key=(3, 1 << 10))
+    parity.check_eddsa_grouped(gpu, chk, 64, label="c4g/min", per_key=(4, 1, 9))
+
+
 def test_decaf_vectors(gpu, vectors):
     parity.check_decaf_vectors(gpu, vectors)
 

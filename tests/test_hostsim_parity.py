@@ -52,6 +52,7 @@ def test_eddsa(sim, chk, vectors):
     _threads(sim, chk)
     parity.check_eddsa_vectors(sim, vectors)
     parity.check_eddsa_random(sim, chk, 192)
+    parity.check_eddsa_grouped(sim, chk, 160)
 
 
 def test_decaf_vectors(sim, vectors):

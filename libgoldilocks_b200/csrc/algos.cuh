@@ -25,11 +25,14 @@
 #define WIDE_LANES 128                         /* lanes that build one table at init */
 #define WIDE_PER_LANE (WIDE_ENTRIES / WIDE_LANES)
 /* Verification under a REPEATED public key splits both scalars into VSH_CHUNKS columns of VSH_ROWS
- * 5-bit digits: digit k = VSH_ROWS*c + r is served by tables of 2^(115c)*A (built once per key) and 2^(115c)*B
- * (wide tables 1..3, built at init next to table 0), so one signature costs 22*5 doublings instead of 89*5. */
-#define VSH_CHUNKS 4
-#define VSH_ROWS 23
-#define VSH_SHIFT (VSH_ROWS * WINDOW_BITS)     /* 115 bits between columns */
+ * 5-bit digits: digit k = VSH_ROWS*c + r is served by tables of 2^(75c)*A (built once per key) and 2^(75c)*B
+ * (wide tables 1..5, built at init next to table 0), so one signature costs 14*5 doublings instead of 89*5.
+ * Measured on the bench corpus (16 signatures per key): 4 x 23 -> 50.7 ms, 6 x 15 -> see DESIGN.md. */
+#ifndef VSH_CHUNKS
+#define VSH_CHUNKS 6
+#define VSH_ROWS 15
+#endif
+#define VSH_SHIFT (VSH_ROWS * WINDOW_BITS)     /* bits between columns */
 #define WIDE_TABLES VSH_CHUNKS
 
 /* Doubling-free fixed-base table of the batched comb kernel: the reference's signed comb generalised to
@@ -294,13 +297,13 @@ GD void build_wnaf_base(niels *out32, const pt &base) {
 // (2e+1)B.  `tmp`/`pre` are global scratch (one pniels / one gf per entry).  Start point from the
 // comb table, then repeated +2B; normalised with one inversion per lane (Montgomery's trick).
 GD void build_wide_lane(niels *out, pniels *tmp, gf *pre, const niels *comb, int lane_all) {
-    const int c = lane_all / WIDE_LANES, lane = lane_all % WIDE_LANES;   /* table c holds multiples of 2^(115c) B */
+    const int c = lane_all / WIDE_LANES, lane = lane_all % WIDE_LANES;   /* table c holds multiples of 2^(VSH_SHIFT c) B */
     out += (size_t)c * WIDE_ENTRIES; tmp += (size_t)c * WIDE_ENTRIES; pre += (size_t)c * WIDE_ENTRIES;
     pt twob, p;
     sc start, two;
     sc_set_zero(start);
     sc_set_zero(two);
-    {   /* (2 e0 + 1) << 115c and 2 << 115c: both far below q, no reduction needed */
+    {   /* (2 e0 + 1) << (VSH_SHIFT c) and 2 << (VSH_SHIFT c): both far below q, no reduction needed */
         const uint64_t odd = 2u * (uint32_t)(WIDE_PER_LANE * lane) + 1u;
         const int sh = VSH_SHIFT * c, word = sh / 32, bit = sh % 32;
         const uint64_t lo = odd << bit;                    /* odd < 2^15, bit < 32 */

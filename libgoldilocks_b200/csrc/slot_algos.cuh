@@ -268,12 +268,12 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
 // ---------------------------------------------------------------------------------------------
 // Verification under a repeated public key (same group element as s_base_double_scalarmul).
 // The 90 signed 5-bit digits d_k of scalar2 and the 30 signed 15-bit digits e_m of scalar1 (the very recoding
-// above) are regrouped by column: k = 23c + r, so
-//     combo = sum_r 2^(5r) * ( sum_c d_(23c+r) * A_c  +  sum_{c : 3 | 23c+r} e_((23c+r)/3) * B_c ),
-// with A_c = 2^(115c) A from a table built ONCE PER KEY (s_build_key_tables: 3 x 115 doublings + four
-// 16-entry tables of odd multiples, shared read-only by every signature under that key) and B_c = 2^(115c) B from
-// the init-time wide tables.  One signature then costs 22 x 5 doublings + 90 + 30 additions.
-// Table layout: KTAB_ENTRIES pniels, entry 16c + e = (2e+1) A_c; entries 64, 65 are build scratch.
+// above) are regrouped by column: k = R c + r with R = VSH_ROWS (15) rows and VSH_CHUNKS (6) columns, so
+//     combo = sum_r 2^(5r) * ( sum_c d_(Rc+r) * A_c  +  sum_{c : 3 | Rc+r} e_((Rc+r)/3) * B_c ),
+// with A_c = 2^(5Rc) A from a table built ONCE PER KEY (s_build_key_tables: 5 x 75 doublings + six
+// 16-entry tables of odd multiples, shared read-only by every signature under that key) and B_c = 2^(5Rc) B from
+// the init-time wide tables.  One signature then costs 14 x 5 doublings + 90 + 30 additions.
+// Table layout: KTAB_ENTRIES pniels, entry 16c + e = (2e+1) A_c; the last two entries are build scratch.
 // ---------------------------------------------------------------------------------------------
 #define KTAB_ENTRIES (VSH_CHUNKS * WINDOW_NTABLE + 2)
 #define KTAB_QUADS (KTAB_ENTRIES * 16)
@@ -319,7 +319,7 @@ GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const
             for (int j = 0; j < WINDOW_BITS - 1; j++) s_pt_double(p, w, true);
             s_pt_double(p, w, false);
         }
-        const int last_k = (VSH_CHUNKS - 1) * VSH_ROWS + r <= 89 ? (VSH_CHUNKS - 1) * VSH_ROWS + r : (VSH_CHUNKS - 2) * VSH_ROWS + r;
+        const int last_k = (VSH_CHUNKS - 1) * VSH_ROWS + r <= 89 ? (VSH_CHUNKS - 1) * VSH_ROWS + r : (VSH_CHUNKS - 2) * VSH_ROWS + r; /* last column with a digit in this row */
         const bool last_fixed = (last_k % 3) == 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1

@@ -13,4 +13,4 @@ timeout 300 python tools/opbench.py --ops sign,scalarmul,comb,x448,gf_mul,point_
 cat gpurun_out/${tag}_opbench.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > /dev/null 2>&1
-tools/gpu_ncu.sh $tag finish decode x448 comb
+tools/gpu_ncu.sh $tag finish ktab decode x448 comb ptadd

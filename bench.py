@@ -268,7 +268,7 @@ def run_ours(args):
     for k in range(cnt):
         nm = names.raw[64 * k:64 * k + 64].split(b"\0")[0].decode()
         per_kernel.setdefault(nm, []).append(ms[k])
-    kavg = {k: float(np.mean(v)) for k, v in per_kernel.items()}
+    kavg = {k: float(np.sum(v)) / K for k, v in per_kernel.items()}   # ms per step and kernel (a kernel may launch more than once per step)
     dominant = "SlotEdVerifyFinishShared" if "SlotEdVerifyFinishShared" in kavg else "SlotEdVerifyFinish"
     t_finish = kavg.get(dominant, 0.0) / 1e3
     peak, peak_how = imad_peak()

@@ -239,6 +239,9 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_derive_public_key_batch(
 /* message i = msg[msg_off[i] .. msg_off[i+1]); prehashed/context are shared by the whole batch,
  * exactly the per-call arguments of the reference (eddsa.c:146-155,253-261). */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature /*n*114*/, const uint8_t *privkey /*n*57*/, const uint8_t *pubkey /*n*57*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n);
+/* status[i] is exactly what goldilocks_ed448_verify (eddsa.c:253-306) returns for element i.  Batches of 64 or more are
+ * grouped by public key on the device: signatures whose 57 key bytes are identical share one decode of the key and one
+ * table of its multiples, which only changes the cost, never the accept bit. */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature /*n*114*/, const uint8_t *pubkey /*n*57*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n);
 /* SHAKE256 one-shot over n inputs, each squeezed to outlen bytes (shake.c:177-190, SHAKE256 params 211-213) */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out /*n*outlen*/, size_t outlen, const uint8_t *in, const size_t *in_off /*n+1*/, size_t n);
@@ -248,6 +251,8 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *o
  *    current CUDA device, `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *    Calls are asynchronous on that stream; `scratch` must hold goldilocks_b200_*_scratch_bytes(n).
  * ====================================================================================== */
+/* scratch of a device-resident verification: decoded points and scalars, the key-grouping work lists and room for
+ * n/8 + 1 per-key tables (25 KB each); about 3.9 KB per signature */
 GOLDILOCKS_B200_API size_t goldilocks_b200_verify_scratch_bytes(size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off, uint8_t prehashed, const uint8_t *context /*device or NULL*/, uint8_t context_len, size_t n, void *scratch, void *stream);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream);

@@ -37,6 +37,8 @@ struct Ctx {
     bool ready = false, failed = false;
     int dev = -1, sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // signatures and messages of a verification cross PCIe here while the main stream groups the keys
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
     fixed_tables *ft = nullptr;
     niels *wide = nullptr;       // WIDE_TABLES x 16384-entry verification tables: odd multiples of 2^(75c) B (18 MB, L2 resident)
     std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
@@ -165,6 +167,8 @@ bool ctx_init(Ctx &c, int dev) {
     c.dev = dev;
     c.sms = p.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    for (auto &e : c.copy_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaMalloc(&c.ft, sizeof(fixed_tables)));
     LaneBuildTables f = {c.ft};
     if (!launch(c, f, TABLE_LANES, c.stream)) return false;
@@ -225,6 +229,12 @@ struct Call {
         return d;
     }
     template <class T> T *out(size_t count) { return (T *)alloc(count * sizeof(T)); }
+    // host -> device on the copy stream; `dev` was carved with out<>()
+    template <class T> void push(T *dev, const T *host, size_t count) {
+        if (!ok || count == 0) return;
+        cudaError_t e = cudaMemcpyAsync(dev, host, count * sizeof(T), cudaMemcpyHostToDevice, c->copy_stream);
+        if (e != cudaSuccess) ok = fail("cudaMemcpyAsync(H2D, copy stream)", e);
+    }
     template <class T> void fetch(T *host, const T *dev, size_t count) {
         if (!ok || count == 0) return;
         cudaError_t e = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream);
@@ -709,8 +719,12 @@ struct VerifyGrids { int unique = 1, shared = 1, tables = 1; };
 static bool verify_grids(Ctx &c, VerifyGrids *g) {
     return smp_grid<SlotEdVerifyFinish>(c, &g->unique) && smp_grid<SlotEdVerifyFinishShared>(c, &g->shared) && smp_grid<SlotKeyTables>(c, &g->tables);
 }
+// Host-pointer calls feed the signatures and messages in two halves on the copy stream: [0, split) is on the device
+// when ready[0] fires, the rest at ready[1]; the public keys (all the grouping pass needs) go first on the main stream.
+struct VerifyFeed { size_t split; cudaEvent_t ready[2]; };
 static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off, uint8_t prehashed,
-                       const uint8_t *ctx, uint8_t ctx_len, size_t n, void *scratch, uint4 *slots, const VerifyGrids &grids, cudaStream_t s) {
+                       const uint8_t *ctx, uint8_t ctx_len, size_t n, void *scratch, uint4 *slots, const VerifyGrids &grids, cudaStream_t s,
+                       const VerifyFeed *feed = nullptr) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     char *p = (char *)scratch;
     abi_pt *pts = (abi_pt *)p; p += al(2 * n * sizeof(abi_pt));
@@ -728,10 +742,24 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
         if (e != cudaSuccess) return fail("group_keys", e);
         g_launches += launched;
     }
-    LaneEdVerifyDecode f1 = {pts, ok, sig, pk, n, plan};
-    if (!launch(c, f1, 2 * n, s)) return false;
-    LaneEdVerifyScalars f2 = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len};
-    if (!launch(c, f2, n, s)) return false;
+    /* R of signatures [lo, hi) -- and, without a plan, their public keys (interleaved lanes) */
+    auto decode_range = [&](size_t lo, size_t hi) {
+        LaneEdVerifyDecode f = {pts, ok, sig, pk, n, plan, plan.unique_sig ? lo : 2 * lo};
+        return launch(c, f, plan.unique_sig ? hi - lo : 2 * (hi - lo), s);
+    };
+    auto scalars_range = [&](size_t lo, size_t hi) {
+        LaneEdVerifyScalars f = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len, lo};
+        return launch(c, f, hi - lo, s);
+    };
+    if (plan.unique_sig) { /* one decode per distinct key: needs the keys only, so it runs while the signatures still cross PCIe */
+        LaneEdVerifyDecode fa = {pts, ok, sig, pk, n, plan, n};
+        if (!launch(c, fa, n, s)) return false;
+    }
+    const size_t split = feed ? feed->split : n;
+    if (feed) CU(cudaStreamWaitEvent(s, feed->ready[0], 0));
+    if (!decode_range(0, split) || !scalars_range(0, split)) return false;
+    if (feed) CU(cudaStreamWaitEvent(s, feed->ready[1], 0));
+    if (split < n && (!decode_range(split, n) || !scalars_range(split, n))) return false;
     if (plan.unique_sig) {
         SlotKeyTables ft = {pts, ktabs, plan};
         if (!launch_smp(c, ft, cap, grids.tables, s)) return false;
@@ -743,22 +771,35 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
 }
 goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                  uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n) {
-    /* One pass over the whole batch.  (Splitting it so that the copy of a second chunk hides behind the first chunk's
-     * kernels was measured both ways on the grouped path: every chunk pays its own key-grouping pass and key-table
-     * wave, ~5.5 ms, against ~4 ms of PCIe time saved -- 67.9 ms split vs 66.3 ms in one piece at 2^20.) */
+    /* One pass over the whole batch (splitting the BATCH costs more than it hides: every chunk pays its own key-grouping
+     * pass and key-table wave, 67.9 ms split vs 66.3 ms whole at 2^20).  Only the COPIES are split: keys first, then the
+     * signatures and messages in two halves on the copy stream, so the grouping pass, the per-key decodes and the first
+     * half's decode run while the rest is still crossing PCIe. */
     Call k;
     size_t total = n ? msg_off[n] : 0;
     const size_t *doff = k.in(msg_off, n + 1);
     const uint8_t *dctx = k.in(context, context_len);
-    const uint8_t *dpk = k.in(pubkey, 57 * n), *dsig = k.in(signature, 114 * n), *dmsg = k.in(msg, total);
+    const uint8_t *dpk = k.in(pubkey, 57 * n);
+    uint8_t *dsig = k.out<uint8_t>(114 * n), *dmsg = k.out<uint8_t>(total);
     int32_t *dst = k.out<int32_t>(n);
     VerifyGrids grids;
     if (k.ok) k.ok = verify_grids(*k.c, &grids);
     const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
     uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
     void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(n));
-    if (k.ok) k.ok = verify_dev(*k.c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, scratch, slots, grids, k.c->stream);
+    VerifyFeed feed = {n >= 2 * VERIFY_GROUP_MIN ? n / 2 : n, {nullptr, nullptr}};
+    if (k.ok) {
+        feed.ready[0] = k.c->copy_done[0]; feed.ready[1] = k.c->copy_done[1];
+        const size_t lo[2] = {0, feed.split}, hi[2] = {feed.split, n};
+        for (int h = 0; h < 2 && k.ok; h++) {
+            k.push(dsig + 114 * lo[h], signature + 114 * lo[h], 114 * (hi[h] - lo[h]));
+            if (hi[h] > lo[h]) k.push(dmsg + msg_off[lo[h]], msg + msg_off[lo[h]], msg_off[hi[h]] - msg_off[lo[h]]);
+            if (cudaEventRecord(feed.ready[h], k.c->copy_stream) != cudaSuccess) k.ok = false;
+        }
+    }
+    if (k.ok) k.ok = verify_dev(*k.c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, scratch, slots, grids, k.c->stream, &feed);
     k.fetch((int32_t *)status, dst, n);
+    if (!k.ok && k.c) cudaStreamSynchronize(k.c->copy_stream); /* never leave copies in flight behind an error */
     return k.finish();
 }
 

@@ -504,8 +504,9 @@ struct LaneEdVerifyDecode {
      * (verify_plan.cuh) a public key is decoded once per key: lanes [0, n) = R of every signature, then the keys of
      * the stand-alone signatures, then one representative per key table; the remaining lanes retire at once.
      * Either way the result lands in pts[2i] (key of signature i) / pts[2i+1] (its R). */
-    abi_pt *pts; int32_t *ok; const uint8_t *sig, *pk; size_t n; verify_plan plan;
-    GDM void operator()(size_t j) const {
+    abi_pt *pts; int32_t *ok; const uint8_t *sig, *pk; size_t n; verify_plan plan; size_t lane0; /* first lane of this launch */
+    GDM void operator()(size_t j0) const {
+        const size_t j = j0 + lane0;
         size_t i = j >> 1, which = j & 1;
         if (plan.unique_sig) {
             if (j < n) { i = j; which = 1; }
@@ -534,8 +535,9 @@ struct LaneEdVerifyDecode {
     }
 };
 struct LaneEdVerifyScalars {
-    abi_sc *challenge, *response; const uint8_t *sig, *pk, *msg; const size_t *off; uint32_t prehashed; const uint8_t *ctx; uint32_t ctx_len;
-    GDM void operator()(size_t i) const {
+    abi_sc *challenge, *response; const uint8_t *sig, *pk, *msg; const size_t *off; uint32_t prehashed; const uint8_t *ctx; uint32_t ctx_len; size_t i0;
+    GDM void operator()(size_t k) const {
+        const size_t i = k + i0;
         sc c, nc, r;
         ed448_challenge(c, sig + 114 * i, pk + 57 * i, msg, off[i], off[i + 1], prehashed, ctx, ctx_len);
         sc_neg(nc, c);

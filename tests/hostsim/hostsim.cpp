@@ -184,7 +184,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     std::vector<abi_pt> pts(2 * n);
     std::vector<int32_t> ok(2 * n);
     std::vector<abi_sc> chal(n), resp(n);
-    LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len};
+    LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len, 0};
     run(f2, n);
     /* the key-grouping pass of k_group.cu restated on the host: byte-identical keys that occur at least twice share a table */
     std::map<std::string, std::vector<uint32_t>> groups;
@@ -203,7 +203,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     shared_sig.push_back(0); shared_tab.push_back(0); unique_sig.push_back(0); tab_rep.push_back(0); /* never empty */
     verify_plan plan = {shared_sig.data(), shared_tab.data(), unique_sig.data(), tab_rep.data(), counts.data()};
     std::vector<uint4> ktabs((size_t)(counts[2] + 1) * KTAB_QUADS);
-    LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, plan};
+    LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, plan, 0};
     run(f1, 2 * n);
     SlotKeyTables ft = {pts.data(), ktabs.data(), plan};
     run_smp(ft, counts[2]);

@@ -40,6 +40,20 @@ def main():
         tot = sum(t for _, t in ks)
         print("sign      n=%d kernels %s  -> %.2f M signatures/s (kernels only)" % (m, ks, m / tot / 1e3))
         a.ops = ",".join(o for o in a.ops.split(",") if o != "sign")
+    if "elligator" in a.ops.split(","):
+        m = min(n, 1 << 20)
+        h = stream_bytes("opbench/h2c", m * 112).reshape(m, 112)
+        which = (np.arange(m) % 8).astype(np.uint32)
+        hp = lib.from_hash_uniform(h)
+        peak_ = json.load(open(os.path.join(ROOT, "profiles", "r01_imad_peak.json")))["imad_wide_u32_gmac_s"]
+        for name, fn, mac in (("from_hash_nonuniform", lambda: lib.from_hash_nonuniform(h[:, :56]), 90672), ("from_hash_uniform", lambda: lib.from_hash_uniform(h), 182896),
+                              ("invert_elligator_nonuniform", lambda: lib.invert_elligator_nonuniform(hp, which), 2 * 90000),
+                              ("invert_elligator_uniform", lambda: lib.invert_elligator_uniform(hp, h[:, 56:], which), 3 * 90000)):
+            fn()
+            ks = kernel_ms(fn)
+            tot = sum(t for _, t in ks)
+            print("%-30s n=%d kernels %s -> %.2f Mops/s imad_frac %.3f" % (name, m, ks, m / tot / 1e3, m * mac / (tot / 1e3) / 1e9 / peak_))
+        a.ops = ",".join(o for o in a.ops.split(",") if o != "elligator")
     if "scalarmul" in a.ops.split(","):
         m = min(n, 1 << 18)
         hs = lib.scalar_decode_long(stream_bytes("opbench/vs", m * 56).reshape(m, 56), 56)

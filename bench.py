@@ -104,11 +104,12 @@ class ClockSampler:
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.window = index, [], None, None
 
     def start(self):
+        """started before the warm-up steps (nvidia-smi needs ~0.1 s to deliver its first sample); mark() brackets the timed region"""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -116,7 +117,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self, t0, t1):
+        self.window = (t0, t1)
 
     def stop(self):
         if self.proc:
@@ -125,16 +129,21 @@ class ClockSampler:
                 self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows, where = [r for _, r in self.rows], "warm-up + timed region (same load)"
+        if self.window:
+            inside = [r for t, r in self.rows if self.window[0] <= t <= self.window[1] + 0.02]
+            if inside:
+                rows, where = inside, "timed region"
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
 def host_cores():
@@ -239,16 +248,17 @@ def run_ours(args):
     def step():
         eng.ed448_verify(d_st, d_sig, d_pk, d_msg, d_off, d_scratch)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(W):
         step()
     torch.cuda.synchronize()
     assert (d_st.cpu().numpy() == expect).all(), "device verify disagrees with the corpus' expected accept bits"
 
     # ---- device-resident timed region -------------------------------------------------------------------
-    sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
+    t_wall0 = time.time()
     l0 = eng.launch_count()
     lib.lib.goldilocks_b200_profile(C.c_int(1))
     e0.record()
@@ -256,6 +266,7 @@ def run_ours(args):
         step()
     e1.record()
     barrier()
+    sampler.mark(t_wall0, time.time())
     lib.lib.goldilocks_b200_profile(C.c_int(0))
     launches = eng.launch_count() - l0
     clocks = sampler.stop()
@@ -388,7 +399,7 @@ def main():
     os.dup2(2, 1)          # anything a library prints to fd 1 from here on goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="signatures per GPU per step (default 2^20, the BASELINE size)")

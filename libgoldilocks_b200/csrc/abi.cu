@@ -709,10 +709,11 @@ goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t
 // occur more than once get one shared table (at most n/8 + 1 tables per call; the rest verify stand-alone).
 constexpr size_t VERIFY_GROUP_MIN = 64;
 static size_t verify_tab_cap(size_t n) { return n / 8 + 1; }
+static bool verify_groups(size_t n) { return n >= VERIFY_GROUP_MIN && n < ((size_t)1 << 31); } /* the work lists are 32-bit */
 size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t base = al(2 * n * sizeof(abi_pt)) + al(2 * n * sizeof(int32_t)) + 2 * al(n * sizeof(abi_sc));
-    if (n >= VERIFY_GROUP_MIN) base += al(group_scratch_bytes(n, verify_tab_cap(n))) + al(verify_tab_cap(n) * KTAB_QUADS * sizeof(uint4));
+    if (verify_groups(n)) base += al(group_scratch_bytes(n, verify_tab_cap(n))) + al(verify_tab_cap(n) * KTAB_QUADS * sizeof(uint4));
     return base;
 }
 struct VerifyGrids { int unique = 1, shared = 1, tables = 1; };
@@ -734,7 +735,7 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
     verify_plan plan = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint4 *ktabs = nullptr;
     const size_t cap = verify_tab_cap(n);
-    if (n >= VERIFY_GROUP_MIN) {
+    if (verify_groups(n)) {
         void *gs = p; p += al(group_scratch_bytes(n, cap));
         ktabs = (uint4 *)p;
         uint64_t launched = 0;

@@ -77,15 +77,21 @@ def hbm_peak():
 # ------------------------------------------------------------------------------------------------
 # workload (synthetic, seeded): 2^16 keys x 16 messages of 32 bytes, 1/8 corrupted
 # ------------------------------------------------------------------------------------------------
-def make_corpus(signer, n, label, per=16):
+def make_corpus(signer, n, label, per=16, varlen=False):
+    """varlen: message lengths uniform in [0, 256) (second run) instead of MSG_LEN bytes each"""
     from util import stream_bytes
     nk = max(1, n // per)
     sk = stream_bytes(label + "/sk", nk * 57).reshape(nk, 57)
     pk = signer.ed448_derive_public_key(sk)
     sk_all = np.repeat(sk, per, axis=0)[:n]
     pk_all = np.repeat(pk, per, axis=0)[:n].copy()
-    arena = stream_bytes(label + "/msg", n * MSG_LEN)
-    off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
+    if varlen:
+        lens = stream_bytes(label + "/len", n).astype(np.uint64)
+        off = np.concatenate([np.zeros(1, np.uint64), np.cumsum(lens, dtype=np.uint64)])
+        arena = stream_bytes(label + "/msg", int(off[-1]) + 1)
+    else:
+        arena = stream_bytes(label + "/msg", n * MSG_LEN)
+        off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
     sig = signer.ed448_sign(sk_all, pk_all, (arena, off))
     kinds = np.zeros(n, np.int32)
     kinds[::8] = 1 + (np.arange((n + 7) // 8) % 4)
@@ -93,7 +99,13 @@ def make_corpus(signer, n, label, per=16):
     i = np.flatnonzero(kinds == 1); sig[i, sel[i] % 57] ^= 1
     i = np.flatnonzero(kinds == 2); sig[i, 57 + sel[i] % 56] ^= 2
     i = np.flatnonzero(kinds == 3); pk_all[i, sel[i] % 57] ^= 4
-    i = np.flatnonzero(kinds == 4); arena[i * MSG_LEN + sel[i] % MSG_LEN] ^= 8
+    i = np.flatnonzero(kinds == 4)
+    if varlen:
+        i = i[off[i + 1] > off[i]]                       # an empty message has no byte to flip: left valid
+        kinds[np.setdiff1d(np.flatnonzero(kinds == 4), i)] = 0
+        arena[(off[i] + sel[i] % (off[i + 1] - off[i])).astype(np.int64)] ^= 8
+    else:
+        arena[i * MSG_LEN + sel[i] % MSG_LEN] ^= 8
     expect = np.where(kinds == 0, -1, 0).astype(np.int32)
     return sig, pk_all, arena, off, expect
 
@@ -347,26 +359,28 @@ def run_ours(args):
             extra[name] = {"value": world * n / t, "unit": "ops/s", "ms_per_step": t * 1e3, "batch_per_gpu": n,
                            "imad_frac": n * mac / t / 1e9 / peak, "algorithmic_mac32_per_op": mac}
 
-    # ---- extra: the same batch size with 2^20 DISTINCT keys (no table can be shared) -------------------------------
+    # ---- extra: the same batch size (a) with 2^20 DISTINCT keys (no table can be shared), (b) with message lengths
+    #      uniform in [0, 256) under the 2^16 x 16 keys (second run) --------------------------------------
     if not args.no_extra:
-        sig1, pk1, arena1, off1, expect1 = make_corpus(lib, n, "bench/distinct/rank%d" % rank, per=1)
-        t_sig, t_pk, t_msg, t_off = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (sig1.reshape(-1), pk1.reshape(-1), arena1, off1.view(np.int64)))
-        for _ in range(2):
-            eng.ed448_verify(d_st, t_sig, t_pk, t_msg, t_off, d_scratch)
-        torch.cuda.synchronize()
-        assert (d_st.cpu().numpy() == expect1).all(), "device verify (distinct keys) disagrees with the expected accept bits"
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kx = max(2, min(K, 3))
-        barrier()
-        a.record()
-        for _ in range(kx):
-            eng.ed448_verify(d_st, t_sig, t_pk, t_msg, t_off, d_scratch)
-        b.record()
-        barrier()
-        t = max_over_ranks(a.elapsed_time(b) / 1e3 / kx)
-        extra["verify_distinct_keys"] = {"value": world * n / t, "unit": UNIT, "ms_per_step": t * 1e3, "batch_per_gpu": n,
-                                         "imad_frac": n * MAC32["verify"] / t / 1e9 / peak, "algorithmic_mac32_per_op": MAC32["verify"]}
-        del t_sig, t_pk, t_msg, t_off
+        for name, kw in (("verify_distinct_keys", {"per": 1}), ("verify_varlen_msgs", {"varlen": True})):
+            sig1, pk1, arena1, off1, expect1 = make_corpus(lib, n, "bench/%s/rank%d" % (name, rank), **kw)
+            t_sig, t_pk, t_msg, t_off = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (sig1.reshape(-1), pk1.reshape(-1), arena1, off1.view(np.int64)))
+            for _ in range(2):
+                eng.ed448_verify(d_st, t_sig, t_pk, t_msg, t_off, d_scratch)
+            torch.cuda.synchronize()
+            assert (d_st.cpu().numpy() == expect1).all(), "device verify (%s) disagrees with the expected accept bits" % name
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kx = max(2, min(K, 3))
+            barrier()
+            a.record()
+            for _ in range(kx):
+                eng.ed448_verify(d_st, t_sig, t_pk, t_msg, t_off, d_scratch)
+            b.record()
+            barrier()
+            t = max_over_ranks(a.elapsed_time(b) / 1e3 / kx)
+            extra[name] = {"value": world * n / t, "unit": UNIT, "ms_per_step": t * 1e3, "batch_per_gpu": n,
+                           "imad_frac": n * MAC32["verify"] / t / 1e9 / peak, "algorithmic_mac32_per_op": MAC32["verify"]}
+            del t_sig, t_pk, t_msg, t_off
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
     cpu = None

@@ -44,6 +44,7 @@ struct Ctx {
     std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
     size_t used = 0;             // bytes used in the active block
     void *slot_scratch = nullptr;
+    unsigned *work_counter = nullptr;   // dynamic hand-out counter of the persistent kernels (launch_smp)
     size_t slot_cap = 0;
 };
 constexpr int MAX_DEV = 64;
@@ -140,16 +141,25 @@ bool smp_grid(Ctx &c, int *grid) {
     *grid = c.sms * occ;
     return true;
 }
+// `counter`: a zeroed device word for the kernel's dynamic hand-out.  Null = the context's own word, zeroed here on `s`
+// (host-pointer calls hold the context lock until their stream has drained, so one launch uses it at a time);
+// GRID_STRIDE = no counter, fixed assignment (device-pointer calls on caller streams that bring no word of their own).
+unsigned *const GRID_STRIDE = reinterpret_cast<unsigned *>(1);
 template <class F>
-bool launch_smp(Ctx &c, const F &f, size_t n, int grid, cudaStream_t s) {
+bool launch_smp(Ctx &c, const F &f, size_t n, int grid, cudaStream_t s, unsigned *counter = nullptr) {
     if (n == 0) return true;
+    if (counter == GRID_STRIDE) counter = nullptr;
+    else if (!counter) {
+        counter = c.work_counter;
+        CU(cudaMemsetAsync(counter, 0, sizeof(unsigned), s));
+    }
     size_t need_blocks = (n + SLOT_BLOCK - 1) / SLOT_BLOCK;
     if ((size_t)grid > need_blocks) grid = (int)need_blocks;
     g_launches++;
     cudaEvent_t a = nullptr, b = nullptr;
     const bool prof = g_prof_on.load() != 0;
     if (prof) a = prof_begin(typeid(F).name(), s, &b);
-    CU(launch_sm_persist<F>(f, n, grid, s));
+    CU(launch_sm_persist<F>(f, n, grid, s, counter));
     if (prof) prof_end(typeid(F).name(), s, a, b);
     return true;
 }
@@ -169,6 +179,7 @@ bool ctx_init(Ctx &c, int dev) {
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     for (auto &e : c.copy_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaMalloc(&c.work_counter, 256));
     CU(cudaMalloc(&c.ft, sizeof(fixed_tables)));
     LaneBuildTables f = {c.ft};
     if (!launch(c, f, TABLE_LANES, c.stream)) return false;
@@ -763,12 +774,12 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
     if (split < n && (!decode_range(split, n) || !scalars_range(split, n))) return false;
     if (plan.unique_sig) {
         SlotKeyTables ft = {pts, ktabs, plan};
-        if (!launch_smp(c, ft, cap, grids.tables, s)) return false;
+        if (!launch_smp(c, ft, cap, grids.tables, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3], counts[4] = 0, left by the grouping pass */
         SlotEdVerifyFinishShared fs = {status, pts, ok, chal, resp, c.wide, ktabs, slots, plan};
-        return launch_smp(c, fs, n, grids.shared, s);
+        return launch_smp(c, fs, n, grids.shared, s, const_cast<uint32_t *>(plan.counts) + 3);
     }
     SlotEdVerifyFinish f3 = {status, pts, ok, chal, resp, c.wide, slots};
-    return launch_smp(c, f3, n, grids.unique, s);
+    return launch_smp(c, f3, n, grids.unique, s, GRID_STRIDE); /* fewer than 64 signatures: one partial round */
 }
 goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                  uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n) {

@@ -69,7 +69,7 @@ __global__ void k_lists(uint32_t *shared_sig, uint32_t *shared_tab, uint32_t *un
     else unique_sig[j - pos[j]] = is[j];
     if (j == n - 1) {
         const uint32_t ns = pos[j] + adm[j], nt = tslot[g] + sflag[g];
-        counts[0] = ns; counts[1] = n - ns; counts[2] = nt < cap ? nt : cap;
+        counts[0] = ns; counts[1] = n - ns; counts[2] = nt < cap ? nt : cap; counts[3] = 0; counts[4] = 0;
     }
 }
 struct Layout {
@@ -85,7 +85,7 @@ Layout lay(void *scratch, size_t n, size_t cap) {
     L.gstart = (uint32_t *)take(4 * (n + 1)); L.sflag = (uint32_t *)take(4 * n); L.tslot = (uint32_t *)take(4 * n);
     L.adm = (uint32_t *)take(4 * n); L.pos = (uint32_t *)take(4 * n);
     L.shared_sig = (uint32_t *)take(4 * n); L.shared_tab = (uint32_t *)take(4 * n); L.unique_sig = (uint32_t *)take(4 * n);
-    L.tab_rep = (uint32_t *)take(4 * (cap + 1)); L.counts = (uint32_t *)take(16); L.ngroups = (uint32_t *)take(4);
+    L.tab_rep = (uint32_t *)take(4 * (cap + 1)); L.counts = (uint32_t *)take(32); L.ngroups = (uint32_t *)take(4);
     size_t b1 = 0, b2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
     cub::DeviceScan::InclusiveSum(nullptr, b2, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);

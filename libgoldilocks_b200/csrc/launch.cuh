@@ -71,8 +71,8 @@ cudaError_t sm_configure(int *blocks_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_slots_persist<F>, SLOT_BLOCK, smem);
 }
 template <class F>
-cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
-    k_slots_persist<F><<<grid, SLOT_BLOCK, F::NSLOTS * 64 * SLOT_BLOCK, s>>>(f, n);
+cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s, unsigned *work_counter) {
+    k_slots_persist<F><<<grid, SLOT_BLOCK, F::NSLOTS * 64 * SLOT_BLOCK, s>>>(f, n, work_counter); /* *work_counter == 0 on entry */
     return cudaGetLastError();
 }
 
@@ -92,9 +92,9 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s) {
 #define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotEdVerifyFinishShared) X(SlotKeyTables) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul) X(SlotDualScalarmul) X(SlotDirectScalarmul)
 #define INSTANTIATE_SMP(F)                                                                          \
     template cudaError_t sm_configure<F>(int *);                                                    \
-    template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t);
+    template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t, unsigned *);
 #define DECLARE_SMP(F)                                                                              \
     extern template cudaError_t sm_configure<F>(int *);                                             \
-    extern template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t);
+    extern template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t, unsigned *);
 #define INSTANTIATE_PLAIN(F) template cudaError_t launch_lanes<F>(const F &, size_t, cudaStream_t);
 #define DECLARE_PLAIN(F) extern INSTANTIATE_PLAIN(F)

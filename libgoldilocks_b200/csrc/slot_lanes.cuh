@@ -96,19 +96,21 @@ struct SlotKeyTables {
         s_build_key_tables(sb, ktab_of(ktabs, t));
     }
 };
-// The finish kernel of a grouped batch.  Work items [0, counts[0]) are signatures whose public key (byte-identical)
-// occurs more than once: the multiples of the key come from the table its group built.  Items [counts[0],
-// counts[0] + counts[1]) are the stand-alone signatures, verified exactly like SlotEdVerifyFinish (own window table in
-// `scratch`).  One launch for both, so the stand-alone tail fills the lanes the table path leaves idle.
+// The finish kernel of a grouped batch.  Work items [0, counts[1]) are the stand-alone signatures, verified exactly like
+// SlotEdVerifyFinish (own window table in `scratch`); items [counts[1], counts[1] + counts[0]) are signatures whose
+// public key (byte-identical) occurs more than once: the multiples of the key come from the table its group built.
+// One launch for both; the expensive stand-alone items go first and the items are handed out dynamically
+// (k_slots_persist, slots.cuh), so the cheap ones fill in behind them.
 struct SlotEdVerifyFinishShared {
     static constexpr int NSLOTS = BDSM_NSLOTS;
     int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; uint4 *ktabs; uint4 *scratch;
     verify_plan plan;
     GDM void operator()(size_t j, sref sb, size_t slot) const {
-        const size_t ns = plan.counts[0];
+        const size_t nu = plan.counts[1];
         sc c, r;
-        if (j < ns) {
-            const size_t i = plan.shared_sig[j], t = plan.shared_tab[j];
+        if (j >= nu) {
+            if (j - nu >= plan.counts[0]) return;
+            const size_t i = plan.shared_sig[j - nu], t = plan.shared_tab[j - nu];
             sc_from_abi(c, challenge + i);
             sc_from_abi(r, response + i);
             s_verify_shared_key(sb, r, c, wide, ktab_of(ktabs, t));
@@ -116,8 +118,7 @@ struct SlotEdVerifyFinishShared {
             /* the key bytes are the representative's, so its decode flag is this signature's */
             s_verify_accept(status, i, sb, pts + 2 * i + 1, (gmask_t)ok[2 * (size_t)plan.tab_rep[t]] & (gmask_t)ok[2 * i + 1]);
         } else {
-            if (j - ns >= plan.counts[1]) return;
-            const size_t i = plan.unique_sig[j - ns];
+            const size_t i = plan.unique_sig[j];
             sc_from_abi(c, challenge + i);
             sc_from_abi(r, response + i);
             s_pt_from_abi(sb, pts + 2 * i);

@@ -225,15 +225,32 @@ __global__ void __launch_bounds__(SLOT_BLOCK, slot_min_blocks<F>::value) k_slots
     f(i < n ? i : n - 1, s_base_handle(), i < n);
 #endif
 }
-// Persistent grid-stride shape for functors that also own a per-thread scratch area in HBM
-// (`slot` = global thread index): f(i, base, slot).
+// Persistent shape for functors that also own a per-thread scratch area in HBM (`slot` = global thread index):
+// f(i, base, slot).  Elements are handed out 32 at a time to whichever warp asks next (one atomicAdd per warp and
+// chunk on `work_counter`, which the launcher leaves at zero): warps do not run at the same speed (4 vs 3 resident
+// blocks per SM at the edges of the grid, different table hit rates) and elements may differ in cost, so a fixed
+// grid-stride assignment left lanes idle behind slow neighbours (verify, 2^20 distinct keys: 8.13 -> 8.66 M/s).
+// A null counter falls back to the grid-stride loop.
 template <class F>
-__global__ void __launch_bounds__(SLOT_BLOCK, slot_min_blocks<F>::value) k_slots_persist(F f, size_t n) {
+__global__ void __launch_bounds__(SLOT_BLOCK, slot_min_blocks<F>::value) k_slots_persist(F f, size_t n, unsigned *work_counter) {
     const size_t slot = (size_t)blockIdx.x * SLOT_BLOCK + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * SLOT_BLOCK;
 #if defined(__CUDA_ARCH__)
     const sref base = s_base_handle();
-    for (size_t i = slot; i < n; i += stride) f(i, base, slot);
+    if (work_counter) {
+        const unsigned lane = threadIdx.x & 31u;
+        for (;;) {
+            unsigned chunk = 0;
+            if (lane == 0) chunk = atomicAdd(work_counter, 1u);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            const size_t i = (size_t)chunk * 32u + lane;
+            if ((size_t)chunk * 32u >= n) break;
+            if (i < n) f(i, base, slot);
+            __syncwarp();
+        }
+    } else {
+        for (size_t i = slot; i < n; i += stride) f(i, base, slot);
+    }
 #endif
 }
 #endif

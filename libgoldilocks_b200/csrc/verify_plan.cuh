@@ -8,7 +8,8 @@
 //                                  that signatures under one key are adjacent lanes (their table rows stay in L1/L2)
 //   unique_sig[j]                : signature index of the j-th stand-alone signature
 //   tab_rep[t]                   : a signature whose public key is key t (its decoded point seeds the table)
-//   counts[0..2]                 : number of table-path signatures, stand-alone signatures, key tables
+//   counts[0..2]                 : number of table-path signatures, stand-alone signatures, key tables;
+//                                  counts[3] = counts[4] = 0: work counters of the finish / key-table kernels' dynamic hand-out
 // A null unique_sig means "no plan: every signature, in order, stand-alone".
 struct verify_plan {
     const uint32_t *shared_sig, *shared_tab, *unique_sig, *tab_rep, *counts;

@@ -189,7 +189,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     /* the key-grouping pass of k_group.cu restated on the host: byte-identical keys that occur at least twice share a table */
     std::map<std::string, std::vector<uint32_t>> groups;
     for (size_t i = 0; i < n; i++) groups[std::string((const char *)pk + 57 * i, 57)].push_back((uint32_t)i);
-    std::vector<uint32_t> shared_sig, shared_tab, unique_sig, tab_rep, counts(3);
+    std::vector<uint32_t> shared_sig, shared_tab, unique_sig, tab_rep, counts(4);
     const size_t cap = n / 8 + 1;
     for (auto &g : groups) {
         if (g.second.size() >= 2 && tab_rep.size() < cap) {

@@ -206,8 +206,9 @@ def run_reference(args):
     emit(line)
 
 
-def config_dict(gpus, n_per_step):
-    return {"workload": "BASELINE configs[3]: Ed448 batch verify (SHAKE256 + double scalarmul), 2^16 keys x 16 messages of 32 B, 1/8 corrupted",
+def config_dict(gpus, n_per_step, per_key=16):
+    return {"workload": "BASELINE configs[3]: Ed448 batch verify (SHAKE256 + double scalarmul), 2^16 keys x 16 messages of 32 B, 1/8 corrupted"
+                        + ("" if per_key == 16 else " -- NON-DEFAULT corpus: %d signatures per key" % per_key),
             "keys": "SURVEY 8(d) C4: 2^16 distinct keys x 16 signatures each; byte-identical keys of a batch share one per-key table "
                     "(extra.verify_distinct_keys = the same batch size with 2^20 distinct keys, no sharing possible)",
             "signatures_per_gpu_per_step": n_per_step, "parallelism": "independent shards x%d, no collective" % gpus,
@@ -244,7 +245,7 @@ def run_ours(args):
         return float(t.item())
 
     # ---- inputs (host, pinned) -----------------------------------------------------------------------
-    sig, pk, arena, off, expect = make_corpus(lib, n, "bench/rank%d" % rank)
+    sig, pk, arena, off, expect = make_corpus(lib, n, "bench/rank%d" % rank, per=args.per_key)
 
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -391,7 +392,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": world * n / t_step, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_step * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (448-bit integers)", "data": "synthetic",
-                "config": config_dict(world, n), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "config": config_dict(world, n, args.per_key), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "extra": extra}
         emit(line)
     if world > 1:
@@ -417,6 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="signatures per GPU per step (default 2^20, the BASELINE size)")
+    ap.add_argument("--per-key", type=int, default=16, help="signatures per public key in the corpus (SURVEY 8(d) C4: 16); other values are for the "
+                    "sensitivity table in DESIGN.md, not the headline")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -252,7 +252,7 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *o
  *    Calls are asynchronous on that stream; `scratch` must hold goldilocks_b200_*_scratch_bytes(n).
  * ====================================================================================== */
 /* scratch of a device-resident verification: decoded points and scalars, the key-grouping work lists and room for
- * n/8 + 1 per-key tables (25 KB each); about 3.9 KB per signature */
+ * n/4 + 1 per-key tables (25 KB each); about 7 KB per signature */
 GOLDILOCKS_B200_API size_t goldilocks_b200_verify_scratch_bytes(size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off, uint8_t prehashed, const uint8_t *context /*device or NULL*/, uint8_t context_len, size_t n, void *scratch, void *stream);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream);

@@ -717,9 +717,9 @@ goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t
 }
 
 // Batches of at least VERIFY_GROUP_MIN signatures are grouped by public key on the device (k_group.cu); keys that
-// occur more than once get one shared table (at most n/8 + 1 tables per call; the rest verify stand-alone).
+// occur more than once get one shared table (at most n/4 + 1 tables per call -- every key of a batch with four or more signatures per key; the rest verify stand-alone).
 constexpr size_t VERIFY_GROUP_MIN = 64;
-static size_t verify_tab_cap(size_t n) { return n / 8 + 1; }
+static size_t verify_tab_cap(size_t n) { return n / 4 + 1; }
 static bool verify_groups(size_t n) { return n >= VERIFY_GROUP_MIN && n < ((size_t)1 << 31); } /* the work lists are 32-bit */
 size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };

@@ -190,7 +190,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     std::map<std::string, std::vector<uint32_t>> groups;
     for (size_t i = 0; i < n; i++) groups[std::string((const char *)pk + 57 * i, 57)].push_back((uint32_t)i);
     std::vector<uint32_t> shared_sig, shared_tab, unique_sig, tab_rep, counts(4);
-    const size_t cap = n / 8 + 1;
+    const size_t cap = n / 4 + 1;
     for (auto &g : groups) {
         if (g.second.size() >= 2 && tab_rep.size() < cap) {
             for (uint32_t i : g.second) { shared_sig.push_back(i); shared_tab.push_back((uint32_t)tab_rep.size()); }

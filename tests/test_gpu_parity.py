@@ -68,7 +68,7 @@ def test_eddsa_random(gpu, chk):
 
 def test_eddsa_repeated_keys(gpu, chk):
     """per-key tables (device-side key grouping): mixed multiplicities, more groups than tables (all pairs: the
-    table budget of n/8 + 1 overflows and the rest must fall back to stand-alone verification), one key for the
+    table budget of n/4 + 1 overflows and the rest must fall back to stand-alone verification), one key for the
     whole batch, and a batch just at the grouping threshold"""
     parity.check_eddsa_grouped(gpu, chk, 1 << 12)
     parity.check_eddsa_grouped(gpu, chk, 1 << 11, label="c4g/pairs", per_key=(2,))

@@ -278,7 +278,7 @@ def check_eddsa_random(lib, chk, n, label="c4"):
         eq(lib.ed448_verify(s1, pk0[idx[:m]], sub_msgs[:m], ph, ctx), np.full(m, -1, np.int32), "verify ctx/ph")
 
 
-def check_eddsa_grouped(lib, chk, n, label="c4g", per_key=(1, 2, 3, 16, 5, 1, 40)):
+def check_eddsa_grouped(lib, chk, n, label="c4g", per_key=(1, 2, 3, 16, 5, 1, 40), prehashed=False, context=b""):
     """Repeated public keys: the batch path groups byte-identical keys and verifies them against one
     per-key table; accept bits must still be the reference's, whatever the multiplicities and the order.  Keys come with
     multiplicities cycling through `per_key`, the batch is shuffled, 1/8 of the entries are corrupted (R, S, A, message,
@@ -295,7 +295,7 @@ def check_eddsa_grouped(lib, chk, n, label="c4g", per_key=(1, 2, 3, 16, 5, 1, 40
     offs = np.concatenate([[0], np.cumsum(lens)])
     msgs = [bytes(blob[offs[i]:offs[i + 1]]) for i in range(n)]
     pk = pk_k[key_of].copy()
-    sig = chk.ed448_sign(sk[key_of], pk, msgs)
+    sig = chk.ed448_sign(sk[key_of], pk, msgs, prehashed, context)
     sel = stream_bytes(label + "/sel", 2 * n)
     for i in range(0, n, 8):
         kind = 1 + (i // 8) % 5
@@ -311,9 +311,11 @@ def check_eddsa_grouped(lib, chk, n, label="c4g", per_key=(1, 2, 3, 16, 5, 1, 40
         pk[key_of == g] = enc
     perm = np.argsort(stream_bytes(label + "/perm", 4 * n).view("<u4")[:n], kind="stable")
     sig, pk, msgs = sig[perm], pk[perm], [msgs[i] for i in perm]
-    want = chk.ed448_verify(sig, pk, msgs)
-    got = lib.ed448_verify(sig, pk, msgs)
+    want = chk.ed448_verify(sig, pk, msgs, prehashed, context)
+    got = lib.ed448_verify(sig, pk, msgs, prehashed, context)
     eq(got, want, "ed448_verify status with repeated public keys")
+    if context or prehashed:   # the context and the prehash flag are part of the challenge: without them nothing verifies
+        assert (lib.ed448_verify(sig, pk, msgs) == 0).all()
     assert (want == -1).sum() > n // 2 and (want == 0).sum() >= n // 16
     return want
 

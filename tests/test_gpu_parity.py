@@ -74,6 +74,8 @@ def test_eddsa_repeated_keys(gpu, chk):
     parity.check_eddsa_grouped(gpu, chk, 1 << 11, label="c4g/pairs", per_key=(2,))
     parity.check_eddsa_grouped(gpu, chk, 1 << 10, label="c4g/one", per_key=(3, 1 << 10))
     parity.check_eddsa_grouped(gpu, chk, 64, label="c4g/min", per_key=(4, 1, 9))
+    parity.check_eddsa_grouped(gpu, chk, 512, label="c4g/ctx", prehashed=True, context=b"\x01" * 255)
+    parity.check_eddsa_grouped(gpu, chk, 300, label="c4g/ctx2", context=b"repeated keys")
 
 
 def test_decaf_vectors(gpu, vectors):

@@ -11,8 +11,18 @@ sk = stream_bytes("san/sk", n * 57).reshape(n, 57)
 msgs = [bytes(stream_bytes("san/m%d" % i, i % 40)) for i in range(n)]
 pk = lib.ed448_derive_public_key(sk)
 sig = lib.ed448_sign(sk, pk, msgs)
-st = lib.ed448_verify(sig, pk, msgs)
+st = lib.ed448_verify(sig, pk, msgs)       # 200 distinct keys: grouping pass, every signature stand-alone
 assert (st == -1).all()
+rep = np.arange(n) % 7                     # 7 keys, ~28 signatures each: key tables + table-path finish, dynamic hand-out
+pk2 = pk[rep]; sig2 = lib.ed448_sign(sk[rep], pk2, msgs)
+sig2[::9, 3] ^= 1
+st = lib.ed448_verify(sig2, pk2, msgs)
+assert (st[np.arange(n) % 9 != 0] == -1).all() and (st[::9] == 0).all()
+a56 = stream_bytes("san/a", 300 * 56).reshape(300, 56); b56 = stream_bytes("san/b", 300 * 56).reshape(300, 56)
+lib.gf_mul(a56, b56); lib.gf_sqr(a56)      # staged field kernels: two full blocks (TMA bulk + mbarrier) and a ragged tail
+pp = lib.from_hash_uniform(stream_bytes("san/h", 300 * 112).reshape(300, 112))
+lib.point_add(pp, pp[::-1].copy()); lib.point_double(pp)   # staged point kernels
+rec, ok = lib.invert_elligator_nonuniform(pp, (np.arange(300) % 8).astype(np.uint32))
 u = stream_bytes("san/u", n * 56).reshape(n, 56); k = stream_bytes("san/k", n * 56).reshape(n, 56)
 o, s = lib.x448(u, k)
 sc = lib.scalar_decode_long(k, 56)

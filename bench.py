@@ -383,6 +383,35 @@ def run_ours(args):
                            "imad_frac": n * MAC32["verify"] / t / 1e9 / peak, "algorithmic_mac32_per_op": MAC32["verify"]}
             del t_sig, t_pk, t_msg, t_off
 
+    # ---- extra: the same corpus against a KEY SET (tables of the 2^16 keys built once, outside the timed region), host pointers ----
+    if not args.no_extra and args.per_key == 16:
+        nk = n // 16
+        keys = np.ascontiguousarray(pk.reshape(n, 57)[::16]).copy()
+        idx8 = np.arange(0, n, 8)
+        flipped = idx8[(np.arange(len(idx8)) % 4) == 2]          # make_corpus kind 3: the key bytes of these entries were changed
+        keys[flipped[flipped % 16 == 0] // 16] = np.ascontiguousarray(pk.reshape(n, 57))[flipped[flipped % 16 == 0] + 1]
+        expect_ks = expect.copy(); expect_ks[flipped] = -1        # under the key SET they verify against the intact key
+        handle = lib.keyset_create(keys)
+        h_idx = pinned((np.arange(n, dtype=np.uint32) // 16).astype(np.uint32))
+        fk = lib.lib.goldilocks_ed448_verify_keyset_batch
+        fk.restype = C.c_int32
+        argk = [C.c_void_p(h_st.data_ptr()), handle, C.c_void_p(h_idx.data_ptr()), C.c_void_p(h_sig.data_ptr()), C.c_void_p(h_msg.data_ptr()),
+                C.c_void_p(h_off.data_ptr()), C.c_uint8(0), None, C.c_uint8(0), C.c_size_t(n)]
+        for _ in range(2):
+            assert fk(*argk) == -1
+        assert (h_st.numpy() == expect_ks).all(), "key-set verify disagrees with the expected accept bits"
+        kx = max(2, min(K, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(kx):
+            assert fk(*argk) == -1
+        torch.cuda.synchronize()
+        t = max_over_ranks((time.perf_counter() - t0) / kx)
+        barrier()
+        lib.keyset_destroy(handle)
+        extra["verify_keyset_e2e"] = {"value": world * n / t, "unit": UNIT, "ms_per_step": t * 1e3, "batch_per_gpu": n, "keys_in_set": int(nk),
+                                      "api": "goldilocks_ed448_verify_keyset_batch (host pointers, pinned; tables of the key set built once, not timed)"}
+
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -243,6 +243,17 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *sign
  * grouped by public key on the device: signatures whose 57 key bytes are identical share one decode of the key and one
  * table of its multiples, which only changes the cost, never the accept bit. */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature /*n*114*/, const uint8_t *pubkey /*n*57*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n);
+/* Key sets (our extension; SURVEY 8(f)4, "precomputed per-public-key tables for repeated verification under the same key").
+ * goldilocks_ed448_verify_batch already shares one table among the byte-identical keys of ONE batch; a key set keeps the
+ * tables of m public keys in HBM (25 KB per key) ACROSS calls, so a verifier that sees the same signers again pays neither
+ * the key decode nor the table build again.  status[i] is what goldilocks_ed448_verify(signature i, pubkeys[key_index[i]],
+ * message i, ...) returns; an undecodable key is accepted into the set and rejects its signatures, like the reference;
+ * key_index[i] >= m yields FAILURE for element i.  The handle belongs to the CUDA device that was current at creation. */
+typedef struct goldilocks_b200_keyset_s goldilocks_b200_keyset;
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_keyset_create(goldilocks_b200_keyset **keyset, const uint8_t *pubkeys /*m*57*/, size_t m);
+GOLDILOCKS_B200_API void goldilocks_b200_keyset_destroy(goldilocks_b200_keyset *keyset);
+GOLDILOCKS_B200_API size_t goldilocks_b200_keyset_size(const goldilocks_b200_keyset *keyset);
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_keyset_batch(goldilocks_error_t *status, const goldilocks_b200_keyset *keyset, const uint32_t *key_index /*n*/, const uint8_t *signature /*n*114*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n);
 /* SHAKE256 one-shot over n inputs, each squeezed to outlen bytes (shake.c:177-190, SHAKE256 params 211-213) */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out /*n*outlen*/, size_t outlen, const uint8_t *in, const size_t *in_off /*n+1*/, size_t n);
 

@@ -307,6 +307,27 @@ class BatchLib:
         self._call("goldilocks_ed448_sign_batch", sig, sk, pk, arena, off, C.c_uint8(1 if prehashed else 0), ctx, C.c_uint8(ctx_len), _Z(len(sk)))
         return sig
 
+    # ---- key sets: per-key verification tables kept on the device across calls ----
+    def keyset_create(self, pk):
+        """handle for m public keys ((m,57) u8); free it with keyset_destroy"""
+        pk = _u8(pk, 57)
+        h = C.c_void_p()
+        self._call("goldilocks_b200_keyset_create", C.byref(h), pk, _Z(len(pk)))
+        return h
+
+    def keyset_destroy(self, handle):
+        self.lib.goldilocks_b200_keyset_destroy.restype = None
+        self.lib.goldilocks_b200_keyset_destroy(handle)
+
+    def ed448_verify_keyset(self, handle, key_index, sig, msgs, prehashed=False, context=b""):
+        """status int32[n] of signature i under key key_index[i] of the set"""
+        sig = _u8(sig, 114); key_index = np.ascontiguousarray(key_index, np.uint32)
+        arena, off = pack_messages(msgs) if isinstance(msgs, list) else msgs
+        ctx, ctx_len = self._ctx(context)
+        st = np.zeros(len(sig), np.int32)
+        self._call("goldilocks_ed448_verify_keyset_batch", st, handle, key_index, sig, arena, off, C.c_uint8(1 if prehashed else 0), ctx, C.c_uint8(ctx_len), _Z(len(sig)))
+        return st
+
     def ed448_verify(self, sig, pk, msgs, prehashed=False, context=b""):
         sig, pk = _u8(sig, 114), _u8(pk, 57)
         arena, off = pack_messages(msgs) if isinstance(msgs, list) else msgs

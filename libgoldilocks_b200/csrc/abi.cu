@@ -815,6 +815,75 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
     return k.finish();
 }
 
+// ---- key sets: per-key verification tables that outlive a call ---------------------------------------
+struct goldilocks_b200_keyset_s {
+    int dev; size_t m;
+    uint8_t *pk;      /* m x 57 key bytes (the challenge hashes them) */
+    int32_t *key_ok;  /* decode status per key */
+    uint4 *ktabs;     /* m tables of KTAB_QUADS quads */
+};
+goldilocks_error_t goldilocks_b200_keyset_create(goldilocks_b200_keyset **out, const uint8_t *pubkeys, size_t m) {
+    if (!out) return GOLDILOCKS_FAILURE;
+    *out = nullptr;
+    Call k;
+    if (!k.ok) return k.finish();
+    goldilocks_b200_keyset_s *ks = new goldilocks_b200_keyset_s{k.c->dev, m, nullptr, nullptr, nullptr};
+    const size_t mm = m ? m : 1;
+    bool ok = cudaMalloc(&ks->pk, 57 * mm) == cudaSuccess && cudaMalloc(&ks->key_ok, sizeof(int32_t) * mm) == cudaSuccess &&
+              cudaMalloc(&ks->ktabs, mm * KTAB_QUADS * sizeof(uint4)) == cudaSuccess;
+    if (ok && m) {
+        ok = cudaMemcpyAsync(ks->pk, pubkeys, 57 * m, cudaMemcpyHostToDevice, k.c->stream) == cudaSuccess;
+        abi_pt *pts = k.out<abi_pt>(m);
+        LaneDecodeEddsa fd = {pts, ks->key_ok, ks->pk};
+        k.run(fd, m);
+        int grid = k.smp_grid_for<SlotKeysetTables>();
+        SlotKeysetTables ft = {pts, ks->ktabs};
+        k.run_smp(ft, m, grid);
+    }
+    goldilocks_error_t r = k.finish();
+    if (!ok || r != GOLDILOCKS_SUCCESS) {
+        if (!ok) g_err = "goldilocks_b200_keyset_create: device allocation or copy failed";
+        cudaFree(ks->pk); cudaFree(ks->key_ok); cudaFree(ks->ktabs);
+        delete ks;
+        return GOLDILOCKS_FAILURE;
+    }
+    *out = ks;
+    return GOLDILOCKS_SUCCESS;
+}
+void goldilocks_b200_keyset_destroy(goldilocks_b200_keyset *ks) {
+    if (!ks) return;
+    int cur = 0;
+    const bool sw = cudaGetDevice(&cur) == cudaSuccess && cur != ks->dev && cudaSetDevice(ks->dev) == cudaSuccess;
+    cudaFree(ks->pk); cudaFree(ks->key_ok); cudaFree(ks->ktabs);
+    if (sw) cudaSetDevice(cur);
+    delete ks;
+}
+size_t goldilocks_b200_keyset_size(const goldilocks_b200_keyset *ks) { return ks ? ks->m : 0; }
+goldilocks_error_t goldilocks_ed448_verify_keyset_batch(goldilocks_error_t *status, const goldilocks_b200_keyset *ks, const uint32_t *key_index,
+                                                        const uint8_t *signature, const uint8_t *msg, const size_t *msg_off, uint8_t prehashed,
+                                                        const uint8_t *context, uint8_t context_len, size_t n) {
+    Call k;
+    if (!k.ok) return k.finish();
+    if (!ks || ks->dev != k.c->dev) { g_err = "goldilocks_ed448_verify_keyset_batch: the key set lives on another device"; return GOLDILOCKS_FAILURE; }
+    const size_t total = n ? msg_off[n] : 0;
+    const size_t *doff = k.in(msg_off, n + 1);
+    const uint8_t *dctx = k.in(context, context_len);
+    const uint32_t *dki = k.in(key_index, n);
+    const uint8_t *dsig = k.in(signature, 114 * n), *dmsg = k.in(msg, total);
+    int32_t *dst = k.out<int32_t>(n), *rok = k.out<int32_t>(n);
+    abi_pt *rpts = k.out<abi_pt>(n);
+    abi_sc *chal = k.out<abi_sc>(n), *resp = k.out<abi_sc>(n);
+    LaneKeysetDecodeR f1 = {rpts, rok, dsig};
+    k.run(f1, n);
+    LaneEdVerifyScalars f2 = {chal, resp, dsig, ks->pk, dmsg, doff, prehashed, dctx, context_len, 0, dki, (uint32_t)ks->m};
+    k.run(f2, n);
+    int grid = k.smp_grid_for<SlotEdVerifyFinishKeyset>();
+    SlotEdVerifyFinishKeyset f3 = {dst, rpts, rok, ks->key_ok, chal, resp, k.ok ? k.c->wide : nullptr, ks->ktabs, dki, (uint32_t)ks->m};
+    k.run_smp(f3, n, grid);
+    k.fetch((int32_t *)status, dst, n);
+    return k.finish();
+}
+
 // ---- device-resident variants -------------------------------------------------------------------------------
 goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                      uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, void *scratch, void *stream) {

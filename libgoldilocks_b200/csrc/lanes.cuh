@@ -536,16 +536,36 @@ struct LaneEdVerifyDecode {
 };
 struct LaneEdVerifyScalars {
     abi_sc *challenge, *response; const uint8_t *sig, *pk, *msg; const size_t *off; uint32_t prehashed; const uint8_t *ctx; uint32_t ctx_len; size_t i0;
+    const uint32_t *key_index; uint32_t n_keys; /* key set calls: the key of signature i is pk[key_index[i]] (out of range: key 0, rejected later) */
     GDM void operator()(size_t k) const {
         const size_t i = k + i0;
+        size_t ki = i;
+        if (key_index) { ki = key_index[i]; if (ki >= n_keys) ki = 0; }
         sc c, nc, r;
-        ed448_challenge(c, sig + 114 * i, pk + 57 * i, msg, off[i], off[i + 1], prehashed, ctx, ctx_len);
+        ed448_challenge(c, sig + 114 * i, pk + 57 * ki, msg, off[i], off[i + 1], prehashed, ctx, ctx_len);
         sc_neg(nc, c);
         ByteAtPtr at = {sig + 114 * i + 57};
         sc_decode_long(r, at, 57);   /* reduces mod q, no range check (eddsa.c:287-291) */
         /* GOLDILOCKS_448_EDDSA_DECODE_RATIO = 1: no doubling of the response */
         sc_to_abi(challenge + i, nc);
         sc_to_abi(response + i, r);
+    }
+};
+struct LaneKeysetDecodeR { /* key set calls: R of signature i -> pts[i], ok[i] (weakly reduced limbs, like LaneEdVerifyDecode) */
+    abi_pt *pts; int32_t *ok; const uint8_t *sig;
+    GDM void operator()(size_t i) const {
+        pt p; uint32_t w[15];
+        words_load_bytes(w, 15, sig + 114 * i, 57);
+        gmask_t good = pt_decode_like_eddsa(p, w, w[14] & 0xff);
+        abi_pt *o = pts + i;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            o->x.limb[k] = (uint64_t)p.x.v[2 * k] + ((uint64_t)p.x.v[2 * k + 1] << 28);
+            o->y.limb[k] = (uint64_t)p.y.v[2 * k] + ((uint64_t)p.y.v[2 * k + 1] << 28);
+            o->z.limb[k] = (uint64_t)p.z.v[2 * k] + ((uint64_t)p.z.v[2 * k + 1] << 28);
+            o->t.limb[k] = (uint64_t)p.t.v[2 * k] + ((uint64_t)p.t.v[2 * k + 1] << 28);
+        }
+        ok[i] = ST_OK(good);
     }
 };
 struct LaneBuildWide { /* verification table, WIDE_LANES lanes */

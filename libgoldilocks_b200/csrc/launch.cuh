@@ -41,6 +41,8 @@ template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int va
 template <> struct slot_min_blocks<SlotBaseDoubleScalarmul> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotEdVerifyFinishShared> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotKeyTables> { static constexpr int value = 4; };
+template <> struct slot_min_blocks<SlotKeysetTables> { static constexpr int value = 4; };
+template <> struct slot_min_blocks<SlotEdVerifyFinishKeyset> { static constexpr int value = 4; };
 template <class F>
 cudaError_t launch_sm(const F &f, size_t n, cudaStream_t s) {
     const int smem = F::NSLOTS * 64 * SLOT_BLOCK;
@@ -84,12 +86,12 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s, un
     X(LaneSc<SCOP_ADD>) X(LaneSc<SCOP_SUB>) X(LaneSc<SCOP_MUL>) X(LaneSc<SCOP_HALVE>)               \
     X(LaneScDecodeLong) X(LaneScInvert) X(LaneShake256) X(LaneSpongeUpdate) X(LaneSpongeOutput) X(LaneEdPkToX448) X(LaneEdSkToX448) X(LanePrecompute) X(LaneNielsFromAbi)                                                             \
     X(LaneEdSecretScalar) X(LaneEdSignExpand) X(LaneEdSignNonce) X(LaneEdSignFinish)   \
-    X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneBuildTables) X(LaneBuildWide)
+    X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneKeysetDecodeR) X(LaneBuildTables) X(LaneBuildWide)
 
 #define LANES_SM(X) X(SlotX448) X(SlotComb) X(SlotCombTable) X(SlotX448DerivePk) X(SlotEdDerivePk) X(SlotEdSignR)
 #define INSTANTIATE_SM(F) template cudaError_t launch_sm<F>(const F &, size_t, cudaStream_t);
 #define DECLARE_SM(F) extern INSTANTIATE_SM(F)
-#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotEdVerifyFinishShared) X(SlotKeyTables) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul) X(SlotDualScalarmul) X(SlotDirectScalarmul)
+#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotEdVerifyFinishShared) X(SlotKeyTables) X(SlotKeysetTables) X(SlotEdVerifyFinishKeyset) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul) X(SlotDualScalarmul) X(SlotDirectScalarmul)
 #define INSTANTIATE_SMP(F)                                                                          \
     template cudaError_t sm_configure<F>(int *);                                                    \
     template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t, unsigned *);

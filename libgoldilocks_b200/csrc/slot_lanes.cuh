@@ -129,6 +129,34 @@ struct SlotEdVerifyFinishShared {
     }
 };
 
+// Key sets (include/goldilocks_b200.h, goldilocks_b200_keyset_*): the same per-key tables, built once by
+// goldilocks_b200_keyset_create and kept in HBM across calls.
+struct SlotKeysetTables { /* one lane per key: decoded key t -> table t */
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    const abi_pt *pts; uint4 *ktabs;
+    GDM void operator()(size_t t, sref sb, size_t slot) const {
+        (void)slot;
+        s_pt_from_abi(sb, pts + t);
+        s_build_key_tables(sb, ktab_of(ktabs, t));
+    }
+};
+struct SlotEdVerifyFinishKeyset { /* signature i under key key_index[i] of the set */
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    int32_t *status; const abi_pt *r_pts; const int32_t *r_ok, *key_ok; const abi_sc *challenge, *response; const niels *wide; const uint4 *ktabs;
+    const uint32_t *key_index; uint32_t n_keys;
+    GDM void operator()(size_t i, sref sb, size_t slot) const {
+        (void)slot;
+        const uint32_t t = key_index[i];
+        if (t >= n_keys) { status[i] = 0; return; } /* no such key: FAILURE */
+        sc c, r;
+        sc_from_abi(c, challenge + i);
+        sc_from_abi(r, response + i);
+        s_verify_shared_key(sb, r, c, wide, ktab_of(const_cast<uint4 *>(ktabs), t));
+        s_bdsm_quirk(sb, c);
+        s_verify_accept(status, i, sb, r_pts + i, (gmask_t)key_ok[t] & (gmask_t)r_ok[i]);
+    }
+};
+
 GD void s_pt_to_abi(abi_pt *o, sref sb) { /* slots 0..3 -> canonical host limbs */
     gf v;
     s_ld(v, s_slot(sb, 0)); gf_to_abi(&o->x, v);

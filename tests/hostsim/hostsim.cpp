@@ -179,6 +179,33 @@ EXPORT int32_t goldilocks_ed448_sign_batch(uint8_t *sig, const uint8_t *sk, cons
     run(f3, n);
     return -1;
 }
+// key sets (include/goldilocks_b200.h): same functors, host memory
+struct hostsim_keyset { size_t m; std::vector<uint8_t> pk; std::vector<int32_t> key_ok; std::vector<uint4> ktabs; };
+EXPORT int32_t goldilocks_b200_keyset_create(hostsim_keyset **out, const uint8_t *pubkeys, size_t m) {
+    hostsim_keyset *ks = new hostsim_keyset{m, std::vector<uint8_t>(pubkeys, pubkeys + 57 * m), std::vector<int32_t>(m + 1), std::vector<uint4>((m + 1) * KTAB_QUADS)};
+    std::vector<abi_pt> pts(m + 1);
+    LaneDecodeEddsa fd = {pts.data(), ks->key_ok.data(), ks->pk.data()};
+    run(fd, m);
+    SlotKeysetTables ft = {pts.data(), ks->ktabs.data()};
+    run_smp(ft, m);
+    *out = ks;
+    return -1;
+}
+EXPORT void goldilocks_b200_keyset_destroy(hostsim_keyset *ks) { delete ks; }
+EXPORT size_t goldilocks_b200_keyset_size(const hostsim_keyset *ks) { return ks ? ks->m : 0; }
+EXPORT int32_t goldilocks_ed448_verify_keyset_batch(int32_t *st, const hostsim_keyset *ks, const uint32_t *key_index, const uint8_t *sig, const uint8_t *msg,
+                                                    const size_t *off, uint8_t prehashed, const uint8_t *ctx, uint8_t ctx_len, size_t n) {
+    std::vector<abi_pt> rpts(n + 1);
+    std::vector<int32_t> rok(n + 1);
+    std::vector<abi_sc> chal(n + 1), resp(n + 1);
+    LaneKeysetDecodeR f1 = {rpts.data(), rok.data(), sig};
+    run(f1, n);
+    LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, ks->pk.data(), msg, off, prehashed, ctx, ctx_len, 0, key_index, (uint32_t)ks->m};
+    run(f2, n);
+    SlotEdVerifyFinishKeyset f3 = {st, rpts.data(), rok.data(), ks->key_ok.data(), chal.data(), resp.data(), wide_table(), ks->ktabs.data(), key_index, (uint32_t)ks->m};
+    run_smp(f3, n);
+    return -1;
+}
 EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off,
                                              uint8_t prehashed, const uint8_t *ctx, uint8_t ctx_len, size_t n) {
     std::vector<abi_pt> pts(2 * n);

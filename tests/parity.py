@@ -320,6 +320,46 @@ def check_eddsa_grouped(lib, chk, n, label="c4g", per_key=(1, 2, 3, 16, 5, 1, 40
     return want
 
 
+def check_eddsa_keyset(lib, chk, n, nkeys=11, label="c4k"):
+    """Key sets (goldilocks_b200_keyset_*): tables of `nkeys` public keys built once, then several batches verified against
+    them; status must equal the reference's per-signature verify with pubkeys[key_index[i]], including undecodable keys in
+    the set (y = 1, y >= p), corrupted signatures / messages, S + q, and out-of-range key indices (FAILURE)."""
+    sk = stream_bytes(label + "/sk", nkeys * 57).reshape(nkeys, 57)
+    keys = chk.ed448_derive_public_key(sk)
+    keys[3] = le(1, 57)
+    if nkeys > 7:
+        keys[7] = le(P + 2, 57)
+    h = lib.keyset_create(keys)
+    try:
+        for rnd, (ph, ctx) in enumerate(((False, b""), (True, b"keyset ctx"), (False, b"\x02" * 255))):
+            kidx = (stream_bytes(label + "/kidx%d" % rnd, n).astype(np.uint32) * 7 + np.arange(n, dtype=np.uint32)) % nkeys
+            lens = stream_bytes(label + "/len%d" % rnd, n).astype(np.int64) % 90
+            blob = stream_bytes(label + "/msg%d" % rnd, int(lens.sum()) + 1)
+            offs = np.concatenate([[0], np.cumsum(lens)])
+            msgs = [bytes(blob[offs[i]:offs[i + 1]]) for i in range(n)]
+            good_pk = chk.ed448_derive_public_key(sk)
+            sig = chk.ed448_sign(sk[kidx], good_pk[kidx], msgs, ph, ctx)
+            sel = stream_bytes(label + "/sel%d" % rnd, 2 * n)
+            for i in range(0, n, 6):
+                kind = (i // 6) % 4
+                if kind == 0: sig[i, int(sel[2 * i]) % 57] ^= 1 << (sel[2 * i + 1] & 7)
+                elif kind == 1: sig[i, 57 + int(sel[2 * i]) % 56] ^= 1 << (sel[2 * i + 1] & 7)
+                elif kind == 2:
+                    m = bytearray(msgs[i]) or bytearray(b"\0"); m[0] ^= 0x40; msgs[i] = bytes(m)
+                else: sig[i, 57:114] = le(util.from_le(sig[i, 57:114]) + util.Q, 57)
+            want = chk.ed448_verify(sig, keys[kidx], msgs, ph, ctx)
+            got = lib.ed448_verify_keyset(h, kidx, sig, msgs, ph, ctx)
+            eq(got, want, "ed448_verify_keyset status (round %d)" % rnd)
+            assert (want == -1).sum() > n // 3 and (want == 0).sum() > n // 8
+            bad = kidx.copy(); bad[::5] = nkeys + (np.arange(len(bad[::5])) % 3).astype(np.uint32) * 1000
+            got = lib.ed448_verify_keyset(h, bad, sig, msgs, ph, ctx)
+            assert (got[::5] == 0).all(), "out-of-range key index must fail"
+            keep = np.ones(n, bool); keep[::5] = False
+            eq(got[keep], want[keep], "ed448_verify_keyset status next to bad indices")
+    finally:
+        lib.keyset_destroy(h)
+
+
 def check_shake(lib, n=40):
     msgs = [bytes(stream_bytes("shake/%d" % i, i * 7)) for i in range(n)] + [b"", b"a" * 135, b"b" * 136, b"c" * 137, b"d" * 272]
     for outlen in (32, 57, 114, 136, 137, 300):

@@ -78,6 +78,13 @@ def test_eddsa_repeated_keys(gpu, chk):
     parity.check_eddsa_grouped(gpu, chk, 300, label="c4g/ctx2", context=b"repeated keys")
 
 
+def test_eddsa_keyset(gpu, chk):
+    """per-key tables that outlive a call (goldilocks_b200_keyset_*)"""
+    parity.check_eddsa_keyset(gpu, chk, 1 << 12)
+    parity.check_eddsa_keyset(gpu, chk, 700, nkeys=300, label="c4k/many")
+    parity.check_eddsa_keyset(gpu, chk, 40, nkeys=5, label="c4k/few")
+
+
 def test_decaf_vectors(gpu, vectors):
     parity.check_decaf_vectors(gpu, vectors)
 

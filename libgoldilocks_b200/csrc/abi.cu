@@ -292,6 +292,7 @@ inline const abi_sc *S(const hsc *p) { return (const abi_sc *)p; }
 inline abi_sc *S(hsc *p) { return (abi_sc *)p; }
 static_assert(sizeof(hpt) == sizeof(abi_pt) && sizeof(hsc) == sizeof(abi_sc), "ABI layout");
 static_assert(sizeof(niels) == 192 && sizeof(pniels) == 256, "table layout");
+static_assert(sizeof(verify_aux) == sizeof(abi_pt), "the aux record of a signature lives in the R half of its point pair");
 
 cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 // Device-pointer entry points only need the tables; they never touch the arena or the lock while
@@ -754,10 +755,12 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
         if (e != cudaSuccess) return fail("group_keys", e);
         g_launches += launched;
     }
-    /* R of signatures [lo, hi) -- and, without a plan, their public keys (interleaved lanes) */
+    /* without a plan: R and public key of signatures [lo, hi) (interleaved lanes).  With a plan nothing decodes R: the
+     * finish kernel works from its bytes (s_verify_accept_fast). */
     auto decode_range = [&](size_t lo, size_t hi) {
-        LaneEdVerifyDecode f = {pts, ok, sig, pk, n, plan, plan.unique_sig ? lo : 2 * lo};
-        return launch(c, f, plan.unique_sig ? hi - lo : 2 * (hi - lo), s);
+        if (plan.unique_sig) return true;
+        LaneEdVerifyDecode f = {pts, ok, sig, pk, n, plan, 2 * lo};
+        return launch(c, f, 2 * (hi - lo), s);
     };
     auto scalars_range = [&](size_t lo, size_t hi) {
         LaneEdVerifyScalars f = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len, lo};
@@ -775,8 +778,10 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
     if (plan.unique_sig) {
         SlotKeyTables ft = {pts, ktabs, plan};
         if (!launch_smp(c, ft, cap, grids.tables, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3], counts[4] = 0, left by the grouping pass */
-        SlotEdVerifyFinishShared fs = {status, pts, ok, chal, resp, c.wide, ktabs, slots, plan};
-        return launch_smp(c, fs, n, grids.shared, s, const_cast<uint32_t *>(plan.counts) + 3);
+        SlotEdVerifyFinishShared fs = {pts, ok, chal, resp, c.wide, ktabs, slots, plan, sig};
+        if (!launch_smp(c, fs, n, grids.shared, s, const_cast<uint32_t *>(plan.counts) + 3)) return false;
+        LaneVerifySign fv = {status, (verify_aux *)(pts + 1), 2, n};    /* aux record of signature i = the R half of pts[2i..2i+1] */
+        return launch(c, fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH, s);
     }
     SlotEdVerifyFinish f3 = {status, pts, ok, chal, resp, c.wide, slots};
     return launch_smp(c, f3, n, grids.unique, s, GRID_STRIDE); /* fewer than 64 signatures: one partial round */
@@ -870,16 +875,16 @@ goldilocks_error_t goldilocks_ed448_verify_keyset_batch(goldilocks_error_t *stat
     const uint8_t *dctx = k.in(context, context_len);
     const uint32_t *dki = k.in(key_index, n);
     const uint8_t *dsig = k.in(signature, 114 * n), *dmsg = k.in(msg, total);
-    int32_t *dst = k.out<int32_t>(n), *rok = k.out<int32_t>(n);
-    abi_pt *rpts = k.out<abi_pt>(n);
+    int32_t *dst = k.out<int32_t>(n);
     abi_sc *chal = k.out<abi_sc>(n), *resp = k.out<abi_sc>(n);
-    LaneKeysetDecodeR f1 = {rpts, rok, dsig};
-    k.run(f1, n);
     LaneEdVerifyScalars f2 = {chal, resp, dsig, ks->pk, dmsg, doff, prehashed, dctx, context_len, 0, dki, (uint32_t)ks->m};
     k.run(f2, n);
     int grid = k.smp_grid_for<SlotEdVerifyFinishKeyset>();
-    SlotEdVerifyFinishKeyset f3 = {dst, rpts, rok, ks->key_ok, chal, resp, k.ok ? k.c->wide : nullptr, ks->ktabs, dki, (uint32_t)ks->m};
+    verify_aux *aux = k.out<verify_aux>(n);
+    SlotEdVerifyFinishKeyset f3 = {aux, ks->key_ok, chal, resp, k.ok ? k.c->wide : nullptr, ks->ktabs, dki, (uint32_t)ks->m, dsig};
     k.run_smp(f3, n, grid);
+    LaneVerifySign fv = {dst, aux, 1, n};
+    k.run(fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH);
     k.fetch((int32_t *)status, dst, n);
     return k.finish();
 }

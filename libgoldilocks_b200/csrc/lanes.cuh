@@ -501,16 +501,16 @@ struct LaneEdSignFinish {
 //      (SlotEdVerifyFinish, slot_lanes.cuh)
 struct LaneEdVerifyDecode {
     /* Without a plan: lane 2i = public key i, lane 2i+1 = R of signature i.  With the plan of a grouped batch
-     * (verify_plan.cuh) a public key is decoded once per key: lanes [0, n) = R of every signature, then the keys of
-     * the stand-alone signatures, then one representative per key table; the remaining lanes retire at once.
-     * Either way the result lands in pts[2i] (key of signature i) / pts[2i+1] (its R). */
+     * (verify_plan.cuh) only public keys are decoded, once per key, by the lanes from n on: the keys of the stand-alone
+     * signatures, then one representative per key table; the remaining lanes retire at once (R is not decoded at all on
+     * that path, slot_lanes.cuh s_verify_accept_fast).  The result lands in pts[2i] (key of signature i) / pts[2i+1] (its R). */
     abi_pt *pts; int32_t *ok; const uint8_t *sig, *pk; size_t n; verify_plan plan; size_t lane0; /* first lane of this launch */
     GDM void operator()(size_t j0) const {
         const size_t j = j0 + lane0;
         size_t i = j >> 1, which = j & 1;
         if (plan.unique_sig) {
-            if (j < n) { i = j; which = 1; }
-            else {
+            if (j < n) return;
+            {
                 const size_t k = j - n, nu = plan.counts[1];
                 if (k < nu) i = plan.unique_sig[k];
                 else if (k - nu < plan.counts[2]) i = plan.tab_rep[k - nu];
@@ -551,21 +551,42 @@ struct LaneEdVerifyScalars {
         sc_to_abi(response + i, r);
     }
 };
-struct LaneKeysetDecodeR { /* key set calls: R of signature i -> pts[i], ok[i] (weakly reduced limbs, like LaneEdVerifyDecode) */
-    abi_pt *pts; int32_t *ok; const uint8_t *sig;
-    GDM void operator()(size_t i) const {
-        pt p; uint32_t w[15];
-        words_load_bytes(w, 15, sig + 114 * i, 57);
-        gmask_t good = pt_decode_like_eddsa(p, w, w[14] & 0xff);
-        abi_pt *o = pts + i;
+// What the finish kernels leave per signature for the last step (slot_lanes.cuh s_verify_accept_prep): G D, H and flags.
+// 256 bytes, so that the grouped path can keep it in the unused R half of its point array.
+#define VAUX_FAST 1u  /* every other condition holds: accept iff lobit(H / (G D)) == sign bit */
+#define VAUX_SLOW 2u  /* degenerate case already decided: accept */
+#define VAUX_LOW  4u  /* the sign bit of the encoding */
+struct verify_aux { abi_gf gd, h, prefix; uint32_t flags; uint32_t pad[15]; };
+// Sign check of the square-root-free R comparison, VSIGN_BATCH signatures per lane and inversion (Montgomery's trick:
+// prefix products out, one inversion, back-substitution).  aux record of signature i = aux[i * stride].
+#define VSIGN_BATCH 16
+struct LaneVerifySign {
+    int32_t *status; verify_aux *aux; size_t stride, n;
+    GDM void operator()(size_t l) const {
+        const size_t lo = l * VSIGN_BATCH, hi = lo + VSIGN_BATCH < n ? lo + VSIGN_BATCH : n;
+        gf acc, v, t;
+        gf_set_ui(acc, 1);
+        for (size_t i = lo; i < hi; i++) {
+            verify_aux *a = aux + i * stride;
+            gf_from_abi(v, &a->gd);
+            gf_mul(acc, acc, v);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            o->x.limb[k] = (uint64_t)p.x.v[2 * k] + ((uint64_t)p.x.v[2 * k + 1] << 28);
-            o->y.limb[k] = (uint64_t)p.y.v[2 * k] + ((uint64_t)p.y.v[2 * k + 1] << 28);
-            o->z.limb[k] = (uint64_t)p.z.v[2 * k] + ((uint64_t)p.z.v[2 * k + 1] << 28);
-            o->t.limb[k] = (uint64_t)p.t.v[2 * k] + ((uint64_t)p.t.v[2 * k + 1] << 28);
+            for (int k = 0; k < 8; k++) a->prefix.limb[k] = (uint64_t)acc.v[2 * k] + ((uint64_t)acc.v[2 * k + 1] << 28);
         }
-        ok[i] = ST_OK(good);
+        gf inv;
+        gf_invert(inv, acc);
+        for (size_t i = hi; i-- > lo;) {
+            verify_aux *a = aux + i * stride;
+            if (i > lo) { gf_from_abi(t, &aux[(i - 1) * stride].prefix); gf_mul(t, inv, t); } /* 1 / (G D)_i */
+            else gf_copy(t, inv);
+            gf_from_abi(v, &a->gd);
+            gf_mul(inv, inv, v);
+            gf_from_abi(v, &a->h);
+            gf_mul(t, t, v);                                  /* x = H / (G D) */
+            const uint32_t f = a->flags;
+            const uint32_t sign_ok = ((gf_lobit(t) & 1u) == ((f & VAUX_LOW) ? 1u : 0u)) ? 1u : 0u;
+            status[i] = (((f & VAUX_FAST) && sign_ok) || (f & VAUX_SLOW)) ? -1 : 0;
+        }
     }
 };
 struct LaneBuildWide { /* verification table, WIDE_LANES lanes */

@@ -72,6 +72,76 @@ GD void s_verify_accept(int32_t *status, size_t i, sref sb, const abi_pt *r_pt, 
     s_ld(b, t1);
     status[i] = ST_OK(gf_eq(a, b) & decoded);
 }
+// The same accept bit WITHOUT the square root of the R decode (goldilocks.c:949-1004 needs isr(N D), 446 squarings).
+// With y = the encoded coordinate of R, N = 1 - y^2, D = 1 - d y^2 (never 0: d is a non-square), the reference decodes
+// x = +-sqrt(N/D) with lobit(x) = the sign bit, maps (x, y) through the 4-isogeny to (X_R : Y_R) and accepts iff
+// Y_c X_R == Y_R X_c.  Multiplied by D^2 that equation is linear in W = x D (W^2 = N D):
+//     G W == H,   G = 2 y (2D - N - y^2 D) Y_c,   H = (y^2 D - N)(N + y^2 D) X_c.
+// If G != 0 the reference accepts iff N D != 0, H^2 == G^2 N D (then N D is a square and W = +-H/G) and
+// lobit(H / (G D)) == sign bit (W = H/G picks the root the decoder picks; the two roots have different low bits).
+// That needs one INVERSION, not a square root, and inversions batch (Montgomery's trick): this step leaves G D, H and
+// the flags in the signature's `aux` record and LaneVerifySign (lanes.cuh) finishes 16 signatures per inversion.
+// If G == 0 (y = 0, Y_c = 0, ... : never on honest data) the lane takes the reference's own route here and now:
+// accept iff N D is a non-zero square (s_isr) and H == 0.  The other decode conditions (y < p, low seven bits of the
+// last byte clear) are checked as the reference checks them.
+// On entry slots 0, 1 hold X_c, Y_c; all seven slots are clobbered.
+GD void s_verify_accept_prep(verify_aux *aux, sref sb, const uint8_t *r_enc, gmask_t key_ok) {
+    const sref s0 = s_slot(sb, 0), s1 = s_slot(sb, 1), s2 = s_slot(sb, 2), s3 = s_slot(sb, 3), s4 = s_slot(sb, 4), s5 = s_slot(sb, 5), s6 = s_slot(sb, 6);
+    gf a, b, one, N, D, E;
+    uint32_t w[15];
+    gf_set_ui(one, 1);
+    words_load_bytes(w, 15, r_enc, 57);
+    gmask_t good = gf_from_words(a, w);                      /* y < p (f_generic.c:48-68) */
+    good &= ((w[14] & 0x7f) == 0) ? ~0u : 0u;                /* goldilocks.c:965 */
+    good &= key_ok;
+    const uint32_t low = (w[14] >> 7) & 1u;
+    s_st(s2, a);                                             /* y */
+    s_sqr(s3, s2);                                           /* y^2 */
+    s_ld(b, s3);
+    gf_sub(N, one, b);
+    gf_mulw_signed(a, b, GOLD_EDWARDS_D);
+    gf_sub(D, one, a);
+    s_st(s4, N); s_st(s5, D);
+    s_mul(s6, s3, s5);                                       /* E = y^2 D */
+    s_ld(E, s6); s_ld(N, s4); s_ld(D, s5);
+    gf_add(a, D, D); gf_sub(a, a, N); gf_sub(a, a, E);       /* 2D - N - E */
+    s_st(s3, a);
+    s_mul(s3, s2, s3);
+    s_mul(s3, s3, s1);                                       /* y (2D - N - E) Y_c = G / 2 */
+    s_ld(N, s4); s_ld(E, s6);
+    gf_sub(a, E, N); s_st(s1, a);
+    gf_add(a, N, E); s_st(s2, a);
+    s_mul(s6, s1, s2);
+    s_mul(s6, s6, s0);                                       /* H */
+    s_mul(s4, s4, s5);                                       /* N D */
+    s_ld(a, s3); gf_add(a, a, a); s_st(s3, a);               /* G */
+    s_sqr(s0, s6);
+    s_sqr(s2, s3);
+    s_mul(s2, s2, s4);
+    s_ld(a, s0); s_ld(b, s2);
+    gmask_t fast = gf_eq(a, b);                              /* H^2 == G^2 N D */
+    s_ld(a, s4);
+    fast &= ~gf_is_zero(a);                                  /* N D != 0 (y = +-1 is rejected: isr(0) fails, goldilocks.c:974) */
+    s_ld(a, s3);
+    const gmask_t g_zero = gf_is_zero(a);
+    fast &= ~g_zero;
+    gmask_t slow = 0;
+    if (g_zero) {                                            /* degenerate: the reference's own route */
+        const gmask_t square = s_isr(s0, s2, s4);
+        s_ld(a, s6);
+        slow = square & gf_is_zero(a);
+    }
+    s_mul(s5, s3, s5);                                       /* G D (1 where it is 0: it only feeds the batched inversion) */
+    s_ld(a, s5);
+    gf_cond_sel(a, a, one, g_zero);
+    s_ld(b, s6);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {                            /* weakly reduced limbs: the next kernel only multiplies them */
+        aux->gd.limb[k] = (uint64_t)a.v[2 * k] + ((uint64_t)a.v[2 * k + 1] << 28);
+        aux->h.limb[k] = (uint64_t)b.v[2 * k] + ((uint64_t)b.v[2 * k + 1] << 28);
+    }
+    aux->flags = ((good & fast) ? VAUX_FAST : 0u) | ((good & slow) ? VAUX_SLOW : 0u) | (low ? VAUX_LOW : 0u);
+}
 struct SlotEdVerifyFinish {
     static constexpr int NSLOTS = BDSM_NSLOTS;
     int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; uint4 *scratch;
@@ -100,32 +170,35 @@ struct SlotKeyTables {
 // SlotEdVerifyFinish (own window table in `scratch`); items [counts[1], counts[1] + counts[0]) are signatures whose
 // public key (byte-identical) occurs more than once: the multiples of the key come from the table its group built.
 // One launch for both; the expensive stand-alone items go first and the items are handed out dynamically
-// (k_slots_persist, slots.cuh), so the cheap ones fill in behind them.
+// (k_slots_persist, slots.cuh), so the cheap ones fill in behind them.  R is never decoded: s_verify_accept_prep works
+// from its bytes and leaves the sign check to LaneVerifySign.
 struct SlotEdVerifyFinishShared {
     static constexpr int NSLOTS = BDSM_NSLOTS;
-    int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; uint4 *ktabs; uint4 *scratch;
-    verify_plan plan;
+    abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; uint4 *ktabs; uint4 *scratch;
+    verify_plan plan; const uint8_t *sig;
     GDM void operator()(size_t j, sref sb, size_t slot) const {
         const size_t nu = plan.counts[1];
+        size_t i;
+        gmask_t key_ok;
         sc c, r;
         if (j >= nu) {
             if (j - nu >= plan.counts[0]) return;
-            const size_t i = plan.shared_sig[j - nu], t = plan.shared_tab[j - nu];
+            const size_t t = plan.shared_tab[j - nu];
+            i = plan.shared_sig[j - nu];
             sc_from_abi(c, challenge + i);
             sc_from_abi(r, response + i);
             s_verify_shared_key(sb, r, c, wide, ktab_of(ktabs, t));
-            s_bdsm_quirk(sb, c);
-            /* the key bytes are the representative's, so its decode flag is this signature's */
-            s_verify_accept(status, i, sb, pts + 2 * i + 1, (gmask_t)ok[2 * (size_t)plan.tab_rep[t]] & (gmask_t)ok[2 * i + 1]);
+            key_ok = (gmask_t)ok[2 * (size_t)plan.tab_rep[t]]; /* the key bytes are the representative's, so is the decode flag */
         } else {
-            const size_t i = plan.unique_sig[j];
+            i = plan.unique_sig[j];
             sc_from_abi(c, challenge + i);
             sc_from_abi(r, response + i);
             s_pt_from_abi(sb, pts + 2 * i);
             s_base_double_scalarmul(sb, r, c, wide, wtab_of<1>(scratch, slot));
-            s_bdsm_quirk(sb, c);
-            s_verify_accept(status, i, sb, pts + 2 * i + 1, (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1]);
+            key_ok = (gmask_t)ok[2 * i];
         }
+        s_bdsm_quirk(sb, c);
+        s_verify_accept_prep((verify_aux *)(pts + 2 * i + 1), sb, sig + 114 * i, key_ok); /* the R slot of pts is free: R is never decoded */
     }
 };
 
@@ -142,18 +215,22 @@ struct SlotKeysetTables { /* one lane per key: decoded key t -> table t */
 };
 struct SlotEdVerifyFinishKeyset { /* signature i under key key_index[i] of the set */
     static constexpr int NSLOTS = BDSM_NSLOTS;
-    int32_t *status; const abi_pt *r_pts; const int32_t *r_ok, *key_ok; const abi_sc *challenge, *response; const niels *wide; const uint4 *ktabs;
-    const uint32_t *key_index; uint32_t n_keys;
+    verify_aux *aux; const int32_t *key_ok; const abi_sc *challenge, *response; const niels *wide; const uint4 *ktabs;
+    const uint32_t *key_index; uint32_t n_keys; const uint8_t *sig;
     GDM void operator()(size_t i, sref sb, size_t slot) const {
         (void)slot;
         const uint32_t t = key_index[i];
-        if (t >= n_keys) { status[i] = 0; return; } /* no such key: FAILURE */
+        if (t >= n_keys) { /* no such key: FAILURE */
+            abi_gf one = {{1, 0, 0, 0, 0, 0, 0, 0}};
+            aux[i].gd = one; aux[i].h = one; aux[i].flags = 0;
+            return;
+        }
         sc c, r;
         sc_from_abi(c, challenge + i);
         sc_from_abi(r, response + i);
         s_verify_shared_key(sb, r, c, wide, ktab_of(const_cast<uint4 *>(ktabs), t));
         s_bdsm_quirk(sb, c);
-        s_verify_accept(status, i, sb, r_pts + i, (gmask_t)key_ok[t] & (gmask_t)r_ok[i]);
+        s_verify_accept_prep(aux + i, sb, sig + 114 * i, (gmask_t)key_ok[t]);
     }
 };
 

@@ -195,15 +195,14 @@ EXPORT void goldilocks_b200_keyset_destroy(hostsim_keyset *ks) { delete ks; }
 EXPORT size_t goldilocks_b200_keyset_size(const hostsim_keyset *ks) { return ks ? ks->m : 0; }
 EXPORT int32_t goldilocks_ed448_verify_keyset_batch(int32_t *st, const hostsim_keyset *ks, const uint32_t *key_index, const uint8_t *sig, const uint8_t *msg,
                                                     const size_t *off, uint8_t prehashed, const uint8_t *ctx, uint8_t ctx_len, size_t n) {
-    std::vector<abi_pt> rpts(n + 1);
-    std::vector<int32_t> rok(n + 1);
     std::vector<abi_sc> chal(n + 1), resp(n + 1);
-    LaneKeysetDecodeR f1 = {rpts.data(), rok.data(), sig};
-    run(f1, n);
     LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, ks->pk.data(), msg, off, prehashed, ctx, ctx_len, 0, key_index, (uint32_t)ks->m};
     run(f2, n);
-    SlotEdVerifyFinishKeyset f3 = {st, rpts.data(), rok.data(), ks->key_ok.data(), chal.data(), resp.data(), wide_table(), ks->ktabs.data(), key_index, (uint32_t)ks->m};
+    std::vector<verify_aux> aux(n + 1);
+    SlotEdVerifyFinishKeyset f3 = {aux.data(), ks->key_ok.data(), chal.data(), resp.data(), wide_table(), ks->ktabs.data(), key_index, (uint32_t)ks->m, sig};
     run_smp(f3, n);
+    LaneVerifySign fv = {st, aux.data(), 1, n};
+    run(fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH);
     return -1;
 }
 EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off,
@@ -230,11 +229,13 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     shared_sig.push_back(0); shared_tab.push_back(0); unique_sig.push_back(0); tab_rep.push_back(0); /* never empty */
     verify_plan plan = {shared_sig.data(), shared_tab.data(), unique_sig.data(), tab_rep.data(), counts.data()};
     std::vector<uint4> ktabs((size_t)(counts[2] + 1) * KTAB_QUADS);
-    LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, plan, 0};
-    run(f1, 2 * n);
+    LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, plan, n};   /* keys only: R is never decoded on this path */
+    run(f1, n);
     SlotKeyTables ft = {pts.data(), ktabs.data(), plan};
     run_smp(ft, counts[2]);
-    SlotEdVerifyFinishShared fs = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), ktabs.data(), slots(1), plan};
+    SlotEdVerifyFinishShared fs = {pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), ktabs.data(), slots(1), plan, sig};
     run_smp(fs, (size_t)counts[0] + counts[1]);
+    LaneVerifySign fv = {st, (verify_aux *)(pts.data() + 1), 2, n};
+    run(fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH);
     return -1;
 }

@@ -360,6 +360,92 @@ def check_eddsa_keyset(lib, chk, n, nkeys=11, label="c4k"):
         lib.keyset_destroy(h)
 
 
+# ---- hand-made signatures around the corner cases of the R check (torsion, y = 0, y = +-1, non-canonical y) -------------
+_D = -39081
+_BX = 224580040295924300187604334099896036246789641632564134246125461686950415467406032909029192869357953282578032075146446173674602635247710
+_BY = 298819210078481492676017930443930673437544040154080242095928241372331506189835876003536878655418784733982303233503462500531545062832660
+
+
+def _ed_add(p1, p2):
+    (x1, y1), (x2, y2) = p1, p2
+    t = _D * x1 * x2 * y1 * y2 % P
+    return ((x1 * y2 + y1 * x2) * pow(1 + t, P - 2, P) % P, (y1 * y2 - x1 * x2) * pow(1 - t, P - 2, P) % P)
+
+
+def _ed_mul(k, pt):
+    acc = (0, 1)
+    while k:
+        if k & 1:
+            acc = _ed_add(acc, pt)
+        pt = _ed_add(pt, pt)
+        k >>= 1
+    return acc
+
+
+def _ed_enc(pt):
+    b = bytearray(int(pt[1]).to_bytes(57, "little"))
+    b[56] |= 0x80 if pt[0] & 1 else 0
+    return bytes(b)
+
+
+def _ed_secret(sk):
+    h = bytearray(hashlib.shake_256(bytes(sk)).digest(114)[:57])
+    h[0] &= 0xfc; h[55] |= 0x80; h[56] = 0
+    return int.from_bytes(h, "little")
+
+
+def _ed_challenge(r_enc, a_enc, msg):
+    return int.from_bytes(hashlib.shake_256(b"SigEd448\0\0" + r_enc + a_enc + msg).digest(114), "little") % util.Q
+
+
+def check_eddsa_adversarial(lib, chk, copies=3):
+    """Signatures built by hand (plain Python Ed448 arithmetic) so that R or A carry 2- and 4-torsion, R is a small-order
+    point (y = 0: the degenerate branch of the square-root-free R check; y = +-1: undecodable), R is non-canonical, or the
+    low bits of the last byte are set.  Whatever the reference says is the answer; the list is repeated so that the
+    grouped path (n >= 64) sees it too, and a short prefix goes through the plain path."""
+    B = (_BX, _BY)
+    torsion = [(0, 1), (0, P - 1), (1, 0), (P - 1, 0)]
+    sigs, pks, msgs = [], [], []
+    for t in range(6):
+        sk = bytes(stream_bytes("adv/sk%d" % t, 57))
+        s = _ed_secret(sk)
+        A = _ed_mul(s, B)
+        for ti, T in enumerate(torsion):
+            for tj, TA in enumerate(torsion if t < 2 else torsion[:1]):
+                msg = bytes(stream_bytes("adv/m%d.%d.%d" % (t, ti, tj), 5 + t))
+                r = util.from_le(stream_bytes("adv/r%d.%d.%d" % (t, ti, tj), 56)) % util.Q
+                a_enc = _ed_enc(_ed_add(A, TA))
+                r_enc = _ed_enc(_ed_add(_ed_mul(r, B), T))
+                k = _ed_challenge(r_enc, a_enc, msg)
+                sigs.append(r_enc + int((r + k * s) % util.Q).to_bytes(57, "little")); pks.append(a_enc); msgs.append(msg)
+        a_enc = _ed_enc(A)
+        for r_pt, extra in (((1, 0), 0), ((P - 1, 0), 0), ((0, 1), 0), ((0, P - 1), 0), ((1, 0), 1), ((1, 0), 0x40)):
+            msg = bytes(stream_bytes("adv/small%d" % t, 9))
+            r_enc = bytearray(_ed_enc(r_pt)); r_enc[56] |= extra; r_enc = bytes(r_enc)
+            k = _ed_challenge(r_enc, a_enc, msg)
+            sigs.append(r_enc + int(k * s % util.Q).to_bytes(57, "little")); pks.append(a_enc); msgs.append(msg)   # r = 0: S B - k A = identity
+        for y_nc in (P, P + 1):                                    # non-canonical y: the decoder must refuse
+            msg = b"nc"
+            r_enc = int(y_nc).to_bytes(57, "little")
+            k = _ed_challenge(r_enc, a_enc, msg)
+            sigs.append(r_enc + int(k * s % util.Q).to_bytes(57, "little")); pks.append(a_enc); msgs.append(msg)
+    sig = np.frombuffer(b"".join(sigs), np.uint8).reshape(-1, 114).copy()
+    pk = np.frombuffer(b"".join(pks), np.uint8).reshape(-1, 57).copy()
+    sig, pk, msgs = np.tile(sig, (copies, 1)), np.tile(pk, (copies, 1)), msgs * copies
+    want = chk.ed448_verify(sig, pk, msgs)
+    assert (want == -1).any() and (want == 0).any()
+    eq(lib.ed448_verify(sig, pk, msgs), want, "ed448_verify status, hand-made corner cases (grouped path)")
+    eq(lib.ed448_verify(sig[:40], pk[:40], msgs[:40]), want[:40], "ed448_verify status, hand-made corner cases (plain path)")
+    if lib.has("goldilocks_b200_keyset_create"):
+        keys, kidx = np.unique(pk, axis=0, return_inverse=True)
+        h = lib.keyset_create(keys)
+        try:
+            eq(lib.ed448_verify_keyset(h, kidx.reshape(-1), sig, msgs), want, "ed448_verify_keyset status, hand-made corner cases")
+        finally:
+            lib.keyset_destroy(h)
+    return want
+
+
 def check_shake(lib, n=40):
     msgs = [bytes(stream_bytes("shake/%d" % i, i * 7)) for i in range(n)] + [b"", b"a" * 135, b"b" * 136, b"c" * 137, b"d" * 272]
     for outlen in (32, 57, 114, 136, 137, 300):

@@ -85,6 +85,11 @@ def test_eddsa_keyset(gpu, chk):
     parity.check_eddsa_keyset(gpu, chk, 40, nkeys=5, label="c4k/few")
 
 
+def test_eddsa_corner_cases(gpu, chk):
+    """torsion in R and A, small-order and undecodable R, non-canonical R: the square-root-free R check against the reference"""
+    parity.check_eddsa_adversarial(gpu, chk)
+
+
 def test_decaf_vectors(gpu, vectors):
     parity.check_decaf_vectors(gpu, vectors)
 

@@ -54,6 +54,7 @@ def test_eddsa(sim, chk, vectors):
     parity.check_eddsa_random(sim, chk, 192)
     parity.check_eddsa_grouped(sim, chk, 160)
     parity.check_eddsa_keyset(sim, chk, 120)
+    parity.check_eddsa_adversarial(sim, chk, copies=1)
     parity.check_eddsa_grouped(sim, chk, 96, label="c4g/ctx", prehashed=True, context=b"ctx")
 
 

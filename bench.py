@@ -37,8 +37,8 @@ MSG_LEN = 32
 MAC32 = {"verify": 981120, "verify_finish": 800300, "x448": 870208, "comb": 142656}  # the REFERENCE's algorithm
 # IMAD.WIDE actually issued per signature by the finish kernel (multiply = 193, square = 110):
 #   under a per-key table: 70 doublings (4S + 3M, +1M for T on every fifth), 90 x 8M + 30 x 7M additions (14 without T), the
-#   final comparison (2M);  stand-alone: 445 doublings + own window table
-EXECUTED_MAC32 = {"finish_shared": 280 * 110 + 1142 * 193, "finish_alone": 1784 * 110 + 2390 * 193}
+#   square-root-free R comparison (3S + 8M);  stand-alone: 445 doublings + own window table + the same comparison
+EXECUTED_MAC32 = {"finish_shared": 283 * 110 + 1148 * 193, "finish_alone": 1787 * 110 + 2396 * 193}
 METRIC = "Ed448 verifies/s at batch 2^20 per GPU (X448 and comb ops/s in extra)"
 UNIT = "verifies/s"
 
@@ -53,10 +53,10 @@ def imad_peak():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-    `ncu --set full` capture of this same workload (profiles/r01z_finish_ncu.txt); None if absent."""
+    `ncu --set full` capture of this same workload (profiles/r01zz_finish_ncu.txt); None if absent."""
     try:
         tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        with open(os.path.join(ROOT, "profiles", "r01z_finish_ncu.txt")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01zz_finish_ncu.txt")) as f:
             for line in f:
                 t = line.split()
                 if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
@@ -302,7 +302,7 @@ def run_ours(args):
     n_shared = int((cnt[inv.reshape(-1)] >= 2).sum())
     executed = n_shared * EXECUTED_MAC32["finish_shared"] + (n - n_shared) * EXECUTED_MAC32["finish_alone"]
     roofline = {"bound": "imad", "kernel": "k_slots_persist<%s>" % dominant, "achieved": achieved, "peak": peak, "unit": "GMAC32/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes/launch (ncu --set full, profiles/r01z_finish_ncu.txt)",
+                "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes/launch (ncu --set full, profiles/r01zz_finish_ncu.txt)",
                 "algorithmic_bytes_per_launch": n * (512 + 112 + 8 + 4), "peak_source": peak_how,
                 "algorithmic_mac32_per_signature": MAC32["verify_finish"],
                 "executed_mac32_per_launch": executed, "signatures_under_a_shared_key_table": n_shared,

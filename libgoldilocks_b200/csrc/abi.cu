@@ -756,7 +756,7 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
         g_launches += launched;
     }
     /* without a plan: R and public key of signatures [lo, hi) (interleaved lanes).  With a plan nothing decodes R: the
-     * finish kernel works from its bytes (s_verify_accept_fast). */
+     * finish kernel works from its bytes (s_verify_accept_prep, slot_lanes.cuh). */
     auto decode_range = [&](size_t lo, size_t hi) {
         if (plan.unique_sig) return true;
         LaneEdVerifyDecode f = {pts, ok, sig, pk, n, plan, 2 * lo};
@@ -784,14 +784,14 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
         return launch(c, fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH, s);
     }
     SlotEdVerifyFinish f3 = {status, pts, ok, chal, resp, c.wide, slots};
-    return launch_smp(c, f3, n, grids.unique, s, GRID_STRIDE); /* fewer than 64 signatures: one partial round */
+    return launch_smp(c, f3, n, grids.unique, s, GRID_STRIDE); /* no plan: fewer than 64 signatures (one partial round), or more than 2^31 */
 }
 goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                  uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n) {
     /* One pass over the whole batch (splitting the BATCH costs more than it hides: every chunk pays its own key-grouping
      * pass and key-table wave, 67.9 ms split vs 66.3 ms whole at 2^20).  Only the COPIES are split: keys first, then the
      * signatures and messages in two halves on the copy stream, so the grouping pass, the per-key decodes and the first
-     * half's decode run while the rest is still crossing PCIe. */
+     * half's challenge hashes run while the rest is still crossing PCIe. */
     Call k;
     size_t total = n ? msg_off[n] : 0;
     const size_t *doff = k.in(msg_off, n + 1);

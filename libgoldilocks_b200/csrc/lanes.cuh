@@ -503,7 +503,7 @@ struct LaneEdVerifyDecode {
     /* Without a plan: lane 2i = public key i, lane 2i+1 = R of signature i.  With the plan of a grouped batch
      * (verify_plan.cuh) only public keys are decoded, once per key, by the lanes from n on: the keys of the stand-alone
      * signatures, then one representative per key table; the remaining lanes retire at once (R is not decoded at all on
-     * that path, slot_lanes.cuh s_verify_accept_fast).  The result lands in pts[2i] (key of signature i) / pts[2i+1] (its R). */
+     * that path, slot_lanes.cuh s_verify_accept_prep).  The result lands in pts[2i] (key of signature i) / pts[2i+1] (its R). */
     abi_pt *pts; int32_t *ok; const uint8_t *sig, *pk; size_t n; verify_plan plan; size_t lane0; /* first lane of this launch */
     GDM void operator()(size_t j0) const {
         const size_t j = j0 + lane0;

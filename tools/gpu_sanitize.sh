@@ -18,6 +18,10 @@ pk2 = pk[rep]; sig2 = lib.ed448_sign(sk[rep], pk2, msgs)
 sig2[::9, 3] ^= 1
 st = lib.ed448_verify(sig2, pk2, msgs)
 assert (st[np.arange(n) % 9 != 0] == -1).all() and (st[::9] == 0).all()
+h = lib.keyset_create(pk[:7])              # key set: tables kept across calls, square-root-free R check, batched sign kernel
+st = lib.ed448_verify_keyset(h, rep.astype(np.uint32), sig2, msgs)
+assert (st[np.arange(n) % 9 != 0] == -1).all() and (st[::9] == 0).all()
+lib.keyset_destroy(h)
 a56 = stream_bytes("san/a", 300 * 56).reshape(300, 56); b56 = stream_bytes("san/b", 300 * 56).reshape(300, 56)
 lib.gf_mul(a56, b56); lib.gf_sqr(a56)      # staged field kernels: two full blocks (TMA bulk + mbarrier) and a ragged tail
 pp = lib.from_hash_uniform(stream_bytes("san/h", 300 * 112).reshape(300, 112))

@@ -85,7 +85,7 @@ GD void s_verify_accept(int32_t *status, size_t i, sref sb, const abi_pt *r_pt, 
 // accept iff N D is a non-zero square (s_isr) and H == 0.  The other decode conditions (y < p, low seven bits of the
 // last byte clear) are checked as the reference checks them.
 // On entry slots 0, 1 hold X_c, Y_c; all seven slots are clobbered.
-GD void s_verify_accept_prep(verify_aux *aux, sref sb, const uint8_t *r_enc, gmask_t key_ok) {
+SFN void s_verify_accept_prep(verify_aux *aux, sref sb, const uint8_t *r_enc, gmask_t key_ok) {
     const sref s0 = s_slot(sb, 0), s1 = s_slot(sb, 1), s2 = s_slot(sb, 2), s3 = s_slot(sb, 3), s4 = s_slot(sb, 4), s5 = s_slot(sb, 5), s6 = s_slot(sb, 6);
     gf a, b, one, N, D, E;
     uint32_t w[15];

@@ -36,9 +36,9 @@ N_PER_GPU = 1 << 20
 MSG_LEN = 32
 MAC32 = {"verify": 981120, "verify_finish": 800300, "x448": 870208, "comb": 142656}  # the REFERENCE's algorithm
 # IMAD.WIDE actually issued per signature by the finish kernel (multiply = 193, square = 110):
-#   under a per-key table: 70 doublings (4S + 3M, +1M for T on every fifth), 90 x 8M + 30 x 7M additions (14 without T), the
+#   under a per-key table: 40 doublings (4S + 3M, +1M for T on every fifth), 90 x 8M + 30 x 7M additions (8 without T), the
 #   square-root-free R comparison (3S + 8M);  stand-alone: 445 doublings + own window table + the same comparison
-EXECUTED_MAC32 = {"finish_shared": 283 * 110 + 1148 * 193, "finish_alone": 1787 * 110 + 2396 * 193}
+EXECUTED_MAC32 = {"finish_shared": 163 * 110 + 1058 * 193, "finish_alone": 1787 * 110 + 2396 * 193}
 METRIC = "Ed448 verifies/s at batch 2^20 per GPU (X448 and comb ops/s in extra)"
 UNIT = "verifies/s"
 
@@ -313,7 +313,7 @@ def run_ours(args):
                 "note": "integer-multiply-pipe roofline (north_star). `achieved`/`frac` count the REFERENCE's algorithmic work per signature "
                         "(SURVEY 8(d): 800 300 MAC32 for the double-scalar multiplication), so sharing a per-key table pushes them above 1; "
                         "`frac_executed` counts the IMAD.WIDE this kernel really issues and is the pipe utilisation. DRAM traffic = key tables "
-                        "(16.5 KB per key) + wide fixed-base tables (12 MB, L2 resident): a few % of the HBM roof"}
+                        "(41 KB per key, re-read once per row because the keys resident at a time overflow L2) + wide fixed-base tables (30 MB): ~5 % of the HBM roof"}
 
     # ---- end to end through the host-pointer C ABI ---------------------------------------------------------
     fn = lib.lib.goldilocks_ed448_verify_batch

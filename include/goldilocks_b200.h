@@ -245,7 +245,7 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *sign
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature /*n*114*/, const uint8_t *pubkey /*n*57*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n);
 /* Key sets (our extension; SURVEY 8(f)4, "precomputed per-public-key tables for repeated verification under the same key").
  * goldilocks_ed448_verify_batch already shares one table among the byte-identical keys of ONE batch; a key set keeps the
- * tables of m public keys in HBM (25 KB per key) ACROSS calls, so a verifier that sees the same signers again pays neither
+ * tables of m public keys in HBM (41 KB per key) ACROSS calls, so a verifier that sees the same signers again pays neither
  * the key decode nor the table build again.  status[i] is what goldilocks_ed448_verify(signature i, pubkeys[key_index[i]],
  * message i, ...) returns; an undecodable key is accepted into the set and rejects its signatures, like the reference;
  * key_index[i] >= m yields FAILURE for element i.  The handle belongs to the CUDA device that was current at creation. */
@@ -263,7 +263,7 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *o
  *    Calls are asynchronous on that stream; `scratch` must hold goldilocks_b200_*_scratch_bytes(n).
  * ====================================================================================== */
 /* scratch of a device-resident verification: decoded points and scalars, the key-grouping work lists and room for
- * n/4 + 1 per-key tables (25 KB each); about 7 KB per signature */
+ * n/4 + 1 per-key tables (41 KB each); about 11 KB per signature */
 GOLDILOCKS_B200_API size_t goldilocks_b200_verify_scratch_bytes(size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off, uint8_t prehashed, const uint8_t *context /*device or NULL*/, uint8_t context_len, size_t n, void *scratch, void *stream);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream);

@@ -40,7 +40,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;   // signatures and messages of a verification cross PCIe here while the main stream groups the keys
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     fixed_tables *ft = nullptr;
-    niels *wide = nullptr;       // WIDE_TABLES x 16384-entry verification tables: odd multiples of 2^(75c) B (18 MB, L2 resident)
+    niels *wide = nullptr;       // WIDE_TABLES x 16384-entry verification tables: odd multiples of 2^(45c) B (30 MB, L2 resident)
     std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
     size_t used = 0;             // bytes used in the active block
     void *slot_scratch = nullptr;

@@ -25,12 +25,13 @@
 #define WIDE_LANES 128                         /* lanes that build one table at init */
 #define WIDE_PER_LANE (WIDE_ENTRIES / WIDE_LANES)
 /* Verification under a REPEATED public key splits both scalars into VSH_CHUNKS columns of VSH_ROWS
- * 5-bit digits: digit k = VSH_ROWS*c + r is served by tables of 2^(75c)*A (built once per key) and 2^(75c)*B
- * (wide tables 1..5, built at init next to table 0), so one signature costs 14*5 doublings instead of 89*5.
- * Measured on the bench corpus (16 signatures per key): 4 x 23 -> 50.7 ms, 6 x 15 -> see DESIGN.md. */
+ * 5-bit digits: digit k = VSH_ROWS*c + r is served by tables of 2^(45c)*A (built once per key) and 2^(45c)*B
+ * (wide tables 1..9, built at init next to table 0), so one signature costs 8*5 doublings instead of 89*5.
+ * Measured on the bench corpus (16 signatures per key), finish + key tables: 4 x 23 -> 50.7 + 5.3 ms, 6 x 15 -> 41.3 + 6.3,
+ * 10 x 9 -> 36.0 + 7.8, 15 x 6 -> 34.0 + 9.6 (and 62 KB per key); 10 x 9 is never worse than 6 x 15 from 4 signatures per key on. */
 #ifndef VSH_CHUNKS
-#define VSH_CHUNKS 6
-#define VSH_ROWS 15
+#define VSH_CHUNKS 10
+#define VSH_ROWS 9
 #endif
 #define VSH_SHIFT (VSH_ROWS * WINDOW_BITS)     /* bits between columns */
 #define WIDE_TABLES VSH_CHUNKS
@@ -307,9 +308,10 @@ GD void build_wide_lane(niels *out, pniels *tmp, gf *pre, const niels *comb, int
         const uint64_t odd = 2u * (uint32_t)(WIDE_PER_LANE * lane) + 1u;
         const int sh = VSH_SHIFT * c, word = sh / 32, bit = sh % 32;
         const uint64_t lo = odd << bit;                    /* odd < 2^15, bit < 32 */
-        start.w[word] = (uint32_t)lo; start.w[word + 1] = (uint32_t)(lo >> 32);
+        start.w[word] = (uint32_t)lo;
         const uint64_t t2 = (uint64_t)2 << bit;
-        two.w[word] = (uint32_t)t2; two.w[word + 1] = (uint32_t)(t2 >> 32);
+        two.w[word] = (uint32_t)t2;
+        if (word + 1 < SC_WORDS) { start.w[word + 1] = (uint32_t)(lo >> 32); two.w[word + 1] = (uint32_t)(t2 >> 32); }
     }
     comb_scalarmul(twob, comb, two);
     comb_scalarmul(p, comb, start);

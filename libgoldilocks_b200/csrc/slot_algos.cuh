@@ -268,11 +268,11 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
 // ---------------------------------------------------------------------------------------------
 // Verification under a repeated public key (same group element as s_base_double_scalarmul).
 // The 90 signed 5-bit digits d_k of scalar2 and the 30 signed 15-bit digits e_m of scalar1 (the very recoding
-// above) are regrouped by column: k = R c + r with R = VSH_ROWS (15) rows and VSH_CHUNKS (6) columns, so
+// above) are regrouped by column: k = R c + r with R = VSH_ROWS (9) rows and VSH_CHUNKS (10) columns, so
 //     combo = sum_r 2^(5r) * ( sum_c d_(Rc+r) * A_c  +  sum_{c : 3 | Rc+r} e_((Rc+r)/3) * B_c ),
-// with A_c = 2^(5Rc) A from a table built ONCE PER KEY (s_build_key_tables: 5 x 75 doublings + six
+// with A_c = 2^(5Rc) A from a table built ONCE PER KEY (s_build_key_tables: 9 x 45 doublings + ten
 // 16-entry tables of odd multiples, shared read-only by every signature under that key) and B_c = 2^(5Rc) B from
-// the init-time wide tables.  One signature then costs 14 x 5 doublings + 90 + 30 additions.
+// the init-time wide tables.  One signature then costs 8 x 5 doublings + 90 + 30 additions.
 // Table layout: KTAB_ENTRIES pniels, entry 16c + e = (2e+1) A_c; the last two entries are build scratch.
 // ---------------------------------------------------------------------------------------------
 #define KTAB_ENTRIES (VSH_CHUNKS * WINDOW_NTABLE + 2)

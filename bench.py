@@ -53,10 +53,10 @@ def imad_peak():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-    `ncu --set full` capture of this same workload (profiles/r01zz_finish_ncu.txt); None if absent."""
+    `ncu --set full` capture of this same workload (profiles/r01f_finish_ncu.txt); None if absent."""
     try:
         tot, mult = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        with open(os.path.join(ROOT, "profiles", "r01zz_finish_ncu.txt")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01f_finish_ncu.txt")) as f:
             for line in f:
                 t = line.split()
                 if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
@@ -302,7 +302,7 @@ def run_ours(args):
     n_shared = int((cnt[inv.reshape(-1)] >= 2).sum())
     executed = n_shared * EXECUTED_MAC32["finish_shared"] + (n - n_shared) * EXECUTED_MAC32["finish_alone"]
     roofline = {"bound": "imad", "kernel": "k_slots_persist<%s>" % dominant, "achieved": achieved, "peak": peak, "unit": "GMAC32/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes/launch (ncu --set full, profiles/r01zz_finish_ncu.txt)",
+                "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes/launch (ncu --set full, profiles/r01f_finish_ncu.txt)",
                 "algorithmic_bytes_per_launch": n * (512 + 112 + 8 + 4), "peak_source": peak_how,
                 "algorithmic_mac32_per_signature": MAC32["verify_finish"],
                 "executed_mac32_per_launch": executed, "signatures_under_a_shared_key_table": n_shared,

@@ -77,7 +77,7 @@ def hbm_peak():
 # ------------------------------------------------------------------------------------------------
 # workload (synthetic, seeded): 2^16 keys x 16 messages of 32 bytes, 1/8 corrupted
 # ------------------------------------------------------------------------------------------------
-def make_corpus(signer, n, label, per=16, varlen=False):
+def make_corpus(signer, n, label, per=16, varlen=False, corrupt=True):
     """varlen: message lengths uniform in [0, 256) (second run) instead of MSG_LEN bytes each"""
     from util import stream_bytes
     nk = max(1, n // per)
@@ -94,7 +94,8 @@ def make_corpus(signer, n, label, per=16, varlen=False):
         off = np.arange(n + 1, dtype=np.uint64) * MSG_LEN
     sig = signer.ed448_sign(sk_all, pk_all, (arena, off))
     kinds = np.zeros(n, np.int32)
-    kinds[::8] = 1 + (np.arange((n + 7) // 8) % 4)
+    if corrupt:
+        kinds[::8] = 1 + (np.arange((n + 7) // 8) % 4)
     sel = stream_bytes(label + "/sel", n)
     i = np.flatnonzero(kinds == 1); sig[i, sel[i] % 57] ^= 1
     i = np.flatnonzero(kinds == 2); sig[i, 57 + sel[i] % 56] ^= 2
@@ -411,6 +412,46 @@ def run_ours(args):
         lib.keyset_destroy(handle)
         extra["verify_keyset_e2e"] = {"value": world * n / t, "unit": UNIT, "ms_per_step": t * 1e3, "batch_per_gpu": n, "keys_in_set": int(nk),
                                       "api": "goldilocks_ed448_verify_keyset_batch (host pointers, pinned; tables of the key set built once, not timed)"}
+
+    # ---- extra: random-linear-combination batch verification on an ALL-VALID corpus of the same shape, host
+    #      pointers; and the price of the fallback when one signature of the batch is bad -----------------------------------------
+    if not args.no_extra and lib.has("goldilocks_ed448_verify_rlc_batch"):
+        sig2, pk2, arena2, off2, expect2 = make_corpus(lib, n, "bench/rlc/rank%d" % rank, per=args.per_key, corrupt=False)
+        r_sig, r_pk, r_msg, r_off = pinned(sig2.reshape(-1)), pinned(pk2.reshape(-1)), pinned(arena2), pinned(off2.view(np.int64))
+        fr = lib.lib.goldilocks_ed448_verify_rlc_batch
+        fr.restype = C.c_int32
+        fast = C.c_int(0)
+        argr = [C.c_void_p(h_st.data_ptr()), C.c_void_p(r_sig.data_ptr()), C.c_void_p(r_pk.data_ptr()), C.c_void_p(r_msg.data_ptr()),
+                C.c_void_p(r_off.data_ptr()), C.c_uint8(0), None, C.c_uint8(0), C.c_size_t(n), C.byref(fast)]
+        for _ in range(2):
+            assert fr(*argr) == -1
+        assert (h_st.numpy() == -1).all() and fast.value == 1, "the batch equation must decide an all-valid batch"
+        kx = max(2, min(K, 3))
+        barrier()
+        lib.lib.goldilocks_b200_profile(C.c_int(1))
+        t0 = time.perf_counter()
+        for _ in range(kx):
+            assert fr(*argr) == -1
+        torch.cuda.synchronize()
+        t = max_over_ranks((time.perf_counter() - t0) / kx)
+        lib.lib.goldilocks_b200_profile(C.c_int(0))
+        cnt2 = lib.lib.goldilocks_b200_profile_read(names, ms, C.c_size_t(4096))
+        krlc = {}
+        for k in range(cnt2):
+            nm = names.raw[64 * k:64 * k + 64].split(b"\0")[0].decode()
+            krlc[nm] = krlc.get(nm, 0.0) + ms[k] / kx
+        barrier()
+        r_sig[114 * 12345 + 70] ^= 1                                  # one wrong S: the equation fails, the ordinary path decides
+        t0 = time.perf_counter()
+        assert fr(*argr) == -1
+        t_bad = time.perf_counter() - t0
+        st_bad = h_st.numpy()
+        assert fast.value == 0 and st_bad[12345] == 0 and (st_bad == -1).sum() == n - 1
+        extra["verify_rlc_all_valid_e2e"] = {"value": world * n / t, "unit": UNIT, "ms_per_step": t * 1e3, "batch_per_gpu": n, "fast_path": 1,
+                                             "kernel_ms": krlc, "ms_when_one_signature_is_bad": t_bad * 1e3,
+                                             "api": "goldilocks_ed448_verify_rlc_batch (host pointers, pinned): one multi-scalar multiplication with secret 128-bit "
+                                                    "weights decides the batch; per-signature fallback when it fails; corpus = the bench shape with NO corrupted entries"}
+        del r_sig, r_pk, r_msg, r_off
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
     cpu = None

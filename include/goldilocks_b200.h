@@ -254,6 +254,14 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_keyset_create(goldilocks_
 GOLDILOCKS_B200_API void goldilocks_b200_keyset_destroy(goldilocks_b200_keyset *keyset);
 GOLDILOCKS_B200_API size_t goldilocks_b200_keyset_size(const goldilocks_b200_keyset *keyset);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_keyset_batch(goldilocks_error_t *status, const goldilocks_b200_keyset *keyset, const uint32_t *key_index /*n*/, const uint8_t *signature /*n*114*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n);
+/* Random-linear-combination batch verification (csrc/rlc.cuh): an OPTIONAL fast path for batches in which
+ * (nearly) every signature is expected to be valid.  Same arguments and per-element statuses as
+ * goldilocks_ed448_verify_batch (eddsa.c:253-306).  Signatures whose R or public key does not decode are rejected up
+ * front like the reference does; the rest are checked by ONE multi-scalar multiplication with fresh secret 128-bit
+ * weights.  If that equation holds every remaining signature is reported valid (wrong with probability < 2^-127 per
+ * call); if it does not, the ordinary per-signature path runs over the batch, so the statuses are the reference's
+ * either way.  *fast_path (may be NULL) receives 1 when the equation decided the batch, 0 when the call fell back. */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status, const uint8_t *signature /*n*114*/, const uint8_t *pubkey /*n*57*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, int *fast_path);
 /* SHAKE256 one-shot over n inputs, each squeezed to outlen bytes (shake.c:177-190, SHAKE256 params 211-213) */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out /*n*outlen*/, size_t outlen, const uint8_t *in, const size_t *in_off /*n+1*/, size_t n);
 
@@ -266,6 +274,9 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *o
  * n/4 + 1 per-key tables (41 KB each); about 11 KB per signature */
 GOLDILOCKS_B200_API size_t goldilocks_b200_verify_scratch_bytes(size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off, uint8_t prehashed, const uint8_t *context /*device or NULL*/, uint8_t context_len, size_t n, void *scratch, void *stream);
+/* device-pointer form of goldilocks_ed448_verify_rlc_batch: scratch comes from the library's own arena and the call
+ * synchronises `stream` (it needs the number of distinct keys and the verdict on the host) */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_rlc_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off, uint8_t prehashed, const uint8_t *context /*device or NULL*/, uint8_t context_len, size_t n, void *stream, int *fast_path);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch_dev(goldilocks_448_point_s *out, const goldilocks_448_scalar_s *scalar, size_t n, void *stream);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_gf_mul_batch_dev(uint8_t *out, const uint8_t *a, const uint8_t *b, size_t n, void *stream);

@@ -336,6 +336,17 @@ class BatchLib:
         self._call("goldilocks_ed448_verify_batch", st, sig, pk, arena, off, C.c_uint8(1 if prehashed else 0), ctx, C.c_uint8(ctx_len), _Z(len(sig)))
         return st
 
+    def ed448_verify_rlc(self, sig, pk, msgs, prehashed=False, context=b""):
+        """(status int32[n], fast) -- goldilocks_ed448_verify_rlc_batch: random-linear-combination fast path with
+        per-element fallback; fast = 1 when the batch equation decided the call"""
+        sig, pk = _u8(sig, 114), _u8(pk, 57)
+        arena, off = pack_messages(msgs) if isinstance(msgs, list) else msgs
+        ctx, ctx_len = self._ctx(context)
+        st = np.zeros(len(sig), np.int32)
+        fast = C.c_int(0)
+        self._call("goldilocks_ed448_verify_rlc_batch", st, sig, pk, arena, off, C.c_uint8(1 if prehashed else 0), ctx, C.c_uint8(ctx_len), _Z(len(sig)), C.byref(fast))
+        return st, fast.value
+
     # ---- tables ----
     def export_comb_table(self):
         out = np.empty(15360, np.uint8)

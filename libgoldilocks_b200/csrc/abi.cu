@@ -4,6 +4,7 @@
 // Everything between the first and the last kernel of a call stays in HBM.  There is NO CPU
 // implementation behind these symbols: without a usable sm_100 GPU every call fails loudly.
 #include <cuda_runtime.h>
+#include <sys/random.h>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -817,6 +818,136 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
     if (k.ok) k.ok = verify_dev(*k.c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, scratch, slots, grids, k.c->stream, &feed);
     k.fetch((int32_t *)status, dst, n);
     if (!k.ok && k.c) cudaStreamSynchronize(k.c->copy_stream); /* never leave copies in flight behind an error */
+    return k.finish();
+}
+
+// ---- random-linear-combination batch verification (rlc.cuh): optional fast path, per-element fallback --
+// One multi-scalar multiplication decides the whole batch; if its equation fails (or anything looks odd) the ordinary
+// per-signature path above runs over the same device buffers, so the statuses are per element either way.
+constexpr size_t RLC_MIN = 64;
+static bool rlc_seed(uint8_t seed[32]) { /* fresh secret weights per call: the signer must not be able to predict them */
+    size_t got = 0;
+    while (got < 32) {
+        ssize_t r = getrandom(seed + got, 32 - got, 0);
+        if (r <= 0) { g_err = "getrandom failed: no entropy for the batch-verification weights"; return false; }
+        got += (size_t)r;
+    }
+    return true;
+}
+static bool rlc_usable(size_t n) { return n >= RLC_MIN && n < ((size_t)1 << 26); } /* pair lists are 32-bit, CUB counts are int */
+static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *dpk, const uint8_t *dmsg, const size_t *doff, uint8_t prehashed,
+                     const uint8_t *dctx, uint8_t ctx_len, size_t n, cudaStream_t s, int *fast) {
+    Ctx &c = *k.c;
+    *fast = 0;
+    auto ordinary = [&]() {
+        VerifyGrids grids;
+        if (!verify_grids(c, &grids)) return false;
+        const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
+        uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
+        void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(n));
+        if (!k.ok) return false;
+        return verify_dev(c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, n, scratch, slots, grids, s);
+    };
+    if (!rlc_usable(n)) return ordinary();
+    uint8_t seed[32];
+    if (!rlc_seed(seed)) return false;
+    void *gs = k.alloc(group_all_scratch_bytes(n));
+    uint8_t *dseed = k.out<uint8_t>(32);
+    if (!k.ok) return false;
+    key_groups kg;
+    uint64_t launched = 0;
+    cudaError_t e = group_keys_all(dpk, n, gs, &kg, s, &launched);
+    if (e != cudaSuccess) return fail("group_keys_all", e);
+    g_launches += launched;
+    uint32_t m = 0;
+    CU(cudaMemcpyAsync(&m, kg.ngroups, sizeof m, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s)); /* the number of distinct keys sizes everything below */
+    if (m == 0 || m > n) { g_err = "rlc: key grouping returned an impossible group count"; return false; }
+    const rlc_groups g = {kg.order, kg.gid, kg.gstart, m};
+    const rlc_shape sh = rlc_shape_for(n, 0);
+    const size_t npts = n + m + 1, npairs = n * sh.w1 + ((size_t)m + 1) * sh.w2, nb = (size_t)sh.w2 << sh.c;
+    pt *pts = k.out<pt>(npts);
+    int32_t *ok = k.out<int32_t>(npts), *valid = k.out<int32_t>(n);
+    uint32_t *flags = k.out<uint32_t>(2); /* [0] force fallback, [1] verdict */
+    abi_sc *chal = k.out<abi_sc>(n), *resp = k.out<abi_sc>(n);
+    uint32_t *z = k.out<uint32_t>(RLC_ZWORDS * n);
+    unsigned long long *key_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * m), *s_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * RLC_SCELLS);
+    uint32_t *kscal = k.out<uint32_t>(SC_WORDS * ((size_t)m + 1));
+    uint32_t *keys = k.out<uint32_t>(npairs), *vals = k.out<uint32_t>(npairs), *keys_s = k.out<uint32_t>(npairs), *vals_s = k.out<uint32_t>(npairs);
+    const size_t sort_bytes = pair_sort_scratch_bytes(npairs);
+    void *sort_tmp = k.alloc(sort_bytes);
+    pt *buckets = k.out<pt>(nb), *segsum = k.out<pt>((size_t)sh.w2 * sh.segs), *nodesum = k.out<pt>((size_t)sh.w2 * sh.nodes), *winsum = k.out<pt>(sh.w2);
+    if (!k.ok) return false;
+    CU(cudaMemsetAsync(flags, 0, 2 * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(key_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * m, s));
+    CU(cudaMemsetAsync(s_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * RLC_SCELLS, s));
+    LaneRlcDecode f1 = {pts, ok, flags, dsig, dpk, n, g};
+    if (!launch(c, f1, npts, s)) return false;
+    LaneEdVerifyScalars f2 = {chal, resp, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, 0};
+    if (!launch(c, f2, n, s)) return false;
+    LaneRlcZ f3 = {z, dseed, n};
+    if (!launch(c, f3, (n + 7) / 8, s)) return false;
+    LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g};
+    if (!launch(c, f4, n, s)) return false;
+    LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m};
+    if (!launch(c, f5, (size_t)m + 1, s)) return false;
+    LaneRlcDigits f6 = {keys, vals, z, kscal, n, sh};
+    if (!launch(c, f6, npts, s)) return false;
+    int key_bits = 1;
+    while ((sh.w2 << sh.c) >> key_bits) key_bits++;
+    e = pair_sort(sort_tmp, sort_bytes, keys, keys_s, vals, vals_s, npairs, key_bits, s);
+    if (e != cudaSuccess) return fail("pair_sort", e);
+    LaneRlcBucket f7 = {buckets, keys_s, vals_s, npairs, pts, sh};
+    if (!launch(c, f7, nb, s)) return false;
+    LaneRlcSegments f8 = {segsum, buckets, sh};
+    if (!launch(c, f8, (size_t)sh.w2 * sh.segs, s)) return false;
+    LaneRlcNodes f9 = {nodesum, segsum, sh};
+    if (!launch(c, f9, (size_t)sh.w2 * sh.nodes, s)) return false;
+    LaneRlcWindows f10 = {winsum, nodesum, sh};
+    if (!launch(c, f10, sh.w2, s)) return false;
+    LaneRlcVerdict f11 = {flags + 1, winsum, flags, sh};
+    if (!launch(c, f11, 1, s)) return false;
+    uint32_t hflags[2] = {0, 0};
+    CU(cudaMemcpyAsync(hflags, flags, sizeof hflags, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaMemsetAsync(z, 0, sizeof(uint32_t) * RLC_ZWORDS * n, s)); /* the weights are secret until the verdict is out; wipe them */
+    if (hflags[1]) {
+        *fast = 1;
+        CU(cudaMemcpyAsync(dst, valid, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
+        return true;
+    }
+    return ordinary();
+}
+goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
+                                                     uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, int *fast_path) {
+    Call k;
+    int fast = 0;
+    size_t total = n ? msg_off[n] : 0;
+    const size_t *doff = k.in(msg_off, n + 1);
+    const uint8_t *dctx = k.in(context, context_len);
+    const uint8_t *dpk = k.in(pubkey, 57 * n);
+    const uint8_t *dsig = k.in(signature, 114 * n);
+    const uint8_t *dmsg = k.in(msg, total);
+    int32_t *dst = k.out<int32_t>(n);
+    if (k.ok && n) k.ok = rlc_core(k, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, k.c->stream, &fast);
+    k.fetch((int32_t *)status, dst, n);
+    if (fast_path) *fast_path = fast;
+    return k.finish();
+}
+goldilocks_error_t goldilocks_ed448_verify_rlc_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
+                                                         uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, void *stream, int *fast_path) {
+    /* device pointers; scratch comes from the library's arena (the call holds the device lock) and the call synchronises
+     * `stream` twice (the number of distinct keys, the verdict): it returns with the statuses written */
+    Call k;
+    int fast = 0;
+    cudaStream_t s = as_stream(stream);
+    if (k.ok && n) {
+        if (cudaStreamSynchronize(k.c->stream) != cudaSuccess) k.ok = false; /* arena reuse: nothing of an earlier call may still run */
+        if (k.ok) k.ok = rlc_core(k, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, s, &fast);
+        if (k.ok && cudaStreamSynchronize(s) != cudaSuccess) k.ok = false;
+    }
+    if (fast_path) *fast_path = fast;
     return k.finish();
 }
 

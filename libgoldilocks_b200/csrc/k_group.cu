@@ -120,3 +120,49 @@ cudaError_t group_keys(const uint8_t *pk, size_t n, uint32_t cap, void *scratch,
     plan->shared_sig = L.shared_sig; plan->shared_tab = L.shared_tab; plan->unique_sig = L.unique_sig; plan->tab_rep = L.tab_rep; plan->counts = L.counts;
     return cudaGetLastError();
 }
+
+// ---- every group of the batch, no table budget: the key view of the random-linear-combination path (rlc.cuh) --------
+// order[j] = signature at sorted position j, gid[j] = 1-based group of that position, gstart[g] = first position of
+// group g (gstart[ngroups] = n), *ngroups = number of distinct keys.  Hash collisions can only split a group.
+size_t group_all_scratch_bytes(size_t n) {
+    if (!n) return 256;
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    cub::DeviceScan::InclusiveSum(nullptr, b2, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    return 2 * al(8 * n) + 4 * al(4 * n) + al(4 * (n + 1)) + al(4) + al((b1 > b2 ? b1 : b2) + 256);
+}
+cudaError_t group_keys_all(const uint8_t *pk, size_t n, void *scratch, key_groups *out, cudaStream_t s, uint64_t *launches) {
+    char *p = (char *)scratch;
+    auto take = [&](size_t bytes) { char *r = p; p += al(bytes); return (void *)r; };
+    uint64_t *h = (uint64_t *)take(8 * n), *hs = (uint64_t *)take(8 * n);
+    uint32_t *idx = (uint32_t *)take(4 * n), *is = (uint32_t *)take(4 * n), *head = (uint32_t *)take(4 * n), *gid = (uint32_t *)take(4 * n);
+    uint32_t *gstart = (uint32_t *)take(4 * (n + 1)), *ngroups = (uint32_t *)take(4);
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    cub::DeviceScan::InclusiveSum(nullptr, b2, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
+    const size_t cub_bytes = (b1 > b2 ? b1 : b2) + 256;
+    void *cub_tmp = take(cub_bytes);
+    const uint32_t m = (uint32_t)n;
+    size_t tmp = cub_bytes;
+    cudaError_t e;
+    k_hash<<<blocks(n), GB, 0, s>>>(h, idx, pk, m);
+    if ((e = cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, h, hs, idx, is, (int)n, 0, 64, s)) != cudaSuccess) return e;
+    k_heads<<<blocks(n), GB, 0, s>>>(head, is, pk, m);
+    tmp = cub_bytes;
+    if ((e = cub::DeviceScan::InclusiveSum(cub_tmp, tmp, head, gid, (int)n, s)) != cudaSuccess) return e;
+    k_gstart<<<blocks(n), GB, 0, s>>>(gstart, ngroups, head, gid, m);
+    if (launches) *launches += 3;
+    out->order = is; out->gid = gid; out->gstart = gstart; out->ngroups = ngroups;
+    return cudaGetLastError();
+}
+
+// Radix sort of the (window | digit) -> point pairs of the bucket method (rlc.cuh); a CUB primitive, plumbing.
+size_t pair_sort_scratch_bytes(size_t npairs) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)npairs);
+    return b + 256;
+}
+cudaError_t pair_sort(void *tmp, size_t tmp_bytes, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in, uint32_t *vals_out, size_t npairs,
+                      int key_bits, cudaStream_t s) {
+    return cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)npairs, 0, key_bits, s);
+}

@@ -1,0 +1,288 @@
+// rlc.cuh -- random-linear-combination batch verification of Ed448 signatures: an OPTIONAL fast path
+// with per-element fallback.  Results are the reference's (eddsa.c:253-306) except with probability < 2^-127 per call.
+//
+// The reference accepts signature i iff  resp_i*B + chal_i*A_i == R_i  on the internal curve, where A_i, R_i come out of
+// `point_decode_like_eddsa_and_mul_by_ratio` (goldilocks.c:949-1004), chal_i = -SHAKE256(dom || R || A || M) mod q and
+// resp_i = S mod q (eddsa.c:273-291), and `==` is `point_eq` (goldilocks.c:644-653).  Every decoded point is the image of
+// a curve point under the 4-isogeny whose kernel is the whole 4-torsion of Ed448, so all of these points live in the
+// subgroup of prime order q and `point_eq` on them is plain equality up to the 2-torsion point the isogeny never hits.
+// With secret random 128-bit weights z_i (drawn per call, after the signatures are fixed):
+//
+//     sum_i z_i*(-R_i)  +  sum_keys (sum_{i under key} z_i*chal_i mod q)*A_key  +  (sum_i z_i*resp_i mod q)*B  ==  identity
+//
+// holds if every signature is valid, and fails with probability >= 1 - 2^-127 if any is not (a non-zero element of a
+// group of prime order times a uniform odd 128-bit weight).  Signatures whose R or public key does not decode are
+// rejected up front, exactly like the reference (eddsa.c:266-270), and take no part in the sum.  When the equation
+// fails the caller runs the ordinary per-signature path over the batch, so statuses are always per element.
+//
+// The sum is ONE multi-scalar multiplication (bucket method): every scalar is cut into c-bit digits, the pairs
+// (window, digit) -> point are radix-sorted, one lane adds up each bucket, and the buckets of a window are folded with
+// running sums over segments of 32, a two-level tree and c*w doublings per window.  A signature costs its R decode
+// (one inverse square root), ceil(128 / c) point additions and a share of the per-key work, instead of the
+// 90 + 30 additions and 40 doublings of the table path (slot_lanes.cuh SlotEdVerifyFinishShared).
+//
+// Everything below is a per-lane functor (host/device clean: tests/hostsim runs the same code on the CPU tier).
+#pragma once
+#include "lanes.cuh"
+
+#define RLC_ZWORDS 4          /* 128-bit weights */
+#define RLC_ZBITS 128
+#define RLC_SEG 32            /* buckets per running-sum segment, segments per tree node */
+#define RLC_SCELLS 1024       /* accumulator cells of the response sum (spreads the atomics) */
+#define RLC_ACC_WORDS 14      /* one 64-bit cell per 32-bit scalar word: sums of up to 2^32 words never overflow */
+#define RLC_MAX_C 15
+
+// Key groups of a batch (k_group.cu group_keys_all): order[j] = signature at sorted position j, gid[j] = 1-based group
+// of that position, gstart[g] = first sorted position of group g.
+struct rlc_groups { const uint32_t *order, *gid, *gstart; uint32_t ngroups; };
+
+struct rlc_shape { /* chosen on the host from n (rlc_shape_for) */
+    uint32_t c;        /* digit bits */
+    uint32_t w1, w2;   /* windows of a 128-bit weight / of a 446-bit scalar */
+    uint32_t seg;      /* min(RLC_SEG, 2^c) buckets per segment */
+    uint32_t segs;     /* segments per window = 2^c / seg */
+    uint32_t nodes;    /* tree nodes per window = ceil(segs / RLC_SEG) */
+};
+static inline rlc_shape rlc_shape_for(size_t n, int force_c) {
+    rlc_shape s;
+    int c = 0;
+    while (c < 31 && ((size_t)2 << c) <= n) c++; /* floor(log2 n) */
+    c -= 5;                                        /* ~32 points per bucket */
+    if (c < 2) c = 2;
+    if (c > RLC_MAX_C) c = RLC_MAX_C;
+    if (force_c > 0) c = force_c;
+    s.c = (uint32_t)c;
+    s.w1 = (RLC_ZBITS + c - 1) / c;
+    s.w2 = (GOLDILOCKS_SCALAR_BITS_ + c - 1) / c;
+    s.seg = (1u << c) < RLC_SEG ? (1u << c) : RLC_SEG;
+    s.segs = (1u << c) / s.seg;
+    s.nodes = (s.segs + RLC_SEG - 1) / RLC_SEG;
+    return s;
+}
+
+GD void rlc_atomic_add(unsigned long long *p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);
+#else
+    __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+#endif
+}
+GD void pt_ld(pt &o, const pt *p) { gf_ld<false>(o.x, &p->x); gf_ld<false>(o.y, &p->y); gf_ld<false>(o.z, &p->z); gf_ld<false>(o.t, &p->t); }
+GD void pt_st(pt *p, const pt &a) { gf_copy(p->x, a.x); gf_copy(p->y, a.y); gf_copy(p->z, a.z); gf_copy(p->t, a.t); }
+GD gmask_t gf_is_zero_mod_p(const gf &a) { gf z; gf_set_zero(z); return gf_eq(a, z); }
+
+// 1) decode: lane j < n: -R_j; lane n + k (k < ngroups): the key of group k; lane n + ngroups: the base point B.
+//    A decoded point with Z = 0 cannot occur for a point of the curve; if one ever shows up the whole call falls back.
+struct LaneRlcDecode {
+    pt *pts; int32_t *ok; uint32_t *force_fallback; const uint8_t *sig, *pk; size_t n; rlc_groups g;
+    GDM void operator()(size_t j) const {
+        pt p;
+        gmask_t good;
+        if (j == n + g.ngroups) {
+            const uint32_t bw[14] = GOLD_CONST_BASE_WORDS;
+            good = pt_decode(p, bw, 0);
+        } else {
+            const uint8_t *enc = j < n ? sig + 114 * j : pk + 57 * (size_t)g.order[g.gstart[j - n]];
+            uint32_t w[15];
+            words_load_bytes(w, 15, enc, 57);
+            good = pt_decode_like_eddsa(p, w, w[14] & 0xff);
+            if (j < n) { pt q; pt_negate(q, p); pt_copy(p, q); }
+        }
+        if (good && gf_is_zero_mod_p(p.z)) *force_fallback = 1u;
+        pt_st(pts + j, p);
+        ok[j] = ST_OK(good);
+    }
+};
+
+// 2) weights: one Keccak-f per 8 signatures: SHAKE256("b200-rlc" || seed32 || le64(l)) -> z_{8l} .. z_{8l+7}, made odd.
+struct LaneRlcZ {
+    uint32_t *z; const uint8_t *seed32; size_t n;
+    GDM void operator()(size_t l) const {
+        shake256_ctx h;
+        shake256_init(h);
+        const uint8_t tag[8] = {'b', '2', '0', '0', '-', 'r', 'l', 'c'};
+        for (int k = 0; k < 8; k++) shake256_absorb_byte(h, tag[k]);
+        for (int k = 0; k < 32; k++) shake256_absorb_byte(h, seed32[k]);
+        for (int k = 0; k < 8; k++) shake256_absorb_byte(h, (uint8_t)((uint64_t)l >> (8 * k)));
+        shake256_finish_absorb(h);
+        for (int e = 0; e < 8; e++) {
+            uint32_t w[RLC_ZWORDS];
+            for (int k = 0; k < RLC_ZWORDS; k++) {
+                uint32_t x = 0;
+                for (int b = 0; b < 4; b++) x |= (uint32_t)shake256_squeeze_byte(h) << (8 * b);
+                w[k] = x;
+            }
+            w[0] |= 1u;
+            const size_t i = 8 * l + e;
+            if (i < n) for (int k = 0; k < RLC_ZWORDS; k++) z[RLC_ZWORDS * i + k] = w[k];
+        }
+    }
+};
+
+// 3) products: lane j = sorted position.  Excluded signatures get weight 0 (no digit, no bucket) and valid = FAILURE.
+struct LaneRlcWeights {
+    uint32_t *z; int32_t *valid; unsigned long long *key_acc, *s_acc; const abi_sc *chal, *resp; const int32_t *ok; size_t n; rlc_groups g;
+    GDM void operator()(size_t j) const {
+        const size_t i = g.order[j], k = g.gid[j] - 1;
+        const bool v = ok[i] && ok[n + k];
+        valid[i] = v ? -1 : 0;
+        if (!v) { for (int q = 0; q < RLC_ZWORDS; q++) z[RLC_ZWORDS * i + q] = 0; return; }
+        sc zi, c, r, zc, zr;
+        sc_set_zero(zi);
+        for (int q = 0; q < RLC_ZWORDS; q++) zi.w[q] = z[RLC_ZWORDS * i + q];
+        sc_from_abi(c, chal + i);
+        sc_from_abi(r, resp + i);
+        sc_mul(zc, zi, c);
+        sc_mul(zr, zi, r);
+        unsigned long long *ka = key_acc + RLC_ACC_WORDS * k, *sa = s_acc + RLC_ACC_WORDS * (j % RLC_SCELLS);
+        for (int q = 0; q < SC_WORDS; q++) { rlc_atomic_add(ka + q, zc.w[q]); rlc_atomic_add(sa + q, zr.w[q]); }
+    }
+};
+
+// 4) per-key scalars: carry-propagate the accumulator cells (an integer below 2^(448 + 32)) and reduce mod q.
+//    lane k < ngroups: key k; lane ngroups: the response sum, scalar of B.
+struct LaneRlcKeyScalars {
+    uint32_t *kscal; const unsigned long long *key_acc, *s_acc; uint32_t ngroups;
+    GDM void operator()(size_t k) const {
+        unsigned long long cell[RLC_ACC_WORDS];
+        if (k < ngroups) {
+            for (int q = 0; q < RLC_ACC_WORDS; q++) cell[q] = key_acc[RLC_ACC_WORDS * k + q];
+        } else {
+            for (int q = 0; q < RLC_ACC_WORDS; q++) cell[q] = 0;
+            for (int s = 0; s < RLC_SCELLS; s++)
+                for (int q = 0; q < RLC_ACC_WORDS; q++) cell[q] += s_acc[RLC_ACC_WORDS * s + q]; /* < 2^10 * 2^52 */
+        }
+        uint32_t w[28]; /* 112 bytes, two 56-byte chunks for sc_decode_long */
+        unsigned long long carry = 0;
+        for (int q = 0; q < 28; q++) {
+            if (q < RLC_ACC_WORDS) carry += cell[q];
+            w[q] = (uint32_t)carry;
+            carry >>= 32;
+        }
+        sc out;
+        ByteAtWords at = {w};
+        sc_decode_long(out, at, 112);
+        for (int q = 0; q < SC_WORDS; q++) kscal[SC_WORDS * k + q] = out.w[q];
+    }
+};
+
+// 5) digits: lane p = point index ([0, n): -R with its 128-bit weight; [n, n + ngroups]: keys and B with 446-bit scalars).
+//    Pair (window << c | digit) -> p; digit 0 goes to the sentinel key (sorted last, ignored).
+GD uint32_t rlc_bits(const uint32_t *w, int nwords, uint32_t pos, uint32_t nbits) {
+    const uint32_t wi = pos >> 5;
+    const uint64_t lo = wi < (uint32_t)nwords ? w[wi] : 0u, hi = wi + 1 < (uint32_t)nwords ? w[wi + 1] : 0u;
+    return (uint32_t)(((hi << 32) | lo) >> (pos & 31)) & ((1u << nbits) - 1u);
+}
+struct LaneRlcDigits {
+    uint32_t *keys, *vals; const uint32_t *z, *kscal; size_t n; rlc_shape sh;
+    GDM void operator()(size_t p) const {
+        const bool isr = p < n;
+        const uint32_t *w = isr ? z + RLC_ZWORDS * p : kscal + SC_WORDS * (p - n);
+        const int nw = isr ? RLC_ZWORDS : SC_WORDS;
+        const uint32_t W = isr ? sh.w1 : sh.w2;
+        const size_t off = isr ? p * sh.w1 : n * sh.w1 + (p - n) * sh.w2;
+        const uint32_t sentinel = sh.w2 << sh.c;
+        for (uint32_t k = 0; k < W; k++) {
+            const uint32_t d = rlc_bits(w, nw, k * sh.c, sh.c);
+            keys[off + k] = d ? ((k << sh.c) | d) : sentinel;
+            vals[off + k] = (uint32_t)p;
+        }
+    }
+};
+
+// 6) buckets: lane b = (window << c | digit) adds up the points of its run in the sorted pair list.
+struct LaneRlcBucket {
+    pt *buckets; const uint32_t *keys, *vals; size_t npairs; const pt *pts; rlc_shape sh;
+    GDM void operator()(size_t b) const {
+        pt acc;
+        pt_set_identity(acc);
+        if (b & ((1u << sh.c) - 1u)) {
+            size_t lo = 0, hi = npairs; /* lower bound of key b */
+            while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (keys[mid] < (uint32_t)b) lo = mid + 1; else hi = mid; }
+            bool first = true;
+            for (size_t j = lo; j < npairs && keys[j] == (uint32_t)b; j++) {
+                pt q;
+                pt_ld(q, pts + vals[j]);
+                if (first) { pt_copy(acc, q); first = false; }
+                else { pt r; pt_add(r, acc, q); pt_copy(acc, r); }
+            }
+        }
+        pt_st(buckets + b, acc);
+    }
+};
+
+GD void pt_mul_small(pt &out, const pt &p, uint32_t k) { /* 0 < k < 2^16, public; double-and-add from the top set bit */
+    pt acc, t;
+    pt_copy(acc, p);
+    int bit = 15;
+    while (bit > 0 && !((k >> bit) & 1u)) bit--;
+    for (bit--; bit >= 0; bit--) {
+        pt_double(t, acc, false); pt_copy(acc, t);
+        if ((k >> bit) & 1u) { pt_add(t, acc, p); pt_copy(acc, t); }
+    }
+    pt_copy(out, acc);
+}
+
+// 7) segments: lane s covers buckets [s*seg, (s+1)*seg) of one window (digits base .. base + seg - 1):
+//    out = sum_d d * bucket_d = sum_k k * bucket_{base+k} (running sums from the top) + base * sum_k bucket_{base+k}.
+struct LaneRlcSegments {
+    pt *segsum; const pt *buckets; rlc_shape sh;
+    GDM void operator()(size_t s) const {
+        const uint32_t base = (uint32_t)((s * sh.seg) & ((1u << sh.c) - 1u));
+        const pt *bk = buckets + s * sh.seg;
+        pt run, acc, t, q;
+        pt_set_identity(run);
+        pt_set_identity(acc);
+        for (uint32_t k = sh.seg; k-- > 0;) {
+            pt_ld(q, bk + k);
+            pt_add(t, run, q); pt_copy(run, t);
+            if (k) { pt_add(t, acc, run); pt_copy(acc, t); }
+        }
+        if (base) {
+            pt_mul_small(q, run, base);
+            pt_add(t, acc, q); pt_copy(acc, t);
+        }
+        pt_st(segsum + s, acc);
+    }
+};
+
+// 8) tree: lane (w, node) adds up to RLC_SEG segment sums of window w.
+struct LaneRlcNodes {
+    pt *nodesum; const pt *segsum; rlc_shape sh;
+    GDM void operator()(size_t l) const {
+        const size_t w = l / sh.nodes, node = l % sh.nodes;
+        const size_t lo = node * RLC_SEG, hi = lo + RLC_SEG < sh.segs ? lo + RLC_SEG : sh.segs;
+        pt acc, t, q;
+        pt_ld(acc, segsum + w * sh.segs + lo);
+        for (size_t k = lo + 1; k < hi; k++) { pt_ld(q, segsum + w * sh.segs + k); pt_add(t, acc, q); pt_copy(acc, t); }
+        pt_st(nodesum + l, acc);
+    }
+};
+// 9) windows: lane w adds the nodes of its window and doubles c*w times.
+struct LaneRlcWindows {
+    pt *winsum; const pt *nodesum; rlc_shape sh;
+    GDM void operator()(size_t w) const {
+        pt acc, t, q;
+        pt_ld(acc, nodesum + w * sh.nodes);
+        for (size_t k = 1; k < sh.nodes; k++) { pt_ld(q, nodesum + w * sh.nodes + k); pt_add(t, acc, q); pt_copy(acc, t); }
+        const uint32_t dbl = (uint32_t)w * sh.c;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (uint32_t k = 0; k < dbl; k++) { pt_double(t, acc, false); pt_copy(acc, t); }
+        pt_st(winsum + w, acc);
+    }
+};
+// 10) verdict: one lane adds the window sums; the equation holds iff the total is the identity of the quotient group
+//     (point_eq against (0, 1): X == 0, goldilocks.c:644-653) and nothing asked for the fallback.
+struct LaneRlcVerdict {
+    uint32_t *verdict; const pt *winsum; const uint32_t *force_fallback; rlc_shape sh;
+    GDM void operator()(size_t) const {
+        pt acc, t, q, id;
+        pt_ld(acc, winsum);
+        for (uint32_t w = 1; w < sh.w2; w++) { pt_ld(q, winsum + w); pt_add(t, acc, q); pt_copy(acc, t); }
+        pt_set_identity(id);
+        const gmask_t same = pt_eq(acc, id) & ~gf_is_zero_mod_p(acc.z);
+        *verdict = (same && !*force_fallback) ? 1u : 0u;
+    }
+};

@@ -19,5 +19,12 @@ struct verify_plan {
 // Bytes of device scratch group_keys() needs for n signatures and at most `cap` key tables.
 size_t group_scratch_bytes(size_t n, size_t cap);
 // Enqueues the grouping pass on `s`; `plan` receives pointers into `scratch`.  No host synchronisation.
+// Every distinct key of a batch (k_group.cu group_keys_all): the view the random-linear-combination path works from.
+struct key_groups { const uint32_t *order, *gid, *gstart, *ngroups; };
+size_t group_all_scratch_bytes(size_t n);
+cudaError_t group_keys_all(const uint8_t *pk, size_t n, void *scratch, key_groups *out, cudaStream_t s, uint64_t *launches);
+size_t pair_sort_scratch_bytes(size_t npairs);
+cudaError_t pair_sort(void *tmp, size_t tmp_bytes, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in, uint32_t *vals_out, size_t npairs,
+                      int key_bits, cudaStream_t s);
 cudaError_t group_keys(const uint8_t *pk, size_t n, uint32_t cap, void *scratch, verify_plan *plan, cudaStream_t s, uint64_t *launches);
 #endif

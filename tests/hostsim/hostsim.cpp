@@ -239,3 +239,67 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     run(fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH);
     return -1;
 }
+
+// ---- random-linear-combination batch verification (csrc/rlc.cuh): the same lane functors, host orchestration ----------
+// `force_c` > 0 overrides the digit width so small batches exercise several bucket shapes; `seed32` makes the weights
+// reproducible in tests (the product draws them from getrandom()).
+#include <algorithm>
+#include "../../libgoldilocks_b200/csrc/rlc.cuh"
+static int g_rlc_force_c = 0;
+static uint8_t g_rlc_seed[32] = {1, 2, 3};
+EXPORT void hostsim_rlc_config(int force_c, const uint8_t *seed32) { g_rlc_force_c = force_c; if (seed32) memcpy(g_rlc_seed, seed32, 32); }
+EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off,
+                                                 uint8_t prehashed, const uint8_t *ctx, uint8_t ctx_len, size_t n, int *fast_path) {
+    if (fast_path) *fast_path = 0;
+    if (n == 0) return -1;
+    /* key groups, as k_group.cu group_keys_all leaves them */
+    std::map<std::string, std::vector<uint32_t>> groups;
+    for (size_t i = 0; i < n; i++) groups[std::string((const char *)pk + 57 * i, 57)].push_back((uint32_t)i);
+    std::vector<uint32_t> order, gid, gstart;
+    for (auto &g : groups) {
+        gstart.push_back((uint32_t)order.size());
+        for (uint32_t i : g.second) { order.push_back(i); gid.push_back((uint32_t)gstart.size()); }
+    }
+    const uint32_t m = (uint32_t)gstart.size();
+    gstart.push_back((uint32_t)n);
+    const rlc_groups g = {order.data(), gid.data(), gstart.data(), m};
+    const rlc_shape sh = rlc_shape_for(n, g_rlc_force_c);
+    const size_t npts = n + m + 1, npairs = n * sh.w1 + ((size_t)m + 1) * sh.w2, nb = (size_t)sh.w2 << sh.c;
+    std::vector<pt> pts(npts), buckets(nb), segsum((size_t)sh.w2 * sh.segs), nodesum((size_t)sh.w2 * sh.nodes), winsum(sh.w2);
+    std::vector<int32_t> ok(npts), valid(n);
+    std::vector<uint32_t> flags(2, 0), z(RLC_ZWORDS * (n + 8)), kscal(SC_WORDS * ((size_t)m + 1)), keys(npairs), vals(npairs);
+    std::vector<abi_sc> chal(n), resp(n);
+    std::vector<unsigned long long> key_acc((size_t)RLC_ACC_WORDS * m, 0), s_acc((size_t)RLC_ACC_WORDS * RLC_SCELLS, 0);
+    LaneRlcDecode f1 = {pts.data(), ok.data(), flags.data(), sig, pk, n, g};
+    run(f1, npts);
+    LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len, 0};
+    run(f2, n);
+    LaneRlcZ f3 = {z.data(), g_rlc_seed, n};
+    run(f3, (n + 7) / 8);
+    LaneRlcWeights f4 = {z.data(), valid.data(), key_acc.data(), s_acc.data(), chal.data(), resp.data(), ok.data(), n, g};
+    run(f4, n);
+    LaneRlcKeyScalars f5 = {kscal.data(), key_acc.data(), s_acc.data(), m};
+    run(f5, (size_t)m + 1);
+    LaneRlcDigits f6 = {keys.data(), vals.data(), z.data(), kscal.data(), n, sh};
+    run(f6, npts);
+    std::vector<std::pair<uint32_t, uint32_t>> pairs(npairs);
+    for (size_t j = 0; j < npairs; j++) pairs[j] = {keys[j], vals[j]};
+    std::stable_sort(pairs.begin(), pairs.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
+    for (size_t j = 0; j < npairs; j++) { keys[j] = pairs[j].first; vals[j] = pairs[j].second; }
+    LaneRlcBucket f7 = {buckets.data(), keys.data(), vals.data(), npairs, pts.data(), sh};
+    run(f7, nb);
+    LaneRlcSegments f8 = {segsum.data(), buckets.data(), sh};
+    run(f8, (size_t)sh.w2 * sh.segs);
+    LaneRlcNodes f9 = {nodesum.data(), segsum.data(), sh};
+    run(f9, (size_t)sh.w2 * sh.nodes);
+    LaneRlcWindows f10 = {winsum.data(), nodesum.data(), sh};
+    run(f10, sh.w2);
+    LaneRlcVerdict f11 = {flags.data() + 1, winsum.data(), flags.data(), sh};
+    run(f11, 1);
+    if (flags[1]) {
+        if (fast_path) *fast_path = 1;
+        for (size_t i = 0; i < n; i++) st[i] = valid[i];
+        return -1;
+    }
+    return goldilocks_ed448_verify_batch(st, sig, pk, msg, off, prehashed, ctx, ctx_len, n);
+}

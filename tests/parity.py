@@ -443,7 +443,87 @@ def check_eddsa_adversarial(lib, chk, copies=3):
             eq(lib.ed448_verify_keyset(h, kidx.reshape(-1), sig, msgs), want, "ed448_verify_keyset status, hand-made corner cases")
         finally:
             lib.keyset_destroy(h)
+    if lib.has("goldilocks_ed448_verify_rlc_batch"):
+        check_eddsa_rlc_adversarial(lib, chk, sig, pk, msgs, want)
     return want
+
+
+def check_eddsa_rlc(lib, chk, n, label="c4r", per_key=(1, 2, 3, 16, 5, 1, 40)):
+    """Random-linear-combination batch verification (goldilocks_ed448_verify_rlc_batch): statuses must
+    be the reference's per-signature verdicts, whichever way the call went.
+    (a) all signatures valid, repeated keys, S + q mixed in (the reference accepts it): the batch equation must decide
+        (fast = 1);
+    (b) the same batch with some R / public keys made undecodable: rejected up front, the equation still decides the rest;
+    (c) one signature with a wrong S, one with a flipped message bit, one with a decodable but wrong R: the equation must
+        fail and the per-signature fallback must find exactly those;
+    (d) hand-made torsion / small-order corner cases: whatever the reference says."""
+    mult = []
+    while sum(mult) < n:
+        mult.append(per_key[len(mult) % len(per_key)])
+    nk = len(mult)
+    key_of = np.repeat(np.arange(nk), mult)[:n]
+    sk = stream_bytes(label + "/sk", nk * 57).reshape(nk, 57)
+    pk_k = chk.ed448_derive_public_key(sk)
+    lens = stream_bytes(label + "/len", n).astype(np.int64) % 70
+    blob = stream_bytes(label + "/msg", int(lens.sum()) + 1)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    msgs = [bytes(blob[offs[i]:offs[i + 1]]) for i in range(n)]
+    pk = pk_k[key_of].copy()
+    sig = chk.ed448_sign(sk[key_of], pk, msgs)
+    for i in range(5, n, 9):
+        sig[i, 57:114] = le(util.from_le(sig[i, 57:114]) + util.Q, 57)
+    perm = np.argsort(stream_bytes(label + "/perm", 4 * n).view("<u4")[:n], kind="stable")
+    sig, pk, msgs = sig[perm], pk[perm], [msgs[i] for i in perm]
+    # (a)
+    want = chk.ed448_verify(sig, pk, msgs)
+    assert (want == -1).all()
+    got, fast = lib.ed448_verify_rlc(sig, pk, msgs)
+    eq(got, want, "ed448_verify_rlc status, all valid")
+    assert fast == 1, "an all-valid batch must be decided by the batch equation"
+    # (b)
+    sig_b, pk_b = sig.copy(), pk.copy()
+    sig_b[3, :57] = le(1, 57)            # R: y = 1, the decoder refuses
+    sig_b[10, :57] = le(P + 2, 57)       # R: non-canonical y
+    pk_b[17] = le(1, 57)                 # A undecodable (its whole group when the key repeats)
+    sig_b[20, 56] |= 0x01                # stray bit in the last byte of R
+    want = chk.ed448_verify(sig_b, pk_b, msgs)
+    assert (want[[3, 10, 17, 20]] == 0).all()
+    got, fast = lib.ed448_verify_rlc(sig_b, pk_b, msgs)
+    eq(got, want, "ed448_verify_rlc status, undecodable entries")
+    assert (want == 0).sum() == 4
+    assert fast == 1, "undecodable entries are rejected up front; the equation decides the rest"
+    # (c)
+    for kind in range(3):
+        sig_c, msgs_c = sig.copy(), list(msgs)
+        i = 7 + 11 * kind
+        if kind == 0: sig_c[i, 60] ^= 4
+        elif kind == 1: msgs_c[i] = msgs_c[i] + b"x"
+        else: sig_c[i, :57] = sig[(i + 1) % n, :57]       # someone else's R: decodes, does not match
+        want = chk.ed448_verify(sig_c, pk, msgs_c)
+        assert want[i] == 0 and (want == -1).sum() == n - 1
+        got, fast = lib.ed448_verify_rlc(sig_c, pk, msgs_c)
+        eq(got, want, "ed448_verify_rlc status, one bad signature (kind %d)" % kind)
+        assert fast == 0, "a bad signature must fail the batch equation"
+    # contexts and prehash flag go through the same challenge hash
+    m = min(n, 80)
+    s1 = chk.ed448_sign(sk[key_of[perm][:m]], pk[:m], msgs[:m], True, b"rlc ctx")
+    got, fast = lib.ed448_verify_rlc(s1, pk[:m], msgs[:m], True, b"rlc ctx")
+    eq(got, np.full(m, -1, np.int32), "ed448_verify_rlc with context + prehash flag")
+    if m >= 64: assert fast == 1
+    got, fast = lib.ed448_verify_rlc(s1, pk[:m], msgs[:m])
+    assert (got == 0).all() and fast == 0
+    return want
+
+
+def check_eddsa_rlc_adversarial(lib, chk, sig, pk, msgs, want):
+    """the hand-made corner cases of check_eddsa_adversarial through the RLC entry point"""
+    got, _ = lib.ed448_verify_rlc(sig, pk, msgs)
+    eq(got, want, "ed448_verify_rlc status, hand-made corner cases")
+    ok = np.flatnonzero(want == -1)
+    if len(ok) >= 64:   # the accepted ones alone (torsion on R and A, small-order R): the equation must hold for them
+        got, fast = lib.ed448_verify_rlc(sig[ok], pk[ok], [msgs[i] for i in ok])
+        eq(got, want[ok], "ed448_verify_rlc status, accepted corner cases only")
+        assert fast == 1, "torsion components vanish under the isogeny: the batch equation must hold"
 
 
 def check_shake(lib, n=40):

@@ -90,6 +90,22 @@ def test_eddsa_corner_cases(gpu, chk):
     parity.check_eddsa_adversarial(gpu, chk)
 
 
+def test_eddsa_rlc(gpu, chk):
+    """random-linear-combination batch verification (goldilocks_ed448_verify_rlc_batch): all-valid batches are decided by
+    the batch equation, undecodable entries are rejected up front, a single bad signature sends the call to the
+    per-signature path; digit widths 3 .. 7, one key for the whole batch, all keys distinct, below the threshold"""
+    parity.check_eddsa_rlc(gpu, chk, 1 << 12)
+    parity.check_eddsa_rlc(gpu, chk, 300, label="c4r/small")
+    parity.check_eddsa_rlc(gpu, chk, 1 << 11, label="c4r/one", per_key=(1 << 11,))
+    parity.check_eddsa_rlc(gpu, chk, 1 << 10, label="c4r/distinct", per_key=(1,))
+    sig, pk, msgs, kinds = util.verify_corpus(chk, "c4r/tiny", 40)       # fewer than 64: the ordinary path, fast = 0
+    st, fast = gpu.ed448_verify_rlc(sig, pk, msgs)
+    parity.eq(st, chk.ed448_verify(sig, pk, msgs), "ed448_verify_rlc below the threshold")
+    assert fast == 0
+    st, fast = gpu.ed448_verify_rlc(np.zeros((0, 114), np.uint8), np.zeros((0, 57), np.uint8), [])
+    assert st.shape == (0,)
+
+
 def test_decaf_vectors(gpu, vectors):
     parity.check_decaf_vectors(gpu, vectors)
 
@@ -357,6 +373,31 @@ def test_verify_full(gpu, chk):
     parity.eq(sig[idx[:512]] if False else gpu.ed448_sign(sk_all[idx[:512]], pk_all[idx[:512]] if False else np.repeat(pk, per, axis=0)[idx[:512]],
               (sub[0][: 512 * 32], sub[1][:513])),
               chk.ed448_sign(sk_all[idx[:512]], np.repeat(pk, per, axis=0)[idx[:512]], (sub[0][: 512 * 32], sub[1][:513])), "sign sample vs checker")
+
+
+def test_verify_rlc_full(gpu, chk):
+    """2^20 valid signatures (2^16 keys x 16 messages): the batch equation accepts them all; with one wrong S, one
+    undecodable R and one swapped message among them the statuses are exactly those three rejections"""
+    nk, per = 1 << 16, 16
+    n = nk * per
+    sk = stream_bytes("c4rfull/sk", nk * 57).reshape(nk, 57)
+    pk = gpu.ed448_derive_public_key(sk)
+    sk_all, pk_all = np.repeat(sk, per, axis=0), np.repeat(pk, per, axis=0)
+    arena = stream_bytes("c4rfull/msg", n * 32)
+    off = (np.arange(n + 1, dtype=np.uint64) * 32)
+    sig = gpu.ed448_sign(sk_all, pk_all, (arena, off))
+    st, fast = gpu.ed448_verify_rlc(sig, pk_all, (arena, off))
+    assert fast == 1 and (st == -1).all()
+    sig[777, :57] = util.le(1, 57)                     # undecodable R: rejected up front, the equation still decides
+    st, fast = gpu.ed448_verify_rlc(sig, pk_all, (arena, off))
+    assert fast == 1 and st[777] == 0 and (st == -1).sum() == n - 1
+    sig[123456, 99] ^= 0x10                            # wrong S
+    arena[32 * 999999 + 5] ^= 1                        # another message
+    st, fast = gpu.ed448_verify_rlc(sig, pk_all, (arena, off))
+    assert fast == 0
+    expect = np.full(n, -1, np.int32); expect[[777, 123456, 999999]] = 0
+    parity.eq(st, expect, "verify_rlc statuses over 2^20 after the fallback")
+    parity.eq(st, gpu.ed448_verify(sig, pk_all, (arena, off)), "verify_rlc vs verify over 2^20")
 
 
 def test_codec_roundtrip_large(gpu, chk):

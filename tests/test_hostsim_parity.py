@@ -68,3 +68,13 @@ def test_shake(sim):
 
 def test_widened(sim, chk):
     parity.check_widened(sim, chk, 96)
+
+
+def test_eddsa_rlc(sim, chk):
+    """random-linear-combination batch verification (csrc/rlc.cuh) at several digit widths"""
+    import ctypes
+    _threads(sim, chk)
+    for c in (0, 2, 5, 7):   # 0 = the width the product picks for this n; 7 > log2(32): segments and tree nodes both in play
+        sim.lib.hostsim_rlc_config(ctypes.c_int(c), None)
+        parity.check_eddsa_rlc(sim, chk, 150 if c else 100, label="c4r/%d" % c)
+    sim.lib.hostsim_rlc_config(ctypes.c_int(0), None)

@@ -40,6 +40,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // signatures and messages of a verification cross PCIe here while the main stream groups the keys
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
+    cudaStream_t side_stream = nullptr;   // the latency-bound doubling chain of the key class (rlc.cuh) runs here beside the R-class buckets
+    cudaEvent_t side_evt[4] = {nullptr, nullptr, nullptr, nullptr};
     fixed_tables *ft = nullptr;
     niels *wide = nullptr;       // WIDE_TABLES x 16384-entry verification tables: odd multiples of 2^(45c) B (30 MB, L2 resident)
     std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
@@ -180,6 +182,8 @@ bool ctx_init(Ctx &c, int dev) {
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     for (auto &e : c.copy_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&c.side_stream, cudaStreamNonBlocking));
+    for (auto &e : c.side_evt) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaMalloc(&c.work_counter, 256));
     CU(cudaMalloc(&c.ft, sizeof(fixed_tables)));
     LaneBuildTables f = {c.ft};
@@ -835,20 +839,47 @@ static bool rlc_seed(uint8_t seed[32]) { /* fresh secret weights per call: the s
     return true;
 }
 static bool rlc_usable(size_t n) { return n >= RLC_MIN && n < ((size_t)1 << 26); } /* pair lists are 32-bit, CUB counts are int */
+// One class of points through the bucket method: digits -> radix sort -> buckets -> segments -> tree nodes.  The window
+// sums (the c*w doublings) are a separate launch so that the key class can run its long chain on the side stream.
+struct RlcClass { rlc_shape sh; size_t count, npairs, nb; uint32_t *keys, *vals, *keys_s, *vals_s; void *sort_tmp; size_t sort_bytes; pt *buckets, *segsum, *nodesum, *winsum; };
+static bool rlc_class_alloc(Call &k, RlcClass &q, const rlc_shape &sh, size_t count) {
+    q.sh = sh; q.count = count; q.npairs = count * sh.wn; q.nb = (size_t)sh.wn << sh.c;
+    q.keys = k.out<uint32_t>(q.npairs); q.vals = k.out<uint32_t>(q.npairs); q.keys_s = k.out<uint32_t>(q.npairs); q.vals_s = k.out<uint32_t>(q.npairs);
+    q.sort_bytes = pair_sort_scratch_bytes(q.npairs);
+    q.sort_tmp = k.alloc(q.sort_bytes);
+    q.buckets = k.out<pt>(q.nb); q.segsum = k.out<pt>((size_t)sh.wn * sh.segs); q.nodesum = k.out<pt>((size_t)sh.wn * sh.nodes); q.winsum = k.out<pt>(sh.wn);
+    return k.ok;
+}
+static bool rlc_class_run(Ctx &c, const RlcClass &q, const uint32_t *scal, uint32_t nwords, size_t p0, const pt *recs, cudaStream_t s, bool subtract) {
+    LaneRlcDigits f6 = {q.keys, q.vals, scal, nwords, p0, q.sh};
+    if (!launch(c, f6, q.count, s)) return false;
+    int key_bits = 1;
+    while ((q.sh.wn << q.sh.c) >> key_bits) key_bits++;
+    cudaError_t e = pair_sort(q.sort_tmp, q.sort_bytes, q.keys, q.keys_s, q.vals, q.vals_s, q.npairs, key_bits, s);
+    if (e != cudaSuccess) return fail("pair_sort", e);
+    SlotRlcBucket f7 = {q.buckets, q.keys_s, q.vals_s, q.npairs, recs, q.sh, subtract ? ~0u : 0u};
+    if (!launch_slots(c, f7, q.nb, s)) return false;
+    LaneRlcSegments f8 = {q.segsum, q.buckets, q.sh};
+    if (!launch(c, f8, (size_t)q.sh.wn * q.sh.segs, s)) return false;
+    LaneRlcNodes f9 = {q.nodesum, q.segsum, q.sh};
+    if (!launch(c, f9, (size_t)q.sh.wn * q.sh.nodes, s)) return false;
+    LaneRlcWindows f10 = {q.winsum, q.nodesum, q.sh};
+    return launch(c, f10, q.sh.wn, s);
+}
 static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *dpk, const uint8_t *dmsg, const size_t *doff, uint8_t prehashed,
-                     const uint8_t *dctx, uint8_t ctx_len, size_t n, cudaStream_t s, int *fast) {
+                     const uint8_t *dctx, uint8_t ctx_len, size_t n, cudaStream_t s, int *fast, const VerifyFeed *feed = nullptr) {
     Ctx &c = *k.c;
     *fast = 0;
-    auto ordinary = [&]() {
+    auto ordinary = [&](bool waited) {
         VerifyGrids grids;
         if (!verify_grids(c, &grids)) return false;
         const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
         uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
         void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(n));
         if (!k.ok) return false;
-        return verify_dev(c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, n, scratch, slots, grids, s);
+        return verify_dev(c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, n, scratch, slots, grids, s, waited ? nullptr : feed);
     };
-    if (!rlc_usable(n)) return ordinary();
+    if (!rlc_usable(n)) return ordinary(false);
     uint8_t seed[32];
     if (!rlc_seed(seed)) return false;
     void *gs = k.alloc(group_all_scratch_bytes(n));
@@ -865,8 +896,8 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     CU(cudaStreamSynchronize(s)); /* the number of distinct keys sizes everything below */
     if (m == 0 || m > n) { g_err = "rlc: key grouping returned an impossible group count"; return false; }
     const rlc_groups g = {kg.order, kg.gid, kg.gstart, m};
-    const rlc_shape sh = rlc_shape_for(n, 0);
-    const size_t npts = n + m + 1, npairs = n * sh.w1 + ((size_t)m + 1) * sh.w2, nb = (size_t)sh.w2 << sh.c;
+    const rlc_shape sh_r = rlc_shape_for(n, 0, 0), sh_k = rlc_shape_for((size_t)m + 1, 0, 1);
+    const size_t npts = n + m + 1;
     pt *pts = k.out<pt>(npts);
     int32_t *ok = k.out<int32_t>(npts), *valid = k.out<int32_t>(n);
     uint32_t *flags = k.out<uint32_t>(2); /* [0] force fallback, [1] verdict */
@@ -874,39 +905,45 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     uint32_t *z = k.out<uint32_t>(RLC_ZWORDS * n);
     unsigned long long *key_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * m), *s_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * RLC_SCELLS);
     uint32_t *kscal = k.out<uint32_t>(SC_WORDS * ((size_t)m + 1));
-    uint32_t *keys = k.out<uint32_t>(npairs), *vals = k.out<uint32_t>(npairs), *keys_s = k.out<uint32_t>(npairs), *vals_s = k.out<uint32_t>(npairs);
-    const size_t sort_bytes = pair_sort_scratch_bytes(npairs);
-    void *sort_tmp = k.alloc(sort_bytes);
-    pt *buckets = k.out<pt>(nb), *segsum = k.out<pt>((size_t)sh.w2 * sh.segs), *nodesum = k.out<pt>((size_t)sh.w2 * sh.nodes), *winsum = k.out<pt>(sh.w2);
-    if (!k.ok) return false;
+    RlcClass cr, ck;
+    if (!rlc_class_alloc(k, cr, sh_r, n) || !rlc_class_alloc(k, ck, sh_k, (size_t)m + 1)) return false;
     CU(cudaMemsetAsync(flags, 0, 2 * sizeof(uint32_t), s));
     CU(cudaMemsetAsync(key_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * m, s));
     CU(cudaMemsetAsync(s_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * RLC_SCELLS, s));
-    LaneRlcDecode f1 = {pts, ok, flags, dsig, dpk, n, g};
-    if (!launch(c, f1, npts, s)) return false;
-    LaneEdVerifyScalars f2 = {chal, resp, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, 0};
-    if (!launch(c, f2, n, s)) return false;
-    LaneRlcZ f3 = {z, dseed, n};
-    if (!launch(c, f3, (n + 7) / 8, s)) return false;
+    /* Two streams.  Main: the multiplier-bound work -- key decodes (they need the key bytes only), the R decodes as the two
+     * halves of the copies land, later the R class of the multi-scalar multiplication.  Side: the challenge hashes (ALU work,
+     * it shares the SMs with the decodes) and later the whole key class, whose kernels are short chains of dependent
+     * additions and doublings (latency-bound: up to 446 - c doublings in a row) that would leave the machine idle. */
+    cudaStream_t side = c.side_stream;
+    CU(cudaEventRecord(c.side_evt[0], s));
+    CU(cudaStreamWaitEvent(side, c.side_evt[0], 0)); /* whatever produced the inputs on `s` */
+    LaneRlcDecode fk = {pts, ok, flags, dsig, dpk, n, g, n};
+    if (!launch(c, fk, (size_t)m + 1, s)) return false;
+    const size_t split = feed ? feed->split : n;
+    const size_t lo[2] = {0, split}, hi[2] = {split, n};
+    for (int h = 0; h < 2; h++) {
+        if (feed) { CU(cudaStreamWaitEvent(s, feed->ready[h], 0)); CU(cudaStreamWaitEvent(side, feed->ready[h], 0)); }
+        if (hi[h] == lo[h]) continue;
+        LaneRlcDecode f1 = {pts, ok, flags, dsig, dpk, n, g, lo[h]};
+        if (!launch(c, f1, hi[h] - lo[h], s)) return false;
+        LaneEdVerifyScalars f2 = {chal, resp, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, lo[h]};
+        if (!launch(c, f2, hi[h] - lo[h], side)) return false;
+    }
+    CU(cudaEventRecord(c.side_evt[1], side));
+    LaneRlcZ f3 = {z, dseed, n, sh_r.zbits};
+    if (!launch(c, f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE, s)) return false;
+    CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));
     LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g};
     if (!launch(c, f4, n, s)) return false;
     LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m};
     if (!launch(c, f5, (size_t)m + 1, s)) return false;
-    LaneRlcDigits f6 = {keys, vals, z, kscal, n, sh};
-    if (!launch(c, f6, npts, s)) return false;
-    int key_bits = 1;
-    while ((sh.w2 << sh.c) >> key_bits) key_bits++;
-    e = pair_sort(sort_tmp, sort_bytes, keys, keys_s, vals, vals_s, npairs, key_bits, s);
-    if (e != cudaSuccess) return fail("pair_sort", e);
-    LaneRlcBucket f7 = {buckets, keys_s, vals_s, npairs, pts, sh};
-    if (!launch(c, f7, nb, s)) return false;
-    LaneRlcSegments f8 = {segsum, buckets, sh};
-    if (!launch(c, f8, (size_t)sh.w2 * sh.segs, s)) return false;
-    LaneRlcNodes f9 = {nodesum, segsum, sh};
-    if (!launch(c, f9, (size_t)sh.w2 * sh.nodes, s)) return false;
-    LaneRlcWindows f10 = {winsum, nodesum, sh};
-    if (!launch(c, f10, sh.w2, s)) return false;
-    LaneRlcVerdict f11 = {flags + 1, winsum, flags, sh};
+    CU(cudaEventRecord(c.side_evt[2], s));
+    CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));
+    if (!rlc_class_run(c, ck, kscal, SC_WORDS, n, pts, side, false)) return false;
+    CU(cudaEventRecord(c.side_evt[3], side));
+    if (!rlc_class_run(c, cr, z, RLC_ZWORDS, 0, pts, s, true)) return false;
+    CU(cudaStreamWaitEvent(s, c.side_evt[3], 0));
+    LaneRlcVerdict f11 = {flags + 1, cr.winsum, ck.winsum, flags, cr.sh.wn, ck.sh.wn};
     if (!launch(c, f11, 1, s)) return false;
     uint32_t hflags[2] = {0, 0};
     CU(cudaMemcpyAsync(hflags, flags, sizeof hflags, cudaMemcpyDeviceToHost, s));
@@ -917,21 +954,33 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
         CU(cudaMemcpyAsync(dst, valid, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
         return true;
     }
-    return ordinary();
+    return ordinary(true);
 }
 goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                      uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, int *fast_path) {
+    /* copies as in goldilocks_ed448_verify_batch: keys first on the main stream (the grouping pass needs nothing else), signatures
+     * and messages in two halves on the copy stream */
     Call k;
     int fast = 0;
     size_t total = n ? msg_off[n] : 0;
     const size_t *doff = k.in(msg_off, n + 1);
     const uint8_t *dctx = k.in(context, context_len);
     const uint8_t *dpk = k.in(pubkey, 57 * n);
-    const uint8_t *dsig = k.in(signature, 114 * n);
-    const uint8_t *dmsg = k.in(msg, total);
+    uint8_t *dsig = k.out<uint8_t>(114 * n), *dmsg = k.out<uint8_t>(total);
     int32_t *dst = k.out<int32_t>(n);
-    if (k.ok && n) k.ok = rlc_core(k, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, k.c->stream, &fast);
+    VerifyFeed feed = {n >= 2 * VERIFY_GROUP_MIN ? n / 2 : n, {nullptr, nullptr}};
+    if (k.ok) {
+        feed.ready[0] = k.c->copy_done[0]; feed.ready[1] = k.c->copy_done[1];
+        const size_t lo[2] = {0, feed.split}, hi[2] = {feed.split, n};
+        for (int h = 0; h < 2 && k.ok; h++) {
+            k.push(dsig + 114 * lo[h], signature + 114 * lo[h], 114 * (hi[h] - lo[h]));
+            if (hi[h] > lo[h]) k.push(dmsg + msg_off[lo[h]], msg + msg_off[lo[h]], msg_off[hi[h]] - msg_off[lo[h]]);
+            if (cudaEventRecord(feed.ready[h], k.c->copy_stream) != cudaSuccess) k.ok = false;
+        }
+    }
+    if (k.ok && n) k.ok = rlc_core(k, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, k.c->stream, &fast, &feed);
     k.fetch((int32_t *)status, dst, n);
+    if (!k.ok && k.c) { cudaStreamSynchronize(k.c->copy_stream); cudaStreamSynchronize(k.c->side_stream); }
     if (fast_path) *fast_path = fast;
     return k.finish();
 }
@@ -945,7 +994,7 @@ goldilocks_error_t goldilocks_ed448_verify_rlc_batch_dev(goldilocks_error_t *sta
     if (k.ok && n) {
         if (cudaStreamSynchronize(k.c->stream) != cudaSuccess) k.ok = false; /* arena reuse: nothing of an earlier call may still run */
         if (k.ok) k.ok = rlc_core(k, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, s, &fast);
-        if (k.ok && cudaStreamSynchronize(s) != cudaSuccess) k.ok = false;
+        if (cudaStreamSynchronize(s) != cudaSuccess || cudaStreamSynchronize(k.c->side_stream) != cudaSuccess) k.ok = false;
     }
     if (fast_path) *fast_path = fast;
     return k.finish();

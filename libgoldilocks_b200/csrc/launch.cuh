@@ -42,6 +42,7 @@ template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int va
 template <> struct slot_min_blocks<SlotBaseDoubleScalarmul> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotEdVerifyFinishShared> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotKeyTables> { static constexpr int value = 4; };
+template <> struct slot_min_blocks<SlotRlcBucket> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotKeysetTables> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotEdVerifyFinishKeyset> { static constexpr int value = 4; };
 template <class F>
@@ -88,9 +89,9 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s, un
     X(LaneScDecodeLong) X(LaneScInvert) X(LaneShake256) X(LaneSpongeUpdate) X(LaneSpongeOutput) X(LaneEdPkToX448) X(LaneEdSkToX448) X(LanePrecompute) X(LaneNielsFromAbi)                                                             \
     X(LaneEdSecretScalar) X(LaneEdSignExpand) X(LaneEdSignNonce) X(LaneEdSignFinish)   \
     X(LaneEdVerifyDecode) X(LaneEdVerifyScalars) X(LaneVerifySign) X(LaneBuildTables) X(LaneBuildWide) \
-    X(LaneRlcDecode) X(LaneRlcZ) X(LaneRlcWeights) X(LaneRlcKeyScalars) X(LaneRlcDigits) X(LaneRlcBucket) X(LaneRlcSegments) X(LaneRlcNodes) X(LaneRlcWindows) X(LaneRlcVerdict)
+    X(LaneRlcDecode) X(LaneRlcZ) X(LaneRlcWeights) X(LaneRlcKeyScalars) X(LaneRlcDigits) X(LaneRlcSegments) X(LaneRlcNodes) X(LaneRlcWindows) X(LaneRlcVerdict)
 
-#define LANES_SM(X) X(SlotX448) X(SlotComb) X(SlotCombTable) X(SlotX448DerivePk) X(SlotEdDerivePk) X(SlotEdSignR)
+#define LANES_SM(X) X(SlotX448) X(SlotComb) X(SlotCombTable) X(SlotX448DerivePk) X(SlotEdDerivePk) X(SlotEdSignR) X(SlotRlcBucket)
 #define INSTANTIATE_SM(F) template cudaError_t launch_sm<F>(const F &, size_t, cudaStream_t);
 #define DECLARE_SM(F) extern INSTANTIATE_SM(F)
 #define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotEdVerifyFinishShared) X(SlotKeyTables) X(SlotKeysetTables) X(SlotEdVerifyFinishKeyset) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul) X(SlotDualScalarmul) X(SlotDirectScalarmul)

@@ -24,9 +24,11 @@
 // Everything below is a per-lane functor (host/device clean: tests/hostsim runs the same code on the CPU tier).
 #pragma once
 #include "lanes.cuh"
+#include "slot_algos.cuh"
 
-#define RLC_ZWORDS 4          /* 128-bit weights */
+#define RLC_ZWORDS 5          /* weights: w1 * c bits, 128 <= bits < 143, so that every window of a weight is a full one */
 #define RLC_ZBITS 128
+#define RLC_Z_PER_LANE 6      /* weights per Keccak-f: 6 x 20 bytes of one 136-byte block */
 #define RLC_SEG 32            /* buckets per running-sum segment, segments per tree node */
 #define RLC_SCELLS 1024       /* accumulator cells of the response sum (spreads the atomics) */
 #define RLC_ACC_WORDS 14      /* one 64-bit cell per 32-bit scalar word: sums of up to 2^32 words never overflow */
@@ -36,27 +38,35 @@
 // of that position, gstart[g] = first sorted position of group g.
 struct rlc_groups { const uint32_t *order, *gid, *gstart; uint32_t ngroups; };
 
-struct rlc_shape { /* chosen on the host from n (rlc_shape_for) */
+struct rlc_shape { /* one per class of points, chosen on the host from n (rlc_shape_for) */
     uint32_t c;        /* digit bits */
-    uint32_t w1, w2;   /* windows of a 128-bit weight / of a 446-bit scalar */
+    uint32_t wn;       /* windows of this class: ceil(128 / c) for the weights of the R points, ceil(446 / c) for keys and B */
     uint32_t seg;      /* min(RLC_SEG, 2^c) buckets per segment */
     uint32_t segs;     /* segments per window = 2^c / seg */
     uint32_t nodes;    /* tree nodes per window = ceil(segs / RLC_SEG) */
+    uint32_t zbits;    /* bits of a weight: ceil(128 / c) * c, so that every window of a weight is a full one */
+    uint32_t top;      /* index of the one window with fewer than c bits (the last window of a 446-bit scalar), or ~0 */
+    uint32_t top_shift; /* that window holds r = 446 - top * c bits: its 2^r digits get 2^(c - r) sub-buckets each (picked by the low
+                         * bits of the point index), so that no bucket of it is longer than the others' */
 };
-static inline rlc_shape rlc_shape_for(size_t n, int force_c) {
+// is_key = 0: the n points -R_i with their weights; 1: the keys and B with 446-bit scalars.  Each class picks its digit
+// width from its own number of points (about 32 points per bucket).
+static inline rlc_shape rlc_shape_for(size_t count, int force_c, int is_key) {
     rlc_shape s;
     int c = 0;
-    while (c < 31 && ((size_t)2 << c) <= n) c++; /* floor(log2 n) */
-    c -= 5;                                        /* ~32 points per bucket */
+    while (c < 31 && ((size_t)2 << c) <= count) c++; /* floor(log2 count) */
+    c -= 5;
     if (c < 2) c = 2;
     if (c > RLC_MAX_C) c = RLC_MAX_C;
     if (force_c > 0) c = force_c;
     s.c = (uint32_t)c;
-    s.w1 = (RLC_ZBITS + c - 1) / c;
-    s.w2 = (GOLDILOCKS_SCALAR_BITS_ + c - 1) / c;
+    s.zbits = ((RLC_ZBITS + c - 1) / c) * c;
+    s.wn = is_key ? (GOLDILOCKS_SCALAR_BITS_ + c - 1) / c : s.zbits / c;
     s.seg = (1u << c) < RLC_SEG ? (1u << c) : RLC_SEG;
     s.segs = (1u << c) / s.seg;
     s.nodes = (s.segs + RLC_SEG - 1) / RLC_SEG;
+    s.top = is_key ? s.wn - 1 : ~0u;
+    s.top_shift = is_key ? s.wn * s.c - GOLDILOCKS_SCALAR_BITS_ : 0u;
     return s;
 }
 
@@ -71,11 +81,13 @@ GD void pt_ld(pt &o, const pt *p) { gf_ld<false>(o.x, &p->x); gf_ld<false>(o.y, 
 GD void pt_st(pt *p, const pt &a) { gf_copy(p->x, a.x); gf_copy(p->y, a.y); gf_copy(p->z, a.z); gf_copy(p->t, a.t); }
 GD gmask_t gf_is_zero_mod_p(const gf &a) { gf z; gf_set_zero(z); return gf_eq(a, z); }
 
-// 1) decode: lane j < n: -R_j; lane n + k (k < ngroups): the key of group k; lane n + ngroups: the base point B.
+// 1) decode: lane j < n: R_j; lane n + k (k < ngroups): the key of group k; lane n + ngroups: the base point B.
+//    (`lane0` = first lane of this launch: the R halves follow the copies, the keys go first.)
 //    A decoded point with Z = 0 cannot occur for a point of the curve; if one ever shows up the whole call falls back.
 struct LaneRlcDecode {
-    pt *pts; int32_t *ok; uint32_t *force_fallback; const uint8_t *sig, *pk; size_t n; rlc_groups g;
-    GDM void operator()(size_t j) const {
+    pt *pts; int32_t *ok; uint32_t *force_fallback; const uint8_t *sig, *pk; size_t n; rlc_groups g; size_t lane0;
+    GDM void operator()(size_t j0) const {
+        const size_t j = j0 + lane0;
         pt p;
         gmask_t good;
         if (j == n + g.ngroups) {
@@ -86,17 +98,23 @@ struct LaneRlcDecode {
             uint32_t w[15];
             words_load_bytes(w, 15, enc, 57);
             good = pt_decode_like_eddsa(p, w, w[14] & 0xff);
-            if (j < n) { pt q; pt_negate(q, p); pt_copy(p, q); }
         }
         if (good && gf_is_zero_mod_p(p.z)) *force_fallback = 1u;
-        pt_st(pts + j, p);
+        /* every point is stored as the projective-niels record the slot machine adds from (slot_algos.cuh
+         * s_pt_to_pniels_negc_g): (y - x, y + x, -2 d' t, 2 z); the bucket kernel SUBTRACTS the R records */
+        pt rec;
+        gf_sub(rec.x, p.y, p.x);
+        gf_add_nr(rec.y, p.y, p.x);
+        gf_mulw(rec.z, p.t, (uint32_t)(-2 * GOLD_TWISTED_D));
+        gf_add_nr(rec.t, p.z, p.z);
+        pt_st(pts + j, rec);
         ok[j] = ST_OK(good);
     }
 };
 
-// 2) weights: one Keccak-f per 8 signatures: SHAKE256("b200-rlc" || seed32 || le64(l)) -> z_{8l} .. z_{8l+7}, made odd.
+// 2) weights: one Keccak-f per 6 signatures: SHAKE256("b200-rlc" || seed32 || le64(l)) -> z_{6l} .. z_{6l+5}, cut to zbits, made odd.
 struct LaneRlcZ {
-    uint32_t *z; const uint8_t *seed32; size_t n;
+    uint32_t *z; const uint8_t *seed32; size_t n; uint32_t zbits;
     GDM void operator()(size_t l) const {
         shake256_ctx h;
         shake256_init(h);
@@ -105,15 +123,18 @@ struct LaneRlcZ {
         for (int k = 0; k < 32; k++) shake256_absorb_byte(h, seed32[k]);
         for (int k = 0; k < 8; k++) shake256_absorb_byte(h, (uint8_t)((uint64_t)l >> (8 * k)));
         shake256_finish_absorb(h);
-        for (int e = 0; e < 8; e++) {
+        for (int e = 0; e < RLC_Z_PER_LANE; e++) {
             uint32_t w[RLC_ZWORDS];
             for (int k = 0; k < RLC_ZWORDS; k++) {
                 uint32_t x = 0;
                 for (int b = 0; b < 4; b++) x |= (uint32_t)shake256_squeeze_byte(h) << (8 * b);
+                const int lo = 32 * k; /* keep bits [0, zbits) */
+                if ((int)zbits <= lo) x = 0;
+                else if ((int)zbits < lo + 32) x &= (1u << (zbits - lo)) - 1u;
                 w[k] = x;
             }
             w[0] |= 1u;
-            const size_t i = 8 * l + e;
+            const size_t i = RLC_Z_PER_LANE * l + e;
             if (i < n) for (int k = 0; k < RLC_ZWORDS; k++) z[RLC_ZWORDS * i + k] = w[k];
         }
     }
@@ -167,47 +188,54 @@ struct LaneRlcKeyScalars {
 };
 
 // 5) digits: lane p = point index ([0, n): -R with its 128-bit weight; [n, n + ngroups]: keys and B with 446-bit scalars).
-//    Pair (window << c | digit) -> p; digit 0 goes to the sentinel key (sorted last, ignored).
+//    Pair (window << c | digit) -> p; digit 0 goes to the sentinel key (sorted last, ignored).  One pair list per class.
 GD uint32_t rlc_bits(const uint32_t *w, int nwords, uint32_t pos, uint32_t nbits) {
     const uint32_t wi = pos >> 5;
     const uint64_t lo = wi < (uint32_t)nwords ? w[wi] : 0u, hi = wi + 1 < (uint32_t)nwords ? w[wi + 1] : 0u;
     return (uint32_t)(((hi << 32) | lo) >> (pos & 31)) & ((1u << nbits) - 1u);
 }
-struct LaneRlcDigits {
-    uint32_t *keys, *vals; const uint32_t *z, *kscal; size_t n; rlc_shape sh;
-    GDM void operator()(size_t p) const {
-        const bool isr = p < n;
-        const uint32_t *w = isr ? z + RLC_ZWORDS * p : kscal + SC_WORDS * (p - n);
-        const int nw = isr ? RLC_ZWORDS : SC_WORDS;
-        const uint32_t W = isr ? sh.w1 : sh.w2;
-        const size_t off = isr ? p * sh.w1 : n * sh.w1 + (p - n) * sh.w2;
-        const uint32_t sentinel = sh.w2 << sh.c;
-        for (uint32_t k = 0; k < W; k++) {
-            const uint32_t d = rlc_bits(w, nw, k * sh.c, sh.c);
+struct LaneRlcDigits { /* lane l = l-th point of the class: point index p0 + l, scalar = nwords words at scal + nwords * l */
+    uint32_t *keys, *vals; const uint32_t *scal; uint32_t nwords; size_t p0; rlc_shape sh;
+    GDM void operator()(size_t l) const {
+        const uint32_t *w = scal + (size_t)nwords * l;
+        const size_t off = l * sh.wn;
+        const uint32_t sentinel = sh.wn << sh.c, p = (uint32_t)(p0 + l);
+        for (uint32_t k = 0; k < sh.wn; k++) {
+            uint32_t d = rlc_bits(w, (int)nwords, k * sh.c, sh.c);
+            if (d && k == sh.top) d = (d << sh.top_shift) | ((uint32_t)l & ((1u << sh.top_shift) - 1u)); /* sub-bucket */
             keys[off + k] = d ? ((k << sh.c) | d) : sentinel;
-            vals[off + k] = (uint32_t)p;
+            vals[off + k] = p;
         }
     }
 };
 
-// 6) buckets: lane b = (window << c | digit) adds up the points of its run in the sorted pair list.
-struct LaneRlcBucket {
-    pt *buckets; const uint32_t *keys, *vals; size_t npairs; const pt *pts; rlc_shape sh;
-    GDM void operator()(size_t b) const {
-        pt acc;
-        pt_set_identity(acc);
-        if (b & ((1u << sh.c) - 1u)) {
-            size_t lo = 0, hi = npairs; /* lower bound of key b */
+GD uint32_t rlc_bucket_digit(size_t b, const rlc_shape &sh) {
+    const uint32_t low = (uint32_t)b & ((1u << sh.c) - 1u);
+    return (b >> sh.c) == sh.top ? (low >> sh.top_shift) : low;
+}
+// 6) buckets: lane b = (window << c | digit) adds up (or, for the R class, subtracts) the points of its run in the sorted
+//    pair list, on the slot machine (slots.cuh): accumulator in shared-memory slots, each point taken straight from its
+//    projective-niels record in global memory (8M per point, no by-value calls).
+struct SlotRlcBucket {
+    static constexpr int NSLOTS = 7;
+    pt *buckets; const uint32_t *keys, *vals; size_t npairs; const pt *recs; rlc_shape sh; gmask_t subtract;
+    GDM void operator()(size_t b, sref sb, bool live) const {
+        const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+        const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+        s_pt_set_identity(p);
+        if (!live) return;
+        if (rlc_bucket_digit(b, sh)) {
+            size_t lo = 0, hi = npairs;
             while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (keys[mid] < (uint32_t)b) lo = mid + 1; else hi = mid; }
-            bool first = true;
             for (size_t j = lo; j < npairs && keys[j] == (uint32_t)b; j++) {
-                pt q;
-                pt_ld(q, pts + vals[j]);
-                if (first) { pt_copy(acc, q); first = false; }
-                else { pt r; pt_add(r, acc, q); pt_copy(acc, r); }
+                wtab<1> t;
+                t.base = reinterpret_cast<uint4 *>(const_cast<pt *>(recs + vals[j]));
+                s_pt_add_pniels_g<1>(p, w, t, 0, subtract, ~subtract, false); /* minus the point: swap (a, b), keep the stored -c */
             }
         }
-        pt_st(buckets + b, acc);
+        pt out;
+        s_ld(out.x, p.x); s_ld(out.y, p.y); s_ld(out.z, p.z); s_ld(out.t, p.t);
+        pt_st(buckets + b, out);
     }
 };
 
@@ -223,12 +251,15 @@ GD void pt_mul_small(pt &out, const pt &p, uint32_t k) { /* 0 < k < 2^16, public
     pt_copy(out, acc);
 }
 
-// 7) segments: lane s covers buckets [s*seg, (s+1)*seg) of one window (digits base .. base + seg - 1):
-//    out = sum_d d * bucket_d = sum_k k * bucket_{base+k} (running sums from the top) + base * sum_k bucket_{base+k}.
+// 7) segments: lane s covers buckets [s*seg, (s+1)*seg) of one window.  Bucket `low` of a window carries the digit
+//    d(low) = low >> shift (shift = top_shift in the last window, else 0), so
+//    out = sum_k d(base+k) * bucket_{base+k} = d(base) * sum_k bucket_{base+k} + sum over the k at which d steps up of
+//    (sum_{k' >= k} bucket_{base+k'})  -- running sums from the top.
 struct LaneRlcSegments {
     pt *segsum; const pt *buckets; rlc_shape sh;
     GDM void operator()(size_t s) const {
         const uint32_t base = (uint32_t)((s * sh.seg) & ((1u << sh.c) - 1u));
+        const uint32_t shift = ((s * sh.seg) >> sh.c) == sh.top ? sh.top_shift : 0u;
         const pt *bk = buckets + s * sh.seg;
         pt run, acc, t, q;
         pt_set_identity(run);
@@ -236,10 +267,10 @@ struct LaneRlcSegments {
         for (uint32_t k = sh.seg; k-- > 0;) {
             pt_ld(q, bk + k);
             pt_add(t, run, q); pt_copy(run, t);
-            if (k) { pt_add(t, acc, run); pt_copy(acc, t); }
+            if (k && ((base + k) >> shift) != ((base + k - 1) >> shift)) { pt_add(t, acc, run); pt_copy(acc, t); }
         }
-        if (base) {
-            pt_mul_small(q, run, base);
+        if (base >> shift) {
+            pt_mul_small(q, run, base >> shift);
             pt_add(t, acc, q); pt_copy(acc, t);
         }
         pt_st(segsum + s, acc);
@@ -273,14 +304,15 @@ struct LaneRlcWindows {
         pt_st(winsum + w, acc);
     }
 };
-// 10) verdict: one lane adds the window sums; the equation holds iff the total is the identity of the quotient group
-//     (point_eq against (0, 1): X == 0, goldilocks.c:644-653) and nothing asked for the fallback.
+// 10) verdict: one lane adds the window sums of both classes; the equation holds iff the total is the identity of the
+//     quotient group (point_eq against (0, 1): X == 0, goldilocks.c:644-653) and nothing asked for the fallback.
 struct LaneRlcVerdict {
-    uint32_t *verdict; const pt *winsum; const uint32_t *force_fallback; rlc_shape sh;
+    uint32_t *verdict; const pt *win_r, *win_k; const uint32_t *force_fallback; uint32_t wn_r, wn_k;
     GDM void operator()(size_t) const {
         pt acc, t, q, id;
-        pt_ld(acc, winsum);
-        for (uint32_t w = 1; w < sh.w2; w++) { pt_ld(q, winsum + w); pt_add(t, acc, q); pt_copy(acc, t); }
+        pt_ld(acc, win_r);
+        for (uint32_t w = 1; w < wn_r; w++) { pt_ld(q, win_r + w); pt_add(t, acc, q); pt_copy(acc, t); }
+        for (uint32_t w = 0; w < wn_k; w++) { pt_ld(q, win_k + w); pt_add(t, acc, q); pt_copy(acc, t); }
         pt_set_identity(id);
         const gmask_t same = pt_eq(acc, id) & ~gf_is_zero_mod_p(acc.z);
         *verdict = (same && !*force_fallback) ? 1u : 0u;

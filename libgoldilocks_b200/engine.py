@@ -82,6 +82,14 @@ class DeviceEngine:
         self._call("goldilocks_ed448_verify_batch_dev", self._p(status), self._p(sig), self._p(pk), self._p(msg), self._p(msg_off),
                    C.c_uint8(prehashed), self._p(ctx), C.c_uint8(ctx_len), _Z(n), self._p(scratch), self._stream())
 
+    def ed448_verify_rlc(self, status, sig, pk, msg, msg_off, prehashed=0, ctx=None, ctx_len=0):
+        """random-linear-combination fast path (goldilocks_ed448_verify_rlc_batch_dev); returns 1 when the batch equation
+        decided the call, 0 when it fell back to the per-signature path.  Synchronises the current stream."""
+        fast = C.c_int(0)
+        self._call("goldilocks_ed448_verify_rlc_batch_dev", self._p(status), self._p(sig), self._p(pk), self._p(msg), self._p(msg_off),
+                   C.c_uint8(prehashed), self._p(ctx), C.c_uint8(ctx_len), _Z(status.numel()), self._stream(), C.byref(fast))
+        return fast.value
+
     def x448(self, out, status, base, scalar):
         self._call("goldilocks_x448_batch_dev", self._p(out), self._p(status), self._p(base), self._p(scalar), _Z(status.numel()), self._stream())
 

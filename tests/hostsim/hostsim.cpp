@@ -263,38 +263,49 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
     const uint32_t m = (uint32_t)gstart.size();
     gstart.push_back((uint32_t)n);
     const rlc_groups g = {order.data(), gid.data(), gstart.data(), m};
-    const rlc_shape sh = rlc_shape_for(n, g_rlc_force_c);
-    const size_t npts = n + m + 1, npairs = n * sh.w1 + ((size_t)m + 1) * sh.w2, nb = (size_t)sh.w2 << sh.c;
-    std::vector<pt> pts(npts), buckets(nb), segsum((size_t)sh.w2 * sh.segs), nodesum((size_t)sh.w2 * sh.nodes), winsum(sh.w2);
+    const rlc_shape sh_r = rlc_shape_for(n, g_rlc_force_c, 0), sh_k = rlc_shape_for((size_t)m + 1, g_rlc_force_c ? g_rlc_force_c + 1 : 0, 1);
+    const size_t npts = n + m + 1;
+    std::vector<pt> pts(npts);
     std::vector<int32_t> ok(npts), valid(n);
-    std::vector<uint32_t> flags(2, 0), z(RLC_ZWORDS * (n + 8)), kscal(SC_WORDS * ((size_t)m + 1)), keys(npairs), vals(npairs);
+    std::vector<uint32_t> flags(2, 0), z(RLC_ZWORDS * (n + 8)), kscal(SC_WORDS * ((size_t)m + 1));
     std::vector<abi_sc> chal(n), resp(n);
     std::vector<unsigned long long> key_acc((size_t)RLC_ACC_WORDS * m, 0), s_acc((size_t)RLC_ACC_WORDS * RLC_SCELLS, 0);
-    LaneRlcDecode f1 = {pts.data(), ok.data(), flags.data(), sig, pk, n, g};
-    run(f1, npts);
+    LaneRlcDecode fk = {pts.data(), ok.data(), flags.data(), sig, pk, n, g, n};
+    run(fk, (size_t)m + 1);
+    LaneRlcDecode f1 = {pts.data(), ok.data(), flags.data(), sig, pk, n, g, 0};
+    run(f1, n);
     LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len, 0};
     run(f2, n);
-    LaneRlcZ f3 = {z.data(), g_rlc_seed, n};
-    run(f3, (n + 7) / 8);
+    LaneRlcZ f3 = {z.data(), g_rlc_seed, n, sh_r.zbits};
+    run(f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE);
     LaneRlcWeights f4 = {z.data(), valid.data(), key_acc.data(), s_acc.data(), chal.data(), resp.data(), ok.data(), n, g};
     run(f4, n);
     LaneRlcKeyScalars f5 = {kscal.data(), key_acc.data(), s_acc.data(), m};
     run(f5, (size_t)m + 1);
-    LaneRlcDigits f6 = {keys.data(), vals.data(), z.data(), kscal.data(), n, sh};
-    run(f6, npts);
-    std::vector<std::pair<uint32_t, uint32_t>> pairs(npairs);
-    for (size_t j = 0; j < npairs; j++) pairs[j] = {keys[j], vals[j]};
-    std::stable_sort(pairs.begin(), pairs.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
-    for (size_t j = 0; j < npairs; j++) { keys[j] = pairs[j].first; vals[j] = pairs[j].second; }
-    LaneRlcBucket f7 = {buckets.data(), keys.data(), vals.data(), npairs, pts.data(), sh};
-    run(f7, nb);
-    LaneRlcSegments f8 = {segsum.data(), buckets.data(), sh};
-    run(f8, (size_t)sh.w2 * sh.segs);
-    LaneRlcNodes f9 = {nodesum.data(), segsum.data(), sh};
-    run(f9, (size_t)sh.w2 * sh.nodes);
-    LaneRlcWindows f10 = {winsum.data(), nodesum.data(), sh};
-    run(f10, sh.w2);
-    LaneRlcVerdict f11 = {flags.data() + 1, winsum.data(), flags.data(), sh};
+    auto run_class = [&](const rlc_shape &sh, size_t count, const uint32_t *scal, uint32_t nwords, size_t p0, std::vector<pt> &winsum, bool subtract) {
+        const size_t npairs = count * sh.wn, nb = (size_t)sh.wn << sh.c;
+        std::vector<uint32_t> keys(npairs), vals(npairs);
+        std::vector<pt> buckets(nb), segsum((size_t)sh.wn * sh.segs), nodesum((size_t)sh.wn * sh.nodes);
+        winsum.resize(sh.wn);
+        LaneRlcDigits f6 = {keys.data(), vals.data(), scal, nwords, p0, sh};
+        run(f6, count);
+        std::vector<std::pair<uint32_t, uint32_t>> pairs(npairs);
+        for (size_t j = 0; j < npairs; j++) pairs[j] = {keys[j], vals[j]};
+        std::stable_sort(pairs.begin(), pairs.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
+        for (size_t j = 0; j < npairs; j++) { keys[j] = pairs[j].first; vals[j] = pairs[j].second; }
+        SlotRlcBucket f7 = {buckets.data(), keys.data(), vals.data(), npairs, pts.data(), sh, subtract ? ~0u : 0u};
+        run_sm(f7, nb);
+        LaneRlcSegments f8 = {segsum.data(), buckets.data(), sh};
+        run(f8, (size_t)sh.wn * sh.segs);
+        LaneRlcNodes f9 = {nodesum.data(), segsum.data(), sh};
+        run(f9, (size_t)sh.wn * sh.nodes);
+        LaneRlcWindows f10 = {winsum.data(), nodesum.data(), sh};
+        run(f10, sh.wn);
+    };
+    std::vector<pt> win_r, win_k;
+    run_class(sh_k, (size_t)m + 1, kscal.data(), SC_WORDS, n, win_k, false);
+    run_class(sh_r, n, z.data(), RLC_ZWORDS, 0, win_r, true);
+    LaneRlcVerdict f11 = {flags.data() + 1, win_r.data(), win_k.data(), flags.data(), sh_r.wn, sh_k.wn};
     run(f11, 1);
     if (flags[1]) {
         if (fast_path) *fast_path = 1;

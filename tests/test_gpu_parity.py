@@ -106,6 +106,27 @@ def test_eddsa_rlc(gpu, chk):
     assert st.shape == (0,)
 
 
+def test_eddsa_rlc_device_pointers(gpu, chk):
+    """goldilocks_ed448_verify_rlc_batch_dev on torch tensors: same statuses and fast-path flag as the host-pointer call"""
+    import torch
+    from libgoldilocks_b200.engine import DeviceEngine
+    from libgoldilocks_b200.capi import pack_messages
+    eng = DeviceEngine()
+    dev = torch.device("cuda")
+    n = 777
+    sig, pk, msgs, kinds = util.verify_corpus(chk, "c4r/dev", n + 1, corrupt_every=n + 1)   # only entry 0 is corrupted: dropped
+    sig, pk, msgs = sig[1:].copy(), pk[1:].copy(), msgs[1:]
+    arena, off = pack_messages(msgs)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    st = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_sig, d_pk, d_msg, d_off = t(sig.reshape(-1)), t(pk.reshape(-1)), t(arena), t(np.asarray(off).view(np.int64))
+    assert eng.ed448_verify_rlc(st, d_sig, d_pk, d_msg, d_off) == 1
+    assert (st.cpu().numpy() == -1).all()
+    bad = sig.copy(); bad[5, 80] ^= 2
+    assert eng.ed448_verify_rlc(st, t(bad.reshape(-1)), d_pk, d_msg, d_off) == 0
+    parity.eq(st.cpu().numpy(), chk.ed448_verify(bad, pk, msgs), "verify_rlc_batch_dev statuses after the fallback")
+
+
 def test_decaf_vectors(gpu, vectors):
     parity.check_decaf_vectors(gpu, vectors)
 

@@ -300,6 +300,9 @@ GOLDILOCKS_B200_API uint64_t goldilocks_b200_launch_count(void);
  * launch k (e.g. "LaneEdVerifyFinish"), ms[k] = its device time.  Returns the number written. */
 GOLDILOCKS_B200_API void goldilocks_b200_profile(int enable);
 GOLDILOCKS_B200_API size_t goldilocks_b200_profile_read(char *names, float *ms, size_t max);
+/* the same log as a timeline: begin and end of launch k in ms after the begin of the first logged launch (kernels of one
+ * call may run on two streams: goldilocks_ed448_verify_rlc_batch) */
+GOLDILOCKS_B200_API size_t goldilocks_b200_profile_timeline(char *names, float *start_ms, float *end_ms, size_t max);
 /* Copies the device-built fixed-base comb table (80 niels x 3 gf, canonical radix-2^56 limbs =
  * 15360 bytes, the layout of the reference's goldilocks_448_precomputed_base) to `out`. */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_export_comb_table(uint8_t out[15360]);

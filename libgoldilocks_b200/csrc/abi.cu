@@ -182,7 +182,11 @@ bool ctx_init(Ctx &c, int dev) {
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     for (auto &e : c.copy_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CU(cudaStreamCreateWithFlags(&c.side_stream, cudaStreamNonBlocking));
+    {   /* the side stream carries short latency-bound chains next to kernels that fill the machine: its blocks go first */
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&c.side_stream, cudaStreamNonBlocking, prio_hi));
+    }
     for (auto &e : c.side_evt) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaMalloc(&c.work_counter, 256));
     CU(cudaMalloc(&c.ft, sizeof(fixed_tables)));
@@ -346,6 +350,27 @@ size_t goldilocks_b200_profile_read(char *names, float *ms, size_t max) {
         while (*nm >= '0' && *nm <= '9') nm++; /* strip the Itanium length prefix of typeid().name() */
         snprintf(names + 64 * k, 64, "%s", nm);
         ms[k] = t;
+        k++;
+    }
+    return k;
+}
+
+size_t goldilocks_b200_profile_timeline(char *names, float *start_ms, float *end_ms, size_t max) {
+    /* the same log as profile_read(), as a timeline: begin / end of every launch relative to the begin of the first one
+     * (events of different streams compare), for paths that run kernels on more than one stream */
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    size_t k = 0;
+    for (auto &r : g_prof) {
+        if (k >= max) break;
+        float t0 = -1.f, t1 = -1.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess) {
+            if (cudaEventElapsedTime(&t0, g_prof[0].a, r.a) != cudaSuccess) t0 = -1.f;
+            if (cudaEventElapsedTime(&t1, g_prof[0].a, r.b) != cudaSuccess) t1 = -1.f;
+        }
+        const char *nm = r.name;
+        while (*nm >= '0' && *nm <= '9') nm++;
+        snprintf(names + 64 * k, 64, "%s", nm);
+        start_ms[k] = t0; end_ms[k] = t1;
         k++;
     }
     return k;
@@ -850,14 +875,17 @@ static bool rlc_class_alloc(Call &k, RlcClass &q, const rlc_shape &sh, size_t co
     q.buckets = k.out<pt>(q.nb); q.segsum = k.out<pt>((size_t)sh.wn * sh.segs); q.nodesum = k.out<pt>((size_t)sh.wn * sh.nodes); q.winsum = k.out<pt>(sh.wn);
     return k.ok;
 }
-static bool rlc_class_run(Ctx &c, const RlcClass &q, const uint32_t *scal, uint32_t nwords, size_t p0, const pt *recs, cudaStream_t s, bool subtract) {
+static bool rlc_class_pairs(Ctx &c, const RlcClass &q, const uint32_t *scal, uint32_t nwords, size_t p0, cudaStream_t s) { /* digits -> sorted pair list */
     LaneRlcDigits f6 = {q.keys, q.vals, scal, nwords, p0, q.sh};
     if (!launch(c, f6, q.count, s)) return false;
     int key_bits = 1;
     while ((q.sh.wn << q.sh.c) >> key_bits) key_bits++;
     cudaError_t e = pair_sort(q.sort_tmp, q.sort_bytes, q.keys, q.keys_s, q.vals, q.vals_s, q.npairs, key_bits, s);
     if (e != cudaSuccess) return fail("pair_sort", e);
-    SlotRlcBucket f7 = {q.buckets, q.keys_s, q.vals_s, q.npairs, recs, q.sh, subtract ? ~0u : 0u};
+    return true;
+}
+static bool rlc_class_sum(Ctx &c, const RlcClass &q, const pt *recs, cudaStream_t s, bool subtract, const int32_t *valid) { /* buckets -> window sums */
+    SlotRlcBucket f7 = {q.buckets, q.keys_s, q.vals_s, q.npairs, recs, q.sh, subtract ? ~0u : 0u, valid};
     if (!launch_slots(c, f7, q.nb, s)) return false;
     LaneRlcSegments f8 = {q.segsum, q.buckets, q.sh};
     if (!launch(c, f8, (size_t)q.sh.wn * q.sh.segs, s)) return false;
@@ -911,12 +939,16 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     CU(cudaMemsetAsync(key_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * m, s));
     CU(cudaMemsetAsync(s_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * RLC_SCELLS, s));
     /* Two streams.  Main: the multiplier-bound work -- key decodes (they need the key bytes only), the R decodes as the two
-     * halves of the copies land, later the R class of the multi-scalar multiplication.  Side: the challenge hashes (ALU work,
-     * it shares the SMs with the decodes) and later the whole key class, whose kernels are short chains of dependent
-     * additions and doublings (latency-bound: up to 446 - c doublings in a row) that would leave the machine idle. */
+     * halves of the copies land, later the bucket sums of the R class.  Side: what needs no decoded point -- the weights and the
+     * sorted pair list of the R class (they depend on the seed alone; excluded signatures are skipped by the bucket kernel), the
+     * challenge hashes (ALU work, it shares the SMs with the decodes) -- and later the whole key class, whose kernels are
+     * short chains of dependent additions and doublings (latency-bound: up to 446 - c doublings in a row). */
     cudaStream_t side = c.side_stream;
     CU(cudaEventRecord(c.side_evt[0], s));
     CU(cudaStreamWaitEvent(side, c.side_evt[0], 0)); /* whatever produced the inputs on `s` */
+    LaneRlcZ f3 = {z, dseed, n, sh_r.zbits};
+    if (!launch(c, f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE, side)) return false;
+    if (!rlc_class_pairs(c, cr, z, RLC_ZWORDS, 0, side)) return false;
     LaneRlcDecode fk = {pts, ok, flags, dsig, dpk, n, g, n};
     if (!launch(c, fk, (size_t)m + 1, s)) return false;
     const size_t split = feed ? feed->split : n;
@@ -930,8 +962,6 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
         if (!launch(c, f2, hi[h] - lo[h], side)) return false;
     }
     CU(cudaEventRecord(c.side_evt[1], side));
-    LaneRlcZ f3 = {z, dseed, n, sh_r.zbits};
-    if (!launch(c, f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE, s)) return false;
     CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));
     LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g};
     if (!launch(c, f4, n, s)) return false;
@@ -939,9 +969,9 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     if (!launch(c, f5, (size_t)m + 1, s)) return false;
     CU(cudaEventRecord(c.side_evt[2], s));
     CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));
-    if (!rlc_class_run(c, ck, kscal, SC_WORDS, n, pts, side, false)) return false;
+    if (!rlc_class_pairs(c, ck, kscal, SC_WORDS, n, side) || !rlc_class_sum(c, ck, pts, side, false, nullptr)) return false;
     CU(cudaEventRecord(c.side_evt[3], side));
-    if (!rlc_class_run(c, cr, z, RLC_ZWORDS, 0, pts, s, true)) return false;
+    if (!rlc_class_sum(c, cr, pts, s, true, valid)) return false;
     CU(cudaStreamWaitEvent(s, c.side_evt[3], 0));
     LaneRlcVerdict f11 = {flags + 1, cr.winsum, ck.winsum, flags, cr.sh.wn, ck.sh.wn};
     if (!launch(c, f11, 1, s)) return false;

@@ -140,7 +140,7 @@ struct LaneRlcZ {
     }
 };
 
-// 3) products: lane j = sorted position.  Excluded signatures get weight 0 (no digit, no bucket) and valid = FAILURE.
+// 3) products: lane j = sorted position.  Excluded signatures get valid = FAILURE (the bucket kernel skips them) and add nothing to the scalar sums.
 struct LaneRlcWeights {
     uint32_t *z; int32_t *valid; unsigned long long *key_acc, *s_acc; const abi_sc *chal, *resp; const int32_t *ok; size_t n; rlc_groups g;
     GDM void operator()(size_t j) const {
@@ -219,6 +219,7 @@ GD uint32_t rlc_bucket_digit(size_t b, const rlc_shape &sh) {
 struct SlotRlcBucket {
     static constexpr int NSLOTS = 7;
     pt *buckets; const uint32_t *keys, *vals; size_t npairs; const pt *recs; rlc_shape sh; gmask_t subtract;
+    const int32_t *valid; /* R class: the pair list is made before the decodes are in, so excluded signatures are skipped here (null: take all) */
     GDM void operator()(size_t b, sref sb, bool live) const {
         const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
         const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
@@ -228,6 +229,7 @@ struct SlotRlcBucket {
             size_t lo = 0, hi = npairs;
             while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (keys[mid] < (uint32_t)b) lo = mid + 1; else hi = mid; }
             for (size_t j = lo; j < npairs && keys[j] == (uint32_t)b; j++) {
+                if (valid && !valid[vals[j]]) continue;
                 wtab<1> t;
                 t.base = reinterpret_cast<uint4 *>(const_cast<pt *>(recs + vals[j]));
                 s_pt_add_pniels_g<1>(p, w, t, 0, subtract, ~subtract, false); /* minus the point: swap (a, b), keep the stored -c */

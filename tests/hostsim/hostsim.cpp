@@ -278,6 +278,7 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
     run(f2, n);
     LaneRlcZ f3 = {z.data(), g_rlc_seed, n, sh_r.zbits};
     run(f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE);
+    const std::vector<uint32_t> z_for_digits = z; /* the product makes the R pair list before the decodes are in */
     LaneRlcWeights f4 = {z.data(), valid.data(), key_acc.data(), s_acc.data(), chal.data(), resp.data(), ok.data(), n, g};
     run(f4, n);
     LaneRlcKeyScalars f5 = {kscal.data(), key_acc.data(), s_acc.data(), m};
@@ -293,7 +294,7 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
         for (size_t j = 0; j < npairs; j++) pairs[j] = {keys[j], vals[j]};
         std::stable_sort(pairs.begin(), pairs.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
         for (size_t j = 0; j < npairs; j++) { keys[j] = pairs[j].first; vals[j] = pairs[j].second; }
-        SlotRlcBucket f7 = {buckets.data(), keys.data(), vals.data(), npairs, pts.data(), sh, subtract ? ~0u : 0u};
+        SlotRlcBucket f7 = {buckets.data(), keys.data(), vals.data(), npairs, pts.data(), sh, subtract ? ~0u : 0u, subtract ? valid.data() : nullptr};
         run_sm(f7, nb);
         LaneRlcSegments f8 = {segsum.data(), buckets.data(), sh};
         run(f8, (size_t)sh.wn * sh.segs);
@@ -304,7 +305,7 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
     };
     std::vector<pt> win_r, win_k;
     run_class(sh_k, (size_t)m + 1, kscal.data(), SC_WORDS, n, win_k, false);
-    run_class(sh_r, n, z.data(), RLC_ZWORDS, 0, win_r, true);
+    run_class(sh_r, n, z_for_digits.data(), RLC_ZWORDS, 0, win_r, true);
     LaneRlcVerdict f11 = {flags.data() + 1, win_r.data(), win_k.data(), flags.data(), sh_r.wn, sh_k.wn};
     run(f11, 1);
     if (flags[1]) {

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--n", type=int, default=1 << 20)
     ap.add_argument("--per-key", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--timeline", action="store_true")
     a = ap.parse_args()
     lib = g.load()
     n = a.n
@@ -55,6 +56,18 @@ def main():
         per = len(v) // a.reps
         print("  %-22s %s ms" % (nm, " + ".join("%.3f" % (sum(v[j::per]) / a.reps) for j in range(per))))
     print("  sum of kernels %.2f ms" % (sum(sum(v) for v in k.values()) / a.reps))
+    if a.timeline:
+        lib.lib.goldilocks_b200_profile(C.c_int(1))
+        t0 = time.perf_counter()
+        assert fr(*argr) == -1
+        wall = time.perf_counter() - t0
+        lib.lib.goldilocks_b200_profile(C.c_int(0))
+        s0, s1 = (C.c_float * 4096)(), (C.c_float * 4096)()
+        lib.lib.goldilocks_b200_profile_timeline.restype = C.c_size_t
+        cnt = lib.lib.goldilocks_b200_profile_timeline(names, s0, s1, C.c_size_t(4096))
+        print("timeline of one call (wall %.2f ms; ms after the first kernel began):" % (wall * 1e3))
+        for i in range(cnt):
+            print("  %7.3f .. %7.3f  %s" % (s0[i], s1[i], names.raw[64 * i:64 * i + 64].split(b"\0")[0].decode()))
 
 
 if __name__ == "__main__":

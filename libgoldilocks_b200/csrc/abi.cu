@@ -41,7 +41,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;   // signatures and messages of a verification cross PCIe here while the main stream groups the keys
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     cudaStream_t side_stream = nullptr;   // the latency-bound doubling chain of the key class (rlc.cuh) runs here beside the R-class buckets
-    cudaEvent_t side_evt[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t side_evt[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     fixed_tables *ft = nullptr;
     niels *wide = nullptr;       // WIDE_TABLES x 16384-entry verification tables: odd multiples of 2^(45c) B (30 MB, L2 resident)
     std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
@@ -885,6 +885,8 @@ static bool rlc_class_pairs(Ctx &c, const RlcClass &q, const uint32_t *scal, uin
     return true;
 }
 static bool rlc_class_sum(Ctx &c, const RlcClass &q, const pt *recs, cudaStream_t s, bool subtract, const int32_t *valid) { /* buckets -> window sums */
+    /* plain grid, not the persistent shape: blocks retire all the time, so the high-priority blocks of the side stream get onto
+     * the SMs between them (persistent blocks held the SMs and starved the side stream: 22.6 vs 20.9 ms per 2^20) */
     SlotRlcBucket f7 = {q.buckets, q.keys_s, q.vals_s, q.npairs, recs, q.sh, subtract ? ~0u : 0u, valid};
     if (!launch_slots(c, f7, q.nb, s)) return false;
     LaneRlcSegments f8 = {q.segsum, q.buckets, q.sh};
@@ -969,8 +971,11 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     if (!launch(c, f5, (size_t)m + 1, s)) return false;
     CU(cudaEventRecord(c.side_evt[2], s));
     CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));
-    if (!rlc_class_pairs(c, ck, kscal, SC_WORDS, n, side) || !rlc_class_sum(c, ck, pts, side, false, nullptr)) return false;
+    if (!rlc_class_pairs(c, ck, kscal, SC_WORDS, n, side)) return false;
+    CU(cudaEventRecord(c.side_evt[4], side));
+    if (!rlc_class_sum(c, ck, pts, side, false, nullptr)) return false;
     CU(cudaEventRecord(c.side_evt[3], side));
+    CU(cudaStreamWaitEvent(s, c.side_evt[4], 0)); /* the radix sort of the key class wants the whole machine for its 0.3 ms: the R buckets wait for it */
     if (!rlc_class_sum(c, cr, pts, s, true, valid)) return false;
     CU(cudaStreamWaitEvent(s, c.side_evt[3], 0));
     LaneRlcVerdict f11 = {flags + 1, cr.winsum, ck.winsum, flags, cr.sh.wn, ck.sh.wn};

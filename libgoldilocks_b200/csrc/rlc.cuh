@@ -55,7 +55,7 @@ static inline rlc_shape rlc_shape_for(size_t count, int force_c, int is_key) {
     rlc_shape s;
     int c = 0;
     while (c < 31 && ((size_t)2 << c) <= count) c++; /* floor(log2 count) */
-    c -= 5;
+    c -= is_key ? 6 : 5;   /* about 32 points per bucket; 64 for the key class: half the lanes, one wave of the machine beside the R class */
     if (c < 2) c = 2;
     if (c > RLC_MAX_C) c = RLC_MAX_C;
     if (force_c > 0) c = force_c;

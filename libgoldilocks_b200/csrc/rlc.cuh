@@ -15,11 +15,15 @@
 // rejected up front, exactly like the reference (eddsa.c:266-270), and take no part in the sum.  When the equation
 // fails the caller runs the ordinary per-signature path over the batch, so statuses are always per element.
 //
-// The sum is ONE multi-scalar multiplication (bucket method): every scalar is cut into c-bit digits, the pairs
-// (window, digit) -> point are radix-sorted, one lane adds up each bucket, and the buckets of a window are folded with
-// running sums over segments of 32, a two-level tree and c*w doublings per window.  A signature costs its R decode
-// (one inverse square root), ceil(128 / c) point additions and a share of the per-key work, instead of the
-// 90 + 30 additions and 40 doublings of the table path (slot_lanes.cuh SlotEdVerifyFinishShared).
+// The sum is a multi-scalar multiplication by the bucket method, in two classes that share nothing but the final addition:
+// the n points R_i with their weights (135 bits for c = 15: whole windows only) and the distinct keys plus B with 446-bit
+// scalars.  Per class: every scalar is cut into c-bit digits (c from the class's own size: about 32 resp. 64 points per
+// bucket), the pairs (window, digit) -> point are radix-sorted, one lane adds up each bucket on the slot machine
+// (slots.cuh; points are stored as projective-niels records, 8M per addition), and the buckets of a window are folded
+// with running sums over segments of 32, a tree level of 32 and c*w doublings per window.  The short top window of the
+// 446-bit class gets sub-buckets so that no bucket is longer than the rest.  A signature costs its R decode (one inverse
+// square root), ceil(128 / c) = 9 point additions and a share of the per-key work, instead of the 90 + 30 additions and
+// 40 doublings of the table path (slot_lanes.cuh SlotEdVerifyFinishShared).  Scheduling (two streams) is in abi.cu rlc_core.
 //
 // Everything below is a per-lane functor (host/device clean: tests/hostsim runs the same code on the CPU tier).
 #pragma once

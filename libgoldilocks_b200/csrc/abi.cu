@@ -39,7 +39,7 @@ struct Ctx {
     int dev = -1, sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // signatures and messages of a verification cross PCIe here while the main stream groups the keys
-    cudaEvent_t copy_done[2] = {nullptr, nullptr};
+    cudaEvent_t copy_done[3] = {nullptr, nullptr, nullptr};
     cudaStream_t side_stream = nullptr;   // the latency-bound doubling chain of the key class (rlc.cuh) runs here beside the R-class buckets
     cudaEvent_t side_evt[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     fixed_tables *ft = nullptr;
@@ -896,73 +896,84 @@ static bool rlc_class_sum(Ctx &c, const RlcClass &q, const pt *recs, cudaStream_
     LaneRlcWindows f10 = {q.winsum, q.nodesum, q.sh};
     return launch(c, f10, q.sh.wn, s);
 }
+// Host-pointer calls feed the copy stream in the order the work can start in: the first half of the signatures (the R decodes,
+// 55 % of the call, need nothing else), then keys / offsets / context (the grouping pass), then the rest.
+struct RlcFeed { size_t split; cudaEvent_t sig0, keys, rest; };
 static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *dpk, const uint8_t *dmsg, const size_t *doff, uint8_t prehashed,
-                     const uint8_t *dctx, uint8_t ctx_len, size_t n, cudaStream_t s, int *fast, const VerifyFeed *feed = nullptr) {
+                     const uint8_t *dctx, uint8_t ctx_len, size_t n, cudaStream_t s, int *fast, const RlcFeed *feed = nullptr) {
     Ctx &c = *k.c;
     *fast = 0;
-    auto ordinary = [&](bool waited) {
+    auto ordinary = [&]() { /* every copy has been waited for on `s` by the time this runs */
         VerifyGrids grids;
         if (!verify_grids(c, &grids)) return false;
         const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
         uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
         void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(n));
         if (!k.ok) return false;
-        return verify_dev(c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, n, scratch, slots, grids, s, waited ? nullptr : feed);
+        return verify_dev(c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, n, scratch, slots, grids, s);
     };
-    if (!rlc_usable(n)) return ordinary(false);
+    if (!rlc_usable(n)) {
+        if (feed) CU(cudaStreamWaitEvent(s, feed->rest, 0));
+        return ordinary();
+    }
     uint8_t seed[32];
     if (!rlc_seed(seed)) return false;
+    /* everything sized by n alone first: the R decodes start before the number of distinct keys is known */
+    const rlc_shape sh_r = rlc_shape_for(n, 0, 0);
     void *gs = k.alloc(group_all_scratch_bytes(n));
     uint8_t *dseed = k.out<uint8_t>(32);
-    if (!k.ok) return false;
-    key_groups kg;
-    uint64_t launched = 0;
-    cudaError_t e = group_keys_all(dpk, n, gs, &kg, s, &launched);
-    if (e != cudaSuccess) return fail("group_keys_all", e);
-    g_launches += launched;
-    uint32_t m = 0;
-    CU(cudaMemcpyAsync(&m, kg.ngroups, sizeof m, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, s));
-    CU(cudaStreamSynchronize(s)); /* the number of distinct keys sizes everything below */
-    if (m == 0 || m > n) { g_err = "rlc: key grouping returned an impossible group count"; return false; }
-    const rlc_groups g = {kg.order, kg.gid, kg.gstart, m};
-    const rlc_shape sh_r = rlc_shape_for(n, 0, 0), sh_k = rlc_shape_for((size_t)m + 1, 0, 1);
-    const size_t npts = n + m + 1;
-    pt *pts = k.out<pt>(npts);
-    int32_t *ok = k.out<int32_t>(npts), *valid = k.out<int32_t>(n);
-    uint32_t *flags = k.out<uint32_t>(2); /* [0] force fallback, [1] verdict */
+    pt *pts = k.out<pt>(2 * n + 1);                                   /* n R records, then at most n keys, then B */
+    int32_t *ok = k.out<int32_t>(2 * n + 1), *valid = k.out<int32_t>(n);
+    uint32_t *flags = k.out<uint32_t>(2);                             /* [0] force fallback, [1] verdict */
     abi_sc *chal = k.out<abi_sc>(n), *resp = k.out<abi_sc>(n);
     uint32_t *z = k.out<uint32_t>(RLC_ZWORDS * n);
-    unsigned long long *key_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * m), *s_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * RLC_SCELLS);
-    uint32_t *kscal = k.out<uint32_t>(SC_WORDS * ((size_t)m + 1));
+    unsigned long long *s_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * RLC_SCELLS);
     RlcClass cr, ck;
-    if (!rlc_class_alloc(k, cr, sh_r, n) || !rlc_class_alloc(k, ck, sh_k, (size_t)m + 1)) return false;
+    if (!rlc_class_alloc(k, cr, sh_r, n)) return false;
     CU(cudaMemsetAsync(flags, 0, 2 * sizeof(uint32_t), s));
-    CU(cudaMemsetAsync(key_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * m, s));
     CU(cudaMemsetAsync(s_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * RLC_SCELLS, s));
-    /* Two streams.  Main: the multiplier-bound work -- key decodes (they need the key bytes only), the R decodes as the two
-     * halves of the copies land, later the bucket sums of the R class.  Side: what needs no decoded point -- the weights and the
-     * sorted pair list of the R class (they depend on the seed alone; excluded signatures are skipped by the bucket kernel), the
-     * challenge hashes (ALU work, it shares the SMs with the decodes) -- and later the whole key class, whose kernels are
-     * short chains of dependent additions and doublings (latency-bound: up to 446 - c doublings in a row). */
+    CU(cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, s));
+    /* Two streams.  Main: the multiplier-bound work -- the R decodes as the signatures land, later the bucket sums of the R class.
+     * Side (high priority): what needs no decoded R -- the weights and the sorted pair list of the R class (they depend on the
+     * seed alone; excluded signatures are skipped by the bucket kernel), the key grouping and the key decodes, the challenge
+     * hashes (ALU work, it shares the SMs with the decodes) -- and later the whole key class, whose kernels are short chains of
+     * dependent additions and doublings (latency-bound: up to 446 - c doublings in a row). */
     cudaStream_t side = c.side_stream;
     CU(cudaEventRecord(c.side_evt[0], s));
-    CU(cudaStreamWaitEvent(side, c.side_evt[0], 0)); /* whatever produced the inputs on `s` */
+    CU(cudaStreamWaitEvent(side, c.side_evt[0], 0)); /* whatever produced the inputs on `s`, and the seed */
     LaneRlcZ f3 = {z, dseed, n, sh_r.zbits};
     if (!launch(c, f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE, side)) return false;
     if (!rlc_class_pairs(c, cr, z, RLC_ZWORDS, 0, side)) return false;
-    LaneRlcDecode fk = {pts, ok, flags, dsig, dpk, n, g, n};
-    if (!launch(c, fk, (size_t)m + 1, s)) return false;
     const size_t split = feed ? feed->split : n;
     const size_t lo[2] = {0, split}, hi[2] = {split, n};
+    const rlc_groups no_groups = {nullptr, nullptr, nullptr, 0};
     for (int h = 0; h < 2; h++) {
-        if (feed) { CU(cudaStreamWaitEvent(s, feed->ready[h], 0)); CU(cudaStreamWaitEvent(side, feed->ready[h], 0)); }
+        if (feed) CU(cudaStreamWaitEvent(s, h ? feed->rest : feed->sig0, 0));
         if (hi[h] == lo[h]) continue;
-        LaneRlcDecode f1 = {pts, ok, flags, dsig, dpk, n, g, lo[h]};
+        LaneRlcDecode f1 = {pts, ok, flags, dsig, dpk, n, no_groups, lo[h]}; /* lanes below n never look at the groups */
         if (!launch(c, f1, hi[h] - lo[h], s)) return false;
-        LaneEdVerifyScalars f2 = {chal, resp, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, lo[h]};
-        if (!launch(c, f2, hi[h] - lo[h], side)) return false;
     }
+    if (feed) CU(cudaStreamWaitEvent(side, feed->keys, 0));
+    key_groups kg;
+    uint64_t launched = 0;
+    cudaError_t e = group_keys_all(dpk, n, gs, &kg, side, &launched);
+    if (e != cudaSuccess) return fail("group_keys_all", e);
+    g_launches += launched;
+    uint32_t m = 0;
+    CU(cudaMemcpyAsync(&m, kg.ngroups, sizeof m, cudaMemcpyDeviceToHost, side));
+    CU(cudaStreamSynchronize(side)); /* the number of distinct keys sizes the key class; the R decodes are already queued */
+    if (m == 0 || m > n) { g_err = "rlc: key grouping returned an impossible group count"; return false; }
+    const rlc_groups g = {kg.order, kg.gid, kg.gstart, m};
+    const rlc_shape sh_k = rlc_shape_for((size_t)m + 1, 0, 1);
+    unsigned long long *key_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * m);
+    uint32_t *kscal = k.out<uint32_t>(SC_WORDS * ((size_t)m + 1));
+    if (!rlc_class_alloc(k, ck, sh_k, (size_t)m + 1)) return false;
+    CU(cudaMemsetAsync(key_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * m, side));
+    LaneRlcDecode fk = {pts, ok, flags, dsig, dpk, n, g, n};
+    if (!launch(c, fk, (size_t)m + 1, side)) return false;
+    if (feed) CU(cudaStreamWaitEvent(side, feed->rest, 0));
+    LaneEdVerifyScalars f2 = {chal, resp, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, 0};
+    if (!launch(c, f2, n, side)) return false;
     CU(cudaEventRecord(c.side_evt[1], side));
     CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));
     LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g};
@@ -989,29 +1000,28 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
         CU(cudaMemcpyAsync(dst, valid, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
         return true;
     }
-    return ordinary(true);
+    return ordinary();
 }
 goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                      uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, int *fast_path) {
-    /* copies as in goldilocks_ed448_verify_batch: keys first on the main stream (the grouping pass needs nothing else), signatures
-     * and messages in two halves on the copy stream */
     Call k;
     int fast = 0;
     size_t total = n ? msg_off[n] : 0;
-    const size_t *doff = k.in(msg_off, n + 1);
-    const uint8_t *dctx = k.in(context, context_len);
-    const uint8_t *dpk = k.in(pubkey, 57 * n);
-    uint8_t *dsig = k.out<uint8_t>(114 * n), *dmsg = k.out<uint8_t>(total);
+    size_t *doff = k.out<size_t>(n + 1);
+    uint8_t *dctx = k.out<uint8_t>(context_len), *dpk = k.out<uint8_t>(57 * n), *dsig = k.out<uint8_t>(114 * n), *dmsg = k.out<uint8_t>(total);
     int32_t *dst = k.out<int32_t>(n);
-    VerifyFeed feed = {n >= 2 * VERIFY_GROUP_MIN ? n / 2 : n, {nullptr, nullptr}};
+    RlcFeed feed = {n >= 2 * RLC_MIN ? n / 2 : n, nullptr, nullptr, nullptr};
     if (k.ok) {
-        feed.ready[0] = k.c->copy_done[0]; feed.ready[1] = k.c->copy_done[1];
-        const size_t lo[2] = {0, feed.split}, hi[2] = {feed.split, n};
-        for (int h = 0; h < 2 && k.ok; h++) {
-            k.push(dsig + 114 * lo[h], signature + 114 * lo[h], 114 * (hi[h] - lo[h]));
-            if (hi[h] > lo[h]) k.push(dmsg + msg_off[lo[h]], msg + msg_off[lo[h]], msg_off[hi[h]] - msg_off[lo[h]]);
-            if (cudaEventRecord(feed.ready[h], k.c->copy_stream) != cudaSuccess) k.ok = false;
-        }
+        feed.sig0 = k.c->copy_done[0]; feed.keys = k.c->copy_done[1]; feed.rest = k.c->copy_done[2];
+        k.push(dsig, signature, 114 * feed.split);
+        if (k.ok && cudaEventRecord(feed.sig0, k.c->copy_stream) != cudaSuccess) k.ok = false;
+        k.push(dpk, pubkey, 57 * n);
+        k.push(doff, msg_off, n + 1);
+        k.push(dctx, context, context_len);
+        if (k.ok && cudaEventRecord(feed.keys, k.c->copy_stream) != cudaSuccess) k.ok = false;
+        k.push(dsig + 114 * feed.split, signature + 114 * feed.split, 114 * (n - feed.split));
+        k.push(dmsg, msg, total);
+        if (k.ok && cudaEventRecord(feed.rest, k.c->copy_stream) != cudaSuccess) k.ok = false;
     }
     if (k.ok && n) k.ok = rlc_core(k, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, k.c->stream, &fast, &feed);
     k.fetch((int32_t *)status, dst, n);

@@ -442,6 +442,7 @@ def run_ours(args):
             krlc[nm] = krlc.get(nm, 0.0) + ms[k] / kx
         barrier()
         r_sig[114 * 12345 + 70] ^= 1                                  # one wrong S: the equation fails, the ordinary path decides
+        assert fr(*argr) == -1                                        # the first fallback also grows the arena by the ordinary path's scratch
         t0 = time.perf_counter()
         assert fr(*argr) == -1
         t_bad = time.perf_counter() - t0

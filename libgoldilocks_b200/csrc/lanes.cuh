@@ -257,8 +257,18 @@ struct LaneScDecodeLong {
     abi_sc *out; const uint8_t *ser; size_t len;
     GDM void operator()(size_t i) const {
         sc z;
-        ByteAtPtr at = {ser + len * i};
-        sc_decode_long(z, at, (int)len);
+        if (len == 114) {        /* the two EdDSA lengths take the folding reduction the verify / sign kernels use (sc.cuh) */
+            uint32_t w[29];
+            words_load_bytes(w, 29, ser + len * i, 114);
+            sc_reduce_114(z, w);
+        } else if (len == 57) {
+            uint32_t w[15];
+            words_load_bytes(w, 15, ser + len * i, 57);
+            sc_reduce_57(z, w);
+        } else {
+            ByteAtPtr at = {ser + len * i};
+            sc_decode_long(z, at, (int)len);
+        }
         sc_to_abi(out + i, z);
     }
 };
@@ -413,8 +423,7 @@ GD void ed448_secret_scalar(sc &secret, shake256_ctx &h, const uint8_t *sk) {
     for (int k = 0; k < 15; k++) w[k] = 0;
     for (int k = 0; k < 57; k++) w[k >> 2] |= (uint32_t)shake256_squeeze_byte(h) << (8 * (k & 3));
     ed448_clamp_words(w);
-    ByteAtWords at = {w};
-    sc_decode_long(secret, at, 57);
+    sc_reduce_57(secret, w); /* folding reduction (sc.cuh): branch-free, same canonical value as scalar_decode_long */
 }
 struct LaneEdSecretScalar { /* goldilocks_ed448_derive_secret_scalar, eddsa.c:98-127 */
     abi_sc *out; const uint8_t *sk;
@@ -453,11 +462,11 @@ struct LaneEdSignNonce { /* eddsa.c:173-199: nonce = SHAKE256(dom || seed || msg
         for (int k = 0; k < 57; k++) shake256_absorb_byte(h, seed[57 * i + k]);
         for (size_t k = off[i]; k < off[i + 1]; k++) shake256_absorb_byte(h, msg[k]);
         shake256_finish_absorb(h);
-        uint32_t w[29];
-        for (int k = 0; k < 29; k++) w[k] = 0;
-        for (int k = 0; k < 114; k++) w[k >> 2] |= (uint32_t)shake256_squeeze_byte(h) << (8 * (k & 3));
-        ByteAtWords at = {w};
-        sc_decode_long(n, at, 114);
+        uint32_t w[29]; /* the first 136 output bytes sit in the sponge's word buffer; 114 of them, reduced by folding (sc.cuh) */
+#pragma unroll
+        for (int k = 0; k < 28; k++) w[k] = h.buf[k];
+        w[28] = h.buf[28] & 0xffffu;
+        sc_reduce_114(n, w);
         sc_halve(h1, n);
         sc_halve(h2, h1);
         sc_to_abi(nonce + i, n);
@@ -473,11 +482,12 @@ GD void ed448_challenge(sc &c, const uint8_t *r57, const uint8_t *pk57, const ui
     for (int k = 0; k < 57; k++) shake256_absorb_byte(h, pk57[k]);
     for (size_t k = lo; k < hi; k++) shake256_absorb_byte(h, msg[k]);
     shake256_finish_absorb(h);
+    /* the first 136 output bytes sit in the sponge's word buffer; 114 of them, reduced by folding (sc.cuh) */
     uint32_t w[29];
-    for (int k = 0; k < 29; k++) w[k] = 0;
-    for (int k = 0; k < 114; k++) w[k >> 2] |= (uint32_t)shake256_squeeze_byte(h) << (8 * (k & 3));
-    ByteAtWords at = {w};
-    sc_decode_long(c, at, 114);
+#pragma unroll
+    for (int k = 0; k < 28; k++) w[k] = h.buf[k];
+    w[28] = h.buf[28] & 0xffffu;
+    sc_reduce_114(c, w);
 }
 struct LaneEdSignFinish {
     uint8_t *sig; const abi_sc *secret, *nonce; const uint8_t *pk, *msg; const size_t *off; uint32_t prehashed; const uint8_t *ctx; uint32_t ctx_len;
@@ -544,8 +554,9 @@ struct LaneEdVerifyScalars {
         sc c, nc, r;
         ed448_challenge(c, sig + 114 * i, pk + 57 * ki, msg, off[i], off[i + 1], prehashed, ctx, ctx_len);
         sc_neg(nc, c);
-        ByteAtPtr at = {sig + 114 * i + 57};
-        sc_decode_long(r, at, 57);   /* reduces mod q, no range check (eddsa.c:287-291) */
+        uint32_t sw[15];
+        words_load_bytes(sw, 15, sig + 114 * i + 57, 57);
+        sc_reduce_57(r, sw);         /* reduces mod q, no range check (eddsa.c:287-291) */
         /* GOLDILOCKS_448_EDDSA_DECODE_RATIO = 1: no doubling of the response */
         sc_to_abi(challenge + i, nc);
         sc_to_abi(response + i, r);

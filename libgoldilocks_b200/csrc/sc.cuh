@@ -193,6 +193,81 @@ GD void sc_decode_long(sc &out, ByteAt get, int len) {
     sc_copy(out, t1);
 }
 
+// ---- wide reduction by folding (the EdDSA hot path: 114-byte SHAKE outputs and 57-byte S strings) -----------------------
+// q = 2^446 - c with c of 224 bits, so 2^448 == 4c (mod q): a value of N > 14 words is its low 14 words plus its high words
+// times 4c (8 words), until 15 words are left; then the bits from 446 up are folded with c and one conditional subtraction
+// makes the result canonical.  Same value as sc_decode_long (reference scalar.c:257-293: the canonical residue), at 255
+// word multiplications for 114 bytes instead of six Montgomery multiplications (2 352).  c = 2^446 - q, from GOLD_CONST_SC_Q.
+#define GOLD_CONST_SC_C { 0x54a7bb0du, 0xdc873d6du, 0x723a70aau, 0xde933d8du, 0x5129c96fu, 0x3bb124b6u, 0x8335dc16u }
+#define GOLD_CONST_SC_4C { 0x529eec34u, 0x721cf5b5u, 0xc8e9c2abu, 0x7a4cf635u, 0x44a725bfu, 0xeec492d9u, 0x0cd77058u, 0x00000002u }
+// y (OUT words) = x[0..14) + x[14..N) * 4c; the caller guarantees the value fits OUT words.
+template <int N, int OUT>
+GD void sc_fold448(uint32_t (&y)[OUT], const uint32_t (&x)[N]) {
+    const uint32_t c4[8] = GOLD_CONST_SC_4C;
+#pragma unroll
+    for (int i = 0; i < OUT; i++) y[i] = i < SC_WORDS ? x[i] : 0u;
+    uint32_t pend = 0; /* carry out of the previous row, due at position i + 8 */
+#pragma unroll
+    for (int i = 0; i < N - SC_WORDS; i++) {
+        const uint32_t h = x[SC_WORDS + i];
+        uint64_t chain = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (i + j < OUT) {
+                chain += (uint64_t)h * c4[j] + y[i + j];
+                y[i + j] = (uint32_t)chain;
+                chain >>= 32;
+            }
+        }
+        if (i + 8 < OUT) {
+            chain += (uint64_t)y[i + 8] + pend;
+            y[i + 8] = (uint32_t)chain;
+            pend = (uint32_t)(chain >> 32);
+        }
+    }
+#pragma unroll
+    for (int k = N - SC_WORDS + 8; k < OUT; k++) { /* the last row's carry ripples through the low words it lands in */
+        const uint64_t t = (uint64_t)y[k] + pend;
+        y[k] = (uint32_t)t;
+        pend = (uint32_t)(t >> 32);
+    }
+}
+// x < 2^448 + small (15 words, word 14 <= 1 after the folds) -> canonical residue
+GD void sc_fold_finish(sc &out, const uint32_t (&x)[15]) {
+    uint32_t y[15];
+    sc_fold448<15, 15>(y, x);                /* word 14 is 0 now (see the bounds above) */
+    const uint32_t c[7] = GOLD_CONST_SC_C;
+    const uint32_t hi = y[13] >> 30;         /* bits 446, 447 */
+    y[13] &= 0x3fffffffu;
+    uint64_t chain = 0;
+#pragma unroll
+    for (int j = 0; j < SC_WORDS; j++) {
+        chain += (uint64_t)y[j] + (j < 7 ? (uint64_t)hi * c[j] : 0u);
+        y[j] = (uint32_t)chain;
+        chain >>= 32;
+    }                                        /* < 2^446 + 3 * 2^224 < 2q */
+    uint32_t v[SC_WORDS];
+#pragma unroll
+    for (int j = 0; j < SC_WORDS; j++) v[j] = y[j];
+    sc q;
+    sc_set_q(q);
+    sc_subx(out, v, q.w, 0);
+}
+// 114 little-endian bytes in 29 words (the upper half of word 28 must be zero)
+GD void sc_reduce_114(sc &out, const uint32_t (&w)[29]) {
+    uint32_t a[24], b[19], c[15];
+    sc_fold448<29, 24>(a, w);   /* < 2^706 */
+    sc_fold448<24, 19>(b, a);   /* < 2^485 */
+    sc_fold448<19, 15>(c, b);   /* < 2^448 + 2^263 */
+    sc_fold_finish(out, c);
+}
+// 57 little-endian bytes in 15 words (the upper three bytes of word 14 must be zero)
+GD void sc_reduce_57(sc &out, const uint32_t (&w)[15]) {
+    uint32_t c[15];
+    sc_fold448<15, 15>(c, w);   /* < 2^448 + 2^234 */
+    sc_fold_finish(out, c);
+}
+
 // bit `pos` of the scalar (0 for pos >= 448)
 GD uint32_t sc_bit(const sc &a, int pos) {
     uint32_t r = 0;

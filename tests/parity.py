@@ -146,6 +146,21 @@ def check_scalars(lib, chk, n):
         eq(got, want, "scalar_decode_long len %d" % ln)
         for i in range(min(4, len(ser))):
             assert util.from_le(want[i]) == util.from_le(ser[i]) % Q
+    # the two EdDSA lengths are reduced by folding at 2^448 = 4c (csrc/sc.cuh): values that make every carry ripple
+    c = 2**446 - Q
+    for ln in (57, 114):
+        top = 2**(8 * ln)
+        vals = [0, 1, Q - 1, Q, Q + 1, 2 * Q - 1, 2 * Q, 2**446 - 1, 2**446, 2**448 - 1, 2**448, 2**448 + 1, 2**448 - 4 * c, 2**448 - 4 * c - 1,
+                2**448 - 4 * c + 1, top - 1, top - 2**448, top - 2**446, top - Q, (top // Q) * Q, (top // Q) * Q - 1, top - 4 * c, 2**448 + 2**264 - 1,
+                2**449 - 1, 2**450 - 4 * c, (2**448 - 1) ^ (2**288 - 1), (2**448 - 1) - 2**300]
+        vals += [v ^ ((1 << k) - 1) for v in (top - 1, 2**448 - 1) for k in (31, 32, 33, 224, 287, 288, 289, 415, 416, 446)]
+        vals += [(top - 1) // 3, (top - 1) // 5 * 3, (top - 1) - (2**448 - 1), ((top - 1) >> 448 << 448) + 2**448 - 4 * c * ((top - 1) >> 448)]
+        vals = [v % top for v in vals if v >= 0]
+        ser = np.stack([le(v, ln) for v in vals])
+        got = lib.scalar_decode_long(ser, ln)
+        for i, v in enumerate(vals):
+            assert util.from_le(got[i]) == v % Q, "scalar_decode_long (folding) len %d case %d" % (ln, i)
+        eq(got, chk.scalar_decode_long(ser, ln), "scalar_decode_long edge values len %d" % ln)
 
 
 def check_comb(lib, chk, n):

@@ -34,7 +34,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_PER_GPU = 1 << 20
 MSG_LEN = 32
-MAC32 = {"verify": 981120, "verify_finish": 800300, "x448": 870208, "comb": 142656}  # the REFERENCE's algorithm
+MAC32 = {"verify": 981120, "verify_finish": 800300, "x448": 870208, "comb": 142656, "encode": 89696, "decode": 90064}  # the REFERENCE's algorithm
 # IMAD.WIDE actually issued per signature by the finish kernel (multiply = 193, square = 110):
 #   under a per-key table: 40 doublings (4S + 3M, +1M for T on every fifth), 90 x 8M + 30 x 7M additions (8 without T), the
 #   square-root-free R comparison (3S + 8M);  stand-alone: 445 doublings + own window table + the same comparison
@@ -309,6 +309,8 @@ def run_ours(args):
                 "executed_mac32_per_launch": executed, "signatures_under_a_shared_key_table": n_shared,
                 "frac_executed": executed / t_finish / 1e9 / peak if t_finish > 0 else None,
                 "kernel_ms": kavg,
+                "hbm": (lambda tr, pk: None if not tr or t_finish <= 0 else {"achieved": tr / t_finish / 1e9, "peak": pk[0], "unit": "GB/s", "frac": tr / t_finish / 1e9 / pk[0],
+                                                                               "peak_source": pk[1], "note": "informational: DRAM traffic of the ncu capture / this run's launch time; the kernel is multiplier-bound"})(ncu_traffic(), hbm_peak()),
                 "kernel_share_of_step": t_finish / (e0.elapsed_time(e1) / 1e3 / K) if t_finish > 0 else None,
                 "step_frac": n * MAC32["verify"] / t_step / 1e9 / peak,
                 "note": "integer-multiply-pipe roofline (north_star). `achieved`/`frac` count the REFERENCE's algorithmic work per signature "
@@ -360,6 +362,32 @@ def run_ours(args):
             t = max_over_ranks(a.elapsed_time(b) / 1e3 / kx)
             extra[name] = {"value": world * n / t, "unit": "ops/s", "ms_per_step": t * 1e3, "batch_per_gpu": n,
                            "imad_frac": n * mac / t / 1e9 / peak, "algorithmic_mac32_per_op": mac}
+
+    # ---- extra: decaf encode / decode (BASELINE configs[4]: 2^24 elements over 8 GPUs; here 2^20 per GPU like the other lines), on the
+    #      comb outputs above (valid points).  Multiplier-bound like everything else (one inverse square root each); HBM GB/s is the
+    #      informational figure BASELINE.json asks for on these paths ----------------------------------------------------------------------
+    if not args.no_extra:
+        enc = torch.empty(n * 56, dtype=torch.uint8, device=dev)
+        dpts = torch.empty(n * 256, dtype=torch.uint8, device=dev)
+        dstat = torch.empty(n, dtype=torch.int32, device=dev)
+        hbm, _ = hbm_peak()
+        for name, fnc, mac, nbytes in (("decaf_encode", lambda: eng.point_encode(enc, co), MAC32["encode"], 256 + 56),
+                                       ("decaf_decode", lambda: eng.point_decode(dpts, dstat, enc, True), MAC32["decode"], 56 + 256 + 4)):
+            for _ in range(2):
+                fnc()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kx = max(2, min(K, 3))
+            barrier()
+            a.record()
+            for _ in range(kx):
+                fnc()
+            b.record()
+            barrier()
+            t = max_over_ranks(a.elapsed_time(b) / 1e3 / kx)
+            extra[name] = {"value": world * n / t, "unit": "ops/s", "ms_per_step": t * 1e3, "batch_per_gpu": n, "imad_frac": n * mac / t / 1e9 / peak,
+                           "algorithmic_mac32_per_op": mac, "hbm_gbs": n * nbytes / t / 1e9, "hbm_frac": n * nbytes / t / 1e9 / hbm}
+        assert int((dstat == -1).sum().item()) == n, "decode(encode(P)) must succeed for every comb output"
+        del enc, dpts, dstat
 
     # ---- extra: the same batch size (a) with 2^20 DISTINCT keys (no table can be shared), (b) with message lengths
     #      uniform in [0, 256) under the 2^16 x 16 keys (second run) --------------------------------------

@@ -36,6 +36,11 @@ def _worker(rank, world, port, tmp):
     sig, pk, msgs, kinds = util.verify_corpus(sim, "shard", n, corrupt_every=4)
     lo, hi = shard_range(n, rank, world)
     st = sim.ed448_verify(sig[lo:hi], pk[lo:hi], msgs[lo:hi])
+    st_rlc, _ = sim.ed448_verify_rlc(sig[lo:hi], pk[lo:hi], msgs[lo:hi])   # per-shard batch equation (own weights), same statuses
+    assert (st_rlc == st).all()
+    ok = np.flatnonzero(kinds[lo:hi] == 0) + lo                            # the shard's untouched entries alone: the equation decides
+    st_ok, fast = sim.ed448_verify_rlc(sig[ok], pk[ok], [msgs[i] for i in ok])
+    assert fast == 1 and (st_ok == -1).all()
     u = util.stream_bytes("shard/u", n * 56).reshape(n, 56)
     k = util.stream_bytes("shard/k", n * 56).reshape(n, 56)
     xo, _ = sim.x448(u[lo:hi], k[lo:hi])

@@ -6,12 +6,12 @@
 // resp_i = S mod q (eddsa.c:273-291), and `==` is `point_eq` (goldilocks.c:644-653).  Every decoded point is the image of
 // a curve point under the 4-isogeny whose kernel is the whole 4-torsion of Ed448, so all of these points live in the
 // subgroup of prime order q and `point_eq` on them is plain equality up to the 2-torsion point the isogeny never hits.
-// With secret random 128-bit weights z_i (drawn per call, after the signatures are fixed):
+// With secret random odd weights z_i of at least 128 bits (drawn per call, after the signatures are fixed):
 //
 //     sum_i z_i*(-R_i)  +  sum_keys (sum_{i under key} z_i*chal_i mod q)*A_key  +  (sum_i z_i*resp_i mod q)*B  ==  identity
 //
 // holds if every signature is valid, and fails with probability >= 1 - 2^-127 if any is not (a non-zero element of a
-// group of prime order times a uniform odd 128-bit weight).  Signatures whose R or public key does not decode are
+// group of prime order times a uniform odd weight of >= 128 bits).  Signatures whose R or public key does not decode are
 // rejected up front, exactly like the reference (eddsa.c:266-270), and take no part in the sum.  When the equation
 // fails the caller runs the ordinary per-signature path over the batch, so statuses are always per element.
 //

@@ -39,7 +39,7 @@ struct Ctx {
     int dev = -1, sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // signatures and messages of a verification cross PCIe here while the main stream groups the keys
-    cudaEvent_t copy_done[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t side_stream = nullptr;   // the latency-bound doubling chain of the key class (rlc.cuh) runs here beside the R-class buckets
     cudaEvent_t side_evt[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     fixed_tables *ft = nullptr;
@@ -866,13 +866,13 @@ static bool rlc_seed(uint8_t seed[32]) { /* fresh secret weights per call: the s
 static bool rlc_usable(size_t n) { return n >= RLC_MIN && n < ((size_t)1 << 26); } /* pair lists are 32-bit, CUB counts are int */
 // One class of points through the bucket method: digits -> radix sort -> buckets -> segments -> tree nodes.  The window
 // sums (the c*w doublings) are a separate launch so that the key class can run its long chain on the side stream.
-struct RlcClass { rlc_shape sh; size_t count, npairs, nb; uint32_t *keys, *vals, *keys_s, *vals_s; void *sort_tmp; size_t sort_bytes; pt *buckets, *segsum, *nodesum, *winsum; };
+struct RlcClass { rlc_shape sh; size_t count, npairs, nb; uint32_t *keys, *vals, *keys_s, *vals_s; void *sort_tmp; size_t sort_bytes; pt *buckets, *segsum, *nodesum, *winsum, *total; };
 static bool rlc_class_alloc(Call &k, RlcClass &q, const rlc_shape &sh, size_t count) {
     q.sh = sh; q.count = count; q.npairs = count * sh.wn; q.nb = (size_t)sh.wn << sh.c;
     q.keys = k.out<uint32_t>(q.npairs); q.vals = k.out<uint32_t>(q.npairs); q.keys_s = k.out<uint32_t>(q.npairs); q.vals_s = k.out<uint32_t>(q.npairs);
     q.sort_bytes = pair_sort_scratch_bytes(q.npairs);
     q.sort_tmp = k.alloc(q.sort_bytes);
-    q.buckets = k.out<pt>(q.nb); q.segsum = k.out<pt>((size_t)sh.wn * sh.segs); q.nodesum = k.out<pt>((size_t)sh.wn * sh.nodes); q.winsum = k.out<pt>(sh.wn);
+    q.buckets = k.out<pt>(q.nb); q.segsum = k.out<pt>((size_t)sh.wn * sh.segs); q.nodesum = k.out<pt>((size_t)sh.wn * sh.nodes); q.winsum = k.out<pt>(sh.wn); q.total = k.out<pt>(1);
     return k.ok;
 }
 static bool rlc_class_pairs(Ctx &c, const RlcClass &q, const uint32_t *scal, uint32_t nwords, size_t p0, cudaStream_t s) { /* digits -> sorted pair list */
@@ -894,11 +894,13 @@ static bool rlc_class_sum(Ctx &c, const RlcClass &q, const pt *recs, cudaStream_
     LaneRlcNodes f9 = {q.nodesum, q.segsum, q.sh};
     if (!launch(c, f9, (size_t)q.sh.wn * q.sh.nodes, s)) return false;
     LaneRlcWindows f10 = {q.winsum, q.nodesum, q.sh};
-    return launch(c, f10, q.sh.wn, s);
+    if (!launch(c, f10, q.sh.wn, s)) return false;
+    LaneRlcTotal f11 = {q.total, q.winsum, q.sh.wn};
+    return launch(c, f11, 1, s);
 }
 // Host-pointer calls feed the copy stream in the order the work can start in: the first half of the signatures (the R decodes,
 // 55 % of the call, need nothing else), then keys / offsets / context (the grouping pass), then the rest.
-struct RlcFeed { size_t split; cudaEvent_t sig0, keys, rest; };
+struct RlcFeed { size_t split[2]; cudaEvent_t sig0, keys, sig1, rest; }; /* signatures [0, split[0]) | keys | [split[0], split[1]) | the rest */
 static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *dpk, const uint8_t *dmsg, const size_t *doff, uint8_t prehashed,
                      const uint8_t *dctx, uint8_t ctx_len, size_t n, cudaStream_t s, int *fast, const RlcFeed *feed = nullptr) {
     Ctx &c = *k.c;
@@ -944,11 +946,11 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     LaneRlcZ f3 = {z, dseed, n, sh_r.zbits};
     if (!launch(c, f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE, side)) return false;
     if (!rlc_class_pairs(c, cr, z, RLC_ZWORDS, 0, side)) return false;
-    const size_t split = feed ? feed->split : n;
-    const size_t lo[2] = {0, split}, hi[2] = {split, n};
+    const size_t s0 = feed ? feed->split[0] : n, s1 = feed ? feed->split[1] : n;
+    const size_t lo[3] = {0, s0, s1}, hi[3] = {s0, s1, n};
     const rlc_groups no_groups = {nullptr, nullptr, nullptr, 0};
-    for (int h = 0; h < 2; h++) {
-        if (feed) CU(cudaStreamWaitEvent(s, h ? feed->rest : feed->sig0, 0));
+    for (int h = 0; h < 3; h++) {
+        if (feed) CU(cudaStreamWaitEvent(s, h == 0 ? feed->sig0 : h == 1 ? feed->sig1 : feed->rest, 0));
         if (hi[h] == lo[h]) continue;
         LaneRlcDecode f1 = {pts, ok, flags, dsig, dpk, n, no_groups, lo[h]}; /* lanes below n never look at the groups */
         if (!launch(c, f1, hi[h] - lo[h], s)) return false;
@@ -989,7 +991,7 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     CU(cudaStreamWaitEvent(s, c.side_evt[4], 0)); /* the radix sort of the key class wants the whole machine for its 0.3 ms: the R buckets wait for it */
     if (!rlc_class_sum(c, cr, pts, s, true, valid)) return false;
     CU(cudaStreamWaitEvent(s, c.side_evt[3], 0));
-    LaneRlcVerdict f11 = {flags + 1, cr.winsum, ck.winsum, flags, cr.sh.wn, ck.sh.wn};
+    LaneRlcVerdict f11 = {flags + 1, cr.total, ck.total, flags};
     if (!launch(c, f11, 1, s)) return false;
     uint32_t hflags[2] = {0, 0};
     CU(cudaMemcpyAsync(hflags, flags, sizeof hflags, cudaMemcpyDeviceToHost, s));
@@ -1010,16 +1012,20 @@ goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status,
     size_t *doff = k.out<size_t>(n + 1);
     uint8_t *dctx = k.out<uint8_t>(context_len), *dpk = k.out<uint8_t>(57 * n), *dsig = k.out<uint8_t>(114 * n), *dmsg = k.out<uint8_t>(total);
     int32_t *dst = k.out<int32_t>(n);
-    RlcFeed feed = {n >= 2 * RLC_MIN ? n / 2 : n, nullptr, nullptr, nullptr};
+    /* a quarter of the signatures first (the R decodes start half a millisecond into the call), the keys, the second quarter, the rest */
+    const bool chunked = n >= 4 * RLC_MIN;
+    RlcFeed feed = {{chunked ? n / 4 : n, chunked ? n / 2 : n}, nullptr, nullptr, nullptr, nullptr};
     if (k.ok) {
-        feed.sig0 = k.c->copy_done[0]; feed.keys = k.c->copy_done[1]; feed.rest = k.c->copy_done[2];
-        k.push(dsig, signature, 114 * feed.split);
+        feed.sig0 = k.c->copy_done[0]; feed.keys = k.c->copy_done[1]; feed.sig1 = k.c->copy_done[2]; feed.rest = k.c->copy_done[3];
+        k.push(dsig, signature, 114 * feed.split[0]);
         if (k.ok && cudaEventRecord(feed.sig0, k.c->copy_stream) != cudaSuccess) k.ok = false;
         k.push(dpk, pubkey, 57 * n);
         k.push(doff, msg_off, n + 1);
         k.push(dctx, context, context_len);
         if (k.ok && cudaEventRecord(feed.keys, k.c->copy_stream) != cudaSuccess) k.ok = false;
-        k.push(dsig + 114 * feed.split, signature + 114 * feed.split, 114 * (n - feed.split));
+        k.push(dsig + 114 * feed.split[0], signature + 114 * feed.split[0], 114 * (feed.split[1] - feed.split[0]));
+        if (k.ok && cudaEventRecord(feed.sig1, k.c->copy_stream) != cudaSuccess) k.ok = false;
+        k.push(dsig + 114 * feed.split[1], signature + 114 * feed.split[1], 114 * (n - feed.split[1]));
         k.push(dmsg, msg, total);
         if (k.ok && cudaEventRecord(feed.rest, k.c->copy_stream) != cudaSuccess) k.ok = false;
     }

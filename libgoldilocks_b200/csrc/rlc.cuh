@@ -310,15 +310,25 @@ struct LaneRlcWindows {
         pt_st(winsum + w, acc);
     }
 };
-// 10) verdict: one lane adds the window sums of both classes; the equation holds iff the total is the identity of the
-//     quotient group (point_eq against (0, 1): X == 0, goldilocks.c:644-653) and nothing asked for the fallback.
-struct LaneRlcVerdict {
-    uint32_t *verdict; const pt *win_r, *win_k; const uint32_t *force_fallback; uint32_t wn_r, wn_k;
+// 10) class total: one lane adds the window sums of a class (the key class does this on the side stream, off the critical path).
+struct LaneRlcTotal {
+    pt *total; const pt *winsum; uint32_t wn;
     GDM void operator()(size_t) const {
-        pt acc, t, q, id;
-        pt_ld(acc, win_r);
-        for (uint32_t w = 1; w < wn_r; w++) { pt_ld(q, win_r + w); pt_add(t, acc, q); pt_copy(acc, t); }
-        for (uint32_t w = 0; w < wn_k; w++) { pt_ld(q, win_k + w); pt_add(t, acc, q); pt_copy(acc, t); }
+        pt acc, t, q;
+        pt_ld(acc, winsum);
+        for (uint32_t w = 1; w < wn; w++) { pt_ld(q, winsum + w); pt_add(t, acc, q); pt_copy(acc, t); }
+        pt_st(total, acc);
+    }
+};
+// 11) verdict: the equation holds iff the two class totals add up to the identity of the quotient group (point_eq against
+//     (0, 1): X == 0, goldilocks.c:644-653) and nothing asked for the fallback.
+struct LaneRlcVerdict {
+    uint32_t *verdict; const pt *total_r, *total_k; const uint32_t *force_fallback;
+    GDM void operator()(size_t) const {
+        pt acc, a, b, id;
+        pt_ld(a, total_r);
+        pt_ld(b, total_k);
+        pt_add(acc, a, b);
         pt_set_identity(id);
         const gmask_t same = pt_eq(acc, id) & ~gf_is_zero_mod_p(acc.z);
         *verdict = (same && !*force_fallback) ? 1u : 0u;

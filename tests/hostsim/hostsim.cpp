@@ -306,7 +306,11 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
     std::vector<pt> win_r, win_k;
     run_class(sh_k, (size_t)m + 1, kscal.data(), SC_WORDS, n, win_k, false);
     run_class(sh_r, n, z_for_digits.data(), RLC_ZWORDS, 0, win_r, true);
-    LaneRlcVerdict f11 = {flags.data() + 1, win_r.data(), win_k.data(), flags.data(), sh_r.wn, sh_k.wn};
+    pt tot_r, tot_k;
+    LaneRlcTotal ftr = {&tot_r, win_r.data(), sh_r.wn}, ftk = {&tot_k, win_k.data(), sh_k.wn};
+    run(ftr, 1);
+    run(ftk, 1);
+    LaneRlcVerdict f11 = {flags.data() + 1, &tot_r, &tot_k, flags.data()};
     run(f11, 1);
     if (flags[1]) {
         if (fast_path) *fast_path = 1;

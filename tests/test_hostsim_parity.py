@@ -78,3 +78,35 @@ def test_eddsa_rlc(sim, chk):
         sim.lib.hostsim_rlc_config(ctypes.c_int(c), None)
         parity.check_eddsa_rlc(sim, chk, 150 if c else 100, label="c4r/%d" % c)
     sim.lib.hostsim_rlc_config(ctypes.c_int(0), None)
+
+
+def test_scalar_folding_reduction_fuzz(sim):
+    """sc_reduce_114 / sc_reduce_57 (csrc/sc.cuh: folding at 2^448 = 4c) against Python integers: random values, long runs
+    of ones and zeros (carry ripples), multiples of q plus small offsets, values just below the top"""
+    import random
+    import numpy as np
+    _threads(sim)
+    rnd = random.Random(448)
+    for ln in (57, 114):
+        top = 2 ** (8 * ln)
+        vals = []
+        for t in range(6000):
+            r = rnd.random()
+            if r < 0.3:
+                v = rnd.getrandbits(8 * ln)
+            elif r < 0.6:
+                v, pos = 0, 0
+                while pos < 8 * ln:
+                    run = rnd.choice([1, 7, 31, 32, 33, 64, 100, 224])
+                    if rnd.random() < 0.5:
+                        v |= ((1 << run) - 1) << pos
+                    pos += run
+                v %= top
+            elif r < 0.8:
+                v = (rnd.getrandbits(8 * ln - 446) * util.Q + rnd.choice([0, 1, util.Q - 1, rnd.getrandbits(200)])) % top
+            else:
+                v = (top - 1 - rnd.getrandbits(rnd.randrange(1, 8 * ln))) % top
+            vals.append(v)
+        ser = np.stack([util.le(v, ln) for v in vals])
+        want = np.stack([util.le(v % util.Q, 56) for v in vals])
+        parity.eq(sim.scalar_decode_long(ser, ln), want, "scalar_decode_long by folding, len %d" % ln)

@@ -78,6 +78,21 @@ def test_eddsa_rlc(sim, chk):
         sim.lib.hostsim_rlc_config(ctypes.c_int(c), None)
         parity.check_eddsa_rlc(sim, chk, 150 if c else 100, label="c4r/%d" % c)
     sim.lib.hostsim_rlc_config(ctypes.c_int(0), None)
+    # tiny batches (the host simulator has no size threshold) and a batch in which every key is undecodable
+    import numpy as np
+    for n in (1, 2, 5):
+        sk = util.stream_bytes("c4r/tiny/sk%d" % n, n * 57).reshape(n, 57)
+        pk = chk.ed448_derive_public_key(sk)
+        msgs = [bytes(util.stream_bytes("c4r/tiny/m%d.%d" % (n, i), i)) for i in range(n)]
+        sig = chk.ed448_sign(sk, pk, msgs)
+        st, fast = sim.ed448_verify_rlc(sig, pk, msgs)
+        assert fast == 1 and (st == -1).all()
+        sig[0, 100] ^= 1
+        st, fast = sim.ed448_verify_rlc(sig, pk, msgs)
+        assert fast == 0 and st[0] == 0 and (st[1:] == -1).all()
+        pk[:] = util.le(1, 57)
+        st, fast = sim.ed448_verify_rlc(sig, pk, msgs)
+        assert (st == 0).all() and fast == 1     # everything rejected up front; the empty equation holds
 
 
 def test_scalar_folding_reduction_fuzz(sim):

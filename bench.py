@@ -469,13 +469,14 @@ def run_ours(args):
             nm = names.raw[64 * k:64 * k + 64].split(b"\0")[0].decode()
             krlc[nm] = krlc.get(nm, 0.0) + ms[k] / kx
         barrier()
-        r_sig[114 * 12345 + 70] ^= 1                                  # one wrong S: the equation fails, the ordinary path decides
+        bad_i = 12345 % n
+        r_sig[114 * bad_i + 70] ^= 1                                  # one wrong S: the equation fails, the ordinary path decides
         assert fr(*argr) == -1                                        # the first fallback also grows the arena by the ordinary path's scratch
         t0 = time.perf_counter()
         assert fr(*argr) == -1
         t_bad = time.perf_counter() - t0
         st_bad = h_st.numpy()
-        assert fast.value == 0 and st_bad[12345] == 0 and (st_bad == -1).sum() == n - 1
+        assert fast.value == 0 and st_bad[bad_i] == 0 and (st_bad == -1).sum() == n - 1
         extra["verify_rlc_all_valid_e2e"] = {"value": world * n / t, "unit": UNIT, "ms_per_step": t * 1e3, "batch_per_gpu": n, "fast_path": 1,
                                              "kernel_ms": krlc, "ms_when_one_signature_is_bad": t_bad * 1e3,
                                              "api": "goldilocks_ed448_verify_rlc_batch (host pointers, pinned): one multi-scalar multiplication with secret 128-bit "

@@ -270,8 +270,10 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *o
  *    current CUDA device, `stream` is a cudaStream_t passed as void* (NULL = default stream).
  *    Calls are asynchronous on that stream; `scratch` must hold goldilocks_b200_*_scratch_bytes(n).
  * ====================================================================================== */
-/* scratch of a device-resident verification: decoded points and scalars, the key-grouping work lists and room for
- * n/4 + 1 per-key tables (41 KB each); about 11 KB per signature */
+/* scratch of a device-resident verification on the CURRENT device: decoded points and scalars, the key-grouping work
+ * lists, room for n/4 + 1 per-key tables (41 KB each) and the per-lane window tables of the finish kernel; about 11 KB
+ * per signature.  Everything the call writes lives in this scratch, so calls in flight on different streams with
+ * different scratch buffers are independent.  Returns 0 without a usable GPU. */
 GOLDILOCKS_B200_API size_t goldilocks_b200_verify_scratch_bytes(size_t n);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off, uint8_t prehashed, const uint8_t *context /*device or NULL*/, uint8_t context_len, size_t n, void *scratch, void *stream);
 /* device-pointer form of goldilocks_ed448_verify_rlc_batch: scratch comes from the library's own arena and the call
@@ -292,6 +294,24 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_448_point_encode_batch_dev(uin
  * Called lazily by every entry point; thread-safe.  Returns FAILURE when no usable GPU exists. */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_init(void);
 GOLDILOCKS_B200_API const char *goldilocks_b200_last_error(void);
+/* Device sets: ONE host-pointer batch spread over several GPUs (the reference has no counterpart -- its
+ * per-element functions eddsa.c:253-306, goldilocks.c:1006-1076, 98-176 are what each range runs).  After
+ * goldilocks_b200_set_devices(devs, count) every `*_batch` entry point with HOST pointers cuts [0, n) into contiguous
+ * ranges, one run of ranges per listed device, each executed on a worker thread bound to that device with its own
+ * stream and arena; the calling thread blocks until all ranges are back.  No collective and no peer traffic.  Heavy
+ * operations (verify, sign, X448, scalar multiplications) get one range per device; the light, PCIe-bound field / point /
+ * codec operations are pipelined in ~24 MB chunks over three contexts per device so copy-in, kernel and copy-out overlap
+ * (a set of ONE device therefore still pipelines them).  Results are identical to the unsharded call (elements are
+ * independent); verification groups keys per range.  count = 0 restores the default: the caller's current device only.
+ * The environment variable GOLDILOCKS_B200_DEVICES ("all" or "0,1,2,3") sets the same thing at first use.  `_dev` entry
+ * points and key sets always run on the current device.  A device may be listed more than once (its ranges then queue
+ * on the same contexts: useful to exercise the partition on a single GPU).  Host buffers should be pinned (cudaHostAlloc/cudaHostRegister)
+ * for full PCIe speed; pageable buffers work. */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_set_devices(const int *devices, int count);
+GOLDILOCKS_B200_API int goldilocks_b200_get_devices(int *devices, int max); /* returns the size of the set (0 = default) */
+/* The partition such a call would use over `ndev` devices (pure arithmetic, needs no GPU): piece k covers [lo[k], hi[k]) on
+ * device_slot[k] (index into the set) and context lane[k]; returns the number of pieces (writes at most `max`). */
+GOLDILOCKS_B200_API size_t goldilocks_b200_shard_plan(size_t *lo, size_t *hi, int *device_slot, int *lane, size_t max, size_t n, int ndev, size_t bytes_per_elem, int pipelined);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 GOLDILOCKS_B200_API uint64_t goldilocks_b200_launch_count(void);
 /* Per-launch CUDA-event timing for bench.py's roofline leg.  profile(1) clears the log and starts

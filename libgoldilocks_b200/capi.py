@@ -347,6 +347,29 @@ class BatchLib:
         self._call("goldilocks_ed448_verify_rlc_batch", st, sig, pk, arena, off, C.c_uint8(1 if prehashed else 0), ctx, C.c_uint8(ctx_len), _Z(len(sig)), C.byref(fast))
         return st, fast.value
 
+    # ---- device sets: one host-pointer batch over several GPUs (include/goldilocks_b200.h, section 4) ----
+    def set_devices(self, devices):
+        """spread every later `*_batch` host-pointer call over these CUDA devices ([] = the current device only)"""
+        devs = (C.c_int * max(1, len(devices)))(*devices)
+        self._call("goldilocks_b200_set_devices", devs, C.c_int(len(devices)))
+
+    def get_devices(self):
+        buf = (C.c_int * 64)()
+        self.lib.goldilocks_b200_get_devices.restype = C.c_int
+        n = self.lib.goldilocks_b200_get_devices(buf, C.c_int(64))
+        return list(buf[:n])
+
+    def shard_plan(self, n, ndev, bytes_per_elem=0, pipelined=False):
+        """[(lo, hi, device_slot, lane)] -- the partition a sharded call uses (pure arithmetic, no GPU needed)"""
+        cap = 1 << 16
+        lo, hi = (C.c_size_t * cap)(), (C.c_size_t * cap)()
+        slot, lane = (C.c_int * cap)(), (C.c_int * cap)()
+        f = self.lib.goldilocks_b200_shard_plan
+        f.restype = C.c_size_t
+        k = f(lo, hi, slot, lane, _Z(cap), _Z(n), C.c_int(ndev), _Z(bytes_per_elem), C.c_int(1 if pipelined else 0))
+        assert k <= cap
+        return [(lo[i], hi[i], slot[i], lane[i]) for i in range(k)]
+
     # ---- tables ----
     def export_comb_table(self):
         out = np.empty(15360, np.uint8)

@@ -16,6 +16,7 @@
 #include "../../include/goldilocks_b200.h"
 #include "launch.cuh"
 #include "staged.cuh"
+#include "shard.h"
 
 // kernels live in k_*.cu
 LANES_PLAIN(DECLARE_PLAIN)
@@ -36,7 +37,7 @@ struct Block { void *p; size_t cap; };
 struct Ctx {
     std::mutex mu;
     bool ready = false, failed = false;
-    int dev = -1, sms = 0;
+    int dev = -1, lane = 0, sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // signatures and messages of a verification cross PCIe here while the main stream groups the keys
     cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -51,7 +52,7 @@ struct Ctx {
     size_t slot_cap = 0;
 };
 constexpr int MAX_DEV = 64;
-Ctx g_ctx[MAX_DEV];
+Ctx g_ctx[MAX_DEV][shard::LANES];   /* lane 0 serves the caller's own thread; lanes 1.. belong to the shard workers (shard.h) */
 
 bool fail(const char *what, cudaError_t e) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -166,9 +167,14 @@ bool launch_smp(Ctx &c, const F &f, size_t n, int grid, cudaStream_t s, unsigned
     if (prof) prof_end(typeid(F).name(), s, a, b);
     return true;
 }
-bool ctx_init(Ctx &c, int dev) {
+bool ctx_init(Ctx &c, int dev, int lane = 0) {
     if (c.ready) return true;
     if (c.failed) { g_err = "device initialisation failed earlier"; return false; }
+    if (lane > 0) { /* the read-only tables are built once per device, by lane 0 */
+        Ctx &c0 = g_ctx[dev][0];
+        std::lock_guard<std::mutex> g0(c0.mu);
+        if (!ctx_init(c0, dev, 0)) return false;
+    }
     c.failed = true;
     cudaDeviceProp p;
     CU(cudaGetDeviceProperties(&p, dev));
@@ -178,6 +184,7 @@ bool ctx_init(Ctx &c, int dev) {
         return false;
     }
     c.dev = dev;
+    c.lane = lane;
     c.sms = p.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
@@ -189,6 +196,13 @@ bool ctx_init(Ctx &c, int dev) {
     }
     for (auto &e : c.side_evt) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaMalloc(&c.work_counter, 256));
+    if (lane > 0) {
+        c.ft = g_ctx[dev][0].ft;
+        c.wide = g_ctx[dev][0].wide;
+        c.failed = false;
+        c.ready = true;
+        return true;
+    }
     CU(cudaMalloc(&c.ft, sizeof(fixed_tables)));
     LaneBuildTables f = {c.ft};
     if (!launch(c, f, TABLE_LANES, c.stream)) return false;
@@ -218,10 +232,17 @@ struct Call {
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) { fail("cudaGetDevice (is there a GPU?)", e); return; }
         if (dev >= MAX_DEV) { g_err = "device index too large"; return; }
-        c = &g_ctx[dev];
+        c = &g_ctx[dev][shard::t_lane];
         lk = std::unique_lock<std::mutex>(c->mu);
-        ok = ctx_init(*c, dev);
+        ok = ctx_init(*c, dev, shard::t_lane);
         if (ok && !c->blocks.empty()) c->used = 0;
+    }
+    /* device copies of secrets (private keys, scalars, nonces, window tables of the secret paths): zeroed by finish() on
+     * every path out of the call, like the reference's goldilocks_bzero of its stack copies (eddsa.c:120-126,220-229) */
+    std::vector<std::pair<void *, size_t>> wipes;
+    template <class T> T *secret(T *dev_ptr, size_t count) {
+        if (dev_ptr && count) wipes.push_back({(void *)dev_ptr, count * sizeof(T)});
+        return dev_ptr;
     }
     void *alloc(size_t bytes) {
         if (!ok) return nullptr;
@@ -277,9 +298,12 @@ struct Call {
     template <class F> int smp_grid_for() { int g = 1; if (ok) ok = smp_grid<F>(*c, &g); return g; }
     template <class F> void run_smp(const F &f, size_t n, int grid) { if (ok) ok = launch_smp(*c, f, n, grid, c->stream); }
     goldilocks_error_t finish() {
-        if (ok) {
+        if (c && c->ready && lk.owns_lock()) {
+            for (auto &w : wipes)
+                if (cudaMemsetAsync(w.first, 0, w.second, c->stream) != cudaSuccess) ok = false;
+            wipes.clear();
             cudaError_t e = cudaStreamSynchronize(c->stream);
-            if (e != cudaSuccess) ok = fail("cudaStreamSynchronize", e);
+            if (e != cudaSuccess && ok) ok = fail("cudaStreamSynchronize", e);
         }
         if (c && lk.owns_lock() && c->blocks.size() > 1) { /* coalesce into one block for the next call */
             size_t total = 0;
@@ -304,17 +328,104 @@ static_assert(sizeof(niels) == 192 && sizeof(pniels) == 256, "table layout");
 static_assert(sizeof(verify_aux) == sizeof(abi_pt), "the aux record of a signature lives in the R half of its point pair");
 
 cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
+
+// ---- device sets: one batch over several GPUs (shard.h) ---------------------------------------------------------
+std::mutex g_pool_mu;
+std::shared_ptr<shard::Pool> g_pool;                      /* null = the caller's current device only */
+std::vector<shard::Worker *> g_workers[MAX_DEV];          /* created on first use, kept for the life of the process */
+bool g_env_read = false;
+bool pool_install(const int *devs, int n) { /* g_pool_mu held */
+    if (n <= 0) { g_pool.reset(); return true; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) { g_err = "goldilocks_b200_set_devices: no CUDA device"; return false; }
+    auto pool = std::make_shared<shard::Pool>();
+    for (int i = 0; i < n; i++) {
+        if (devs[i] < 0 || devs[i] >= count || devs[i] >= MAX_DEV) { g_err = "goldilocks_b200_set_devices: device index out of range"; return false; }
+        pool->devs.push_back(devs[i]);
+    }
+    for (int d : pool->devs) {
+        if (g_workers[d].empty())
+            for (int l = 0; l < shard::LANES; l++) g_workers[d].push_back(new shard::Worker(d, l));
+        for (auto *w : g_workers[d]) pool->workers.push_back(w);
+    }
+    g_pool = pool;
+    return true;
+}
+void pool_from_env() { /* GOLDILOCKS_B200_DEVICES = "all" | "0,1,2,..." ; read once, an explicit set_devices() wins */
+    if (g_env_read) return;
+    g_env_read = true;
+    const char *e = getenv("GOLDILOCKS_B200_DEVICES");
+    if (!e || !*e) return;
+    std::vector<int> devs;
+    if (!strcmp(e, "all")) {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess) return;
+        for (int i = 0; i < count && i < MAX_DEV; i++) devs.push_back(i);
+    } else {
+        for (const char *q = e; *q;) {
+            char *end = nullptr;
+            long v = strtol(q, &end, 10);
+            if (end == q) break;
+            devs.push_back((int)v);
+            q = (*end == ',') ? end + 1 : end;
+            if (*end && *end != ',') break;
+        }
+    }
+    if (!devs.empty() && !pool_install(devs.data(), (int)devs.size()))
+        fprintf(stderr, "[goldilocks_b200] GOLDILOCKS_B200_DEVICES ignored: %s\n", g_err.c_str());
+}
+// The plan of a call, or null when it runs on the caller's device as one piece: worker threads never re-shard, a set of
+// one device only pipelines the light operations.
+constexpr size_t HEAVY_MIN = 2048;   /* elements per device below which a heavy batch is not cut */
+std::shared_ptr<shard::Pool> shard_pool(size_t n, bool pipelined, size_t bytes_per_elem) {
+    if (shard::t_worker || n < 2 * shard::MIN_CHUNK) return nullptr;
+    std::shared_ptr<shard::Pool> p;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        pool_from_env();
+        p = g_pool;
+    }
+    if (!p) return nullptr;
+    if (!pipelined && (p->devs.size() < 2 || n < 2 * HEAVY_MIN)) return nullptr;
+    if (pipelined && p->devs.size() < 2 && n * bytes_per_elem < 2 * shard::CHUNK_BYTES) return nullptr;
+    return p;
+}
+template <class Fn>
+goldilocks_error_t shard_go(const std::shared_ptr<shard::Pool> &p, size_t n, bool pipelined, size_t bytes_per_elem, Fn fn) {
+    std::string err;
+    const int r = shard::run(p, n, HEAVY_MIN, bytes_per_elem, pipelined, &err, fn);
+    if (r != -1) g_err = err;
+    return r == -1 ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+}
+// SHARD_HEAVY / SHARD_LIGHT(bytes per element) open a batch entry point: with a device set configured the call re-enters
+// itself once per range on the workers (`lo` = first element, `m` = count of the range) and returns their verdict.
+#define SHARD_HEAVY(n, call) \
+    if (auto pool_ = shard_pool((n), false, 0)) return shard_go(pool_, (n), false, 0, [=](size_t lo, size_t m) { return (call); });
+#define SHARD_LIGHT(n, bytes, call) \
+    if (auto pool_ = shard_pool((n), true, (bytes))) return shard_go(pool_, (n), true, (bytes), [=](size_t lo, size_t m) { return (call); });
+// offsets of messages [lo, lo + m] rebased to the first one of the range
+struct SubOffsets {
+    std::vector<size_t> v;
+    SubOffsets(const size_t *off, size_t lo, size_t m) : v(m + 1) { for (size_t i = 0; i <= m; i++) v[i] = off[lo + i] - off[lo]; }
+};
 // Device-pointer entry points only need the tables; they never touch the arena or the lock while
 // kernels run (the caller owns the stream ordering).
 Ctx *dev_ctx() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEV) { g_err = "no CUDA device"; return nullptr; }
-    Ctx &c = g_ctx[dev];
+    Ctx &c = g_ctx[dev][shard::t_lane];
     std::lock_guard<std::mutex> g(c.mu);
-    return ctx_init(c, dev) ? &c : nullptr;
+    return ctx_init(c, dev, shard::t_lane) ? &c : nullptr;
 }
 
 }  // namespace
+
+namespace shard {
+thread_local bool t_worker = false;
+thread_local int t_lane = 0;
+const std::string &worker_error() { return g_err; }
+std::shared_ptr<Pool> current() { std::lock_guard<std::mutex> g(g_pool_mu); return g_pool; }
+}  // namespace shard
 
 extern "C" {
 
@@ -331,6 +442,37 @@ const size_t goldilocks_448_sizeof_precomputed_s = 15360, goldilocks_448_alignof
 goldilocks_error_t goldilocks_b200_init(void) { Call k; return k.finish(); }
 const char *goldilocks_b200_last_error(void) { return g_err.c_str(); }
 uint64_t goldilocks_b200_launch_count(void) { return g_launches.load(); }
+goldilocks_error_t goldilocks_b200_set_devices(const int *devices, int count) {
+    std::shared_ptr<shard::Pool> p;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        g_env_read = true; /* an explicit set wins over GOLDILOCKS_B200_DEVICES */
+        if (!pool_install(devices, count)) return GOLDILOCKS_FAILURE;
+        p = g_pool;
+    }
+    if (!p) return GOLDILOCKS_SUCCESS;
+    /* build every device's tables now (in parallel, on the workers), not inside the first timed call */
+    std::string err;
+    const int r = shard::run_everywhere(p, &err, [](size_t, size_t) { return (int)goldilocks_b200_init(); });
+    if (r != -1) { g_err = err; return GOLDILOCKS_FAILURE; }
+    return GOLDILOCKS_SUCCESS;
+}
+int goldilocks_b200_get_devices(int *devices, int max) {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    pool_from_env();
+    if (!g_pool) return 0;
+    const int n = (int)g_pool->devs.size();
+    for (int i = 0; i < n && i < max; i++) devices[i] = g_pool->devs[i];
+    return n;
+}
+size_t goldilocks_b200_shard_plan(size_t *lo, size_t *hi, int *device_slot, int *lane, size_t max, size_t n, int ndev, size_t bytes_per_elem, int pipelined) {
+    const std::vector<shard::Piece> pl = shard::plan(n, ndev, HEAVY_MIN, bytes_per_elem, pipelined != 0);
+    for (size_t i = 0; i < pl.size() && i < max; i++) {
+        lo[i] = pl[i].lo; hi[i] = pl[i].hi;
+        device_slot[i] = pl[i].slot / shard::LANES; lane[i] = pl[i].slot % shard::LANES;
+    }
+    return pl.size();
+}
 void goldilocks_b200_profile(int enable) {
     std::lock_guard<std::mutex> g(g_prof_mu);
     if (enable) {
@@ -410,6 +552,7 @@ goldilocks_error_t goldilocks_b200_export_wnaf_table(uint8_t out[6144]) {
 // ---- field level ---------------------------------------------------------------------------------------
 #define GF_BINOP(NAME, OP)                                                                                   \
     goldilocks_error_t NAME(uint8_t *out, const uint8_t *a, const uint8_t *b, size_t n) {                    \
+        SHARD_LIGHT(n, 168, NAME(out + 56 * lo, a + 56 * lo, b + 56 * lo, m))                                \
         Call k;                                                                                              \
         LaneGf<OP> f = {k.out<uint8_t>(56 * n), nullptr, k.in(a, 56 * n), k.in(b, 56 * n), 0};               \
         k.run(f, n);                                                                                         \
@@ -420,6 +563,7 @@ GF_BINOP(goldilocks_448_gf_mul_batch, GFOP_MUL)
 GF_BINOP(goldilocks_448_gf_add_batch, GFOP_ADD)
 GF_BINOP(goldilocks_448_gf_sub_batch, GFOP_SUB)
 goldilocks_error_t goldilocks_448_gf_sqr_batch(uint8_t *out, const uint8_t *a, size_t n) {
+    SHARD_LIGHT(n, 112, goldilocks_448_gf_sqr_batch(out + 56 * lo, a + 56 * lo, m))
     Call k;
     LaneGf<GFOP_SQR> f = {k.out<uint8_t>(56 * n), nullptr, k.in(a, 56 * n), nullptr, 0};
     k.run(f, n);
@@ -427,6 +571,7 @@ goldilocks_error_t goldilocks_448_gf_sqr_batch(uint8_t *out, const uint8_t *a, s
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_gf_mulw_batch(uint8_t *out, const uint8_t *a, uint32_t w, size_t n) {
+    SHARD_LIGHT(n, 112, goldilocks_448_gf_mulw_batch(out + 56 * lo, a + 56 * lo, w, m))
     Call k;
     if (w >= (1u << 28)) { g_err = "gf_mulw: w must be < 2^28"; return GOLDILOCKS_FAILURE; }
     LaneGf<GFOP_MULW> f = {k.out<uint8_t>(56 * n), nullptr, k.in(a, 56 * n), nullptr, w};
@@ -435,6 +580,7 @@ goldilocks_error_t goldilocks_448_gf_mulw_batch(uint8_t *out, const uint8_t *a, 
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_gf_isr_batch(uint8_t *out, goldilocks_error_t *status, const uint8_t *x, size_t n) {
+    SHARD_LIGHT(n, 116, goldilocks_448_gf_isr_batch(out + 56 * lo, status + lo, x + 56 * lo, m))
     Call k;
     LaneGf<GFOP_ISR> f = {k.out<uint8_t>(56 * n), k.out<int32_t>(n), k.in(x, 56 * n), nullptr, 0};
     k.run(f, n);
@@ -443,6 +589,7 @@ goldilocks_error_t goldilocks_448_gf_isr_batch(uint8_t *out, goldilocks_error_t 
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_gf_invert_batch(uint8_t *out, const uint8_t *x, size_t n) {
+    SHARD_LIGHT(n, 112, goldilocks_448_gf_invert_batch(out + 56 * lo, x + 56 * lo, m))
     Call k;
     LaneGf<GFOP_INVERT> f = {k.out<uint8_t>(56 * n), nullptr, k.in(x, 56 * n), nullptr, 0};
     k.run(f, n);
@@ -453,6 +600,7 @@ goldilocks_error_t goldilocks_448_gf_invert_batch(uint8_t *out, const uint8_t *x
 // ---- group level ---------------------------------------------------------------------------------------
 #define PT_BINOP(NAME, OP)                                                                                   \
     goldilocks_error_t NAME(hpt *out, const hpt *a, const hpt *b, size_t n) {                                \
+        SHARD_LIGHT(n, 768, NAME(out + lo, a + lo, b + lo, m))                                               \
         Call k;                                                                                              \
         LanePt<OP> f = {k.out<abi_pt>(n), k.in(P(a), n), k.in(P(b), n)};                                     \
         k.run(f, n);                                                                                         \
@@ -463,6 +611,7 @@ PT_BINOP(goldilocks_448_point_add_batch, PTOP_ADD)
 PT_BINOP(goldilocks_448_point_sub_batch, PTOP_SUB)
 #define PT_UNOP(NAME, OP)                                                                                    \
     goldilocks_error_t NAME(hpt *out, const hpt *a, size_t n) {                                              \
+        SHARD_LIGHT(n, 512, NAME(out + lo, a + lo, m))                                                       \
         Call k;                                                                                              \
         LanePt<OP> f = {k.out<abi_pt>(n), k.in(P(a), n), nullptr};                                           \
         k.run(f, n);                                                                                         \
@@ -473,6 +622,7 @@ PT_UNOP(goldilocks_448_point_double_batch, PTOP_DBL)
 PT_UNOP(goldilocks_448_point_negate_batch, PTOP_NEG)
 PT_UNOP(goldilocks_448_point_debugging_torque_batch, PTOP_TORQUE)
 goldilocks_error_t goldilocks_448_point_debugging_pscale_batch(hpt *out, const hpt *a, const uint8_t *factor, size_t n) {
+    SHARD_LIGHT(n, 568, goldilocks_448_point_debugging_pscale_batch(out + lo, a + lo, factor + 56 * lo, m))
     Call k;
     LanePtPscale f = {k.out<abi_pt>(n), k.in(P(a), n), k.in(factor, 56 * n)};
     k.run(f, n);
@@ -481,6 +631,7 @@ goldilocks_error_t goldilocks_448_point_debugging_pscale_batch(hpt *out, const h
 }
 
 goldilocks_error_t goldilocks_448_point_eq_batch(goldilocks_bool_t *out, const hpt *a, const hpt *b, size_t n) {
+    SHARD_LIGHT(n, 520, goldilocks_448_point_eq_batch(out + lo, a + lo, b + lo, m))
     Call k;
     LanePtEq f = {k.out<uint64_t>(n), k.in(P(a), n), k.in(P(b), n)};
     k.run(f, n);
@@ -488,6 +639,7 @@ goldilocks_error_t goldilocks_448_point_eq_batch(goldilocks_bool_t *out, const h
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_valid_batch(goldilocks_bool_t *out, const hpt *a, size_t n) {
+    SHARD_LIGHT(n, 264, goldilocks_448_point_valid_batch(out + lo, a + lo, m))
     Call k;
     LanePtValid f = {k.out<uint64_t>(n), k.in(P(a), n)};
     k.run(f, n);
@@ -495,6 +647,7 @@ goldilocks_error_t goldilocks_448_point_valid_batch(goldilocks_bool_t *out, cons
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_encode_batch(uint8_t *ser, const hpt *pts, size_t n) {
+    SHARD_LIGHT(n, 312, goldilocks_448_point_encode_batch(ser + 56 * lo, pts + lo, m))
     Call k;
     LanePtEncode f = {k.out<uint8_t>(56 * n), k.in(P(pts), n)};
     k.run(f, n);
@@ -502,6 +655,7 @@ goldilocks_error_t goldilocks_448_point_encode_batch(uint8_t *ser, const hpt *pt
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_decode_batch(hpt *pts, goldilocks_error_t *status, const uint8_t *ser, goldilocks_bool_t allow_identity, size_t n) {
+    SHARD_LIGHT(n, 316, goldilocks_448_point_decode_batch(pts + lo, status + lo, ser + 56 * lo, allow_identity, m))
     Call k;
     LanePtDecode f = {k.out<abi_pt>(n), k.out<int32_t>(n), k.in(ser, 56 * n), allow_identity ? 1u : 0u};
     k.run(f, n);
@@ -510,6 +664,7 @@ goldilocks_error_t goldilocks_448_point_decode_batch(hpt *pts, goldilocks_error_
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_from_hash_nonuniform_batch(hpt *pts, const uint8_t *hashed, size_t n) {
+    SHARD_LIGHT(n, 312, goldilocks_448_point_from_hash_nonuniform_batch(pts + lo, hashed + 56 * lo, m))
     Call k;
     LaneFromHash<false> f = {k.out<abi_pt>(n), k.in(hashed, 56 * n)};
     k.run(f, n);
@@ -517,6 +672,7 @@ goldilocks_error_t goldilocks_448_point_from_hash_nonuniform_batch(hpt *pts, con
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_from_hash_uniform_batch(hpt *pts, const uint8_t *hashed, size_t n) {
+    SHARD_LIGHT(n, 368, goldilocks_448_point_from_hash_uniform_batch(pts + lo, hashed + 112 * lo, m))
     Call k;
     LaneFromHash<true> f = {k.out<abi_pt>(n), k.in(hashed, 112 * n)};
     k.run(f, n);
@@ -524,6 +680,7 @@ goldilocks_error_t goldilocks_448_point_from_hash_uniform_batch(hpt *pts, const 
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_invert_elligator_nonuniform_batch(uint8_t *recovered, goldilocks_error_t *status, const hpt *pts, const uint32_t *which, size_t n) {
+    SHARD_LIGHT(n, 320, goldilocks_448_invert_elligator_nonuniform_batch(recovered + 56 * lo, status + lo, pts + lo, which + lo, m))
     Call k;
     LaneInvertElligator<false> f = {k.out<uint8_t>(56 * n), k.out<int32_t>(n), k.in(P(pts), n), k.in(which, n)};
     k.run(f, n);
@@ -532,6 +689,7 @@ goldilocks_error_t goldilocks_448_invert_elligator_nonuniform_batch(uint8_t *rec
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_invert_elligator_uniform_batch(uint8_t *partial, goldilocks_error_t *status, const hpt *pts, const uint32_t *which, size_t n) {
+    SHARD_LIGHT(n, 488, goldilocks_448_invert_elligator_uniform_batch(partial + 112 * lo, status + lo, pts + lo, which + lo, m))
     Call k;
     LaneInvertElligator<true> f = {k.in(partial, 112 * n), k.out<int32_t>(n), k.in(P(pts), n), k.in(which, n)};
     k.run(f, n);
@@ -540,6 +698,7 @@ goldilocks_error_t goldilocks_448_invert_elligator_uniform_batch(uint8_t *partia
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(uint8_t *enc, const hpt *pts, size_t n) {
+    SHARD_LIGHT(n, 313, goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch(enc + 57 * lo, pts + lo, m))
     Call k;
     LaneEncodeEddsa f = {k.out<uint8_t>(57 * n), k.in(P(pts), n)};
     k.run(f, n);
@@ -547,6 +706,7 @@ goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_eddsa_batch
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(hpt *pts, goldilocks_error_t *status, const uint8_t *enc, size_t n) {
+    SHARD_LIGHT(n, 317, goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch(pts + lo, status + lo, enc + 57 * lo, m))
     Call k;
     LaneDecodeEddsa f = {k.out<abi_pt>(n), k.out<int32_t>(n), k.in(enc, 57 * n)};
     k.run(f, n);
@@ -555,6 +715,7 @@ goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio_batch
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(uint8_t *out, const hpt *pts, size_t n) {
+    SHARD_LIGHT(n, 312, goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(out + 56 * lo, pts + lo, m))
     Call k;
     LaneEncodeX448 f = {k.out<uint8_t>(56 * n), k.in(P(pts), n)};
     k.run(f, n);
@@ -564,9 +725,10 @@ goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(
 
 // ---- scalar multiplications ------------------------------------------------------------------------------
 goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(hpt *out, const goldilocks_448_precomputed_s *base, const hsc *scalar, size_t n) {
+    SHARD_LIGHT(n, 312, goldilocks_448_precomputed_scalarmul_batch(out + lo, base, scalar + lo, m))
     Call k;
     if (base == goldilocks_448_precomputed_base) { /* the library's own base-point table: doubling-free comb */
-        SlotComb f = {k.out<abi_pt>(n), k.in(S(scalar), n), k.ok ? k.c->ft : nullptr};
+        SlotComb f = {k.out<abi_pt>(n), k.secret(k.in(S(scalar), n), n), k.ok ? k.c->ft : nullptr};
         k.run_sm(f, n);
         k.fetch(P(out), f.out, n);
         return k.finish();
@@ -576,13 +738,14 @@ goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(hpt *out, const go
     niels *tab = k.out<niels>(COMB_ENTRIES);
     LaneNielsFromAbi cv = {tab, up};
     k.run(cv, COMB_ENTRIES);
-    SlotCombTable f = {k.out<abi_pt>(n), k.in(S(scalar), n), tab};
+    SlotCombTable f = {k.out<abi_pt>(n), k.secret(k.in(S(scalar), n), n), tab};
     k.run_sm(f, n);
     k.fetch(P(out), f.out, n);
     return k.finish();
 }
 /* tables[k] = precompute(points[k]): 15 360 bytes each, byte-identical to the reference's (goldilocks.c:757-818) */
 goldilocks_error_t goldilocks_448_precompute_batch(goldilocks_448_precomputed_s *tables, const hpt *points, size_t n) {
+    SHARD_LIGHT(n, 15616, goldilocks_448_precompute_batch((goldilocks_448_precomputed_s *)((uint8_t *)tables + 15360 * lo), points + lo, m))
     Call k;
     LanePrecompute f = {k.out<abi_niels>(COMB_ENTRIES * n), k.in(P(points), n), k.out<niels>(16 * COMB_N * n)};
     k.run(f, COMB_N * n);
@@ -590,9 +753,10 @@ goldilocks_error_t goldilocks_448_precompute_batch(goldilocks_448_precomputed_s 
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_dual_scalarmul_batch(hpt *out1, hpt *out2, const hpt *base, const hsc *scalar1, const hsc *scalar2, size_t n) {
+    SHARD_HEAVY(n, goldilocks_448_point_dual_scalarmul_batch(out1 + lo, out2 + lo, base + lo, scalar1 + lo, scalar2 + lo, m))
     Call k;
     int grid = k.smp_grid_for<SlotDualScalarmul>();
-    SlotDualScalarmul f = {k.out<abi_pt>(n), k.out<abi_pt>(n), k.in(P(base), n), k.in(S(scalar1), n), k.in(S(scalar2), n), k.slots((size_t)grid * SLOT_BLOCK, 1)};
+    SlotDualScalarmul f = {k.secret(k.out<abi_pt>(n), n), k.secret(k.out<abi_pt>(n), n), k.in(P(base), n), k.secret(k.in(S(scalar1), n), n), k.secret(k.in(S(scalar2), n), n), k.slots((size_t)grid * SLOT_BLOCK, 1)};
     k.run_smp(f, n, grid);
     k.fetch(P(out1), f.out1, n);
     k.fetch(P(out2), f.out2, n);
@@ -600,10 +764,12 @@ goldilocks_error_t goldilocks_448_point_dual_scalarmul_batch(hpt *out1, hpt *out
 }
 goldilocks_error_t goldilocks_448_direct_scalarmul_batch(uint8_t *scaled, goldilocks_error_t *status, const uint8_t *base, const hsc *scalar,
                                                          goldilocks_bool_t allow_identity, goldilocks_bool_t short_circuit, size_t n) {
+    SHARD_HEAVY(n, goldilocks_448_direct_scalarmul_batch(scaled + 56 * lo, status + lo, base + 56 * lo, scalar + lo, allow_identity, short_circuit, m))
     Call k;
     int grid = k.smp_grid_for<SlotDirectScalarmul>();
     uint8_t *dout = k.in(scaled, 56 * n); /* short-circuited elements keep the caller's bytes */
-    SlotDirectScalarmul f = {dout, k.out<int32_t>(n), k.in(base, 56 * n), k.in(S(scalar), n), allow_identity ? 1u : 0u, short_circuit ? 1u : 0u,
+    k.secret(dout, 56 * n);
+    SlotDirectScalarmul f = {dout, k.out<int32_t>(n), k.in(base, 56 * n), k.secret(k.in(S(scalar), n), n), allow_identity ? 1u : 0u, short_circuit ? 1u : 0u,
                              k.ok ? k.c->ft : nullptr, k.slots((size_t)grid * SLOT_BLOCK, 1)};
     k.run_smp(f, n, grid);
     k.fetch(scaled, dout, 56 * n);
@@ -611,23 +777,26 @@ goldilocks_error_t goldilocks_448_direct_scalarmul_batch(uint8_t *scaled, goldil
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_scalarmul_batch(hpt *out, const hpt *base, const hsc *scalar, size_t n) {
+    SHARD_HEAVY(n, goldilocks_448_point_scalarmul_batch(out + lo, base + lo, scalar + lo, m))
     Call k;
     int grid = k.smp_grid_for<SlotScalarmul>();
-    SlotScalarmul f = {k.out<abi_pt>(n), k.in(P(base), n), k.in(S(scalar), n), k.slots((size_t)grid * SLOT_BLOCK, 1)};
+    SlotScalarmul f = {k.secret(k.out<abi_pt>(n), n), k.in(P(base), n), k.secret(k.in(S(scalar), n), n), k.slots((size_t)grid * SLOT_BLOCK, 1)};
     k.run_smp(f, n, grid);
     k.fetch(P(out), f.out, n);
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_point_double_scalarmul_batch(hpt *out, const hpt *base1, const hsc *scalar1, const hpt *base2, const hsc *scalar2, size_t n) {
+    SHARD_HEAVY(n, goldilocks_448_point_double_scalarmul_batch(out + lo, base1 + lo, scalar1 + lo, base2 + lo, scalar2 + lo, m))
     Call k;
     int grid = k.smp_grid_for<SlotDoubleScalarmul>();
-    SlotDoubleScalarmul f = {k.out<abi_pt>(n), k.in(P(base1), n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n),
+    SlotDoubleScalarmul f = {k.secret(k.out<abi_pt>(n), n), k.in(P(base1), n), k.secret(k.in(S(scalar1), n), n), k.in(P(base2), n), k.secret(k.in(S(scalar2), n), n),
                              k.slots((size_t)grid * SLOT_BLOCK, 2), (size_t)grid * SLOT_BLOCK};
     k.run_smp(f, n, grid);
     k.fetch(P(out), f.out, n);
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *out, const hsc *scalar1, const hpt *base2, const hsc *scalar2, size_t n) {
+    SHARD_HEAVY(n, goldilocks_448_base_double_scalarmul_non_secret_batch(out + lo, scalar1 + lo, base2 + lo, scalar2 + lo, m))
     Call k;
     int grid = k.smp_grid_for<SlotBaseDoubleScalarmul>();
     SlotBaseDoubleScalarmul f = {k.out<abi_pt>(n), k.in(S(scalar1), n), k.in(P(base2), n), k.in(S(scalar2), n), k.ok ? k.c->wide : nullptr,
@@ -640,6 +809,7 @@ goldilocks_error_t goldilocks_448_base_double_scalarmul_non_secret_batch(hpt *ou
 // ---- scalars -----------------------------------------------------------------------------------------------
 #define SC_BINOP(NAME, OP)                                                                                   \
     goldilocks_error_t NAME(hsc *out, const hsc *a, const hsc *b, size_t n) {                                \
+        SHARD_LIGHT(n, 168, NAME(out + lo, a + lo, b + lo, m))                                               \
         Call k;                                                                                              \
         LaneSc<OP> f = {k.out<abi_sc>(n), k.in(S(a), n), k.in(S(b), n)};                                     \
         k.run(f, n);                                                                                         \
@@ -650,6 +820,7 @@ SC_BINOP(goldilocks_448_scalar_add_batch, SCOP_ADD)
 SC_BINOP(goldilocks_448_scalar_sub_batch, SCOP_SUB)
 SC_BINOP(goldilocks_448_scalar_mul_batch, SCOP_MUL)
 goldilocks_error_t goldilocks_448_scalar_invert_batch(hsc *out, goldilocks_error_t *status, const hsc *a, size_t n) {
+    SHARD_LIGHT(n, 116, goldilocks_448_scalar_invert_batch(out + lo, status + lo, a + lo, m))
     Call k;
     LaneScInvert f = {k.out<abi_sc>(n), k.out<int32_t>(n), k.in(S(a), n)};
     k.run(f, n);
@@ -658,6 +829,7 @@ goldilocks_error_t goldilocks_448_scalar_invert_batch(hsc *out, goldilocks_error
     return k.finish();
 }
 goldilocks_error_t goldilocks_ed448_convert_public_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) {
+    SHARD_LIGHT(n, 113, goldilocks_ed448_convert_public_key_to_x448_batch(x + 56 * lo, ed + 57 * lo, m))
     Call k;
     LaneEdPkToX448 f = {k.out<uint8_t>(56 * n), k.in(ed, 57 * n)};
     k.run(f, n);
@@ -665,14 +837,15 @@ goldilocks_error_t goldilocks_ed448_convert_public_key_to_x448_batch(uint8_t *x,
     return k.finish();
 }
 goldilocks_error_t goldilocks_ed448_convert_private_key_to_x448_batch(uint8_t *x, const uint8_t *ed, size_t n) {
+    SHARD_LIGHT(n, 113, goldilocks_ed448_convert_private_key_to_x448_batch(x + 56 * lo, ed + 57 * lo, m))
     Call k;
-    LaneEdSkToX448 f = {k.out<uint8_t>(56 * n), k.in(ed, 57 * n)};
+    LaneEdSkToX448 f = {k.secret(k.out<uint8_t>(56 * n), 56 * n), k.secret(k.in(ed, 57 * n), 57 * n)};
     k.run(f, n);
     k.fetch(x, f.x, 56 * n);
-    if (k.ok) cudaMemsetAsync((void *)f.ed, 0, 57 * n, k.c->stream); /* wipe the private keys' device copy */
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_scalar_halve_batch(hsc *out, const hsc *a, size_t n) {
+    SHARD_LIGHT(n, 112, goldilocks_448_scalar_halve_batch(out + lo, a + lo, m))
     Call k;
     LaneSc<SCOP_HALVE> f = {k.out<abi_sc>(n), k.in(S(a), n), nullptr};
     k.run(f, n);
@@ -680,6 +853,7 @@ goldilocks_error_t goldilocks_448_scalar_halve_batch(hsc *out, const hsc *a, siz
     return k.finish();
 }
 goldilocks_error_t goldilocks_448_scalar_decode_long_batch(hsc *out, const uint8_t *ser, size_t ser_len, size_t n) {
+    SHARD_LIGHT(n, ser_len + 56, goldilocks_448_scalar_decode_long_batch(out + lo, ser + ser_len * lo, ser_len, m))
     Call k;
     LaneScDecodeLong f = {k.out<abi_sc>(n), k.in(ser, ser_len * n), ser_len};
     k.run(f, n);
@@ -689,21 +863,25 @@ goldilocks_error_t goldilocks_448_scalar_decode_long_batch(hsc *out, const uint8
 
 // ---- CFRG ----------------------------------------------------------------------------------------------------
 goldilocks_error_t goldilocks_x448_batch(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n) {
+    SHARD_HEAVY(n, goldilocks_x448_batch(out + 56 * lo, status + lo, base + 56 * lo, scalar + 56 * lo, m))
     Call k;
-    SlotX448 f = {k.out<uint8_t>(56 * n), k.out<int32_t>(n), k.in(base, 56 * n), k.in(scalar, 56 * n)};
+    SlotX448 f = {k.secret(k.out<uint8_t>(56 * n), 56 * n), k.out<int32_t>(n), k.in(base, 56 * n), k.secret(k.in(scalar, 56 * n), 56 * n)};
     k.run_sm(f, n);
     k.fetch(out, f.out, 56 * n);
     k.fetch((int32_t *)status, f.status, n);
     return k.finish();
 }
 goldilocks_error_t goldilocks_x448_derive_public_key_batch(uint8_t *out, const uint8_t *scalar, size_t n) {
+    SHARD_HEAVY(n, goldilocks_x448_derive_public_key_batch(out + 56 * lo, scalar + 56 * lo, m))
     Call k;
-    SlotX448DerivePk f = {k.out<uint8_t>(56 * n), k.in(scalar, 56 * n), k.ok ? k.c->ft : nullptr};
+    SlotX448DerivePk f = {k.out<uint8_t>(56 * n), k.secret(k.in(scalar, 56 * n), 56 * n), k.ok ? k.c->ft : nullptr};
     k.run_sm(f, n);
     k.fetch(out, f.out, 56 * n);
     return k.finish();
 }
 goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out, size_t outlen, const uint8_t *in, const size_t *in_off, size_t n) {
+    if (n == 0) return GOLDILOCKS_SUCCESS;
+    SHARD_LIGHT(n, outlen + in_off[n] / n, goldilocks_shake256_hash_batch(out + outlen * lo, outlen, in + in_off[lo], SubOffsets(in_off, lo, m).v.data(), m))
     Call k;
     size_t total = n ? in_off[n] : 0;
     LaneShake256 f = {k.out<uint8_t>(outlen * n), outlen, k.in(in, total), k.in(in_off, n + 1)};
@@ -712,23 +890,26 @@ goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out, size_t outlen, c
     return k.finish();
 }
 goldilocks_error_t goldilocks_ed448_derive_public_key_batch(uint8_t *pubkey, const uint8_t *privkey, size_t n) {
+    SHARD_HEAVY(n, goldilocks_ed448_derive_public_key_batch(pubkey + 57 * lo, privkey + 57 * lo, m))
     Call k;
-    SlotEdDerivePk f = {k.out<uint8_t>(57 * n), k.in(privkey, 57 * n), k.ok ? k.c->ft : nullptr};
+    SlotEdDerivePk f = {k.out<uint8_t>(57 * n), k.secret(k.in(privkey, 57 * n), 57 * n), k.ok ? k.c->ft : nullptr};
     k.run_sm(f, n);
     k.fetch(pubkey, f.pk, 57 * n);
     return k.finish();
 }
 goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t *privkey, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n) {
+    if (n == 0) return GOLDILOCKS_SUCCESS;
+    SHARD_HEAVY(n, goldilocks_ed448_sign_batch(signature + 114 * lo, privkey + 57 * lo, pubkey + 57 * lo, msg + msg_off[lo], SubOffsets(msg_off, lo, m).v.data(), prehashed, context, context_len, m))
     Call k;
     size_t total = n ? msg_off[n] : 0;
     const uint8_t *dmsg = k.in(msg, total);
     const size_t *doff = k.in(msg_off, n + 1);
     const uint8_t *dctx = k.in(context, context_len);
-    const uint8_t *dsk = k.in(privkey, 57 * n), *dpk = k.in(pubkey, 57 * n);
-    abi_sc *secret = k.out<abi_sc>(n), *nonce = k.out<abi_sc>(n), *nonce4 = k.out<abi_sc>(n);
+    const uint8_t *dsk = k.secret(k.in(privkey, 57 * n), 57 * n), *dpk = k.in(pubkey, 57 * n);
+    abi_sc *secret = k.secret(k.out<abi_sc>(n), n), *nonce = k.secret(k.out<abi_sc>(n), n), *nonce4 = k.secret(k.out<abi_sc>(n), n);
     uint8_t *dsig = k.out<uint8_t>(114 * n);
-    uint8_t *seed = k.out<uint8_t>(57 * n);
+    uint8_t *seed = k.secret(k.out<uint8_t>(57 * n), 57 * n);
     LaneEdSignExpand f0 = {secret, seed, dsk};
     k.run(f0, n);
     LaneEdSignNonce f1 = {nonce, nonce4, seed, dmsg, doff, prehashed, dctx, context_len};
@@ -738,13 +919,7 @@ goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t
     LaneEdSignFinish f3 = {dsig, secret, nonce, dpk, dmsg, doff, prehashed, dctx, context_len};
     k.run(f3, n);
     k.fetch(signature, dsig, 114 * n);
-    if (k.ok) { /* wipe secret scratch */
-        cudaMemsetAsync(secret, 0, sizeof(abi_sc) * n, k.c->stream);
-        cudaMemsetAsync(nonce, 0, sizeof(abi_sc) * n, k.c->stream);
-        cudaMemsetAsync(nonce4, 0, sizeof(abi_sc) * n, k.c->stream);
-        cudaMemsetAsync(seed, 0, 57 * n, k.c->stream);
-    }
-    return k.finish();
+    return k.finish(); /* zeroes the device copies of the private keys, secret scalars, nonces and seeds on every path */
 }
 
 // Batches of at least VERIFY_GROUP_MIN signatures are grouped by public key on the device (k_group.cu); keys that
@@ -752,7 +927,7 @@ goldilocks_error_t goldilocks_ed448_sign_batch(uint8_t *signature, const uint8_t
 constexpr size_t VERIFY_GROUP_MIN = 64;
 static size_t verify_tab_cap(size_t n) { return n / 4 + 1; }
 static bool verify_groups(size_t n) { return n >= VERIFY_GROUP_MIN && n < ((size_t)1 << 31); } /* the work lists are 32-bit */
-size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
+static size_t verify_core_scratch_bytes(size_t n) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t base = al(2 * n * sizeof(abi_pt)) + al(2 * n * sizeof(int32_t)) + 2 * al(n * sizeof(abi_sc));
     if (verify_groups(n)) base += al(group_scratch_bytes(n, verify_tab_cap(n))) + al(verify_tab_cap(n) * KTAB_QUADS * sizeof(uint4));
@@ -761,6 +936,21 @@ size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
 struct VerifyGrids { int unique = 1, shared = 1, tables = 1; };
 static bool verify_grids(Ctx &c, VerifyGrids *g) {
     return smp_grid<SlotEdVerifyFinish>(c, &g->unique) && smp_grid<SlotEdVerifyFinishShared>(c, &g->shared) && smp_grid<SlotKeyTables>(c, &g->tables);
+}
+// per-thread window tables of the stand-alone signatures (wtab, slot_algos.cuh): one per resident lane of the finish kernel
+static size_t verify_slot_bytes(const VerifyGrids &g, size_t n) {
+    size_t lanes = (size_t)(g.unique > g.shared ? g.unique : g.shared) * SLOT_BLOCK;
+    const size_t need = (n + SLOT_BLOCK - 1) / SLOT_BLOCK * SLOT_BLOCK;
+    if (lanes > need) lanes = need;
+    return (lanes * WTAB_QUADS_PER_LANE * sizeof(uint4) + 255) & ~(size_t)255;
+}
+size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
+    /* the device-pointer call carves EVERYTHING it writes from the caller's scratch (two verifications in flight on two
+     * streams share nothing), so the figure includes the window tables and depends on the current device's SM count */
+    Ctx *c = dev_ctx();
+    VerifyGrids grids;
+    if (!c || !verify_grids(*c, &grids)) return 0;
+    return verify_core_scratch_bytes(n) + verify_slot_bytes(grids, n);
 }
 // Host-pointer calls feed the signatures and messages in two halves on the copy stream: [0, split) is on the device
 // when ready[0] fires, the rest at ready[1]; the public keys (all the grouping pass needs) go first on the main stream.
@@ -818,6 +1008,8 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
 }
 goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                  uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n) {
+    if (n == 0) return GOLDILOCKS_SUCCESS;
+    SHARD_HEAVY(n, goldilocks_ed448_verify_batch(status + lo, signature + 114 * lo, pubkey + 57 * lo, msg + msg_off[lo], SubOffsets(msg_off, lo, m).v.data(), prehashed, context, context_len, m))
     /* One pass over the whole batch (splitting the BATCH costs more than it hides: every chunk pays its own key-grouping
      * pass and key-table wave, 67.9 ms split vs 66.3 ms whole at 2^20).  Only the COPIES are split: keys first, then the
      * signatures and messages in two halves on the copy stream, so the grouping pass, the per-key decodes and the first
@@ -833,7 +1025,7 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
     if (k.ok) k.ok = verify_grids(*k.c, &grids);
     const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
     uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
-    void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(n));
+    void *scratch = k.alloc(verify_core_scratch_bytes(n));
     VerifyFeed feed = {n >= 2 * VERIFY_GROUP_MIN ? n / 2 : n, {nullptr, nullptr}};
     if (k.ok) {
         feed.ready[0] = k.c->copy_done[0]; feed.ready[1] = k.c->copy_done[1];
@@ -910,7 +1102,7 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
         if (!verify_grids(c, &grids)) return false;
         const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
         uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
-        void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(n));
+        void *scratch = k.alloc(verify_core_scratch_bytes(n));
         if (!k.ok) return false;
         return verify_dev(c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, n, scratch, slots, grids, s);
     };
@@ -1006,6 +1198,20 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
 }
 goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                      uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, int *fast_path) {
+    if (n == 0) { if (fast_path) *fast_path = 0; return GOLDILOCKS_SUCCESS; }
+    if (auto pool_ = shard_pool(n, false, 0)) { /* every range decides its own equation; fast_path = 1 iff all of them did */
+        std::atomic<int> slow{0};
+        std::atomic<int> *slowp = &slow;
+        goldilocks_error_t r = shard_go(pool_, n, false, 0, [=](size_t lo, size_t m) {
+            int f = 0;
+            goldilocks_error_t e = goldilocks_ed448_verify_rlc_batch(status + lo, signature + 114 * lo, pubkey + 57 * lo, msg + msg_off[lo], SubOffsets(msg_off, lo, m).v.data(),
+                                                                     prehashed, context, context_len, m, &f);
+            if (!f) slowp->fetch_add(1);
+            return e;
+        });
+        if (fast_path) *fast_path = slow.load() == 0 ? 1 : 0;
+        return r;
+    }
     Call k;
     int fast = 0;
     size_t total = n ? msg_off[n] : 0;
@@ -1098,6 +1304,7 @@ size_t goldilocks_b200_keyset_size(const goldilocks_b200_keyset *ks) { return ks
 goldilocks_error_t goldilocks_ed448_verify_keyset_batch(goldilocks_error_t *status, const goldilocks_b200_keyset *ks, const uint32_t *key_index,
                                                         const uint8_t *signature, const uint8_t *msg, const size_t *msg_off, uint8_t prehashed,
                                                         const uint8_t *context, uint8_t context_len, size_t n) {
+    if (n == 0) return GOLDILOCKS_SUCCESS;
     Call k;
     if (!k.ok) return k.finish();
     if (!ks || ks->dev != k.c->dev) { g_err = "goldilocks_ed448_verify_keyset_batch: the key set lives on another device"; return GOLDILOCKS_FAILURE; }
@@ -1123,19 +1330,15 @@ goldilocks_error_t goldilocks_ed448_verify_keyset_batch(goldilocks_error_t *stat
 // ---- device-resident variants -------------------------------------------------------------------------------
 goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                      uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, void *scratch, void *stream) {
+    if (n == 0) return GOLDILOCKS_SUCCESS;
     Ctx *c = dev_ctx();
     if (!c) return GOLDILOCKS_FAILURE;
-    std::lock_guard<std::mutex> g(c->mu); /* the per-thread table slots are shared per device */
     VerifyGrids grids;
     if (!verify_grids(*c, &grids)) return GOLDILOCKS_FAILURE;
-    size_t bytes = (size_t)(grids.unique > grids.shared ? grids.unique : grids.shared) * SLOT_BLOCK * WTAB_QUADS_PER_LANE * sizeof(uint4);
-    if (bytes > c->slot_cap) {
-        if (c->slot_scratch) cudaFree(c->slot_scratch);
-        c->slot_scratch = nullptr; c->slot_cap = 0;
-        if (cudaMalloc(&c->slot_scratch, bytes) != cudaSuccess) { g_err = "cudaMalloc(slot scratch)"; return GOLDILOCKS_FAILURE; }
-        c->slot_cap = bytes;
-    }
-    return verify_dev(*c, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, scratch, (uint4 *)c->slot_scratch, grids, as_stream(stream))
+    /* nothing of the context is written while the kernels run: window tables, work lists and hand-out counters all live in
+     * the caller's scratch, so calls on different streams (and host-pointer calls of other threads) do not interfere */
+    uint4 *slots = (uint4 *)((char *)scratch + verify_core_scratch_bytes(n));
+    return verify_dev(*c, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, scratch, slots, grids, as_stream(stream))
                ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
 }
 goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream) {
@@ -1235,7 +1438,7 @@ goldilocks_error_t goldilocks_x448(uint8_t out[56], const uint8_t base[56], cons
 void goldilocks_x448_derive_public_key(uint8_t out[56], const uint8_t scalar[56]) { goldilocks_x448_derive_public_key_batch(out, scalar, 1); }
 void goldilocks_ed448_derive_secret_scalar(goldilocks_448_scalar_p secret, const uint8_t privkey[57]) {
     Call k;
-    LaneEdSecretScalar f = {k.out<abi_sc>(1), k.in(privkey, 57)};
+    LaneEdSecretScalar f = {k.secret(k.out<abi_sc>(1), 1), k.secret(k.in(privkey, 57), 57)};
     k.run(f, 1);
     k.fetch(S(secret), f.out, 1);
     k.finish();
@@ -1361,8 +1564,16 @@ size_t goldilocks_sha3_max_output_bytes(const goldilocks_keccak_sponge_p s) {
 }
 // ---- sponge CSPRNG (reference spongerng.c:92-205): host composition of the streaming calls above ----
 static void os_entropy(uint8_t *buf, size_t len) { /* stands in for the reference's RDRAND/RDTSC read (spongerng.c:28-90) */
-    FILE *f = fopen("/dev/urandom", "rb");
-    if (f) { size_t got = fread(buf, 1, len, f); (void)got; fclose(f); }
+    size_t got = 0;
+    while (got < len) {
+        ssize_t r = getrandom(buf + got, len - got, 0);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    if (got < len) { /* a non-deterministic generator without entropy must not keep going on zeros: fail closed */
+        fprintf(stderr, "[goldilocks_b200] spongerng: getrandom() failed, no entropy available\n");
+        abort();
+    }
 }
 void goldilocks_spongerng_stir(goldilocks_keccak_prng_p prng, const uint8_t *in, size_t len) {
     uint8_t seed[32];
@@ -1444,10 +1655,10 @@ goldilocks_error_t goldilocks_448_scalar_decode(goldilocks_448_scalar_p o, const
     static const uint8_t q_le[56] = {0xf3, 0x44, 0x58, 0xab, 0x92, 0xc2, 0x78, 0x23, 0x55, 0x8f, 0xc5, 0x8d, 0x72, 0xc2, 0x6c, 0x21, 0x90, 0x36, 0xd6, 0xae,
                                      0x49, 0xdb, 0x4e, 0xc4, 0xe9, 0x23, 0xca, 0x7c, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff,
                                      0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0xff, 0x3f};
-    int lt = 0;
-    for (int i = 55; i >= 0; i--) { if (ser[i] != q_le[i]) { lt = ser[i] < q_le[i]; break; } }
+    int borrow = 0; /* ser - q over all 56 bytes, no early exit: the value is often a secret scalar (the reference's loop, scalar.c:240-245) */
+    for (int i = 0; i < 56; i++) borrow = ((int)ser[i] - (int)q_le[i] - borrow) >> 8 & 1;
     goldilocks_448_scalar_decode_long_batch(o, ser, 56, 1);
-    return lt ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+    return (goldilocks_error_t)(-borrow); /* borrow = 1 iff ser < q: SUCCESS = -1, FAILURE = 0 */
 }
 void goldilocks_448_scalar_encode(uint8_t ser[56], const goldilocks_448_scalar_p s) { memcpy(ser, s->limb, 56); }
 

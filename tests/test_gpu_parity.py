@@ -28,8 +28,9 @@ def test_field_full(gpu, chk):
     parity.check_field_isr(gpu, chk, 1 << 14)
 
 
-def test_points_full(gpu, chk):
-    parity.check_points(gpu, chk, 1 << 17)
+def test_points_edge_and_glue(gpu, chk):
+    """identity / mixed representatives, negate, eq, valid (the 2^20 coordinate comparison is test_points_all_2_20)"""
+    parity.check_points(gpu, chk, 1 << 14)
 
 
 def test_codec_elligator(gpu, chk):
@@ -333,67 +334,179 @@ def test_device_pointer_entry_points_any_alignment(gpu, chk):
     torch.cuda.synchronize()
 
 
-# ---- size-independent properties at the full 2^20 batch -------------------------------------------
+def test_device_set_sharded_equals_unsharded(gpu, chk):
+    """goldilocks_b200_set_devices: ONE host-pointer batch cut into contiguous ranges over the device set (csrc/shard.h) gives
+    the bytes of the unsharded call for every kind of entry point -- heavy (one range per device: verify incl. key groups
+    that straddle a cut, RLC, sign, X448, scalar multiplications) and light (chunks pipelined over three contexts per
+    device).  On a one-GPU box the same device is listed three times, which exercises the same partition and workers."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devs = list(range(ndev)) if ndev >= 2 else [0, 0, 0]
+    n = 3 * 4096 + 77
+    sig, pk, msgs, kinds = util.verify_corpus(chk, "shard/v", n)
+    pk[100:4200] = pk[100]                                # one key group across the first cut (its signatures now fail: fine)
+    sk = stream_bytes("shard/sk", n * 57).reshape(n, 57)
+    u = stream_bytes("shard/u", n * 56).reshape(n, 56); k = stream_bytes("shard/k", n * 56).reshape(n, 56)
+    sc = util.random_scalars(chk, "shard/s", n); pts = util.random_points(chk, "shard/p", n)
+    big = 1 << 18                                          # light operations: enough traffic for several chunks per lane
+    h = stream_bytes("shard/h", big * 56).reshape(big, 56)
 
-def test_x448_full_dh_commutes(gpu, chk):
-    """config 3 at 2^20: x448(x448(5,a),b) == x448(x448(5,b),a); a checker-compared sample rides along"""
+    def run():
+        out = {}
+        out["verify"] = gpu.ed448_verify(sig, pk, msgs)
+        out["rlc"] = gpu.ed448_verify_rlc(sig, pk, msgs)[0]
+        pkd = gpu.ed448_derive_public_key(sk)
+        out["pk"] = pkd
+        out["sign"] = gpu.ed448_sign(sk, pkd, msgs, context=b"shard")
+        out["x448"], out["x448_st"] = gpu.x448(u, k)
+        out["scalarmul"] = gpu.point_encode(gpu.point_scalarmul(pts, sc))
+        out["bdsm"] = gpu.point_encode(gpu.base_double_scalarmul_non_secret(sc, pts, sc[::-1].copy()))
+        p = gpu.from_hash_nonuniform(h)
+        out["elligator"] = util.coords_fast(chk, p)
+        out["encode"] = gpu.point_encode(p)
+        d, st = gpu.point_decode(out["encode"])
+        out["decode"], out["decode_st"] = util.coords_fast(chk, d), st
+        out["add"] = util.coords_fast(chk, gpu.point_add(p, d[::-1].copy()))
+        out["comb"] = gpu.point_encode(gpu.precomputed_scalarmul(util.random_scalars(chk, "shard/c", big)))
+        out["gf_mul"] = gpu.gf_mul(h, h[::-1].copy())
+        out["shake"] = gpu.shake256(msgs, 33) if hasattr(gpu, "shake256") else np.zeros(1)
+        return out
+
+    assert gpu.get_devices() == []
+    base = run()
+    parity.eq(base["verify"], chk.ed448_verify(sig, pk, msgs), "unsharded verify vs reference")
+    gpu.set_devices(devs)
+    try:
+        assert gpu.get_devices() == devs
+        got = run()
+    finally:
+        gpu.set_devices([])
+    for name in base:
+        parity.eq(got[name], base[name], "device set %s: %s" % (devs, name))
+    assert gpu.get_devices() == []
+    gpu.set_devices([0])                                   # a set of one device: light operations are still pipelined
+    try:
+        parity.eq(gpu.point_encode(gpu.from_hash_nonuniform(h)), base["encode"], "one-device set: pipelined elligator + encode")
+        parity.eq(gpu.ed448_verify(sig, pk, msgs), base["verify"], "one-device set: verify")
+    finally:
+        gpu.set_devices([])
+
+
+# ---- the full 2^20 batches of BASELINE.json, every element compared with the compiled reference (all host cores) ----
+
+def _timed(what, t0):
+    import time
+    print("[full-parity] %s: %.1f s" % (what, time.time() - t0))
+
+
+def test_points_all_2_20(gpu, chk):
+    """config 1 (group half) at 2^20: all four coordinates of point_add / point_sub / point_double against the reference
+    (goldilocks.c:178-258) on 2^20 pairs, half of them non-trivial projective representatives"""
+    import time
+    t0 = time.time()
+    n = FULL
+    p = util.random_points(chk, "c1full/p", n)
+    q = util.random_points(chk, "c1full/q", n)
+    p[1::2] = chk.point_add(p[1::2], q[::2])          # Z != 1 inputs
+    q[1::2] = chk.point_double(q[1::2])
+    c = util.coords_fast
+    parity.eq(c(chk, gpu.point_add(p, q)), c(chk, chk.point_add(p, q)), "point_add coords over 2^20")
+    parity.eq(c(chk, gpu.point_sub(p, q)), c(chk, chk.point_sub(p, q)), "point_sub coords over 2^20")
+    parity.eq(c(chk, gpu.point_double(p)), c(chk, chk.point_double(p)), "point_double coords over 2^20")
+    _timed("point add/sub/double 2^20 vs reference", t0)
+
+
+def test_x448_all_2_20(gpu, chk):
+    """config 3 at 2^20: output bytes and status of every element against the reference (goldilocks.c:1006-1076), random u
+    (any 56 bytes, so non-canonical u too) and random scalars, the edge block of check_x448 riding along; DH commutes"""
+    import time
+    t0 = time.time()
     n = FULL
     a = stream_bytes("c3full/a", n * 56).reshape(n, 56)
     b = stream_bytes("c3full/b", n * 56).reshape(n, 56)
+    u = stream_bytes("c3full/u", n * 56).reshape(n, 56)
+    u[-9:] = parity.x448_inputs(1)[0][-9:]           # 0, 1, p-1, p, p+5, 2^448-1, ...
+    o1, s1 = gpu.x448(u, a)
+    o2, s2 = chk.x448(u, a)
+    parity.eq(s1, s2, "x448 status over 2^20")
+    parity.eq(o1, o2, "x448 output over 2^20")
+    _timed("x448 2^20 vs reference", t0)
     base = np.zeros((n, 56), np.uint8); base[:, 0] = 5
     pa, sa = gpu.x448(base, a)
     pb, sb = gpu.x448(base, b)
-    ab, s1 = gpu.x448(pa, b)
-    ba, s2 = gpu.x448(pb, a)
-    assert (sa == -1).all() and (sb == -1).all() and (s1 == -1).all() and (s2 == -1).all()
+    ab, s3 = gpu.x448(pa, b)
+    ba, s4 = gpu.x448(pb, a)
+    assert (sa == -1).all() and (sb == -1).all() and (s3 == -1).all() and (s4 == -1).all()
     parity.eq(ab, ba, "x448 DH commutativity over 2^20")
-    m = 1 << 11
-    idx = np.arange(0, n, n // m)
-    parity.eq(ab[idx], chk.x448(pa[idx], b[idx])[0], "x448 sample vs checker")
 
 
-def test_comb_full_linearity(gpu, chk):
-    """config 2 at 2^20: comb(a) + comb(b) == comb(a+b), plus a checker-compared sample"""
+def test_comb_all_2_20(gpu, chk):
+    """config 2 at 2^20: decaf encoding of precomputed_scalarmul(k) for every k against the reference
+    (goldilocks.c:830-877 then 98-140); comb(a) + comb(b) == comb(a+b)"""
+    import time
+    t0 = time.time()
     n = FULL
     a = gpu.scalar_decode_long(stream_bytes("c2full/a", n * 56).reshape(n, 56), 56)
+    a[-len(util.scalar_edge_bytes()):] = util.scalar_edge_bytes()
+    pa = gpu.precomputed_scalarmul(a)
+    parity.eq(gpu.point_encode(pa), chk.point_encode(chk.precomputed_scalarmul(a)), "comb decaf encoding over 2^20")
+    _timed("comb + encode 2^20 vs reference", t0)
     b = gpu.scalar_decode_long(stream_bytes("c2full/b", n * 56).reshape(n, 56), 56)
-    pa, pb = gpu.precomputed_scalarmul(a), gpu.precomputed_scalarmul(b)
     pab = gpu.precomputed_scalarmul(gpu.scalar_add(a, b))
-    assert gpu.point_eq(gpu.point_add(pa, pb), pab).all()
-    idx = np.arange(0, n, n // (1 << 12))
-    parity.eq(gpu.point_encode(pa[idx]), chk.point_encode(chk.precomputed_scalarmul(a[idx])), "comb sample vs checker")
+    assert gpu.point_eq(gpu.point_add(pa, gpu.precomputed_scalarmul(b)), pab).all()
 
 
-def test_verify_full(gpu, chk):
-    """config 4 at 2^20: 2^16 keys x 16 messages, 1/8 corrupted; accept bits must follow the corruption
-    kinds (S+q accepted, everything else rejected) and a checker-compared sample must agree bit for bit"""
-    nk, per = 1 << 16, 16
+def _c4_corpus(signer, label, nk, per, kinds_mod=5):
+    """nk keys x per messages of 32 bytes SIGNED BY `signer` (the reference), 1/8 corrupted"""
     n = nk * per
-    sk = stream_bytes("c4full/sk", nk * 57).reshape(nk, 57)
-    pk = gpu.ed448_derive_public_key(sk)
+    sk = stream_bytes(label + "/sk", nk * 57).reshape(nk, 57)
+    pk = signer.ed448_derive_public_key(sk)
     sk_all, pk_all = np.repeat(sk, per, axis=0), np.repeat(pk, per, axis=0)
-    arena = stream_bytes("c4full/msg", n * 32)
+    arena = stream_bytes(label + "/msg", n * 32)
     off = (np.arange(n + 1, dtype=np.uint64) * 32)
-    sig = gpu.ed448_sign(sk_all, pk_all, (arena, off))
+    sig = signer.ed448_sign(sk_all, pk_all, (arena, off))
     kinds = np.zeros(n, np.int32)
-    kinds[::8] = 1 + (np.arange(n // 8) % 5)
-    sel = stream_bytes("c4full/sel", n)
+    kinds[::8] = 1 + (np.arange(n // 8) % kinds_mod)
+    sel = stream_bytes(label + "/sel", n)
     i1 = np.flatnonzero(kinds == 1); sig[i1, sel[i1] % 57] ^= 1
     i2 = np.flatnonzero(kinds == 2); sig[i2, 57 + sel[i2] % 56] ^= 2
     i3 = np.flatnonzero(kinds == 3); pk_all[i3, sel[i3] % 57] ^= 4
     i4 = np.flatnonzero(kinds == 4); arena[i4 * 32 + sel[i4] % 32] ^= 8
     for i in np.flatnonzero(kinds == 5)[:4096]:
-        sig[i, 57:114] = util.le(util.from_le(sig[i, 57:114]) + util.Q, 57)
+        sig[i, 57:114] = util.le(util.from_le(sig[i, 57:114]) + util.Q, 57)      # S + q: accepted by the reference
     kinds[np.flatnonzero(kinds == 5)[4096:]] = 0
+    return sk_all, pk, sig, pk_all, arena, off, kinds
+
+
+def test_verify_all_2_20(gpu, chk):
+    """config 4 at 2^20, corpus signed by the REFERENCE: 2^16 keys x 16 messages, 1/8 corrupted.  All 2^20
+    accept bits against goldilocks_ed448_verify of the reference (eddsa.c:253-306), the product's signatures over the
+    same 2^20 (key, message) pairs byte for byte against the reference's, and the corruption kinds' expected verdicts"""
+    import time
+    t0 = time.time()
+    sk_all, pk, sig, pk_all, arena, off, kinds = _c4_corpus(chk, "c4full", 1 << 16, 16)
+    _timed("reference keygen + sign 2^20", t0)
+    t0 = time.time()
     st = gpu.ed448_verify(sig, pk_all, (arena, off))
-    expect = np.where((kinds == 0) | (kinds == 5), -1, 0).astype(np.int32)
-    parity.eq(st, expect, "verify accept bits over 2^20")
-    idx = np.arange(0, n, n // (1 << 12) - 1)[: 1 << 12]
-    sub = (np.concatenate([arena[i * 32:(i + 1) * 32] for i in idx]), np.arange(len(idx) + 1, dtype=np.uint64) * 32)
-    parity.eq(st[idx], chk.ed448_verify(sig[idx], pk_all[idx], sub), "verify sample vs checker")
-    parity.eq(sig[idx[:512]] if False else gpu.ed448_sign(sk_all[idx[:512]], pk_all[idx[:512]] if False else np.repeat(pk, per, axis=0)[idx[:512]],
-              (sub[0][: 512 * 32], sub[1][:513])),
-              chk.ed448_sign(sk_all[idx[:512]], np.repeat(pk, per, axis=0)[idx[:512]], (sub[0][: 512 * 32], sub[1][:513])), "sign sample vs checker")
+    want = chk.ed448_verify(sig, pk_all, (arena, off))
+    _timed("reference verify 2^20", t0)
+    parity.eq(st, want, "verify accept bits over 2^20 vs reference")
+    parity.eq(st, np.where((kinds == 0) | (kinds == 5), -1, 0).astype(np.int32), "verify accept bits over 2^20 vs corruption kinds")
+    parity.eq(gpu.ed448_derive_public_key(sk_all[::16]), pk, "derive_public_key over 2^16 vs reference")
+    clean = kinds == 0                                   # the signatures the corpus left untouched are the reference's own bytes
+    arena0, pk0 = stream_bytes("c4full/msg", len(arena)), np.repeat(pk, 16, axis=0)
+    parity.eq(gpu.ed448_sign(sk_all, pk0, (arena0, off))[clean], sig[clean], "sign over 2^20 vs reference")
+
+
+def test_verify_all_2_20_distinct_keys(gpu, chk):
+    """the same with 2^20 DISTINCT keys (no per-key table can be shared: every signature takes the stand-alone finish)"""
+    import time
+    t0 = time.time()
+    sk_all, pk, sig, pk_all, arena, off, kinds = _c4_corpus(chk, "c4fulld", 1 << 20, 1)
+    st = gpu.ed448_verify(sig, pk_all, (arena, off))
+    parity.eq(st, chk.ed448_verify(sig, pk_all, (arena, off)), "verify accept bits over 2^20 distinct keys vs reference")
+    parity.eq(st, np.where((kinds == 0) | (kinds == 5), -1, 0).astype(np.int32), "verify accept bits (distinct keys) vs corruption kinds")
+    _timed("distinct-key corpus: reference keygen + sign + verify 2^20", t0)
 
 
 def test_verify_rlc_full(gpu, chk):

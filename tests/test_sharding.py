@@ -61,3 +61,56 @@ def test_two_rank_sharded_verify_gloo(tmp_path):
     import socket
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
+# ---- the library's own partition of ONE batch over a device set (goldilocks_b200_set_devices, csrc/shard.h) ----
+
+def _lib():
+    import libgoldilocks_b200 as g
+    return g.load()
+
+
+def test_library_shard_plan_heavy_is_one_contiguous_range_per_device():
+    lib = _lib()
+    for n in (4096, 4097, 1 << 20, (1 << 20) + 5, (1 << 24) + 1):
+        for ndev in (1, 2, 3, 4, 8):
+            pl = lib.shard_plan(n, ndev)
+            assert len(pl) == min(ndev, n // 2048)
+            assert pl[0][0] == 0 and pl[-1][1] == n
+            assert all(pl[i][1] == pl[i + 1][0] for i in range(len(pl) - 1))
+            sizes = [b - a for a, b, _, _ in pl]
+            assert max(sizes) - min(sizes) <= 1
+            assert [s for _, _, s, _ in pl] == list(range(len(pl))) and all(l == 0 for _, _, _, l in pl)
+    assert lib.shard_plan(0, 8) == []
+    assert lib.shard_plan(100, 8) == [(0, 100, 0, 0)]          # too small to cut
+
+
+def test_library_shard_plan_light_pipelines_chunks_over_lanes():
+    lib = _lib()
+    for n, ndev, bpe in (((1 << 24), 8, 312), ((1 << 20) + 3, 2, 768), (1 << 21, 1, 316), (10000, 4, 168)):
+        pl = lib.shard_plan(n, ndev, bpe, pipelined=True)
+        assert pl[0][0] == 0 and pl[-1][1] == n
+        assert all(pl[i][1] == pl[i + 1][0] for i in range(len(pl) - 1))       # contiguous, in order
+        assert all(pl[i][2] <= pl[i + 1][2] for i in range(len(pl) - 1))       # a device owns one contiguous region
+        per_dev = {}
+        for a, b, s, l in pl:
+            per_dev.setdefault(s, []).append((b - a, l))
+        assert len(per_dev) == min(ndev, n // 2048)
+        for s, chunks in per_dev.items():
+            assert [l for _, l in chunks] == [i % 3 for i in range(len(chunks))]   # lanes dealt round-robin
+            sizes = [c for c, _ in chunks]
+            assert max(sizes) - min(sizes) <= 1
+            assert len(chunks) == 1 or max(sizes) * bpe <= (24 << 20) + bpe * 4096
+        totals = [sum(c for c, _ in v) for v in per_dev.values()]
+        assert max(totals) - min(totals) <= 1
+
+
+def test_set_devices_fails_loudly_without_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib()
+    with pytest.raises(RuntimeError):
+        lib.set_devices([0])
+    assert lib.get_devices() == []

@@ -13,8 +13,11 @@ OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(KERNELS)) $(OBJDIR)/abi.o
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/goldilocks_b200.h
 LIB       ?= libgoldilocks_b200/libgoldilocks_b200.so
 
-.PHONY: all lib hostsim oracle clean
-all: lib hostsim oracle
+.PHONY: all lib hostsim oracle tools clean
+all: lib hostsim oracle tools
+tools: tools/imad_peak
+tools/imad_peak: tools/imad_peak.cu
+	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
 lib: $(LIB)
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS_$*) $(HDRS)
@@ -26,7 +29,7 @@ $(LIB): $(OBJS)
 
 hostsim: tests/hostsim/_hostsim.so
 tests/hostsim/_hostsim.so: tests/hostsim/hostsim.cpp $(HDRS)
-	$(CXX) -std=c++17 -O2 -fPIC -shared -DGF_CHECK_BOUNDS -o $@ $< -lpthread
+	$(CXX) -std=c++17 -O2 -fPIC -shared -DGF_CHECK_BOUNDS -DGF_COUNT_OPS -o $@ $< -lpthread
 
 oracle:
 	$(MAKE) -C oracle all

@@ -48,6 +48,16 @@
 #define GF_ASSERT_TIGHT(x) do { } while (0)
 #endif
 
+// Multiplier-call counters for the host simulator (tools/count_ops.py -> profiles/executed_ops.json: the executed
+// IMAD.WIDE of every entry point = 193 x multiplications + 110 x squarings + 16 x word multiplications).  Host only.
+#if defined(GF_COUNT_OPS) && !defined(__CUDA_ARCH__)
+#include <atomic>
+inline std::atomic<unsigned long long> &gf_op_counter(int k) { static std::atomic<unsigned long long> c[3]; return c[k]; }
+#define GF_COUNT(k) gf_op_counter(k).fetch_add(1, std::memory_order_relaxed)
+#else
+#define GF_COUNT(k) do { } while (0)
+#endif
+
 // A zero the compiler cannot see through (constant bank, never written).  Adding it as a third
 // operand keeps an addition a three-input IADD3 on the ALU pipe: ptxas otherwise turns about half of
 // the two-input adds and register moves around the multiplier into IMAD.IADD / IMAD.MOV, which
@@ -181,6 +191,7 @@ GD void gf_fold_top(gf &c, uint64_t acc0, uint64_t acc1) {
 // (same identity as the reference's arch_32/f_impl.c:15-69; the subtracted P0[j+8] terms are
 //  accumulated with a signed IMAD.WIDE on a pre-negated operand so they cost no extra instruction.)
 GD void gf_mul_body(gf &c, const gf &a, const gf &b) {
+    GF_COUNT(0);
     GF_ASSERT_LOOSE(a);
     GF_ASSERT_LOOSE(b);
     uint32_t aa[8], bb[8];
@@ -243,6 +254,7 @@ GD void gf_mul_body(gf &c, const gf &a, const gf &b) {
 // c = a^2 mod p.  LOOSE input, TIGHT output.  108 IMAD.WIDE (the reference's arch_32 has no
 // dedicated squaring, arch_32/f_impl.c:98-100; arch_ref64/f_impl.c:151-301 does).
 GD void gf_sqr_body(gf &c, const gf &a) {
+    GF_COUNT(1);
     GF_ASSERT_LOOSE(a);
     uint32_t lo[8], hi[8], aa[8], lo2[8], hi2[8], aa2[8];
     int32_t nlo[8];
@@ -311,6 +323,7 @@ GD void gf_sqrn(gf &y, const gf &x, int n) { /* reference field.h:19-38 */
 // c = a * w for a small unsigned w < 2^28.  LOOSE input, TIGHT output.  16 IMAD.WIDE.
 // (reference arch_32/f_impl.c:71-96 gf_mulw_unsigned)
 GD void gf_mulw(gf &c, const gf &a, uint32_t w) {
+    GF_COUNT(2);
     GF_ASSERT_LOOSE(a);
     uint64_t acc0 = 0, acc1 = 0;
     gf r;

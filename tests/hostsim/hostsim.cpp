@@ -19,11 +19,46 @@
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
+// multiplier-call counters (gf.cuh GF_COUNT): [0] multiplications, [1] squarings, [2] word multiplications since the last reset
+EXPORT void hostsim_op_counts(unsigned long long out[3], int reset) {
+    for (int k = 0; k < 3; k++) { out[k] = gf_op_counter(k).load(); if (reset) gf_op_counter(k).store(0); }
+}
+// the same counters per functor (= per kernel of the product): every run*() below adds what its functor executed
+#include <mutex>
+#include <typeinfo>
+static std::mutex g_stage_mu;
+static std::map<std::string, std::vector<unsigned long long>> g_stage;   /* name -> {mul, sqr, mulw, elements} */
+struct StageScope {
+    const char *name; size_t n; unsigned long long before[3];
+    StageScope(const char *nm, size_t n_) : name(nm), n(n_) { for (int k = 0; k < 3; k++) before[k] = gf_op_counter(k).load(); }
+    ~StageScope() {
+        std::lock_guard<std::mutex> g(g_stage_mu);
+        const char *nm = name;
+        while (*nm >= '0' && *nm <= '9') nm++;
+        auto &v = g_stage[nm];
+        v.resize(4);
+        for (int k = 0; k < 3; k++) v[k] += gf_op_counter(k).load() - before[k];
+        v[3] += n;
+    }
+};
+EXPORT size_t hostsim_stage_counts(char *names, unsigned long long *counts, size_t max, int reset) {
+    std::lock_guard<std::mutex> g(g_stage_mu);
+    size_t k = 0;
+    for (auto &kv : g_stage) {
+        if (k >= max) break;
+        snprintf(names + 64 * k, 64, "%s", kv.first.c_str());
+        for (int j = 0; j < 4; j++) counts[4 * k + j] = kv.second[j];
+        k++;
+    }
+    if (reset) g_stage.clear();
+    return k;
+}
 static int g_threads = 1;
 EXPORT void hostsim_set_threads(int t) { g_threads = t < 1 ? 1 : t; }
 
 template <class F>
 static void run(const F &f, size_t n) {
+    StageScope stage_(typeid(F).name(), n);
     int nt = g_threads;
     if ((size_t)nt > n) nt = n ? (int)n : 1;
     if (nt <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
@@ -33,7 +68,8 @@ static void run(const F &f, size_t n) {
     for (auto &x : th) x.join();
 }
 template <class F>
-static void run_sm(const F &f, size_t n) { /* slot machine: F::NSLOTS field elements of scratch per worker */
+static void run_sm(const F &f, size_t n) {
+    StageScope stage_(typeid(F).name(), n); /* slot machine: F::NSLOTS field elements of scratch per worker */
     int nt = g_threads;
     if ((size_t)nt > n) nt = n ? (int)n : 1;
     auto work = [&f](size_t lo, size_t hi) {
@@ -48,7 +84,8 @@ static void run_sm(const F &f, size_t n) { /* slot machine: F::NSLOTS field elem
 }
 
 template <class F>
-static void run_smp(const F &f, size_t n) { /* persistent slot machine: slots + one HBM scratch area per worker */
+static void run_smp(const F &f, size_t n) {
+    StageScope stage_(typeid(F).name(), n); /* persistent slot machine: slots + one HBM scratch area per worker */
     int nt = g_threads;
     if ((size_t)nt > n) nt = n ? (int)n : 1;
     auto work = [&f](size_t lo, size_t hi, size_t slot) {

@@ -164,6 +164,13 @@ int main(int argc, char **argv) {
     uint64_t *out; long long *cyc;
     CK(cudaMalloc(&out, (size_t)sms * 8 * 1024 * sizeof(uint64_t))); CK(cudaMalloc(&cyc, sms * 8 * sizeof(long long)));
     std::vector<Result> rs;
+    const bool quick = argc > 1 && !strcmp(argv[1], "--quick");   /* bench.py: the three best IMAD.WIDE shapes only, JSON on stdout (~1 s) */
+    if (quick) {
+        rs.push_back(run_scan<0>("imad_wide_u32", sms, 1024, 1, out, cyc));
+        rs.push_back(run_scan<0>("imad_wide_u32", sms, 512, 2, out, cyc));
+        rs.push_back(run_scan<0>("imad_wide_u32", sms, 256, 4, out, cyc));
+        argc = 1;
+    } else {
     rs.push_back(run_scan<0>("imad_wide_u32", sms, 1024, 1, out, cyc));
     rs.push_back(run_scan<0>("imad_wide_u32", sms, 512, 1, out, cyc));
     rs.push_back(run_scan<0>("imad_wide_u32", sms, 256, 1, out, cyc));
@@ -179,6 +186,7 @@ int main(int argc, char **argv) {
     rs.push_back(run<K_WIDE_CC, 8>("imad_wide_carry_chain", sms, 1024, 1, out, cyc));
     rs.push_back(run<K_WIDE_CC, 8>("imad_wide_carry_chain", sms, 512, 1, out, cyc));
     rs.push_back(run<K_DFMA, 8>("dfma", sms, 1024, 1, out, cyc));
+    }
     FILE *f = argc > 1 ? fopen(argv[1], "w") : stdout;
     double best_wide = 0, best_wide_clk = 0, mhz = 0;
     for (auto &r : rs) if (!strcmp(r.name, "imad_wide_u32") && r.gops > best_wide) { best_wide = r.gops; best_wide_clk = r.per_clk_sm; mhz = r.mhz; }

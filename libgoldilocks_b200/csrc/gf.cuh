@@ -431,22 +431,28 @@ GD gmask_t gf_lobit(const gf &a_in) { /* reference f_generic.c:40-45 */
 // Same exponent as the reference's addition chain (f_arithmetic.c:14-47: 446 S + 13 M) walked as a
 // 12-step table so the GPU code holds one squaring loop and one multiply instead of 26 inlined bodies:
 //   step: square `n` times, multiply by x or by the single saved power, optionally save.
+// The schedule lives in two 60-bit immediates (ten bits per step), not in an array: a local array read in a loop
+// is a dynamically addressed local load, which costs a memory access per step and which a static constant-time
+// audit of the SASS (tools/ct_audit.py) cannot tell from secret-indexed data.
+GD uint32_t gf_isr_step(int s) { /* n (bits 0-7), multiply-by-x flag (bit 8), save-after flag (bit 9) */
+    const uint64_t lo = 0x4060980c03c0501ull, hi = 0x37d019be2509612ull;
+    return (uint32_t)((s < 6 ? lo >> (10 * s) : hi >> (10 * (s - 6))) & 0x3ff);
+}
 GD gmask_t gf_isr(gf &a, const gf &x) {
     gf cur, saved;
     gf_copy(cur, x);
     gf_copy(saved, x);
-    /* n, multiply-by-x flag (bit 8), save-after flag (bit 9) */
-    const uint16_t steps[12] = {1 | 0x100,  1 | 0x100 | 0x200, 3,           3 | 0x200,  9 | 0x200,  1 | 0x100,
-                                18 | 0x200, 37,                37 | 0x200, 111 | 0x200, 1 | 0x100, 223};
+    /* steps: {1|X, 1|X|S, 3, 3|S, 9|S, 1|X, 18|S, 37, 37|S, 111|S, 1|X, 223}  (X = multiply by x, S = save afterwards) */
 #pragma unroll 1
     for (int s = 0; s < 12; s++) {
-        const int n = steps[s] & 0xff;
-        const gmask_t by_x = (steps[s] & 0x100) ? ~0u : 0u;
+        const uint32_t step = gf_isr_step(s);
+        const int n = (int)(step & 0xff);
+        const gmask_t by_x = (step & 0x100) ? ~0u : 0u;
         gf_sqrn(cur, cur, n);
         gf m;
         gf_cond_sel(m, saved, x, by_x); /* schedule is public: not secret dependent */
         gf_mul(cur, cur, m);
-        if (steps[s] & 0x200) gf_copy(saved, cur);
+        if (step & 0x200) gf_copy(saved, cur);
     }
     gf t0, t1;
     gf_sqr(t0, cur);

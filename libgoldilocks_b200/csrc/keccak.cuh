@@ -14,15 +14,25 @@ struct keccak_state { uint64_t a[25]; };
 
 GD uint64_t kc_rol(uint64_t x, int s) { return s == 0 ? x : ((x << s) | (x >> (64 - s))); }
 
+// Round constants: constant memory on the device (indexed by the public round counter), a plain table on the host.  As a
+// local array inside the function they were copied to the stack of every lane and re-read with dynamic local loads.
+#define KC_RC_TABLE                                                                                     \
+    {0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,       \
+     0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,       \
+     0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,       \
+     0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,       \
+     0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,       \
+     0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull}
+#if defined(__CUDACC__)
+static __constant__ uint64_t kc_rc_dev[24] = KC_RC_TABLE;
+#endif
 GD uint64_t kc_rc(int r) {
-    const uint64_t rc[24] = {
-        0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
-        0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
-        0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,
-        0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
-        0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
-        0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+#if defined(__CUDA_ARCH__)
+    return kc_rc_dev[r];
+#else
+    static const uint64_t rc[24] = KC_RC_TABLE;
     return rc[r];
+#endif
 }
 
 // One round, lanes indexed a[x + 5y] (FIPS 202 section 3.2).
@@ -54,59 +64,68 @@ GD void keccak_f1600(keccak_state &st) {
     for (int r = 0; r < 24; r++) kc_round(st.a, kc_rc(r));
 }
 
-// Streaming byte-wise SHAKE256 sponge.  Bytes are staged in a 136-byte word buffer (dynamic indexing
-// -> local memory, L1 resident) and whole blocks are XORed into the register-resident state with
-// compile-time lane indices; squeezing reads the same buffer.  Hashing is <1% of an EdDSA verify.
+// Streaming byte-wise SHAKE256 sponge, register resident.  The 25 state lanes stay in registers; incoming bytes are
+// gathered into one 64-bit accumulator and XORed into lane pos/8 by a compile-time unrolled select chain (17 SELs per
+// eight bytes), so there is NO dynamically indexed local array: round 1's 136-byte word buffer lived in local memory
+// (29.9 M local loads and 664 MB of DRAM writes per 2^20 challenge hashes, profiles/r01i_scalars_ncu.txt) and made the
+// position counter look data-dependent to a static audit (tools/ct_audit.py).  Positions are public (lengths), data only
+// ever flows into `acc` and the state.  Fixed-size digests are read straight from the state words (shake256_out_words).
 struct shake256_ctx {
     keccak_state st;
-    uint32_t buf[SHAKE256_RATE / 4];
-    int pos;
+    uint64_t acc;   /* absorbing: the bytes of lane pos/8 gathered so far; squeezing: the lane being handed out */
+    uint32_t pos;   /* byte position inside the current block, 0 .. 135 */
 };
-GD void kc_buf_clear(shake256_ctx &c) {
-#pragma unroll
-    for (int i = 0; i < SHAKE256_RATE / 4; i++) c.buf[i] = 0;
-}
 GD void shake256_init(shake256_ctx &c) {
 #pragma unroll
     for (int i = 0; i < 25; i++) c.st.a[i] = 0;
-    kc_buf_clear(c);
+    c.acc = 0;
     c.pos = 0;
 }
-// state ^= buffered block; permute (reference shake.c:89-112 absorb + dokeccak)
-GD void kc_absorb_block(shake256_ctx &c) {
+// a[li] ^= v for a run-time lane index below the rate (branch-free, register only)
+GD void kc_xor_lane(keccak_state &st, uint32_t li, uint64_t v) {
 #pragma unroll
-    for (int i = 0; i < SHAKE256_RATE / 8; i++) c.st.a[i] ^= (uint64_t)c.buf[2 * i] | ((uint64_t)c.buf[2 * i + 1] << 32);
+    for (int i = 0; i < SHAKE256_RATE / 8; i++) st.a[i] ^= (li == (uint32_t)i) ? v : 0ull;
+}
+GD uint64_t kc_get_lane(const keccak_state &st, uint32_t li) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < SHAKE256_RATE / 8; i++) v |= (li == (uint32_t)i) ? st.a[i] : 0ull;
+    return v;
+}
+GD void shake256_absorb_byte(shake256_ctx &c, uint8_t v) { /* reference shake.c:89-112 */
+    c.acc |= (uint64_t)v << (8 * (c.pos & 7));
+    c.pos++;
+    if ((c.pos & 7) == 0) {
+        kc_xor_lane(c.st, (c.pos >> 3) - 1, c.acc);
+        c.acc = 0;
+        if (c.pos == SHAKE256_RATE) {
+            keccak_f1600(c.st);
+            c.pos = 0;
+        }
+    }
+}
+GD void shake256_finish_absorb(shake256_ctx &c) { /* reference shake.c:136-142: pad 0x1f ... 0x80, permute, switch to squeezing */
+    c.acc ^= (uint64_t)0x1f << (8 * (c.pos & 7));
+    kc_xor_lane(c.st, c.pos >> 3, c.acc);
+    c.st.a[SHAKE256_RATE / 8 - 1] ^= 0x8000000000000000ull;
     keccak_f1600(c.st);
-}
-GD void kc_fill_output(shake256_ctx &c) {
-#pragma unroll
-    for (int i = 0; i < SHAKE256_RATE / 8; i++) {
-        c.buf[2 * i] = (uint32_t)c.st.a[i];
-        c.buf[2 * i + 1] = (uint32_t)(c.st.a[i] >> 32);
-    }
-}
-GD void shake256_absorb_byte(shake256_ctx &c, uint8_t v) {
-    c.buf[c.pos >> 2] |= (uint32_t)v << (8 * (c.pos & 3));
-    if (++c.pos == SHAKE256_RATE) {
-        kc_absorb_block(c);
-        kc_buf_clear(c);
-        c.pos = 0;
-    }
-}
-GD void shake256_finish_absorb(shake256_ctx &c) { /* reference shake.c:136-142: pad 0x1f ... 0x80 */
-    c.buf[c.pos >> 2] ^= 0x1fu << (8 * (c.pos & 3));
-    c.buf[SHAKE256_RATE / 4 - 1] ^= 0x80000000u;
-    kc_absorb_block(c);
-    kc_fill_output(c);
+    c.acc = 0;
     c.pos = 0;
 }
-GD uint8_t shake256_squeeze_byte(shake256_ctx &c) {
+// First NW 32-bit words of the output, straight from the state (call right after shake256_finish_absorb; NW * 4 <= 136).
+template <int NW>
+GD void shake256_out_words(const shake256_ctx &c, uint32_t *w) {
+    static_assert(NW * 4 <= SHAKE256_RATE, "one block");
+#pragma unroll
+    for (int k = 0; k < NW; k++) w[k] = (uint32_t)(c.st.a[k >> 1] >> (32 * (k & 1)));
+}
+GD uint8_t shake256_squeeze_byte(shake256_ctx &c) { /* generic output lengths (goldilocks_shake256_hash_batch); reference shake.c:114-162 */
     if (c.pos == SHAKE256_RATE) {
         keccak_f1600(c.st);
-        kc_fill_output(c);
         c.pos = 0;
     }
-    const uint8_t r = (uint8_t)(c.buf[c.pos >> 2] >> (8 * (c.pos & 3)));
+    if ((c.pos & 7) == 0) c.acc = kc_get_lane(c.st, c.pos >> 3);
+    const uint8_t r = (uint8_t)(c.acc >> (8 * (c.pos & 7)));
     c.pos++;
     return r;
 }

@@ -372,7 +372,9 @@ struct LaneEdSkToX448 { /* goldilocks_ed448_convert_private_key_to_x448 (eddsa.c
         shake256_init(h);
         for (int k = 0; k < 57; k++) shake256_absorb_byte(h, ed[57 * i + k]);
         shake256_finish_absorb(h);
-        for (int k = 0; k < 56; k++) x[56 * i + k] = shake256_squeeze_byte(h);
+        uint32_t w[14];
+        shake256_out_words<14>(h, w);
+        words_store_bytes(x + 56 * i, 56, w);
     }
 };
 // ---- caller-supplied fixed-base tables (goldilocks_448_precompute, goldilocks.c:757-818) -------------
@@ -420,8 +422,8 @@ GD void ed448_secret_scalar(sc &secret, shake256_ctx &h, const uint8_t *sk) {
     for (int k = 0; k < 57; k++) shake256_absorb_byte(h, sk[k]);
     shake256_finish_absorb(h);
     uint32_t w[15];
-    for (int k = 0; k < 15; k++) w[k] = 0;
-    for (int k = 0; k < 57; k++) w[k >> 2] |= (uint32_t)shake256_squeeze_byte(h) << (8 * (k & 3));
+    shake256_out_words<15>(h, w);   /* bytes 0 .. 56 of the 114-byte output; the clamp clears byte 56 and leaves 57 .. 59 out */
+    w[14] &= 0xffu;
     ed448_clamp_words(w);
     sc_reduce_57(secret, w); /* folding reduction (sc.cuh): branch-free, same canonical value as scalar_decode_long */
 }
@@ -448,7 +450,11 @@ struct LaneEdSignExpand { /* eddsa.c:161-171: SHAKE256(sk) -> clamped secret sca
         sc s;
         shake256_ctx hk;
         ed448_secret_scalar(s, hk, sk + 57 * i);
-        for (int k = 0; k < 57; k++) seed[57 * i + k] = shake256_squeeze_byte(hk);
+        uint32_t w[29], sw[15];      /* seed = bytes 57 .. 113 of the same output block (eddsa.c:161-176) */
+        shake256_out_words<29>(hk, w);
+#pragma unroll
+        for (int k = 0; k < 15; k++) sw[k] = k < 14 ? (w[14 + k] >> 8) | (w[15 + k] << 24) : (w[28] >> 8) & 0xffu;
+        words_store_bytes(seed + 57 * i, 57, sw);
         sc_to_abi(secret + i, s);
     }
 };
@@ -462,10 +468,9 @@ struct LaneEdSignNonce { /* eddsa.c:173-199: nonce = SHAKE256(dom || seed || msg
         for (int k = 0; k < 57; k++) shake256_absorb_byte(h, seed[57 * i + k]);
         for (size_t k = off[i]; k < off[i + 1]; k++) shake256_absorb_byte(h, msg[k]);
         shake256_finish_absorb(h);
-        uint32_t w[29]; /* the first 136 output bytes sit in the sponge's word buffer; 114 of them, reduced by folding (sc.cuh) */
-#pragma unroll
-        for (int k = 0; k < 28; k++) w[k] = h.buf[k];
-        w[28] = h.buf[28] & 0xffffu;
+        uint32_t w[29]; /* 114 output bytes straight from the state words, reduced by folding (sc.cuh) */
+        shake256_out_words<29>(h, w);
+        w[28] &= 0xffffu;
         sc_reduce_114(n, w);
         sc_halve(h1, n);
         sc_halve(h2, h1);
@@ -482,11 +487,9 @@ GD void ed448_challenge(sc &c, const uint8_t *r57, const uint8_t *pk57, const ui
     for (int k = 0; k < 57; k++) shake256_absorb_byte(h, pk57[k]);
     for (size_t k = lo; k < hi; k++) shake256_absorb_byte(h, msg[k]);
     shake256_finish_absorb(h);
-    /* the first 136 output bytes sit in the sponge's word buffer; 114 of them, reduced by folding (sc.cuh) */
-    uint32_t w[29];
-#pragma unroll
-    for (int k = 0; k < 28; k++) w[k] = h.buf[k];
-    w[28] = h.buf[28] & 0xffffu;
+    uint32_t w[29]; /* 114 output bytes straight from the state words, reduced by folding (sc.cuh) */
+    shake256_out_words<29>(h, w);
+    w[28] &= 0xffffu;
     sc_reduce_114(c, w);
 }
 struct LaneEdSignFinish {

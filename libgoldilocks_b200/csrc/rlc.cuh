@@ -127,11 +127,14 @@ struct LaneRlcZ {
         for (int k = 0; k < 32; k++) shake256_absorb_byte(h, seed32[k]);
         for (int k = 0; k < 8; k++) shake256_absorb_byte(h, (uint8_t)((uint64_t)l >> (8 * k)));
         shake256_finish_absorb(h);
+        uint32_t ow[RLC_Z_PER_LANE * RLC_ZWORDS]; /* one output block, read straight from the state words */
+        shake256_out_words<RLC_Z_PER_LANE * RLC_ZWORDS>(h, ow);
+#pragma unroll
         for (int e = 0; e < RLC_Z_PER_LANE; e++) {
             uint32_t w[RLC_ZWORDS];
+#pragma unroll
             for (int k = 0; k < RLC_ZWORDS; k++) {
-                uint32_t x = 0;
-                for (int b = 0; b < 4; b++) x |= (uint32_t)shake256_squeeze_byte(h) << (8 * b);
+                uint32_t x = ow[e * RLC_ZWORDS + k];
                 const int lo = 32 * k; /* keep bits [0, zbits) */
                 if ((int)zbits <= lo) x = 0;
                 else if ((int)zbits < lo + 32) x &= (1u << (zbits - lo)) - 1u;

@@ -369,7 +369,13 @@ struct SlotDirectScalarmul {
         pt_deisogenize(e, q);
         gf_to_words(wd, e);
         status[i] = ST_OK(ok);
-        if (ok || !short_circuit) words_store56(scaled + 56 * i, wd);
+        /* short-circuited elements keep the caller's bytes (goldilocks.c:896): a masked merge, not a branch on the decode's verdict */
+        uint32_t keep[14];
+        words_load56(keep, scaled + 56 * i);
+        const gmask_t wr = ok | (short_circuit ? 0u : ~0u);
+#pragma unroll
+        for (int k = 0; k < 14; k++) wd[k] = (wd[k] & wr) | (keep[k] & ~wr);
+        words_store56(scaled + 56 * i, wd);
     }
 };
 struct SlotCombTable { /* goldilocks_448_precomputed_scalarmul over a caller-supplied table (goldilocks.c:830-877) */

@@ -187,15 +187,14 @@ SFN void s_stg(uint4 *g, sref a) { gf x; s_ld(x, a); gq_st<QS>(g, x); } /* slot 
 GD gmask_t s_isr(sref a, sref saved, sref x) {
     s_copy(a, x);
     s_copy(saved, x);
-    const uint16_t steps[12] = {1 | 0x100,  1 | 0x100 | 0x200, 3,           3 | 0x200,  9 | 0x200,  1 | 0x100,
-                                18 | 0x200, 37,                37 | 0x200, 111 | 0x200, 1 | 0x100, 223};
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int s = 0; s < 12; s++) {
-        s_sqrn(a, a, steps[s] & 0xff);
-        s_mul(a, a, (steps[s] & 0x100) ? x : saved); /* public schedule */
-        if (steps[s] & 0x200) s_copy(saved, a);
+        const uint32_t step = gf_isr_step(s); /* the schedule of gf_isr, held in immediates (gf.cuh) */
+        s_sqrn(a, a, (int)(step & 0xff));
+        s_mul(a, a, (step & 0x100) ? x : saved); /* public schedule */
+        if (step & 0x200) s_copy(saved, a);
     }
     s_sqr(saved, a);
     s_mul(saved, saved, x);

@@ -334,6 +334,64 @@ def test_device_pointer_entry_points_any_alignment(gpu, chk):
     torch.cuda.synchronize()
 
 
+def _kernel_ms(gpu, fn, reps=5):
+    """best-of-`reps` sum of the kernel times of one host-pointer call (the library's per-launch CUDA events)"""
+    import ctypes as C
+    L = gpu.lib
+    L.goldilocks_b200_profile_read.restype = C.c_size_t
+    names = C.create_string_buffer(64 * 256); ms = (C.c_float * 256)()
+    best = None
+    fn()
+    for _ in range(reps):
+        L.goldilocks_b200_profile(C.c_int(1))
+        fn()
+        L.goldilocks_b200_profile(C.c_int(0))
+        cnt = L.goldilocks_b200_profile_read(names, ms, C.c_size_t(256))
+        t = sum(ms[k] for k in range(cnt))
+        best = t if best is None else min(best, t)
+    return best
+
+
+def test_secret_paths_time_independent_of_the_scalar(gpu, chk):
+    """dynamic side of the constant-time claim (static side: tools/ct_audit.py on the SASS): the kernels of the secret paths
+    take the same time for all-zero, all-ones, single-bit and random scalars -- 2^18 lanes each, best of 5, within 2 %.  A
+    secret-indexed table or a secret-dependent branch would show up as a cache / divergence difference between the
+    degenerate patterns (every lane the same index) and the random one (every lane another)."""
+    n = 1 << 18
+    pats = {"zero": np.zeros((n, 56), np.uint8), "ones": np.full((n, 56), 0xff, np.uint8), "random": stream_bytes("ct/r", n * 56).reshape(n, 56)}
+    bit = np.zeros((n, 56), np.uint8); bit[:, 30] = 0x10
+    pats["one_bit"] = bit
+    pts = util.random_points(chk, "ct/p", n)
+    u = stream_bytes("ct/u", n * 56).reshape(n, 56)
+    sk57 = {k: np.concatenate([v, v[:, :1]], axis=1) for k, v in pats.items()}
+    msgs = (stream_bytes("ct/m", n * 32), np.arange(n + 1, dtype=np.uint64) * 32)
+    pk = gpu.ed448_derive_public_key(sk57["random"])
+    report = {}
+    for name, call in (("precomputed_scalarmul", lambda s, k: gpu.precomputed_scalarmul(gpu.scalar_decode_long(s, 56))),
+                       ("x448", lambda s, k: gpu.x448(u, s)),
+                       ("point_scalarmul", lambda s, k: gpu.point_scalarmul(pts, gpu.scalar_decode_long(s, 56))),
+                       ("ed448_derive_public_key", lambda s, k: gpu.ed448_derive_public_key(k)),
+                       ("ed448_sign", lambda s, k: gpu.ed448_sign(k, pk, msgs))):
+        times = {}
+        for pat in pats:
+            s, k = pats[pat], sk57[pat]
+            if name in ("precomputed_scalarmul", "point_scalarmul"):
+                sc = gpu.scalar_decode_long(s, 56)
+                fn = (lambda sc=sc: gpu.precomputed_scalarmul(sc)) if name == "precomputed_scalarmul" else (lambda sc=sc: gpu.point_scalarmul(pts, sc))
+            else:
+                fn = lambda s=s, k=k: call(s, k)
+            times[pat] = _kernel_ms(gpu, fn)
+        report[name] = times
+        lo, hi = min(times.values()), max(times.values())
+        print("[ct-timing] %-24s %s  spread %.2f %%" % (name, {k: round(v, 3) for k, v in times.items()}, 100 * (hi - lo) / lo))
+        assert hi <= 1.02 * lo, "%s: kernel time depends on the scalar pattern: %s" % (name, times)
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        import json
+        with open(os.path.join(out, "ct_timing.json"), "w") as f:
+            json.dump(report, f, indent=1)
+
+
 def test_device_set_sharded_equals_unsharded(gpu, chk):
     """goldilocks_b200_set_devices: ONE host-pointer batch cut into contiguous ranges over the device set (csrc/shard.h) gives
     the bytes of the unsharded call for every kind of entry point -- heavy (one range per device: verify incl. key groups

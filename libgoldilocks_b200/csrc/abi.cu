@@ -1068,7 +1068,7 @@ static bool rlc_class_alloc(Call &k, RlcClass &q, const rlc_shape &sh, size_t co
     return k.ok;
 }
 static bool rlc_class_pairs(Ctx &c, const RlcClass &q, const uint32_t *scal, uint32_t nwords, size_t p0, cudaStream_t s) { /* digits -> sorted pair list */
-    LaneRlcDigits f6 = {q.keys, q.vals, scal, nwords, p0, q.sh};
+    LaneRlcDigits f6 = {q.keys, q.vals, scal, nwords, p0, q.sh, nullptr}; /* one chunk (chunked orchestration: next round, see tests/hostsim) */
     if (!launch(c, f6, q.count, s)) return false;
     int key_bits = 1;
     while ((q.sh.wn << q.sh.c) >> key_bits) key_bits++;
@@ -1170,9 +1170,9 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     if (!launch(c, f2, n, side)) return false;
     CU(cudaEventRecord(c.side_evt[1], side));
     CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));
-    LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g};
+    LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g, sh_r};
     if (!launch(c, f4, n, s)) return false;
-    LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m};
+    LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m, RLC_SCELLS};
     if (!launch(c, f5, (size_t)m + 1, s)) return false;
     CU(cudaEventRecord(c.side_evt[2], s));
     CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));

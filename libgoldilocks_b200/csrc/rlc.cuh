@@ -52,6 +52,9 @@ struct rlc_shape { /* one per class of points, chosen on the host from n (rlc_sh
     uint32_t top;      /* index of the one window with fewer than c bits (the last window of a 446-bit scalar), or ~0 */
     uint32_t top_shift; /* that window holds r = 446 - top * c bits: its 2^r digits get 2^(c - r) sub-buckets each (picked by the low
                          * bits of the point index), so that no bucket of it is longer than the others' */
+    uint32_t nch;      /* chunks: every chunk of `csize` consecutive signatures has its own equation (own buckets, sums, verdict), so a
+                        * bad signature sends only its chunk to the per-signature path.  Window ids run over nch * wn. */
+    uint32_t csize;    /* signatures per chunk */
 };
 // is_key = 0: the n points -R_i with their weights; 1: the keys and B with 446-bit scalars.  Each class picks its digit
 // width from its own number of points (about 32 points per bucket).
@@ -71,8 +74,12 @@ static inline rlc_shape rlc_shape_for(size_t count, int force_c, int is_key) {
     s.nodes = (s.segs + RLC_SEG - 1) / RLC_SEG;
     s.top = is_key ? s.wn - 1 : ~0u;
     s.top_shift = is_key ? s.wn * s.c - GOLDILOCKS_SCALAR_BITS_ : 0u;
+    s.nch = 1;
+    s.csize = ~0u;
     return s;
 }
+#define RLC_SCELLS_CH 64 /* accumulator cells of the response sum per chunk when there is more than one chunk */
+GD uint32_t rlc_scells(const rlc_shape &sh) { return sh.nch > 1 ? RLC_SCELLS_CH : RLC_SCELLS; }
 
 GD void rlc_atomic_add(unsigned long long *p, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
@@ -94,7 +101,7 @@ struct LaneRlcDecode {
         const size_t j = j0 + lane0;
         pt p;
         gmask_t good;
-        if (j == n + g.ngroups) {
+        if (j >= n + g.ngroups) { /* one copy of B per chunk */
             const uint32_t bw[14] = GOLD_CONST_BASE_WORDS;
             good = pt_decode(p, bw, 0);
         } else {
@@ -149,7 +156,7 @@ struct LaneRlcZ {
 
 // 3) products: lane j = sorted position.  Excluded signatures get valid = FAILURE (the bucket kernel skips them) and add nothing to the scalar sums.
 struct LaneRlcWeights {
-    uint32_t *z; int32_t *valid; unsigned long long *key_acc, *s_acc; const abi_sc *chal, *resp; const int32_t *ok; size_t n; rlc_groups g;
+    uint32_t *z; int32_t *valid; unsigned long long *key_acc, *s_acc; const abi_sc *chal, *resp; const int32_t *ok; size_t n; rlc_groups g; rlc_shape sh; /* R-class shape: chunks */
     GDM void operator()(size_t j) const {
         const size_t i = g.order[j], k = g.gid[j] - 1;
         const bool v = ok[i] && ok[n + k];
@@ -162,7 +169,8 @@ struct LaneRlcWeights {
         sc_from_abi(r, resp + i);
         sc_mul(zc, zi, c);
         sc_mul(zr, zi, r);
-        unsigned long long *ka = key_acc + RLC_ACC_WORDS * k, *sa = s_acc + RLC_ACC_WORDS * (j % RLC_SCELLS);
+        const uint32_t cells = rlc_scells(sh);
+        unsigned long long *ka = key_acc + RLC_ACC_WORDS * k, *sa = s_acc + RLC_ACC_WORDS * ((i / sh.csize) * cells + j % cells);
         for (int q = 0; q < SC_WORDS; q++) { rlc_atomic_add(ka + q, zc.w[q]); rlc_atomic_add(sa + q, zr.w[q]); }
     }
 };
@@ -170,15 +178,16 @@ struct LaneRlcWeights {
 // 4) per-key scalars: carry-propagate the accumulator cells (an integer below 2^(448 + 32)) and reduce mod q.
 //    lane k < ngroups: key k; lane ngroups: the response sum, scalar of B.
 struct LaneRlcKeyScalars {
-    uint32_t *kscal; const unsigned long long *key_acc, *s_acc; uint32_t ngroups;
+    uint32_t *kscal; const unsigned long long *key_acc, *s_acc; uint32_t ngroups; uint32_t cells; /* lane ngroups + ch: the response sum of chunk ch */
     GDM void operator()(size_t k) const {
         unsigned long long cell[RLC_ACC_WORDS];
         if (k < ngroups) {
             for (int q = 0; q < RLC_ACC_WORDS; q++) cell[q] = key_acc[RLC_ACC_WORDS * k + q];
         } else {
+            const unsigned long long *base = s_acc + (size_t)RLC_ACC_WORDS * cells * (k - ngroups);
             for (int q = 0; q < RLC_ACC_WORDS; q++) cell[q] = 0;
-            for (int s = 0; s < RLC_SCELLS; s++)
-                for (int q = 0; q < RLC_ACC_WORDS; q++) cell[q] += s_acc[RLC_ACC_WORDS * s + q]; /* < 2^10 * 2^52 */
+            for (uint32_t s = 0; s < cells; s++)
+                for (int q = 0; q < RLC_ACC_WORDS; q++) cell[q] += base[RLC_ACC_WORDS * s + q]; /* < 2^10 * 2^52 */
         }
         uint32_t w[28]; /* 112 bytes, two 56-byte chunks for sc_decode_long */
         unsigned long long carry = 0;
@@ -203,14 +212,16 @@ GD uint32_t rlc_bits(const uint32_t *w, int nwords, uint32_t pos, uint32_t nbits
 }
 struct LaneRlcDigits { /* lane l = l-th point of the class: point index p0 + l, scalar = nwords words at scal + nwords * l */
     uint32_t *keys, *vals; const uint32_t *scal; uint32_t nwords; size_t p0; rlc_shape sh;
+    const uint32_t *chunk_of; /* key class: chunk of the l-th point (null: l / csize, the R class) */
     GDM void operator()(size_t l) const {
         const uint32_t *w = scal + (size_t)nwords * l;
         const size_t off = l * sh.wn;
-        const uint32_t sentinel = sh.wn << sh.c, p = (uint32_t)(p0 + l);
+        const uint32_t sentinel = (sh.nch * sh.wn) << sh.c, p = (uint32_t)(p0 + l);
+        const uint32_t w0 = (chunk_of ? chunk_of[l] : (uint32_t)(l / sh.csize)) * sh.wn;
         for (uint32_t k = 0; k < sh.wn; k++) {
             uint32_t d = rlc_bits(w, (int)nwords, k * sh.c, sh.c);
             if (d && k == sh.top) d = (d << sh.top_shift) | ((uint32_t)l & ((1u << sh.top_shift) - 1u)); /* sub-bucket */
-            keys[off + k] = d ? ((k << sh.c) | d) : sentinel;
+            keys[off + k] = d ? (((w0 + k) << sh.c) | d) : sentinel;
             vals[off + k] = p;
         }
     }
@@ -218,7 +229,7 @@ struct LaneRlcDigits { /* lane l = l-th point of the class: point index p0 + l, 
 
 GD uint32_t rlc_bucket_digit(size_t b, const rlc_shape &sh) {
     const uint32_t low = (uint32_t)b & ((1u << sh.c) - 1u);
-    return (b >> sh.c) == sh.top ? (low >> sh.top_shift) : low;
+    return (uint32_t)(b >> sh.c) % sh.wn == sh.top ? (low >> sh.top_shift) : low;
 }
 // 6) buckets: lane b = (window << c | digit) adds up (or, for the R class, subtracts) the points of its run in the sorted
 //    pair list, on the slot machine (slots.cuh): accumulator in shared-memory slots, each point taken straight from its
@@ -268,7 +279,7 @@ struct LaneRlcSegments {
     pt *segsum; const pt *buckets; rlc_shape sh;
     GDM void operator()(size_t s) const {
         const uint32_t base = (uint32_t)((s * sh.seg) & ((1u << sh.c) - 1u));
-        const uint32_t shift = ((s * sh.seg) >> sh.c) == sh.top ? sh.top_shift : 0u;
+        const uint32_t shift = (uint32_t)((s * sh.seg) >> sh.c) % sh.wn == sh.top ? sh.top_shift : 0u;
         const pt *bk = buckets + s * sh.seg;
         pt run, acc, t, q;
         pt_set_identity(run);
@@ -305,7 +316,7 @@ struct LaneRlcWindows {
         pt acc, t, q;
         pt_ld(acc, nodesum + w * sh.nodes);
         for (size_t k = 1; k < sh.nodes; k++) { pt_ld(q, nodesum + w * sh.nodes + k); pt_add(t, acc, q); pt_copy(acc, t); }
-        const uint32_t dbl = (uint32_t)w * sh.c;
+        const uint32_t dbl = ((uint32_t)w % sh.wn) * sh.c; /* w = chunk * wn + window */
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -313,27 +324,28 @@ struct LaneRlcWindows {
         pt_st(winsum + w, acc);
     }
 };
-// 10) class total: one lane adds the window sums of a class (the key class does this on the side stream, off the critical path).
+// 10) class totals: lane ch adds the window sums of chunk ch (the key class does this on the side stream, off the critical path).
 struct LaneRlcTotal {
     pt *total; const pt *winsum; uint32_t wn;
-    GDM void operator()(size_t) const {
+    GDM void operator()(size_t ch) const {
+        const pt *ws = winsum + ch * wn;
         pt acc, t, q;
-        pt_ld(acc, winsum);
-        for (uint32_t w = 1; w < wn; w++) { pt_ld(q, winsum + w); pt_add(t, acc, q); pt_copy(acc, t); }
-        pt_st(total, acc);
+        pt_ld(acc, ws);
+        for (uint32_t w = 1; w < wn; w++) { pt_ld(q, ws + w); pt_add(t, acc, q); pt_copy(acc, t); }
+        pt_st(total + ch, acc);
     }
 };
-// 11) verdict: the equation holds iff the two class totals add up to the identity of the quotient group (point_eq against
-//     (0, 1): X == 0, goldilocks.c:644-653) and nothing asked for the fallback.
+// 11) verdicts: the equation of chunk ch holds iff its two class totals add up to the identity of the quotient group
+//     (point_eq against (0, 1): X == 0, goldilocks.c:644-653) and nothing asked for the fallback.
 struct LaneRlcVerdict {
     uint32_t *verdict; const pt *total_r, *total_k; const uint32_t *force_fallback;
-    GDM void operator()(size_t) const {
+    GDM void operator()(size_t ch) const {
         pt acc, a, b, id;
-        pt_ld(a, total_r);
-        pt_ld(b, total_k);
+        pt_ld(a, total_r + ch);
+        pt_ld(b, total_k + ch);
         pt_add(acc, a, b);
         pt_set_identity(id);
         const gmask_t same = pt_eq(acc, id) & ~gf_is_zero_mod_p(acc.z);
-        *verdict = (same && !*force_fallback) ? 1u : 0u;
+        verdict[ch] = (same && !*force_fallback) ? 1u : 0u;
     }
 };

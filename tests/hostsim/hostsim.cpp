@@ -283,32 +283,40 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
 #include <algorithm>
 #include "../../libgoldilocks_b200/csrc/rlc.cuh"
 static int g_rlc_force_c = 0;
+static size_t g_rlc_csize = 0; /* 0: one chunk */
 static uint8_t g_rlc_seed[32] = {1, 2, 3};
 EXPORT void hostsim_rlc_config(int force_c, const uint8_t *seed32) { g_rlc_force_c = force_c; if (seed32) memcpy(g_rlc_seed, seed32, 32); }
+EXPORT void hostsim_rlc_chunk(size_t csize) { g_rlc_csize = csize; }
 EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off,
                                                  uint8_t prehashed, const uint8_t *ctx, uint8_t ctx_len, size_t n, int *fast_path) {
     if (fast_path) *fast_path = 0;
     if (n == 0) return -1;
-    /* key groups, as k_group.cu group_keys_all leaves them */
-    std::map<std::string, std::vector<uint32_t>> groups;
-    for (size_t i = 0; i < n; i++) groups[std::string((const char *)pk + 57 * i, 57)].push_back((uint32_t)i);
-    std::vector<uint32_t> order, gid, gstart;
+    const size_t csize = g_rlc_csize && g_rlc_csize < n ? g_rlc_csize : n;
+    const uint32_t nch = (uint32_t)((n + csize - 1) / csize);
+    /* key groups per chunk, as k_group.cu leaves them when the chunk id is part of the key */
+    std::map<std::pair<uint32_t, std::string>, std::vector<uint32_t>> groups;
+    for (size_t i = 0; i < n; i++) groups[{(uint32_t)(i / csize), std::string((const char *)pk + 57 * i, 57)}].push_back((uint32_t)i);
+    std::vector<uint32_t> order, gid, gstart, kchunk;
     for (auto &g : groups) {
         gstart.push_back((uint32_t)order.size());
+        kchunk.push_back(g.first.first);
         for (uint32_t i : g.second) { order.push_back(i); gid.push_back((uint32_t)gstart.size()); }
     }
     const uint32_t m = (uint32_t)gstart.size();
     gstart.push_back((uint32_t)n);
+    for (uint32_t ch = 0; ch < nch; ch++) kchunk.push_back(ch); /* the B of every chunk */
     const rlc_groups g = {order.data(), gid.data(), gstart.data(), m};
-    const rlc_shape sh_r = rlc_shape_for(n, g_rlc_force_c, 0), sh_k = rlc_shape_for((size_t)m + 1, g_rlc_force_c ? g_rlc_force_c + 1 : 0, 1);
-    const size_t npts = n + m + 1;
+    rlc_shape sh_r = rlc_shape_for(csize, g_rlc_force_c, 0), sh_k = rlc_shape_for(((size_t)m + nch + nch - 1) / nch, g_rlc_force_c ? g_rlc_force_c + 1 : 0, 1);
+    sh_r.nch = sh_k.nch = nch; sh_r.csize = sh_k.csize = (uint32_t)csize;
+    const uint32_t cells = rlc_scells(sh_r);
+    const size_t npts = n + m + nch;
     std::vector<pt> pts(npts);
     std::vector<int32_t> ok(npts), valid(n);
-    std::vector<uint32_t> flags(2, 0), z(RLC_ZWORDS * (n + 8)), kscal(SC_WORDS * ((size_t)m + 1));
+    std::vector<uint32_t> flags(1 + nch, 0), z(RLC_ZWORDS * (n + 8)), kscal(SC_WORDS * ((size_t)m + nch));
     std::vector<abi_sc> chal(n), resp(n);
-    std::vector<unsigned long long> key_acc((size_t)RLC_ACC_WORDS * m, 0), s_acc((size_t)RLC_ACC_WORDS * RLC_SCELLS, 0);
+    std::vector<unsigned long long> key_acc((size_t)RLC_ACC_WORDS * m, 0), s_acc((size_t)RLC_ACC_WORDS * cells * nch, 0);
     LaneRlcDecode fk = {pts.data(), ok.data(), flags.data(), sig, pk, n, g, n};
-    run(fk, (size_t)m + 1);
+    run(fk, (size_t)m + nch);
     LaneRlcDecode f1 = {pts.data(), ok.data(), flags.data(), sig, pk, n, g, 0};
     run(f1, n);
     LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len, 0};
@@ -316,16 +324,16 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
     LaneRlcZ f3 = {z.data(), g_rlc_seed, n, sh_r.zbits};
     run(f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE);
     const std::vector<uint32_t> z_for_digits = z; /* the product makes the R pair list before the decodes are in */
-    LaneRlcWeights f4 = {z.data(), valid.data(), key_acc.data(), s_acc.data(), chal.data(), resp.data(), ok.data(), n, g};
+    LaneRlcWeights f4 = {z.data(), valid.data(), key_acc.data(), s_acc.data(), chal.data(), resp.data(), ok.data(), n, g, sh_r};
     run(f4, n);
-    LaneRlcKeyScalars f5 = {kscal.data(), key_acc.data(), s_acc.data(), m};
-    run(f5, (size_t)m + 1);
-    auto run_class = [&](const rlc_shape &sh, size_t count, const uint32_t *scal, uint32_t nwords, size_t p0, std::vector<pt> &winsum, bool subtract) {
-        const size_t npairs = count * sh.wn, nb = (size_t)sh.wn << sh.c;
+    LaneRlcKeyScalars f5 = {kscal.data(), key_acc.data(), s_acc.data(), m, cells};
+    run(f5, (size_t)m + nch);
+    auto run_class = [&](const rlc_shape &sh, size_t count, const uint32_t *scal, uint32_t nwords, size_t p0, std::vector<pt> &total, bool subtract, const uint32_t *chunk_of) {
+        const size_t npairs = count * sh.wn, nw = (size_t)sh.nch * sh.wn, nb = nw << sh.c;
         std::vector<uint32_t> keys(npairs), vals(npairs);
-        std::vector<pt> buckets(nb), segsum((size_t)sh.wn * sh.segs), nodesum((size_t)sh.wn * sh.nodes);
-        winsum.resize(sh.wn);
-        LaneRlcDigits f6 = {keys.data(), vals.data(), scal, nwords, p0, sh};
+        std::vector<pt> buckets(nb), segsum(nw * sh.segs), nodesum(nw * sh.nodes), winsum(nw);
+        total.resize(sh.nch);
+        LaneRlcDigits f6 = {keys.data(), vals.data(), scal, nwords, p0, sh, chunk_of};
         run(f6, count);
         std::vector<std::pair<uint32_t, uint32_t>> pairs(npairs);
         for (size_t j = 0; j < npairs; j++) pairs[j] = {keys[j], vals[j]};
@@ -334,25 +342,27 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
         SlotRlcBucket f7 = {buckets.data(), keys.data(), vals.data(), npairs, pts.data(), sh, subtract ? ~0u : 0u, subtract ? valid.data() : nullptr};
         run_sm(f7, nb);
         LaneRlcSegments f8 = {segsum.data(), buckets.data(), sh};
-        run(f8, (size_t)sh.wn * sh.segs);
+        run(f8, nw * sh.segs);
         LaneRlcNodes f9 = {nodesum.data(), segsum.data(), sh};
-        run(f9, (size_t)sh.wn * sh.nodes);
+        run(f9, nw * sh.nodes);
         LaneRlcWindows f10 = {winsum.data(), nodesum.data(), sh};
-        run(f10, sh.wn);
+        run(f10, nw);
+        LaneRlcTotal f11 = {total.data(), winsum.data(), sh.wn};
+        run(f11, sh.nch);
     };
-    std::vector<pt> win_r, win_k;
-    run_class(sh_k, (size_t)m + 1, kscal.data(), SC_WORDS, n, win_k, false);
-    run_class(sh_r, n, z_for_digits.data(), RLC_ZWORDS, 0, win_r, true);
-    pt tot_r, tot_k;
-    LaneRlcTotal ftr = {&tot_r, win_r.data(), sh_r.wn}, ftk = {&tot_k, win_k.data(), sh_k.wn};
-    run(ftr, 1);
-    run(ftk, 1);
-    LaneRlcVerdict f11 = {flags.data() + 1, &tot_r, &tot_k, flags.data()};
-    run(f11, 1);
-    if (flags[1]) {
-        if (fast_path) *fast_path = 1;
-        for (size_t i = 0; i < n; i++) st[i] = valid[i];
-        return -1;
+    std::vector<pt> tot_r, tot_k;
+    run_class(sh_k, (size_t)m + nch, kscal.data(), SC_WORDS, n, tot_k, false, kchunk.data());
+    run_class(sh_r, n, z_for_digits.data(), RLC_ZWORDS, 0, tot_r, true, nullptr);
+    LaneRlcVerdict f12 = {flags.data() + 1, tot_r.data(), tot_k.data(), flags.data()};
+    run(f12, nch);
+    /* chunks whose equation held take their statuses from `valid`; every other chunk goes through the ordinary path on its own */
+    int all = 1;
+    for (uint32_t ch = 0; ch < nch; ch++) {
+        const size_t lo = (size_t)ch * csize, hi = lo + csize < n ? lo + csize : n;
+        if (flags[1 + ch]) { for (size_t i = lo; i < hi; i++) st[i] = valid[i]; continue; }
+        all = 0;
+        goldilocks_ed448_verify_batch(st + lo, sig + 114 * lo, pk + 57 * lo, msg, off + lo, prehashed, ctx, ctx_len, hi - lo);
     }
-    return goldilocks_ed448_verify_batch(st, sig, pk, msg, off, prehashed, ctx, ctx_len, n);
+    if (fast_path) *fast_path = all;
+    return -1;
 }

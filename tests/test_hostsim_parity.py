@@ -95,6 +95,22 @@ def test_eddsa_rlc(sim, chk):
         assert (st == 0).all() and fast == 1     # everything rejected up front; the empty equation holds
 
 
+def test_eddsa_rlc_chunks(sim, chk):
+    """chunked batch equations (branch next/rlc-chunks): every chunk of consecutive signatures has its own verdict, so a bad
+    signature sends only its chunk to the per-signature path; statuses are the reference's for every chunk size"""
+    import ctypes
+    _threads(sim, chk)
+    try:
+        for csize in (16, 50, 149):
+            sim.lib.hostsim_rlc_chunk(ctypes.c_size_t(csize))
+            for c in (0, 3):
+                sim.lib.hostsim_rlc_config(ctypes.c_int(c), None)
+                parity.check_eddsa_rlc(sim, chk, 150, label="c4r/chunk%d.%d" % (csize, c))
+    finally:
+        sim.lib.hostsim_rlc_chunk(ctypes.c_size_t(0))
+        sim.lib.hostsim_rlc_config(ctypes.c_int(0), None)
+
+
 def test_scalar_folding_reduction_fuzz(sim):
     """sc_reduce_114 / sc_reduce_57 (csrc/sc.cuh: folding at 2^448 = 4c) against Python integers: random values, long runs
     of ones and zeros (carry ripples), multiples of q plus small offsets, values just below the top"""

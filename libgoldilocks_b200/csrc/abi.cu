@@ -1060,18 +1060,19 @@ static bool rlc_usable(size_t n) { return n >= RLC_MIN && n < ((size_t)1 << 26);
 // sums (the c*w doublings) are a separate launch so that the key class can run its long chain on the side stream.
 struct RlcClass { rlc_shape sh; size_t count, npairs, nb; uint32_t *keys, *vals, *keys_s, *vals_s; void *sort_tmp; size_t sort_bytes; pt *buckets, *segsum, *nodesum, *winsum, *total; };
 static bool rlc_class_alloc(Call &k, RlcClass &q, const rlc_shape &sh, size_t count) {
-    q.sh = sh; q.count = count; q.npairs = count * sh.wn; q.nb = (size_t)sh.wn << sh.c;
+    const size_t nw = (size_t)sh.nch * sh.wn; /* window ids run over chunks x windows */
+    q.sh = sh; q.count = count; q.npairs = count * sh.wn; q.nb = nw << sh.c;
     q.keys = k.out<uint32_t>(q.npairs); q.vals = k.out<uint32_t>(q.npairs); q.keys_s = k.out<uint32_t>(q.npairs); q.vals_s = k.out<uint32_t>(q.npairs);
     q.sort_bytes = pair_sort_scratch_bytes(q.npairs);
     q.sort_tmp = k.alloc(q.sort_bytes);
-    q.buckets = k.out<pt>(q.nb); q.segsum = k.out<pt>((size_t)sh.wn * sh.segs); q.nodesum = k.out<pt>((size_t)sh.wn * sh.nodes); q.winsum = k.out<pt>(sh.wn); q.total = k.out<pt>(1);
+    q.buckets = k.out<pt>(q.nb); q.segsum = k.out<pt>(nw * sh.segs); q.nodesum = k.out<pt>(nw * sh.nodes); q.winsum = k.out<pt>(nw); q.total = k.out<pt>(sh.nch);
     return k.ok;
 }
-static bool rlc_class_pairs(Ctx &c, const RlcClass &q, const uint32_t *scal, uint32_t nwords, size_t p0, cudaStream_t s) { /* digits -> sorted pair list */
-    LaneRlcDigits f6 = {q.keys, q.vals, scal, nwords, p0, q.sh, nullptr}; /* one chunk (chunked orchestration: next round, see tests/hostsim) */
+static bool rlc_class_pairs(Ctx &c, const RlcClass &q, const uint32_t *scal, uint32_t nwords, size_t p0, cudaStream_t s, const uint32_t *chunk_of) { /* digits -> sorted pair list */
+    LaneRlcDigits f6 = {q.keys, q.vals, scal, nwords, p0, q.sh, chunk_of};
     if (!launch(c, f6, q.count, s)) return false;
     int key_bits = 1;
-    while ((q.sh.wn << q.sh.c) >> key_bits) key_bits++;
+    while (((q.sh.nch * q.sh.wn) << q.sh.c) >> key_bits) key_bits++;
     cudaError_t e = pair_sort(q.sort_tmp, q.sort_bytes, q.keys, q.keys_s, q.vals, q.vals_s, q.npairs, key_bits, s);
     if (e != cudaSuccess) return fail("pair_sort", e);
     return true;
@@ -1081,14 +1082,15 @@ static bool rlc_class_sum(Ctx &c, const RlcClass &q, const pt *recs, cudaStream_
      * the SMs between them (persistent blocks held the SMs and starved the side stream: 22.6 vs 20.9 ms per 2^20) */
     SlotRlcBucket f7 = {q.buckets, q.keys_s, q.vals_s, q.npairs, recs, q.sh, subtract ? ~0u : 0u, valid};
     if (!launch_slots(c, f7, q.nb, s)) return false;
+    const size_t nw = (size_t)q.sh.nch * q.sh.wn;
     LaneRlcSegments f8 = {q.segsum, q.buckets, q.sh};
-    if (!launch(c, f8, (size_t)q.sh.wn * q.sh.segs, s)) return false;
+    if (!launch(c, f8, nw * q.sh.segs, s)) return false;
     LaneRlcNodes f9 = {q.nodesum, q.segsum, q.sh};
-    if (!launch(c, f9, (size_t)q.sh.wn * q.sh.nodes, s)) return false;
+    if (!launch(c, f9, nw * q.sh.nodes, s)) return false;
     LaneRlcWindows f10 = {q.winsum, q.nodesum, q.sh};
-    if (!launch(c, f10, q.sh.wn, s)) return false;
+    if (!launch(c, f10, nw, s)) return false;
     LaneRlcTotal f11 = {q.total, q.winsum, q.sh.wn};
-    return launch(c, f11, 1, s);
+    return launch(c, f11, q.sh.nch, s);
 }
 // Host-pointer calls feed the copy stream in the order the work can start in: the first half of the signatures (the R decodes,
 // 55 % of the call, need nothing else), then keys / offsets / context (the grouping pass), then the rest.
@@ -1112,20 +1114,28 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     }
     uint8_t seed[32];
     if (!rlc_seed(seed)) return false;
+    /* chunks: GOLDILOCKS_B200_RLC_CHUNK = signatures per chunk (0 / unset: one chunk = one equation for the whole call).  With
+     * chunks a bad signature sends only its chunk to the per-signature path; the price is a smaller digit width (more additions
+     * per signature) and nch times the tail work. */
+    size_t csize = n;
+    if (const char *e = getenv("GOLDILOCKS_B200_RLC_CHUNK")) { const long v = atol(e); if (v >= (long)RLC_MIN && (size_t)v < n) csize = (size_t)v; }
+    const uint32_t nch = (uint32_t)((n + csize - 1) / csize);
     /* everything sized by n alone first: the R decodes start before the number of distinct keys is known */
-    const rlc_shape sh_r = rlc_shape_for(n, 0, 0);
+    rlc_shape sh_r = rlc_shape_for(csize, 0, 0);
+    sh_r.nch = nch; sh_r.csize = (uint32_t)csize;
+    const uint32_t cells = rlc_scells(sh_r);
     void *gs = k.alloc(group_all_scratch_bytes(n));
     uint8_t *dseed = k.out<uint8_t>(32);
-    pt *pts = k.out<pt>(2 * n + 1);                                   /* n R records, then at most n keys, then B */
-    int32_t *ok = k.out<int32_t>(2 * n + 1), *valid = k.out<int32_t>(n);
-    uint32_t *flags = k.out<uint32_t>(2);                             /* [0] force fallback, [1] verdict */
+    pt *pts = k.out<pt>(2 * n + nch);                                 /* n R records, then at most n key groups, then one B per chunk */
+    int32_t *ok = k.out<int32_t>(2 * n + nch), *valid = k.out<int32_t>(n);
+    uint32_t *flags = k.out<uint32_t>(1 + (size_t)nch);               /* [0] force fallback, [1 + ch] verdict of chunk ch */
     abi_sc *chal = k.out<abi_sc>(n), *resp = k.out<abi_sc>(n);
     uint32_t *z = k.out<uint32_t>(RLC_ZWORDS * n);
-    unsigned long long *s_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * RLC_SCELLS);
+    unsigned long long *s_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * cells * nch);
     RlcClass cr, ck;
     if (!rlc_class_alloc(k, cr, sh_r, n)) return false;
-    CU(cudaMemsetAsync(flags, 0, 2 * sizeof(uint32_t), s));
-    CU(cudaMemsetAsync(s_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * RLC_SCELLS, s));
+    CU(cudaMemsetAsync(flags, 0, (1 + (size_t)nch) * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(s_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * cells * nch, s));
     CU(cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, s));
     /* Two streams.  Main: the multiplier-bound work -- the R decodes as the signatures land, later the bucket sums of the R class.
      * Side (high priority): what needs no decoded R -- the weights and the sorted pair list of the R class (they depend on the
@@ -1137,7 +1147,7 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     CU(cudaStreamWaitEvent(side, c.side_evt[0], 0)); /* whatever produced the inputs on `s`, and the seed */
     LaneRlcZ f3 = {z, dseed, n, sh_r.zbits};
     if (!launch(c, f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE, side)) return false;
-    if (!rlc_class_pairs(c, cr, z, RLC_ZWORDS, 0, side)) return false;
+    if (!rlc_class_pairs(c, cr, z, RLC_ZWORDS, 0, side, nullptr)) return false;
     const size_t s0 = feed ? feed->split[0] : n, s1 = feed ? feed->split[1] : n;
     const size_t lo[3] = {0, s0, s1}, hi[3] = {s0, s1, n};
     const rlc_groups no_groups = {nullptr, nullptr, nullptr, 0};
@@ -1150,21 +1160,26 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     if (feed) CU(cudaStreamWaitEvent(side, feed->keys, 0));
     key_groups kg;
     uint64_t launched = 0;
-    cudaError_t e = group_keys_all(dpk, n, gs, &kg, side, &launched);
+    cudaError_t e = group_keys_all(dpk, n, gs, &kg, side, &launched, nch > 1 ? (uint32_t)csize : 0u);
     if (e != cudaSuccess) return fail("group_keys_all", e);
     g_launches += launched;
     uint32_t m = 0;
     CU(cudaMemcpyAsync(&m, kg.ngroups, sizeof m, cudaMemcpyDeviceToHost, side));
-    CU(cudaStreamSynchronize(side)); /* the number of distinct keys sizes the key class; the R decodes are already queued */
+    CU(cudaStreamSynchronize(side)); /* the number of key groups sizes the key class; the R decodes are already queued */
     if (m == 0 || m > n) { g_err = "rlc: key grouping returned an impossible group count"; return false; }
     const rlc_groups g = {kg.order, kg.gid, kg.gstart, m};
-    const rlc_shape sh_k = rlc_shape_for((size_t)m + 1, 0, 1);
+    const size_t nkey = (size_t)m + nch;                                 /* key groups, then the B of every chunk */
+    rlc_shape sh_k = rlc_shape_for((nkey + nch - 1) / nch, 0, 1);
+    sh_k.nch = nch; sh_k.csize = (uint32_t)csize;
     unsigned long long *key_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * m);
-    uint32_t *kscal = k.out<uint32_t>(SC_WORDS * ((size_t)m + 1));
-    if (!rlc_class_alloc(k, ck, sh_k, (size_t)m + 1)) return false;
+    uint32_t *kscal = k.out<uint32_t>(SC_WORDS * nkey), *kchunk = k.out<uint32_t>(nkey);
+    if (!rlc_class_alloc(k, ck, sh_k, nkey)) return false;
     CU(cudaMemsetAsync(key_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * m, side));
+    e = key_chunks(kchunk, &kg, m, nch, nch > 1 ? (uint32_t)csize : 0u, side);
+    if (e != cudaSuccess) return fail("key_chunks", e);
+    g_launches++;
     LaneRlcDecode fk = {pts, ok, flags, dsig, dpk, n, g, n};
-    if (!launch(c, fk, (size_t)m + 1, side)) return false;
+    if (!launch(c, fk, nkey, side)) return false;
     if (feed) CU(cudaStreamWaitEvent(side, feed->rest, 0));
     LaneEdVerifyScalars f2 = {chal, resp, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, 0};
     if (!launch(c, f2, n, side)) return false;
@@ -1172,11 +1187,11 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));
     LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g, sh_r};
     if (!launch(c, f4, n, s)) return false;
-    LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m, RLC_SCELLS};
-    if (!launch(c, f5, (size_t)m + 1, s)) return false;
+    LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m, cells};
+    if (!launch(c, f5, nkey, s)) return false;
     CU(cudaEventRecord(c.side_evt[2], s));
     CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));
-    if (!rlc_class_pairs(c, ck, kscal, SC_WORDS, n, side)) return false;
+    if (!rlc_class_pairs(c, ck, kscal, SC_WORDS, n, side, kchunk)) return false;
     CU(cudaEventRecord(c.side_evt[4], side));
     if (!rlc_class_sum(c, ck, pts, side, false, nullptr)) return false;
     CU(cudaEventRecord(c.side_evt[3], side));
@@ -1184,17 +1199,33 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     if (!rlc_class_sum(c, cr, pts, s, true, valid)) return false;
     CU(cudaStreamWaitEvent(s, c.side_evt[3], 0));
     LaneRlcVerdict f11 = {flags + 1, cr.total, ck.total, flags};
-    if (!launch(c, f11, 1, s)) return false;
-    uint32_t hflags[2] = {0, 0};
-    CU(cudaMemcpyAsync(hflags, flags, sizeof hflags, cudaMemcpyDeviceToHost, s));
+    if (!launch(c, f11, nch, s)) return false;
+    std::vector<uint32_t> hflags(1 + (size_t)nch, 0);
+    CU(cudaMemcpyAsync(hflags.data(), flags, hflags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     CU(cudaMemsetAsync(z, 0, sizeof(uint32_t) * RLC_ZWORDS * n, s)); /* the weights are secret until the verdict is out; wipe them */
-    if (hflags[1]) {
+    size_t failed = 0;
+    for (uint32_t ch = 0; ch < nch; ch++) failed += hflags[1 + ch] ? 0 : 1;
+    if (failed == 0) {
         *fast = 1;
         CU(cudaMemcpyAsync(dst, valid, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
         return true;
     }
-    return ordinary();
+    if (nch == 1 || failed * 4 > nch) return ordinary(); /* more than a quarter of the chunks: one pass over everything is cheaper */
+    /* chunks whose equation held take their statuses from `valid`; the others go through the per-signature path, one by one */
+    CU(cudaMemcpyAsync(dst, valid, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
+    VerifyGrids grids;
+    if (!verify_grids(c, &grids)) return false;
+    const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
+    uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
+    void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(csize));
+    if (!k.ok) return false;
+    for (uint32_t ch = 0; ch < nch; ch++) {
+        if (hflags[1 + ch]) continue;
+        const size_t clo = (size_t)ch * csize, chi = clo + csize < n ? clo + csize : n;
+        if (!verify_dev(c, dst + clo, dsig + 114 * clo, dpk + 57 * clo, dmsg, doff + clo, prehashed, dctx, ctx_len, chi - clo, scratch, slots, grids, s)) return false;
+    }
+    return true;
 }
 goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                      uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, int *fast_path) {

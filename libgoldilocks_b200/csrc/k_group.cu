@@ -15,7 +15,8 @@ inline unsigned blocks(size_t n) { return (unsigned)((n + GB - 1) / GB); }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; }
 
-__global__ void k_hash(uint64_t *h, uint32_t *idx, const uint8_t *pk, uint32_t n) {
+// `csize`: signatures per chunk when the chunk id is part of the grouping key (rlc.cuh: one equation per chunk); 0 = no chunks
+__global__ void k_hash(uint64_t *h, uint32_t *idx, const uint8_t *pk, uint32_t n, uint32_t csize = 0) {
     const uint32_t i = blockIdx.x * GB + threadIdx.x;
     if (i >= n) return;
     const uint8_t *p = pk + 57 * (size_t)i;
@@ -25,10 +26,11 @@ __global__ void k_hash(uint64_t *h, uint32_t *idx, const uint8_t *pk, uint32_t n
         for (int b = 0; b < 8; b++) { const int k = 8 * w + b; if (k < 57) x |= (uint64_t)p[k] << (8 * b); }
         acc = mix64(acc ^ x) + 0x9e3779b97f4a7c15ull * (uint64_t)(w + 1);
     }
+    if (csize) acc = mix64(acc ^ (uint64_t)(i / csize));
     h[i] = acc;
     idx[i] = i;
 }
-__global__ void k_heads(uint32_t *head, const uint32_t *is, const uint8_t *pk, uint32_t n) {
+__global__ void k_heads(uint32_t *head, const uint32_t *is, const uint8_t *pk, uint32_t n, uint32_t csize = 0) {
     const uint32_t j = blockIdx.x * GB + threadIdx.x;
     if (j >= n) return;
     uint32_t differ = 1;
@@ -36,6 +38,7 @@ __global__ void k_heads(uint32_t *head, const uint32_t *is, const uint8_t *pk, u
         const uint8_t *a = pk + 57 * (size_t)is[j], *b = pk + 57 * (size_t)is[j - 1];
         uint32_t d = 0;
         for (int k = 0; k < 57; k++) d |= (uint32_t)(a[k] ^ b[k]);
+        if (csize) d |= (is[j] / csize) ^ (is[j - 1] / csize);
         differ = d ? 1u : 0u;
     }
     head[j] = differ;
@@ -131,7 +134,16 @@ size_t group_all_scratch_bytes(size_t n) {
     cub::DeviceScan::InclusiveSum(nullptr, b2, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n);
     return 2 * al(8 * n) + 4 * al(4 * n) + al(4 * (n + 1)) + al(4) + al((b1 > b2 ? b1 : b2) + 256);
 }
-cudaError_t group_keys_all(const uint8_t *pk, size_t n, void *scratch, key_groups *out, cudaStream_t s, uint64_t *launches) {
+__global__ void k_kchunk(uint32_t *kchunk, const uint32_t *is, const uint32_t *gstart, uint32_t m, uint32_t nch, uint32_t csize) {
+    const uint32_t l = blockIdx.x * GB + threadIdx.x;
+    if (l < m) kchunk[l] = csize ? is[gstart[l]] / csize : 0u;   /* chunk of key group l */
+    else if (l < m + nch) kchunk[l] = l - m;                      /* the B of chunk l - m */
+}
+cudaError_t key_chunks(uint32_t *kchunk, const key_groups *g, uint32_t m, uint32_t nch, uint32_t csize, cudaStream_t s) {
+    k_kchunk<<<blocks((size_t)m + nch), GB, 0, s>>>(kchunk, g->order, g->gstart, m, nch, csize);
+    return cudaGetLastError();
+}
+cudaError_t group_keys_all(const uint8_t *pk, size_t n, void *scratch, key_groups *out, cudaStream_t s, uint64_t *launches, uint32_t csize) {
     char *p = (char *)scratch;
     auto take = [&](size_t bytes) { char *r = p; p += al(bytes); return (void *)r; };
     uint64_t *h = (uint64_t *)take(8 * n), *hs = (uint64_t *)take(8 * n);
@@ -145,9 +157,9 @@ cudaError_t group_keys_all(const uint8_t *pk, size_t n, void *scratch, key_group
     const uint32_t m = (uint32_t)n;
     size_t tmp = cub_bytes;
     cudaError_t e;
-    k_hash<<<blocks(n), GB, 0, s>>>(h, idx, pk, m);
+    k_hash<<<blocks(n), GB, 0, s>>>(h, idx, pk, m, csize);
     if ((e = cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, h, hs, idx, is, (int)n, 0, 64, s)) != cudaSuccess) return e;
-    k_heads<<<blocks(n), GB, 0, s>>>(head, is, pk, m);
+    k_heads<<<blocks(n), GB, 0, s>>>(head, is, pk, m, csize);
     tmp = cub_bytes;
     if ((e = cub::DeviceScan::InclusiveSum(cub_tmp, tmp, head, gid, (int)n, s)) != cudaSuccess) return e;
     k_gstart<<<blocks(n), GB, 0, s>>>(gstart, ngroups, head, gid, m);

@@ -22,7 +22,8 @@ size_t group_scratch_bytes(size_t n, size_t cap);
 // Every distinct key of a batch (k_group.cu group_keys_all): the view the random-linear-combination path works from.
 struct key_groups { const uint32_t *order, *gid, *gstart, *ngroups; };
 size_t group_all_scratch_bytes(size_t n);
-cudaError_t group_keys_all(const uint8_t *pk, size_t n, void *scratch, key_groups *out, cudaStream_t s, uint64_t *launches);
+cudaError_t group_keys_all(const uint8_t *pk, size_t n, void *scratch, key_groups *out, cudaStream_t s, uint64_t *launches, uint32_t csize = 0);
+cudaError_t key_chunks(uint32_t *kchunk, const key_groups *g, uint32_t m, uint32_t nch, uint32_t csize, cudaStream_t s);
 size_t pair_sort_scratch_bytes(size_t npairs);
 cudaError_t pair_sort(void *tmp, size_t tmp_bytes, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in, uint32_t *vals_out, size_t npairs,
                       int key_bits, cudaStream_t s);

@@ -583,6 +583,7 @@ def run_ours(args):
         fast = C.c_int(0)
         argr = [C.c_void_p(h_st.data_ptr()), C.c_void_p(r_sig.data_ptr()), C.c_void_p(r_pk.data_ptr()), C.c_void_p(r_msg.data_ptr()),
                 C.c_void_p(r_off.data_ptr()), C.c_uint8(0), None, C.c_uint8(0), C.c_size_t(n), C.byref(fast)]
+        lib.rlc_policy(16)
         for _ in range(2):
             assert fr(*argr) == -1
         assert (h_st.numpy() == -1).all() and fast.value == 1, "the batch equation must decide an all-valid batch"
@@ -599,7 +600,9 @@ def run_ours(args):
                                              "api": "goldilocks_ed448_verify_rlc_batch (host pointers, pinned): one multi-scalar multiplication per chunk with secret "
                                                     "weights decides it; per-signature fallback for the chunks whose equation fails; corpus = the bench shape with NO corrupted entries"}
         # corruption sweep: flip one S bit in every `1/rate`-th signature (spread evenly), time the call, check the statuses
-        sweep = {}
+        sweep = {"note": "per rate: one untimed call, then two timed ones (steady state: after a call in which most chunks failed the library "
+                         "skips the equation for the next calls, goldilocks_b200_rlc_policy); fast_path 1 = whole-batch equation, 2 = per-chunk "
+                         "equations + the failing chunks re-verified, 0 = per-signature path over everything"}
         clean = sig2.copy()
         for label, every in (("0", 0), ("1_bad", n), ("2^-14", 1 << 14), ("2^-10", 1 << 10), ("2^-6", 1 << 6), ("1/8", 8)):
             cur = clean.copy()

@@ -260,8 +260,18 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_keyset_batch(gold
  * front like the reference does; the rest are checked by ONE multi-scalar multiplication with fresh secret 128-bit
  * weights.  If that equation holds every remaining signature is reported valid (wrong with probability < 2^-127 per
  * call); if it does not, the ordinary per-signature path runs over the batch, so the statuses are the reference's
- * either way.  *fast_path (may be NULL) receives 1 when the equation decided the batch, 0 when the call fell back. */
+ * either way.  When the whole-batch equation fails the call localises the damage: the equations are evaluated again per
+ * chunk of ~4096 consecutive signatures (same R decodes, challenges and weights), chunks whose equation holds are decided,
+ * and only the signatures of the failing chunks go through the per-signature path (packed into one batch).  If more than
+ * half of the chunks fail, the per-signature path runs over everything and the next calls on this device skip the equation
+ * (see goldilocks_b200_rlc_policy).  *fast_path (may be NULL) receives 1 when the whole-batch equation decided the call,
+ * 2 when the per-chunk equations did (failing chunks re-verified one signature at a time), 0 when the per-signature path ran
+ * over everything. */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status, const uint8_t *signature /*n*114*/, const uint8_t *pubkey /*n*57*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, int *fast_path);
+/* After a call in which most chunks failed, the next `reprobe` - 1 calls of goldilocks_ed448_verify_rlc_batch on that device go
+ * straight to the per-signature path and the one after tries the equation again (default 16; 0 = always try).  Setting the
+ * policy also clears the remembered outcomes. */
+GOLDILOCKS_B200_API void goldilocks_b200_rlc_policy(unsigned reprobe);
 /* SHAKE256 one-shot over n inputs, each squeezed to outlen bytes (shake.c:177-190, SHAKE256 params 211-213) */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out /*n*outlen*/, size_t outlen, const uint8_t *in, const size_t *in_off /*n+1*/, size_t n);
 

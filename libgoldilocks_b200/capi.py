@@ -347,6 +347,11 @@ class BatchLib:
         self._call("goldilocks_ed448_verify_rlc_batch", st, sig, pk, arena, off, C.c_uint8(1 if prehashed else 0), ctx, C.c_uint8(ctx_len), _Z(len(sig)), C.byref(fast))
         return st, fast.value
 
+    def rlc_policy(self, reprobe):
+        """goldilocks_b200_rlc_policy: how many calls skip the batch equation after one in which most chunks failed (0 = never skip)"""
+        self.lib.goldilocks_b200_rlc_policy.restype = None
+        self.lib.goldilocks_b200_rlc_policy(C.c_uint(reprobe))
+
     # ---- device sets: one host-pointer batch over several GPUs (include/goldilocks_b200.h, section 4) ----
     def set_devices(self, devices):
         """spread every later `*_batch` host-pointer call over these CUDA devices ([] = the current device only)"""

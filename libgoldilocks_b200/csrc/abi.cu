@@ -5,9 +5,11 @@
 // implementation behind these symbols: without a usable sm_100 GPU every call fails loudly.
 #include <cuda_runtime.h>
 #include <sys/random.h>
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <typeinfo>
@@ -49,6 +51,7 @@ struct Ctx {
     size_t used = 0;             // bytes used in the active block
     void *slot_scratch = nullptr;
     unsigned *work_counter = nullptr;   // dynamic hand-out counter of the persistent kernels (launch_smp)
+    unsigned rlc_skip = 0;              // calls of the RLC entry point that go straight to the per-signature path (rlc_core)
     size_t slot_cap = 0;
 };
 constexpr int MAX_DEV = 64;
@@ -1089,143 +1092,201 @@ static bool rlc_class_sum(Ctx &c, const RlcClass &q, const pt *recs, cudaStream_
     if (!launch(c, f9, nw * q.sh.nodes, s)) return false;
     LaneRlcWindows f10 = {q.winsum, q.nodesum, q.sh};
     if (!launch(c, f10, nw, s)) return false;
-    LaneRlcTotal f11 = {q.total, q.winsum, q.sh.wn};
+    LaneRlcTotal f11 = {q.total, q.winsum, q.sh.wn, q.sh.nch > 1 ? q.sh.c : 0u};
     return launch(c, f11, q.sh.nch, s);
 }
 // Host-pointer calls feed the copy stream in the order the work can start in: the first half of the signatures (the R decodes,
 // 55 % of the call, need nothing else), then keys / offsets / context (the grouping pass), then the rest.
 struct RlcFeed { size_t split[2]; cudaEvent_t sig0, keys, sig1, rest; }; /* signatures [0, split[0]) | keys | [split[0], split[1]) | the rest */
+// goldilocks_ed448_verify_rlc_batch, on device buffers.  *fast: 1 = the whole-batch equation decided the call; 2 = it failed, the
+// equations were run again per chunk of consecutive signatures (same R decodes, challenges and weights) and only the chunks that
+// failed were re-verified one signature at a time; 0 = the ordinary per-signature path ran over everything.
+//
+// Why two passes instead of chunks from the start: chunks cost digit width (a chunk of 4 096 signatures fills its buckets with
+// c = 9, i.e. 15 additions per signature instead of 9, and every chunk pays its own bucket folding and key class), so the
+// all-valid call -- the one this entry point exists for -- stays one equation; what a failure adds is the second pass
+// (no decodes, no hashes) plus the per-signature path over the failed chunks only, packed into one batch.
+// Traffic that keeps failing most chunks gains nothing from either pass, so the context remembers the last outcome: after
+// a call in which more than RLC_GIVE_UP of the chunks failed, the next reprobe - 1 calls on this context (goldilocks_b200_rlc_policy, default 16) go straight to the
+// per-signature path (cost: the ordinary call's) and the one after that tries the equation again.
+constexpr size_t RLC_CHUNK_TARGET = 4096;   /* signatures per chunk of the localisation pass (GOLDILOCKS_B200_RLC_CHUNK overrides) */
+constexpr uint32_t RLC_MAX_CHUNKS = 1024;
+std::atomic<unsigned> g_rlc_reprobe{16};     /* goldilocks_b200_rlc_policy */
 static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *dpk, const uint8_t *dmsg, const size_t *doff, uint8_t prehashed,
                      const uint8_t *dctx, uint8_t ctx_len, size_t n, cudaStream_t s, int *fast, const RlcFeed *feed = nullptr) {
     Ctx &c = *k.c;
     *fast = 0;
-    auto ordinary = [&]() { /* every copy has been waited for on `s` by the time this runs */
+    auto ordinary_on = [&](int32_t *st, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off, size_t cnt) {
         VerifyGrids grids;
         if (!verify_grids(c, &grids)) return false;
         const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
         uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
-        void *scratch = k.alloc(verify_core_scratch_bytes(n));
+        void *scratch = k.alloc(verify_core_scratch_bytes(cnt));
         if (!k.ok) return false;
-        return verify_dev(c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, n, scratch, slots, grids, s);
+        return verify_dev(c, st, sig, pk, msg, off, prehashed, dctx, ctx_len, cnt, scratch, slots, grids, s);
     };
-    if (!rlc_usable(n)) {
+    auto ordinary = [&]() { return ordinary_on(dst, dsig, dpk, dmsg, doff, n); }; /* every copy has been waited for on `s` by the time this runs */
+    const bool skip = c.rlc_skip > 0;       /* recent calls failed most of their chunks: do not even try (see above) */
+    if (skip) c.rlc_skip--;
+    if (!rlc_usable(n) || skip) {
         if (feed) CU(cudaStreamWaitEvent(s, feed->rest, 0));
         return ordinary();
     }
     uint8_t seed[32];
     if (!rlc_seed(seed)) return false;
-    /* chunks: GOLDILOCKS_B200_RLC_CHUNK = signatures per chunk (0 / unset: one chunk = one equation for the whole call).  With
-     * chunks a bad signature sends only its chunk to the per-signature path; the price is a smaller digit width (more additions
-     * per signature) and nch times the tail work. */
-    size_t csize = n;
-    if (const char *e = getenv("GOLDILOCKS_B200_RLC_CHUNK")) { const long v = atol(e); if (v >= (long)RLC_MIN && (size_t)v < n) csize = (size_t)v; }
-    const uint32_t nch = (uint32_t)((n + csize - 1) / csize);
-    /* everything sized by n alone first: the R decodes start before the number of distinct keys is known */
-    rlc_shape sh_r = rlc_shape_for(csize, 0, 0);
-    sh_r.nch = nch; sh_r.csize = (uint32_t)csize;
-    const uint32_t cells = rlc_scells(sh_r);
+    cudaStream_t side = c.side_stream;
+    /* shared by both passes: everything sized by n alone -- the R decodes start before the number of distinct keys is known */
     void *gs = k.alloc(group_all_scratch_bytes(n));
     uint8_t *dseed = k.out<uint8_t>(32);
-    pt *pts = k.out<pt>(2 * n + nch);                                 /* n R records, then at most n key groups, then one B per chunk */
-    int32_t *ok = k.out<int32_t>(2 * n + nch), *valid = k.out<int32_t>(n);
-    uint32_t *flags = k.out<uint32_t>(1 + (size_t)nch);               /* [0] force fallback, [1 + ch] verdict of chunk ch */
+    const uint32_t max_ch = RLC_MAX_CHUNKS;
+    pt *pts = k.out<pt>(2 * n + max_ch);                               /* n R records, then at most n key groups, then one B per chunk */
+    int32_t *ok = k.out<int32_t>(2 * n + max_ch), *valid = k.out<int32_t>(n);
+    uint32_t *flags = k.out<uint32_t>(1 + (size_t)max_ch);             /* [0] force fallback, [1 + ch] verdict of chunk ch */
     abi_sc *chal = k.out<abi_sc>(n), *resp = k.out<abi_sc>(n);
     uint32_t *z = k.out<uint32_t>(RLC_ZWORDS * n);
-    unsigned long long *s_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * cells * nch);
-    RlcClass cr, ck;
-    if (!rlc_class_alloc(k, cr, sh_r, n)) return false;
-    CU(cudaMemsetAsync(flags, 0, (1 + (size_t)nch) * sizeof(uint32_t), s));
-    CU(cudaMemsetAsync(s_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * cells * nch, s));
+    k.secret(z, RLC_ZWORDS * n);                                      /* the weights are secret until the verdict is out: wiped when the call ends */
+    if (!k.ok) return false;
     CU(cudaMemcpyAsync(dseed, seed, 32, cudaMemcpyHostToDevice, s));
-    /* Two streams.  Main: the multiplier-bound work -- the R decodes as the signatures land, later the bucket sums of the R class.
-     * Side (high priority): what needs no decoded R -- the weights and the sorted pair list of the R class (they depend on the
-     * seed alone; excluded signatures are skipped by the bucket kernel), the key grouping and the key decodes, the challenge
-     * hashes (ALU work, it shares the SMs with the decodes) -- and later the whole key class, whose kernels are short chains of
-     * dependent additions and doublings (latency-bound: up to 446 - c doublings in a row). */
-    cudaStream_t side = c.side_stream;
-    CU(cudaEventRecord(c.side_evt[0], s));
-    CU(cudaStreamWaitEvent(side, c.side_evt[0], 0)); /* whatever produced the inputs on `s`, and the seed */
-    LaneRlcZ f3 = {z, dseed, n, sh_r.zbits};
-    if (!launch(c, f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE, side)) return false;
-    if (!rlc_class_pairs(c, cr, z, RLC_ZWORDS, 0, side, nullptr)) return false;
-    const size_t s0 = feed ? feed->split[0] : n, s1 = feed ? feed->split[1] : n;
-    const size_t lo[3] = {0, s0, s1}, hi[3] = {s0, s1, n};
-    const rlc_groups no_groups = {nullptr, nullptr, nullptr, 0};
-    for (int h = 0; h < 3; h++) {
-        if (feed) CU(cudaStreamWaitEvent(s, h == 0 ? feed->sig0 : h == 1 ? feed->sig1 : feed->rest, 0));
-        if (hi[h] == lo[h]) continue;
-        LaneRlcDecode f1 = {pts, ok, flags, dsig, dpk, n, no_groups, lo[h]}; /* lanes below n never look at the groups */
-        if (!launch(c, f1, hi[h] - lo[h], s)) return false;
-    }
-    if (feed) CU(cudaStreamWaitEvent(side, feed->keys, 0));
-    key_groups kg;
-    uint64_t launched = 0;
-    cudaError_t e = group_keys_all(dpk, n, gs, &kg, side, &launched, nch > 1 ? (uint32_t)csize : 0u);
-    if (e != cudaSuccess) return fail("group_keys_all", e);
-    g_launches += launched;
-    uint32_t m = 0;
-    CU(cudaMemcpyAsync(&m, kg.ngroups, sizeof m, cudaMemcpyDeviceToHost, side));
-    CU(cudaStreamSynchronize(side)); /* the number of key groups sizes the key class; the R decodes are already queued */
-    if (m == 0 || m > n) { g_err = "rlc: key grouping returned an impossible group count"; return false; }
-    const rlc_groups g = {kg.order, kg.gid, kg.gstart, m};
-    const size_t nkey = (size_t)m + nch;                                 /* key groups, then the B of every chunk */
-    rlc_shape sh_k = rlc_shape_for((nkey + nch - 1) / nch, 0, 1);
-    sh_k.nch = nch; sh_k.csize = (uint32_t)csize;
-    unsigned long long *key_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * m);
-    uint32_t *kscal = k.out<uint32_t>(SC_WORDS * nkey), *kchunk = k.out<uint32_t>(nkey);
-    if (!rlc_class_alloc(k, ck, sh_k, nkey)) return false;
-    CU(cudaMemsetAsync(key_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * m, side));
-    e = key_chunks(kchunk, &kg, m, nch, nch > 1 ? (uint32_t)csize : 0u, side);
-    if (e != cudaSuccess) return fail("key_chunks", e);
-    g_launches++;
-    LaneRlcDecode fk = {pts, ok, flags, dsig, dpk, n, g, n};
-    if (!launch(c, fk, nkey, side)) return false;
-    if (feed) CU(cudaStreamWaitEvent(side, feed->rest, 0));
-    LaneEdVerifyScalars f2 = {chal, resp, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, 0};
-    if (!launch(c, f2, n, side)) return false;
-    CU(cudaEventRecord(c.side_evt[1], side));
-    CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));
-    LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g, sh_r};
-    if (!launch(c, f4, n, s)) return false;
-    LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m, cells};
-    if (!launch(c, f5, nkey, s)) return false;
-    CU(cudaEventRecord(c.side_evt[2], s));
-    CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));
-    if (!rlc_class_pairs(c, ck, kscal, SC_WORDS, n, side, kchunk)) return false;
-    CU(cudaEventRecord(c.side_evt[4], side));
-    if (!rlc_class_sum(c, ck, pts, side, false, nullptr)) return false;
-    CU(cudaEventRecord(c.side_evt[3], side));
-    CU(cudaStreamWaitEvent(s, c.side_evt[4], 0)); /* the radix sort of the key class wants the whole machine for its 0.3 ms: the R buckets wait for it */
-    if (!rlc_class_sum(c, cr, pts, s, true, valid)) return false;
-    CU(cudaStreamWaitEvent(s, c.side_evt[3], 0));
-    LaneRlcVerdict f11 = {flags + 1, cr.total, ck.total, flags};
-    if (!launch(c, f11, nch, s)) return false;
-    std::vector<uint32_t> hflags(1 + (size_t)nch, 0);
-    CU(cudaMemcpyAsync(hflags.data(), flags, hflags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    CU(cudaMemsetAsync(z, 0, sizeof(uint32_t) * RLC_ZWORDS * n, s)); /* the weights are secret until the verdict is out; wipe them */
-    size_t failed = 0;
-    for (uint32_t ch = 0; ch < nch; ch++) failed += hflags[1 + ch] ? 0 : 1;
-    if (failed == 0) {
+    std::vector<uint32_t> hflags;
+    uint32_t zbits = 0;
+    /* one pass of equations over chunks of `csize` consecutive signatures (csize = n: the one whole-batch equation).  Everything that
+     * depends on the chunking is built here: the key groups (a key that occurs in two chunks is two groups) and their decodes, the
+     * per-group scalar sums, both sorted pair lists, the bucket sums, one verdict per chunk. */
+    auto equations = [&](size_t csize, bool first) -> bool {
+        const uint32_t nch = (uint32_t)((n + csize - 1) / csize);
+        auto log2_floor = [](size_t v) { int l = 0; while (((size_t)2 << l) <= v) l++; return l; };
+        /* digit widths of a chunked pass: with many chunks the lanes are plentiful, so the widths minimise additions (bucket
+         * accumulation + folding = count + 2 * 2^c per window) instead of filling one wave: ~16 points per R bucket, ~8 per key bucket */
+        rlc_shape sh_r = rlc_shape_for(csize, nch > 1 ? std::max(2, std::min((int)RLC_MAX_C, log2_floor(csize) - 4)) : 0, 0);
+        sh_r.nch = nch; sh_r.csize = (uint32_t)csize;
+        if (first) zbits = sh_r.zbits;
+        else sh_r.wn = (zbits + sh_r.c - 1) / sh_r.c;        /* the weights were drawn for the first pass: the digits must cover all of their bits */
+        const uint32_t cells = rlc_scells(sh_r);
+        unsigned long long *s_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * cells * nch);
+        RlcClass cr, ck;
+        if (!rlc_class_alloc(k, cr, sh_r, n)) return false;
+        CU(cudaMemsetAsync(flags, 0, (1 + (size_t)nch) * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(s_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * cells * nch, s));
+        /* Two streams.  Main: the multiplier-bound work -- the R decodes as the signatures land, later the bucket sums of the R class.
+         * Side (high priority): what needs no decoded R -- the weights and the sorted pair list of the R class (they depend on the
+         * seed alone; excluded signatures are skipped by the bucket kernel), the key grouping and the key decodes, the challenge
+         * hashes (ALU work, it shares the SMs with the decodes) -- and later the whole key class, whose kernels are short chains of
+         * dependent additions and doublings (latency-bound: up to 446 - c doublings in a row). */
+        CU(cudaEventRecord(c.side_evt[0], s));
+        CU(cudaStreamWaitEvent(side, c.side_evt[0], 0)); /* whatever produced the inputs on `s`, and the seed */
+        if (first) {
+            LaneRlcZ f3 = {z, dseed, n, sh_r.zbits};         /* zbits = 9 x 15 = 135 for the whole-batch shape: enough for any later digit width */
+            if (!launch(c, f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE, side)) return false;
+        }
+        if (!rlc_class_pairs(c, cr, z, RLC_ZWORDS, 0, side, nullptr)) return false;
+        if (first) {
+            const size_t s0 = feed ? feed->split[0] : n, s1 = feed ? feed->split[1] : n;
+            const size_t lo[3] = {0, s0, s1}, hi[3] = {s0, s1, n};
+            const rlc_groups no_groups = {nullptr, nullptr, nullptr, 0};
+            for (int h = 0; h < 3; h++) {
+                if (feed) CU(cudaStreamWaitEvent(s, h == 0 ? feed->sig0 : h == 1 ? feed->sig1 : feed->rest, 0));
+                if (hi[h] == lo[h]) continue;
+                LaneRlcDecode f1 = {pts, ok, flags, dsig, dpk, n, no_groups, lo[h]}; /* lanes below n never look at the groups */
+                if (!launch(c, f1, hi[h] - lo[h], s)) return false;
+            }
+            if (feed) CU(cudaStreamWaitEvent(side, feed->keys, 0));
+        }
+        key_groups kg;
+        uint64_t launched = 0;
+        cudaError_t e = group_keys_all(dpk, n, gs, &kg, side, &launched, nch > 1 ? (uint32_t)csize : 0u);
+        if (e != cudaSuccess) return fail("group_keys_all", e);
+        g_launches += launched;
+        uint32_t m = 0;
+        CU(cudaMemcpyAsync(&m, kg.ngroups, sizeof m, cudaMemcpyDeviceToHost, side));
+        CU(cudaStreamSynchronize(side)); /* the number of key groups sizes the key class; the R decodes are already queued */
+        if (m == 0 || m > n) { g_err = "rlc: key grouping returned an impossible group count"; return false; }
+        const rlc_groups g = {kg.order, kg.gid, kg.gstart, m};
+        const size_t nkey = (size_t)m + nch;                                 /* key groups, then the B of every chunk */
+        rlc_shape sh_k = rlc_shape_for((nkey + nch - 1) / nch, nch > 1 ? std::max(2, std::min((int)RLC_MAX_C, log2_floor((nkey + nch - 1) / nch) - 3)) : 0, 1);
+        sh_k.nch = nch; sh_k.csize = (uint32_t)csize;
+        unsigned long long *key_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * m);
+        uint32_t *kscal = k.out<uint32_t>(SC_WORDS * nkey), *kchunk = k.out<uint32_t>(nkey);
+        if (!rlc_class_alloc(k, ck, sh_k, nkey)) return false;
+        CU(cudaMemsetAsync(key_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * m, side));
+        e = key_chunks(kchunk, &kg, m, nch, nch > 1 ? (uint32_t)csize : 0u, side);
+        if (e != cudaSuccess) return fail("key_chunks", e);
+        g_launches++;
+        LaneRlcDecode fk = {pts, ok, flags, dsig, dpk, n, g, n};
+        if (!launch(c, fk, nkey, side)) return false;
+        if (first) {
+            if (feed) CU(cudaStreamWaitEvent(side, feed->rest, 0));
+            LaneEdVerifyScalars f2 = {chal, resp, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, 0};
+            if (!launch(c, f2, n, side)) return false;
+        }
+        CU(cudaEventRecord(c.side_evt[1], side));
+        CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));
+        LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g, sh_r};
+        if (!launch(c, f4, n, s)) return false;
+        LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m, cells};
+        if (!launch(c, f5, nkey, s)) return false;
+        CU(cudaEventRecord(c.side_evt[2], s));
+        CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));
+        if (!rlc_class_pairs(c, ck, kscal, SC_WORDS, n, side, kchunk)) return false;
+        CU(cudaEventRecord(c.side_evt[4], side));
+        if (!rlc_class_sum(c, ck, pts, side, false, nullptr)) return false;
+        CU(cudaEventRecord(c.side_evt[3], side));
+        CU(cudaStreamWaitEvent(s, c.side_evt[4], 0)); /* the radix sort of the key class wants the whole machine for its 0.3 ms: the R buckets wait for it */
+        if (!rlc_class_sum(c, cr, pts, s, true, valid)) return false;
+        CU(cudaStreamWaitEvent(s, c.side_evt[3], 0));
+        LaneRlcVerdict f11 = {flags + 1, cr.total, ck.total, flags};
+        if (!launch(c, f11, nch, s)) return false;
+        hflags.assign(1 + (size_t)nch, 0);
+        CU(cudaMemcpyAsync(hflags.data(), flags, hflags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        return true;
+    };
+    if (!equations(n, true)) return false;
+    if (hflags[1]) {
         *fast = 1;
         CU(cudaMemcpyAsync(dst, valid, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
         return true;
     }
-    if (nch == 1 || failed * 4 > nch) return ordinary(); /* more than a quarter of the chunks: one pass over everything is cheaper */
-    /* chunks whose equation held take their statuses from `valid`; the others go through the per-signature path, one by one */
-    CU(cudaMemcpyAsync(dst, valid, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));
-    VerifyGrids grids;
-    if (!verify_grids(c, &grids)) return false;
-    const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
-    uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
-    void *scratch = k.alloc(goldilocks_b200_verify_scratch_bytes(csize));
-    if (!k.ok) return false;
-    for (uint32_t ch = 0; ch < nch; ch++) {
-        if (hflags[1 + ch]) continue;
-        const size_t clo = (size_t)ch * csize, chi = clo + csize < n ? clo + csize : n;
-        if (!verify_dev(c, dst + clo, dsig + 114 * clo, dpk + 57 * clo, dmsg, doff + clo, prehashed, dctx, ctx_len, chi - clo, scratch, slots, grids, s)) return false;
+    /* the whole-batch equation failed: localise.  Chunk size from the batch (about RLC_CHUNK_TARGET signatures, at most RLC_MAX_CHUNKS chunks). */
+    size_t csize = RLC_CHUNK_TARGET;
+    if (const char *e = getenv("GOLDILOCKS_B200_RLC_CHUNK")) { const long v = atol(e); if (v >= (long)RLC_MIN) csize = (size_t)v; }
+    if ((n + csize - 1) / csize > RLC_MAX_CHUNKS) csize = (n + RLC_MAX_CHUNKS - 1) / RLC_MAX_CHUNKS;
+    const uint32_t nch = (uint32_t)((n + csize - 1) / csize);
+    if (hflags[0] || nch < 4 || csize < RLC_MIN) return ordinary();      /* a decoded Z = 0 (never for a curve point), or nothing to localise */
+    if (!equations(csize, false)) return false;
+    std::vector<uint32_t> failed;
+    for (uint32_t ch = 0; ch < nch; ch++) if (!hflags[1 + ch]) failed.push_back(ch);
+    if (hflags[0] || failed.size() * 2 > nch) {                        /* most chunks bad: one pass over everything is cheaper, and stop trying for a while */
+        { const unsigned rp = g_rlc_reprobe.load(); c.rlc_skip = rp ? rp - 1 : 0; }
+        return ordinary();
     }
-    return true;
+    *fast = 2;
+    CU(cudaMemcpyAsync(dst, valid, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));  /* chunks whose equation held: decided */
+    if (failed.empty()) return true;                                   /* (cannot happen unless the first equation failed on its own) */
+    size_t np = 0;
+    for (uint32_t ch : failed) np += ((size_t)ch * csize + csize <= n) ? csize : n - (size_t)ch * csize;
+    size_t total = 0;
+    CU(cudaMemcpyAsync(&total, doff + n, sizeof(size_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    uint32_t *fc = k.out<uint32_t>(failed.size());
+    size_t *mbase = k.out<size_t>(failed.size() + 1), *poff = k.out<size_t>(np + 1);
+    uint8_t *psig = k.out<uint8_t>(114 * np), *ppk = k.out<uint8_t>(57 * np), *pmsg = k.out<uint8_t>(total);
+    uint32_t *src = k.out<uint32_t>(np);
+    int32_t *pst = k.out<int32_t>(np);
+    if (!k.ok) return false;
+    CU(cudaMemcpyAsync(fc, failed.data(), failed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    LaneRlcPackPlan fp = {mbase, fc, (uint32_t)failed.size(), doff, n, (uint32_t)csize};
+    if (!launch(c, fp, 1, s)) return false;
+    LaneRlcPack fq = {psig, ppk, pmsg, poff, src, dsig, dpk, dmsg, doff, mbase, fc, (uint32_t)failed.size(), np, (uint32_t)csize};
+    if (!launch(c, fq, np + 1, s)) return false;
+    CU(cudaStreamSynchronize(s));                                      /* `failed` (host vector) must outlive its copy */
+    if (!ordinary_on(pst, psig, ppk, pmsg, poff, np)) return false;
+    LaneRlcUnpack fu = {dst, pst, src};
+    return launch(c, fu, np, s);
+}
+void goldilocks_b200_rlc_policy(unsigned reprobe) {
+    g_rlc_reprobe.store(reprobe);
+    for (int d = 0; d < MAX_DEV; d++)
+        for (int l = 0; l < shard::LANES; l++) { std::lock_guard<std::mutex> g(g_ctx[d][l].mu); g_ctx[d][l].rlc_skip = 0; }
 }
 goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status, const uint8_t *signature, const uint8_t *pubkey, const uint8_t *msg, const size_t *msg_off,
                                                      uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n, int *fast_path) {

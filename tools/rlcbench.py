@@ -22,9 +22,11 @@ def main():
     ap.add_argument("--per-key", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--timeline", action="store_true")
+    ap.add_argument("--bad", type=int, default=0, help="corrupt this many signatures (spread evenly) before the timeline run: shows the localisation pass")
     a = ap.parse_args()
     lib = g.load()
     n = a.n
+    lib.rlc_policy(0)
     sig, pk, arena, off, expect = bench.make_corpus(lib, n, "rlcbench", per=a.per_key, corrupt=False)
     pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
     h_sig, h_pk, h_msg, h_off = pin(sig.reshape(-1)), pin(pk.reshape(-1)), pin(arena), pin(off.view(np.int64))
@@ -57,6 +59,12 @@ def main():
         print("  %-22s %s ms" % (nm, " + ".join("%.3f" % (sum(v[j::per]) / a.reps) for j in range(per))))
     print("  sum of kernels %.2f ms" % (sum(sum(v) for v in k.values()) / a.reps))
     if a.timeline:
+        if a.bad:
+            idx = np.arange(n // (2 * a.bad), n, n // a.bad)[: a.bad]
+            sig2 = sig.copy(); sig2[idx, 70] ^= 1
+            h_sig.copy_(torch.from_numpy(sig2.reshape(-1)))
+            assert fr(*argr) == -1       # warm-up of the localisation pass (grows the arena)
+            print("with %d bad signatures: fast_path = %d, rejected = %d" % (a.bad, fast.value, int((h_st.numpy() == 0).sum())))
         lib.lib.goldilocks_b200_profile(C.c_int(1))
         t0 = time.perf_counter()
         assert fr(*argr) == -1

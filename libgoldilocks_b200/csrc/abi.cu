@@ -45,6 +45,11 @@ struct Ctx {
     cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t side_stream = nullptr;   // the latency-bound doubling chain of the key class (rlc.cuh) runs here beside the R-class buckets
     cudaEvent_t side_evt[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    /* the same fork / join for the device-pointer verification (caller's stream, context lock NOT held while kernels run): its own side
+     * stream and events, and a lock that covers only the enqueue, so that two threads cannot interleave record / wait pairs */
+    cudaStream_t dev_side = nullptr;
+    cudaEvent_t dev_evt[2] = {nullptr, nullptr};
+    std::mutex dev_side_mu;
     fixed_tables *ft = nullptr;
     niels *wide = nullptr;       // WIDE_TABLES x 16384-entry verification tables: odd multiples of 2^(45c) B (30 MB, L2 resident)
     std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
@@ -198,6 +203,8 @@ bool ctx_init(Ctx &c, int dev, int lane = 0) {
         CU(cudaStreamCreateWithPriority(&c.side_stream, cudaStreamNonBlocking, prio_hi));
     }
     for (auto &e : c.side_evt) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&c.dev_side, cudaStreamNonBlocking));
+    for (auto &e : c.dev_evt) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaMalloc(&c.work_counter, 256));
     if (lane > 0) {
         c.ft = g_ctx[dev][0].ft;
@@ -225,6 +232,13 @@ bool ctx_init(Ctx &c, int dev, int lane = 0) {
     return true;
 }
 
+// Context lane of the calling thread: workers are bound to theirs; caller threads are dealt the lanes round-robin on their first
+// call, so up to shard::LANES host threads run host-pointer calls on one GPU side by side instead of queueing on one lock.
+std::atomic<unsigned> g_next_lane{0};
+int my_lane() {
+    if (shard::t_lane < 0) shard::t_lane = (int)(g_next_lane.fetch_add(1) % shard::LANES);
+    return shard::t_lane;
+}
 // One API call: locks the device context, carves device buffers from the arena, copies, launches.
 struct Call {
     Ctx *c = nullptr;
@@ -235,9 +249,9 @@ struct Call {
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) { fail("cudaGetDevice (is there a GPU?)", e); return; }
         if (dev >= MAX_DEV) { g_err = "device index too large"; return; }
-        c = &g_ctx[dev][shard::t_lane];
+        c = &g_ctx[dev][my_lane()];
         lk = std::unique_lock<std::mutex>(c->mu);
-        ok = ctx_init(*c, dev, shard::t_lane);
+        ok = ctx_init(*c, dev, my_lane());
         if (ok && !c->blocks.empty()) c->used = 0;
     }
     /* device copies of secrets (private keys, scalars, nonces, window tables of the secret paths): zeroed by finish() on
@@ -416,16 +430,16 @@ struct SubOffsets {
 Ctx *dev_ctx() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEV) { g_err = "no CUDA device"; return nullptr; }
-    Ctx &c = g_ctx[dev][shard::t_lane];
+    Ctx &c = g_ctx[dev][my_lane()];
     std::lock_guard<std::mutex> g(c.mu);
-    return ctx_init(c, dev, shard::t_lane) ? &c : nullptr;
+    return ctx_init(c, dev, my_lane()) ? &c : nullptr;
 }
 
 }  // namespace
 
 namespace shard {
 thread_local bool t_worker = false;
-thread_local int t_lane = 0;
+thread_local int t_lane = -1;     /* caller threads pick a context lane on their first call (my_lane) */
 const std::string &worker_error() { return g_err; }
 std::shared_ptr<Pool> current() { std::lock_guard<std::mutex> g(g_pool_mu); return g_pool; }
 }  // namespace shard
@@ -960,7 +974,7 @@ size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
 struct VerifyFeed { size_t split; cudaEvent_t ready[2]; };
 static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off, uint8_t prehashed,
                        const uint8_t *ctx, uint8_t ctx_len, size_t n, void *scratch, uint4 *slots, const VerifyGrids &grids, cudaStream_t s,
-                       const VerifyFeed *feed = nullptr) {
+                       const VerifyFeed *feed = nullptr, cudaStream_t side = nullptr, cudaEvent_t *side_evt = nullptr) {
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     char *p = (char *)scratch;
     abi_pt *pts = (abi_pt *)p; p += al(2 * n * sizeof(abi_pt));
@@ -994,6 +1008,32 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
         if (!launch(c, fa, n, s)) return false;
     }
     const size_t split = feed ? feed->split : n;
+    if (plan.unique_sig && side) {
+        /* The key tables need the decoded keys only; the challenge hashes need the signatures and messages only.  The table kernel is
+         * a multiplier-bound chain on less than one wave of lanes (one lane per distinct key), the hashes are ALU work: the hashes go
+         * to the side stream and fill the issue slots the table kernel leaves (verify_dev's caller owns `side` for the call). */
+        CU(cudaEventRecord(side_evt[0], s));
+        CU(cudaStreamWaitEvent(side, side_evt[0], 0));
+        if (feed) CU(cudaStreamWaitEvent(side, feed->ready[0], 0));
+        {
+            LaneEdVerifyScalars f = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len, 0};
+            if (!launch(c, f, split, side)) return false;
+        }
+        if (feed) CU(cudaStreamWaitEvent(side, feed->ready[1], 0));
+        if (split < n) {
+            LaneEdVerifyScalars f = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len, split};
+            if (!launch(c, f, n - split, side)) return false;
+        }
+        CU(cudaEventRecord(side_evt[1], side));
+        SlotKeyTables ft = {pts, ktabs, plan};
+        if (!launch_smp(c, ft, cap, grids.tables, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3], counts[4] = 0, left by the grouping pass */
+        CU(cudaStreamWaitEvent(s, side_evt[1], 0));
+        if (feed) { CU(cudaStreamWaitEvent(s, feed->ready[0], 0)); CU(cudaStreamWaitEvent(s, feed->ready[1], 0)); } /* the finish kernel reads the signature bytes too */
+        SlotEdVerifyFinishShared fs = {pts, ok, chal, resp, c.wide, ktabs, slots, plan, sig};
+        if (!launch_smp(c, fs, n, grids.shared, s, const_cast<uint32_t *>(plan.counts) + 3)) return false;
+        LaneVerifySign fv = {status, (verify_aux *)(pts + 1), 2, n};    /* aux record of signature i = the R half of pts[2i..2i+1] */
+        return launch(c, fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH, s);
+    }
     if (feed) CU(cudaStreamWaitEvent(s, feed->ready[0], 0));
     if (!decode_range(0, split) || !scalars_range(0, split)) return false;
     if (feed) CU(cudaStreamWaitEvent(s, feed->ready[1], 0));
@@ -1039,7 +1079,7 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
             if (cudaEventRecord(feed.ready[h], k.c->copy_stream) != cudaSuccess) k.ok = false;
         }
     }
-    if (k.ok) k.ok = verify_dev(*k.c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, scratch, slots, grids, k.c->stream, &feed);
+    if (k.ok) k.ok = verify_dev(*k.c, dst, dsig, dpk, dmsg, doff, prehashed, dctx, context_len, n, scratch, slots, grids, k.c->stream, &feed, k.c->side_stream, k.c->side_evt);
     k.fetch((int32_t *)status, dst, n);
     if (!k.ok && k.c) cudaStreamSynchronize(k.c->copy_stream); /* never leave copies in flight behind an error */
     return k.finish();
@@ -1255,10 +1295,12 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     if (!equations(csize, false)) return false;
     std::vector<uint32_t> failed;
     for (uint32_t ch = 0; ch < nch; ch++) if (!hflags[1 + ch]) failed.push_back(ch);
-    if (hflags[0] || failed.size() * 2 > nch) {                        /* most chunks bad: one pass over everything is cheaper, and stop trying for a while */
-        { const unsigned rp = g_rlc_reprobe.load(); c.rlc_skip = rp ? rp - 1 : 0; }
-        return ordinary();
-    }
+    /* Both passes are spent by now; what is left to decide is how to finish THIS call and whether to try again on the NEXT ones.  The
+     * packed per-signature pass over a fraction f of the batch costs about f of the ordinary call, so it wins up to f ~ 0.9.  But a call
+     * that had to run both passes plus a fallback over more than a fifth of the batch was slower than the ordinary path would have been
+     * (two passes ~ 2/3 of an ordinary call): traffic like that should skip the equation for a while. */
+    if (failed.size() * 5 > nch) { const unsigned rp = g_rlc_reprobe.load(); c.rlc_skip = rp ? rp - 1 : 0; }
+    if (hflags[0] || failed.size() * 10 > (size_t)nch * 9) return ordinary();
     *fast = 2;
     CU(cudaMemcpyAsync(dst, valid, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, s));  /* chunks whose equation held: decided */
     if (failed.empty()) return true;                                   /* (cannot happen unless the first equation failed on its own) */
@@ -1303,6 +1345,18 @@ goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilocks_error_t *status,
         });
         if (fast_path) *fast_path = slow.load() == 0 ? 1 : 0;
         return r;
+    }
+    {   /* recent calls on this context failed most of their chunks: this one goes straight to the ordinary entry point (rlc_core explains) */
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev < MAX_DEV) {
+            Ctx &cx = g_ctx[dev][my_lane()];
+            bool skip = false;
+            { std::lock_guard<std::mutex> g(cx.mu); if (cx.rlc_skip > 0) { cx.rlc_skip--; skip = true; } }
+            if (skip) {
+                if (fast_path) *fast_path = 0;
+                return goldilocks_ed448_verify_batch(status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n);
+            }
+        }
     }
     Call k;
     int fast = 0;
@@ -1430,8 +1484,9 @@ goldilocks_error_t goldilocks_ed448_verify_batch_dev(goldilocks_error_t *status,
     /* nothing of the context is written while the kernels run: window tables, work lists and hand-out counters all live in
      * the caller's scratch, so calls on different streams (and host-pointer calls of other threads) do not interfere */
     uint4 *slots = (uint4 *)((char *)scratch + verify_core_scratch_bytes(n));
-    return verify_dev(*c, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, scratch, slots, grids, as_stream(stream))
-               ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
+    std::lock_guard<std::mutex> g(c->dev_side_mu); /* held while the launches are queued, not while they run */
+    return verify_dev(*c, (int32_t *)status, signature, pubkey, msg, msg_off, prehashed, context, context_len, n, scratch, slots, grids, as_stream(stream), nullptr,
+                      c->dev_side, c->dev_evt) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
 }
 goldilocks_error_t goldilocks_x448_batch_dev(uint8_t *out, goldilocks_error_t *status, const uint8_t *base, const uint8_t *scalar, size_t n, void *stream) {
     Ctx *c = dev_ctx();

@@ -69,7 +69,7 @@ def imad_peak(device_index, measure=True):
         except Exception as e:  # noqa: BLE001
             why = "tools/imad_peak failed (%s)" % type(e).__name__
     else:
-        why = "tools/imad_peak not built"
+        why = "tools/imad_peak not built" if measure else "measurement skipped (--no-peak, or not rank 0)"
     try:
         with open(os.path.join(ROOT, "profiles", "r01_imad_peak.json")) as f:
             j = json.load(f)

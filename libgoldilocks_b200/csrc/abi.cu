@@ -1003,16 +1003,18 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
         LaneEdVerifyScalars f = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len, lo};
         return launch(c, f, hi - lo, s);
     };
+    const size_t split = feed ? feed->split : n;
+    if (plan.unique_sig && side) {
+        CU(cudaEventRecord(side_evt[0], s));            /* fork here: the hashes also run beside the per-key decodes (one inverse square root chain per key) */
+    }
     if (plan.unique_sig) { /* one decode per distinct key: needs the keys only, so it runs while the signatures still cross PCIe */
         LaneEdVerifyDecode fa = {pts, ok, sig, pk, n, plan, n};
         if (!launch(c, fa, n, s)) return false;
     }
-    const size_t split = feed ? feed->split : n;
     if (plan.unique_sig && side) {
         /* The key tables need the decoded keys only; the challenge hashes need the signatures and messages only.  The table kernel is
          * a multiplier-bound chain on less than one wave of lanes (one lane per distinct key), the hashes are ALU work: the hashes go
          * to the side stream and fill the issue slots the table kernel leaves (verify_dev's caller owns `side` for the call). */
-        CU(cudaEventRecord(side_evt[0], s));
         CU(cudaStreamWaitEvent(side, side_evt[0], 0));
         if (feed) CU(cudaStreamWaitEvent(side, feed->ready[0], 0));
         {

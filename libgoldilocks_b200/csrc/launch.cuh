@@ -12,6 +12,21 @@
 
 // Resident blocks per SM the register allocator is asked to allow (default: whatever fits).
 template <class F> struct lane_min_blocks { static constexpr int value = 1; };
+/* The one-inverse-square-root kernels run the by-value multiplier and want ~186 registers, i.e. two blocks = two warps per scheduler.
+ * Capping the registers for three / four resident blocks costs 64-600 bytes of spills outside the squaring loop and wins 2-3.5 %
+ * (B200, 2^20: RLC call 17.96 -> 17.43 ms with 3, 17.56 with 4; decaf decode 8.24 -> 8.07 / 7.95 ms, encode 8.12 -> 7.87 / 7.89,
+ * Elligator 8.29 -> 8.13 / 8.05; tools/gpu_variants_decode.sh). */
+#ifndef DECODE_MIN_BLOCKS
+#define DECODE_MIN_BLOCKS 3
+#endif
+#ifndef CODEC_MIN_BLOCKS
+#define CODEC_MIN_BLOCKS 4
+#endif
+template <> struct lane_min_blocks<LaneRlcDecode> { static constexpr int value = DECODE_MIN_BLOCKS; };
+template <> struct lane_min_blocks<LaneEdVerifyDecode> { static constexpr int value = DECODE_MIN_BLOCKS; };
+template <> struct lane_min_blocks<LanePtDecode> { static constexpr int value = CODEC_MIN_BLOCKS; };
+template <> struct lane_min_blocks<LanePtEncode> { static constexpr int value = CODEC_MIN_BLOCKS; };
+template <> struct lane_min_blocks<LaneFromHash<false>> { static constexpr int value = CODEC_MIN_BLOCKS; };
 
 template <class F>
 __global__ void __launch_bounds__(BLOCK, lane_min_blocks<F>::value) k_lanes(F f, size_t n) {

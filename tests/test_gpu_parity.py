@@ -434,6 +434,53 @@ def test_secret_paths_time_independent_of_the_scalar(gpu, chk):
             json.dump(report, f, indent=1)
 
 
+def test_concurrent_host_threads(gpu, chk):
+    """host threads that call at the same time are dealt the three contexts of a device round-robin (abi.cu my_lane): six threads, each
+    looping over a different mix of entry points (verify, X448, sign, codec, comb), must all get the single-threaded answers -- with and
+    without a device set installed underneath them"""
+    import threading
+    n = 3000
+    sig, pk, msgs, kinds = util.verify_corpus(chk, "thr/v", n)
+    u = stream_bytes("thr/u", n * 56).reshape(n, 56); k = stream_bytes("thr/k", n * 56).reshape(n, 56)
+    sk = stream_bytes("thr/sk", n * 57).reshape(n, 57)
+    h = stream_bytes("thr/h", 20000 * 56).reshape(20000, 56)
+    sc = util.random_scalars(chk, "thr/s", n)
+    want = {"verify": gpu.ed448_verify(sig, pk, msgs), "x448": gpu.x448(u, k)[0], "pk": gpu.ed448_derive_public_key(sk),
+            "enc": gpu.point_encode(gpu.from_hash_nonuniform(h)), "comb": gpu.point_encode(gpu.precomputed_scalarmul(sc))}
+    want["sign"] = gpu.ed448_sign(sk, want["pk"], msgs)
+    parity.eq(want["verify"], chk.ed448_verify(sig, pk, msgs), "single-threaded verify vs reference")
+    errors = []
+
+    def worker(t):
+        try:
+            for it in range(4):
+                which = (t + it) % 5
+                if which == 0:
+                    parity.eq(gpu.ed448_verify(sig, pk, msgs), want["verify"], "thread %d verify" % t)
+                elif which == 1:
+                    parity.eq(gpu.x448(u, k)[0], want["x448"], "thread %d x448" % t)
+                elif which == 2:
+                    parity.eq(gpu.ed448_sign(sk, want["pk"], msgs), want["sign"], "thread %d sign" % t)
+                elif which == 3:
+                    parity.eq(gpu.point_encode(gpu.from_hash_nonuniform(h)), want["enc"], "thread %d elligator + encode" % t)
+                else:
+                    parity.eq(gpu.point_encode(gpu.precomputed_scalarmul(sc)), want["comb"], "thread %d comb" % t)
+        except Exception as e:  # noqa: BLE001
+            errors.append("thread %d: %r" % (t, e))
+
+    for devs in ([], [0, 0]):
+        gpu.set_devices(devs)
+        try:
+            threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+        finally:
+            gpu.set_devices([])
+        assert not errors, errors
+
+
 def test_device_set_sharded_equals_unsharded(gpu, chk):
     """goldilocks_b200_set_devices: ONE host-pointer batch cut into contiguous ranges over the device set (csrc/shard.h) gives
     the bytes of the unsharded call for every kind of entry point -- heavy (one range per device: verify incl. key groups

@@ -333,6 +333,11 @@ GOLDILOCKS_B200_API size_t goldilocks_b200_profile_read(char *names, float *ms, 
 /* the same log as a timeline: begin and end of launch k in ms after the begin of the first logged launch (kernels of one
  * call may run on two streams: goldilocks_ed448_verify_rlc_batch) */
 GOLDILOCKS_B200_API size_t goldilocks_b200_profile_timeline(char *names, float *start_ms, float *end_ms, size_t max);
+/* Test entry point (no counterpart in the reference's API: goldilocks.c:271-380 keeps these static).  One mixed addition or conversion
+ * per element, all four coordinates returned: op 0 pniels_to_pt(pt_to_pniels(q)); 1 / 2 p +/- pniels(q) and 3 / 4 p +/- comb[which % 80]
+ * through the by-value code of the lane kernels; 5 niels_to_pt(comb[which % 80]); 6 / 7 and 8 / 9 the same additions through the
+ * slot-machine code of the scalar-multiplication kernels.  comb = the base-point comb table (goldilocks_b200_export_comb_table). */
+GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_debug_niels_batch(goldilocks_448_point_s *out, const goldilocks_448_point_s *p, const goldilocks_448_point_s *q, const uint32_t *which, uint32_t op, size_t n);
 /* Copies the device-built fixed-base comb table (80 niels x 3 gf, canonical radix-2^56 limbs =
  * 15360 bytes, the layout of the reference's goldilocks_448_precomputed_base) to `out`. */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_export_comb_table(uint8_t out[15360]);

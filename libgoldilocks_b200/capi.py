@@ -375,6 +375,13 @@ class BatchLib:
         assert k <= cap
         return [(lo[i], hi[i], slot[i], lane[i]) for i in range(k)]
 
+    def debug_niels(self, p, q, which, op):
+        """goldilocks_b200_debug_niels_batch: one mixed addition / conversion of goldilocks.c:271-380 per element -> (n,256) points"""
+        p, q = _u8(p, 256), _u8(q, 256); which = np.ascontiguousarray(which, np.uint32)
+        out = np.empty_like(p)
+        self._call("goldilocks_b200_debug_niels_batch", out, p, q, which, C.c_uint32(op), _Z(len(p)))
+        return out
+
     # ---- tables ----
     def export_comb_table(self):
         out = np.empty(15360, np.uint8)

@@ -740,6 +740,28 @@ goldilocks_error_t goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(
     return k.finish();
 }
 
+/* test entry point: one mixed addition / conversion of goldilocks.c:271-380 per element (slot_lanes.cuh LanePtNiels, SlotNielsDebug) */
+goldilocks_error_t goldilocks_b200_debug_niels_batch(hpt *out, const hpt *p, const hpt *q, const uint32_t *which, uint32_t op, size_t n) {
+    if (op > 9) { g_err = "goldilocks_b200_debug_niels_batch: op must be 0..9"; return GOLDILOCKS_FAILURE; }
+    Call k;
+    abi_pt *dout = k.out<abi_pt>(n);
+    const abi_pt *dp = k.in(P(p), n), *dq = k.in(P(q), n);
+    const uint32_t *dw = k.in(which, n);
+    pt *recs = k.out<pt>(n);
+    const niels *comb = k.ok ? k.c->ft->comb : nullptr;
+    if (op < 6) {
+        LanePtNiels f = {dout, recs, dp, dq, comb, dw, op};
+        k.run(f, n);
+    } else {
+        LanePtNiels f0 = {dout, recs, dp, dq, comb, dw, 10};
+        k.run(f0, n);
+        SlotNielsDebug f = {dout, dp, recs, comb, dw, op};
+        k.run_sm(f, n);
+    }
+    k.fetch(P(out), dout, n);
+    return k.finish();
+}
+
 // ---- scalar multiplications ------------------------------------------------------------------------------
 goldilocks_error_t goldilocks_448_precomputed_scalarmul_batch(hpt *out, const goldilocks_448_precomputed_s *base, const hsc *scalar, size_t n) {
     SHARD_LIGHT(n, 312, goldilocks_448_precomputed_scalarmul_batch(out + lo, base, scalar + lo, m))

@@ -3,3 +3,4 @@
 INSTANTIATE_SM(SlotComb)
 INSTANTIATE_SM(SlotX448DerivePk)
 INSTANTIATE_SM(SlotCombTable)
+INSTANTIATE_SM(SlotNielsDebug)

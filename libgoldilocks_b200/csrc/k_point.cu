@@ -8,3 +8,4 @@ INSTANTIATE_PLAIN(LanePtEq)
 INSTANTIATE_PLAIN(LanePtValid)
 INSTANTIATE_PLAIN(LanePt<PTOP_TORQUE>)
 INSTANTIATE_PLAIN(LanePtPscale)
+INSTANTIATE_PLAIN(LanePtNiels)

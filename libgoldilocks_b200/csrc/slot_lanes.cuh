@@ -388,3 +388,57 @@ struct SlotCombTable { /* goldilocks_448_precomputed_scalarmul over a caller-sup
         if (live) s_pt_to_abi(out + i, sb);
     }
 };
+
+// ---- direct access to the mixed additions (goldilocks.c:271-380) -- test entry point only -------------------
+// The reference keeps pt_to_pniels / pniels_to_pt / niels_to_pt / add_niels_to_pt / sub_niels_from_pt / add_pniels_to_pt /
+// sub_pniels_from_pt static, so every caller reaches them through a scalar multiplication.  goldilocks_b200_debug_niels_batch runs ONE of
+// them per element, in both shapes the kernels use -- by value (point.cuh, the lane kernels) and on the slot machine (slot_algos.cuh,
+// the scalar-multiplication kernels) -- so that all four output coordinates can be pinned to the reference's formulas.
+//   op 0: pniels_to_pt(pt_to_pniels(q))      1 / 2: p +/- pniels(q), by value        3 / 4: p +/- comb[which], by value
+//   op 5: niels_to_pt(comb[which])           6 / 7: p +/- pniels(q), slot machine    8 / 9: p +/- comb[which], slot machine
+//   op 10 (internal): recs[i] = the projective-niels record of q the slot machine adds from (y - x, y + x, -2 d' t, 2 z)
+struct LanePtNiels {
+    abi_pt *out; pt *recs; const abi_pt *p, *q; const niels *comb; const uint32_t *which; uint32_t op;
+    GDM void operator()(size_t i) const {
+        pt P, Q, R;
+        pt_from_abi(P, p + i);
+        pt_from_abi(Q, q + i);
+        pniels pn;
+        pt_to_pniels(pn, Q);
+        niels e;
+        const niels *src = comb + which[i] % COMB_ENTRIES;
+        gf_ld<false>(e.a, &src->a); gf_ld<false>(e.b, &src->b); gf_ld<false>(e.c, &src->c);
+        pt_copy(R, P);
+        if (op == 0) pniels_to_pt(R, pn);
+        else if (op == 1) pt_addsub_pniels<false>(R, pn, false);
+        else if (op == 2) pt_addsub_pniels<true>(R, pn, false);
+        else if (op == 3) pt_addsub_niels<false>(R, e, false);
+        else if (op == 4) pt_addsub_niels<true>(R, e, false);
+        else if (op == 5) niels_to_pt(R, e);
+        else {
+            pt rec;
+            gf_copy(rec.x, pn.n.a); gf_copy(rec.y, pn.n.b); gf_neg(rec.z, pn.n.c); gf_copy(rec.t, pn.z);
+            gf_copy(recs[i].x, rec.x); gf_copy(recs[i].y, rec.y); gf_copy(recs[i].z, rec.z); gf_copy(recs[i].t, rec.t);
+        }
+        pt_to_abi(out + i, R);
+    }
+};
+struct SlotNielsDebug {
+    static constexpr int NSLOTS = 7;
+    abi_pt *out; const abi_pt *p; const pt *recs; const niels *comb; const uint32_t *which; uint32_t op;
+    GDM void operator()(size_t i, sref sb, bool live) const {
+        const spt P = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+        const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+        s_pt_from_abi(sb, p + i);
+        const gmask_t sub = (op & 1u) ? ~0u : 0u;
+        if (op < 8) {
+            wtab<1> t;
+            t.base = reinterpret_cast<uint4 *>(const_cast<pt *>(recs + i));
+            s_pt_add_pniels_g<1>(P, w, t, 0, sub, ~sub, false);      /* the record holds -c: an addition negates it back */
+        } else {
+            const niels *e = comb + which[i] % COMB_ENTRIES;
+            s_pt_add_niels_g<1>(P, w, gq(&e->a), gq(&e->b), gq(&e->c), sub, sub, false);
+        }
+        if (live) s_pt_to_abi(out + i, sb);
+    }
+};

@@ -150,6 +150,16 @@ EXPORT int32_t goldilocks_448_point_add_batch(hpt *o, const hpt *a, const hpt *b
 EXPORT int32_t goldilocks_448_point_sub_batch(hpt *o, const hpt *a, const hpt *b, size_t n) { LanePt<PTOP_SUB> f = {o, a, b}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_double_batch(hpt *o, const hpt *a, size_t n) { LanePt<PTOP_DBL> f = {o, a, nullptr}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_negate_batch(hpt *o, const hpt *a, size_t n) { LanePt<PTOP_NEG> f = {o, a, nullptr}; run(f, n); return -1; }
+EXPORT int32_t goldilocks_b200_debug_niels_batch(hpt *out, const hpt *p, const hpt *q, const uint32_t *which, uint32_t op, size_t n) {
+    if (op > 9) return 0;
+    std::vector<pt> recs(n + 1);
+    if (op < 6) { LanePtNiels f = {out, recs.data(), p, q, tables()->comb, which, op}; run(f, n); return -1; }
+    LanePtNiels f0 = {out, recs.data(), p, q, tables()->comb, which, 10};
+    run(f0, n);
+    SlotNielsDebug f = {out, p, recs.data(), tables()->comb, which, op};
+    run_sm(f, n);
+    return -1;
+}
 EXPORT int32_t goldilocks_448_point_eq_batch(uint64_t *o, const hpt *a, const hpt *b, size_t n) { LanePtEq f = {o, a, b}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_valid_batch(uint64_t *o, const hpt *a, size_t n) { LanePtValid f = {o, a}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_encode_batch(uint8_t *o, const hpt *a, size_t n) { LanePtEncode f = {o, a}; run(f, n); return -1; }

@@ -60,6 +60,77 @@ def check_points(lib, chk, n):
     eq(lib.point_valid(garbage), chk.point_valid(garbage), "point_valid garbage")
 
 
+def check_niels(lib, chk, n):
+    """SURVEY 8(a) row a9, directly: pt_to_pniels / pniels_to_pt / niels_to_pt / add_niels_to_pt / sub_niels_from_pt / add_pniels_to_pt /
+    sub_pniels_from_pt (goldilocks.c:271-380).  The reference keeps them static, so the expected coordinates are its formulas restated
+    on Python integers below (line for line: the projective representative matters, all four coordinates are compared), and the results
+    are tied to the reference itself as group elements through its exported point_add / point_sub.  Both shapes of the product's code:
+    by value (ops 0-5) and on the slot machine (ops 6-9)."""
+    D2 = (2 * -39082) % P                                   # 2 * TWISTED_D (goldilocks.c:45,286)
+    p = util.random_points(chk, "a9/p", n)
+    q = util.random_points(chk, "a9/q", n)
+    p[1::2] = chk.point_add(p[1::2], q[::2][: len(p[1::2])])  # Z != 1 representatives on both sides
+    q[::3] = chk.point_double(q[::3])
+    which = (stream_bytes("a9/w", n).astype(np.uint32) * 7 + np.arange(n, dtype=np.uint32)) % 200   # reduced mod 80 by the library
+    comb = np.frombuffer(lib.export_comb_table().tobytes(), dtype="<u8").reshape(80, 3, 8)
+    comb = [[sum(int(comb[e, j, l]) << (56 * l) for l in range(8)) for j in range(3)] for e in range(80)]
+    cp, cq = util.coords_fast(chk, p).reshape(n, 4, 56), util.coords_fast(chk, q).reshape(n, 4, 56)
+    P4 = [[util.from_le(c) for c in row] for row in cp]
+    Q4 = [[util.from_le(c) for c in row] for row in cq]
+
+    def to_pniels(x, y, z, t):                               # goldilocks.c:280-288
+        return (y - x) % P, (x + y) % P, (t * D2) % P, (2 * z) % P
+
+    def pniels_to_pt(a, b, c, z):                            # goldilocks.c:290-301
+        eu, ey = (b + a) % P, (b - a) % P
+        return (z * ey) % P, (z * eu) % P, (z * z) % P, (ey * eu) % P
+
+    def niels_to_pt(a, b, c):                                # goldilocks.c:303-313
+        ey, ex = (b + a) % P, (b - a) % P
+        return ex, ey, 1, (ey * ex) % P
+
+    def add_niels(d, e, sub):                                # goldilocks.c:315-359 (before_double = 0)
+        x, y, z, t = d
+        ea, eb, ec = e
+        if sub:
+            ea, eb = eb, ea
+        a = ea * (y - x) % P
+        yy = eb * (x + y) % P
+        xx = ec * t % P
+        c, b = (a + yy) % P, (yy - a) % P
+        if not sub:
+            y2, a2 = (z - xx) % P, (xx + z) % P
+        else:
+            y2, a2 = (z + xx) % P, (z - xx) % P
+        return (y2 * b) % P, (a2 * c) % P, (a2 * y2) % P, (b * c) % P
+
+    def add_pniels(d, pn, sub):                              # goldilocks.c:361-380
+        x, y, z, t = d
+        return add_niels((x, y, z * pn[3] % P, t), pn[:3], sub)
+
+    def pack(rows):
+        return np.stack([np.concatenate([util.le(v) for v in r]) for r in rows])
+
+    c = util.coords_fast
+    pnq = [to_pniels(*r) for r in Q4]
+    want = {0: [pniels_to_pt(*pn) for pn in pnq],
+            1: [add_pniels(d, pn, False) for d, pn in zip(P4, pnq)], 2: [add_pniels(d, pn, True) for d, pn in zip(P4, pnq)],
+            3: [add_niels(d, comb[w % 80], False) for d, w in zip(P4, which)], 4: [add_niels(d, comb[w % 80], True) for d, w in zip(P4, which)],
+            5: [niels_to_pt(*comb[w % 80]) for w in which]}
+    want[6], want[7], want[8], want[9] = want[1], want[2], want[3], want[4]
+    got = {}
+    for op in range(10):
+        got[op] = lib.debug_niels(p, q, which, op)
+        eq(c(chk, got[op]), pack(want[op]), "niels op %d coordinates" % op)
+    # the same results as group elements, against the reference's own exported group law
+    eq(chk.point_eq(got[0], q), np.ones(n, bool), "pniels_to_pt(pt_to_pniels(q)) == q")
+    eq(chk.point_eq(got[1], chk.point_add(p, q)), np.ones(n, bool), "p + pniels(q) == point_add(p, q)")
+    eq(chk.point_eq(got[7], chk.point_sub(p, q)), np.ones(n, bool), "p - pniels(q) == point_sub(p, q) (slot machine)")
+    eq(chk.point_eq(chk.point_sub(got[8], got[5]), p), np.ones(n, bool), "(p + comb[e]) - niels_to_pt(comb[e]) == p (slot machine)")
+    eq(chk.point_eq(chk.point_add(got[4], got[5]), p), np.ones(n, bool), "(p - comb[e]) + niels_to_pt(comb[e]) == p")
+    assert chk.point_valid(got[5]).all() and chk.point_valid(got[9]).all()
+
+
 def check_codec(lib, chk, n):
     """BASELINE config 5: decaf encode/decode + Elligator"""
     h = stream_bytes("c5/h", n * 112).reshape(n, 112)

@@ -33,6 +33,12 @@ def test_points_edge_and_glue(gpu, chk):
     parity.check_points(gpu, chk, 1 << 14)
 
 
+def test_niels_mixed_additions(gpu, chk):
+    """row a9 directly (goldilocks.c:271-380): all four coordinates of every mixed addition / conversion, by value and on the slot
+    machine, against the reference's formulas restated on integers, and as group elements against its exported point_add / point_sub"""
+    parity.check_niels(gpu, chk, 5000)
+
+
 def test_codec_elligator(gpu, chk):
     parity.check_codec(gpu, chk, 1 << 14)
     parity.check_elligator_inverse(gpu, chk, 1 << 12)

@@ -21,6 +21,11 @@ def test_points(sim, chk):
     parity.check_points(sim, chk, 1024)
 
 
+def test_niels_mixed_additions(sim, chk):
+    """row a9 directly: the mixed additions and conversions of goldilocks.c:271-380, by value and on the slot machine"""
+    parity.check_niels(sim, chk, 300)
+
+
 def test_codec_elligator(sim, chk):
     parity.check_codec(sim, chk, 256)
     parity.check_elligator_inverse(sim, chk, 96)

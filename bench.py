@@ -328,6 +328,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         import datetime
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")   # one node: never depend on the container's hostname resolving
         dist.init_process_group("gloo", timeout=datetime.timedelta(minutes=30))   # rendezvous, barrier and max-over-ranks only: the data path has no exchange step
     dev = torch.device("cuda", local)
     n = args.n

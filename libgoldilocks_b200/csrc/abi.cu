@@ -1125,13 +1125,17 @@ static bool rlc_seed(uint8_t seed[32]) { /* fresh secret weights per call: the s
 static bool rlc_usable(size_t n) { return n >= RLC_MIN && n < ((size_t)1 << 26); } /* pair lists are 32-bit, CUB counts are int */
 // One class of points through the bucket method: digits -> radix sort -> buckets -> segments -> tree nodes.  The window
 // sums (the c*w doublings) are a separate launch so that the key class can run its long chain on the side stream.
-struct RlcClass { rlc_shape sh; size_t count, npairs, nb; uint32_t *keys, *vals, *keys_s, *vals_s; void *sort_tmp; size_t sort_bytes; pt *buckets, *segsum, *nodesum, *winsum, *total; };
+struct RlcClass { rlc_shape sh; size_t count, npairs, nb; uint32_t *keys, *vals, *keys_s, *vals_s; void *sort_tmp; size_t sort_bytes; pt *buckets, *segsum, *nodesum, *winsum, *total;
+                  uint32_t *bstart, *blen, *bid, *blen_s, *perm; void *bsort_tmp; size_t bsort_bytes; };
 static bool rlc_class_alloc(Call &k, RlcClass &q, const rlc_shape &sh, size_t count) {
     const size_t nw = (size_t)sh.nch * sh.wn; /* window ids run over chunks x windows */
     q.sh = sh; q.count = count; q.npairs = count * sh.wn; q.nb = nw << sh.c;
     q.keys = k.out<uint32_t>(q.npairs); q.vals = k.out<uint32_t>(q.npairs); q.keys_s = k.out<uint32_t>(q.npairs); q.vals_s = k.out<uint32_t>(q.npairs);
     q.sort_bytes = pair_sort_scratch_bytes(q.npairs);
     q.sort_tmp = k.alloc(q.sort_bytes);
+    q.bstart = k.out<uint32_t>(q.nb); q.blen = k.out<uint32_t>(q.nb); q.bid = k.out<uint32_t>(q.nb); q.blen_s = k.out<uint32_t>(q.nb); q.perm = k.out<uint32_t>(q.nb);
+    q.bsort_bytes = pair_sort_scratch_bytes(q.nb);
+    q.bsort_tmp = k.alloc(q.bsort_bytes);
     q.buckets = k.out<pt>(q.nb); q.segsum = k.out<pt>(nw * sh.segs); q.nodesum = k.out<pt>(nw * sh.nodes); q.winsum = k.out<pt>(nw); q.total = k.out<pt>(sh.nch);
     return k.ok;
 }
@@ -1142,12 +1146,17 @@ static bool rlc_class_pairs(Ctx &c, const RlcClass &q, const uint32_t *scal, uin
     while (((q.sh.nch * q.sh.wn) << q.sh.c) >> key_bits) key_bits++;
     cudaError_t e = pair_sort(q.sort_tmp, q.sort_bytes, q.keys, q.keys_s, q.vals, q.vals_s, q.npairs, key_bits, s);
     if (e != cudaSuccess) return fail("pair_sort", e);
+    /* the runs of the buckets and the order the bucket kernel takes them in (longest first: equal lengths share a warp) */
+    LaneRlcBucketRuns fr = {q.bstart, q.blen, q.bid, q.keys_s, q.npairs, q.sh};
+    if (!launch(c, fr, q.nb, s)) return false;
+    e = pair_sort(q.bsort_tmp, q.bsort_bytes, q.blen, q.blen_s, q.bid, q.perm, q.nb, 8, s);
+    if (e != cudaSuccess) return fail("pair_sort (bucket lengths)", e);
     return true;
 }
 static bool rlc_class_sum(Ctx &c, const RlcClass &q, const pt *recs, cudaStream_t s, bool subtract, const int32_t *valid) { /* buckets -> window sums */
     /* plain grid, not the persistent shape: blocks retire all the time, so the high-priority blocks of the side stream get onto
      * the SMs between them (persistent blocks held the SMs and starved the side stream: 22.6 vs 20.9 ms per 2^20) */
-    SlotRlcBucket f7 = {q.buckets, q.keys_s, q.vals_s, q.npairs, recs, q.sh, subtract ? ~0u : 0u, valid};
+    SlotRlcBucket f7 = {q.buckets, q.keys_s, q.vals_s, q.npairs, recs, q.sh, subtract ? ~0u : 0u, valid, q.perm, q.bstart};
     if (!launch_slots(c, f7, q.nb, s)) return false;
     const size_t nw = (size_t)q.sh.nch * q.sh.wn;
     LaneRlcSegments f8 = {q.segsum, q.buckets, q.sh};

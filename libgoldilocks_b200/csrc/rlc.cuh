@@ -234,23 +234,46 @@ GD uint32_t rlc_bucket_digit(size_t b, const rlc_shape &sh) {
 // 6) buckets: lane b = (window << c | digit) adds up (or, for the R class, subtracts) the points of its run in the sorted
 //    pair list, on the slot machine (slots.cuh): accumulator in shared-memory slots, each point taken straight from its
 //    projective-niels record in global memory (8M per point, no by-value calls).
+// 5b) bucket runs: lane b finds the run of bucket b in the sorted pair list and files the bucket under its LENGTH.  The bucket kernel
+//     then takes its buckets in order of length (a second, 8-bit radix sort of (255 - length, bucket)), so the 32 lanes of a warp add up
+//     runs of nearly the same length: with one lane per bucket in bucket order a warp waited for its longest run -- Poisson around 32,
+//     the longest of 32 is about 46 -- and the kernel sat at 52 % of the multiply pipe (profiles/r02h_rlcbucket_ncu.txt).
+struct LaneRlcBucketRuns {
+    uint32_t *start, *lenkey, *ident; const uint32_t *keys; size_t npairs; rlc_shape sh;
+    GDM void operator()(size_t b) const {
+        uint32_t lo = 0, len = 0;
+        if (rlc_bucket_digit(b, sh)) {
+            size_t l = 0, h = npairs;
+            while (l < h) { const size_t mid = (l + h) >> 1; if (keys[mid] < (uint32_t)b) l = mid + 1; else h = mid; }
+            size_t l2 = l;
+            h = npairs;
+            while (l2 < h) { const size_t mid = (l2 + h) >> 1; if (keys[mid] <= (uint32_t)b) l2 = mid + 1; else h = mid; }
+            lo = (uint32_t)l; len = (uint32_t)(l2 - l);
+        }
+        start[b] = lo;
+        lenkey[b] = 255u - (len > 255u ? 255u : len);
+        ident[b] = (uint32_t)b;
+    }
+};
 struct SlotRlcBucket {
     static constexpr int NSLOTS = 7;
     pt *buckets; const uint32_t *keys, *vals; size_t npairs; const pt *recs; rlc_shape sh; gmask_t subtract;
     const int32_t *valid; /* R class: the pair list is made before the decodes are in, so excluded signatures are skipped here (null: take all) */
-    GDM void operator()(size_t b, sref sb, bool live) const {
+    const uint32_t *perm, *start; /* lane l takes bucket perm[l], whose run begins at start[bucket] (LaneRlcBucketRuns) */
+    GDM void operator()(size_t lane, sref sb, bool live) const {
         const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
         const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
         s_pt_set_identity(p);
         if (!live) return;
+        const size_t b = perm[lane];
         if (rlc_bucket_digit(b, sh)) {
-            size_t lo = 0, hi = npairs;
-            while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (keys[mid] < (uint32_t)b) lo = mid + 1; else hi = mid; }
-            for (size_t j = lo; j < npairs && keys[j] == (uint32_t)b; j++) {
+            {
+            for (size_t j = start[b]; j < npairs && keys[j] == (uint32_t)b; j++) {
                 if (valid && !valid[vals[j]]) continue;
                 wtab<1> t;
                 t.base = reinterpret_cast<uint4 *>(const_cast<pt *>(recs + vals[j]));
                 s_pt_add_pniels_g<1>(p, w, t, 0, subtract, ~subtract, false); /* minus the point: swap (a, b), keep the stored -c */
+            }
             }
         }
         pt out;

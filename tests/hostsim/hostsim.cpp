@@ -349,7 +349,12 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
         for (size_t j = 0; j < npairs; j++) pairs[j] = {keys[j], vals[j]};
         std::stable_sort(pairs.begin(), pairs.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
         for (size_t j = 0; j < npairs; j++) { keys[j] = pairs[j].first; vals[j] = pairs[j].second; }
-        SlotRlcBucket f7 = {buckets.data(), keys.data(), vals.data(), npairs, pts.data(), sh, subtract ? ~0u : 0u, subtract ? valid.data() : nullptr};
+        std::vector<uint32_t> bstart(nb), blen(nb), bid(nb), perm(nb);
+        LaneRlcBucketRuns fr = {bstart.data(), blen.data(), bid.data(), keys.data(), npairs, sh};
+        run(fr, nb);
+        for (size_t b = 0; b < nb; b++) perm[b] = (uint32_t)b;
+        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return blen[a] < blen[b]; });
+        SlotRlcBucket f7 = {buckets.data(), keys.data(), vals.data(), npairs, pts.data(), sh, subtract ? ~0u : 0u, subtract ? valid.data() : nullptr, perm.data(), bstart.data()};
         run_sm(f7, nb);
         LaneRlcSegments f8 = {segsum.data(), buckets.data(), sh};
         run(f8, nw * sh.segs);

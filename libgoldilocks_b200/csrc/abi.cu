@@ -1214,7 +1214,7 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     const uint32_t max_ch = RLC_MAX_CHUNKS;
     pt *pts = k.out<pt>(2 * n + max_ch);                               /* n R records, then at most n key groups, then one B per chunk */
     int32_t *ok = k.out<int32_t>(2 * n + max_ch), *valid = k.out<int32_t>(n);
-    uint32_t *flags = k.out<uint32_t>(1 + (size_t)max_ch);             /* [0] force fallback, [1 + ch] verdict of chunk ch */
+    uint32_t *flags = k.out<uint32_t>(2 + (size_t)max_ch);             /* [0] force fallback, [1 + ch] verdict of chunk ch, [1 + chunks] redo the key class */
     abi_sc *chal = k.out<abi_sc>(n), *resp = k.out<abi_sc>(n);
     uint32_t *z = k.out<uint32_t>(RLC_ZWORDS * n);
     k.secret(z, RLC_ZWORDS * n);                                      /* the weights are secret until the verdict is out: wiped when the call ends */
@@ -1238,7 +1238,7 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
         unsigned long long *s_acc = k.out<unsigned long long>((size_t)RLC_ACC_WORDS * cells * nch);
         RlcClass cr, ck;
         if (!rlc_class_alloc(k, cr, sh_r, n)) return false;
-        CU(cudaMemsetAsync(flags, 0, (1 + (size_t)nch) * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(flags, 0, (2 + (size_t)nch) * sizeof(uint32_t), s));
         CU(cudaMemsetAsync(s_acc, 0, sizeof(unsigned long long) * RLC_ACC_WORDS * cells * nch, s));
         /* Two streams.  Main: the multiplier-bound work -- the R decodes as the signatures land, later the bucket sums of the R class.
          * Side (high priority): what needs no decoded R -- the weights and the sorted pair list of the R class (they depend on the
@@ -1286,31 +1286,57 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
         g_launches++;
         LaneRlcDecode fk = {pts, ok, flags, dsig, dpk, n, g, n};
         if (!launch(c, fk, nkey, side)) return false;
+        /* the key class from its scalars to its totals, on `side` */
+        auto key_class = [&]() -> bool {
+            LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m, cells};
+            if (!launch(c, f5, nkey, side)) return false;
+            if (!rlc_class_pairs(c, ck, kscal, SC_WORDS, n, side, kchunk)) return false;
+            CU(cudaEventRecord(c.side_evt[4], side));
+            if (!rlc_class_sum(c, ck, pts, side, false, nullptr)) return false;
+            CU(cudaEventRecord(c.side_evt[3], side));
+            return true;
+        };
         if (first) {
+            /* whole-batch pass: the key class does not wait for the R decodes.  The scalar sums are taken as soon as the key decodes and
+             * the challenge hashes are in (a signature counts if its KEY decodes), the key class runs on them beside the decodes, and
+             * LaneRlcLate settles the rest: it writes `valid` and takes a signature whose R does not decode out of the sums again, raising
+             * the redo flag -- then the key class (only) is run once more on the corrected sums, below.  Never on honest traffic. */
             if (feed) CU(cudaStreamWaitEvent(side, feed->rest, 0));
             LaneEdVerifyScalars f2 = {chal, resp, dsig, dpk, dmsg, doff, prehashed, dctx, ctx_len, 0};
             if (!launch(c, f2, n, side)) return false;
+            LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g, sh_r, 1u};
+            if (!launch(c, f4, n, side)) return false;
+            CU(cudaEventRecord(c.side_evt[1], side));
+            if (!key_class()) return false;
+            CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));          /* behind the R decodes on `s` */
+            LaneRlcLate fl = {z, valid, key_acc, s_acc, chal, resp, ok, n, g, sh_r, flags + 1 + nch};
+            if (!launch(c, fl, n, s)) return false;
+        } else {
+            CU(cudaEventRecord(c.side_evt[1], side));
+            CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));
+            LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g, sh_r, 0u};
+            if (!launch(c, f4, n, s)) return false;
+            CU(cudaEventRecord(c.side_evt[2], s));
+            CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));
+            if (!key_class()) return false;
         }
-        CU(cudaEventRecord(c.side_evt[1], side));
-        CU(cudaStreamWaitEvent(s, c.side_evt[1], 0));
-        LaneRlcWeights f4 = {z, valid, key_acc, s_acc, chal, resp, ok, n, g, sh_r};
-        if (!launch(c, f4, n, s)) return false;
-        LaneRlcKeyScalars f5 = {kscal, key_acc, s_acc, m, cells};
-        if (!launch(c, f5, nkey, s)) return false;
-        CU(cudaEventRecord(c.side_evt[2], s));
-        CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));
-        if (!rlc_class_pairs(c, ck, kscal, SC_WORDS, n, side, kchunk)) return false;
-        CU(cudaEventRecord(c.side_evt[4], side));
-        if (!rlc_class_sum(c, ck, pts, side, false, nullptr)) return false;
-        CU(cudaEventRecord(c.side_evt[3], side));
         CU(cudaStreamWaitEvent(s, c.side_evt[4], 0)); /* the radix sort of the key class wants the whole machine for its 0.3 ms: the R buckets wait for it */
         if (!rlc_class_sum(c, cr, pts, s, true, valid)) return false;
         CU(cudaStreamWaitEvent(s, c.side_evt[3], 0));
         LaneRlcVerdict f11 = {flags + 1, cr.total, ck.total, flags};
         if (!launch(c, f11, nch, s)) return false;
-        hflags.assign(1 + (size_t)nch, 0);
+        hflags.assign(2 + (size_t)nch, 0);
         CU(cudaMemcpyAsync(hflags.data(), flags, hflags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        if (first && hflags[1 + nch]) { /* an R that does not decode under a key that does: the key class again, on the corrected sums */
+            CU(cudaEventRecord(c.side_evt[2], s));
+            CU(cudaStreamWaitEvent(side, c.side_evt[2], 0));
+            if (!key_class()) return false;
+            CU(cudaStreamWaitEvent(s, c.side_evt[3], 0));
+            if (!launch(c, f11, nch, s)) return false;
+            CU(cudaMemcpyAsync(hflags.data(), flags, hflags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+        }
         return true;
     };
     if (!equations(n, true)) return false;

@@ -155,13 +155,18 @@ struct LaneRlcZ {
 };
 
 // 3) products: lane j = sorted position.  Excluded signatures get valid = FAILURE (the bucket kernel skips them) and add nothing to the scalar sums.
+//    `early` (the whole-batch pass): the sums are taken as soon as the KEY decodes and the challenge hashes are in -- a signature counts
+//    if its key decodes -- so that the whole key class runs beside the R decodes; LaneRlcLate settles the rest when those are in.
 struct LaneRlcWeights {
     uint32_t *z; int32_t *valid; unsigned long long *key_acc, *s_acc; const abi_sc *chal, *resp; const int32_t *ok; size_t n; rlc_groups g; rlc_shape sh; /* R-class shape: chunks */
+    uint32_t early;
     GDM void operator()(size_t j) const {
         const size_t i = g.order[j], k = g.gid[j] - 1;
-        const bool v = ok[i] && ok[n + k];
-        valid[i] = v ? -1 : 0;
-        if (!v) { for (int q = 0; q < RLC_ZWORDS; q++) z[RLC_ZWORDS * i + q] = 0; return; }
+        const bool v = early ? ok[n + k] != 0 : (ok[i] && ok[n + k]);
+        if (!early) {
+            valid[i] = v ? -1 : 0;
+            if (!v) { for (int q = 0; q < RLC_ZWORDS; q++) z[RLC_ZWORDS * i + q] = 0; return; }
+        } else if (!v) return;
         sc zi, c, r, zc, zr;
         sc_set_zero(zi);
         for (int q = 0; q < RLC_ZWORDS; q++) zi.w[q] = z[RLC_ZWORDS * i + q];
@@ -172,6 +177,34 @@ struct LaneRlcWeights {
         const uint32_t cells = rlc_scells(sh);
         unsigned long long *ka = key_acc + RLC_ACC_WORDS * k, *sa = s_acc + RLC_ACC_WORDS * ((i / sh.csize) * cells + j % cells);
         for (int q = 0; q < SC_WORDS; q++) { rlc_atomic_add(ka + q, zc.w[q]); rlc_atomic_add(sa + q, zr.w[q]); }
+    }
+};
+
+// 3b) after the R decodes: the verdicts the bucket kernel and the caller read (valid = R and key both decode), and the correction of the
+//     early sums -- a signature whose key decodes but whose R does not was counted by LaneRlcWeights(early) and is taken out again
+//     (the cells are plain integers mod 2^64: subtracting is adding the complement).  Any such signature raises *redo: the key class that
+//     ran on the early sums is then run again on the corrected ones (abi.cu rlc_core).  Never on honest traffic.
+struct LaneRlcLate {
+    uint32_t *z; int32_t *valid; unsigned long long *key_acc, *s_acc; const abi_sc *chal, *resp; const int32_t *ok; size_t n; rlc_groups g; rlc_shape sh; uint32_t *redo;
+    GDM void operator()(size_t j) const {
+        const size_t i = g.order[j], k = g.gid[j] - 1;
+        const bool okk = ok[n + k] != 0, okr = ok[i] != 0;
+        valid[i] = (okk && okr) ? -1 : 0;
+        if (okk && okr) return;
+        if (okk) {
+            sc zi, c, r, zc, zr;
+            sc_set_zero(zi);
+            for (int q = 0; q < RLC_ZWORDS; q++) zi.w[q] = z[RLC_ZWORDS * i + q];
+            sc_from_abi(c, chal + i);
+            sc_from_abi(r, resp + i);
+            sc_mul(zc, zi, c);
+            sc_mul(zr, zi, r);
+            const uint32_t cells = rlc_scells(sh);
+            unsigned long long *ka = key_acc + RLC_ACC_WORDS * k, *sa = s_acc + RLC_ACC_WORDS * ((i / sh.csize) * cells + j % cells);
+            for (int q = 0; q < SC_WORDS; q++) { rlc_atomic_add(ka + q, 0ull - (unsigned long long)zc.w[q]); rlc_atomic_add(sa + q, 0ull - (unsigned long long)zr.w[q]); }
+            *redo = 1u;
+        }
+        for (int q = 0; q < RLC_ZWORDS; q++) z[RLC_ZWORDS * i + q] = 0;
     }
 };
 

@@ -334,8 +334,18 @@ EXPORT int32_t goldilocks_ed448_verify_rlc_batch(int32_t *st, const uint8_t *sig
     LaneRlcZ f3 = {z.data(), g_rlc_seed, n, sh_r.zbits};
     run(f3, (n + RLC_Z_PER_LANE - 1) / RLC_Z_PER_LANE);
     const std::vector<uint32_t> z_for_digits = z; /* the product makes the R pair list before the decodes are in */
-    LaneRlcWeights f4 = {z.data(), valid.data(), key_acc.data(), s_acc.data(), chal.data(), resp.data(), ok.data(), n, g, sh_r};
-    run(f4, n);
+    /* the product's whole-batch pass: sums taken early (a signature counts if its key decodes), corrected when the R decodes are in;
+     * its per-chunk pass takes them in one go.  Both orders here, by the parity of the chunk count, so that the CPU tier runs both. */
+    uint32_t redo = 0;
+    if (nch & 1) {
+        LaneRlcWeights f4 = {z.data(), valid.data(), key_acc.data(), s_acc.data(), chal.data(), resp.data(), ok.data(), n, g, sh_r, 1u};
+        run(f4, n);
+        LaneRlcLate fl = {z.data(), valid.data(), key_acc.data(), s_acc.data(), chal.data(), resp.data(), ok.data(), n, g, sh_r, &redo};
+        run(fl, n);
+    } else {
+        LaneRlcWeights f4 = {z.data(), valid.data(), key_acc.data(), s_acc.data(), chal.data(), resp.data(), ok.data(), n, g, sh_r, 0u};
+        run(f4, n);
+    }
     LaneRlcKeyScalars f5 = {kscal.data(), key_acc.data(), s_acc.data(), m, cells};
     run(f5, (size_t)m + nch);
     auto run_class = [&](const rlc_shape &sh, size_t count, const uint32_t *scal, uint32_t nwords, size_t p0, std::vector<pt> &total, bool subtract, const uint32_t *chunk_of) {

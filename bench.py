@@ -440,8 +440,20 @@ def run_ours(args):
     t_e2e = max_over_ranks((time.perf_counter() - t0) / ke)
     barrier()
     h2d = sig.nbytes + pk.nbytes + arena.nbytes + off.nbytes
+    # what the PCIe path of this rank delivers on its own: the same pinned buffers copied to the device with nothing else running on it
+    # (all ranks at once, slowest rank reported: at 8 GPUs they share the host's memory system)
+    ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ca.record()
+    for _ in range(3):
+        for hsrc, ddst in ((h_sig, d_sig), (h_pk, d_pk), (h_msg, d_msg), (h_off, d_off)):
+            ddst.copy_(hsrc, non_blocking=True)
+    cb.record()
+    barrier()
+    t_copy = max_over_ranks(ca.elapsed_time(cb) / 1e3 / 3)
     e2e = {"value": world * n / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(4 * n), "ms_per_step": t_e2e * 1e3,
-           "api": "goldilocks_ed448_verify_batch (host pointers, pinned)"}
+           "api": "goldilocks_ed448_verify_batch (host pointers, pinned)",
+           "h2d_gbs_per_rank_copy_alone": h2d / t_copy / 1e9, "h2d_ms_copy_alone": t_copy * 1e3}
 
     extra = {"corpus_seconds": round(t_corpus, 1)}
 
@@ -630,6 +642,37 @@ def run_ours(args):
         sweep["ordinary_path_same_buffers"] = {"ms": tt * 1e3, "value": world * n / tt}
         extra["rlc_sweep"] = sweep
         del r_sig, r_pk, r_msg, r_off
+        # the same entry point on 2^20 DISTINCT keys (no key repeats: the key class is as big as the R class): all valid, one bad, 1/8 bad
+        sig3, pk3, arena3, off3, _ = cached_corpus(n, "bench/rlc_distinct", rank, world, barrier, per=1, corrupt=False)
+        q_sig, q_pk, q_msg, q_off = pinned(sig3.reshape(-1)), pinned(pk3.reshape(-1)), pinned(arena3), pinned(off3.view(np.int64))
+        argq = [C.c_void_p(h_st.data_ptr()), C.c_void_p(q_sig.data_ptr()), C.c_void_p(q_pk.data_ptr()), C.c_void_p(q_msg.data_ptr()),
+                C.c_void_p(q_off.data_ptr()), C.c_uint8(0), None, C.c_uint8(0), C.c_size_t(n), C.byref(fast)]
+        lib.rlc_policy(16)
+        sweep_d = {}
+        for label, every in (("0", 0), ("1_bad", n), ("1/8", 8)):
+            cur = sig3.copy()
+            bad = np.arange(every // 2, n, every) if every else np.zeros(0, np.int64)
+            cur[bad, 70] ^= 1
+            q_sig.copy_(torch.from_numpy(cur.reshape(-1)))
+            want = np.full(n, -1, np.int32); want[bad] = 0
+            assert fr(*argq) == -1
+            assert (h_st.numpy() == want).all(), "rlc sweep (distinct keys) %s: statuses" % label
+            t0 = time.perf_counter()
+            for _ in range(2):
+                assert fr(*argq) == -1
+            tt = max_over_ranks((time.perf_counter() - t0) / 2)
+            sweep_d[label] = {"bad_signatures": int(len(bad)), "ms": tt * 1e3, "value": world * n / tt, "fast_path": int(fast.value)}
+            barrier()
+        argo = [C.c_void_p(h_st.data_ptr()), C.c_void_p(q_sig.data_ptr()), C.c_void_p(q_pk.data_ptr()), C.c_void_p(q_msg.data_ptr()),
+                C.c_void_p(q_off.data_ptr()), C.c_uint8(0), None, C.c_uint8(0), C.c_size_t(n)]
+        assert fn(*argo) == -1
+        t0 = time.perf_counter()
+        assert fn(*argo) == -1
+        tt = max_over_ranks(time.perf_counter() - t0)
+        sweep_d["ordinary_path_same_buffers"] = {"ms": tt * 1e3, "value": world * n / tt}
+        extra["rlc_sweep_distinct_keys"] = sweep_d
+        lib.rlc_policy(16)
+        del q_sig, q_pk, q_msg, q_off
 
     # ---- extra.strong: ONE batch sharded over all N GPUs by the library itself (rank 0 drives, the other ranks wait) ------------------
     if not args.no_extra and not args.no_strong:

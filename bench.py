@@ -674,6 +674,13 @@ def run_ours(args):
         lib.rlc_policy(16)
         del q_sig, q_pk, q_msg, q_off
 
+    # ---- extra.single_calls_from_threads: the reference's own one-signature call from a pool of host threads, gathered or not -------
+    if not args.no_extra:
+        barrier()
+        if rank == 0:
+            extra["single_calls_from_threads"] = single_call_leg(lib, sig, pk, arena, off, expect)
+        barrier()
+
     # ---- extra.strong: ONE batch sharded over all N GPUs by the library itself (rank 0 drives, the other ranks wait) ------------------
     if not args.no_extra and not args.no_strong:
         barrier()
@@ -706,6 +713,49 @@ def run_ours(args):
     barrier()
     if world > 1:
         dist.destroy_process_group()
+
+
+def single_call_leg(lib, sig, pk, arena, off, expect):
+    """goldilocks_ed448_verify (the reference's one-signature entry point, ed448.h:157-165) called from host threads on signatures of
+    the bench corpus: every thread makes its calls one after the other.  Without gathering each call is a batch of one on the GPU;
+    with goldilocks_b200_coalesce(window) concurrent calls share a launch (csrc/coalesce.h).  Python threads: ctypes drops the GIL
+    for the duration of a call."""
+    import threading
+    fn = lib.lib.goldilocks_ed448_verify
+    fn.restype = C.c_int32
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_void_p, C.c_uint8]
+    sp, pp, ap = sig.ctypes.data, pk.ctypes.data, arena.ctypes.data
+    o = off.astype(np.int64)
+
+    def run(T, K, window_us):
+        lib.coalesce(window_us)
+        wrong = []
+        c0, b0, _ = lib.coalesce_stats()
+
+        def worker(t):
+            for j in range(K):
+                i = t * K + j
+                st = fn(sp + 114 * i, pp + 57 * i, ap + int(o[i]), int(o[i + 1] - o[i]), 0, None, 0)
+                if st != expect[i]:
+                    wrong.append(i)
+
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        dt = time.perf_counter() - t0
+        lib.coalesce(0)
+        assert not wrong, "single calls: %d statuses differ from the corpus' expected accept bits" % len(wrong)
+        c1, b1, big = lib.coalesce_stats()
+        return {"threads": T, "calls": T * K, "window_us": window_us, "value": T * K / dt, "unit": UNIT, "seconds": dt,
+                "batches": int(b1 - b0), "largest_batch": int(big) if window_us else 1}
+
+    run(8, 2, 0)                                    # warm-up of the one-element shapes
+    out = {"alone": run(8, 16, 0), "gathered": run(256, 24, 250), "gathered_64_threads": run(64, 48, 250)}
+    out["speedup_gathered_over_alone"] = out["gathered"]["value"] / out["alone"]["value"]
+    return out
 
 
 def strong_leg(lib, torch, world, n, corpus, peak, ops, reps):

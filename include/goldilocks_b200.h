@@ -272,6 +272,17 @@ GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_rlc_batch(goldilo
  * straight to the per-signature path and the one after tries the equation again (default 16; 0 = always try).  Setting the
  * policy also clears the remembered outcomes. */
 GOLDILOCKS_B200_API void goldilocks_b200_rlc_policy(unsigned reprobe);
+/* Concurrent single-element calls gathered into one batch (csrc/coalesce.h).  The reference's own entry points
+ * goldilocks_ed448_verify (ed448.h:157-165; also reached through goldilocks_ed448_verify_prehash), goldilocks_ed448_sign
+ * (ed448.h:108-118) and goldilocks_x448 (point_448.h) take one element; called from many host threads at once they are
+ * independent, so with window_us > 0 the first caller of a kind waits up to window_us microseconds (or until max_batch calls
+ * are in; 0 = 4096) for others, runs ONE batch launch for all of them on its own thread and current device, and every caller
+ * gets exactly the result its own call would have produced.  Calls that differ in (prehashed, context) are batched separately.
+ * window_us = 0 (the default) turns it off: a lone caller would only pay the window as latency.  The environment variables
+ * GOLDILOCKS_B200_COALESCE_US / GOLDILOCKS_B200_COALESCE_MAX set the same thing for unmodified programs.
+ * goldilocks_b200_coalesce_stats: calls that went through a gathering, batches launched for them, largest batch (any may be NULL). */
+GOLDILOCKS_B200_API void goldilocks_b200_coalesce(unsigned window_us, unsigned max_batch);
+GOLDILOCKS_B200_API void goldilocks_b200_coalesce_stats(unsigned long long *calls, unsigned long long *batches, unsigned long long *largest);
 /* SHAKE256 one-shot over n inputs, each squeezed to outlen bytes (shake.c:177-190, SHAKE256 params 211-213) */
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_shake256_hash_batch(uint8_t *out /*n*outlen*/, size_t outlen, const uint8_t *in, const size_t *in_off /*n+1*/, size_t n);
 

@@ -352,6 +352,44 @@ class BatchLib:
         self.lib.goldilocks_b200_rlc_policy.restype = None
         self.lib.goldilocks_b200_rlc_policy(C.c_uint(reprobe))
 
+    # ---- the reference's own single-element calls, and their gathering into batches (csrc/coalesce.h) ----
+    def coalesce(self, window_us, max_batch=0):
+        """goldilocks_b200_coalesce: concurrent single-element verify / sign / X448 calls wait up to window_us for each other and share
+        one batch launch (0 = off)"""
+        self.lib.goldilocks_b200_coalesce.restype = None
+        self.lib.goldilocks_b200_coalesce(C.c_uint(window_us), C.c_uint(max_batch))
+
+    def coalesce_stats(self):
+        """(calls that went through a gathering, batches launched for them, largest batch)"""
+        a, b, c = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
+        self.lib.goldilocks_b200_coalesce_stats.restype = None
+        self.lib.goldilocks_b200_coalesce_stats(C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def ed448_verify_one(self, sig, pk, msg, prehashed=False, context=b""):
+        """goldilocks_ed448_verify (ed448.h:157-165) on one signature: -1 / 0"""
+        fn = self.lib.goldilocks_ed448_verify
+        fn.restype = C.c_int32
+        return fn(C.c_char_p(bytes(sig)), C.c_char_p(bytes(pk)), C.c_char_p(bytes(msg)), _Z(len(msg)), C.c_uint8(1 if prehashed else 0),
+                  C.c_char_p(bytes(context)) if context else None, C.c_uint8(len(context)))
+
+    def ed448_sign_one(self, sk, pk, msg, prehashed=False, context=b""):
+        """goldilocks_ed448_sign (ed448.h:108-118) on one message: the 114 signature bytes"""
+        out = C.create_string_buffer(114)
+        fn = self.lib.goldilocks_ed448_sign
+        fn.restype = None
+        fn(out, C.c_char_p(bytes(sk)), C.c_char_p(bytes(pk)), C.c_char_p(bytes(msg)), _Z(len(msg)), C.c_uint8(1 if prehashed else 0),
+           C.c_char_p(bytes(context)) if context else None, C.c_uint8(len(context)))
+        return out.raw
+
+    def x448_one(self, base, scalar):
+        """goldilocks_x448 on one (u, k) pair: (56 bytes, -1 / 0)"""
+        out = C.create_string_buffer(56)
+        fn = self.lib.goldilocks_x448
+        fn.restype = C.c_int32
+        st = fn(out, C.c_char_p(bytes(base)), C.c_char_p(bytes(scalar)))
+        return out.raw, st
+
     # ---- device sets: one host-pointer batch over several GPUs (include/goldilocks_b200.h, section 4) ----
     def set_devices(self, devices):
         """spread every later `*_batch` host-pointer call over these CUDA devices ([] = the current device only)"""

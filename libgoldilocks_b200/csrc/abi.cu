@@ -19,6 +19,7 @@
 #include "launch.cuh"
 #include "staged.cuh"
 #include "shard.h"
+#include "coalesce.h"
 
 // kernels live in k_*.cu
 LANES_PLAIN(DECLARE_PLAIN)
@@ -981,7 +982,7 @@ static size_t verify_slot_bytes(const VerifyGrids &g, size_t n) {
     size_t lanes = (size_t)(g.unique > g.shared ? g.unique : g.shared) * SLOT_BLOCK;
     const size_t need = (n + SLOT_BLOCK - 1) / SLOT_BLOCK * SLOT_BLOCK;
     if (lanes > need) lanes = need;
-    return (lanes * WTAB_QUADS_PER_LANE * sizeof(uint4) + 255) & ~(size_t)255;
+    return (lanes * 2 * WTAB_QUADS_PER_LANE * sizeof(uint4) + 255) & ~(size_t)255;   /* two tables per lane: the key's and R's (s_verify_half_item) */
 }
 size_t goldilocks_b200_verify_scratch_bytes(size_t n) {
     /* the device-pointer call carves EVERYTHING it writes from the caller's scratch (two verifications in flight on two
@@ -1048,6 +1049,10 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
             LaneEdVerifyScalars f = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len, split};
             if (!launch(c, f, n - split, side)) return false;
         }
+        {   /* the stand-alone signatures: their R and the half-size multipliers (the lanes past counts[1] retire at once) */
+            LaneVerifyHalf fh = {pts, ok, chal, resp, sig, plan};
+            if (!launch(c, fh, n, side)) return false;
+        }
         CU(cudaEventRecord(side_evt[1], side));
         SlotKeyTables ft = {pts, ktabs, plan};
         if (!launch_smp(c, ft, cap, grids.tables, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3], counts[4] = 0, left by the grouping pass */
@@ -1062,6 +1067,10 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
     if (!decode_range(0, split) || !scalars_range(0, split)) return false;
     if (feed) CU(cudaStreamWaitEvent(s, feed->ready[1], 0));
     if (split < n && (!decode_range(split, n) || !scalars_range(split, n))) return false;
+    {
+        LaneVerifyHalf fh = {pts, ok, chal, resp, sig, plan};
+        if (!launch(c, fh, n, s)) return false;
+    }
     if (plan.unique_sig) {
         SlotKeyTables ft = {pts, ktabs, plan};
         if (!launch_smp(c, ft, cap, grids.tables, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3], counts[4] = 0, left by the grouping pass */
@@ -1091,7 +1100,7 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
     VerifyGrids grids;
     if (k.ok) k.ok = verify_grids(*k.c, &grids);
     const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
-    uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
+    uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 2);
     void *scratch = k.alloc(verify_core_scratch_bytes(n));
     VerifyFeed feed = {n >= 2 * VERIFY_GROUP_MIN ? n / 2 : n, {nullptr, nullptr}};
     if (k.ok) {
@@ -1193,7 +1202,7 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
         VerifyGrids grids;
         if (!verify_grids(c, &grids)) return false;
         const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
-        uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 1);
+        uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 2);
         void *scratch = k.alloc(verify_core_scratch_bytes(cnt));
         if (!k.ok) return false;
         return verify_dev(c, st, sig, pk, msg, off, prehashed, dctx, ctx_len, cnt, scratch, slots, grids, s);
@@ -1590,6 +1599,98 @@ goldilocks_error_t goldilocks_448_point_encode_batch_dev(uint8_t *ser, const hpt
     return launch(*c, f, n, as_stream(stream)) ? GOLDILOCKS_SUCCESS : GOLDILOCKS_FAILURE;
 }
 
+// ---- concurrent single-element calls gathered into one batch (coalesce.h; goldilocks_b200_coalesce) ----------
+extern "C++" {
+namespace {
+coalesce::Settings g_coalesce;
+coalesce::Stats g_coalesce_stats;
+std::once_flag g_coalesce_env;
+bool coalescing() {
+    std::call_once(g_coalesce_env, [] {
+        if (const char *w = getenv("GOLDILOCKS_B200_COALESCE_US")) g_coalesce.window_us.store((unsigned)strtoul(w, nullptr, 10));
+        if (const char *m = getenv("GOLDILOCKS_B200_COALESCE_MAX")) { const unsigned v = (unsigned)strtoul(m, nullptr, 10); if (v) g_coalesce.max_batch.store(v); }
+    });
+    return g_coalesce.window_us.load(std::memory_order_relaxed) != 0 && !shard::t_worker;
+}
+struct MsgArgs { uint8_t prehashed; const uint8_t *context; uint8_t context_len; const uint8_t *message; size_t message_len; };
+struct VerifyReq { bool done; MsgArgs m; const uint8_t *sig, *pk; goldilocks_error_t st; };
+struct SignReq { bool done; MsgArgs m; uint8_t *sig; const uint8_t *sk, *pk; };
+struct X448Req { bool done; uint8_t *out; const uint8_t *base, *scalar; goldilocks_error_t st; };
+coalesce::Gate<VerifyReq> g_gate_verify;
+coalesce::Gate<SignReq> g_gate_sign;
+coalesce::Gate<X448Req> g_gate_x448;
+bool same_domain(const MsgArgs &a, const MsgArgs &b) { /* the batch entry points take one (prehashed, context) for the whole batch */
+    return a.prehashed == b.prehashed && a.context_len == b.context_len && (a.context_len == 0 || memcmp(a.context, b.context, a.context_len) == 0);
+}
+// Requests of one gathering, split into runs that share (prehashed, context); fn(first request, indices of the run, messages, offsets).
+template <class Req, class Fn>
+void for_each_domain(Req **q, size_t n, Fn fn) {
+    std::vector<char> taken(n, 0);
+    std::vector<size_t> idx, off;
+    std::vector<uint8_t> msg;
+    for (size_t i = 0; i < n; i++) {
+        if (taken[i]) continue;
+        idx.clear(); off.assign(1, 0); msg.clear();
+        for (size_t j = i; j < n; j++) {
+            if (taken[j] || !same_domain(q[i]->m, q[j]->m)) continue;
+            taken[j] = 1;
+            idx.push_back(j);
+            if (q[j]->m.message_len) msg.insert(msg.end(), q[j]->m.message, q[j]->m.message + q[j]->m.message_len);
+            off.push_back(msg.size());
+        }
+        if (msg.empty()) msg.push_back(0);
+        fn(q[i]->m, idx, msg, off);
+    }
+}
+void run_verify_requests(VerifyReq **q, size_t n) {
+    for_each_domain(q, n, [&](const MsgArgs &d, const std::vector<size_t> &idx, const std::vector<uint8_t> &msg, const std::vector<size_t> &off) {
+        const size_t m = idx.size();
+        std::vector<uint8_t> sig(114 * m), pk(57 * m);
+        std::vector<goldilocks_error_t> st(m, GOLDILOCKS_FAILURE);
+        for (size_t k = 0; k < m; k++) { memcpy(&sig[114 * k], q[idx[k]]->sig, 114); memcpy(&pk[57 * k], q[idx[k]]->pk, 57); }
+        const bool ok = goldilocks_ed448_verify_batch(st.data(), sig.data(), pk.data(), msg.data(), off.data(), d.prehashed, d.context, d.context_len, m) == GOLDILOCKS_SUCCESS;
+        for (size_t k = 0; k < m; k++) q[idx[k]]->st = ok ? st[k] : GOLDILOCKS_FAILURE;
+    });
+}
+void run_sign_requests(SignReq **q, size_t n) {
+    for_each_domain(q, n, [&](const MsgArgs &d, const std::vector<size_t> &idx, const std::vector<uint8_t> &msg, const std::vector<size_t> &off) {
+        const size_t m = idx.size();
+        std::vector<uint8_t> sig(114 * m), sk(57 * m), pk(57 * m);
+        for (size_t k = 0; k < m; k++) { memcpy(&sk[57 * k], q[idx[k]]->sk, 57); memcpy(&pk[57 * k], q[idx[k]]->pk, 57); }
+        const bool ok = goldilocks_ed448_sign_batch(sig.data(), sk.data(), pk.data(), msg.data(), off.data(), d.prehashed, d.context, d.context_len, m) == GOLDILOCKS_SUCCESS;
+        for (size_t k = 0; k < m; k++) {
+            if (ok) memcpy(q[idx[k]]->sig, &sig[114 * k], 114);
+            else memset(q[idx[k]]->sig, 0, 114);
+        }
+        goldilocks_bzero(sk.data(), sk.size());             /* the gathered private keys */
+    });
+}
+void run_x448_requests(X448Req **q, size_t n) {
+    std::vector<uint8_t> out(56 * n), base(56 * n), scalar(56 * n);
+    std::vector<goldilocks_error_t> st(n, GOLDILOCKS_FAILURE);
+    for (size_t k = 0; k < n; k++) { memcpy(&base[56 * k], q[k]->base, 56); memcpy(&scalar[56 * k], q[k]->scalar, 56); }
+    const bool ok = goldilocks_x448_batch(out.data(), st.data(), base.data(), scalar.data(), n) == GOLDILOCKS_SUCCESS;
+    for (size_t k = 0; k < n; k++) {
+        if (ok) memcpy(q[k]->out, &out[56 * k], 56);
+        else memset(q[k]->out, 0, 56);
+        q[k]->st = ok ? st[k] : GOLDILOCKS_FAILURE;
+    }
+    goldilocks_bzero(scalar.data(), scalar.size());         /* the gathered secret scalars ... */
+    goldilocks_bzero(out.data(), out.size());               /* ... and shared secrets */
+}
+}  // namespace
+}  // extern "C++"
+void goldilocks_b200_coalesce(unsigned window_us, unsigned max_batch) {
+    coalescing();                                           /* read the environment first, so that this call wins over it */
+    g_coalesce.max_batch.store(max_batch ? max_batch : 4096);
+    g_coalesce.window_us.store(window_us);
+}
+void goldilocks_b200_coalesce_stats(unsigned long long *calls, unsigned long long *batches, unsigned long long *largest) {
+    if (calls) *calls = g_coalesce_stats.calls.load();
+    if (batches) *batches = g_coalesce_stats.batches.load();
+    if (largest) *largest = g_coalesce_stats.largest.load();
+}
+
 // ---- legacy single-element entry points: a batch of one on the GPU ------------------------------------------
 void goldilocks_448_point_add(goldilocks_448_point_p o, const goldilocks_448_point_p a, const goldilocks_448_point_p b) { goldilocks_448_point_add_batch(o, a, b, 1); }
 void goldilocks_448_point_sub(goldilocks_448_point_p o, const goldilocks_448_point_p a, const goldilocks_448_point_p b) { goldilocks_448_point_sub_batch(o, a, b, 1); }
@@ -1637,6 +1738,11 @@ goldilocks_error_t goldilocks_448_point_decode_like_eddsa_and_mul_by_ratio(goldi
 }
 void goldilocks_448_point_mul_by_ratio_and_encode_like_x448(uint8_t out[56], const goldilocks_448_point_p p) { goldilocks_448_point_mul_by_ratio_and_encode_like_x448_batch(out, p, 1); }
 goldilocks_error_t goldilocks_x448(uint8_t out[56], const uint8_t base[56], const uint8_t scalar[56]) {
+    if (coalescing()) {
+        X448Req r = {false, out, base, scalar, GOLDILOCKS_FAILURE};
+        g_gate_x448.submit(&r, g_coalesce, g_coalesce_stats, run_x448_requests);
+        return r.st;
+    }
     goldilocks_error_t st = GOLDILOCKS_FAILURE;
     if (goldilocks_x448_batch(out, &st, base, scalar, 1) != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;
     return st;
@@ -1652,11 +1758,21 @@ void goldilocks_ed448_derive_secret_scalar(goldilocks_448_scalar_p secret, const
 void goldilocks_ed448_derive_public_key(uint8_t pubkey[57], const uint8_t privkey[57]) { goldilocks_ed448_derive_public_key_batch(pubkey, privkey, 1); }
 void goldilocks_ed448_sign(uint8_t signature[114], const uint8_t privkey[57], const uint8_t pubkey[57], const uint8_t *message, size_t message_len,
                            uint8_t prehashed, const uint8_t *context, uint8_t context_len) {
+    if (coalescing()) {
+        SignReq r = {false, {prehashed, context, context_len, message, message_len}, signature, privkey, pubkey};
+        g_gate_sign.submit(&r, g_coalesce, g_coalesce_stats, run_sign_requests);
+        return;
+    }
     const size_t off[2] = {0, message_len};
     goldilocks_ed448_sign_batch(signature, privkey, pubkey, message, off, prehashed, context, context_len, 1);
 }
 goldilocks_error_t goldilocks_ed448_verify(const uint8_t signature[114], const uint8_t pubkey[57], const uint8_t *message, size_t message_len,
                                            uint8_t prehashed, const uint8_t *context, uint8_t context_len) {
+    if (coalescing()) {
+        VerifyReq r = {false, {prehashed, context, context_len, message, message_len}, signature, pubkey, GOLDILOCKS_FAILURE};
+        g_gate_verify.submit(&r, g_coalesce, g_coalesce_stats, run_verify_requests);
+        return r.st;
+    }
     const size_t off[2] = {0, message_len};
     goldilocks_error_t st = GOLDILOCKS_FAILURE;
     if (goldilocks_ed448_verify_batch(&st, signature, pubkey, message, off, prehashed, context, context_len, 1) != GOLDILOCKS_SUCCESS) return GOLDILOCKS_FAILURE;

@@ -565,6 +565,49 @@ struct LaneEdVerifyScalars {
         sc_to_abi(response + i, r);
     }
 };
+// Stand-alone signatures (no key table to share) are verified with half-size multipliers (sc.cuh sc_half_gcd, slot_algos.cuh
+// s_verify_half).  One lane per such signature, after LaneEdVerifyScalars: from the challenge c and the response s it leaves
+//     challenge[i] <- u in words 0..6, |v| in words 7..13, the sign of v in bit 31 of word 13   (v c == u mod q)
+//     response[i]  <- sB = v s mod q
+// and, on the grouped path (where nothing else decodes an R), the decoded R of the signature in pts[2i+1] / ok[2i+1].
+// c = 0 keeps the reference's quirk (goldilocks.c:1281-1284: the combination is the identity whatever s is): u = 0, v = 1, sB = 0.
+struct LaneVerifyHalf {
+    abi_pt *pts; int32_t *ok; abi_sc *challenge, *response; const uint8_t *sig; verify_plan plan;
+    GDM void operator()(size_t j) const {
+        size_t i = j;
+        if (plan.unique_sig) {
+            if (j >= plan.counts[1]) return;
+            i = plan.unique_sig[j];
+            pt p; uint32_t w[15];
+            words_load_bytes(w, 15, sig + 114 * i, 57);
+            gmask_t good = pt_decode_like_eddsa(p, w, w[14] & 0xff);
+            abi_pt *o = pts + 2 * i + 1;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                o->x.limb[k] = (uint64_t)p.x.v[2 * k] + ((uint64_t)p.x.v[2 * k + 1] << 28);
+                o->y.limb[k] = (uint64_t)p.y.v[2 * k] + ((uint64_t)p.y.v[2 * k + 1] << 28);
+                o->z.limb[k] = (uint64_t)p.z.v[2 * k] + ((uint64_t)p.z.v[2 * k + 1] << 28);
+                o->t.limb[k] = (uint64_t)p.t.v[2 * k] + ((uint64_t)p.t.v[2 * k + 1] << 28);
+            }
+            ok[2 * i + 1] = ST_OK(good);
+        }
+        sc c, r, u, v, sB, packed;
+        sc_from_abi(c, challenge + i);
+        sc_from_abi(r, response + i);
+        const gmask_t v_neg = sc_half_gcd(u, v, c);
+        sc_mul(sB, v, r);
+        if (v_neg) sc_neg(sB, sB);
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < SC_WORDS; k++) any |= c.w[k];
+        if (!any) sc_set_zero(sB);
+#pragma unroll
+        for (int k = 0; k < 7; k++) { packed.w[k] = u.w[k]; packed.w[7 + k] = v.w[k]; }
+        packed.w[13] |= v_neg & 0x80000000u;
+        sc_to_abi(challenge + i, packed);
+        sc_to_abi(response + i, sB);
+    }
+};
 // What the finish kernels leave per signature for the last step (slot_lanes.cuh s_verify_accept_prep): G D, H and flags.
 // 256 bytes, so that the grouped path can keep it in the unused R half of its point array.
 #define VAUX_FAST 1u  /* every other condition holds: accept iff lobit(H / (G D)) == sign bit */

@@ -287,3 +287,117 @@ GD uint32_t sc_bits(const sc &a, int pos, int nbits) {
     uint64_t x = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(x >> (pos & 31)) & ((1u << nbits) - 1u);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Half-size multipliers for a verification equation (Antipa, Brown, Gallant, Lambert, Struik: "Accelerated verification
+// of ECDSA signatures", SAC 2005).  For a scalar c < q there are integers u, v with
+//     v c == u (mod q),   0 <= u < 2^223,   0 < |v| < 2^223 :
+// the extended Euclidean algorithm on (q, c), stopped at the first remainder r_i below 2^223; its cofactor t_i obeys
+// |t_i| r_(i-1) <= q and r_(i-1) >= 2^223.  An equation  s B + c A == R  in a group of prime order q then holds iff
+//     (v s) B + u A - v R == 0 ,
+// which needs HALF the doublings: u and v are 223-bit multipliers and the full-size one sits on the fixed base.
+// c = 0 gives u = 0, v = 1.  Public data only -- the number of steps depends on c.
+// Quotients are taken by shift-and-subtract (they are small: 1.5 bits on average); everything is statically indexed.
+// Returns all-ones when v is negative; u and |v| come back as 14-word scalars (upper half zero).
+// ---------------------------------------------------------------------------------------------
+#define HG_TW 8 /* words of a cofactor (< 2^224, one spare bit for the aligned divisor's companion) */
+GD int hg_bitlen(const uint32_t (&a)[SC_WORDS]) {
+    int len = 0;
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) {
+#if defined(__CUDA_ARCH__)
+        if (a[i]) len = 32 * i + 32 - __clz((int)a[i]);
+#else
+        if (a[i]) len = 32 * i + 32 - __builtin_clz(a[i]);
+#endif
+    }
+    return len;
+}
+template <int N>
+GD void hg_shl(uint32_t (&a)[N], int s) {
+    const int ws = s >> 5, bs = s & 31;
+#pragma unroll 1
+    for (int k = 0; k < ws; k++) {
+#pragma unroll
+        for (int i = N - 1; i > 0; i--) a[i] = a[i - 1];
+        a[0] = 0;
+    }
+    if (bs) {
+#pragma unroll
+        for (int i = N - 1; i > 0; i--) a[i] = (a[i] << bs) | (a[i - 1] >> (32 - bs));
+        a[0] <<= bs;
+    }
+}
+template <int N>
+GD void hg_shr1(uint32_t (&a)[N]) {
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[N - 1] >>= 1;
+}
+GD gmask_t sc_half_gcd(sc &u, sc &v, const sc &c) {
+    uint32_t r0[SC_WORDS], r1[SC_WORDS], d[SC_WORDS], t0[HG_TW], t1[HG_TW], td[HG_TW];
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) { r0[i] = sc_q(i); r1[i] = c.w[i]; }
+#pragma unroll
+    for (int i = 0; i < HG_TW; i++) { t0[i] = 0; t1[i] = i == 0 ? 1u : 0u; }
+    gmask_t neg = 0;
+#pragma unroll 1
+    for (;;) {
+        uint32_t high = r1[6] >> 31;                       /* r1 >= 2^223 ? */
+#pragma unroll
+        for (int i = 7; i < SC_WORDS; i++) high |= r1[i];
+        if (!high) break;
+        int s = hg_bitlen(r0) - hg_bitlen(r1);              /* r0 > r1 throughout, so s >= 0 */
+#pragma unroll
+        for (int i = 0; i < SC_WORDS; i++) d[i] = r1[i];
+#pragma unroll
+        for (int i = 0; i < HG_TW; i++) td[i] = t1[i];
+        hg_shl(d, s);
+        hg_shl(td, s);
+#pragma unroll 1
+        for (; s >= 0; s--) {                               /* r0 = r0 mod r1, t0 += (r0 div r1) t1 */
+            uint32_t diff[SC_WORDS];
+            int64_t chain = 0;
+#pragma unroll
+            for (int i = 0; i < SC_WORDS; i++) {
+                chain = chain + r0[i] - d[i];
+                diff[i] = (uint32_t)chain;
+                chain >>= 32;
+            }
+            const uint32_t ge = ~(uint32_t)chain;           /* all-ones when r0 >= d */
+#pragma unroll
+            for (int i = 0; i < SC_WORDS; i++) r0[i] = (diff[i] & ge) | (r0[i] & ~ge);
+            uint64_t carry = 0;
+#pragma unroll
+            for (int i = 0; i < HG_TW; i++) {
+                carry = carry + t0[i] + (td[i] & ge);
+                t0[i] = (uint32_t)carry;
+                carry >>= 32;
+            }
+            hg_shr1(d);
+            hg_shr1(td);
+        }
+#pragma unroll
+        for (int i = 0; i < SC_WORDS; i++) { const uint32_t x = r0[i]; r0[i] = r1[i]; r1[i] = x; }
+#pragma unroll
+        for (int i = 0; i < HG_TW; i++) { const uint32_t x = t0[i]; t0[i] = t1[i]; t1[i] = x; }
+        neg = ~neg;
+    }
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) { u.w[i] = r1[i]; v.w[i] = i < HG_TW ? t1[i] : 0u; }
+    return neg;
+}
+// The 45 signed 5-bit digits of a multiplier m < 2^223 (values -16..15, zero allowed): digit k = window k of m + HALF_BIAS, minus 16,
+// with HALF_BIAS = sum_k 16 * 32^k (no carries to propagate: one addition, then plain windows).  m + HALF_BIAS < 2^225.
+#define HALF_WINDOWS 45
+#define GOLD_CONST_HALF_BIAS { 0x21084210u, 0x08421084u, 0x42108421u, 0x10842108u, 0x84210842u, 0x21084210u, 0x08421084u, 0x00000001u }
+GD void sc_half_bias(sc &out, const sc &m) {
+    const uint32_t bias[8] = GOLD_CONST_HALF_BIAS;
+    uint64_t chain = 0;
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) {
+        chain = chain + m.w[i] + (i < 8 ? bias[i] : 0u);
+        out.w[i] = (uint32_t)chain;
+        chain >>= 32;
+    }
+}

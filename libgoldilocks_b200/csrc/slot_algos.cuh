@@ -266,6 +266,72 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stand-alone verification with half-size multipliers (sc.cuh sc_half_gcd): instead of combo = s B + c A, compared with R,
+//     slots 0..3  <-  sB * B  +  u * A  -+  |v| * R          (sB = v s mod q,  v c == u mod q,  u, |v| < 2^223),
+// which is the identity of the quotient group exactly when combo == R there (v is a unit mod q and the quotient group has
+// prime order q; goldilocks.c:644-653 point_eq is equality in that group).  u and |v| are 45 signed 5-bit digits each
+// (sc_half_bias), so there are 44 x 5 doublings instead of 89 x 5; the 30 signed 15-bit digits of the full-size sB go to the
+// init-time tables of B (digits 0..14) and of 2^225 B (digits 15..29, column table 5 of the shared-key path).
+// Window tables: entry e = (e + 1) P for e = 0..15, entry 16 = the identity (digit 0) -- 15 additions per table.
+// ---------------------------------------------------------------------------------------------
+template <int QS>
+GD void s_prepare_signed_window(const spt &p, const swk &w, const wtab<QS> &t) {
+    s_pt_to_pniels_negc_g<QS>(t, 0, p, w);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 1; i < WINDOW_NTABLE; i++) {
+        s_pt_add_pniels_g<QS>(p, w, t, 0, 0, ~0u, false);
+        s_pt_to_pniels_negc_g<QS>(t, i, p, w);
+    }
+    s_pt_set_identity(p);
+    s_pt_to_pniels_negc_g<QS>(t, WINDOW_NTABLE, p, w);       /* a = b = 1, c = 0, z = 2 */
+}
+// p += d * P for the signed digit d = biased - 16 of a window table built by s_prepare_signed_window; `flip` negates the term
+GD void s_pt_add_signed_digit(const spt &p, const swk &w, const wtab<1> &t, uint32_t biased, gmask_t flip, bool before_double) {
+    const int32_t d = (int32_t)biased - 16;
+    const uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+    const gmask_t neg = (d < 0 ? ~0u : 0u) ^ flip;
+    s_pt_add_pniels_g<1>(p, w, t, mag ? (int)mag - 1 : WINDOW_NTABLE, neg, ~neg, before_double);
+}
+#define HALF_WIDE_COLUMN 5 /* 2^225 B = B_5 of the shared-key path's column tables (45 bits per column) */
+// On entry ta and tr hold the window tables of A and R; ub, vb are the biased multipliers (sc_half_bias), v_neg the sign of v.
+GD void s_verify_half(sref sb, const sc &sB, const sc &ub, const sc &vb, gmask_t v_neg, const niels *wide, const wtab<1> &ta, const wtab<1> &tr) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    sc s1x;
+    sc_recode_signed(s1x, sB);
+    s_pt_set_identity(p);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = HALF_WINDOWS - 1; k >= 0; k--) {
+        const bool fixed_here = (k % 3) == 0;
+        if (k != HALF_WINDOWS - 1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = 0; j < WINDOW_BITS - 1; j++) s_pt_double(p, w, true);
+            s_pt_double(p, w, false);
+        }
+        s_pt_add_signed_digit(p, w, ta, sc_window5(ub, k * WINDOW_BITS), 0, false);
+        s_pt_add_signed_digit(p, w, tr, sc_window5(vb, k * WINDOW_BITS), ~v_neg, !fixed_here && k != 0);   /* - v R */
+        if (fixed_here) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int half = 0; half < 2; half++) {
+                uint32_t bits1 = sc_bits(s1x, (k + (half ? HALF_WINDOWS : 0)) * WINDOW_BITS, WIDE_BITS);
+                const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
+                bits1 ^= inv1;
+                const niels *e = wide + (half ? (size_t)HALF_WIDE_COLUMN * WIDE_ENTRIES : 0) + (bits1 & (WIDE_ENTRIES - 1));
+                s_pt_add_niels_g<1>(p, w, gq(&e->a), gq(&e->b), gq(&e->c), inv1, inv1, half == 1 && k != 0);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Verification under a repeated public key (same group element as s_base_double_scalarmul).
 // The 90 signed 5-bit digits d_k of scalar2 and the 30 signed 15-bit digits e_m of scalar1 (the very recoding
 // above) are regrouped by column: k = R c + r with R = VSH_ROWS (9) rows and VSH_CHUNKS (10) columns, so

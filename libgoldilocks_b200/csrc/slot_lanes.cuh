@@ -57,22 +57,9 @@ struct SlotBaseDoubleScalarmul { /* goldilocks_448_base_double_scalarmul_non_sec
         s_ld(v, s_slot(sb, 3)); gf_to_abi(&out[i].t, v);
     }
 };
-// Third launch of verification (eddsa.c:293-305): combo = response*B + challenge*A, accept iff
-// combo == R on the quotient group (goldilocks.c:644-653) and both decodes succeeded.
-// accept iff combo (slots 0..3) == R on the quotient group and both decodes succeeded
-GD void s_verify_accept(int32_t *status, size_t i, sref sb, const abi_pt *r_pt, gmask_t decoded) {
-    /* pt_eq(combo, R): combo.y * R.x == R.y * combo.x */
-    const sref t0 = s_slot(sb, 4), t1 = s_slot(sb, 5);
-    gf a, b;
-    gf_from_abi(a, &r_pt->x); s_st(t0, a);
-    gf_from_abi(b, &r_pt->y); s_st(t1, b);
-    s_mul(t0, s_slot(sb, 1), t0);
-    s_mul(t1, s_slot(sb, 0), t1);
-    s_ld(a, t0);
-    s_ld(b, t1);
-    status[i] = ST_OK(gf_eq(a, b) & decoded);
-}
-// The same accept bit WITHOUT the square root of the R decode (goldilocks.c:949-1004 needs isr(N D), 446 squarings).
+// Verification under a repeated key (eddsa.c:293-305): combo = response*B + challenge*A from the key's tables, accept iff
+// combo == R on the quotient group (goldilocks.c:644-653) and both decodes succeeded --
+// that accept bit WITHOUT the square root of the R decode (goldilocks.c:949-1004 needs isr(N D), 446 squarings).
 // With y = the encoded coordinate of R, N = 1 - y^2, D = 1 - d y^2 (never 0: d is a non-square), the reference decodes
 // x = +-sqrt(N/D) with lobit(x) = the sign bit, maps (x, y) through the 4-isogeny to (X_R : Y_R) and accepts iff
 // Y_c X_R == Y_R X_c.  Multiplied by D^2 that equation is linear in W = x D (W^2 = N D):
@@ -142,17 +129,39 @@ SFN void s_verify_accept_prep(verify_aux *aux, sref sb, const uint8_t *r_enc, gm
     }
     aux->flags = ((good & fast) ? VAUX_FAST : 0u) | ((good & slow) ? VAUX_SLOW : 0u) | (low ? VAUX_LOW : 0u);
 }
+// A stand-alone signature with half-size multipliers (slot_algos.cuh s_verify_half): key2[0], key2[1] = the decoded public key and R,
+// *challenge / *response as LaneVerifyHalf (lanes.cuh) left them; two window tables per lane in `scratch`.  All-ones iff
+// response B + challenge A == R on the quotient group (eddsa.c:293-305, goldilocks.c:644-653): the combination's x is 0.
+GD gmask_t s_verify_half_item(sref sb, const abi_pt *key2, const abi_sc *challenge, const abi_sc *response, const niels *wide, uint4 *scratch, size_t slot) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    sc packed, sB, u, v;
+    sc_from_abi(packed, challenge);
+    sc_from_abi(sB, response);
+    sc_set_zero(u);
+    sc_set_zero(v);
+#pragma unroll
+    for (int k = 0; k < 7; k++) { u.w[k] = packed.w[k]; v.w[k] = packed.w[7 + k]; }
+    const gmask_t v_neg = (gmask_t)0 - (v.w[6] >> 31);
+    v.w[6] &= 0x7fffffffu;
+    sc_half_bias(u, u);
+    sc_half_bias(v, v);
+    const wtab<1> ta = wtab_of<1>(scratch, 2 * slot), tr = wtab_of<1>(scratch, 2 * slot + 1);
+    s_pt_from_abi(sb, key2);
+    s_prepare_signed_window<1>(p, w, ta);
+    s_pt_from_abi(sb, key2 + 1);
+    s_prepare_signed_window<1>(p, w, tr);
+    s_verify_half(sb, sB, u, v, v_neg, wide, ta, tr);
+    gf x;
+    s_ld(x, p.x);
+    return gf_is_zero(x);
+}
 struct SlotEdVerifyFinish {
     static constexpr int NSLOTS = BDSM_NSLOTS;
     int32_t *status; const abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; uint4 *scratch;
     GDM void operator()(size_t i, sref sb, size_t slot) const {
-        sc c, r;
-        sc_from_abi(c, challenge + i);
-        sc_from_abi(r, response + i);
-        s_pt_from_abi(sb, pts + 2 * i);
-        s_base_double_scalarmul(sb, r, c, wide, wtab_of<1>(scratch, slot));
-        s_bdsm_quirk(sb, c);
-        s_verify_accept(status, i, sb, pts + 2 * i + 1, (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1]);
+        const gmask_t eq = s_verify_half_item(sb, pts + 2 * i, challenge + i, response + i, wide, scratch, slot);
+        status[i] = ST_OK(eq & (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1]);
     }
 };
 // One lane per key table: the decoded public key of the group's representative signature -> its column tables.
@@ -170,8 +179,9 @@ struct SlotKeyTables {
 // SlotEdVerifyFinish (own window table in `scratch`); items [counts[1], counts[1] + counts[0]) are signatures whose
 // public key (byte-identical) occurs more than once: the multiples of the key come from the table its group built.
 // One launch for both; the expensive stand-alone items go first and the items are handed out dynamically
-// (k_slots_persist, slots.cuh), so the cheap ones fill in behind them.  R is never decoded: s_verify_accept_prep works
-// from its bytes and leaves the sign check to LaneVerifySign.
+// (k_slots_persist, slots.cuh), so the cheap ones fill in behind them.  The shared items never decode R: s_verify_accept_prep
+// works from its bytes and leaves the sign check to LaneVerifySign; the stand-alone items (half-size multipliers, R decoded by
+// LaneVerifyHalf) leave their verdict in the same record.
 struct SlotEdVerifyFinishShared {
     static constexpr int NSLOTS = BDSM_NSLOTS;
     abi_pt *pts; const int32_t *ok; const abi_sc *challenge, *response; const niels *wide; uint4 *ktabs; uint4 *scratch;
@@ -191,11 +201,12 @@ struct SlotEdVerifyFinishShared {
             key_ok = (gmask_t)ok[2 * (size_t)plan.tab_rep[t]]; /* the key bytes are the representative's, so is the decode flag */
         } else {
             i = plan.unique_sig[j];
-            sc_from_abi(c, challenge + i);
-            sc_from_abi(r, response + i);
-            s_pt_from_abi(sb, pts + 2 * i);
-            s_base_double_scalarmul(sb, r, c, wide, wtab_of<1>(scratch, slot));
-            key_ok = (gmask_t)ok[2 * i];
+            const gmask_t eq = s_verify_half_item(sb, pts + 2 * i, challenge + i, response + i, wide, scratch, slot);
+            verify_aux *aux = (verify_aux *)(pts + 2 * i + 1);   /* the decoded R has been consumed */
+            const abi_gf one = {{1, 0, 0, 0, 0, 0, 0, 0}};
+            aux->gd = one; aux->h = one;
+            aux->flags = (eq & (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1]) ? VAUX_SLOW : 0u;
+            return;
         }
         s_bdsm_quirk(sb, c);
         s_verify_accept_prep((verify_aux *)(pts + 2 * i + 1), sb, sig + 114 * i, key_ok); /* the R slot of pts is free: R is never decoded */

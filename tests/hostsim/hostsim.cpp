@@ -160,6 +160,17 @@ EXPORT int32_t goldilocks_b200_debug_niels_batch(hpt *out, const hpt *p, const h
     run_sm(f, n);
     return -1;
 }
+// sc_half_gcd (sc.cuh) on n scalars: u, |v| as 56-byte little-endian numbers, v_neg[i] = 1 when v is negative
+EXPORT int32_t hostsim_half_gcd(hsc *u, hsc *v, uint32_t *v_neg, const hsc *c, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        sc cc, uu, vv;
+        sc_from_abi(cc, c + i);
+        v_neg[i] = sc_half_gcd(uu, vv, cc) ? 1u : 0u;
+        sc_to_abi(u + i, uu);
+        sc_to_abi(v + i, vv);
+    }
+    return -1;
+}
 EXPORT int32_t goldilocks_448_point_eq_batch(uint64_t *o, const hpt *a, const hpt *b, size_t n) { LanePtEq f = {o, a, b}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_valid_batch(uint64_t *o, const hpt *a, size_t n) { LanePtValid f = {o, a}; run(f, n); return -1; }
 EXPORT int32_t goldilocks_448_point_encode_batch(uint8_t *o, const hpt *a, size_t n) { LanePtEncode f = {o, a}; run(f, n); return -1; }
@@ -259,6 +270,16 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     std::vector<abi_sc> chal(n), resp(n);
     LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, pk, msg, off, prehashed, ctx, ctx_len, 0};
     run(f2, n);
+    if (n < 64) { /* abi.cu VERIFY_GROUP_MIN: no grouping pass, every signature stand-alone with half-size multipliers */
+        const verify_plan none = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, none, 0};
+        run(f1, 2 * n);
+        LaneVerifyHalf fh = {pts.data(), ok.data(), chal.data(), resp.data(), sig, none};
+        run(fh, n);
+        SlotEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), slots(2)};
+        run_smp(f3, n);
+        return -1;
+    }
     /* the key-grouping pass of k_group.cu restated on the host: byte-identical keys that occur at least twice share a table */
     std::map<std::string, std::vector<uint32_t>> groups;
     for (size_t i = 0; i < n; i++) groups[std::string((const char *)pk + 57 * i, 57)].push_back((uint32_t)i);
@@ -278,9 +299,11 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     std::vector<uint4> ktabs((size_t)(counts[2] + 1) * KTAB_QUADS);
     LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, plan, n};   /* keys only: R is never decoded on this path */
     run(f1, n);
+    LaneVerifyHalf fh = {pts.data(), ok.data(), chal.data(), resp.data(), sig, plan};   /* stand-alone signatures: R, half-size multipliers */
+    run(fh, n);
     SlotKeyTables ft = {pts.data(), ktabs.data(), plan};
     run_smp(ft, counts[2]);
-    SlotEdVerifyFinishShared fs = {pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), ktabs.data(), slots(1), plan, sig};
+    SlotEdVerifyFinishShared fs = {pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), ktabs.data(), slots(2), plan, sig};
     run_smp(fs, (size_t)counts[0] + counts[1]);
     LaneVerifySign fv = {st, (verify_aux *)(pts.data() + 1), 2, n};
     run(fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH);

@@ -708,3 +708,65 @@ def test_codec_roundtrip_large(gpu, chk):
     assert gpu.point_eq(gpu.from_hash_nonuniform(rec[good]), pts[good]).all(), "from_hash(invert_elligator(P)) != P"
     idx = np.arange(0, n, n // (1 << 13))
     parity.eq(ser[idx], chk.point_encode(chk.from_hash_nonuniform(h[idx])), "elligator+encode sample vs checker")
+
+
+def test_single_calls_from_many_threads_are_gathered(gpu, chk):
+    """goldilocks_b200_coalesce (csrc/coalesce.h): 32 host threads call the reference's own one-element entry points -- verify (three
+    different (prehashed, context) domains mixed in one gathering), sign and X448 -- and every call must return what the reference returns for
+    it, while the library runs them as a few batches instead of one launch per call"""
+    import threading
+    T, K = 32, 12
+    n = T * K
+    doms = [(False, b""), (False, b"gathered"), (True, b"\x07" * 9)]
+    sk = stream_bytes("coal/sk", n * 57).reshape(n, 57)
+    pk = chk.ed448_derive_public_key(sk)
+    msgs = [bytes(stream_bytes("coal/m%d" % i, 64 if doms[i % 3][0] else i % 50)) for i in range(n)]
+    sig = np.zeros((n, 114), np.uint8)
+    for d, (ph, ctx) in enumerate(doms):
+        idx = np.arange(d, n, 3)
+        sig[idx] = chk.ed448_sign(sk[idx], pk[idx], [msgs[i] for i in idx], ph, ctx)
+    bad = sig.copy()
+    bad[::4, 60] ^= 1
+    want_v = np.zeros(n, np.int32)
+    for d, (ph, ctx) in enumerate(doms):
+        idx = np.arange(d, n, 3)
+        want_v[idx] = chk.ed448_verify(bad[idx], pk[idx], [msgs[i] for i in idx], ph, ctx)
+    assert (want_v == -1).sum() > n // 2 and (want_v == 0).sum() >= n // 5
+    u = stream_bytes("coal/u", n * 56).reshape(n, 56); k = stream_bytes("coal/k", n * 56).reshape(n, 56)
+    u[5] = 0                                                       # a low-order point: FAILURE and 56 zero bytes
+    want_x, want_xs = chk.x448(u, k)
+    errors = []
+
+    def worker(t):
+        try:
+            for j in range(K):
+                i = t * K + j
+                ph, ctx = doms[i % 3]
+                st = gpu.ed448_verify_one(bad[i], pk[i], msgs[i], ph, ctx)
+                if st != want_v[i]:
+                    errors.append("verify %d: %d, reference %d" % (i, st, want_v[i]))
+                s = gpu.ed448_sign_one(sk[i], pk[i], msgs[i], ph, ctx)
+                if s != bytes(sig[i]):
+                    errors.append("sign %d differs" % i)
+                o, st = gpu.x448_one(u[i], k[i])
+                if o != bytes(want_x[i]) or st != want_xs[i]:
+                    errors.append("x448 %d differs" % i)
+        except Exception as e:  # noqa: BLE001
+            errors.append("thread %d: %r" % (t, e))
+
+    calls0, batches0, _ = gpu.coalesce_stats()
+    gpu.coalesce(300)
+    try:
+        threads = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+    finally:
+        gpu.coalesce(0)
+    assert not errors, errors[:5]
+    calls, batches, largest = gpu.coalesce_stats()
+    assert calls - calls0 == 3 * n
+    assert batches - batches0 < (calls - calls0) // 3 and largest >= 4, (calls - calls0, batches - batches0, largest)
+    # switched off again: a call runs alone and still answers
+    assert gpu.ed448_verify_one(sig[0], pk[0], msgs[0]) == -1 and gpu.coalesce_stats()[0] == calls

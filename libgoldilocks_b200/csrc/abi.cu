@@ -1049,9 +1049,11 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
             LaneEdVerifyScalars f = {chal, resp, sig, pk, msg, off, prehashed, ctx, ctx_len, split};
             if (!launch(c, f, n - split, side)) return false;
         }
-        {   /* the stand-alone signatures: their R and the half-size multipliers (the lanes past counts[1] retire at once) */
-            LaneVerifyHalf fh = {pts, ok, chal, resp, sig, plan};
+        {   /* the stand-alone signatures: the half-size multipliers and their R (the lanes past counts[1] retire at once) */
+            LaneVerifyHalf fh = {chal, resp, plan};
             if (!launch(c, fh, n, side)) return false;
+            LaneEdVerifyDecode fr = {pts, ok, sig, pk, n, plan, 2 * n};
+            if (!launch(c, fr, n, side)) return false;
         }
         CU(cudaEventRecord(side_evt[1], side));
         SlotKeyTables ft = {pts, ktabs, plan};
@@ -1068,8 +1070,12 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
     if (feed) CU(cudaStreamWaitEvent(s, feed->ready[1], 0));
     if (split < n && (!decode_range(split, n) || !scalars_range(split, n))) return false;
     {
-        LaneVerifyHalf fh = {pts, ok, chal, resp, sig, plan};
+        LaneVerifyHalf fh = {chal, resp, plan};
         if (!launch(c, fh, n, s)) return false;
+        if (plan.unique_sig) {
+            LaneEdVerifyDecode fr = {pts, ok, sig, pk, n, plan, 2 * n};
+            if (!launch(c, fr, n, s)) return false;
+        }
     }
     if (plan.unique_sig) {
         SlotKeyTables ft = {pts, ktabs, plan};

@@ -515,8 +515,9 @@ struct LaneEdSignFinish {
 struct LaneEdVerifyDecode {
     /* Without a plan: lane 2i = public key i, lane 2i+1 = R of signature i.  With the plan of a grouped batch
      * (verify_plan.cuh) only public keys are decoded, once per key, by the lanes from n on: the keys of the stand-alone
-     * signatures, then one representative per key table; the remaining lanes retire at once (R is not decoded at all on
-     * that path, slot_lanes.cuh s_verify_accept_prep).  The result lands in pts[2i] (key of signature i) / pts[2i+1] (its R). */
+     * signatures, then one representative per key table; the remaining lanes retire at once.  R is not decoded for signatures
+     * under a key table (slot_lanes.cuh s_verify_accept_prep); the lanes from 2n on decode the R of the stand-alone ones.
+     * The result lands in pts[2i] (key of signature i) / pts[2i+1] (its R). */
     abi_pt *pts; int32_t *ok; const uint8_t *sig, *pk; size_t n; verify_plan plan; size_t lane0; /* first lane of this launch */
     GDM void operator()(size_t j0) const {
         const size_t j = j0 + lane0;
@@ -525,10 +526,14 @@ struct LaneEdVerifyDecode {
             if (j < n) return;
             {
                 const size_t k = j - n, nu = plan.counts[1];
-                if (k < nu) i = plan.unique_sig[k];
+                which = 0;
+                if (k >= n) {                                   /* lanes from 2n on: R of the stand-alone signatures (half-size path) */
+                    if (k - n >= nu) return;
+                    i = plan.unique_sig[k - n];
+                    which = 1;
+                } else if (k < nu) i = plan.unique_sig[k];
                 else if (k - nu < plan.counts[2]) i = plan.tab_rep[k - nu];
                 else return;
-                which = 0;
             }
         }
         const uint8_t *enc = which ? sig + 114 * i : pk + 57 * i;
@@ -569,27 +574,14 @@ struct LaneEdVerifyScalars {
 // s_verify_half).  One lane per such signature, after LaneEdVerifyScalars: from the challenge c and the response s it leaves
 //     challenge[i] <- u in words 0..6, |v| in words 7..13, the sign of v in bit 31 of word 13   (v c == u mod q)
 //     response[i]  <- sB = v s mod q
-// and, on the grouped path (where nothing else decodes an R), the decoded R of the signature in pts[2i+1] / ok[2i+1].
 // c = 0 keeps the reference's quirk (goldilocks.c:1281-1284: the combination is the identity whatever s is): u = 0, v = 1, sB = 0.
 struct LaneVerifyHalf {
-    abi_pt *pts; int32_t *ok; abi_sc *challenge, *response; const uint8_t *sig; verify_plan plan;
+    abi_sc *challenge, *response; verify_plan plan;
     GDM void operator()(size_t j) const {
         size_t i = j;
         if (plan.unique_sig) {
             if (j >= plan.counts[1]) return;
             i = plan.unique_sig[j];
-            pt p; uint32_t w[15];
-            words_load_bytes(w, 15, sig + 114 * i, 57);
-            gmask_t good = pt_decode_like_eddsa(p, w, w[14] & 0xff);
-            abi_pt *o = pts + 2 * i + 1;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                o->x.limb[k] = (uint64_t)p.x.v[2 * k] + ((uint64_t)p.x.v[2 * k + 1] << 28);
-                o->y.limb[k] = (uint64_t)p.y.v[2 * k] + ((uint64_t)p.y.v[2 * k + 1] << 28);
-                o->z.limb[k] = (uint64_t)p.z.v[2 * k] + ((uint64_t)p.z.v[2 * k + 1] << 28);
-                o->t.limb[k] = (uint64_t)p.t.v[2 * k] + ((uint64_t)p.t.v[2 * k + 1] << 28);
-            }
-            ok[2 * i + 1] = ST_OK(good);
         }
         sc c, r, u, v, sB, packed;
         sc_from_abi(c, challenge + i);

@@ -24,7 +24,6 @@ template <class F> struct lane_min_blocks { static constexpr int value = 1; };
 #endif
 template <> struct lane_min_blocks<LaneRlcDecode> { static constexpr int value = DECODE_MIN_BLOCKS; };
 template <> struct lane_min_blocks<LaneEdVerifyDecode> { static constexpr int value = DECODE_MIN_BLOCKS; };
-template <> struct lane_min_blocks<LaneVerifyHalf> { static constexpr int value = DECODE_MIN_BLOCKS; };
 template <> struct lane_min_blocks<LanePtDecode> { static constexpr int value = CODEC_MIN_BLOCKS; };
 template <> struct lane_min_blocks<LanePtEncode> { static constexpr int value = CODEC_MIN_BLOCKS; };
 template <> struct lane_min_blocks<LaneFromHash<false>> { static constexpr int value = CODEC_MIN_BLOCKS; };

@@ -334,8 +334,145 @@ GD void hg_shr1(uint32_t (&a)[N]) {
     for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
     a[N - 1] >>= 1;
 }
+// 62 bits of a starting at bit k (k + 62 <= 448 + 32 is fine: words past the end read as zero)
+GD uint64_t hg_window62(const uint32_t (&a)[SC_WORDS], int k) {
+    const int wi = k >> 5, bs = k & 31;
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) {
+        w0 |= (i == wi) ? a[i] : 0u;
+        w1 |= (i == wi + 1) ? a[i] : 0u;
+        w2 |= (i == wi + 2) ? a[i] : 0u;
+    }
+    uint64_t lo = ((uint64_t)w1 << 32) | w0;
+    if (bs) lo = (lo >> bs) | ((uint64_t)w2 << (64 - bs));
+    return lo & 0x3fffffffffffffffull;
+}
+GD uint64_t hg_mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+// out = |m1 * x - m2 * y| for 32-bit multipliers, where the caller knows which of the two products is the larger one
+// (y_minus_x: out = m2 y - m1 x).  The true result fits N words.
+template <int N>
+GD void hg_submul2(uint32_t (&out)[N], uint32_t m1, const uint32_t (&x)[N], uint32_t m2, const uint32_t (&y)[N], bool y_minus_x) {
+    uint64_t cx = 0, cy = 0;
+    int64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        cx += (uint64_t)m1 * x[i];
+        cy += (uint64_t)m2 * y[i];
+        const uint32_t px = (uint32_t)cx, py = (uint32_t)cy;
+        cx >>= 32; cy >>= 32;
+        borrow += y_minus_x ? (int64_t)py - (int64_t)px : (int64_t)px - (int64_t)py;
+        out[i] = (uint32_t)borrow;
+        borrow >>= 32;
+    }
+}
+// out = m1 * x + m2 * y (fits N words)
+template <int N>
+GD void hg_addmul2(uint32_t (&out)[N], uint32_t m1, const uint32_t (&x)[N], uint32_t m2, const uint32_t (&y)[N]) {
+    uint64_t cx = 0, cy = 0, carry = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        cx += (uint64_t)m1 * x[i];
+        cy += (uint64_t)m2 * y[i];
+        carry += (uint64_t)(uint32_t)cx + (uint32_t)cy;
+        cx >>= 32; cy >>= 32;
+        out[i] = (uint32_t)carry;
+        carry >>= 32;
+    }
+}
+// One exact division step: r0 <- r0 mod r1, t0 <- t0 + (r0 div r1) t1, by shift-and-subtract (quotients are small: 1.5 bits on
+// average), then the roles swap.  Everything statically indexed.
+GD void hg_exact_step(uint32_t (&r0)[SC_WORDS], uint32_t (&r1)[SC_WORDS], uint32_t (&t0)[HG_TW], uint32_t (&t1)[HG_TW]) {
+    uint32_t d[SC_WORDS], td[HG_TW];
+    int s = hg_bitlen(r0) - hg_bitlen(r1);                  /* r0 > r1 throughout, so s >= 0 */
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) d[i] = r1[i];
+#pragma unroll
+    for (int i = 0; i < HG_TW; i++) td[i] = t1[i];
+    hg_shl(d, s);
+    hg_shl(td, s);
+#pragma unroll 1
+    for (; s >= 0; s--) {
+        uint32_t diff[SC_WORDS];
+        int64_t chain = 0;
+#pragma unroll
+        for (int i = 0; i < SC_WORDS; i++) {
+            chain = chain + r0[i] - d[i];
+            diff[i] = (uint32_t)chain;
+            chain >>= 32;
+        }
+        const uint32_t ge = ~(uint32_t)chain;               /* all-ones when r0 >= d */
+#pragma unroll
+        for (int i = 0; i < SC_WORDS; i++) r0[i] = (diff[i] & ge) | (r0[i] & ~ge);
+        uint64_t carry = 0;
+#pragma unroll
+        for (int i = 0; i < HG_TW; i++) {
+            carry = carry + t0[i] + (td[i] & ge);
+            t0[i] = (uint32_t)carry;
+            carry >>= 32;
+        }
+        hg_shr1(d);
+        hg_shr1(td);
+    }
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) { const uint32_t x = r0[i]; r0[i] = r1[i]; r1[i] = x; }
+#pragma unroll
+    for (int i = 0; i < HG_TW; i++) { const uint32_t x = t0[i]; t0[i] = t1[i]; t1[i] = x; }
+}
+// Lehmer's batching (Knuth, TAOCP 4.5.2 Algorithm L): run Euclid on the leading 62 bits (u^, v^) of (r0, r1) with cofactors A, B, C, D
+// for as long as the quotient is the same at both ends of the interval the truncation leaves -- floor((u^ + A)/(v^ + C)) ==
+// floor((u^ + B)/(v^ + D)) -- and the cofactors stay below 2^32, then apply the 2 x 2 matrix to the full numbers: ~18 division steps
+// for four multiply-accumulate passes.  The cofactors are kept as magnitudes; their signs alternate with the parity of the step count
+// (even: A, D > 0 >= B, C; odd: the other way round).  A step is refused when the new remainder could fall below 2^223 (the stopping
+// point must not be jumped over): v' >= 2^k (v^' - |D'|) because the truncated tails weigh in with at most the cofactors.
+// Returns the number of steps taken (0: the caller takes one exact step instead).
+GD int hg_lehmer_batch(uint32_t (&r0)[SC_WORDS], uint32_t (&r1)[SC_WORDS], uint32_t (&t0)[HG_TW], uint32_t (&t1)[HG_TW]) {
+    const int k = hg_bitlen(r0) - 62;                       /* r0 > r1 >= 2^223: k >= 162 */
+    uint64_t uh = hg_window62(r0, k), vh = hg_window62(r1, k);
+    const uint64_t vmin = k >= 223 ? 1ull : ((1ull << (223 - k)) + 1ull);
+    uint64_t A = 1, B = 0, C = 0, D = 1;
+    int steps = 0;
+#pragma unroll 1
+    for (;;) {
+        const bool even = (steps & 1) == 0;
+        const uint64_t n1 = even ? uh + A : uh - A, d1 = even ? vh - C : vh + C;
+        const uint64_t n2 = even ? uh - B : uh + B, d2 = even ? vh + D : vh - D;
+        if (d1 == 0 || d2 == 0) break;
+        uint64_t q;
+        if (n1 < 4 * d1) { q = 0; uint64_t x = n1; while (x >= d1) { x -= d1; q++; } }   /* two quotients in three are below 4 */
+        else q = n1 / d1;
+        if (q >= (1ull << 32)) break;
+        if (hg_mulhi64(q, d2)) break;
+        const uint64_t qd2 = q * d2;
+        if (qd2 > n2 || n2 - qd2 >= d2) break;              /* floor(n2 / d2) != q */
+        const uint64_t Cn = A + q * C, Dn = B + q * D;
+        if (Cn >= (1ull << 32) || Dn >= (1ull << 32)) break;
+        const uint64_t vn = uh - q * vh;
+        if (vn < vmin + Dn) break;
+        A = C; C = Cn; B = D; D = Dn; uh = vh; vh = vn;
+        steps++;
+    }
+    if (steps == 0) return 0;
+    const bool odd = (steps & 1) != 0;
+    uint32_t n0[SC_WORDS], n1w[SC_WORDS], s0[HG_TW], s1[HG_TW];
+    hg_submul2(n0, (uint32_t)A, r0, (uint32_t)B, r1, odd);   /* even: A r0 - B r1 ; odd: B r1 - A r0 */
+    hg_submul2(n1w, (uint32_t)C, r0, (uint32_t)D, r1, !odd); /* even: D r1 - C r0 ; odd: C r0 - D r1 */
+    hg_addmul2(s0, (uint32_t)A, t0, (uint32_t)B, t1);
+    hg_addmul2(s1, (uint32_t)C, t0, (uint32_t)D, t1);
+#pragma unroll
+    for (int i = 0; i < SC_WORDS; i++) { r0[i] = n0[i]; r1[i] = n1w[i]; }
+#pragma unroll
+    for (int i = 0; i < HG_TW; i++) { t0[i] = s0[i]; t1[i] = s1[i]; }
+    return steps;
+}
 GD gmask_t sc_half_gcd(sc &u, sc &v, const sc &c) {
-    uint32_t r0[SC_WORDS], r1[SC_WORDS], d[SC_WORDS], t0[HG_TW], t1[HG_TW], td[HG_TW];
+    uint32_t r0[SC_WORDS], r1[SC_WORDS], t0[HG_TW], t1[HG_TW];
 #pragma unroll
     for (int i = 0; i < SC_WORDS; i++) { r0[i] = sc_q(i); r1[i] = c.w[i]; }
 #pragma unroll
@@ -347,41 +484,9 @@ GD gmask_t sc_half_gcd(sc &u, sc &v, const sc &c) {
 #pragma unroll
         for (int i = 7; i < SC_WORDS; i++) high |= r1[i];
         if (!high) break;
-        int s = hg_bitlen(r0) - hg_bitlen(r1);              /* r0 > r1 throughout, so s >= 0 */
-#pragma unroll
-        for (int i = 0; i < SC_WORDS; i++) d[i] = r1[i];
-#pragma unroll
-        for (int i = 0; i < HG_TW; i++) td[i] = t1[i];
-        hg_shl(d, s);
-        hg_shl(td, s);
-#pragma unroll 1
-        for (; s >= 0; s--) {                               /* r0 = r0 mod r1, t0 += (r0 div r1) t1 */
-            uint32_t diff[SC_WORDS];
-            int64_t chain = 0;
-#pragma unroll
-            for (int i = 0; i < SC_WORDS; i++) {
-                chain = chain + r0[i] - d[i];
-                diff[i] = (uint32_t)chain;
-                chain >>= 32;
-            }
-            const uint32_t ge = ~(uint32_t)chain;           /* all-ones when r0 >= d */
-#pragma unroll
-            for (int i = 0; i < SC_WORDS; i++) r0[i] = (diff[i] & ge) | (r0[i] & ~ge);
-            uint64_t carry = 0;
-#pragma unroll
-            for (int i = 0; i < HG_TW; i++) {
-                carry = carry + t0[i] + (td[i] & ge);
-                t0[i] = (uint32_t)carry;
-                carry >>= 32;
-            }
-            hg_shr1(d);
-            hg_shr1(td);
-        }
-#pragma unroll
-        for (int i = 0; i < SC_WORDS; i++) { const uint32_t x = r0[i]; r0[i] = r1[i]; r1[i] = x; }
-#pragma unroll
-        for (int i = 0; i < HG_TW; i++) { const uint32_t x = t0[i]; t0[i] = t1[i]; t1[i] = x; }
-        neg = ~neg;
+        int steps = hg_lehmer_batch(r0, r1, t0, t1);
+        if (steps == 0) { hg_exact_step(r0, r1, t0, t1); steps = 1; }
+        if (steps & 1) neg = ~neg;
     }
 #pragma unroll
     for (int i = 0; i < SC_WORDS; i++) { u.w[i] = r1[i]; v.w[i] = i < HG_TW ? t1[i] : 0u; }

@@ -274,7 +274,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
         const verify_plan none = {nullptr, nullptr, nullptr, nullptr, nullptr};
         LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, none, 0};
         run(f1, 2 * n);
-        LaneVerifyHalf fh = {pts.data(), ok.data(), chal.data(), resp.data(), sig, none};
+        LaneVerifyHalf fh = {chal.data(), resp.data(), none};
         run(fh, n);
         SlotEdVerifyFinish f3 = {st, pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), slots(2)};
         run_smp(f3, n);
@@ -299,8 +299,10 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     std::vector<uint4> ktabs((size_t)(counts[2] + 1) * KTAB_QUADS);
     LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, plan, n};   /* keys only: R is never decoded on this path */
     run(f1, n);
-    LaneVerifyHalf fh = {pts.data(), ok.data(), chal.data(), resp.data(), sig, plan};   /* stand-alone signatures: R, half-size multipliers */
+    LaneVerifyHalf fh = {chal.data(), resp.data(), plan};   /* stand-alone signatures: half-size multipliers, then their R */
     run(fh, n);
+    LaneEdVerifyDecode fr = {pts.data(), ok.data(), sig, pk, n, plan, 2 * n};
+    run(fr, n);
     SlotKeyTables ft = {pts.data(), ktabs.data(), plan};
     run_smp(ft, counts[2]);
     SlotEdVerifyFinishShared fs = {pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), ktabs.data(), slots(2), plan, sig};

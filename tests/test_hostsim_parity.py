@@ -2,6 +2,8 @@
 assertions on) against the checker and the reference's golden vectors.  No GPU needed."""
 import os
 
+import numpy as np
+
 import parity
 import util
 
@@ -146,3 +148,41 @@ def test_scalar_folding_reduction_fuzz(sim):
         ser = np.stack([util.le(v, ln) for v in vals])
         want = np.stack([util.le(v % util.Q, 56) for v in vals])
         parity.eq(sim.scalar_decode_long(ser, ln), want, "scalar_decode_long by folding, len %d" % ln)
+
+
+def test_half_gcd(sim):
+    """sc_half_gcd (csrc/sc.cuh, decision 15): for every c < q it must return u, v with v c == u (mod q), 0 <= u < 2^223 and
+    0 < |v| < 2^223 -- checked on Python integers for random scalars and for the inputs that stress Lehmer's batching and the stopping
+    rule: all-ones quotients (q times a Fibonacci ratio), c next to q a / b (a huge quotient late in the sequence), c around 2^223 and
+    around every power of two, inverses of 223-bit numbers (a remainder right at the stopping point), 0, 1, q - 1."""
+    import ctypes as C
+    import random
+    Q = util.Q
+    rnd = random.Random(20260917)
+    fa, fb = 1, 1
+    for _ in range(330):
+        fa, fb = fb, fa + fb
+    cs = [0, 1, 2, 3, Q - 1, Q - 2, Q // 2, Q // 2 + 1, Q * fa // fb]
+    for a in range(1, 24):
+        for b in range(a + 1, 25):
+            cs += [Q * a // b, Q * a // b + 1]
+    for k in range(1, 223):
+        cs += [(1 << 223) + (1 << k), (1 << (223 + k % 200)) - 1]
+    for k in range(2, 446):
+        cs += [Q >> k, (Q >> k) + 1, Q - (1 << k)]
+    for _ in range(200):
+        t = rnd.randrange(1 << 222, 1 << 223) | 1
+        cs += [pow(t, -1, Q), rnd.randrange(1 << 223) * pow(t, -1, Q) % Q]
+    cs += [rnd.randrange(Q) for _ in range(20000)]
+    cs = [x % Q for x in cs]
+    n = len(cs)
+    c = np.frombuffer(b"".join(x.to_bytes(56, "little") for x in cs), np.uint8).reshape(n, 56).copy()
+    u = np.zeros((n, 56), np.uint8); v = np.zeros((n, 56), np.uint8); neg = np.zeros(n, np.uint32)
+    sim.lib.hostsim_half_gcd(u.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), neg.ctypes.data_as(C.c_void_p),
+                             c.ctypes.data_as(C.c_void_p), C.c_size_t(n))
+    for i, x in enumerate(cs):
+        uu = int.from_bytes(bytes(u[i]), "little"); vv = int.from_bytes(bytes(v[i]), "little")
+        if neg[i]:
+            vv = -vv
+        assert (vv * x - uu) % Q == 0, "v c != u (mod q) for c = %x" % x
+        assert 0 <= uu < (1 << 223) and 0 < abs(vv) < (1 << 223), "bounds for c = %x: %d / %d bits" % (x, uu.bit_length(), abs(vv).bit_length())

@@ -14,3 +14,4 @@ for k in ('verify_distinct_keys', 'single_calls_from_threads', 'bdsm', 'verify_k
 print(json.dumps(x.get('rlc_sweep_distinct_keys')))
 P
 tail -5 gpurun_out/r02k_bench.err
+python tools/verify_timeline.py --n 524288 --per-key 1 2>&1 | head -12

@@ -10,14 +10,16 @@ CSRC      := libgoldilocks_b200/csrc
 OBJDIR    ?= build/obj
 KERNELS   := $(wildcard $(CSRC)/k_*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(KERNELS)) $(OBJDIR)/abi.o
-HDRS      := $(wildcard $(CSRC)/*.cuh) include/goldilocks_b200.h
+HDRS      := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/goldilocks_b200.h
 LIB       ?= libgoldilocks_b200/libgoldilocks_b200.so
 
 .PHONY: all lib hostsim oracle tools clean
 all: lib hostsim oracle tools
-tools: tools/imad_peak
+tools: tools/imad_peak tools/single_calls
 tools/imad_peak: tools/imad_peak.cu
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
+tools/single_calls: tools/single_calls.cpp $(LIB) include/goldilocks_b200.h
+	$(CXX) -O2 -std=c++17 -pthread -Iinclude -o $@ $< -Llibgoldilocks_b200 -lgoldilocks_b200 -Wl,-rpath,'$$ORIGIN/../libgoldilocks_b200'
 lib: $(LIB)
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS_$*) $(HDRS)

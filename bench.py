@@ -755,6 +755,13 @@ def single_call_leg(lib, sig, pk, arena, off, expect):
     run(8, 2, 0)                                    # warm-up of the one-element shapes
     out = {"alone": run(8, 16, 0), "gathered": run(256, 24, 250), "gathered_64_threads": run(64, 48, 250)}
     out["speedup_gathered_over_alone"] = out["gathered"]["value"] / out["alone"]["value"]
+    exe = os.path.join(ROOT, "tools", "single_calls")          # the same experiment from native threads (no interpreter in the loop)
+    if os.path.exists(exe):
+        try:
+            p = subprocess.run([exe, "1024", "16", "250"], capture_output=True, text=True, timeout=300)
+            out["native_threads"] = json.loads(p.stdout) if p.returncode == 0 else {"failed": p.stderr[-300:]}
+        except Exception as e:  # noqa: BLE001
+            out["native_threads"] = {"failed": type(e).__name__}
     return out
 
 

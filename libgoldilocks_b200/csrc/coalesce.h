@@ -7,9 +7,12 @@
 // launch without the caller changing a line: the first thread to arrive becomes the leader of a gathering, waits up to
 // `window_us` (or until `max_batch` requests are in), runs the batch for everybody on its own thread and hands the
 // results back; threads that arrive meanwhile start the next gathering, so gatherings overlap with running batches.
+// At most `max_inflight` batches run at a time: a batch takes about as long whether it holds 10 or 10 000 elements (one lane's
+// latency), so when the device is busy the next gathering keeps collecting until a running batch returns instead of adding a small
+// batch to the queue -- the batch size adapts to the load, the window only bounds the wait on an idle device.
 //
 // Off by default (window 0): a lone caller would only pay the window as extra latency.  Host-only code, no CUDA types:
-// the gate is exercised on the CPU tier (tests/coalesce_harness.cpp) with a stand-in for the batch call.
+// the gate is exercised on the CPU tier (tests/coalesce/harness.cpp) with a stand-in for the batch call.
 #pragma once
 #include <atomic>
 #include <chrono>
@@ -23,7 +26,8 @@ namespace coalesce {
 
 struct Settings {
     std::atomic<unsigned> window_us{0};      /* 0 = every call runs alone (the default) */
-    std::atomic<unsigned> max_batch{4096};
+    std::atomic<unsigned> max_batch{4096};   /* a gathering this large stops waiting for its window */
+    std::atomic<unsigned> max_inflight{3};   /* batches running at a time (one per context of a device, shard.h LANES) */
 };
 struct Stats {
     std::atomic<unsigned long long> calls{0}, batches{0}, largest{0};
@@ -47,25 +51,33 @@ public:
         }
         gathering_ = true;                                  /* leader of this gathering */
         const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(cfg.window_us.load());
-        while (pending_.size() < cfg.max_batch.load())
-            if (cv_leader_.wait_until(lk, deadline) == std::cv_status::timeout) break;
+        for (;;) {
+            const bool ripe = pending_.size() >= cfg.max_batch.load() || std::chrono::steady_clock::now() >= deadline;
+            if (ripe && inflight_ < cfg.max_inflight.load()) break;
+            if (ripe) cv_leader_.wait(lk);                  /* the device is busy: keep collecting until a batch returns */
+            else cv_leader_.wait_until(lk, deadline);
+        }
         std::vector<Req *> batch;
         batch.swap(pending_);
         gathering_ = false;                                 /* the next arrival leads the next gathering while this batch runs */
+        inflight_++;
         lk.unlock();
         st.batches.fetch_add(1, std::memory_order_relaxed);
         unsigned long long big = st.largest.load(std::memory_order_relaxed);
         while (batch.size() > big && !st.largest.compare_exchange_weak(big, batch.size())) {}
         run(batch.data(), batch.size());
         lk.lock();
+        inflight_--;
         for (Req *q : batch) q->done = true;                /* under the lock: the requests live on their callers' stacks */
         cv_done_.notify_all();
+        cv_leader_.notify_one();                            /* a leader that waits for a free slot */
     }
 private:
     std::mutex mu_;
     std::condition_variable cv_leader_, cv_done_;
     std::vector<Req *> pending_;
     bool gathering_ = false;
+    unsigned inflight_ = 0;
 };
 
 }  // namespace coalesce

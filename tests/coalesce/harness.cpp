@@ -16,10 +16,15 @@ int main(int argc, char **argv) {
     cfg.max_batch.store(argc > 4 ? (unsigned)atoi(argv[4]) : 4096);
     coalesce::Gate<Req> gate;
     std::atomic<unsigned long long> wrong{0}, over{0}, foreign{0};
+    std::atomic<int> running{0}, most_running{0};
     const unsigned maxb = cfg.max_batch.load();
     auto run = [&](Req **q, size_t n) {
         if (n > maxb + (size_t)threads) over++;            /* arrivals between the wake-up and the swap may ride along, never more than one per thread */
+        const int now = ++running;
+        int seen = most_running.load();
+        while (now > seen && !most_running.compare_exchange_weak(seen, now)) {}
         std::this_thread::sleep_for(std::chrono::microseconds(300));
+        --running;
         for (size_t i = 0; i < n; i++) { q[i]->y = 3 * q[i]->x + 1; q[i]->ran_on = std::this_thread::get_id(); }
     };
     std::vector<std::thread> pool;
@@ -33,7 +38,7 @@ int main(int argc, char **argv) {
             }
         });
     for (auto &th : pool) th.join();
-    printf("{\"threads\": %d, \"calls\": %llu, \"batches\": %llu, \"largest\": %llu, \"wrong\": %llu, \"oversized\": %llu, \"served_by_another_thread\": %llu}\n",
-           threads, st.calls.load(), st.batches.load(), st.largest.load(), wrong.load(), over.load(), foreign.load());
+    printf("{\"threads\": %d, \"calls\": %llu, \"batches\": %llu, \"largest\": %llu, \"wrong\": %llu, \"oversized\": %llu, \"served_by_another_thread\": %llu, \"most_batches_at_a_time\": %d}\n",
+           threads, st.calls.load(), st.batches.load(), st.largest.load(), wrong.load(), over.load(), foreign.load(), most_running.load());
     return wrong.load() ? 1 : 0;
 }

@@ -34,13 +34,21 @@ def test_every_call_gets_its_own_result_and_calls_share_batches(harness):
 
 def test_a_lone_caller_is_served_after_the_window(harness):
     r = run(harness, 1, 20, 100, 4096)
-    assert r == {"threads": 1, "calls": 20, "batches": 20, "largest": 1, "wrong": 0, "oversized": 0, "served_by_another_thread": 0}
+    assert r == {"threads": 1, "calls": 20, "batches": 20, "largest": 1, "wrong": 0, "oversized": 0, "served_by_another_thread": 0,
+                 "most_batches_at_a_time": 1}
 
 
 def test_a_full_gathering_does_not_wait_for_the_window(harness):
     # window of 2 s: 8 calls per thread can only finish in time if reaching max_batch ends the wait
     r = run(harness, 8, 8, 2_000_000, 8)
     assert r["wrong"] == 0 and r["oversized"] == 0 and r["batches"] == 8 and r["largest"] == 8
+
+
+def test_a_busy_device_makes_the_batches_larger_not_more_numerous(harness):
+    # 512 callers, window far shorter than a batch: at most three batches run at a time and the gatherings grow instead
+    r = run(harness, 512, 8, 20, 4096)
+    assert r["wrong"] == 0 and r["calls"] == 4096
+    assert r["most_batches_at_a_time"] <= 3 and r["largest"] >= 64 and r["batches"] <= 200, r
 
 
 def test_library_exports_the_switch():

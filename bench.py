@@ -102,7 +102,8 @@ def executed_ops():
            "verify_keyset": j["ed448_verify_keyset"]["_total_imad_wide"],
            "finish_shared": j["ed448_verify_16_per_key"]["SlotEdVerifyFinishShared"]["imad_wide"],
            "finish_alone": j["ed448_verify_distinct_keys"]["SlotEdVerifyFinishShared"]["imad_wide"],
-           "key_table": j["ed448_verify_16_per_key"]["SlotKeyTables"]["imad_wide"] / j["ed448_verify_16_per_key"]["SlotKeyTables"]["lanes_per_unit"]}
+           "key_table": (j["ed448_verify_16_per_key"]["SlotKeyChain"]["imad_wide"] + j["ed448_verify_16_per_key"]["SlotKeyColumns"]["imad_wide"])
+                        / j["ed448_verify_16_per_key"]["SlotKeyChain"]["lanes_per_unit"]}   # per key: the chain has one lane per key
     return ops
 
 

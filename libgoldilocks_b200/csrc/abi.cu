@@ -973,14 +973,17 @@ static size_t verify_core_scratch_bytes(size_t n) {
     if (verify_groups(n)) base += al(group_scratch_bytes(n, verify_tab_cap(n))) + al(verify_tab_cap(n) * KTAB_QUADS * sizeof(uint4));
     return base;
 }
-struct VerifyGrids { int unique = 1, shared = 1, tables = 1; };
+struct VerifyGrids { int unique = 1, shared = 1, chain = 1, columns = 1; };
 static bool verify_grids(Ctx &c, VerifyGrids *g) {
-    return smp_grid<SlotEdVerifyFinish>(c, &g->unique) && smp_grid<SlotEdVerifyFinishShared>(c, &g->shared) && smp_grid<SlotKeyTables>(c, &g->tables);
+    return smp_grid<SlotEdVerifyFinish>(c, &g->unique) && smp_grid<SlotEdVerifyFinishShared>(c, &g->shared) && smp_grid<SlotKeyChain>(c, &g->chain) &&
+           smp_grid<SlotKeyColumns>(c, &g->columns);
 }
 // per-thread window tables of the stand-alone signatures (wtab, slot_algos.cuh): one per resident lane of the finish kernel
 static size_t verify_slot_bytes(const VerifyGrids &g, size_t n) {
-    size_t lanes = (size_t)(g.unique > g.shared ? g.unique : g.shared) * SLOT_BLOCK;
-    const size_t need = (n + SLOT_BLOCK - 1) / SLOT_BLOCK * SLOT_BLOCK;
+    const int grid = std::max(std::max(g.unique, g.shared), g.columns);
+    size_t lanes = (size_t)grid * SLOT_BLOCK;
+    const size_t items = std::max(n, verify_groups(n) ? verify_tab_cap(n) * VSH_CHUNKS : (size_t)0);   /* the column builder has ten items per key table */
+    const size_t need = (items + SLOT_BLOCK - 1) / SLOT_BLOCK * SLOT_BLOCK;
     if (lanes > need) lanes = need;
     return (lanes * 2 * WTAB_QUADS_PER_LANE * sizeof(uint4) + 255) & ~(size_t)255;   /* two tables per lane: the key's and R's (s_verify_half_item) */
 }
@@ -1056,8 +1059,10 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
             if (!launch(c, fr, n, side)) return false;
         }
         CU(cudaEventRecord(side_evt[1], side));
-        SlotKeyTables ft = {pts, ktabs, plan};
-        if (!launch_smp(c, ft, cap, grids.tables, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3], counts[4] = 0, left by the grouping pass */
+        SlotKeyChain fc = {pts, ktabs, plan};           /* the doubling chain: one lane per key table ... */
+        if (!launch_smp(c, fc, cap, grids.chain, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3..5] = 0, left by the grouping pass */
+        SlotKeyColumns ft = {ktabs, slots, plan};       /* ... then ten lanes per key fill its ten column tables */
+        if (!launch_smp(c, ft, cap * VSH_CHUNKS, grids.columns, s, const_cast<uint32_t *>(plan.counts) + 5)) return false;
         CU(cudaStreamWaitEvent(s, side_evt[1], 0));
         if (feed) { CU(cudaStreamWaitEvent(s, feed->ready[0], 0)); CU(cudaStreamWaitEvent(s, feed->ready[1], 0)); } /* the finish kernel reads the signature bytes too */
         SlotEdVerifyFinishShared fs = {pts, ok, chal, resp, c.wide, ktabs, slots, plan, sig};
@@ -1078,8 +1083,10 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
         }
     }
     if (plan.unique_sig) {
-        SlotKeyTables ft = {pts, ktabs, plan};
-        if (!launch_smp(c, ft, cap, grids.tables, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3], counts[4] = 0, left by the grouping pass */
+        SlotKeyChain fc = {pts, ktabs, plan};           /* the doubling chain: one lane per key table ... */
+        if (!launch_smp(c, fc, cap, grids.chain, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3..5] = 0, left by the grouping pass */
+        SlotKeyColumns ft = {ktabs, slots, plan};       /* ... then ten lanes per key fill its ten column tables */
+        if (!launch_smp(c, ft, cap * VSH_CHUNKS, grids.columns, s, const_cast<uint32_t *>(plan.counts) + 5)) return false;
         SlotEdVerifyFinishShared fs = {pts, ok, chal, resp, c.wide, ktabs, slots, plan, sig};
         if (!launch_smp(c, fs, n, grids.shared, s, const_cast<uint32_t *>(plan.counts) + 3)) return false;
         LaneVerifySign fv = {status, (verify_aux *)(pts + 1), 2, n};    /* aux record of signature i = the R half of pts[2i..2i+1] */
@@ -1105,7 +1112,7 @@ goldilocks_error_t goldilocks_ed448_verify_batch(goldilocks_error_t *status, con
     int32_t *dst = k.out<int32_t>(n);
     VerifyGrids grids;
     if (k.ok) k.ok = verify_grids(*k.c, &grids);
-    const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
+    const int grid = std::max(std::max(grids.unique, grids.shared), grids.columns);
     uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 2);
     void *scratch = k.alloc(verify_core_scratch_bytes(n));
     VerifyFeed feed = {n >= 2 * VERIFY_GROUP_MIN ? n / 2 : n, {nullptr, nullptr}};
@@ -1207,7 +1214,7 @@ static bool rlc_core(Call &k, int32_t *dst, const uint8_t *dsig, const uint8_t *
     auto ordinary_on = [&](int32_t *st, const uint8_t *sig, const uint8_t *pk, const uint8_t *msg, const size_t *off, size_t cnt) {
         VerifyGrids grids;
         if (!verify_grids(c, &grids)) return false;
-        const int grid = grids.unique > grids.shared ? grids.unique : grids.shared;
+        const int grid = std::max(std::max(grids.unique, grids.shared), grids.columns);
         uint4 *slots = k.slots((size_t)grid * SLOT_BLOCK, 2);
         void *scratch = k.alloc(verify_core_scratch_bytes(cnt));
         if (!k.ok) return false;

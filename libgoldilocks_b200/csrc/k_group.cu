@@ -72,7 +72,7 @@ __global__ void k_lists(uint32_t *shared_sig, uint32_t *shared_tab, uint32_t *un
     else unique_sig[j - pos[j]] = is[j];
     if (j == n - 1) {
         const uint32_t ns = pos[j] + adm[j], nt = tslot[g] + sflag[g];
-        counts[0] = ns; counts[1] = n - ns; counts[2] = nt < cap ? nt : cap; counts[3] = 0; counts[4] = 0;
+        counts[0] = ns; counts[1] = n - ns; counts[2] = nt < cap ? nt : cap; counts[3] = 0; counts[4] = 0; counts[5] = 0;
     }
 }
 struct Layout {

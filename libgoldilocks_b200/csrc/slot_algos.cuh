@@ -366,6 +366,47 @@ GD void s_build_key_tables(sref sb, const wtab<1> &t) {
         s_pt_double(p, w, false);
     }
 }
+// The same tables in two steps, for batches (verify_dev): the doubling chain is inherently serial -- one lane per key -- but the ten
+// column tables are independent once their base points A_c exist, so they are built by ten lanes per key.
+//   step 1 (s_key_column_bases): A_c = 2^(45c) A for c = 0..9, parked as raw X, Y, Z, T in the LAST entry of column c
+//   step 2 (s_build_key_column): one lane per (key, column) loads A_c and fills the column's 16 entries (the parked point is
+//          overwritten last); pniels(2 A_c), which the builder reads back, goes to the lane's own scratch table.
+GD void s_key_column_bases(sref sb, const wtab<1> &t) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int c = 0; c < VSH_CHUNKS; c++) {
+        const int park = c * WINDOW_NTABLE + WINDOW_NTABLE - 1;
+        s_stg<1>(t.coord(park, 0), p.x); s_stg<1>(t.coord(park, 1), p.y); s_stg<1>(t.coord(park, 2), p.z); s_stg<1>(t.coord(park, 3), p.t);
+        if (c == VSH_CHUNKS - 1) break;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int j = 0; j < VSH_SHIFT - 1; j++) s_pt_double(p, w, true);
+        s_pt_double(p, w, false);
+    }
+}
+GD void s_build_key_column(sref sb, const wtab<1> &t, int c, const wtab<1> &scratch) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    wtab<1> tc;
+    tc.base = t.base + (size_t)c * WINDOW_NTABLE * 16;
+    const int park = WINDOW_NTABLE - 1;
+    s_ldg<1>(p.x, tc.coord(park, 0)); s_ldg<1>(p.y, tc.coord(park, 1)); s_ldg<1>(p.z, tc.coord(park, 2)); s_ldg<1>(p.t, tc.coord(park, 3));
+    s_pt_to_pniels_negc_g<1>(tc, 0, p, w);
+    s_pt_double(p, w, false);
+    s_pt_to_pniels_negc_g<1>(scratch, 0, p, w);               /* pniels(2 A_c) */
+    s_pt_add_pniels_g<1>(p, w, tc, 0, 0, ~0u, false);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 1; i < WINDOW_NTABLE; i++) {
+        s_pt_to_pniels_negc_g<1>(tc, i, p, w);
+        if (i != WINDOW_NTABLE - 1) s_pt_add_pniels_g<1>(p, w, scratch, 0, 0, ~0u, false);
+    }
+}
 // combo (slots 0..3) = scalar1*B + scalar2*A with A's tables in `kt`; `wide4` = the four init-time tables.
 GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide4, const wtab<1> &kt) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};

@@ -175,6 +175,27 @@ struct SlotKeyTables {
         s_build_key_tables(sb, ktab_of(ktabs, t));
     }
 };
+// The same tables in two launches (slot_algos.cuh s_key_column_bases / s_build_key_column): one lane per key walks the doubling
+// chain, then one lane per (key, column) -- work item 10 t + c -- fills a column.
+struct SlotKeyChain {
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    const abi_pt *pts; uint4 *ktabs; verify_plan plan;
+    GDM void operator()(size_t t, sref sb, size_t slot) const {
+        (void)slot;
+        if (t >= plan.counts[2]) return;
+        s_pt_from_abi(sb, pts + 2 * (size_t)plan.tab_rep[t]);
+        s_key_column_bases(sb, ktab_of(ktabs, t));
+    }
+};
+struct SlotKeyColumns {
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    uint4 *ktabs; uint4 *scratch; verify_plan plan;
+    GDM void operator()(size_t item, sref sb, size_t slot) const {
+        const size_t t = item / VSH_CHUNKS;
+        if (t >= plan.counts[2]) return;
+        s_build_key_column(sb, ktab_of(ktabs, t), (int)(item % VSH_CHUNKS), wtab_of<1>(scratch, slot));
+    }
+};
 // The finish kernel of a grouped batch.  Work items [0, counts[1]) are the stand-alone signatures, verified exactly like
 // SlotEdVerifyFinish (own window table in `scratch`); items [counts[1], counts[1] + counts[0]) are signatures whose
 // public key (byte-identical) occurs more than once: the multiples of the key come from the table its group built.

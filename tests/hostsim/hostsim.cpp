@@ -283,7 +283,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     /* the key-grouping pass of k_group.cu restated on the host: byte-identical keys that occur at least twice share a table */
     std::map<std::string, std::vector<uint32_t>> groups;
     for (size_t i = 0; i < n; i++) groups[std::string((const char *)pk + 57 * i, 57)].push_back((uint32_t)i);
-    std::vector<uint32_t> shared_sig, shared_tab, unique_sig, tab_rep, counts(4);
+    std::vector<uint32_t> shared_sig, shared_tab, unique_sig, tab_rep, counts(8);
     const size_t cap = n / 4 + 1;
     for (auto &g : groups) {
         if (g.second.size() >= 2 && tab_rep.size() < cap) {
@@ -303,8 +303,10 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     run(fh, n);
     LaneEdVerifyDecode fr = {pts.data(), ok.data(), sig, pk, n, plan, 2 * n};
     run(fr, n);
-    SlotKeyTables ft = {pts.data(), ktabs.data(), plan};
-    run_smp(ft, counts[2]);
+    SlotKeyChain fc = {pts.data(), ktabs.data(), plan};
+    run_smp(fc, counts[2]);
+    SlotKeyColumns ft = {ktabs.data(), slots(2), plan};
+    run_smp(ft, (size_t)counts[2] * VSH_CHUNKS);
     SlotEdVerifyFinishShared fs = {pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), ktabs.data(), slots(2), plan, sig};
     run_smp(fs, (size_t)counts[0] + counts[1]);
     LaneVerifySign fv = {st, (verify_aux *)(pts.data() + 1), 2, n};

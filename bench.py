@@ -675,6 +675,73 @@ def run_ours(args):
         lib.rlc_policy(16)
         del q_sig, q_pk, q_msg, q_off
 
+    # ---- extra.two_batches_in_flight: the same step with TWO batches in flight -- the device-pointer entry point on two streams with two scratch
+    # areas, and the host-pointer entry point from two host threads (the library deals them two of its three contexts per device) ----------
+    if not args.no_extra:
+        s_a, s_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        d_st2, d_scratch2 = torch.empty_like(d_st), torch.empty_like(d_scratch)
+        lanes2 = ((d_st, d_scratch, s_a), (d_st2, d_scratch2, s_b))
+
+        def step2(i):
+            st, scr, strm = lanes2[i & 1]
+            with torch.cuda.stream(strm):
+                eng.ed448_verify(st, d_sig, d_pk, d_msg, d_off, scr)
+
+        d_st.zero_(); d_st2.zero_()
+        torch.cuda.synchronize()
+        for i in range(4):
+            step2(i)
+        torch.cuda.synchronize()
+        assert (d_st.cpu().numpy() == expect).all() and (d_st2.cpu().numpy() == expect).all(), "two batches in flight: statuses"
+        k2 = 2 * max(2, K // 2)
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        cur = torch.cuda.current_stream()
+        a2.record()
+        s_a.wait_stream(cur); s_b.wait_stream(cur)
+        for i in range(k2):
+            step2(i)
+        cur.wait_stream(s_a); cur.wait_stream(s_b)
+        b2.record()
+        barrier()
+        t2 = max_over_ranks(a2.elapsed_time(b2) / 1e3 / k2)
+        h_st2 = torch.empty(n, dtype=torch.int32).pin_memory()
+        argv2 = list(argv); argv2[0] = C.c_void_p(h_st2.data_ptr())
+        ke2 = max(2, min(K, 5))
+        h_st.zero_(); h_st2.zero_()
+
+        gate = threading.Barrier(3)
+
+        def caller(av):
+            assert fn(*av) == -1                    # first call of this thread: its context of the device allocates its arena
+            assert fn(*av) == -1
+            gate.wait()
+            gate.wait()                             # the main thread has taken the start time
+            for _ in range(ke2):
+                assert fn(*av) == -1
+
+        th2 = [threading.Thread(target=caller, args=(av,)) for av in (argv, argv2)]
+        for x in th2:
+            x.start()
+        gate.wait()
+        barrier()
+        t0 = time.perf_counter()
+        gate.wait()
+        for x in th2:
+            x.join()
+        torch.cuda.synchronize()
+        t2e = max_over_ranks((time.perf_counter() - t0) / (2 * ke2))
+        assert (h_st.numpy() == expect).all() and (h_st2.numpy() == expect).all(), "two host threads: statuses"
+        barrier()
+        extra["two_batches_in_flight"] = {
+            "value": world * n / t2, "unit": UNIT, "ms_per_step": t2 * 1e3, "steps": k2, "step_frac_executed": executed_step / t2 / 1e9 / peak,
+            "api": "goldilocks_ed448_verify_batch_dev on two streams, each with its own scratch and status array (same inputs)",
+            "e2e": {"value": world * n / t2e, "unit": UNIT, "ms_per_step": t2e * 1e3, "calls": 2 * ke2,
+                    "api": "goldilocks_ed448_verify_batch (host pointers, pinned) from two host threads, each on its own status array"},
+            "note": "the headline `value` and `e2e` run one batch at a time; with a second batch in flight the latency-bound phases of one (key grouping, decodes, "
+                    "the doubling chain of the key tables, copies) run beside the finish kernel of the other"}
+        del d_st2, d_scratch2
+
     # ---- extra.single_calls_from_threads: the reference's own one-signature call from a pool of host threads, gathered or not -------
     if not args.no_extra:
         barrier()

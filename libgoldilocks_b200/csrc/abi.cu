@@ -1508,6 +1508,8 @@ goldilocks_error_t goldilocks_b200_keyset_create(goldilocks_b200_keyset **out, c
         int grid = k.smp_grid_for<SlotKeysetTables>();
         SlotKeysetTables ft = {pts, ks->ktabs};
         k.run_smp(ft, m, grid);
+        LaneKeysetNormalize fn = {ks->ktabs};           /* affine entries: the set pays one inversion per column once, every call saves a multiplication per addition */
+        k.run(fn, m * VSH_CHUNKS);
     }
     goldilocks_error_t r = k.finish();
     if (!ok || r != GOLDILOCKS_SUCCESS) {

@@ -408,6 +408,8 @@ GD void s_build_key_column(sref sb, const wtab<1> &t, int c, const wtab<1> &scra
     }
 }
 // combo (slots 0..3) = scalar1*B + scalar2*A with A's tables in `kt`; `wide4` = the four init-time tables.
+// AFFINE: the entries have been divided by their z (key sets, LaneKeysetNormalize): 7 multiplications per addition instead of 8.
+template <bool AFFINE = false>
 GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide4, const wtab<1> &kt) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
     const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
@@ -439,7 +441,9 @@ GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const
             uint32_t bits2 = sc_window5(s2x, k * WINDOW_BITS);
             const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
             bits2 ^= inv2;
-            s_pt_add_pniels_g<1>(p, w, kt, c * WINDOW_NTABLE + (int)(bits2 & (WINDOW_NTABLE - 1)), inv2, ~inv2, row_ends && !last_fixed);
+            const int e2 = c * WINDOW_NTABLE + (int)(bits2 & (WINDOW_NTABLE - 1));
+            if (AFFINE) s_pt_add_niels_g<1>(p, w, kt.coord(e2, 0), kt.coord(e2, 1), kt.coord(e2, 2), inv2, ~inv2, row_ends && !last_fixed);
+            else s_pt_add_pniels_g<1>(p, w, kt, e2, inv2, ~inv2, row_ends && !last_fixed);
             if (fixed_here) {
                 uint32_t bits1 = sc_bits(s1x, k * WINDOW_BITS, WIDE_BITS);
                 const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);

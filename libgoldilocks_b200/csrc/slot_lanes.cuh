@@ -245,6 +245,44 @@ struct SlotKeysetTables { /* one lane per key: decoded key t -> table t */
         s_build_key_tables(sb, ktab_of(ktabs, t));
     }
 };
+// A key set's tables serve many calls, so their entries are made affine once: niels = pniels.n / pniels.z (goldilocks.c:280-288 has
+// z = 2Z; the reference normalises its fixed-base tables the same way, precompute in goldilocks.c:765-815).  One lane per (key, column):
+// Montgomery's trick over the column's 16 entries, one inversion.  Every addition under the key then costs 7 multiplications, not 8.
+struct LaneKeysetNormalize {
+    uint4 *ktabs;
+    GDM void operator()(size_t item) const {
+        const wtab<1> kt = ktab_of(ktabs, item / VSH_CHUNKS);
+        const int e0 = (int)(item % VSH_CHUNKS) * WINDOW_NTABLE;
+        gf pre[WINDOW_NTABLE], acc, z, zi, x;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int e = 0; e < WINDOW_NTABLE; e++) {
+            gq_ld<false, 1>(z, kt.coord(e0 + e, 3));
+            if (e == 0) gf_copy(acc, z);
+            else gf_mul(acc, acc, z);
+            gf_copy(pre[e], acc);
+        }
+        gf_invert(acc, acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int e = WINDOW_NTABLE - 1; e >= 0; e--) {
+            if (e > 0) gf_mul(zi, acc, pre[e - 1]);          /* 1 / z_e */
+            else gf_copy(zi, acc);
+            gq_ld<false, 1>(z, kt.coord(e0 + e, 3));
+            gf_mul(acc, acc, z);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int j = 0; j < 3; j++) {
+                gq_ld<false, 1>(x, kt.coord(e0 + e, j));
+                gf_mul(x, x, zi);
+                gq_st<1>(kt.coord(e0 + e, j), x);
+            }
+        }
+    }
+};
 struct SlotEdVerifyFinishKeyset { /* signature i under key key_index[i] of the set */
     static constexpr int NSLOTS = BDSM_NSLOTS;
     verify_aux *aux; const int32_t *key_ok; const abi_sc *challenge, *response; const niels *wide; const uint4 *ktabs;
@@ -260,7 +298,7 @@ struct SlotEdVerifyFinishKeyset { /* signature i under key key_index[i] of the s
         sc c, r;
         sc_from_abi(c, challenge + i);
         sc_from_abi(r, response + i);
-        s_verify_shared_key(sb, r, c, wide, ktab_of(const_cast<uint4 *>(ktabs), t));
+        s_verify_shared_key<true>(sb, r, c, wide, ktab_of(const_cast<uint4 *>(ktabs), t));   /* affine entries */
         s_bdsm_quirk(sb, c);
         s_verify_accept_prep(aux + i, sb, sig + 114 * i, (gmask_t)key_ok[t]);
     }

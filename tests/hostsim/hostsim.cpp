@@ -246,6 +246,8 @@ EXPORT int32_t goldilocks_b200_keyset_create(hostsim_keyset **out, const uint8_t
     run(fd, m);
     SlotKeysetTables ft = {pts.data(), ks->ktabs.data()};
     run_smp(ft, m);
+    LaneKeysetNormalize fn = {ks->ktabs.data()};
+    run(fn, m * VSH_CHUNKS);
     *out = ks;
     return -1;
 }

@@ -57,7 +57,6 @@ template <> struct slot_min_blocks<SlotDoubleScalarmul> { static constexpr int v
 template <> struct slot_min_blocks<SlotEdVerifyFinish> { static constexpr int value = 4; }; /* 3 blocks (no spills): 111.7 vs 110.9 ms */
 template <> struct slot_min_blocks<SlotBaseDoubleScalarmul> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotEdVerifyFinishShared> { static constexpr int value = 4; };
-template <> struct slot_min_blocks<SlotKeyTables> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotKeyChain> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotKeyColumns> { static constexpr int value = 4; };
 template <> struct slot_min_blocks<SlotRlcBucket> { static constexpr int value = 4; };
@@ -112,7 +111,7 @@ cudaError_t launch_sm_persist(const F &f, size_t n, int grid, cudaStream_t s, un
 #define LANES_SM(X) X(SlotNielsDebug) X(SlotX448) X(SlotComb) X(SlotCombTable) X(SlotX448DerivePk) X(SlotEdDerivePk) X(SlotEdSignR) X(SlotRlcBucket)
 #define INSTANTIATE_SM(F) template cudaError_t launch_sm<F>(const F &, size_t, cudaStream_t);
 #define DECLARE_SM(F) extern INSTANTIATE_SM(F)
-#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotEdVerifyFinishShared) X(SlotKeyTables) X(SlotKeyChain) X(SlotKeyColumns) X(SlotKeysetTables) X(SlotEdVerifyFinishKeyset) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul) X(SlotDualScalarmul) X(SlotDirectScalarmul)
+#define LANES_SMP(X) X(SlotEdVerifyFinish) X(SlotEdVerifyFinishShared) X(SlotKeyChain) X(SlotKeyColumns) X(SlotKeysetTables) X(SlotEdVerifyFinishKeyset) X(SlotBaseDoubleScalarmul) X(SlotScalarmul) X(SlotDoubleScalarmul) X(SlotDualScalarmul) X(SlotDirectScalarmul)
 #define INSTANTIATE_SMP(F)                                                                          \
     template cudaError_t sm_configure<F>(int *);                                                    \
     template cudaError_t launch_sm_persist<F>(const F &, size_t, int, cudaStream_t, unsigned *);

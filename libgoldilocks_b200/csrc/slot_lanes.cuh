@@ -164,18 +164,7 @@ struct SlotEdVerifyFinish {
         status[i] = ST_OK(eq & (gmask_t)ok[2 * i] & (gmask_t)ok[2 * i + 1]);
     }
 };
-// One lane per key table: the decoded public key of the group's representative signature -> its column tables.
-struct SlotKeyTables {
-    static constexpr int NSLOTS = BDSM_NSLOTS;
-    const abi_pt *pts; uint4 *ktabs; verify_plan plan;
-    GDM void operator()(size_t t, sref sb, size_t slot) const {
-        (void)slot;
-        if (t >= plan.counts[2]) return;
-        s_pt_from_abi(sb, pts + 2 * (size_t)plan.tab_rep[t]);
-        s_build_key_tables(sb, ktab_of(ktabs, t));
-    }
-};
-// The same tables in two launches (slot_algos.cuh s_key_column_bases / s_build_key_column): one lane per key walks the doubling
+// The per-key tables of a batch, in two launches (slot_algos.cuh s_key_column_bases / s_build_key_column): one lane per key walks the doubling
 // chain, then one lane per (key, column) -- work item 10 t + c -- fills a column.
 struct SlotKeyChain {
     static constexpr int NSLOTS = BDSM_NSLOTS;

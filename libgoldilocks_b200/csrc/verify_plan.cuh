@@ -3,13 +3,13 @@
 #include <stddef.h>
 #include <stdint.h>
 // Signatures whose 57 public-key bytes occur at least twice in the batch are verified against one per-key table
-// (SlotKeyTables / SlotEdVerifyFinishShared); everything else goes through SlotEdVerifyFinish on its own.
+// (SlotKeyChain + SlotKeyColumns / SlotEdVerifyFinishShared); everything else goes through SlotEdVerifyFinish on its own.
 //   shared_sig[j], shared_tab[j] : signature index and key-table index of the j-th table-path signature, ordered so
 //                                  that signatures under one key are adjacent lanes (their table rows stay in L1/L2)
 //   unique_sig[j]                : signature index of the j-th stand-alone signature
 //   tab_rep[t]                   : a signature whose public key is key t (its decoded point seeds the table)
 //   counts[0..2]                 : number of table-path signatures, stand-alone signatures, key tables;
-//                                  counts[3] = counts[4] = 0: work counters of the finish / key-table kernels' dynamic hand-out
+//                                  counts[3..5] = 0: work counters of the finish / key-chain / key-column kernels' dynamic hand-out
 // A null unique_sig means "no plan: every signature, in order, stand-alone".
 struct verify_plan {
     const uint32_t *shared_sig, *shared_tab, *unique_sig, *tab_rep, *counts;

@@ -278,6 +278,7 @@ GOLDILOCKS_B200_API void goldilocks_b200_rlc_policy(unsigned reprobe);
  * independent, so with window_us > 0 the first caller of a kind waits up to window_us microseconds (or until max_batch calls
  * are in; 0 = 4096) for others, runs ONE batch launch for all of them on its own thread and current device, and every caller
  * gets exactly the result its own call would have produced.  Calls that differ in (prehashed, context) are batched separately.
+ * At most three gathered batches run at a time; while the device is that busy a gathering keeps collecting, so batches grow with the load.
  * window_us = 0 (the default) turns it off: a lone caller would only pay the window as latency.  The environment variables
  * GOLDILOCKS_B200_COALESCE_US / GOLDILOCKS_B200_COALESCE_MAX set the same thing for unmodified programs.
  * goldilocks_b200_coalesce_stats: calls that went through a gathering, batches launched for them, largest batch (any may be NULL). */

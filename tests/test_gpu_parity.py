@@ -770,3 +770,40 @@ def test_single_calls_from_many_threads_are_gathered(gpu, chk):
     assert batches - batches0 < (calls - calls0) // 3 and largest >= 4, (calls - calls0, batches - batches0, largest)
     # switched off again: a call runs alone and still answers
     assert gpu.ed448_verify_one(sig[0], pk[0], msgs[0]) == -1 and gpu.coalesce_stats()[0] == calls
+
+
+def test_two_verifications_in_flight_on_two_streams(gpu, chk):
+    """goldilocks_ed448_verify_batch_dev writes only into the caller's scratch, so two calls on two streams -- each with its own scratch and
+    status array, one over a batch of repeated keys, one over distinct keys (half-size stand-alone path) -- may overlap freely and must
+    both give the reference's statuses, call after call"""
+    import torch
+    from libgoldilocks_b200.engine import DeviceEngine
+    from libgoldilocks_b200.capi import pack_messages
+    eng = DeviceEngine()
+    dev = torch.device("cuda")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    jobs = []
+    for label, n, per in (("2s/shared", 6000, 12), ("2s/distinct", 5000, 1)):
+        nk = (n + per - 1) // per
+        sk = stream_bytes(label + "/sk", nk * 57).reshape(nk, 57)[np.arange(n) // per]
+        pk = chk.ed448_derive_public_key(sk)
+        msgs = [bytes(stream_bytes(label + "/m%d" % i, i % 40)) for i in range(n)]
+        sig = chk.ed448_sign(sk, pk, msgs)
+        sig[::5, 90] ^= 4
+        arena, off = pack_messages(msgs)
+        want = chk.ed448_verify(sig, pk, msgs)
+        assert (want == 0).sum() == (n + 4) // 5
+        jobs.append({"want": want, "st": torch.zeros(n, dtype=torch.int32, device=dev), "args": (t(sig.reshape(-1)), t(pk.reshape(-1)), t(arena), t(np.asarray(off).view(np.int64))),
+                     "scratch": torch.empty(eng.verify_scratch_bytes(n), dtype=torch.uint8, device=dev), "stream": torch.cuda.Stream(device=dev)})
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for j in jobs:
+            j["st"].zero_()
+        torch.cuda.synchronize()
+        for _ in range(2):                                           # back to back on each stream, interleaved across the two
+            for j in jobs:
+                with torch.cuda.stream(j["stream"]):
+                    eng.ed448_verify(j["st"], *j["args"], j["scratch"])
+        torch.cuda.synchronize()
+        for j in jobs:
+            parity.eq(j["st"].cpu().numpy(), j["want"], "verify_batch_dev statuses with two calls in flight, round %d" % rep)

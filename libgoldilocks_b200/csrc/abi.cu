@@ -52,7 +52,7 @@ struct Ctx {
     cudaEvent_t dev_evt[2] = {nullptr, nullptr};
     std::mutex dev_side_mu;
     fixed_tables *ft = nullptr;
-    niels *wide = nullptr;       // WIDE_TABLES x 16384-entry verification tables: odd multiples of 2^(45c) B (30 MB, L2 resident)
+    niels *wide = nullptr;       // WIDE_TABLES x WIDE_ENTRIES verification tables: odd multiples of 2^(18m) B (25 x 131072 x 192 B = 629 MB, algos.cuh)
     std::vector<Block> blocks;   // arena blocks; blocks.back() is the active one
     size_t used = 0;             // bytes used in the active block
     void *slot_scratch = nullptr;

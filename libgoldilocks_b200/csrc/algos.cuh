@@ -18,15 +18,21 @@
 #define WNAF_FIXED_ENTRIES 32                 /* goldilocks.c:29: odd multiples 1B..63B */
 #define WINDOW_BITS 5                         /* goldilocks.c:28 */
 #define WINDOW_NTABLE 16
-/* Verification-only fixed-base table: odd multiples 1B,3B,...,(2^15-1)B as canonical affine niels
- * (16384 x 192 B = 3 MB, L2 resident).  Public indices only -- never used on a secret scalar. */
-#define WIDE_BITS 15
+/* Verification-only fixed-base tables: the recoded scalar's 450 bits are WIDE_TABLES signed WIDE_BITS-bit digits, digit m looked up
+ * in table m = odd multiples (2e+1) 2^(WIDE_BITS m) B as canonical affine niels, so scalar1 * B costs WIDE_TABLES additions and NO
+ * doublings wherever it is added.  25 tables x 131072 entries x 192 B = 629 MB of HBM per device (the reads are random and miss the L2
+ * either way: the per-key tables stream through it).  Public indices only -- never used on a secret scalar.
+ * WIDE_BITS 15 / 30 digits (tables at the 45-bit column bases, digits added inside the rows) was the scheme up to build r02q. */
+#ifndef WIDE_BITS
+#define WIDE_BITS 18
+#endif
 #define WIDE_ENTRIES (1 << (WIDE_BITS - 1))
-#define WIDE_LANES 128                         /* lanes that build one table at init */
+#define WIDE_TABLES ((450 + WIDE_BITS - 1) / WIDE_BITS)
+#define WIDE_LANES 1024                        /* lanes that build one table at init */
 #define WIDE_PER_LANE (WIDE_ENTRIES / WIDE_LANES)
 /* Verification under a REPEATED public key splits both scalars into VSH_CHUNKS columns of VSH_ROWS
- * 5-bit digits: digit k = VSH_ROWS*c + r is served by tables of 2^(45c)*A (built once per key) and 2^(45c)*B
- * (wide tables 1..9, built at init next to table 0), so one signature costs 8*5 doublings instead of 89*5.
+ * 5-bit digits: digit k = VSH_ROWS*c + r is served by tables of 2^(45c)*A (built once per key); the fixed base comes from the
+ * doubling-free wide tables above, so one signature costs 8*5 doublings instead of 89*5.
  * Measured on the bench corpus (16 signatures per key), finish + key tables: 4 x 23 -> 50.7 + 5.3 ms, 6 x 15 -> 41.3 + 6.3,
  * 10 x 9 -> 36.0 + 7.8, 15 x 6 -> 34.0 + 9.6 (and 62 KB per key); 10 x 9 is never worse than 6 x 15 from 4 signatures per key on. */
 #ifndef VSH_CHUNKS
@@ -34,7 +40,6 @@
 #define VSH_ROWS 9
 #endif
 #define VSH_SHIFT (VSH_ROWS * WINDOW_BITS)     /* bits between columns */
-#define WIDE_TABLES VSH_CHUNKS
 
 /* Doubling-free fixed-base table of the batched comb kernel: the reference's signed comb generalised to
  * (n, t, s) = (90, 5, 1) -- 90 rows of 16 canonical affine niels, row j = {(16 +- 8 +- 4 +- 2 +- 1) 2^(5j) B}.
@@ -211,10 +216,10 @@ GD void window_double_scalarmul(pt &a, const pt &b, const sc &scalarb, const pt 
 // resulting group element is observable (the projective representative is not part of the
 // contract), so the GPU uses a warp-uniform schedule instead: both scalars are
 // recoded with the constant-time paths' signed-digit recoding: scalar2 into 90 odd 5-bit digits,
-// scalar1 into 30 odd 15-bit digits.  Every lane does, per 5-bit window, 5 doublings + one
-// variable-base add (direct index into its own 16-pniels table) and, on every third window, one
-// fixed-base add (direct index into the shared 16384-entry table of odd multiples of B): 445
-// doublings + 90 + 30 additions, against the reference's expected 444 + 75 + 56.  Indices are
+// scalar1 into 25 odd 18-bit digits.  Every lane does, per 5-bit window, 5 doublings + one
+// variable-base add (direct index into its own 16-pniels table) and, after the last window, 25
+// fixed-base adds (direct indices into the init-time tables of odd multiples of 2^(18m) B): 445
+// doublings + 90 + 25 additions, against the reference's expected 444 + 75 + 56.  Indices are
 // public, so lookups are plain loads.
 // ---------------------------------------------------------------------------------------------
 // Implementation: s_base_double_scalarmul (slot_algos.cuh).
@@ -298,20 +303,22 @@ GD void build_wnaf_base(niels *out32, const pt &base) {
 // (2e+1)B.  `tmp`/`pre` are global scratch (one pniels / one gf per entry).  Start point from the
 // comb table, then repeated +2B; normalised with one inversion per lane (Montgomery's trick).
 GD void build_wide_lane(niels *out, pniels *tmp, gf *pre, const niels *comb, int lane_all) {
-    const int c = lane_all / WIDE_LANES, lane = lane_all % WIDE_LANES;   /* table c holds multiples of 2^(VSH_SHIFT c) B */
+    const int c = lane_all / WIDE_LANES, lane = lane_all % WIDE_LANES;   /* table c holds multiples of 2^(WIDE_BITS c) B */
     out += (size_t)c * WIDE_ENTRIES; tmp += (size_t)c * WIDE_ENTRIES; pre += (size_t)c * WIDE_ENTRIES;
     pt twob, p;
     sc start, two;
-    sc_set_zero(start);
-    sc_set_zero(two);
-    {   /* (2 e0 + 1) << (VSH_SHIFT c) and 2 << (VSH_SHIFT c): both far below q, no reduction needed */
-        const uint64_t odd = 2u * (uint32_t)(WIDE_PER_LANE * lane) + 1u;
-        const int sh = VSH_SHIFT * c, word = sh / 32, bit = sh % 32;
-        const uint64_t lo = odd << bit;                    /* odd < 2^15, bit < 32 */
-        start.w[word] = (uint32_t)lo;
-        const uint64_t t2 = (uint64_t)2 << bit;
-        two.w[word] = (uint32_t)t2;
-        if (word + 1 < SC_WORDS) { start.w[word + 1] = (uint32_t)(lo >> 32); two.w[word + 1] = (uint32_t)(t2 >> 32); }
+    {   /* (2 e0 + 1) 2^(WIDE_BITS c) and 2 * 2^(WIDE_BITS c) mod q: the top table's multiples pass q (2^450 > q) */
+        sc odd, pw;
+        sc_set_zero(odd);
+        sc_set_zero(pw);
+        odd.w[0] = 2u * (uint32_t)(WIDE_PER_LANE * lane) + 1u;
+        const int sh = WIDE_BITS * c;                      /* <= 432: 2^sh itself is below q */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < SC_WORDS; i++) pw.w[i] = (i == sh / 32) ? (1u << (sh % 32)) : 0u;
+        sc_mul(start, odd, pw);
+        sc_add(two, pw, pw);
     }
     comb_scalarmul(twob, comb, two);
     comb_scalarmul(p, comb, start);

@@ -225,6 +225,21 @@ GD void s_pt_set_identity(const spt &p) {
     gf_set_ui(v, 1); s_st(p.y, v); s_st(p.z, v);
 }
 
+// p += scalar1 * B for the recoded scalar s1x (sc_recode_signed): its WIDE_TABLES signed WIDE_BITS-bit digits against the init-time
+// tables of odd multiples of 2^(WIDE_BITS m) B (algos.cuh) -- additions only, no doublings.  T of the result only on request.
+GD void s_add_fixed_base(const spt &p, const swk &w, const sc &s1x, const niels *wide, bool need_t) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int m = 0; m < WIDE_TABLES; m++) {
+        uint32_t bits1 = sc_bits(s1x, m * WIDE_BITS, WIDE_BITS);
+        const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
+        bits1 ^= inv1;
+        const niels *e = wide + (size_t)m * WIDE_ENTRIES + (bits1 & (WIDE_ENTRIES - 1));
+        s_pt_add_niels_g<1>(p, w, gq(&e->a), gq(&e->b), gq(&e->c), inv1, inv1, m == WIDE_TABLES - 1 && !need_t);
+    }
+}
+
 #define BDSM_NSLOTS 7
 // combo = scalar1*B + scalar2*base2 for PUBLIC inputs, warp-uniform schedule -- see the comment on
 // "combo = scalar1*B + scalar2*base2" in algos.cuh, which defines the digits and the tables.
@@ -243,7 +258,6 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
 #endif
     for (int k = 89; k >= 0; k--) {
         const int i = k * WINDOW_BITS;
-        const bool fixed_here = (k % 3) == 0;           /* 15-bit fixed-base digit starts at this bit */
         if (k != 89) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -254,15 +268,9 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
         uint32_t bits2 = sc_window5(s2x, i);
         const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
         bits2 ^= inv2;
-        s_pt_add_pniels_g<1>(p, w, multiples, (int)(bits2 & (WINDOW_NTABLE - 1)), inv2, ~inv2, !fixed_here && k != 0);
-        if (fixed_here) {
-            uint32_t bits1 = sc_bits(s1x, i, WIDE_BITS);
-            const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
-            bits1 ^= inv1;
-            const niels *e = wide_base + (bits1 & (WIDE_ENTRIES - 1));
-            s_pt_add_niels_g<1>(p, w, gq(&e->a), gq(&e->b), gq(&e->c), inv1, inv1, k != 0);
-        }
+        s_pt_add_pniels_g<1>(p, w, multiples, (int)(bits2 & (WINDOW_NTABLE - 1)), inv2, ~inv2, k != 0);
     }
+    s_add_fixed_base(p, w, s1x, wide_base, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,8 +278,8 @@ GD void s_base_double_scalarmul(sref sb, const sc &scalar1, const sc &scalar2, c
 //     slots 0..3  <-  sB * B  +  u * A  -+  |v| * R          (sB = v s mod q,  v c == u mod q,  u, |v| < 2^223),
 // which is the identity of the quotient group exactly when combo == R there (v is a unit mod q and the quotient group has
 // prime order q; goldilocks.c:644-653 point_eq is equality in that group).  u and |v| are 45 signed 5-bit digits each
-// (sc_half_bias), so there are 44 x 5 doublings instead of 89 x 5; the 30 signed 15-bit digits of the full-size sB go to the
-// init-time tables of B (digits 0..14) and of 2^225 B (digits 15..29, column table 5 of the shared-key path).
+// (sc_half_bias), so there are 44 x 5 doublings instead of 89 x 5; the full-size sB goes to the doubling-free init-time tables
+// of the fixed base (s_add_fixed_base).
 // Window tables: entry e = (e + 1) P for e = 0..15, entry 16 = the identity (digit 0) -- 15 additions per table.
 // ---------------------------------------------------------------------------------------------
 template <int QS>
@@ -294,7 +302,6 @@ GD void s_pt_add_signed_digit(const spt &p, const swk &w, const wtab<1> &t, uint
     const gmask_t neg = (d < 0 ? ~0u : 0u) ^ flip;
     s_pt_add_pniels_g<1>(p, w, t, mag ? (int)mag - 1 : WINDOW_NTABLE, neg, ~neg, before_double);
 }
-#define HALF_WIDE_COLUMN 5 /* 2^225 B = B_5 of the shared-key path's column tables (45 bits per column) */
 // On entry ta and tr hold the window tables of A and R; ub, vb are the biased multipliers (sc_half_bias), v_neg the sign of v.
 GD void s_verify_half(sref sb, const sc &sB, const sc &ub, const sc &vb, gmask_t v_neg, const niels *wide, const wtab<1> &ta, const wtab<1> &tr) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
@@ -306,7 +313,6 @@ GD void s_verify_half(sref sb, const sc &sB, const sc &ub, const sc &vb, gmask_t
 #pragma unroll 1
 #endif
     for (int k = HALF_WINDOWS - 1; k >= 0; k--) {
-        const bool fixed_here = (k % 3) == 0;
         if (k != HALF_WINDOWS - 1) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -315,30 +321,20 @@ GD void s_verify_half(sref sb, const sc &sB, const sc &ub, const sc &vb, gmask_t
             s_pt_double(p, w, false);
         }
         s_pt_add_signed_digit(p, w, ta, sc_window5(ub, k * WINDOW_BITS), 0, false);
-        s_pt_add_signed_digit(p, w, tr, sc_window5(vb, k * WINDOW_BITS), ~v_neg, !fixed_here && k != 0);   /* - v R */
-        if (fixed_here) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-            for (int half = 0; half < 2; half++) {
-                uint32_t bits1 = sc_bits(s1x, (k + (half ? HALF_WINDOWS : 0)) * WINDOW_BITS, WIDE_BITS);
-                const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
-                bits1 ^= inv1;
-                const niels *e = wide + (half ? (size_t)HALF_WIDE_COLUMN * WIDE_ENTRIES : 0) + (bits1 & (WIDE_ENTRIES - 1));
-                s_pt_add_niels_g<1>(p, w, gq(&e->a), gq(&e->b), gq(&e->c), inv1, inv1, half == 1 && k != 0);
-            }
-        }
+        s_pt_add_signed_digit(p, w, tr, sc_window5(vb, k * WINDOW_BITS), ~v_neg, k != 0);   /* - v R */
     }
+    s_add_fixed_base(p, w, s1x, wide, false);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Verification under a repeated public key (same group element as s_base_double_scalarmul).
-// The 90 signed 5-bit digits d_k of scalar2 and the 30 signed 15-bit digits e_m of scalar1 (the very recoding
-// above) are regrouped by column: k = R c + r with R = VSH_ROWS (9) rows and VSH_CHUNKS (10) columns, so
-//     combo = sum_r 2^(5r) * ( sum_c d_(Rc+r) * A_c  +  sum_{c : 3 | Rc+r} e_((Rc+r)/3) * B_c ),
+// The 90 signed 5-bit digits d_k of scalar2 (the very recoding above) are regrouped by column: k = R c + r with
+// R = VSH_ROWS (9) rows and VSH_CHUNKS (10) columns, so
+//     combo = sum_r 2^(5r) * sum_c d_(Rc+r) * A_c   +   scalar1 * B,
 // with A_c = 2^(5Rc) A from a table built ONCE PER KEY (s_build_key_tables: 9 x 45 doublings + ten
-// 16-entry tables of odd multiples, shared read-only by every signature under that key) and B_c = 2^(5Rc) B from
-// the init-time wide tables.  One signature then costs 8 x 5 doublings + 90 + 30 additions.
+// 16-entry tables of odd multiples, shared read-only by every signature under that key) and scalar1 * B from the
+// doubling-free init-time tables (s_add_fixed_base: 25 signed 18-bit digits).  One signature then costs 8 x 5 doublings
+// + 90 + 25 additions.
 // Table layout: KTAB_ENTRIES pniels, entry 16c + e = (2e+1) A_c; the last two entries are build scratch.
 // ---------------------------------------------------------------------------------------------
 #define KTAB_ENTRIES (VSH_CHUNKS * WINDOW_NTABLE + 2)
@@ -407,10 +403,10 @@ GD void s_build_key_column(sref sb, const wtab<1> &t, int c, const wtab<1> &scra
         if (i != WINDOW_NTABLE - 1) s_pt_add_pniels_g<1>(p, w, scratch, 0, 0, ~0u, false);
     }
 }
-// combo (slots 0..3) = scalar1*B + scalar2*A with A's tables in `kt`; `wide4` = the four init-time tables.
+// combo (slots 0..3) = scalar1*B + scalar2*A with A's tables in `kt`; `wide` = the init-time tables of the fixed base.
 // AFFINE: the entries have been divided by their z (key sets, LaneKeysetNormalize): 7 multiplications per addition instead of 8.
 template <bool AFFINE = false>
-GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide4, const wtab<1> &kt) {
+GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide, const wtab<1> &kt) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
     const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
     sc s1x, s2x;
@@ -429,30 +425,22 @@ GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const
             s_pt_double(p, w, false);
         }
         const int last_k = (VSH_CHUNKS - 1) * VSH_ROWS + r <= 89 ? (VSH_CHUNKS - 1) * VSH_ROWS + r : (VSH_CHUNKS - 2) * VSH_ROWS + r; /* last column with a digit in this row */
-        const bool last_fixed = (last_k % 3) == 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
         for (int c = 0; c < VSH_CHUNKS; c++) {
             const int k = VSH_ROWS * c + r;
             if (k > 89) break;
-            const bool fixed_here = (k % 3) == 0;
             const bool row_ends = r != 0 && k == last_k;    /* a doubling follows: T is not needed */
             uint32_t bits2 = sc_window5(s2x, k * WINDOW_BITS);
             const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
             bits2 ^= inv2;
             const int e2 = c * WINDOW_NTABLE + (int)(bits2 & (WINDOW_NTABLE - 1));
-            if (AFFINE) s_pt_add_niels_g<1>(p, w, kt.coord(e2, 0), kt.coord(e2, 1), kt.coord(e2, 2), inv2, ~inv2, row_ends && !last_fixed);
-            else s_pt_add_pniels_g<1>(p, w, kt, e2, inv2, ~inv2, row_ends && !last_fixed);
-            if (fixed_here) {
-                uint32_t bits1 = sc_bits(s1x, k * WINDOW_BITS, WIDE_BITS);
-                const gmask_t inv1 = (gmask_t)((int32_t)(bits1 >> (WIDE_BITS - 1)) - 1);
-                bits1 ^= inv1;
-                const niels *e = wide4 + (size_t)c * WIDE_ENTRIES + (bits1 & (WIDE_ENTRIES - 1));
-                s_pt_add_niels_g<1>(p, w, gq(&e->a), gq(&e->b), gq(&e->c), inv1, inv1, row_ends);
-            }
+            if (AFFINE) s_pt_add_niels_g<1>(p, w, kt.coord(e2, 0), kt.coord(e2, 1), kt.coord(e2, 2), inv2, ~inv2, row_ends);
+            else s_pt_add_pniels_g<1>(p, w, kt, e2, inv2, ~inv2, row_ends);
         }
     }
+    s_add_fixed_base(p, w, s1x, wide, false);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -113,7 +113,11 @@ static niels *wide_table() {
         w = (niels *)aligned_alloc(64, sizeof(niels) * WIDE_ENTRIES * WIDE_TABLES);
         std::vector<pniels> tmp(WIDE_ENTRIES * WIDE_TABLES);
         std::vector<gf> pre(WIDE_ENTRIES * WIDE_TABLES);
-        for (int lane = 0; lane < WIDE_LANES * WIDE_TABLES; lane++) build_wide_lane(w, tmp.data(), pre.data(), tables()->comb, lane);
+        LaneBuildWide fw = {w, tmp.data(), pre.data(), tables()};   /* 3.3 M entries: every core, whatever hostsim_set_threads says */
+        const int keep = g_threads;
+        g_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+        run(fw, (size_t)WIDE_LANES * WIDE_TABLES);
+        g_threads = keep;
     }
     return w;
 }

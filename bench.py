@@ -99,7 +99,7 @@ def executed_ops():
            "sign": j["ed448_sign"]["_total_imad_wide"] + shared_inv, "derive_public_key": j["ed448_derive_public_key"]["_total_imad_wide"] + shared_inv,
            "point_scalarmul": j["point_scalarmul"]["_total_imad_wide"], "bdsm": j["base_double_scalarmul_non_secret"]["_total_imad_wide"],
            "verify_16_per_key": j["ed448_verify_16_per_key"]["_total_imad_wide"], "verify_distinct": j["ed448_verify_distinct_keys"]["_total_imad_wide"],
-           "verify_keyset": j["ed448_verify_keyset"]["_total_imad_wide"],
+           "verify_keyset": j["ed448_verify_keyset"]["_total_imad_wide"], "verify_keyset_compact": j["ed448_verify_keyset_compact"]["_total_imad_wide"],
            "finish_shared": j["ed448_verify_16_per_key"]["SlotEdVerifyFinishShared"]["imad_wide"],
            "finish_alone": j["ed448_verify_distinct_keys"]["SlotEdVerifyFinishShared"]["imad_wide"],
            "key_table": (j["ed448_verify_16_per_key"]["SlotKeyChain"]["imad_wide"] + j["ed448_verify_16_per_key"]["SlotKeyColumns"]["imad_wide"])
@@ -567,25 +567,33 @@ def run_ours(args):
         keys = pk2d[1::16].copy()                                  # entry 16j + 1 is never corrupted: the intact key of group j
         changed = idx8[(pk2d[idx8] != keys[idx8 // 16]).any(axis=1)]   # make_corpus kind 3: the key bytes of these entries were changed
         expect_ks = expect.copy(); expect_ks[changed] = -1         # under the key SET they verify against the intact key
-        handle = lib.keyset_create(keys)
         h_idx = pinned((np.arange(n, dtype=np.uint32) // 16).astype(np.uint32))
         fk = lib.lib.goldilocks_ed448_verify_keyset_batch
         fk.restype = C.c_int32
-        argk = [C.c_void_p(h_st.data_ptr()), handle, C.c_void_p(h_idx.data_ptr()), C.c_void_p(h_sig.data_ptr()), C.c_void_p(h_msg.data_ptr()),
-                C.c_void_p(h_off.data_ptr()), C.c_uint8(0), None, C.c_uint8(0), C.c_size_t(n)]
-        for _ in range(2):
-            assert fk(*argk) == -1
-        assert (h_st.numpy() == expect_ks).all(), "key-set verify disagrees with the expected accept bits"
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(kx):
-            assert fk(*argk) == -1
-        torch.cuda.synchronize()
-        t = max_over_ranks((time.perf_counter() - t0) / kx)
-        barrier()
-        lib.keyset_destroy(handle)
-        extra["verify_keyset_e2e"] = entry(n, t, "verify_keyset", unit=UNIT, keys_in_set=int(nk),
-                                           api="goldilocks_ed448_verify_keyset_batch (host pointers, pinned; tables of the key set built once, not timed)")
+        # both table layouts (goldilocks_b200_keyset_policy): flat = a table per digit position, 369 KB per key, no doublings per signature
+        # (the default for a set of 2^16 keys: 24 GB); compact = ten columns, 41 KB per key, forty doublings per signature
+        for name, opkey, policy, what in (("verify_keyset_e2e", "verify_keyset", 32 << 30, "flat tables: 369 KB per key, additions only"),
+                                          ("verify_keyset_compact_e2e", "verify_keyset_compact", 0, "compact tables: 41 KB per key")):
+            lib.keyset_policy(policy)
+            t_create = time.perf_counter()
+            handle = lib.keyset_create(keys)
+            t_create = time.perf_counter() - t_create
+            lib.keyset_policy(32 << 30)
+            argk = [C.c_void_p(h_st.data_ptr()), handle, C.c_void_p(h_idx.data_ptr()), C.c_void_p(h_sig.data_ptr()), C.c_void_p(h_msg.data_ptr()),
+                    C.c_void_p(h_off.data_ptr()), C.c_uint8(0), None, C.c_uint8(0), C.c_size_t(n)]
+            for _ in range(2):
+                assert fk(*argk) == -1
+            assert (h_st.numpy() == expect_ks).all(), "key-set verify (%s) disagrees with the expected accept bits" % name
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(kx):
+                assert fk(*argk) == -1
+            torch.cuda.synchronize()
+            t = max_over_ranks((time.perf_counter() - t0) / kx)
+            barrier()
+            lib.keyset_destroy(handle)
+            extra[name] = entry(n, t, opkey, unit=UNIT, keys_in_set=int(nk), layout=what, keyset_create_ms=t_create * 1e3,
+                                api="goldilocks_ed448_verify_keyset_batch (host pointers, pinned; tables of the key set built once, not timed)")
 
     # ---- extra: random-linear-combination batch verification, host pointers: all-valid corpus of the bench shape, and a
     #      sweep of corruption rates -- a bad signature sends only its chunk to the per-signature path -----------------------------------

@@ -253,6 +253,10 @@ typedef struct goldilocks_b200_keyset_s goldilocks_b200_keyset;
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_b200_keyset_create(goldilocks_b200_keyset **keyset, const uint8_t *pubkeys /*m*57*/, size_t m);
 GOLDILOCKS_B200_API void goldilocks_b200_keyset_destroy(goldilocks_b200_keyset *keyset);
 GOLDILOCKS_B200_API size_t goldilocks_b200_keyset_size(const goldilocks_b200_keyset *keyset);
+/* Table layout of the key sets created from now on: a set whose FLAT tables -- 369 KB per key, one 16-entry table of affine multiples per
+ * digit position, so a signature under the key costs additions only and no doubling -- fit max_table_bytes gets them (default 32 GB:
+ * sets of up to 93 000 keys); larger sets keep the 41 KB per key layout (ten columns, forty doublings per signature).  0 = never flat. */
+GOLDILOCKS_B200_API void goldilocks_b200_keyset_policy(unsigned long long max_table_bytes);
 GOLDILOCKS_B200_API goldilocks_error_t goldilocks_ed448_verify_keyset_batch(goldilocks_error_t *status, const goldilocks_b200_keyset *keyset, const uint32_t *key_index /*n*/, const uint8_t *signature /*n*114*/, const uint8_t *msg, const size_t *msg_off /*n+1*/, uint8_t prehashed, const uint8_t *context, uint8_t context_len, size_t n);
 /* Random-linear-combination batch verification (csrc/rlc.cuh): an OPTIONAL fast path for batches in which
  * (nearly) every signature is expected to be valid.  Same arguments and per-element statuses as

@@ -347,6 +347,11 @@ class BatchLib:
         self._call("goldilocks_ed448_verify_rlc_batch", st, sig, pk, arena, off, C.c_uint8(1 if prehashed else 0), ctx, C.c_uint8(ctx_len), _Z(len(sig)), C.byref(fast))
         return st, fast.value
 
+    def keyset_policy(self, max_table_bytes):
+        """goldilocks_b200_keyset_policy: key sets whose flat tables (369 KB per key, no doublings per signature) fit this many bytes get them"""
+        self.lib.goldilocks_b200_keyset_policy.restype = None
+        self.lib.goldilocks_b200_keyset_policy(C.c_ulonglong(max_table_bytes))
+
     def rlc_policy(self, reprobe):
         """goldilocks_b200_rlc_policy: how many calls skip the batch equation after one in which most chunks failed (0 = never skip)"""
         self.lib.goldilocks_b200_rlc_policy.restype = None

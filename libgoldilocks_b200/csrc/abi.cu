@@ -1489,27 +1489,42 @@ struct goldilocks_b200_keyset_s {
     int dev; size_t m;
     uint8_t *pk;      /* m x 57 key bytes (the challenge hashes them) */
     int32_t *key_ok;  /* decode status per key */
-    uint4 *ktabs;     /* m tables of KTAB_QUADS quads */
+    uint4 *ktabs;     /* m tables of KTAB_QUADS quads (10 columns x 9 rows), or of KSET_QUADS (flat: a column per digit position) */
+    bool flat;
 };
+/* A set whose flat tables (369 KB per key) fit this many bytes gets them; larger sets keep the 41 KB layout (goldilocks_b200_keyset_policy) */
+std::atomic<unsigned long long> g_keyset_flat_bytes{32ull << 30};
+void goldilocks_b200_keyset_policy(unsigned long long max_table_bytes) { g_keyset_flat_bytes.store(max_table_bytes); }
 goldilocks_error_t goldilocks_b200_keyset_create(goldilocks_b200_keyset **out, const uint8_t *pubkeys, size_t m) {
     if (!out) return GOLDILOCKS_FAILURE;
     *out = nullptr;
     Call k;
     if (!k.ok) return k.finish();
-    goldilocks_b200_keyset_s *ks = new goldilocks_b200_keyset_s{k.c->dev, m, nullptr, nullptr, nullptr};
     const size_t mm = m ? m : 1;
+    const bool flat = (unsigned long long)mm * KSET_QUADS * sizeof(uint4) <= g_keyset_flat_bytes.load();
+    goldilocks_b200_keyset_s *ks = new goldilocks_b200_keyset_s{k.c->dev, m, nullptr, nullptr, nullptr, flat};
     bool ok = cudaMalloc(&ks->pk, 57 * mm) == cudaSuccess && cudaMalloc(&ks->key_ok, sizeof(int32_t) * mm) == cudaSuccess &&
-              cudaMalloc(&ks->ktabs, mm * KTAB_QUADS * sizeof(uint4)) == cudaSuccess;
+              cudaMalloc(&ks->ktabs, mm * (flat ? KSET_QUADS : KTAB_QUADS) * sizeof(uint4)) == cudaSuccess;
     if (ok && m) {
         ok = cudaMemcpyAsync(ks->pk, pubkeys, 57 * m, cudaMemcpyHostToDevice, k.c->stream) == cudaSuccess;
         abi_pt *pts = k.out<abi_pt>(m);
         LaneDecodeEddsa fd = {pts, ks->key_ok, ks->pk};
         k.run(fd, m);
-        int grid = k.smp_grid_for<SlotKeysetTables>();
-        SlotKeysetTables ft = {pts, ks->ktabs};
-        k.run_smp(ft, m, grid);
-        LaneKeysetNormalize fn = {ks->ktabs};           /* affine entries: the set pays one inversion per column once, every call saves a multiplication per addition */
-        k.run(fn, m * VSH_CHUNKS);
+        if (flat) {
+            int grid = k.smp_grid_for<SlotKeysetChain>();
+            SlotKeysetChain fc = {pts, ks->ktabs};
+            k.run_smp(fc, m, grid);
+            grid = k.smp_grid_for<SlotKeysetColumns>();
+            SlotKeysetColumns fcol = {ks->ktabs, k.slots((size_t)grid * SLOT_BLOCK, 1)};
+            k.run_smp(fcol, m * KSET_COLS, grid);
+        } else {
+            int grid = k.smp_grid_for<SlotKeysetTables>();
+            SlotKeysetTables ft = {pts, ks->ktabs};
+            k.run_smp(ft, m, grid);
+        }
+        /* affine entries: the set pays one inversion per column once, every call saves a multiplication per addition */
+        LaneKeysetNormalize fn = {ks->ktabs, flat ? (uint32_t)KSET_COLS : (uint32_t)VSH_CHUNKS, flat ? (uint32_t)KSET_QUADS : (uint32_t)KTAB_QUADS};
+        k.run(fn, m * (flat ? KSET_COLS : VSH_CHUNKS));
     }
     goldilocks_error_t r = k.finish();
     if (!ok || r != GOLDILOCKS_SUCCESS) {
@@ -1546,10 +1561,16 @@ goldilocks_error_t goldilocks_ed448_verify_keyset_batch(goldilocks_error_t *stat
     abi_sc *chal = k.out<abi_sc>(n), *resp = k.out<abi_sc>(n);
     LaneEdVerifyScalars f2 = {chal, resp, dsig, ks->pk, dmsg, doff, prehashed, dctx, context_len, 0, dki, (uint32_t)ks->m};
     k.run(f2, n);
-    int grid = k.smp_grid_for<SlotEdVerifyFinishKeyset>();
     verify_aux *aux = k.out<verify_aux>(n);
-    SlotEdVerifyFinishKeyset f3 = {aux, ks->key_ok, chal, resp, k.ok ? k.c->wide : nullptr, ks->ktabs, dki, (uint32_t)ks->m, dsig};
-    k.run_smp(f3, n, grid);
+    if (ks->flat) {
+        int grid = k.smp_grid_for<SlotEdVerifyFinishKeysetFlat>();
+        SlotEdVerifyFinishKeysetFlat f3 = {aux, ks->key_ok, chal, resp, k.ok ? k.c->wide : nullptr, ks->ktabs, dki, (uint32_t)ks->m, dsig};
+        k.run_smp(f3, n, grid);
+    } else {
+        int grid = k.smp_grid_for<SlotEdVerifyFinishKeyset>();
+        SlotEdVerifyFinishKeyset f3 = {aux, ks->key_ok, chal, resp, k.ok ? k.c->wide : nullptr, ks->ktabs, dki, (uint32_t)ks->m, dsig};
+        k.run_smp(f3, n, grid);
+    }
     LaneVerifySign fv = {dst, aux, 1, n};
     k.run(fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH);
     k.fetch((int32_t *)status, dst, n);

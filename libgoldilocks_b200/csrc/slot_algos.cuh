@@ -367,20 +367,20 @@ GD void s_build_key_tables(sref sb, const wtab<1> &t) {
 //   step 1 (s_key_column_bases): A_c = 2^(45c) A for c = 0..9, parked as raw X, Y, Z, T in the LAST entry of column c
 //   step 2 (s_build_key_column): one lane per (key, column) loads A_c and fills the column's 16 entries (the parked point is
 //          overwritten last); pniels(2 A_c), which the builder reads back, goes to the lane's own scratch table.
-GD void s_key_column_bases(sref sb, const wtab<1> &t) {
+GD void s_key_column_bases(sref sb, const wtab<1> &t, int ncols = VSH_CHUNKS, int shift = VSH_SHIFT) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
     const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int c = 0; c < VSH_CHUNKS; c++) {
+    for (int c = 0; c < ncols; c++) {
         const int park = c * WINDOW_NTABLE + WINDOW_NTABLE - 1;
         s_stg<1>(t.coord(park, 0), p.x); s_stg<1>(t.coord(park, 1), p.y); s_stg<1>(t.coord(park, 2), p.z); s_stg<1>(t.coord(park, 3), p.t);
-        if (c == VSH_CHUNKS - 1) break;
+        if (c == ncols - 1) break;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-        for (int j = 0; j < VSH_SHIFT - 1; j++) s_pt_double(p, w, true);
+        for (int j = 0; j < shift - 1; j++) s_pt_double(p, w, true);
         s_pt_double(p, w, false);
     }
 }
@@ -402,6 +402,31 @@ GD void s_build_key_column(sref sb, const wtab<1> &t, int c, const wtab<1> &scra
         s_pt_to_pniels_negc_g<1>(tc, i, p, w);
         if (i != WINDOW_NTABLE - 1) s_pt_add_pniels_g<1>(p, w, scratch, 0, 0, ~0u, false);
     }
+}
+// Key sets, flat layout (goldilocks_b200_keyset_policy): a key that serves many calls can afford a table PER DIGIT POSITION -- 90 columns
+// of 16 affine entries, entry 16 k + e = (2e+1) 2^(5k) A, 369 KB per key -- and then a signature under it costs 90 + 25 additions and not
+// one doubling: what decision 17 does for the fixed base, done for the key.
+#define KSET_COLS 90
+#define KSET_QUADS (KSET_COLS * WINDOW_NTABLE * 16)
+GD wtab<1> kset_of(uint4 *ktabs, size_t table) { wtab<1> t; t.base = ktabs + table * KSET_QUADS; return t; }
+GD void s_verify_flat_key(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide, const wtab<1> &kt) {
+    const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
+    const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
+    sc s1x, s2x;
+    sc_recode_signed(s1x, scalar1);
+    sc_recode_signed(s2x, scalar2);
+    s_pt_set_identity(p);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 0; k < KSET_COLS; k++) {
+        uint32_t bits2 = sc_window5(s2x, k * WINDOW_BITS);
+        const gmask_t inv2 = (gmask_t)((int32_t)(bits2 >> (WINDOW_BITS - 1)) - 1);
+        bits2 ^= inv2;
+        const int e2 = k * WINDOW_NTABLE + (int)(bits2 & (WINDOW_NTABLE - 1));
+        s_pt_add_niels_g<1>(p, w, kt.coord(e2, 0), kt.coord(e2, 1), kt.coord(e2, 2), inv2, ~inv2, false);
+    }
+    s_add_fixed_base(p, w, s1x, wide, false);
 }
 // combo (slots 0..3) = scalar1*B + scalar2*A with A's tables in `kt`; `wide` = the init-time tables of the fixed base.
 // AFFINE: the entries have been divided by their z (key sets, LaneKeysetNormalize): 7 multiplications per addition instead of 8.

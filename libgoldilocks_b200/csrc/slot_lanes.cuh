@@ -238,10 +238,11 @@ struct SlotKeysetTables { /* one lane per key: decoded key t -> table t */
 // z = 2Z; the reference normalises its fixed-base tables the same way, precompute in goldilocks.c:765-815).  One lane per (key, column):
 // Montgomery's trick over the column's 16 entries, one inversion.  Every addition under the key then costs 7 multiplications, not 8.
 struct LaneKeysetNormalize {
-    uint4 *ktabs;
+    uint4 *ktabs; uint32_t ncols, quads_per_key;       /* 10 columns of KTAB_QUADS, or the flat layout's 90 of KSET_QUADS */
     GDM void operator()(size_t item) const {
-        const wtab<1> kt = ktab_of(ktabs, item / VSH_CHUNKS);
-        const int e0 = (int)(item % VSH_CHUNKS) * WINDOW_NTABLE;
+        wtab<1> kt;
+        kt.base = ktabs + (item / ncols) * (size_t)quads_per_key;
+        const int e0 = (int)(item % ncols) * WINDOW_NTABLE;
         gf pre[WINDOW_NTABLE], acc, z, zi, x;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -270,6 +271,44 @@ struct LaneKeysetNormalize {
                 gq_st<1>(kt.coord(e0 + e, j), x);
             }
         }
+    }
+};
+// The flat layout of a key set (slot_algos.cuh s_verify_flat_key): chain of 89 x 5 doublings per key, one lane per (key, digit position)
+// for the 90 column tables, then the same normalisation.
+struct SlotKeysetChain {
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    const abi_pt *pts; uint4 *ktabs;
+    GDM void operator()(size_t t, sref sb, size_t slot) const {
+        (void)slot;
+        s_pt_from_abi(sb, pts + t);
+        s_key_column_bases(sb, kset_of(ktabs, t), KSET_COLS, WINDOW_BITS);
+    }
+};
+struct SlotKeysetColumns {
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    uint4 *ktabs; uint4 *scratch;
+    GDM void operator()(size_t item, sref sb, size_t slot) const {
+        s_build_key_column(sb, kset_of(ktabs, item / KSET_COLS), (int)(item % KSET_COLS), wtab_of<1>(scratch, slot));
+    }
+};
+struct SlotEdVerifyFinishKeysetFlat { /* signature i under key key_index[i] of a flat-layout set: no doublings */
+    static constexpr int NSLOTS = BDSM_NSLOTS;
+    verify_aux *aux; const int32_t *key_ok; const abi_sc *challenge, *response; const niels *wide; const uint4 *ktabs;
+    const uint32_t *key_index; uint32_t n_keys; const uint8_t *sig;
+    GDM void operator()(size_t i, sref sb, size_t slot) const {
+        (void)slot;
+        const uint32_t t = key_index[i];
+        if (t >= n_keys) { /* no such key: FAILURE */
+            abi_gf one = {{1, 0, 0, 0, 0, 0, 0, 0}};
+            aux[i].gd = one; aux[i].h = one; aux[i].flags = 0;
+            return;
+        }
+        sc c, r;
+        sc_from_abi(c, challenge + i);
+        sc_from_abi(r, response + i);
+        s_verify_flat_key(sb, r, c, wide, kset_of(const_cast<uint4 *>(ktabs), t));
+        s_bdsm_quirk(sb, c);
+        s_verify_accept_prep(aux + i, sb, sig + 114 * i, (gmask_t)key_ok[t]);
     }
 };
 struct SlotEdVerifyFinishKeyset { /* signature i under key key_index[i] of the set */

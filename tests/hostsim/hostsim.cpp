@@ -242,16 +242,27 @@ EXPORT int32_t goldilocks_ed448_sign_batch(uint8_t *sig, const uint8_t *sk, cons
     return -1;
 }
 // key sets (include/goldilocks_b200.h): same functors, host memory
-struct hostsim_keyset { size_t m; std::vector<uint8_t> pk; std::vector<int32_t> key_ok; std::vector<uint4> ktabs; };
+struct hostsim_keyset { size_t m; std::vector<uint8_t> pk; std::vector<int32_t> key_ok; std::vector<uint4> ktabs; bool flat; };
+static unsigned long long g_keyset_flat_bytes = 32ull << 30;
+EXPORT void goldilocks_b200_keyset_policy(unsigned long long max_table_bytes) { g_keyset_flat_bytes = max_table_bytes; }
 EXPORT int32_t goldilocks_b200_keyset_create(hostsim_keyset **out, const uint8_t *pubkeys, size_t m) {
-    hostsim_keyset *ks = new hostsim_keyset{m, std::vector<uint8_t>(pubkeys, pubkeys + 57 * m), std::vector<int32_t>(m + 1), std::vector<uint4>((m + 1) * KTAB_QUADS)};
+    const bool flat = (unsigned long long)(m ? m : 1) * KSET_QUADS * sizeof(uint4) <= g_keyset_flat_bytes;
+    hostsim_keyset *ks = new hostsim_keyset{m, std::vector<uint8_t>(pubkeys, pubkeys + 57 * m), std::vector<int32_t>(m + 1),
+                                            std::vector<uint4>((m + 1) * (size_t)(flat ? KSET_QUADS : KTAB_QUADS)), flat};
     std::vector<abi_pt> pts(m + 1);
     LaneDecodeEddsa fd = {pts.data(), ks->key_ok.data(), ks->pk.data()};
     run(fd, m);
-    SlotKeysetTables ft = {pts.data(), ks->ktabs.data()};
-    run_smp(ft, m);
-    LaneKeysetNormalize fn = {ks->ktabs.data()};
-    run(fn, m * VSH_CHUNKS);
+    if (flat) {
+        SlotKeysetChain fc = {pts.data(), ks->ktabs.data()};
+        run_smp(fc, m);
+        SlotKeysetColumns fcol = {ks->ktabs.data(), slots(1)};
+        run_smp(fcol, m * KSET_COLS);
+    } else {
+        SlotKeysetTables ft = {pts.data(), ks->ktabs.data()};
+        run_smp(ft, m);
+    }
+    LaneKeysetNormalize fn = {ks->ktabs.data(), flat ? (uint32_t)KSET_COLS : (uint32_t)VSH_CHUNKS, flat ? (uint32_t)KSET_QUADS : (uint32_t)KTAB_QUADS};
+    run(fn, m * (flat ? KSET_COLS : VSH_CHUNKS));
     *out = ks;
     return -1;
 }
@@ -263,8 +274,13 @@ EXPORT int32_t goldilocks_ed448_verify_keyset_batch(int32_t *st, const hostsim_k
     LaneEdVerifyScalars f2 = {chal.data(), resp.data(), sig, ks->pk.data(), msg, off, prehashed, ctx, ctx_len, 0, key_index, (uint32_t)ks->m};
     run(f2, n);
     std::vector<verify_aux> aux(n + 1);
-    SlotEdVerifyFinishKeyset f3 = {aux.data(), ks->key_ok.data(), chal.data(), resp.data(), wide_table(), ks->ktabs.data(), key_index, (uint32_t)ks->m, sig};
-    run_smp(f3, n);
+    if (ks->flat) {
+        SlotEdVerifyFinishKeysetFlat f3 = {aux.data(), ks->key_ok.data(), chal.data(), resp.data(), wide_table(), ks->ktabs.data(), key_index, (uint32_t)ks->m, sig};
+        run_smp(f3, n);
+    } else {
+        SlotEdVerifyFinishKeyset f3 = {aux.data(), ks->key_ok.data(), chal.data(), resp.data(), wide_table(), ks->ktabs.data(), key_index, (uint32_t)ks->m, sig};
+        run_smp(f3, n);
+    }
     LaneVerifySign fv = {st, aux.data(), 1, n};
     run(fv, (n + VSIGN_BATCH - 1) / VSIGN_BATCH);
     return -1;

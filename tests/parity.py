@@ -409,7 +409,14 @@ def check_eddsa_grouped(lib, chk, n, label="c4g", per_key=(1, 2, 3, 16, 5, 1, 40
 def check_eddsa_keyset(lib, chk, n, nkeys=11, label="c4k"):
     """Key sets (goldilocks_b200_keyset_*): tables of `nkeys` public keys built once, then several batches verified against
     them; status must equal the reference's per-signature verify with pubkeys[key_index[i]], including undecodable keys in
-    the set (y = 1, y >= p), corrupted signatures / messages, S + q, and out-of-range key indices (FAILURE)."""
+    the set (y = 1, y >= p), corrupted signatures / messages, S + q, and out-of-range key indices (FAILURE).  Both table layouts
+    (goldilocks_b200_keyset_policy): the flat one -- a table per digit position, no doublings -- and the compact one."""
+    if lib.has("goldilocks_b200_keyset_policy") and not label.endswith("/compact"):
+        lib.keyset_policy(0)
+        try:
+            check_eddsa_keyset(lib, chk, n, nkeys, label + "/compact")
+        finally:
+            lib.keyset_policy(32 << 30)
     sk = stream_bytes(label + "/sk", nkeys * 57).reshape(nkeys, 57)
     keys = chk.ed448_derive_public_key(sk)
     keys[3] = le(1, 57)

@@ -107,6 +107,12 @@ def main():
     stage_counts(sim)
     measure("ed448_verify_keyset", n, lambda: sim.ed448_verify_keyset(handle, (np.arange(n) // per).astype(np.uint32), sig16, msgs))
     sim.keyset_destroy(handle)
+    sim.keyset_policy(0)                                            # the compact layout (ten columns per key)
+    handle = sim.keyset_create(pk[:nk])
+    sim.keyset_policy(32 << 30)
+    stage_counts(sim)
+    measure("ed448_verify_keyset_compact", n, lambda: sim.ed448_verify_keyset(handle, (np.arange(n) // per).astype(np.uint32), sig16, msgs))
+    sim.keyset_destroy(handle)
     inv = res["gf_invert"]["LaneGfILi6EE" if "LaneGfILi6EE" in res["gf_invert"] else next(k for k in res["gf_invert"] if not k.startswith("_"))]
     res["_device_only"] = {
         "block_shared_inversion": "SlotX448, SlotX448DerivePk, SlotEdDerivePk, SlotEdSignR: on the device one inversion serves four lanes "

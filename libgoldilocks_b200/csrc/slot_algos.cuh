@@ -339,7 +339,21 @@ GD void s_verify_half(sref sb, const sc &sB, const sc &ub, const sc &vb, gmask_t
 // ---------------------------------------------------------------------------------------------
 #define KTAB_ENTRIES (VSH_CHUNKS * WINDOW_NTABLE + 2)
 #define KTAB_QUADS (KTAB_ENTRIES * 16)
-GD wtab<1> ktab_of(uint4 *ktabs, size_t table) { wtab<1> t; t.base = ktabs + table * KTAB_QUADS; return t; }
+GD wtab<1> ktab_of(uint4 *ktabs, size_t table, uint32_t quads_per_key = KTAB_QUADS) { wtab<1> t; t.base = ktabs + table * (size_t)quads_per_key; return t; }
+// The column shape of a BATCH's per-key tables is picked on the device, from the work lists the grouping pass leaves (no host round
+// trip): 15 columns x 6 rows save 15 doublings per signature and cost five more column tables per key than 10 x 9, which pays from
+// 8.6 signatures per key table on (B200, 16 per key: step 45.2 -> 44.3 ms).  Both shapes fit the same buffer: the wide one is only
+// taken when there are at most a ninth as many tables as signatures.
+struct vsh_shape { int rows, chunks; uint32_t quads; };
+#define VSH_WIDE_ROWS 6
+#define VSH_WIDE_CHUNKS 15
+#define VSH_WIDE_FROM 9 /* average signatures per key table */
+GD vsh_shape vsh_pick(const uint32_t *counts) { /* counts[0] = signatures under key tables, counts[2] = key tables (verify_plan.cuh) */
+    vsh_shape s;
+    if ((uint64_t)counts[0] >= (uint64_t)VSH_WIDE_FROM * counts[2]) { s.rows = VSH_WIDE_ROWS; s.chunks = VSH_WIDE_CHUNKS; s.quads = VSH_WIDE_CHUNKS * WINDOW_NTABLE * 16; }
+    else { s.rows = VSH_ROWS; s.chunks = VSH_CHUNKS; s.quads = KTAB_QUADS; }
+    return s;
+}
 // On entry slots 0..3 hold A (all four coordinates valid).
 GD void s_build_key_tables(sref sb, const wtab<1> &t) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
@@ -431,7 +445,7 @@ GD void s_verify_flat_key(sref sb, const sc &scalar1, const sc &scalar2, const n
 // combo (slots 0..3) = scalar1*B + scalar2*A with A's tables in `kt`; `wide` = the init-time tables of the fixed base.
 // AFFINE: the entries have been divided by their z (key sets, LaneKeysetNormalize): 7 multiplications per addition instead of 8.
 template <bool AFFINE = false>
-GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide, const wtab<1> &kt) {
+GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const niels *wide, const wtab<1> &kt, int rows = VSH_ROWS, int chunks = VSH_CHUNKS) {
     const spt p = {s_slot(sb, 0), s_slot(sb, 1), s_slot(sb, 2), s_slot(sb, 3)};
     const swk w = {s_slot(sb, 4), s_slot(sb, 5), s_slot(sb, 6)};
     sc s1x, s2x;
@@ -441,20 +455,22 @@ GD void s_verify_shared_key(sref sb, const sc &scalar1, const sc &scalar2, const
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int r = VSH_ROWS - 1; r >= 0; r--) {
-        if (r != VSH_ROWS - 1) {
+    for (int r = rows - 1; r >= 0; r--) {
+        if (r != rows - 1) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
             for (int j = 0; j < WINDOW_BITS - 1; j++) s_pt_double(p, w, true);
             s_pt_double(p, w, false);
         }
-        const int last_k = (VSH_CHUNKS - 1) * VSH_ROWS + r <= 89 ? (VSH_CHUNKS - 1) * VSH_ROWS + r : (VSH_CHUNKS - 2) * VSH_ROWS + r; /* last column with a digit in this row */
+        int c_last = (89 - r) / rows;                       /* last column with a digit in this row */
+        if (c_last > chunks - 1) c_last = chunks - 1;
+        const int last_k = rows * c_last + r;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-        for (int c = 0; c < VSH_CHUNKS; c++) {
-            const int k = VSH_ROWS * c + r;
+        for (int c = 0; c < chunks; c++) {
+            const int k = rows * c + r;
             if (k > 89) break;
             const bool row_ends = r != 0 && k == last_k;    /* a doubling follows: T is not needed */
             uint32_t bits2 = sc_window5(s2x, k * WINDOW_BITS);

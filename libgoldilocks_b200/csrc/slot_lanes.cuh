@@ -165,24 +165,27 @@ struct SlotEdVerifyFinish {
     }
 };
 // The per-key tables of a batch, in two launches (slot_algos.cuh s_key_column_bases / s_build_key_column): one lane per key walks the doubling
-// chain, then one lane per (key, column) -- work item 10 t + c -- fills a column.
+// chain, then one lane per (key, column) -- work item chunks * t + c -- fills a column.  The column shape (10 x 9 or 15 x 6) comes from
+// the plan's counts (vsh_pick, slot_algos.cuh).
 struct SlotKeyChain {
     static constexpr int NSLOTS = BDSM_NSLOTS;
     const abi_pt *pts; uint4 *ktabs; verify_plan plan;
     GDM void operator()(size_t t, sref sb, size_t slot) const {
         (void)slot;
         if (t >= plan.counts[2]) return;
+        const vsh_shape sh = vsh_pick(plan.counts);
         s_pt_from_abi(sb, pts + 2 * (size_t)plan.tab_rep[t]);
-        s_key_column_bases(sb, ktab_of(ktabs, t));
+        s_key_column_bases(sb, ktab_of(ktabs, t, sh.quads), sh.chunks, sh.rows * WINDOW_BITS);
     }
 };
 struct SlotKeyColumns {
     static constexpr int NSLOTS = BDSM_NSLOTS;
     uint4 *ktabs; uint4 *scratch; verify_plan plan;
     GDM void operator()(size_t item, sref sb, size_t slot) const {
-        const size_t t = item / VSH_CHUNKS;
+        const vsh_shape sh = vsh_pick(plan.counts);
+        const size_t t = item / (size_t)sh.chunks;
         if (t >= plan.counts[2]) return;
-        s_build_key_column(sb, ktab_of(ktabs, t), (int)(item % VSH_CHUNKS), wtab_of<1>(scratch, slot));
+        s_build_key_column(sb, ktab_of(ktabs, t, sh.quads), (int)(item % (size_t)sh.chunks), wtab_of<1>(scratch, slot));
     }
 };
 // The finish kernel of a grouped batch.  Work items [0, counts[1]) are the stand-alone signatures, verified exactly like
@@ -207,7 +210,8 @@ struct SlotEdVerifyFinishShared {
             i = plan.shared_sig[j - nu];
             sc_from_abi(c, challenge + i);
             sc_from_abi(r, response + i);
-            s_verify_shared_key(sb, r, c, wide, ktab_of(ktabs, t));
+            const vsh_shape sh = vsh_pick(plan.counts);
+            s_verify_shared_key(sb, r, c, wide, ktab_of(ktabs, t, sh.quads), sh.rows, sh.chunks);
             key_ok = (gmask_t)ok[2 * (size_t)plan.tab_rep[t]]; /* the key bytes are the representative's, so is the decode flag */
         } else {
             i = plan.unique_sig[j];

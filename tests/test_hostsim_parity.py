@@ -59,7 +59,8 @@ def test_eddsa(sim, chk, vectors):
     _threads(sim, chk)
     parity.check_eddsa_vectors(sim, vectors)
     parity.check_eddsa_random(sim, chk, 192)
-    parity.check_eddsa_grouped(sim, chk, 160)
+    parity.check_eddsa_grouped(sim, chk, 160)                                          # 13 signatures per key table: 15 columns x 6 rows
+    parity.check_eddsa_grouped(sim, chk, 80, label="c4g/few", per_key=(2, 3, 1))       # 2.5 per key table: 10 columns x 9 rows (vsh_pick)
     parity.check_eddsa_keyset(sim, chk, 120)
     parity.check_eddsa_adversarial(sim, chk, copies=1)
     parity.check_eddsa_grouped(sim, chk, 96, label="c4g/ctx", prehashed=True, context=b"ctx")

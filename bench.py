@@ -99,6 +99,8 @@ def executed_ops():
            "sign": j["ed448_sign"]["_total_imad_wide"] + shared_inv, "derive_public_key": j["ed448_derive_public_key"]["_total_imad_wide"] + shared_inv,
            "point_scalarmul": j["point_scalarmul"]["_total_imad_wide"], "bdsm": j["base_double_scalarmul_non_secret"]["_total_imad_wide"],
            "verify_16_per_key": j["ed448_verify_16_per_key"]["_total_imad_wide"], "verify_distinct": j["ed448_verify_distinct_keys"]["_total_imad_wide"],
+           "verify_64_per_key": j["ed448_verify_64_per_key"]["_total_imad_wide"], "verify_one_signer": j["ed448_verify_one_signer"]["SlotEdVerifyFinishShared"]["imad_wide"] + j["ed448_verify_one_signer"]["LaneVerifySign"]["imad_wide"],   # one table per 2^20 signatures: its build does not count
+           
            "verify_keyset": j["ed448_verify_keyset"]["_total_imad_wide"], "verify_keyset_compact": j["ed448_verify_keyset_compact"]["_total_imad_wide"],
            "finish_shared": j["ed448_verify_16_per_key"]["SlotEdVerifyFinishShared"]["imad_wide"],
            "finish_alone": j["ed448_verify_distinct_keys"]["SlotEdVerifyFinishShared"]["imad_wide"],
@@ -549,7 +551,8 @@ def run_ours(args):
     # ---- extra: the same batch size (a) with 2^20 DISTINCT keys (no table can be shared), (b) with message lengths
     #      uniform in [0, 256) under the 2^16 x 16 keys (second run) --------------------------------------
     if not args.no_extra:
-        for name, kw, key in (("verify_distinct_keys", {"per": 1}, "verify_distinct"), ("verify_varlen_msgs", {"varlen": True}, "verify_16_per_key")):
+        for name, kw, key in (("verify_distinct_keys", {"per": 1}, "verify_distinct"), ("verify_varlen_msgs", {"varlen": True}, "verify_16_per_key"),
+                              ("verify_64_per_key", {"per": 64}, "verify_64_per_key"), ("verify_one_signer", {"per": n}, "verify_one_signer")):
             sig1, pk1, arena1, off1, expect1 = cached_corpus(n, "bench/" + name, rank, world, barrier, **kw)
             t_sig, t_pk, t_msg, t_off = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (sig1.reshape(-1), pk1.reshape(-1), arena1, off1.view(np.int64)))
             eng.ed448_verify(d_st, t_sig, t_pk, t_msg, t_off, d_scratch)

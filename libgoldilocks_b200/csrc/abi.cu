@@ -343,8 +343,10 @@ inline const abi_sc *S(const hsc *p) { return (const abi_sc *)p; }
 inline abi_sc *S(hsc *p) { return (abi_sc *)p; }
 static_assert(sizeof(hpt) == sizeof(abi_pt) && sizeof(hsc) == sizeof(abi_sc), "ABI layout");
 static_assert(sizeof(niels) == 192 && sizeof(pniels) == 256, "table layout");
-static_assert((size_t)VSH_WIDE_CHUNKS * WINDOW_NTABLE * 16 * 4 <= (size_t)KTAB_QUADS * VSH_WIDE_FROM,
-              "the wide column shape (taken from VSH_WIDE_FROM signatures per table on) must fit the buffer sized for n/4 + 1 tables of KTAB_QUADS");
+static_assert(15 * WINDOW_NTABLE * 16 * 4 <= KTAB_QUADS * 9 && 30 * WINDOW_NTABLE * 16 * 4 <= KTAB_QUADS * 32 && 90 * WINDOW_NTABLE * 16 * 4 <= KTAB_QUADS * 256,
+              "every column shape of vsh_pick (taken from 9 / 32 / 256 signatures per table on) must fit the buffer sized for n/4 + 1 tables of KTAB_QUADS");
+/* work items of the column kernel: ten per table of the narrow shape (at most n/4 + 1 tables), 15 per table for at most n/9 tables, ... */
+static size_t verify_column_items(size_t n) { return std::max((n / 4 + 1) * VSH_CHUNKS, n * VSH_MAX_CHUNKS_PER_SIG_NUM / VSH_MAX_CHUNKS_PER_SIG_DEN + 90); }
 static_assert(sizeof(verify_aux) == sizeof(abi_pt), "the aux record of a signature lives in the R half of its point pair");
 
 cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
@@ -984,7 +986,7 @@ static bool verify_grids(Ctx &c, VerifyGrids *g) {
 static size_t verify_slot_bytes(const VerifyGrids &g, size_t n) {
     const int grid = std::max(std::max(g.unique, g.shared), g.columns);
     size_t lanes = (size_t)grid * SLOT_BLOCK;
-    const size_t items = std::max(n, verify_groups(n) ? verify_tab_cap(n) * VSH_WIDE_CHUNKS : (size_t)0);   /* the column builder has up to fifteen items per key table */
+    const size_t items = std::max(n, verify_groups(n) ? verify_column_items(n) : (size_t)0);
     const size_t need = (items + SLOT_BLOCK - 1) / SLOT_BLOCK * SLOT_BLOCK;
     if (lanes > need) lanes = need;
     return (lanes * 2 * WTAB_QUADS_PER_LANE * sizeof(uint4) + 255) & ~(size_t)255;   /* two tables per lane: the key's and R's (s_verify_half_item) */
@@ -1064,7 +1066,7 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
         SlotKeyChain fc = {pts, ktabs, plan};           /* the doubling chain: one lane per key table ... */
         if (!launch_smp(c, fc, cap, grids.chain, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3..5] = 0, left by the grouping pass */
         SlotKeyColumns ft = {ktabs, slots, plan};       /* ... then a lane per key and column fills the column tables (10 or 15 per key, vsh_pick) */
-        if (!launch_smp(c, ft, cap * VSH_WIDE_CHUNKS, grids.columns, s, const_cast<uint32_t *>(plan.counts) + 5)) return false;
+        if (!launch_smp(c, ft, verify_column_items(n), grids.columns, s, const_cast<uint32_t *>(plan.counts) + 5)) return false;
         CU(cudaStreamWaitEvent(s, side_evt[1], 0));
         if (feed) { CU(cudaStreamWaitEvent(s, feed->ready[0], 0)); CU(cudaStreamWaitEvent(s, feed->ready[1], 0)); } /* the finish kernel reads the signature bytes too */
         SlotEdVerifyFinishShared fs = {pts, ok, chal, resp, c.wide, ktabs, slots, plan, sig};
@@ -1088,7 +1090,7 @@ static bool verify_dev(Ctx &c, int32_t *status, const uint8_t *sig, const uint8_
         SlotKeyChain fc = {pts, ktabs, plan};           /* the doubling chain: one lane per key table ... */
         if (!launch_smp(c, fc, cap, grids.chain, s, const_cast<uint32_t *>(plan.counts) + 4)) return false; /* counts[3..5] = 0, left by the grouping pass */
         SlotKeyColumns ft = {ktabs, slots, plan};       /* ... then a lane per key and column fills the column tables (10 or 15 per key, vsh_pick) */
-        if (!launch_smp(c, ft, cap * VSH_WIDE_CHUNKS, grids.columns, s, const_cast<uint32_t *>(plan.counts) + 5)) return false;
+        if (!launch_smp(c, ft, verify_column_items(n), grids.columns, s, const_cast<uint32_t *>(plan.counts) + 5)) return false;
         SlotEdVerifyFinishShared fs = {pts, ok, chal, resp, c.wide, ktabs, slots, plan, sig};
         if (!launch_smp(c, fs, n, grids.shared, s, const_cast<uint32_t *>(plan.counts) + 3)) return false;
         LaneVerifySign fv = {status, (verify_aux *)(pts + 1), 2, n};    /* aux record of signature i = the R half of pts[2i..2i+1] */

@@ -341,17 +341,24 @@ GD void s_verify_half(sref sb, const sc &sB, const sc &ub, const sc &vb, gmask_t
 #define KTAB_QUADS (KTAB_ENTRIES * 16)
 GD wtab<1> ktab_of(uint4 *ktabs, size_t table, uint32_t quads_per_key = KTAB_QUADS) { wtab<1> t; t.base = ktabs + table * (size_t)quads_per_key; return t; }
 // The column shape of a BATCH's per-key tables is picked on the device, from the work lists the grouping pass leaves (no host round
-// trip): 15 columns x 6 rows save 15 doublings per signature and cost five more column tables per key than 10 x 9, which pays from
-// 8.6 signatures per key table on (B200, 16 per key: step 45.2 -> 44.3 ms).  Both shapes fit the same buffer: the wide one is only
-// taken when there are at most a ninth as many tables as signatures.
+// trip).  More columns = fewer rows = fewer doublings per signature, for more column tables per key:
+//     columns x rows      doublings / signature     MAC32 / key table     taken from (signatures per key table)
+//       10 x 9                   40                      659 k                  --
+//       15 x 6                   25                      792 k                   9      (B200, 16 per key: step 45.2 -> 44.3 ms)
+//       30 x 3                   10                    1 176 k                  32
+//       90 x 1                    0                    2 659 k                 256      (one signer for the whole batch: additions only)
+// Every shape fits the buffer sized for n/4 + 1 tables of the narrow one, because it is only taken when the tables are that few.
 struct vsh_shape { int rows, chunks; uint32_t quads; };
-#define VSH_WIDE_ROWS 6
-#define VSH_WIDE_CHUNKS 15
-#define VSH_WIDE_FROM 9 /* average signatures per key table */
+#define VSH_MAX_CHUNKS_PER_SIG_NUM 15 /* columns built per signature, at most: 15 / 9 for the 15 x 6 shape (launch bound of the column kernel) */
+#define VSH_MAX_CHUNKS_PER_SIG_DEN 9
+GD vsh_shape vsh_make(int rows, int chunks) { vsh_shape s; s.rows = rows; s.chunks = chunks; s.quads = (uint32_t)chunks * WINDOW_NTABLE * 16; return s; }
 GD vsh_shape vsh_pick(const uint32_t *counts) { /* counts[0] = signatures under key tables, counts[2] = key tables (verify_plan.cuh) */
-    vsh_shape s;
-    if ((uint64_t)counts[0] >= (uint64_t)VSH_WIDE_FROM * counts[2]) { s.rows = VSH_WIDE_ROWS; s.chunks = VSH_WIDE_CHUNKS; s.quads = VSH_WIDE_CHUNKS * WINDOW_NTABLE * 16; }
-    else { s.rows = VSH_ROWS; s.chunks = VSH_CHUNKS; s.quads = KTAB_QUADS; }
+    const uint64_t sigs = counts[0], tabs = counts[2];
+    if (sigs >= 256 * tabs) return vsh_make(1, 90);
+    if (sigs >= 32 * tabs) return vsh_make(3, 30);
+    if (sigs >= 9 * tabs) return vsh_make(6, 15);
+    vsh_shape s = vsh_make(VSH_ROWS, VSH_CHUNKS);
+    s.quads = KTAB_QUADS;
     return s;
 }
 // On entry slots 0..3 hold A (all four coordinates valid).

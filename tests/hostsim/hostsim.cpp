@@ -318,7 +318,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     counts[0] = (uint32_t)shared_sig.size(); counts[1] = (uint32_t)unique_sig.size(); counts[2] = (uint32_t)tab_rep.size();
     shared_sig.push_back(0); shared_tab.push_back(0); unique_sig.push_back(0); tab_rep.push_back(0); /* never empty */
     verify_plan plan = {shared_sig.data(), shared_tab.data(), unique_sig.data(), tab_rep.data(), counts.data()};
-    std::vector<uint4> ktabs((size_t)(counts[2] + 1) * std::max<size_t>(KTAB_QUADS, VSH_WIDE_CHUNKS * WINDOW_NTABLE * 16));   /* either column shape (vsh_pick) */
+    std::vector<uint4> ktabs((size_t)(counts[2] + 1) * std::max<size_t>(KTAB_QUADS, vsh_pick(counts.data()).quads));   /* whichever column shape vsh_pick takes */
     LaneEdVerifyDecode f1 = {pts.data(), ok.data(), sig, pk, n, plan, n};   /* keys only: R is never decoded on this path */
     run(f1, n);
     LaneVerifyHalf fh = {chal.data(), resp.data(), plan};   /* stand-alone signatures: half-size multipliers, then their R */
@@ -328,7 +328,7 @@ EXPORT int32_t goldilocks_ed448_verify_batch(int32_t *st, const uint8_t *sig, co
     SlotKeyChain fc = {pts.data(), ktabs.data(), plan};
     run_smp(fc, counts[2]);
     SlotKeyColumns ft = {ktabs.data(), slots(2), plan};
-    run_smp(ft, (size_t)counts[2] * VSH_WIDE_CHUNKS);
+    run_smp(ft, (size_t)counts[2] * vsh_pick(counts.data()).chunks);
     SlotEdVerifyFinishShared fs = {pts.data(), ok.data(), chal.data(), resp.data(), wide_table(), ktabs.data(), slots(2), plan, sig};
     run_smp(fs, (size_t)counts[0] + counts[1]);
     LaneVerifySign fv = {st, (verify_aux *)(pts.data() + 1), 2, n};

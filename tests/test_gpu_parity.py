@@ -79,6 +79,8 @@ def test_eddsa_repeated_keys(gpu, chk):
     whole batch, and a batch just at the grouping threshold"""
     parity.check_eddsa_grouped(gpu, chk, 1 << 12)
     parity.check_eddsa_grouped(gpu, chk, 1 << 11, label="c4g/pairs", per_key=(2,))
+    parity.check_eddsa_grouped(gpu, chk, 44 * 40, label="c4g/44", per_key=(44,))            # 30 columns x 3 rows (slot_algos.cuh vsh_pick)
+    parity.check_eddsa_grouped(gpu, chk, 3000, label="c4g/one-signer", per_key=(3000,))    # 90 columns, no doublings
     parity.check_eddsa_grouped(gpu, chk, 1 << 10, label="c4g/one", per_key=(3, 1 << 10))
     parity.check_eddsa_grouped(gpu, chk, 64, label="c4g/min", per_key=(4, 1, 9))
     parity.check_eddsa_grouped(gpu, chk, 512, label="c4g/ctx", prehashed=True, context=b"\x01" * 255)

@@ -61,6 +61,8 @@ def test_eddsa(sim, chk, vectors):
     parity.check_eddsa_random(sim, chk, 192)
     parity.check_eddsa_grouped(sim, chk, 160)                                          # 13 signatures per key table: 15 columns x 6 rows
     parity.check_eddsa_grouped(sim, chk, 80, label="c4g/few", per_key=(2, 3, 1))       # 2.5 per key table: 10 columns x 9 rows (vsh_pick)
+    parity.check_eddsa_grouped(sim, chk, 132, label="c4g/44", per_key=(44,))           # 30 columns x 3 rows
+    parity.check_eddsa_grouped(sim, chk, 300, label="c4g/300", per_key=(300,))         # one signer: 90 columns, additions only
     parity.check_eddsa_keyset(sim, chk, 120)
     parity.check_eddsa_adversarial(sim, chk, copies=1)
     parity.check_eddsa_grouped(sim, chk, 96, label="c4g/ctx", prehashed=True, context=b"ctx")

@@ -103,6 +103,11 @@ def main():
     sk16, pk16 = np.repeat(sk[:nk], per, axis=0), np.repeat(pk[:nk], per, axis=0)
     sig16 = chk.ed448_sign(sk16, pk16, msgs)
     measure("ed448_verify_16_per_key", n, lambda: sim.ed448_verify(sig16, pk16, msgs))
+    # the other column shapes of the batch path (vsh_pick): 64 signatures per key -> 30 x 3, one signer -> 90 x 1 (additions only)
+    for per2, name2 in ((64, "ed448_verify_64_per_key"), (n, "ed448_verify_one_signer")):
+        skp, pkp = np.repeat(sk[:n // per2], per2, axis=0), np.repeat(pk[:n // per2], per2, axis=0)
+        sigp = chk.ed448_sign(skp, pkp, msgs)
+        measure(name2, n, lambda: sim.ed448_verify(sigp, pkp, msgs))
     handle = sim.keyset_create(pk[:nk])
     stage_counts(sim)
     measure("ed448_verify_keyset", n, lambda: sim.ed448_verify_keyset(handle, (np.arange(n) // per).astype(np.uint32), sig16, msgs))

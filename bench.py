@@ -722,33 +722,50 @@ def run_ours(args):
         h_st.zero_(); h_st2.zero_()
 
         gate = threading.Barrier(3)
+        thread_errors = []
+        dev_index = torch.cuda.current_device()
 
         def caller(av):
-            assert fn(*av) == -1                    # first call of this thread: its context of the device allocates its arena
-            assert fn(*av) == -1
-            gate.wait()
-            gate.wait()                             # the main thread has taken the start time
-            for _ in range(ke2):
+            try:
+                torch.cuda.set_device(dev_index)    # a new host thread starts on device 0: bind it to this rank's GPU before its first call
+                assert fn(*av) == -1                # first call of this thread: its context of the device allocates its arena
                 assert fn(*av) == -1
+                gate.wait(timeout=300)
+                gate.wait(timeout=300)              # the main thread has taken the start time
+                for _ in range(ke2):
+                    assert fn(*av) == -1
+            except BaseException as e:  # noqa: BLE001 -- never leave the main thread waiting at the gate
+                thread_errors.append(repr(e))
+                gate.abort()
 
         th2 = [threading.Thread(target=caller, args=(av,)) for av in (argv, argv2)]
-        for x in th2:
-            x.start()
-        gate.wait()
         barrier()
-        t0 = time.perf_counter()
-        gate.wait()
-        for x in th2:
-            x.join()
-        torch.cuda.synchronize()
-        t2e = max_over_ranks((time.perf_counter() - t0) / (2 * ke2))
-        assert (h_st.numpy() == expect).all() and (h_st2.numpy() == expect).all(), "two host threads: statuses"
+        t2e = float("inf")
+        if world == 1:      # the host-thread half is measured on one GPU only (each thread holds an 11 GB arena of its own: kept out of the scaling runs)
+            for x in th2:
+                x.start()
+            t0 = time.perf_counter()
+            try:
+                gate.wait(timeout=300)
+                t0 = time.perf_counter()
+                gate.wait(timeout=300)
+            except threading.BrokenBarrierError:
+                thread_errors.append("a caller thread failed before the timed region")
+            for x in th2:
+                x.join()
+            torch.cuda.synchronize()
+            ok2 = not thread_errors and bool((h_st.numpy() == expect).all()) and bool((h_st2.numpy() == expect).all())
+            if ok2:
+                t2e = (time.perf_counter() - t0) / (2 * ke2)
+            else:
+                sys.stderr.write("[bench] two host threads: %s\n" % (thread_errors[:1] or ["statuses differ"]))
         barrier()
         extra["two_batches_in_flight"] = {
             "value": world * n / t2, "unit": UNIT, "ms_per_step": t2 * 1e3, "steps": k2, "step_frac_executed": executed_step / t2 / 1e9 / peak,
             "api": "goldilocks_ed448_verify_batch_dev on two streams, each with its own scratch and status array (same inputs)",
-            "e2e": {"value": world * n / t2e, "unit": UNIT, "ms_per_step": t2e * 1e3, "calls": 2 * ke2,
-                    "api": "goldilocks_ed448_verify_batch (host pointers, pinned) from two host threads, each on its own status array"},
+            "e2e": ({"skipped": "measured at N = 1 only" if world > 1 else "failed, see stderr"} if t2e == float("inf") else
+                    {"value": world * n / t2e, "unit": UNIT, "ms_per_step": t2e * 1e3, "calls": 2 * ke2,
+                     "api": "goldilocks_ed448_verify_batch (host pointers, pinned) from two host threads, each on its own status array"}),
             "note": "the headline `value` and `e2e` run one batch at a time; with a second batch in flight the latency-bound phases of one (key grouping, decodes, "
                     "the doubling chain of the key tables, copies) run beside the finish kernel of the other"}
         del d_st2, d_scratch2
@@ -800,6 +817,11 @@ def single_call_leg(lib, sig, pk, arena, off, expect):
     with goldilocks_b200_coalesce(window) concurrent calls share a launch (csrc/coalesce.h).  Python threads: ctypes drops the GIL
     for the duration of a call."""
     import threading
+    try:
+        import torch
+        dev_index = torch.cuda.current_device()
+    except Exception:  # noqa: BLE001
+        torch, dev_index = None, None
     fn = lib.lib.goldilocks_ed448_verify
     fn.restype = C.c_int32
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_void_p, C.c_uint8]
@@ -812,6 +834,8 @@ def single_call_leg(lib, sig, pk, arena, off, expect):
         c0, b0, _ = lib.coalesce_stats()
 
         def worker(t):
+            if dev_index is not None:
+                torch.cuda.set_device(dev_index)    # new host threads start on device 0
             for j in range(K):
                 i = t * K + j
                 st = fn(sp + 114 * i, pp + 57 * i, ap + int(o[i]), int(o[i + 1] - o[i]), 0, None, 0)

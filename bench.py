@@ -754,9 +754,10 @@ def run_ours(args):
             for x in th2:
                 x.join()
             torch.cuda.synchronize()
+            t_end = time.perf_counter()
             ok2 = not thread_errors and bool((h_st.numpy() == expect).all()) and bool((h_st2.numpy() == expect).all())
             if ok2:
-                t2e = (time.perf_counter() - t0) / (2 * ke2)
+                t2e = (t_end - t0) / (2 * ke2)
             else:
                 sys.stderr.write("[bench] two host threads: %s\n" % (thread_errors[:1] or ["statuses differ"]))
         barrier()

@@ -63,6 +63,9 @@ def test_eddsa(sim, chk, vectors):
     parity.check_eddsa_grouped(sim, chk, 80, label="c4g/few", per_key=(2, 3, 1))       # 2.5 per key table: 10 columns x 9 rows (vsh_pick)
     parity.check_eddsa_grouped(sim, chk, 132, label="c4g/44", per_key=(44,))           # 30 columns x 3 rows
     parity.check_eddsa_grouped(sim, chk, 300, label="c4g/300", per_key=(300,))         # one signer: 90 columns, additions only
+    parity.check_eddsa_grouped(sim, chk, 380, label="c4g/edge9", per_key=(9, 10, 8, 11))       # averages right at the shape thresholds
+    parity.check_eddsa_grouped(sim, chk, 384, label="c4g/edge32", per_key=(32, 31, 33))
+    parity.check_eddsa_grouped(sim, chk, 811, label="c4g/edge256", per_key=(256, 300, 255))
     parity.check_eddsa_keyset(sim, chk, 120)
     parity.check_eddsa_adversarial(sim, chk, copies=1)
     parity.check_eddsa_grouped(sim, chk, 96, label="c4g/ctx", prehashed=True, context=b"ctx")
